@@ -1,0 +1,312 @@
+// C-ABI group 1 + 2: device runtime (mirror of exprgrad/runtimes/gpu.nim:25-52 as implemented for
+// OpenCL in exprgrad/runtimes/cl.nim:83-207) and the raw operator entry points.
+#include <string.h>
+
+#include <map>
+#include <sstream>
+
+#include "../../include/egb200.h"
+#include "egb_internal.hpp"
+
+namespace egb {
+
+static thread_local std::string g_last_error;
+
+void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+void* Context::ensure_scratch(size_t bytes) {
+  if (bytes > scratch_bytes) {
+    if (scratch) {
+      EGB_CUDA(cudaStreamSynchronize(stream));
+      EGB_CUDA(cudaFree(scratch));
+      scratch = nullptr;
+      scratch_bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 2);
+    EGB_CUDA(cudaMalloc(&scratch, want));
+    scratch_bytes = want;
+  }
+  return scratch;
+}
+
+}  // namespace egb
+
+using namespace egb;
+
+#define EGB_TRY try {
+#define EGB_CATCH                                  \
+  }                                                \
+  catch (const egb::Error& e) {                    \
+    egb::set_last_error(e.what());                 \
+    return e.code;                                 \
+  }                                                \
+  catch (const std::exception& e) {                \
+    egb::set_last_error(e.what());                 \
+    return EGB_ERR_RUNTIME;                        \
+  }                                                \
+  return EGB_OK;
+
+struct egb_context {
+  Context c;
+};
+struct egb_buffer {
+  egb_context* ctx;
+  size_t size;
+  void* ptr;
+};
+
+static void require_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    fail(EGB_ERR_GPU, "Unable to find device");  // cl.nim:97-98
+  }
+  if (device >= n) fail(EGB_ERR_GPU, "Device %d does not exist (%d devices)", device, n);
+}
+
+extern "C" {
+
+const char* egb_last_error(void) { return g_last_error.c_str(); }
+const char* egb_version(void) { return "egb200 0.1 sm_100a"; }
+
+int egb_device_count(int* count) {
+  EGB_TRY
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  EGB_CATCH
+}
+
+static int copy_str(const std::string& s, char* out, size_t cap) {
+  if (cap == 0) return EGB_OK;
+  size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+  memcpy(out, s.data(), n);
+  out[n] = 0;
+  return EGB_OK;
+}
+
+int egb_device_name(int device, char* out, size_t cap) {
+  EGB_TRY
+  require_device(device);
+  cudaDeviceProp prop;
+  EGB_CUDA(cudaGetDeviceProperties(&prop, device));
+  copy_str(prop.name, out, cap);
+  EGB_CATCH
+}
+int egb_device_vendor(int device, char* out, size_t cap) {
+  EGB_TRY
+  require_device(device);
+  copy_str("NVIDIA Corporation", out, cap);
+  EGB_CATCH
+}
+int egb_device_version(int device, char* out, size_t cap) {
+  EGB_TRY
+  require_device(device);
+  cudaDeviceProp prop;
+  EGB_CUDA(cudaGetDeviceProperties(&prop, device));
+  int rt = 0;
+  cudaRuntimeGetVersion(&rt);
+  std::ostringstream ss;
+  ss << "CUDA " << rt / 1000 << "." << (rt % 1000) / 10 << " sm_" << prop.major << prop.minor;
+  copy_str(ss.str(), out, cap);
+  EGB_CATCH
+}
+int egb_device_is_gpu(int device, int* is_gpu) {
+  EGB_TRY
+  require_device(device);
+  *is_gpu = 1;
+  EGB_CATCH
+}
+
+int egb_context_create(int device, egb_context** out) {
+  EGB_TRY
+  if (device < 0) device = 0;
+  require_device(device);
+  EGB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  EGB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    fail(EGB_ERR_GPU, "egb200 kernels are built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+         prop.minor);
+  egb_context* ctx = new egb_context();
+  ctx->c.device = device;
+  ctx->c.sm_count = prop.multiProcessorCount;
+  EGB_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  EGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled not found in driver");
+  ctx->c.encode_tiled = (PFN_encodeTiled)fn;
+  *out = ctx;
+  EGB_CATCH
+}
+
+int egb_context_destroy(egb_context* ctx) {
+  EGB_TRY
+  if (!ctx) return EGB_OK;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  if (ctx->c.scratch) cudaFree(ctx->c.scratch);
+  cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+  EGB_CATCH
+}
+
+int egb_context_synchronize(egb_context* ctx) {
+  EGB_TRY
+  EGB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  EGB_CATCH
+}
+
+void* egb_context_stream(egb_context* ctx) { return (void*)ctx->c.stream; }
+int64_t egb_context_launch_count(egb_context* ctx) { return (int64_t)ctx->c.launches; }
+
+int egb_alloc_buffer(egb_context* ctx, size_t bytes, egb_buffer** out) {
+  EGB_TRY
+  egb_buffer* b = new egb_buffer();
+  b->ctx = ctx;
+  b->size = bytes;
+  b->ptr = nullptr;
+  if (bytes > 0) {
+    cudaError_t e = cudaMalloc(&b->ptr, bytes);
+    if (e != cudaSuccess) {
+      delete b;
+      fail(EGB_ERR_GPU, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+  }
+  *out = b;
+  EGB_CATCH
+}
+
+int egb_buffer_free(egb_buffer* buf) {
+  EGB_TRY
+  if (!buf) return EGB_OK;
+  if (buf->ptr) {
+    EGB_CUDA(cudaStreamSynchronize(buf->ctx->c.stream));
+    EGB_CUDA(cudaFree(buf->ptr));
+  }
+  delete buf;
+  EGB_CATCH
+}
+
+size_t egb_buffer_size(const egb_buffer* buf) { return buf->size; }
+void* egb_buffer_device_ptr(egb_buffer* buf) { return buf->ptr; }
+
+int egb_buffer_write(egb_buffer* buf, const void* data, size_t bytes) {
+  EGB_TRY
+  if (bytes != buf->size)
+    fail(EGB_ERR_GPU, "Attempted to write %zu bytes, but the size of the buffer is %zu bytes", bytes, buf->size);
+  if (bytes) {
+    EGB_CUDA(cudaMemcpyAsync(buf->ptr, data, bytes, cudaMemcpyHostToDevice, buf->ctx->c.stream));
+    EGB_CUDA(cudaStreamSynchronize(buf->ctx->c.stream));
+  }
+  EGB_CATCH
+}
+
+int egb_buffer_read_into(egb_buffer* buf, void* data, size_t bytes) {
+  EGB_TRY
+  if (bytes != buf->size) fail(EGB_ERR_GPU, "Buffer size is not equal to target size");
+  if (bytes) {
+    EGB_CUDA(cudaMemcpyAsync(data, buf->ptr, bytes, cudaMemcpyDeviceToHost, buf->ctx->c.stream));
+    EGB_CUDA(cudaStreamSynchronize(buf->ctx->c.stream));
+  }
+  EGB_CATCH
+}
+
+int egb_buffer_fill(egb_buffer* buf, const void* value, size_t elem_size) {
+  EGB_TRY
+  if (buf->size == 0) return EGB_OK;
+  if (elem_size == 0 || buf->size % elem_size != 0)
+    fail(EGB_ERR_GPU, "Buffer size is not divisible by item type size");
+  cudaStream_t st = buf->ctx->c.stream;
+  bool all_same = true;
+  const unsigned char* v = (const unsigned char*)value;
+  for (size_t i = 1; i < elem_size; ++i) all_same = all_same && v[i] == v[0];
+  if (all_same) {
+    EGB_CUDA(cudaMemsetAsync(buf->ptr, v[0], buf->size, st));
+  } else if (elem_size == 4) {
+    uint32_t w;
+    memcpy(&w, value, 4);
+    launch_fill_u32(buf->ctx->c, (uint32_t*)buf->ptr, w, buf->size / 4, st);
+  } else if (elem_size == 2) {
+    fail(EGB_ERR_GPU, "fill: 2-byte non-uniform patterns are not supported");
+  } else if (elem_size == 8) {
+    // two interleaved 32-bit halves: stage on host for simplicity (rare path: float64 fill)
+    std::vector<uint64_t> host(buf->size / 8);
+    uint64_t w;
+    memcpy(&w, value, 8);
+    for (auto& x : host) x = w;
+    EGB_CUDA(cudaMemcpyAsync(buf->ptr, host.data(), buf->size, cudaMemcpyHostToDevice, st));
+    EGB_CUDA(cudaStreamSynchronize(st));
+  } else {
+    fail(EGB_ERR_GPU, "fill: unsupported element size %zu", elem_size);
+  }
+  EGB_CATCH
+}
+
+int egb_split_bf16(egb_context* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld, int transpose,
+                   void* hi, void* mid, int64_t dst_ld, int act) {
+  EGB_TRY
+  launch_split_bf16(ctx->c, src, (int)rows, (int)cols, (int)ld, transpose != 0, (__nv_bfloat16*)hi,
+                    (__nv_bfloat16*)mid, (int)dst_ld, act, ctx->c.stream);
+  EGB_CATCH
+}
+
+int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_mid,
+                    int64_t lda, const void* b_hi, const void* b_mid, int64_t ldb, float* C, int64_t ldc,
+                    int flags, const float* bias, float alpha, int bn) {
+  EGB_TRY
+  GemmArgs g;
+  g.a_hi = (const __nv_bfloat16*)a_hi; g.a_mid = (const __nv_bfloat16*)a_mid; g.lda = (int)lda;
+  g.b_hi = (const __nv_bfloat16*)b_hi; g.b_mid = (const __nv_bfloat16*)b_mid; g.ldb = (int)ldb;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.C = C; g.ldc = (int)ldc; g.flags = flags; g.bias = bias; g.alpha = alpha; g.bn = bn;
+  launch_gemm_bf16x3(ctx->c, g, ctx->c.stream);
+  EGB_CATCH
+}
+
+int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, const float* A,
+                 int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int flags,
+                 const float* bias, float alpha) {
+  EGB_TRY
+  if (M <= 0 || N <= 0) return EGB_OK;
+  if (K <= 0) fail(EGB_ERR_GPU, "gemm: K must be positive");
+  Context& c = ctx->c;
+  const int64_t kp = (K + 7) & ~int64_t(7);
+  const size_t a_plane = (size_t)M * kp * 2, b_plane = (size_t)N * kp * 2;
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  char* ws = (char*)c.ensure_scratch(2 * al(a_plane) + 2 * al(b_plane));
+  __nv_bfloat16* a_hi = (__nv_bfloat16*)ws;
+  __nv_bfloat16* a_mid = (__nv_bfloat16*)(ws + al(a_plane));
+  __nv_bfloat16* b_hi = (__nv_bfloat16*)(ws + 2 * al(a_plane));
+  __nv_bfloat16* b_mid = (__nv_bfloat16*)(ws + 2 * al(a_plane) + al(b_plane));
+  // A operand must be [M, K] K-contiguous; stored [K, M] when trans_a
+  if (trans_a) launch_split_bf16(c, A, (int)K, (int)M, (int)lda, true, a_hi, a_mid, (int)kp, 0, c.stream);
+  else launch_split_bf16(c, A, (int)M, (int)K, (int)lda, false, a_hi, a_mid, (int)kp, 0, c.stream);
+  // B operand must be [N, K] K-contiguous; stored [K, N] unless trans_b
+  if (trans_b) launch_split_bf16(c, B, (int)N, (int)K, (int)ldb, false, b_hi, b_mid, (int)kp, 0, c.stream);
+  else launch_split_bf16(c, B, (int)K, (int)N, (int)ldb, true, b_hi, b_mid, (int)kp, 0, c.stream);
+  GemmArgs g;
+  g.a_hi = a_hi; g.a_mid = a_mid; g.lda = (int)kp;
+  g.b_hi = b_hi; g.b_mid = b_mid; g.ldb = (int)kp;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.C = C; g.ldc = (int)ldc; g.flags = flags & 7; g.bias = bias; g.alpha = alpha;
+  launch_gemm_bf16x3(c, g, c.stream);
+  EGB_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Internal declarations shared by the C-ABI layer, the host-side program runtime and the kernels.
+#pragma once
+#include <cuda.h>
+#include "../../include/egb200.h"
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace egb {
+
+// All internal failures are C++ exceptions; the C-ABI boundary converts them into a status
+// code plus a thread-local message (mirrors `GpuError`, reference exprgrad/runtimes/cl.nim:41-43).
+struct Error : std::runtime_error {
+  int code;
+  Error(int code_, const std::string& msg) : std::runtime_error(msg), code(code_) {}
+};
+
+// status codes: EGB_OK / EGB_ERR_* macros from include/egb200.h
+
+[[noreturn]] void fail(int code, const char* fmt, ...);
+
+#define EGB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      ::egb::fail(EGB_ERR_GPU, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                  __FILE__, __LINE__);                                                          \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+struct Context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  PFN_encodeTiled encode_tiled = nullptr;
+  // scratch for operand splitting (bf16 hi/mid planes) used by the standalone GEMM entry point
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  size_t launches = 0;  // number of kernel launches issued through this context
+  void* ensure_scratch(size_t bytes);
+};
+
+// ------------------------------------------------------------------ kernels (host launchers)
+
+// fp32 -> (hi, mid) bf16 planes with x ~= hi + mid (+ lo dropped, |lo| <= 2^-17 |x|).
+// src is [rows, cols] row-major with leading dimension ld. If transpose, the planes are written as
+// [cols, rows] (so that the reduction dimension becomes contiguous = "K-major").
+// dst leading dimension is dst_ld elements. act: 0 none, 1 relu (select(0<=x, x, 0)).
+void launch_split_bf16(Context& ctx, const float* src, int rows, int cols, int ld, bool transpose,
+                       __nv_bfloat16* hi, __nv_bfloat16* mid, int dst_ld, int act, cudaStream_t st);
+
+void launch_fill_u32(Context& ctx, uint32_t* dst, uint32_t value, size_t n, cudaStream_t st);
+
+enum GemmFlags {
+  GEMM_ACCUMULATE = 1,  // C += alpha*acc  (reference `++=` on a tensor that already holds data)
+  GEMM_BIAS = 2,        // + bias[col]     (row-broadcast add, reference dnn.nim:22-24)
+  GEMM_RELU = 4,        // out = select(0 <= v, v, 0) (reference dnn.nim:26-27); pre-activation goes to C_pre
+  GEMM_SPLIT_OUT = 8,   // additionally emit bf16 hi/mid planes of the (activated) output
+};
+
+struct GemmArgs {
+  // operands, both K-major bf16 planes: A is [M, lda] and B is [N, ldb], K contiguous
+  const __nv_bfloat16 *a_hi = nullptr, *a_mid = nullptr;
+  const __nv_bfloat16 *b_hi = nullptr, *b_mid = nullptr;
+  int lda = 0, ldb = 0;
+  int M = 0, N = 0, K = 0;
+  float* C = nullptr;  // [M, ldc] fp32 output
+  int ldc = 0;
+  float* C_pre = nullptr;  // optional pre-activation output (same layout as C) when GEMM_RELU
+  const float* bias = nullptr;
+  float alpha = 1.0f;
+  int flags = 0;
+  __nv_bfloat16 *out_hi = nullptr, *out_mid = nullptr;  // GEMM_SPLIT_OUT: [M, ld_out] planes
+  int ld_out = 0;
+  int bn = 0;        // 0 = choose
+  int split_k = 0;   // 0/1 = none (reserved)
+};
+
+void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
+
+}  // namespace egb

@@ -1,0 +1,329 @@
+// fp32-accurate contraction on the 5th-gen tensor cores (sm_100a):
+//
+//   C[M,N] (+)= alpha * sum_k A[m,k] * B[n,k]        (both operands K-major)
+//
+// This is the device kernel behind the reference's contraction kernels
+//   result[y, x] ++= a[y, it] * b[it, x] | (y, x, it)      (exprgrad/layers/base.nim:27-28,
+//   exprgrad/layers/dnn.nim:19-21, benchmarks/matmul/matmul_gpu.nim:32)
+// and their autodiff adjoints (exprgrad/passes.nim:399-403, 519-549).
+//
+// The tensor cores have no fp32 MMA. Each fp32 operand x is pre-split into two bf16 planes
+// hi = bf16(x), mid = bf16(x - hi); the kernel accumulates the three products
+//   hi*hi + hi*mid + mid*hi
+// in the fp32 TMEM accumulator ("bf16x3"), which keeps the result within ~4e-6 (normalised) of
+// the reference's sequential fp32 loop - far inside the 1e-4 parity bar.
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles of the four planes
+//   warp 1      MMA issuer:  one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 12 per k-block
+//   warp 2      TMEM allocator (512 columns = two 128 x 256 fp32 accumulators, double buffered)
+//   warps 4-7   epilogue: tcgen05.ld -> registers -> alpha / bias / relu / accumulate -> global
+// Pipelines: smem full/empty mbarriers between TMA and MMA; TMEM full/empty between MMA and epilogue,
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "egb_internal.hpp"
+#include "ptx.cuh"
+
+namespace egb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                      // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 256;
+constexpr int NUM_THREADS = 256;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct KParams {
+  float* C;
+  float* C_pre;
+  const float* bias;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_mid;
+  int ldc, ld_out;
+  int M, N, K;
+  int BN, stages;
+  int tiles_m, tiles_n;
+  int flags;
+  float alpha;
+};
+
+__device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* mid, float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *hi = h;
+  *mid = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_mid,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_mid,
+                   const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b_plane_bytes = p.BN * BK * 2;
+  const int stage_bytes = 2 * A_PLANE_BYTES + 2 * b_plane_bytes;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a_hi);
+    ptx::prefetch_tensormap(&tm_a_mid);
+    ptx::prefetch_tensormap(&tm_b_hi);
+    ptx::prefetch_tensormap(&tm_b_mid);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(tmem_slot, TMEM_COLS);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.tiles_m) * BM;
+        const int n0 = (tile / p.tiles_m) * p.BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
+          uint8_t* st = smem + s * stage_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          const int k0 = kb * BK;
+          ptx::tma_load_2d(st, &tm_a_hi, &full_bar[s], k0, m0);
+          ptx::tma_load_2d(st + A_PLANE_BYTES, &tm_a_mid, &full_bar[s], k0, m0);
+          ptx::tma_load_2d(st + 2 * A_PLANE_BYTES, &tm_b_hi, &full_bar[s], k0, n0);
+          ptx::tma_load_2d(st + 2 * A_PLANE_BYTES + b_plane_bytes, &tm_b_mid, &full_bar[s], k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN);
+    uint32_t it = 0;
+    uint32_t local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const uint32_t acc = local_tile & 1;
+      const uint32_t use = local_tile >> 1;
+      ptx::mbar_wait(&tmem_empty[acc], (use & 1) ^ 1, 2);  // epilogue drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        ptx::mbar_wait(&full_bar[s], ph, 3);  // TMA bytes have landed
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = ptx::smem_u32(smem + s * stage_bytes);
+          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(st);
+          const uint64_t a_mid = ptx::make_kmajor_sw128_desc(st + A_PLANE_BYTES);
+          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(st + 2 * A_PLANE_BYTES);
+          const uint64_t b_mid = ptx::make_kmajor_sw128_desc(st + 2 * A_PLANE_BYTES + b_plane_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 address field
+            const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
+            // small cross terms first, dominant hi*hi last
+            ptx::umma_f16<1>(d_tmem, a_mid + adv, b_hi + adv, idesc, (kb | k) != 0);
+            ptx::umma_f16<1>(d_tmem, a_hi + adv, b_mid + adv, idesc, 1);
+            ptx::umma_f16<1>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          ptx::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
+          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t local_tile = 0;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const uint32_t acc = local_tile & 1;
+      const uint32_t use = local_tile >> 1;
+      const int m0 = (tile % p.tiles_m) * BM;
+      const int n0 = (tile / p.tiles_m) * p.BN;
+      ptx::mbar_wait(&tmem_full[acc], use & 1, 4);
+      ptx::tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row < p.M && col0 < p.N) {
+          float* crow = p.C + (size_t)row * p.ldc + col0;
+          const int ncols = min(32, p.N - col0);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (p.flags & GEMM_BIAS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.flags & GEMM_ACCUMULATE) {
+            if (vec_ok && ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = *reinterpret_cast<const float4*>(crow + j);
+                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += crow[j];
+            }
+          }
+          if (p.flags & GEMM_RELU) {
+            if (p.C_pre) {
+              float* prow = p.C_pre + (size_t)row * p.ldc + col0;
+              if (vec_ok && ncols == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(prow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) prow[j] = v[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (0.0f <= v[j]) ? v[j] : 0.0f;
+          }
+          if (vec_ok && ncols == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) crow[j] = v[j];
+          }
+          if (p.flags & GEMM_SPLIT_OUT) {
+            __nv_bfloat16* hrow = p.out_hi + (size_t)row * p.ld_out + col0;
+            __nv_bfloat16* mrow = p.out_mid + (size_t)row * p.ld_out + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) split_store(hrow + j, mrow + j, v[j]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, TMEM_COLS);
+  }
+}
+
+void encode_plane(Context& ctx, CUtensorMap* tm, const __nv_bfloat16* base, int rows, int K, int ld,
+                  int box_rows) {
+  if ((ld & 7) != 0) fail(EGB_ERR_GPU, "bf16 plane leading dimension %d is not a multiple of 8", ld);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) fail(EGB_ERR_GPU, "bf16 plane is not 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx.encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+}
+
+int choose_bn(int M, int N, int sm_count) {
+  // Smallest tile count that still fills the machine wins; prefer wide tiles (more operand reuse).
+  const int tiles_m = (M + BM - 1) / BM;
+  int best = 32;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    const int tiles_n = (N + bn - 1) / bn;
+    const long tiles = (long)tiles_m * tiles_n;
+    const long waves = (tiles + sm_count - 1) / sm_count;
+    // time ~ waves * bn (MMA work per tile) with a small bonus for wider tiles (less smem traffic / flop)
+    double cost = (double)waves * bn * (1.0 + 16.0 / bn);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
+  if (a.M <= 0 || a.N <= 0) return;
+  if (a.K <= 0) fail(EGB_ERR_GPU, "gemm: K must be positive");
+  if (!ctx.encode_tiled) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled entry point not available");
+  KParams p;
+  p.C = a.C; p.C_pre = a.C_pre; p.bias = a.bias; p.out_hi = a.out_hi; p.out_mid = a.out_mid;
+  p.ldc = a.ldc; p.ld_out = a.ld_out;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.flags = a.flags; p.alpha = a.alpha;
+  p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, ctx.sm_count);
+  if (p.BN % 32 != 0 || p.BN < 32 || p.BN > 256) fail(EGB_ERR_GPU, "gemm: invalid BN %d", p.BN);
+  p.tiles_m = (a.M + BM - 1) / BM;
+  p.tiles_n = (a.N + p.BN - 1) / p.BN;
+  const int stage_bytes = 2 * A_PLANE_BYTES + 2 * p.BN * BK * 2;
+  const int bar_bytes = (2 * MAX_STAGES + 4) * 8 + 16;
+  int stages = (SMEM_LIMIT - 1024 - bar_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) fail(EGB_ERR_GPU, "gemm: tile does not fit shared memory");
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
+
+  CUtensorMap tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid;
+  encode_plane(ctx, &tm_a_hi, a.a_hi, a.M, a.K, a.lda, BM);
+  encode_plane(ctx, &tm_a_mid, a.a_mid, a.M, a.K, a.lda, BM);
+  encode_plane(ctx, &tm_b_hi, a.b_hi, a.N, a.K, a.ldb, p.BN);
+  encode_plane(ctx, &tm_b_mid, a.b_mid, a.N, a.K, a.ldb, p.BN);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < ctx.sm_count ? tiles : ctx.sm_count;
+  gemm_bf16x3_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p);
+  EGB_CUDA(cudaGetLastError());
+  ctx.launches++;
+}
+
+}  // namespace egb

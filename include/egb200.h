@@ -1,0 +1,130 @@
+/* egb200.h - C ABI of libegb200.so, the B200 (sm_100a) execution backend for exprgrad's
+ * compiled hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and returns an int status:
+ * 0 = ok, non-zero = one of EGB_ERR_* with a human-readable message in egb_last_error()
+ * (thread-local). The Nim side turns a non-zero status into `raise GpuError(msg: ...)` the way
+ * exprgrad/runtimes/cl.nim:41-43 does for OpenCL status codes (RuntimeError / ShapeError for the
+ * matching EGB_ERR_* codes, exprgrad/model.nim:358-359, 395-396; exprgrad/passes.nim:1393-1403).
+ *
+ * Three groups of functions, from the bottom up:
+ *   1. device runtime   - one-to-one with the backend-neutral stub list in
+ *                         exprgrad/runtimes/gpu.nim:25-52 (what `cl.nim` implements for OpenCL).
+ *   2. operator kernels - the hand-written CUDA kernels, callable on raw device buffers
+ *                         (what a `GpuKernel` launch resolves to).
+ *   3. program / model  - the replacement of the JIT'd `target_<name>(model*)` function plus the
+ *                         CompileGpu branches of exprgrad/model.nim:302-383, 392-454: the Nim side
+ *                         hands over its `Program` (tensors, targets, structured kernels as in
+ *                         exprgrad/ir.nim:211-270) once; call/apply/fit then run entirely on device.
+ *
+ * Threading / sync contract (same as the reference's single in-order command queue,
+ * exprgrad/runtimes/cl.nim:92, 114-131, 199-207): one CUDA stream per context; kernel launches and
+ * fills are asynchronous; write/read are blocking and are the sync points; a context is used from
+ * one host thread at a time.
+ */
+#ifndef EGB200_H
+#define EGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define EGB_OK 0
+#define EGB_ERR_GPU 1       /* GpuError       (exprgrad/runtimes/cl.nim:18)  */
+#define EGB_ERR_RUNTIME 2   /* RuntimeError   (exprgrad/ir.nim:27)           */
+#define EGB_ERR_SHAPE 3     /* ShapeError     (exprgrad/ir.nim:28)           */
+#define EGB_ERR_PARSER 4    /* ParserError    (exprgrad/ir.nim:21)           */
+#define EGB_ERR_GRADIENT 5  /* GradientError  (exprgrad/ir.nim:23)           */
+#define EGB_ERR_GENERATOR 6 /* GeneratorError (exprgrad/ir.nim:24)           */
+#define EGB_ERR_VALUE 7     /* ValueError (linear-system solver, passes.nim:1262-1296) */
+
+typedef struct egb_context egb_context;
+typedef struct egb_buffer egb_buffer;
+typedef struct egb_kernel egb_kernel;
+typedef struct egb_program egb_program;
+typedef struct egb_model egb_model;
+
+/* Message of the last failing call on this thread. Never NULL. */
+const char* egb_last_error(void);
+/* "egb200 <version> sm_100a" */
+const char* egb_version(void);
+
+/* ---- 1. device runtime (exprgrad/runtimes/gpu.nim:25-52, cl.nim:83-207) ---------------------- */
+
+/* listDevices (gpu.nim:32, cl.nim:63-65): number of CUDA devices; 0 (and EGB_OK) when none. */
+int egb_device_count(int* count);
+/* name/vendor/version/isGpu (gpu.nim:33-36, cl.nim:74-81). Strings are copied into caller buffers. */
+int egb_device_name(int device, char* out, size_t cap);
+int egb_device_vendor(int device, char* out, size_t cap);
+int egb_device_version(int device, char* out, size_t cap);
+int egb_device_is_gpu(int device, int* is_gpu);
+
+/* newGpuContext(device) / newGpuContext() (gpu.nim:37-38, cl.nim:83-99); device < 0 = first. */
+int egb_context_create(int device, egb_context** out);
+int egb_context_destroy(egb_context* ctx);
+/* Block until everything queued on the context's stream has finished. */
+int egb_context_synchronize(egb_context* ctx);
+/* The context's cudaStream_t (for callers that want to time with CUDA events). */
+void* egb_context_stream(egb_context* ctx);
+/* Number of CUDA kernels launched through this context so far (graph replays count their nodes). */
+int64_t egb_context_launch_count(egb_context* ctx);
+
+/* allocBuffer(ctx, size) (gpu.nim:39, cl.nim:101-106) and dealloc(buffer) (cl.nim:108-109). */
+int egb_alloc_buffer(egb_context* ctx, size_t bytes, egb_buffer** out);
+int egb_buffer_free(egb_buffer* buf);
+size_t egb_buffer_size(const egb_buffer* buf);
+void* egb_buffer_device_ptr(egb_buffer* buf);
+/* write(buffer, data, size) (gpu.nim:40, cl.nim:111-116): blocking H2D; size must equal the buffer
+ * size, otherwise EGB_ERR_GPU "Attempted to write N bytes, but the size of the buffer is M bytes". */
+int egb_buffer_write(egb_buffer* buf, const void* data, size_t bytes);
+/* fill[T](buffer, value) (gpu.nim:42, cl.nim:122-126): asynchronous pattern fill, elem_size in {1,2,4,8}. */
+int egb_buffer_fill(egb_buffer* buf, const void* value, size_t elem_size);
+/* readInto(buffer, ptr) (gpu.nim:43-44, cl.nim:128-138): blocking D2H; bytes must equal buffer size
+ * ("Buffer size is not equal to target size"). */
+int egb_buffer_read_into(egb_buffer* buf, void* data, size_t bytes);
+
+/* compile(ctx, name, source) (gpu.nim:46-47, cl.nim:149-179). `source` is a kernel DESCRIPTOR, not
+ * OpenCL C: one line "op key=value ...", ops:
+ *   gemm    ta=0|1 tb=0|1 acc=0|1 bias=0|1 relu=0|1   args: 0=A 1=B 2=C [3=bias]   indices: 4=M 5=N 6=K
+ *   axpy                                               args: 0=Y 1=X                indices: 2=n, scalar 3=alpha
+ *   relu                                               args: 0=Y 1=X                indices: 2=n
+ * (the program/model API below is the main path; this descriptor form exists so the reference's
+ * compile/arg/run call sequence, llvmgen.nim:461-500, keeps working against precompiled kernels.) */
+int egb_compile(egb_context* ctx, const char* name, const char* source, egb_kernel** out);
+int egb_kernel_free(egb_kernel* k);
+/* arg(kernel, index, buffer) / arg[T](kernel, index, value) (gpu.nim:48-49, cl.nim:181-188). */
+int egb_kernel_arg_buffer(egb_kernel* k, int index, egb_buffer* buf);
+int egb_kernel_arg_index(egb_kernel* k, int index, int64_t value);
+int egb_kernel_arg_scalar(egb_kernel* k, int index, double value);
+/* run(kernel, groupSize, localSize) (gpu.nim:50, cl.nim:190-207). The launch geometry of the
+ * precompiled kernels is chosen by the library; the arguments are validated like the reference
+ * ("Group size must have at least one dimension", "Dimension of group size must equal dimension of
+ * local size") and otherwise ignored. Asynchronous. */
+int egb_kernel_run(egb_kernel* k, int work_dims, const int64_t* group_size, const int64_t* local_size);
+
+/* ---- 2. operator kernels on raw device pointers ---------------------------------------------- */
+
+/* C[M,N] (+)= alpha * op(A)[M,K] * op(B)[K,N] (+ bias[n]) (relu). fp32 in/out, row-major.
+ * trans_a: A is stored [K,M]; trans_b: B is stored [N,K]. flags: 1 accumulate into C, 2 add bias,
+ * 4 relu. Replaces the contraction loop nests of llvmgen.nim:277-297 for kernels shaped like
+ * exprgrad/layers/base.nim:27-28 and their adjoints (passes.nim:519-549). tcgen05 bf16x3. */
+int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, const float* A,
+                 int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int flags,
+                 const float* bias, float alpha);
+/* Same contraction on operands already split into bf16 (hi, mid) K-major planes. bn = 0 lets the
+ * library choose the N tile. Used by the benchmark to time the tensor-core kernel alone. */
+int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_mid,
+                    int64_t lda, const void* b_hi, const void* b_mid, int64_t ldb, float* C, int64_t ldc,
+                    int flags, const float* bias, float alpha, int bn);
+/* fp32 [rows, cols] -> bf16 hi/mid planes ([cols, rows] when transpose != 0). act: 0 none, 1 relu. */
+int egb_split_bf16(egb_context* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld, int transpose,
+                   void* hi, void* mid, int64_t dst_ld, int act);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGB200_H */
