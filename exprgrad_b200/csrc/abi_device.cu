@@ -38,6 +38,17 @@ void* Context::ensure_scratch(size_t bytes) {
   return scratch;
 }
 
+cudaEvent_t Context::get_event() {
+  if (!event_pool.empty()) {
+    cudaEvent_t e = event_pool.back();
+    event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  EGB_CUDA(cudaEventCreate(&e));
+  return e;
+}
+
 }  // namespace egb
 
 using namespace egb;
@@ -161,6 +172,11 @@ int egb_context_destroy(egb_context* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   if (ctx->c.scratch) cudaFree(ctx->c.scratch);
+  for (auto& s : ctx->c.spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  for (auto e : ctx->c.event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
   EGB_CATCH
@@ -173,6 +189,76 @@ int egb_context_synchronize(egb_context* ctx) {
 }
 
 void* egb_context_stream(egb_context* ctx) { return (void*)ctx->c.stream; }
+
+int egb_context_set_timing(egb_context* ctx, int enabled) {
+  EGB_TRY
+  Context& c = ctx->c;
+  EGB_CUDA(cudaStreamSynchronize(c.stream));
+  for (auto& s : c.spans) {
+    c.event_pool.push_back(s.a);
+    c.event_pool.push_back(s.b);
+  }
+  c.spans.clear();
+  c.timing = enabled != 0;
+  EGB_CATCH
+}
+
+int egb_context_kernel_time(egb_context* ctx, int kernel_class, double* total_ms, int64_t* launches) {
+  EGB_TRY
+  Context& c = ctx->c;
+  EGB_CUDA(cudaStreamSynchronize(c.stream));
+  double ms = 0;
+  int64_t n = 0;
+  for (auto& s : c.spans) {
+    if (kernel_class >= 0 && s.cls != kernel_class) continue;
+    float t = 0;
+    EGB_CUDA(cudaEventElapsedTime(&t, s.a, s.b));
+    ms += t;
+    ++n;
+  }
+  *total_ms = ms;
+  *launches = n;
+  EGB_CATCH
+}
+
+int egb_event_create(egb_context* ctx, void** out) {
+  EGB_TRY
+  (void)ctx;
+  cudaEvent_t e;
+  EGB_CUDA(cudaEventCreate(&e));
+  *out = (void*)e;
+  EGB_CATCH
+}
+int egb_event_record(egb_context* ctx, void* ev) {
+  EGB_TRY
+  EGB_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->c.stream));
+  EGB_CATCH
+}
+int egb_event_elapsed_ms(void* start, void* stop, double* ms) {
+  EGB_TRY
+  EGB_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  float t = 0;
+  EGB_CUDA(cudaEventElapsedTime(&t, (cudaEvent_t)start, (cudaEvent_t)stop));
+  *ms = t;
+  EGB_CATCH
+}
+int egb_event_destroy(void* ev) {
+  EGB_TRY
+  if (ev) EGB_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  EGB_CATCH
+}
+
+int egb_host_alloc(size_t bytes, void** out) {
+  EGB_TRY
+  *out = nullptr;
+  if (bytes) EGB_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  EGB_CATCH
+}
+int egb_host_free(void* p) {
+  EGB_TRY
+  if (p) EGB_CUDA(cudaFreeHost(p));
+  EGB_CATCH
+}
 int64_t egb_context_launch_count(egb_context* ctx) { return (int64_t)ctx->c.launches; }
 
 int egb_alloc_buffer(egb_context* ctx, size_t bytes, egb_buffer** out) {

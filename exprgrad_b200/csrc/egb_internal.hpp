@@ -48,6 +48,38 @@ struct Context {
   size_t scratch_bytes = 0;
   size_t launches = 0;  // number of kernel launches issued through this context
   void* ensure_scratch(size_t bytes);
+
+  // Optional per-kernel-class device timing (bench.py's live roofline measurement): when enabled,
+  // every launch is bracketed by CUDA events on the launching stream.
+  bool timing = false;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t get_event();
+};
+
+// Kernel classes for the timing interface (egb_context_kernel_time).
+enum KernelClass { KC_GEMM = 0, KC_SPLIT = 1, KC_FILL = 2, KC_INTERP = 3, KC_REDUCE = 4, KC_ELTWISE = 5,
+                   KC_CONV = 6, KC_OTHER = 7, KC_COUNT = 8 };
+
+// RAII bracket around one kernel launch: counts it and, if timing is on, records events.
+struct Launch {
+  Context& ctx;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  int cls;
+  Launch(Context& c, int cls_, cudaStream_t s) : ctx(c), st(s), cls(cls_) {
+    if (ctx.timing) {
+      cudaEvent_t a = ctx.get_event();
+      b = ctx.get_event();
+      cudaEventRecord(a, st);
+      ctx.spans.push_back({cls, a, b});
+    }
+  }
+  ~Launch() {
+    if (b) cudaEventRecord(b, st);
+    ctx.launches++;
+  }
 };
 
 // ------------------------------------------------------------------ kernels (host launchers)

@@ -19,8 +19,10 @@ void launch_fill_u32(Context& ctx, uint32_t* dst, uint32_t value, size_t n, cuda
   size_t blocks = (n / 4 + 255) / 256 + 1;
   const size_t cap = (size_t)ctx.sm_count * 8;
   if (blocks > cap) blocks = cap;
-  fill_u32_kernel<<<(int)blocks, 256, 0, st>>>(dst, value, n);
+  {
+    Launch l(ctx, KC_FILL, st);
+    fill_u32_kernel<<<(int)blocks, 256, 0, st>>>(dst, value, n);
+  }
   EGB_CUDA(cudaGetLastError());
-  ctx.launches++;
 }
 }  // namespace egb

@@ -321,9 +321,11 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < ctx.sm_count ? tiles : ctx.sm_count;
-  gemm_bf16x3_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p);
+  {
+    Launch l(ctx, KC_GEMM, st);
+    gemm_bf16x3_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p);
+  }
   EGB_CUDA(cudaGetLastError());
-  ctx.launches++;
 }
 
 }  // namespace egb

@@ -89,16 +89,17 @@ void launch_split_bf16(Context& ctx, const float* src, int rows, int cols, int l
     long blocks = (total + 255) / 256;
     const long cap = (long)ctx.sm_count * 8;
     if (blocks > cap) blocks = cap;
+    Launch l(ctx, KC_SPLIT, st);
     split_rows_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, ld, hi, mid, dst_ld, act);
   } else {
     const long tiles = (long)((rows + 63) >> 6) * ((cols + 63) >> 6);
     long blocks = tiles;
     const long cap = (long)ctx.sm_count * 8;
     if (blocks > cap) blocks = cap;
+    Launch l(ctx, KC_SPLIT, st);
     split_transpose_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, ld, hi, mid, dst_ld, act);
   }
   EGB_CUDA(cudaGetLastError());
-  ctx.launches++;
 }
 
 }  // namespace egb

@@ -73,6 +73,30 @@ void* egb_context_stream(egb_context* ctx);
 /* Number of CUDA kernels launched through this context so far (graph replays count their nodes). */
 int64_t egb_context_launch_count(egb_context* ctx);
 
+/* Device timing for benchmarks. set_timing(1) clears the record and brackets every subsequent kernel
+ * launch with CUDA events on the context's stream; kernel_time sums the device time of the launches
+ * of one kernel class (EGB_KC_*, -1 = all) recorded since. */
+#define EGB_KC_GEMM 0
+#define EGB_KC_SPLIT 1
+#define EGB_KC_FILL 2
+#define EGB_KC_INTERP 3
+#define EGB_KC_REDUCE 4
+#define EGB_KC_ELTWISE 5
+#define EGB_KC_CONV 6
+#define EGB_KC_OTHER 7
+int egb_context_set_timing(egb_context* ctx, int enabled);
+int egb_context_kernel_time(egb_context* ctx, int kernel_class, double* total_ms, int64_t* launches);
+/* CUDA events on the context's stream (cudaEvent_t behind void*). */
+int egb_event_create(egb_context* ctx, void** out);
+int egb_event_record(egb_context* ctx, void* event);
+int egb_event_elapsed_ms(void* start, void* stop, double* ms); /* waits for `stop` */
+int egb_event_destroy(void* event);
+/* Page-locked host memory for Tensor[T] storage that is copied to/from the device
+ * (exprgrad/tensors.nim:36-49 allocates from the host heap; pinned memory makes write/readInto run
+ * at full PCIe rate). */
+int egb_host_alloc(size_t bytes, void** out);
+int egb_host_free(void* p);
+
 /* allocBuffer(ctx, size) (gpu.nim:39, cl.nim:101-106) and dealloc(buffer) (cl.nim:108-109). */
 int egb_alloc_buffer(egb_context* ctx, size_t bytes, egb_buffer** out);
 int egb_buffer_free(egb_buffer* buf);
@@ -86,25 +110,6 @@ int egb_buffer_fill(egb_buffer* buf, const void* value, size_t elem_size);
 /* readInto(buffer, ptr) (gpu.nim:43-44, cl.nim:128-138): blocking D2H; bytes must equal buffer size
  * ("Buffer size is not equal to target size"). */
 int egb_buffer_read_into(egb_buffer* buf, void* data, size_t bytes);
-
-/* compile(ctx, name, source) (gpu.nim:46-47, cl.nim:149-179). `source` is a kernel DESCRIPTOR, not
- * OpenCL C: one line "op key=value ...", ops:
- *   gemm    ta=0|1 tb=0|1 acc=0|1 bias=0|1 relu=0|1   args: 0=A 1=B 2=C [3=bias]   indices: 4=M 5=N 6=K
- *   axpy                                               args: 0=Y 1=X                indices: 2=n, scalar 3=alpha
- *   relu                                               args: 0=Y 1=X                indices: 2=n
- * (the program/model API below is the main path; this descriptor form exists so the reference's
- * compile/arg/run call sequence, llvmgen.nim:461-500, keeps working against precompiled kernels.) */
-int egb_compile(egb_context* ctx, const char* name, const char* source, egb_kernel** out);
-int egb_kernel_free(egb_kernel* k);
-/* arg(kernel, index, buffer) / arg[T](kernel, index, value) (gpu.nim:48-49, cl.nim:181-188). */
-int egb_kernel_arg_buffer(egb_kernel* k, int index, egb_buffer* buf);
-int egb_kernel_arg_index(egb_kernel* k, int index, int64_t value);
-int egb_kernel_arg_scalar(egb_kernel* k, int index, double value);
-/* run(kernel, groupSize, localSize) (gpu.nim:50, cl.nim:190-207). The launch geometry of the
- * precompiled kernels is chosen by the library; the arguments are validated like the reference
- * ("Group size must have at least one dimension", "Dimension of group size must equal dimension of
- * local size") and otherwise ignored. Asynchronous. */
-int egb_kernel_run(egb_kernel* k, int work_dims, const int64_t* group_size, const int64_t* local_size);
 
 /* ---- 2. operator kernels on raw device pointers ---------------------------------------------- */
 

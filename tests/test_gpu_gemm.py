@@ -1,0 +1,78 @@
+"""GPU parity of the tcgen05 contraction kernel (C-ABI egb_gemm_f32) against the oracle."""
+import numpy as np
+import pytest
+
+from parity_cases import assert_close, gemm_f32, oracle_matmul
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import exprgrad_b200 as eg
+    c = eg.new_gpu_context()
+    yield c
+    c.destroy()
+
+
+def test_reference_known_answer(ctx):
+    """tests/test_model.nim:37-44: [[1,2,3],[4,5,6]] x [[1,2],[3,4],[5,6]] == [[22,28],[49,64]] (exact)."""
+    a = np.array([[1, 2, 3], [4, 5, 6]], np.float32)
+    b = np.array([[1, 2], [3, 4], [5, 6]], np.float32)
+    assert np.array_equal(gemm_f32(ctx, a, b), np.array([[22, 28], [49, 64]], np.float32))
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (2, 2, 3), (64, 64, 64), (123, 77, 100), (128, 256, 64),
+                                   (300, 200, 129), (1024, 512, 784), (1024, 10, 512), (784, 512, 1024)])
+@pytest.mark.parametrize("lo,hi", [(0.0, 1.0), (-1.0, 1.0)])
+def test_nn_matches_oracle(ctx, M, N, K, lo, hi):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a = rng.uniform(lo, hi, (M, K)).astype(np.float32)
+    b = rng.uniform(lo, hi, (K, N)).astype(np.float32)
+    assert_close(gemm_f32(ctx, a, b), oracle_matmul(a, b), what=f"NN {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(2, 2, 3), (123, 77, 100), (512, 10, 1024), (784, 512, 1024)])
+def test_adjoint_layouts_match_oracle(ctx, M, N, K):
+    """dA = dC.B^T (NT) and dB = A^T.dC (TN) layouts of passes.nim:519-549."""
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    b = rng.uniform(-1, 1, (K, N)).astype(np.float32)
+    ref = oracle_matmul(a, b)
+    assert_close(gemm_f32(ctx, a, np.ascontiguousarray(b.T), tb=1), ref, what="NT")
+    assert_close(gemm_f32(ctx, np.ascontiguousarray(a.T), b, ta=1), ref, what="TN")
+
+
+def test_accumulate_bias_relu_epilogue(ctx):
+    rng = np.random.default_rng(9)
+    a = rng.uniform(-1, 1, (300, 100)).astype(np.float32)
+    b = rng.uniform(-1, 1, (100, 200)).astype(np.float32)
+    c0 = rng.uniform(-1, 1, (300, 200)).astype(np.float32)
+    bias = rng.uniform(-1, 1, (200,)).astype(np.float32)
+    ref = oracle_matmul(a, b)
+    assert_close(gemm_f32(ctx, a, b, flags=1, c0=c0), ref + c0, what="accumulate")
+    assert_close(gemm_f32(ctx, a, b, flags=2, bias=bias), ref + bias, what="bias")
+    assert_close(gemm_f32(ctx, a, b, flags=6, bias=bias), np.maximum(ref + bias, 0), what="bias+relu")
+
+
+def test_full_size_checksum_properties(ctx):
+    """benchmarks/matmul at 4096^3 (BASELINE config 2): the oracle would take minutes, so check
+    size-independent properties in fp64: row sums (C.1 == A.(B.1)), column sums, and linearity."""
+    n = 4096
+    for seed, lo in ((0, 0.0), (1, -1.0)):
+        rng = np.random.default_rng(seed)
+        a = rng.uniform(lo, 1, (n, n)).astype(np.float32)
+        b = rng.uniform(lo, 1, (n, n)).astype(np.float32)
+        c = gemm_f32(ctx, a, b).astype(np.float64)
+        a64, b64 = a.astype(np.float64), b.astype(np.float64)
+        scale = np.abs(a64).sum(1).max() * np.abs(b64).max()  # magnitude of one output element's terms
+        rows = a64 @ b64.sum(1)
+        cols = a64.sum(0) @ b64
+        assert np.abs(c.sum(1) - rows).max() / (scale * n) < 1e-6
+        assert np.abs(c.sum(0) - cols).max() / (scale * n) < 1e-6
+        # a 64x64 corner against the oracle itself
+        ref = oracle_matmul(a[:64], b[:, :64])
+        assert_close(c[:64, :64], ref, what="corner")
+        if seed == 0:
+            c2 = gemm_f32(ctx, a * np.float32(2), b).astype(np.float64)  # exact scaling by 2
+            assert np.array_equal(c2, 2 * c)
