@@ -148,7 +148,7 @@ struct Reader {
     if (t == "-") return "";
     std::string out;
     for (size_t i = 0; i < t.size(); ++i) {
-      if (t[i] == '%' && i + 2 <= t.size() - 1) {
+      if (t[i] == '%' && i + 2 < t.size() + 0 && i + 2 <= t.size() - 1) {
         out.push_back((char)strtol(t.substr(i + 1, 2).c_str(), nullptr, 16));
         i += 2;
       } else {
@@ -251,6 +251,7 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
   std::string st = r.next();
   if (st == "f64") prog->f64 = true;
   else if (st != "f32") fail(EGB_ERR_PARSER, "unknown scalar type '%s'", st.c_str());
+  prog->compiled = r.i32() != 0;
   r.expect("tensors");
   int nt = r.i32();
   for (int i = 0; i < nt; ++i) {
@@ -273,7 +274,8 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
     t->name = r.str();
     t->output = r.i32();
     t->compile_target = r.i32();
-    int ns = r.i32(), nk = r.i32();
+    int ns = r.i32(), nk = r.i32(), ntens = r.i32();
+    for (int k = 0; k < ntens; ++k) t->tensors.push_back(r.i32());
     for (int s = 0; s < ns; ++s) {
       r.expect("S");
       ShapeConstraint sc;
@@ -287,6 +289,24 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
         sc.kind = ShapeKind::Dims;
         int n = r.i32();
         for (int d = 0; d < n; ++d) sc.dims.push_back(read_li(r));
+      } else if (kind == "rank") {
+        sc.kind = ShapeKind::Rank;
+        sc.rank = r.i32();
+      } else if (kind == "linear") {
+        sc.kind = ShapeKind::Linear;
+        int nr = r.i32();
+        for (int a = 0; a < nr; ++a) {
+          int tensor = r.i32();
+          int nd = r.i32();
+          std::vector<std::vector<LinearIndex>> dims(nd);
+          for (int d = 0; d < nd; ++d) {
+            int ni = r.i32();
+            for (int e = 0; e < ni; ++e) dims[d].push_back(read_li(r));
+          }
+          sc.reads.emplace_back(tensor, dims);
+        }
+        int nw = r.i32();
+        for (int d = 0; d < nw; ++d) sc.write.push_back(read_li(r));
       } else {
         fail(EGB_ERR_PARSER, "unknown shape constraint kind '%s'", kind.c_str());
       }
@@ -296,7 +316,197 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
     prog->targets.push_back(t);
   }
   r.expect("end");
+  if (prog->compiled) {
+    for (size_t i = 0; i < prog->tensors.size(); ++i) {
+      const TensorDef& t = prog->tensors[i];
+      if (t.kind == TensorKind::Param) prog->params.push_back((int)i + 1);
+      else if (t.kind == TensorKind::Cache) prog->caches.push_back((int)i + 1);
+      else if (t.kind == TensorKind::Input) prog->inputs[t.name] = (int)i + 1;
+    }
+  }
   return prog;
+}
+
+// ------------------------------------------------------------------------------ serializer
+
+namespace {
+
+struct Writer {
+  std::ostringstream ss;
+  void tok(const std::string& s) { ss << s << ' '; }
+  void i(int64_t v) { ss << v << ' '; }
+  void f(double v) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%a", v);
+    ss << buf << ' ';
+  }
+  void str(const std::string& s) {
+    if (s.empty()) {
+      ss << "- ";
+      return;
+    }
+    static const char* hex = "0123456789abcdef";
+    for (unsigned char c : s) {
+      if (c <= ' ' || c == '%' || c == '-' || c >= 127) ss << '%' << hex[c >> 4] << hex[c & 15];
+      else ss << c;
+    }
+    ss << ' ';
+  }
+  void nl() { ss << '\n'; }
+};
+
+void write_instr(Writer& w, const Instr& i) {
+  w.tok("I");
+  w.tok(op_name(i.op));
+  w.i(i.res);
+  w.i(i.tensor);
+  w.i(i.dim);
+  w.i((int64_t)i.args.size());
+  for (int a : i.args) w.i(a);
+  w.f(i.scalar);
+  w.i(i.index);
+}
+
+void write_li(Writer& w, const LinearIndex& li) {
+  w.tok("LI");
+  w.i((int64_t)li.setup.size());
+  w.i((int64_t)li.factors.size());
+  w.i(li.constant);
+  for (auto& s : li.setup) write_instr(w, s);
+  for (auto& kv : li.factors) {
+    w.i(kv.first);
+    w.i(kv.second);
+  }
+}
+
+void write_op(Writer& w, const TensorOp& op, const char* tag) {
+  w.tok(tag);
+  w.i(op.tensor);
+  w.i(op.is_raw ? 1 : 0);
+  w.i(op.data);
+  w.i((int64_t)op.dims.size());
+  for (auto& d : op.dims) write_li(w, d);
+}
+
+void write_kernel(Writer& w, const Kernel& k) {
+  w.tok("K");
+  w.i((int)k.gen);
+  w.i(k.gen_tensor);
+  w.i((int64_t)k.reshape.size());
+  for (auto v : k.reshape) w.i(v);
+  w.i(k.nregs);
+  w.i((int64_t)k.loops.size());
+  w.i((int64_t)k.reads.size());
+  w.i((int64_t)k.instrs.size());
+  w.i(k.res);
+  w.i(k.custom_grad ? 1 : 0);
+  w.nl();
+  for (auto& l : k.loops) {
+    w.tok("L");
+    w.i(l.iter);
+    w.i(l.has_bounds ? 1 : 0);
+    w.i(l.step);
+    w.i(l.mode);
+    write_li(w, l.start);
+    write_li(w, l.stop);
+    w.nl();
+  }
+  for (auto& r : k.reads) {
+    write_op(w, r, "R");
+    w.nl();
+  }
+  for (auto& i : k.instrs) write_instr(w, i);
+  w.nl();
+  write_op(w, k.write, "W");
+  w.nl();
+  if (k.custom_grad) {
+    w.tok("C");
+    w.i((int64_t)k.custom_grad->tensors.size());
+    for (auto& kv : k.custom_grad->tensors) {
+      w.i(kv.first);
+      w.i(kv.second);
+    }
+    w.i((int64_t)k.custom_grad->subs.size());
+    for (auto& kv : k.custom_grad->subs) {
+      w.i(kv.first);
+      w.i(kv.second);
+    }
+    w.i((int64_t)k.custom_grad->kernels.size());
+    w.nl();
+    for (auto& g : k.custom_grad->kernels) write_kernel(w, *g);
+  }
+}
+
+}  // namespace
+
+std::string serialize_program(const Program& prog) {
+  Writer w;
+  w.tok("egbprog");
+  w.i(1);
+  w.tok(prog.f64 ? "f64" : "f32");
+  w.i(prog.compiled ? 1 : 0);
+  w.nl();
+  w.tok("tensors");
+  w.i((int64_t)prog.tensors.size());
+  w.nl();
+  for (auto& t : prog.tensors) {
+    w.tok("T");
+    w.i((int)t.kind);
+    w.i((int64_t)t.shape.size());
+    for (auto d : t.shape) w.i(d);
+    w.f(t.range_lo);
+    w.f(t.range_hi);
+    w.i(t.cache);
+    w.str(t.name);
+    w.nl();
+  }
+  w.tok("targets");
+  w.i((int64_t)prog.targets.size());
+  w.nl();
+  for (auto& t : prog.targets) {
+    w.tok("target");
+    w.str(t->name);
+    w.i(t->output);
+    w.i(t->compile_target);
+    w.i((int64_t)t->shapes.size());
+    w.i((int64_t)t->kernels.size());
+    w.i((int64_t)t->tensors.size());
+    for (int id : t->tensors) w.i(id);
+    w.nl();
+    for (auto& sc : t->shapes) {
+      w.tok("S");
+      switch (sc.kind) {
+        case ShapeKind::Copy:
+          w.tok("copy"); w.i(sc.dest); w.i(sc.priority); w.i(sc.src);
+          break;
+        case ShapeKind::Dims:
+          w.tok("dims"); w.i(sc.dest); w.i(sc.priority); w.i((int64_t)sc.dims.size());
+          for (auto& d : sc.dims) write_li(w, d);
+          break;
+        case ShapeKind::Rank:
+          w.tok("rank"); w.i(sc.dest); w.i(sc.priority); w.i(sc.rank);
+          break;
+        case ShapeKind::Linear:
+          w.tok("linear"); w.i(sc.dest); w.i(sc.priority); w.i((int64_t)sc.reads.size());
+          for (auto& rd : sc.reads) {
+            w.i(rd.first);
+            w.i((int64_t)rd.second.size());
+            for (auto& dim : rd.second) {
+              w.i((int64_t)dim.size());
+              for (auto& li : dim) write_li(w, li);
+            }
+          }
+          w.i((int64_t)sc.write.size());
+          for (auto& d : sc.write) write_li(w, d);
+          break;
+      }
+      w.nl();
+    }
+    for (auto& k : t->kernels) write_kernel(w, *k);
+  }
+  w.tok("end");
+  w.nl();
+  return w.ss.str();
 }
 
 std::string describe_kernel(const Kernel& k) {

@@ -93,6 +93,7 @@ struct Kernel {
   int res = 0;
   TensorOp write;
   int alloc_reg() { return ++nregs; }
+  bool is_generator() const { return gen != GenKind::None; }
   std::shared_ptr<Kernel> clone() const;
   void substitute_tensors(const std::map<int, int>& subs);
 };
@@ -137,6 +138,10 @@ struct Program {
   std::vector<int> params, caches;
   std::vector<std::shared_ptr<Target>> targets;  // declaration order
   bool f64 = false;
+  bool compiled = false;
+  // loss-gradient bookkeeping recorded by `generate`: tensor -> its gradient tensor, per target name.
+  // The data-parallel runtime uses it to find the parameter-gradient bucket.
+  std::map<std::string, std::map<int, int>> grad_tensors;
   TensorDef& tdef(int id) { return tensors[id - 1]; }
   const TensorDef& tdef(int id) const { return tensors[id - 1]; }
   int alloc_tensor(const TensorDef& t) { tensors.push_back(t); return (int)tensors.size(); }
@@ -144,8 +149,11 @@ struct Program {
 };
 
 // Text form produced by the front-end (see exprgrad_b200/frontend.py `serialize`, and the Nim
-// serializer sketched in INTEGRATION.md).
+// serializer sketched in INTEGRATION.md). Accepts a source program (stage 0: what `toProgram`
+// produces, parser.nim:404-417) or an already compiled one (stage 1: after the semantics-defining
+// passes, i.e. what exprgrad's own passes.nim hands to a code generator).
 std::shared_ptr<Program> parse_program(const std::string& text);
+std::string serialize_program(const Program& prog);
 
 // The semantics-defining prefix of exprgrad/model.nim:46-77 (see passes.cpp).
 void compile_program(Program& prog);
