@@ -70,6 +70,26 @@ _SIGS = {
     "egb_gemm_f32": (I, [P, I, I, I64, I64, I64, P, I64, P, I64, P, I64, I, P, F]),
     "egb_gemm_planes": (I, [P, I64, I64, I64, P, P, I64, P, P, I64, P, I64, I, P, F, I]),
     "egb_split_bf16": (I, [P, P, I64, I64, I64, I, P, P, I64, I]),
+    "egb_program_parse": (I, [S, SZ, PP]),
+    "egb_program_compile": (I, [P]),
+    "egb_program_serialize": (I, [P, P, SZ, ctypes.POINTER(SZ)]),
+    "egb_program_free": (I, [P]),
+    "egb_program_tensor_count": (I, [P, PI]),
+    "egb_program_tensor_info": (I, [P, I, PI, PI, PI64, P, SZ]),
+    "egb_program_target_output": (I, [P, S, PI]),
+    "egb_program_infer_shapes": (I, [P, S, I, ctypes.POINTER(S), PI, PI64, I, PI, PI64]),
+    "egb_model_create": (I, [P, P, U64, PP]),
+    "egb_model_free": (I, [P]),
+    "egb_model_set_option": (I, [P, S, I64]),
+    "egb_model_epoch": (I, [P, PI64]),
+    "egb_model_write_tensor": (I, [P, I, P, SZ]),
+    "egb_model_read_tensor": (I, [P, I, P, SZ]),
+    "egb_model_tensor_shape": (I, [P, I, PI, PI64]),
+    "egb_model_tensor_device_ptr": (I, [P, I, PP]),
+    "egb_model_call": (I, [P, S, I, ctypes.POINTER(S), PP, PI, PI64, PI, PI, PI64]),
+    "egb_model_read_output": (I, [P, P, SZ]),
+    "egb_model_fit": (I, [P, S, I, ctypes.POINTER(S), PP, PI, PI64, I64, PI64]),
+    "egb_model_describe_plan": (I, [P, P, SZ, ctypes.POINTER(SZ)]),
 }
 
 

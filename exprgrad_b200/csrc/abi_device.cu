@@ -5,7 +5,7 @@
 #include <map>
 #include <sstream>
 
-#include "../../include/egb200.h"
+#include "abi_common.hpp"
 #include "egb_internal.hpp"
 
 namespace egb {
@@ -53,27 +53,8 @@ cudaEvent_t Context::get_event() {
 
 using namespace egb;
 
-#define EGB_TRY try {
-#define EGB_CATCH                                  \
-  }                                                \
-  catch (const egb::Error& e) {                    \
-    egb::set_last_error(e.what());                 \
-    return e.code;                                 \
-  }                                                \
-  catch (const std::exception& e) {                \
-    egb::set_last_error(e.what());                 \
-    return EGB_ERR_RUNTIME;                        \
-  }                                                \
-  return EGB_OK;
 
-struct egb_context {
-  Context c;
-};
-struct egb_buffer {
-  egb_context* ctx;
-  size_t size;
-  void* ptr;
-};
+
 
 static void require_device(int device) {
   int n = 0;

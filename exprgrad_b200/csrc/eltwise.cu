@@ -12,7 +12,34 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t value, size
   for (size_t j = i; j < n4; j += stride) d4[j] = v4;
   for (size_t j = (n4 << 2) + i; j < n; j += stride) dst[j] = value;
 }
+// U(lo, hi) fill for TensorRandom tensors (model.nim:286-294, 310-314: refilled on every call).
+// Counter-based: element i of call c is a hash of (seed, c, i), so a run is reproducible.
+__global__ void fill_uniform_kernel(float* __restrict__ dst, size_t n, float lo, float hi, uint64_t seed,
+                                    uint64_t counter) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t z = seed * 0x9e3779b97f4a7c15ull + counter * 0xd1342543de82ef95ull + i + 1;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z = z ^ (z >> 31);
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // [0, 1)
+    dst[i] = lo + (hi - lo) * u;
+  }
+}
 }  // namespace
+
+void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi, uint64_t seed, uint64_t counter,
+                         cudaStream_t st) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)ctx.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  {
+    Launch l(ctx, KC_FILL, st);
+    fill_uniform_kernel<<<(int)blocks, 256, 0, st>>>(dst, n, lo, hi, seed, counter);
+  }
+  EGB_CUDA(cudaGetLastError());
+}
 
 void launch_fill_u32(Context& ctx, uint32_t* dst, uint32_t value, size_t n, cudaStream_t st) {
   if (n == 0) return;

@@ -1,0 +1,191 @@
+// Generic loop-nest kernel: executes any lowered exprgrad kernel (exprgrad/ir.nim:211-220) on the
+// device, so that every `++=` expression runs under the B200 backend even when no specialised
+// kernel matches (the role clgen.nim:74-257 plays for OpenCL in the reference). The expression is a
+// small register program held in the kernel parameter (constant bank); every thread evaluates it
+// for its share of the iteration space. Opcode semantics follow the reference's CPU lowering
+// (exprgrad/llvmgen.nim:193-321): separate fmul/fadd (this file is built with -fmad=false), `0 - x`
+// negate, ordered float compares, truncating integer division, select evaluating both arms.
+//
+// Thread layout: a block of 256 threads covers PB output points x RB reduction slices
+// (PB * RB == 256). `points_fast` chooses which of the two is the fastest-varying thread index, so
+// that the dimension that is contiguous in memory is the one neighbouring lanes walk. Partial sums
+// of the RB slices are combined through shared memory. RB == 1 keeps the reference's sequential
+// accumulation order (bit-exact mode).
+#include <math.h>
+
+#include "egb_internal.hpp"
+#include "interp.hpp"
+
+namespace egb {
+namespace {
+
+union Slot {
+  float f;
+  int64_t i;
+  uint64_t u;
+};
+
+constexpr int IP_THREADS = 256;
+
+__device__ __forceinline__ void run_instrs(const IpInstr* __restrict__ ins, int n, Slot* s, const IpProgram& p) {
+  for (int k = 0; k < n; ++k) {
+    const IpInstr in = ins[k];
+    Slot r;
+    r.u = 0;
+    switch (in.op) {
+      case IP_FADD: r.f = s[in.a].f + s[in.b].f; break;
+      case IP_FSUB: r.f = s[in.a].f - s[in.b].f; break;
+      case IP_FMUL: r.f = s[in.a].f * s[in.b].f; break;
+      case IP_FDIV: r.f = __fdiv_rn(s[in.a].f, s[in.b].f); break;
+      case IP_FNEG: r.f = 0.0f - s[in.a].f; break;
+      case IP_SIN: r.f = sinf(s[in.a].f); break;
+      case IP_COS: r.f = cosf(s[in.a].f); break;
+      case IP_EXP: r.f = expf(s[in.a].f); break;
+      case IP_LN: r.f = logf(s[in.a].f); break;
+      case IP_SQRT: r.f = __fsqrt_rn(s[in.a].f); break;
+      case IP_POW: r.f = powf(s[in.a].f, s[in.b].f); break;
+      case IP_LOG10: r.f = log10f(s[in.a].f); break;
+      case IP_LOG2: r.f = log2f(s[in.a].f); break;
+      case IP_LOGB: r.f = __fdiv_rn(logf(s[in.a].f), logf(s[in.b].f)); break;
+      case IP_IADD: r.i = s[in.a].i + s[in.b].i; break;
+      case IP_ISUB: r.i = s[in.a].i - s[in.b].i; break;
+      case IP_IMUL: r.i = s[in.a].i * s[in.b].i; break;
+      case IP_IDIV: { const int64_t d = s[in.b].i; r.i = d ? s[in.a].i / d : 0; break; }
+      case IP_IMOD: { const int64_t d = s[in.b].i; r.i = d ? s[in.a].i % d : 0; break; }
+      case IP_IWRAP: {
+        const int64_t d = s[in.b].i;
+        r.i = d ? ((s[in.a].i % d) + d) % d : 0;
+        break;
+      }
+      case IP_INEG: r.i = 0 - s[in.a].i; break;
+      case IP_FEQ: r.i = s[in.a].f == s[in.b].f; break;
+      case IP_FLT: r.i = s[in.a].f < s[in.b].f; break;
+      case IP_FLE: r.i = s[in.a].f <= s[in.b].f; break;
+      case IP_IEQ: r.i = s[in.a].i == s[in.b].i; break;
+      case IP_ILT: r.i = s[in.a].i < s[in.b].i; break;
+      case IP_ILE: r.i = s[in.a].i <= s[in.b].i; break;
+      case IP_BEQ: r.i = (s[in.a].i != 0) == (s[in.b].i != 0); break;
+      case IP_AND: r.i = (s[in.a].i != 0) & (s[in.b].i != 0); break;
+      case IP_OR: r.i = (s[in.a].i != 0) | (s[in.b].i != 0); break;
+      case IP_SELECT: r.u = s[in.a].i ? s[in.b].u : s[in.c].u; break;
+      case IP_TOSCALAR: r.f = (float)s[in.a].i; break;
+      case IP_TOINDEX: r.i = (int64_t)s[in.a].f; break;
+      case IP_ARRAY_READ: r.u = s[p.array_table[in.imm + (int)s[in.a].i]].u; break;
+      default: break;
+    }
+    s[in.dst] = r;
+  }
+}
+
+__device__ __forceinline__ int64_t flat_index(const IpTensorOp& op, const Slot* s) {
+  int64_t idx = op.offset;
+  for (int t = 0; t < op.nterms; ++t) idx += op.coef[t] * s[op.slot[t]].i;
+  return idx;
+}
+
+// Decode a linear index into the iterators of loops [lo, hi) (last loop fastest).
+__device__ __forceinline__ void decode(const IpProgram& p, int lo, int hi, int64_t lin, Slot* s) {
+  if (lin < 0x7fffffffLL) {
+    uint32_t v = (uint32_t)lin;
+    for (int l = hi - 1; l >= lo; --l) {
+      const uint32_t c = (uint32_t)p.loops[l].count;
+      const uint32_t q = v / c;
+      s[p.loops[l].slot].i = p.loops[l].start + p.loops[l].step * (int64_t)(v - q * c);
+      v = q;
+    }
+  } else {
+    int64_t v = lin;
+    for (int l = hi - 1; l >= lo; --l) {
+      const int64_t c = p.loops[l].count;
+      const int64_t q = v / c;
+      s[p.loops[l].slot].i = p.loops[l].start + p.loops[l].step * (v - q * c);
+      v = q;
+    }
+  }
+}
+
+template <bool kStrict>
+__global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constant__ IpProgram p, int pb, int rb,
+                                                            int points_fast) {
+  __shared__ float partial[IP_THREADS];
+  Slot s[IP_MAX_SLOTS];
+  const int t = threadIdx.x;
+  const int pl = points_fast ? t % pb : t / rb;  // point within the block
+  const int rl = points_fast ? t / pb : t % rb;  // reduction slice
+  const int64_t nblocks = (p.npoints + pb - 1) / pb;
+  float* const out = reinterpret_cast<float*>(p.write.base);
+  for (int i = 0; i < p.nlits; ++i) s[p.lit_slot[i]].u = p.lits[i];
+
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t point = blk * pb + pl;
+    const bool active = point < p.npoints;
+    float acc = 0.0f;
+    int64_t widx = 0;
+    if (active) {
+      decode(p, 0, p.npar, point, s);
+      if (!p.scatter) {
+        // the write index does not depend on reduction loops: evaluate it once
+        if (p.nred > 0) {
+          decode(p, p.npar, p.nloops, 0, s);
+          run_instrs(p.index_instrs, p.nindex_instrs, s, p);
+          widx = flat_index(p.write, s);
+        }
+        if (kStrict && p.accumulate && p.nred > 0) acc = out[widx];
+      }
+      for (int64_t r = rl; r < p.nred; r += rb) {
+        decode(p, p.npar, p.nloops, r, s);
+        run_instrs(p.index_instrs, p.nindex_instrs, s, p);
+        for (int k = 0; k < p.nreads; ++k) {
+          const IpTensorOp& op = p.reads[k];
+          s[op.dst].u = 0;
+          s[op.dst].f = reinterpret_cast<const float*>(op.base)[flat_index(op, s)];
+        }
+        run_instrs(p.instrs, p.ninstrs, s, p);
+        const float v = s[p.write.dst].f;
+        if (p.scatter) {
+          const int64_t w = flat_index(p.write, s);
+          out[w] = p.accumulate ? out[w] + v : v;
+        } else {
+          acc = acc + v;
+        }
+      }
+    }
+    if (p.scatter) continue;
+    if (rb > 1) {
+      partial[t] = acc;
+      __syncthreads();
+      for (int half = rb >> 1; half > 0; half >>= 1) {
+        if (rl < half) {
+          const int other = points_fast ? t + half * pb : t + half;
+          partial[t] += partial[other];
+        }
+        __syncthreads();
+      }
+      acc = partial[t];
+      __syncthreads();
+    }
+    if (active && rl == 0 && p.nred > 0) {
+      if (kStrict) out[widx] = acc;
+      else out[widx] = p.accumulate ? out[widx] + acc : acc;
+    }
+  }
+}
+
+}  // namespace
+
+void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
+                   cudaStream_t st) {
+  if (prog.npoints <= 0 || prog.nred <= 0) return;
+  if (pb * rb != IP_THREADS) fail(EGB_ERR_GPU, "interp: PB*RB must be %d", IP_THREADS);
+  const int64_t nblocks = (prog.npoints + pb - 1) / pb;
+  const int64_t cap = (int64_t)ctx.sm_count * 8;
+  const int grid = (int)(nblocks < cap ? nblocks : cap);
+  {
+    Launch l(ctx, KC_INTERP, st);
+    if (strict) interp_kernel<true><<<grid, IP_THREADS, 0, st>>>(prog, pb, rb, points_fast);
+    else interp_kernel<false><<<grid, IP_THREADS, 0, st>>>(prog, pb, rb, points_fast);
+  }
+  EGB_CUDA(cudaGetLastError());
+}
+
+}  // namespace egb

@@ -1,0 +1,376 @@
+// Launch-plan construction and execution (see runtime.hpp).
+#include "runtime.hpp"
+
+#include <string.h>
+
+#include <algorithm>
+#include <set>
+
+#include "lower.hpp"
+
+namespace egb {
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int64_t shape_len(const std::vector<int64_t>& s) {
+  int64_t n = 1;
+  for (auto d : s) n *= d;
+  return n;
+}
+
+std::string shape_text(const std::vector<int64_t>& s) {
+  std::string out = "[";
+  for (size_t i = 0; i < s.size(); ++i) out += (i ? "," : "") + std::to_string(s[i]);
+  return out + "]";
+}
+
+// splitmix64: parameter initialisation U(initRange) (model.nim:244-247). The reference draws from
+// Nim's global RNG, which is not reproducible elsewhere; parity tests inject parameters explicitly.
+struct SplitMix {
+  uint64_t s;
+  explicit SplitMix(uint64_t seed) : s(seed) {}
+  uint64_t next() {
+    uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+  }
+  double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+}  // namespace
+
+Plan::~Plan() {
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (arena) cudaFree(arena);
+}
+
+Model::~Model() {
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  plans.clear();
+  for (auto& kv : state)
+    if (kv.second.owned && kv.second.ptr) cudaFree(kv.second.ptr);
+}
+
+// ------------------------------------------------------------------ plan construction
+
+namespace {
+
+void* tensor_ptr(Model& m, Plan& plan, int id) {
+  auto s = m.state.find(id);
+  if (s != m.state.end()) return s->second.ptr;
+  auto b = plan.bound.find(id);
+  if (b != plan.bound.end() && b->second) return const_cast<void*>(b->second);
+  auto t = plan.tensors.find(id);
+  if (t != plan.tensors.end()) return t->second.ptr;
+  return nullptr;
+}
+
+void build_nodes_impl(Model& m, Plan& plan) {
+  const std::vector<KernelInfo>& info = plan.info;
+  const Target& target = *plan.target;
+  Context& ctx = *m.ctx;
+  plan.nodes.clear();
+  plan.launches_per_run = 0;
+  std::map<int, void*> ptrs;
+  for (int id : target.tensors) ptrs[id] = tensor_ptr(m, plan, id);
+  for (auto& kv : plan.shapes)
+    if (!ptrs.count(kv.first)) ptrs[kv.first] = tensor_ptr(m, plan, kv.first);
+
+  if (plan.zero_bytes) {
+    Node n;
+    n.kind = Node::MEMSET;
+    n.label = "zero results";
+    n.ptr = plan.arena;
+    n.bytes = plan.zero_bytes;
+    plan.nodes.push_back(n);
+  }
+  for (int id : target.tensors) {
+    const TensorDef& td = m.prog->tdef(id);
+    if (td.kind == TensorKind::Random) {
+      Node n;
+      n.kind = Node::RANDOM;
+      n.label = "random tensor" + std::to_string(id - 1);
+      n.ptr = ptrs[id];
+      n.bytes = (size_t)shape_len(plan.shapes.at(id)) * 4;
+      n.lo = (float)td.range_lo;
+      n.hi = (float)td.range_hi;
+      n.tensor = id;
+      plan.nodes.push_back(n);
+    }
+  }
+
+  // bf16 operand planes are cached per (tensor, orientation) until the tensor is written again
+  std::map<std::pair<int, int>, std::pair<__nv_bfloat16*, __nv_bfloat16*>> planes;
+  size_t plane_cursor = 0;
+  char* plane_base = plan.arena + plan.plane_off;
+  const size_t plane_cap = plan.plane_bytes;
+  auto get_planes = [&](int tensor, bool k_major_needs_transpose, int64_t rows, int64_t cols, int64_t ld,
+                        int64_t& out_ld) {
+    // rows x cols is the stored fp32 matrix; the planes are [rows, cols] or (transposed) [cols, rows]
+    const int64_t kdim = k_major_needs_transpose ? rows : cols;
+    const int64_t outer = k_major_needs_transpose ? cols : rows;
+    out_ld = (kdim + 7) & ~int64_t(7);
+    auto key = std::make_pair(tensor, k_major_needs_transpose ? 1 : 0);
+    auto it = planes.find(key);
+    if (it != planes.end()) return it->second;
+    const size_t bytes = align_up((size_t)outer * out_ld * 2, 256);
+    if (plane_cursor + 2 * bytes > plane_cap) fail(EGB_ERR_RUNTIME, "internal: operand plane arena exhausted");
+    auto* hi = (__nv_bfloat16*)(plane_base + plane_cursor);
+    auto* mid = (__nv_bfloat16*)(plane_base + plane_cursor + bytes);
+    plane_cursor += 2 * bytes;
+    Node n;
+    n.kind = Node::SPLIT;
+    n.label = "split tensor" + std::to_string(tensor - 1) + (k_major_needs_transpose ? " (transposed)" : "");
+    n.split_src = (const float*)ptrs[tensor];
+    n.split_rows = (int)rows;
+    n.split_cols = (int)cols;
+    n.split_ld = (int)ld;
+    n.split_transpose = k_major_needs_transpose;
+    n.split_hi = hi;
+    n.split_mid = mid;
+    n.split_dst_ld = (int)out_ld;
+    plan.nodes.push_back(n);
+    planes[key] = std::make_pair(hi, mid);
+    return planes[key];
+  };
+
+  for (size_t ki = 0; ki < target.kernels.size(); ++ki) {
+    const Kernel& k = *target.kernels[ki];
+    const KernelInfo& inf = info[ki];
+    if (inf.is_gemm && !m.strict) {
+      const GemmPattern& g = inf.gemm;
+      Node n;
+      n.kind = Node::GEMM;
+      n.label = "gemm tensor" + std::to_string(g.c_tensor - 1);
+      n.kernel_index = (int)ki;
+      int64_t lda = 0, ldb = 0;
+      // A operand must be [M, K] with K contiguous: stored [M,K] (no transpose) or [K,M] (transpose)
+      auto pa = g.trans_a ? get_planes(g.a_tensor, true, g.K, g.M, g.lda, lda)
+                          : get_planes(g.a_tensor, false, g.M, g.K, g.lda, lda);
+      // B operand must be [N, K] with K contiguous: stored [N,K] (no transpose) or [K,N] (transpose)
+      auto pb = g.trans_b ? get_planes(g.b_tensor, false, g.N, g.K, g.ldb, ldb)
+                          : get_planes(g.b_tensor, true, g.K, g.N, g.ldb, ldb);
+      n.gemm.a_hi = pa.first; n.gemm.a_mid = pa.second; n.gemm.lda = (int)lda;
+      n.gemm.b_hi = pb.first; n.gemm.b_mid = pb.second; n.gemm.ldb = (int)ldb;
+      n.gemm.M = (int)g.M; n.gemm.N = (int)g.N; n.gemm.K = (int)g.K;
+      n.gemm.C = (float*)ptrs[g.c_tensor];
+      n.gemm.ldc = (int)g.ldc;
+      n.gemm.flags = inf.overwrite ? 0 : GEMM_ACCUMULATE;
+      n.gemm.alpha = 1.0f;
+      plan.nodes.push_back(n);
+    } else {
+      Lowered lw = lower_kernel(k, plan.shapes, ptrs, m.epoch, m.strict, inf.overwrite, ctx.sm_count);
+      Node n;
+      n.kind = Node::INTERP;
+      n.label = "kernel " + std::to_string(ki) + " -> tensor" + std::to_string(k.write.tensor - 1);
+      n.ip = lw.ip;
+      n.pb = lw.pb;
+      n.rb = lw.rb;
+      n.points_fast = lw.points_fast;
+      n.strict = m.strict;
+      n.uses_epoch = lw.uses_epoch;
+      n.kernel_index = (int)ki;
+      plan.nodes.push_back(n);
+    }
+    // the written tensor's cached planes are stale now
+    for (auto it = planes.begin(); it != planes.end();)
+      it = it->first.first == k.write.tensor ? planes.erase(it) : std::next(it);
+  }
+  for (auto& n : plan.nodes)
+    if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
+  plan.epoch_built = m.epoch;
+  plan.graph_valid = false;
+}
+
+}  // namespace
+
+void Model::build_nodes(Plan& plan) { build_nodes_impl(*this, plan); }
+
+Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& ids,
+                      const std::vector<std::vector<int64_t>>& in_shapes) {
+  Target* target = prog->find_target(target_name);
+  if (!target) fail(EGB_ERR_RUNTIME, "%s is not a target of the model", target_name.c_str());
+  std::vector<std::pair<int, std::vector<int64_t>>> sig;
+  for (size_t i = 0; i < ids.size(); ++i) sig.emplace_back(ids[i], in_shapes[i]);
+  std::sort(sig.begin(), sig.end());
+  for (auto& p : plans)
+    if (p->target_name == target_name && p->input_sig == sig) return *p;
+
+  // ---- run-time shape inference (passes.nim:1386-1436), once per input-shape signature
+  ShapeTable inputs;
+  for (auto& s : sig) inputs[s.first] = s.second;
+  auto plan = std::make_unique<Plan>();
+  plan->target_name = target_name;
+  plan->target = target;
+  plan->input_sig = sig;
+  plan->shapes = infer_shapes(*prog, *target, inputs);
+  for (auto& kv : state) plan->shapes[kv.first] = kv.second.shape;
+
+  // ---- classify kernels, decide overwrite vs accumulate and which results need zero-filling
+  plan->info.resize(target->kernels.size());
+  std::set<int> written, read_first, needs_zero;
+  size_t plane_bytes = 0;
+  for (size_t ki = 0; ki < target->kernels.size(); ++ki) {
+    const Kernel& k = *target->kernels[ki];
+    if (k.is_generator()) fail(EGB_ERR_GENERATOR, "program still contains generator kernels; compile it first");
+    KernelInfo& inf = plan->info[ki];
+    for (auto& r : k.reads) {
+      if (!plan->shapes.count(r.tensor)) fail(EGB_ERR_SHAPE, "Missing shape for tensor%d", r.tensor - 1);
+      if (!written.count(r.tensor)) read_first.insert(r.tensor);
+    }
+    inf.is_gemm = !strict && match_gemm(k, plan->shapes, inf.gemm);
+    const int wt = k.write.tensor;
+    const bool fresh = prog->tdef(wt).kind == TensorKind::Result && !written.count(wt) && !read_first.count(wt);
+    bool reads_self = false;
+    for (auto& r : k.reads) reads_self = reads_self || r.tensor == wt;
+    inf.overwrite = fresh && !reads_self && (inf.is_gemm || covers_whole_tensor(k, plan->shapes));
+    if (prog->tdef(wt).kind == TensorKind::Result && !written.count(wt) && !inf.overwrite) needs_zero.insert(wt);
+    written.insert(wt);
+    if (inf.is_gemm) {
+      const GemmPattern& g = inf.gemm;
+      const size_t kp = (size_t)((g.K + 7) & ~int64_t(7));
+      plane_bytes += 2 * align_up((size_t)g.M * kp * 2, 256) + 2 * align_up((size_t)g.N * kp * 2, 256);
+    }
+  }
+  for (int id : target->tensors)
+    if (prog->tdef(id).kind == TensorKind::Result && !written.count(id)) needs_zero.insert(id);  // read-only results
+
+  // ---- arena: [results that need zeroing][other results, inputs, random][bf16 operand planes]
+  size_t cursor = 0;
+  std::vector<int> order;
+  for (int id : target->tensors)
+    if (needs_zero.count(id)) order.push_back(id);
+  const size_t n_zero = order.size();
+  for (int id : target->tensors) {
+    const TensorKind kind = prog->tdef(id).kind;
+    if (needs_zero.count(id)) continue;
+    if (kind == TensorKind::Result || kind == TensorKind::Input || kind == TensorKind::Random) order.push_back(id);
+  }
+  std::map<int, size_t> offs;
+  for (size_t i = 0; i < order.size(); ++i) {
+    const int id = order[i];
+    auto sh = plan->shapes.find(id);
+    if (sh == plan->shapes.end()) fail(EGB_ERR_SHAPE, "Missing shape for tensor%d", id - 1);
+    for (auto d : sh->second)
+      if (d < 0) fail(EGB_ERR_SHAPE, "tensor%d has a negative dimension %s", id - 1, shape_text(sh->second).c_str());
+    offs[id] = cursor;
+    cursor += align_up((size_t)shape_len(sh->second) * 4, 256);
+    if (i + 1 == n_zero) plan->zero_bytes = cursor;
+  }
+  if (n_zero == 0) plan->zero_bytes = 0;
+  plan->plane_off = cursor;
+  plan->plane_bytes = plane_bytes;
+  cursor += plane_bytes;
+  plan->arena_bytes = std::max<size_t>(cursor, 256);
+  cudaError_t e = cudaMalloc((void**)&plan->arena, plan->arena_bytes);
+  if (e != cudaSuccess)
+    fail(EGB_ERR_GPU, "cudaMalloc of %zu bytes for target %s failed: %s", plan->arena_bytes, target_name.c_str(),
+         cudaGetErrorString(e));
+  for (int id : order) {
+    DevTensor t;
+    t.ptr = plan->arena + offs[id];
+    t.shape = plan->shapes[id];
+    t.bytes = (size_t)shape_len(t.shape) * 4;
+    plan->tensors[id] = t;
+  }
+  Plan* raw = plan.get();
+  build_nodes(*raw);
+  plans.push_back(std::move(plan));
+  return *raw;
+}
+
+// ------------------------------------------------------------------ execution
+
+static void launch_node(Model& m, Node& n, cudaStream_t st) {
+  Context& ctx = *m.ctx;
+  switch (n.kind) {
+    case Node::MEMSET: EGB_CUDA(cudaMemsetAsync(n.ptr, 0, n.bytes, st)); break;
+    case Node::RANDOM:
+      launch_fill_uniform(ctx, (float*)n.ptr, n.bytes / 4, n.lo, n.hi, m.seed, m.rng_counter, st);
+      break;
+    case Node::SPLIT:
+      launch_split_bf16(ctx, n.split_src, n.split_rows, n.split_cols, n.split_ld, n.split_transpose, n.split_hi,
+                        n.split_mid, n.split_dst_ld, n.split_act, st);
+      break;
+    case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
+    case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st); break;
+    default: fail(EGB_ERR_RUNTIME, "internal: unknown plan node");
+  }
+}
+
+void Model::run(Plan& plan) {
+  Context& c = *ctx;
+  bool has_random = false, uses_epoch = false;
+  for (auto& n : plan.nodes) {
+    has_random = has_random || n.kind == Node::RANDOM;
+    uses_epoch = uses_epoch || n.uses_epoch;
+  }
+  if (uses_epoch && plan.epoch_built != epoch) build_nodes(plan);
+  const bool graphable = use_graphs && !c.timing && !has_random && plan.nodes.size() >= 3;
+  if (graphable) {
+    if (!plan.graph_valid) {
+      if (plan.graph_exec) {
+        cudaGraphExecDestroy(plan.graph_exec);
+        plan.graph_exec = nullptr;
+      }
+      const size_t launches_before = c.launches;
+      cudaGraph_t graph = nullptr;
+      EGB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        for (auto& n : plan.nodes) launch_node(*this, n, c.stream);
+      } catch (...) {
+        cudaStreamEndCapture(c.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      EGB_CUDA(cudaStreamEndCapture(c.stream, &graph));
+      cudaError_t e = cudaGraphInstantiate(&plan.graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) fail(EGB_ERR_GPU, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+      c.launches = launches_before;  // capture is not execution
+      plan.graph_valid = true;
+    }
+    EGB_CUDA(cudaGraphLaunch(plan.graph_exec, c.stream));
+    c.launches += plan.launches_per_run;
+  } else {
+    for (auto& n : plan.nodes) launch_node(*this, n, c.stream);
+  }
+  if (has_random) rng_counter++;
+  plan.runs++;
+  last_plan = &plan;
+}
+
+// ------------------------------------------------------------------ model construction
+
+std::unique_ptr<Model> new_model(Context& ctx, std::shared_ptr<Program> prog, uint64_t seed) {
+  if (prog->f64) fail(EGB_ERR_GENERATOR, "float64 models are not supported by the B200 backend (fp32 only)");
+  if (!prog->compiled) compile_program(*prog);
+  auto m = std::make_unique<Model>();
+  m->ctx = &ctx;
+  m->prog = prog;
+  m->seed = seed;
+  SplitMix rng(seed * 0x2545F4914F6CDD1Dull + 0x1234567ull);
+  auto alloc_state = [&](int id, bool random) {
+    const TensorDef& td = prog->tdef(id);
+    for (auto d : td.shape)
+      if (d < 0) fail(EGB_ERR_SHAPE, "tensor%d (%s) needs a static shape", id - 1, td.name.c_str());
+    DevTensor t;
+    t.shape = td.shape;
+    t.bytes = (size_t)shape_len(td.shape) * 4;
+    t.owned = true;
+    EGB_CUDA(cudaMalloc(&t.ptr, std::max<size_t>(t.bytes, 4)));
+    std::vector<float> host((size_t)shape_len(td.shape), 0.0f);
+    if (random)
+      for (auto& v : host) v = (float)(td.range_lo + (td.range_hi - td.range_lo) * rng.uniform());
+    if (t.bytes) EGB_CUDA(cudaMemcpy(t.ptr, host.data(), t.bytes, cudaMemcpyHostToDevice));
+    m->state[id] = t;
+  };
+  for (int id : prog->params) alloc_state(id, true);
+  for (int id : prog->caches) alloc_state(id, false);
+  return m;
+}
+
+}  // namespace egb

@@ -1,0 +1,119 @@
+// Host runtime of the B200 backend: what exprgrad/model.nim does for a CompileGpu target
+// (model.nim:302-383, 392-454) plus what its JIT'd `target_<name>` function does (launch every
+// kernel of the target, llvmgen.nim:455-500, 518-563) - without a JIT: every kernel of a compiled
+// target is lowered once per input-shape signature into a launch plan (tcgen05 contraction nodes,
+// generic loop-nest nodes, fused nodes), the plan is captured into a CUDA graph, and call/apply/fit
+// replay it.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "egb_internal.hpp"
+#include "interp.hpp"
+#include "lower.hpp"
+#include "program.hpp"
+
+namespace egb {
+
+struct DevTensor {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  std::vector<int64_t> shape;
+  bool owned = false;
+  int64_t len() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct Node {
+  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, FUSED } kind = INTERP;
+  std::string label;
+  // INTERP
+  IpProgram ip;
+  int pb = 256, rb = 1, points_fast = 1;
+  bool strict = false;
+  bool uses_epoch = false;
+  int kernel_index = -1;  // index into target.kernels (for re-lowering when the epoch changes)
+  // GEMM
+  GemmArgs gemm;
+  // SPLIT
+  const float* split_src = nullptr;
+  int split_rows = 0, split_cols = 0, split_ld = 0, split_dst_ld = 0, split_act = 0;
+  bool split_transpose = false;
+  __nv_bfloat16 *split_hi = nullptr, *split_mid = nullptr;
+  // MEMSET / RANDOM / ALLREDUCE
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  float lo = 0, hi = 1;
+  int tensor = 0;
+};
+
+struct Model;
+
+struct KernelInfo {
+  bool is_gemm = false;
+  GemmPattern gemm;
+  bool overwrite = false;  // first writer of a zero-initialised result that it covers completely
+};
+
+struct Plan {
+  std::string target_name;
+  const Target* target = nullptr;
+  ShapeTable shapes;
+  std::vector<std::pair<int, std::vector<int64_t>>> input_sig;
+  std::map<int, DevTensor> tensors;   // plan-owned: inputs, results, random tensors (views into the arena)
+  std::map<int, const void*> bound;   // input tensors currently bound to caller-owned device memory
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  size_t zero_bytes = 0;              // leading part of the arena that must be zeroed before every run
+  std::vector<KernelInfo> info;       // one per target kernel
+  size_t plane_off = 0, plane_bytes = 0;  // bf16 operand-plane region of the arena
+  std::vector<Node> nodes;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+  int64_t epoch_built = -1;
+  uint64_t runs = 0;
+  size_t launches_per_run = 0;
+  ~Plan();
+};
+
+struct CommHooks;  // data-parallel extension (dist.cu)
+
+struct Model {
+  Context* ctx = nullptr;
+  std::shared_ptr<Program> prog;
+  std::map<int, DevTensor> state;  // params + caches, persistent in HBM (model.nim:37-38)
+  int64_t epoch = 0;
+  uint64_t seed = 0;
+  uint64_t rng_counter = 0;
+  bool strict = false;      // bit-exact mode: sequential accumulation everywhere, no tensor cores
+  bool use_graphs = true;
+  std::vector<std::unique_ptr<Plan>> plans;
+  Plan* last_plan = nullptr;
+  CommHooks* comm = nullptr;
+  ~Model();
+
+  Plan& get_plan(const std::string& target, const std::vector<int>& ids,
+                 const std::vector<std::vector<int64_t>>& shapes);
+  void build_nodes(Plan& plan);  // (re)lower every kernel of the plan against the current pointers / epoch
+  void run(Plan& plan);
+};
+
+std::unique_ptr<Model> new_model(Context& ctx, std::shared_ptr<Program> prog, uint64_t seed);
+
+// kernels (host launchers)
+void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
+                   cudaStream_t st);
+void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi, uint64_t seed, uint64_t counter,
+                         cudaStream_t st);
+
+// passes.cpp helpers reused by the planner
+int eval_index_instrs(const std::vector<Instr>& instrs, const ShapeTable& shapes, std::map<int, int64_t>& regs,
+                      int64_t epoch);
+int64_t eval_linear(const LinearIndex& li, const std::map<int, int64_t>& regs);
+
+}  // namespace egb

@@ -42,6 +42,8 @@ extern "C" {
 #define EGB_ERR_GENERATOR 6 /* GeneratorError (exprgrad/ir.nim:24)           */
 #define EGB_ERR_VALUE 7     /* ValueError (linear-system solver, passes.nim:1262-1296) */
 
+#define EGB_MAX_RANK 8
+
 typedef struct egb_context egb_context;
 typedef struct egb_buffer egb_buffer;
 typedef struct egb_kernel egb_kernel;
@@ -128,6 +130,70 @@ int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const voi
 /* fp32 [rows, cols] -> bf16 hi/mid planes ([cols, rows] when transpose != 0). act: 0 none, 1 relu. */
 int egb_split_bf16(egb_context* ctx, const float* src, int64_t rows, int64_t cols, int64_t ld, int transpose,
                    void* hi, void* mid, int64_t dst_ld, int act);
+
+/* ---- 3. program / model --------------------------------------------------------------------- */
+
+/* Parse the text form of an exprgrad `Program` (exprgrad/ir.nim:263-270): either the SOURCE program
+ * that `toProgram` builds from the Fun graphs (exprgrad/parser.nim:404-417; stage 0) or the program
+ * after exprgrad's own semantics-defining passes (model.nim:46-58; stage 1). The grammar is documented
+ * in exprgrad_b200/csrc/program.cpp; INTEGRATION.md shows the Nim serialiser. */
+int egb_program_parse(const char* text, size_t len, egb_program** out);
+/* program.compile() up to and including sortShapeConstraints (exprgrad/model.nim:46-58): dead-code
+ * elimination, index folding, read dedup, shape constraints, reverse-mode autodiff (`generate`,
+ * passes.nim:558-698), dead-kernel elimination, loop bounds, independent loops, loop order.
+ * No-op for a stage-1 program. ShapeError / GradientError are reported as EGB_ERR_SHAPE / _GRADIENT. */
+int egb_program_compile(egb_program* program);
+/* Text form of the current program state (used by the tests to compare the native passes with the
+ * oracle's). Two-call protocol: *needed receives the size including the terminating NUL. */
+int egb_program_serialize(egb_program* program, char* buf, size_t cap, size_t* needed);
+int egb_program_free(egb_program* program);
+int egb_program_tensor_count(egb_program* program, int* count);
+/* kind: 0 result, 1 input, 2 param, 3 cache, 4 random (exprgrad/ir.nim:222-233). dims has room for
+ * EGB_MAX_RANK entries; -1 = dynamic. */
+int egb_program_tensor_info(egb_program* program, int tensor_id, int* kind, int* rank, int64_t* dims, char* name,
+                            size_t name_cap);
+int egb_program_target_output(egb_program* program, const char* target, int* tensor_id);
+/* inferShapes (exprgrad/passes.nim:1386-1436): host-only, integer-exact. Inputs are given by name with
+ * their shapes flattened into `dims` (ranks[i] entries each). Returns the shape of `tensor_id`
+ * (0 = the target's output). Needs no GPU. */
+int egb_program_infer_shapes(egb_program* program, const char* target, int n_args, const char* const* names,
+                             const int* ranks, const int64_t* dims, int tensor_id, int* out_rank,
+                             int64_t* out_dims);
+
+/* newModel (exprgrad/model.nim:232-251): compiles the program if needed, allocates every parameter
+ * in HBM initialised U(initRange) from `seed` and every cache zero-filled. The model keeps the
+ * program alive. float64 programs are rejected (EGB_ERR_GENERATOR). */
+int egb_model_create(egb_context* ctx, egb_program* program, uint64_t seed, egb_model** out);
+int egb_model_free(egb_model* model);
+/* Options: "strict" 1 = bit-exact mode (every kernel runs on the generic loop-nest kernel with the
+ * reference's sequential accumulation order; no tensor cores), "graphs" 0 = launch eagerly instead
+ * of replaying a CUDA graph, "epoch" = set model.epoch (exprgrad/model.nim:39). */
+int egb_model_set_option(egb_model* model, const char* key, int64_t value);
+int egb_model_epoch(egb_model* model, int64_t* epoch);
+/* model.params / model.caches are public in the reference (exprgrad/model.nim:37-38): blocking copies
+ * of one state tensor (or, for read, of any tensor of the most recent call) to / from host memory. */
+int egb_model_write_tensor(egb_model* model, int tensor_id, const void* host, size_t bytes);
+int egb_model_read_tensor(egb_model* model, int tensor_id, void* host, size_t bytes);
+int egb_model_tensor_shape(egb_model* model, int tensor_id, int* rank, int64_t* dims);
+int egb_model_tensor_device_ptr(egb_model* model, int tensor_id, void** ptr);
+/* Model.call / Model.apply (exprgrad/model.nim:392-411). Inputs are passed by name; data[i] is a
+ * host pointer (copied H2D on the context's stream) or, when on_device[i] != 0, a device pointer
+ * that is used in place. Shapes are inferred once per distinct input-shape signature and the launch
+ * plan is cached; the launches are asynchronous. out_rank/out_dims (may be NULL = apply) receive the
+ * output tensor's shape (out_rank = -1 if the target has no output). Errors: unknown target/input ->
+ * EGB_ERR_RUNTIME (model.nim:358-359, 395-396), shape problems -> EGB_ERR_SHAPE. */
+int egb_model_call(egb_model* model, const char* target, int n_args, const char* const* names,
+                   const void* const* data, const int* ranks, const int64_t* dims, const int* on_device,
+                   int* out_rank, int64_t* out_dims);
+/* readOutput (exprgrad/model.nim:370-376): blocking D2H of the last call's output tensor. */
+int egb_model_read_output(egb_model* model, void* dst, size_t bytes);
+/* Model.fit (exprgrad/model.nim:413-454): shapes inferred once with dim 0 = batch_size, epoch += 1,
+ * one plan replay per full batch of host data (trailing partial batch dropped). */
+int egb_model_fit(egb_model* model, const char* target, int n_args, const char* const* names,
+                  const void* const* data, const int* ranks, const int64_t* dims, int64_t batch_size,
+                  int64_t* batches_run);
+/* Human-readable node list of the most recent call's launch plan. */
+int egb_model_describe_plan(egb_model* model, char* buf, size_t cap, size_t* needed);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,102 @@
+"""CPU-only: the library's native passes (csrc/passes.cpp) against the oracle's restatement of
+exprgrad/passes.nim on the same source graphs - compiled programs must be token-identical (kernel
+order, registers, autodiff output, sorted shape constraints), and run-time shape inference
+(passes.nim:1386-1436) must be bit-exact."""
+import numpy as np
+import pytest
+
+import graphs as G
+
+
+def _tokens(text):
+    out = []
+    for t in text.split():
+        if t.startswith(("0x", "-0x")) or t in ("inf", "-inf", "nan"):
+            out.append(float.fromhex(t) if "x" in t else float(t))
+        else:
+            out.append(t)
+    return out
+
+
+def _both(name, **kw):
+    import oracle as o
+    from oracle import layers as OL
+    from oracle.passes import compile_program
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    oprog = o.ir.to_program(G.ALL[name](o, OL, **kw))
+    compile_program(oprog)
+    prog = Program.from_graphs(G.ALL[name](F, PL, **kw)).compile()
+    return o, oprog, F, prog
+
+
+@pytest.mark.parametrize("name", sorted(G.ALL))
+def test_compiled_program_matches_oracle(name):
+    o, oprog, F, prog = _both(name)
+    want = _tokens(F.serialize(oprog, compiled=True))
+    got = _tokens(prog.serialize())
+    assert len(want) == len(got)
+    for i, (a, b) in enumerate(zip(want, got)):
+        assert a == b, f"token {i}: oracle {want[max(0, i - 8):i + 4]} vs library {got[max(0, i - 8):i + 4]}"
+
+
+def test_serialize_parse_round_trip():
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    prog = Program.from_graphs(G.dense_net(F, PL)).compile()
+    text = prog.serialize()
+    again = Program(text)
+    assert _tokens(again.serialize()) == _tokens(text)
+    again.compile()  # stage-1 programs are left untouched
+    assert _tokens(again.serialize()) == _tokens(text)
+
+
+SHAPE_CASES = [
+    ("matmul", "c", {"a": [4096, 4096], "b": [4096, 4096]}),
+    ("matmul", "c", {"a": [2, 3], "b": [3, 2]}),
+    ("matmul", "c", {"a": [123, 100], "b": [100, 77]}),
+    ("dense_net", "predict", {"x": [1024, 784]}),
+    ("dense_net", "loss", {"x": [1024, 784], "y": [1024, 10]}),
+    ("dense_net", "train", {"x": [8192, 784], "y": [8192, 10]}),
+    ("xor_net", "train", {"x": [4, 2], "y": [4, 1]}),
+    ("conv2_net", "conv", {"img": [256, 224, 224, 3]}),
+    ("conv2_net", "dimg", {"img": [2, 9, 8, 3]}),
+    ("conv2_net", "dw", {"img": [2, 9, 8, 3]}),
+    ("fashion_net", "train", {"x": [32, 12, 12, 1], "y": [32, 10]}),
+    ("fashion_net", "predict", {"x": [7, 12, 12, 1]}),
+]
+
+
+@pytest.mark.parametrize("name,target,inputs", SHAPE_CASES)
+def test_infer_shapes_bit_exact(name, target, inputs):
+    o, oprog, F, prog = _both(name)
+    from oracle.passes import infer_shapes
+    want = infer_shapes(oprog, target, {oprog.inputs[k]: v for k, v in inputs.items()})
+    tids = sorted(want)
+    assert len(tids) >= 2
+    for tid in tids:
+        got = prog.infer_shapes(target, inputs, tensor_id=tid)
+        assert got == list(want[tid]), f"tensor{tid - 1}: oracle {want[tid]} vs library {got}"
+
+
+def test_shape_errors_match_reference():
+    """tests/test_errors.nim:46-89 through the C ABI (no GPU needed: compile + infer only)."""
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F
+    from exprgrad_b200.model import Program
+    prog = Program.from_graphs([F.input("x", [2, 3]).target("y")]).compile()
+    with pytest.raises(eg.ShapeError):
+        prog.infer_shapes("y", {"x": [10, 10]})
+    with pytest.raises(eg.RuntimeError_):
+        prog.infer_shapes("nope", {"x": [2, 3]})
+    with pytest.raises(eg.RuntimeError_):
+        prog.infer_shapes("y", {"x": [2, 3], "abc": [2, 3]})
+    r = F.Fun(); r.raw[F.Iter("x")] += F.lift(1.0)
+    with pytest.raises(eg.ShapeError):
+        Program.from_graphs([r.target("y")]).compile()
+    r = F.Fun(); r[0] += F.lift(1.0); r[0, 0] += F.lift(1.0)
+    with pytest.raises(eg.ShapeError):
+        Program.from_graphs([r.target("y")]).compile()
+    c = F.Fun(); it = F.Iter("it"); c.raw[it] += F.input("a").raw[it] + F.input("b").raw[it]
+    with pytest.raises(eg.ShapeError):
+        Program.from_graphs([c.target("c")]).compile()

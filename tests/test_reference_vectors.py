@@ -1,20 +1,32 @@
-"""Pins the CPU oracle against the reference's own known-answer tests.
+"""The reference's own known-answer tests, run against every backend (tests/backends.py).
 
-Every case below restates one test of /root/reference (file:line in each docstring) with the oracle
-DSL and checks the reference's expected values with the reference's comparison (exact `==` on fp32
-tensors unless the reference itself uses a tolerance). The reference cannot be built in this image
-(no Nim / LLVM 13), so these vectors are what anchors the oracle.
+Every case below restates one test of /root/reference (file:line in each docstring) and checks the
+reference's expected values with the reference's comparison (exact `==` on fp32 tensors unless the
+reference itself uses a tolerance).
+  * backend "oracle" (CPU, no GPU needed): pins the CPU oracle - the reference cannot be built in
+    this image (no Nim / LLVM 13), so these vectors are what anchors it.
+  * backends "b200" / "b200_strict" (marked gpu): the same vectors through the product's C-ABI.
 """
 import math
 
 import numpy as np
 import pytest
 
-import oracle as o
-from oracle import Fun, Iter, ShapeError, RuntimeError_, input, param, select, sq, to_scalar
-from oracle import layers as L
+from backends import NAMES, close_libm, make_backend
 
 f32 = np.float32
+o = L = BE = None
+
+
+@pytest.fixture(autouse=True, params=["oracle", pytest.param("b200", marks=pytest.mark.gpu),
+                                      pytest.param("b200_strict", marks=pytest.mark.gpu)])
+def backend(request):
+    be = make_backend(request.param)
+    g = globals()
+    g["o"], g["L"], g["BE"] = be.o, be.L, be
+    for n in NAMES:
+        g[n] = getattr(be, n)
+    yield be
 
 
 def T(shape, vals, dt=np.float32):
@@ -278,24 +290,24 @@ def test_derive_trig_exp_log():
     with Nim `math`, i.e. the same libm, on float32)"""
     x = np.linspace(-8, 8, 17, dtype=f32)
     m = _grad_model({"sin": lambda v, x_, it: o.sin(v), "cos": lambda v, x_, it: o.cos(v)})
-    assert np.array_equal(m.call("sin", {"x": x}), _map1("cosf", x))
-    assert np.array_equal(m.call("cos", {"x": x}), f32(0) - _map1("sinf", x))
+    assert close_libm(m.call("sin", {"x": x}), _map1("cosf", x), BE)
+    assert close_libm(m.call("cos", {"x": x}), f32(0) - _map1("sinf", x), BE)
     m = _grad_model({"exp": lambda v, x_, it: o.exp(v), "exp2x": lambda v, x_, it: o.exp(2.0 * v),
                      "x^3": lambda v, x_, it: o.pow_(v, 3.0), "2^x": lambda v, x_, it: o.pow_(2.0, v)})
-    assert np.array_equal(m.call("exp", {"x": x}), _map1("expf", x))
-    assert np.array_equal(m.call("exp2x", {"x": x}), _map1("expf", f32(2) * x) * f32(2))
-    assert np.array_equal(m.call("x^3", {"x": x}), (x * x) * f32(3))
+    assert close_libm(m.call("exp", {"x": x}), _map1("expf", x), BE)
+    assert close_libm(m.call("exp2x", {"x": x}), _map1("expf", f32(2) * x) * f32(2), BE)
+    assert close_libm(m.call("x^3", {"x": x}), (x * x) * f32(3), BE)
     powf = _libm("powf", None)
     two_x = np.array([powf(2.0, float(v)) for v in x], f32)
-    assert np.array_equal(m.call("2^x", {"x": x}), two_x * f32(math.log(2.0)))
+    assert close_libm(m.call("2^x", {"x": x}), two_x * f32(math.log(2.0)), BE)
     x = np.linspace(1, 8, 8, dtype=f32)
     m = _grad_model({"ln": lambda v, x_, it: o.ln(v), "log10": lambda v, x_, it: o.log10(v),
                      "log2": lambda v, x_, it: o.log2(v), "logx5": lambda v, x_, it: o.log(v, 5.0)})
-    assert np.array_equal(m.call("ln", {"x": x}), f32(1) / x)
-    assert np.array_equal(m.call("log10", {"x": x}), f32(1) / (x * f32(math.log(10.0))))
-    assert np.array_equal(m.call("log2", {"x": x}), f32(1) / (x * f32(math.log(2.0))))
+    assert close_libm(m.call("ln", {"x": x}), f32(1) / x, BE)
+    assert close_libm(m.call("log10", {"x": x}), f32(1) / (x * f32(math.log(10.0))), BE)
+    assert close_libm(m.call("log2", {"x": x}), f32(1) / (x * f32(math.log(2.0))), BE)
     logf = _libm("logf", None)
-    assert np.array_equal(m.call("logx5", {"x": x}), f32(1) / (x * f32(logf(5.0))))
+    assert close_libm(m.call("logx5", {"x": x}), f32(1) / (x * f32(logf(5.0))), BE)
 
 
 def test_talks_linear_and_shared_subgraph():
