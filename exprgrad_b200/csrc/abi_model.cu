@@ -6,20 +6,9 @@
 //   inferShapes           exprgrad/passes.nim:1386-1436 (egb_program_infer_shapes)
 #include <string.h>
 
-#include "abi_common.hpp"
-#include "runtime.hpp"
+#include "abi_model.hpp"
 
 using namespace egb;
-
-
-
-struct egb_program {
-  std::shared_ptr<Program> p;
-};
-struct egb_model {
-  std::unique_ptr<Model> m;
-  egb_context* ctx;
-};
 
 namespace {
 

@@ -1,0 +1,163 @@
+// Data-parallel extension: one process per GPU, full parameter replica per rank, the
+// batch dimension sharded by the caller; the only exchange step of the train target is one all-reduce
+// (average) of the contiguous parameter-gradient bucket, placed between the last adjoint kernel and
+// the first optimizer kernel (the reference has no multi-device path; its gradient kernels reduce over
+// the batch index, exprgrad/passes.nim:519-549, so averaging the per-shard gradients of equal-size
+// shards reproduces the global-batch step, base.nim:66-67 normalising by the local shape[0]).
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2 - the copy torch has already loaded when the host
+// side uses torch.distributed for rendezvous, otherwise the system one), so libegb200.so carries no
+// link-time dependency on it. The communicator runs on the context's stream and is captured into the
+// plan's CUDA graph together with the compute kernels.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "abi_model.hpp"
+
+namespace egb {
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+struct NcclUniqueId {
+  char internal[128];
+};
+typedef int (*PFN_ncclGetUniqueId)(NcclUniqueId*);
+typedef int (*PFN_ncclCommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
+typedef int (*PFN_ncclCommDestroy)(ncclComm_t);
+typedef int (*PFN_ncclAllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef const char* (*PFN_ncclGetErrorString)(int);
+typedef int (*PFN_ncclGetVersion)(int*);
+constexpr int kNcclFloat32 = 7, kNcclSum = 0, kNcclAvg = 4;
+
+struct NcclApi {
+  void* handle = nullptr;
+  PFN_ncclGetUniqueId get_unique_id = nullptr;
+  PFN_ncclCommInitRank comm_init_rank = nullptr;
+  PFN_ncclCommDestroy comm_destroy = nullptr;
+  PFN_ncclAllReduce all_reduce = nullptr;
+  PFN_ncclGetErrorString error_string = nullptr;
+  PFN_ncclGetVersion get_version = nullptr;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.handle) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) fail(EGB_ERR_GPU, "unable to load libnccl.so.2: %s", dlerror());
+  auto sym = [&](const char* name) {
+    void* p = dlsym(api.handle, name);
+    if (!p) fail(EGB_ERR_GPU, "libnccl is missing symbol %s", name);
+    return p;
+  };
+  api.get_unique_id = (PFN_ncclGetUniqueId)sym("ncclGetUniqueId");
+  api.comm_init_rank = (PFN_ncclCommInitRank)sym("ncclCommInitRank");
+  api.comm_destroy = (PFN_ncclCommDestroy)sym("ncclCommDestroy");
+  api.all_reduce = (PFN_ncclAllReduce)sym("ncclAllReduce");
+  api.error_string = (PFN_ncclGetErrorString)sym("ncclGetErrorString");
+  api.get_version = (PFN_ncclGetVersion)sym("ncclGetVersion");
+  return api;
+}
+
+void nccl_check(int rc, const char* what) {
+  if (rc != 0) fail(EGB_ERR_GPU, "%s failed: %s", what, nccl().error_string(rc));
+}
+
+}  // namespace
+
+struct CommHooks {
+  Context* ctx = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  void all_reduce_avg(float* buf, size_t n, cudaStream_t st) {
+    if (world <= 1 || n == 0) return;
+    nccl_check(nccl().all_reduce(buf, buf, n, kNcclFloat32, kNcclAvg, comm, st), "ncclAllReduce");
+  }
+};
+
+void comm_all_reduce_avg(CommHooks* c, float* buf, size_t n, cudaStream_t st) { c->all_reduce_avg(buf, n, st); }
+int comm_world(CommHooks* c) { return c ? c->world : 1; }
+
+}  // namespace egb
+
+using namespace egb;
+
+struct egb_comm {
+  CommHooks h;
+};
+
+extern "C" {
+
+int egb_comm_unique_id(void* out, size_t cap) {
+  EGB_TRY
+  if (cap < 128) fail(EGB_ERR_GPU, "unique id buffer must hold 128 bytes");
+  NcclUniqueId id;
+  nccl_check(nccl().get_unique_id(&id), "ncclGetUniqueId");
+  memcpy(out, &id, 128);
+  EGB_CATCH
+}
+
+int egb_comm_create(egb_context* ctx, const void* unique_id, int rank, int world, egb_comm** out) {
+  EGB_TRY
+  if (world < 1 || rank < 0 || rank >= world) fail(EGB_ERR_GPU, "invalid rank %d of %d", rank, world);
+  EGB_CUDA(cudaSetDevice(ctx->c.device));
+  auto c = new egb_comm();
+  c->h.ctx = &ctx->c;
+  c->h.rank = rank;
+  c->h.world = world;
+  if (world > 1) {
+    NcclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    int rc = nccl().comm_init_rank(&c->h.comm, world, id, rank);
+    if (rc != 0) {
+      delete c;
+      nccl_check(rc, "ncclCommInitRank");
+    }
+  }
+  *out = c;
+  EGB_CATCH
+}
+
+int egb_comm_destroy(egb_comm* comm) {
+  EGB_TRY
+  if (!comm) return EGB_OK;
+  if (comm->h.comm) {
+    cudaStreamSynchronize(comm->h.ctx->stream);
+    nccl().comm_destroy(comm->h.comm);
+  }
+  delete comm;
+  EGB_CATCH
+}
+
+int egb_comm_info(egb_comm* comm, int* rank, int* world, int* nccl_version) {
+  EGB_TRY
+  if (rank) *rank = comm->h.rank;
+  if (world) *world = comm->h.world;
+  if (nccl_version) {
+    *nccl_version = 0;
+    if (comm->h.world > 1) nccl().get_version(nccl_version);
+  }
+  EGB_CATCH
+}
+
+int egb_comm_allreduce_avg_f32(egb_comm* comm, float* device_buf, size_t n) {
+  EGB_TRY
+  comm->h.all_reduce_avg(device_buf, n, comm->h.ctx->stream);
+  EGB_CATCH
+}
+
+}  // extern "C"
+
+extern "C" int egb_model_set_data_parallel(egb_model* model, egb_comm* comm) {
+  EGB_TRY
+  Model& m = *model->m;
+  EGB_CUDA(cudaStreamSynchronize(model->ctx->c.stream));
+  m.plans.clear();  // plans are rebuilt with (or without) the gradient-bucket all-reduce node
+  m.last_plan = nullptr;
+  m.comm = comm ? &comm->h : nullptr;
+  EGB_CATCH
+}

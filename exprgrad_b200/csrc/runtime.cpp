@@ -140,6 +140,14 @@ void build_nodes_impl(Model& m, Plan& plan) {
   for (size_t ki = 0; ki < target.kernels.size(); ++ki) {
     const Kernel& k = *target.kernels[ki];
     const KernelInfo& inf = info[ki];
+    if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes) {
+      Node n;
+      n.kind = Node::ALLREDUCE;
+      n.label = "all-reduce(avg) parameter-gradient bucket";
+      n.ptr = plan.arena + plan.bucket_off;
+      n.bytes = plan.bucket_bytes;
+      plan.nodes.push_back(n);
+    }
     if (inf.is_gemm && !m.strict) {
       const GemmPattern& g = inf.gemm;
       Node n;
@@ -238,17 +246,46 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   for (int id : target->tensors)
     if (prog->tdef(id).kind == TensorKind::Result && !written.count(id)) needs_zero.insert(id);  // read-only results
 
-  // ---- arena: [results that need zeroing][other results, inputs, random][bf16 operand planes]
+  // ---- data parallel: the gradients of the parameters form one contiguous bucket that is
+  // all-reduced right before the first optimizer kernel (the first kernel that writes a param/cache)
+  std::set<int> bucket;
+  if (comm && comm_world(comm) > 1) {
+    auto gt = prog->grad_tensors.find(target_name);
+    if (gt != prog->grad_tensors.end()) {
+      for (int pid : prog->params) {
+        auto g = gt->second.find(pid);
+        if (g != gt->second.end() && written.count(g->second)) bucket.insert(g->second);
+      }
+      for (size_t ki = 0; ki < target->kernels.size() && !bucket.empty(); ++ki) {
+        const TensorKind wk = prog->tdef(target->kernels[ki]->write.tensor).kind;
+        if (wk == TensorKind::Param || wk == TensorKind::Cache) {
+          plan->bucket_before_kernel = (int)ki;
+          break;
+        }
+      }
+      if (plan->bucket_before_kernel < 0) bucket.clear();
+    }
+  }
+
+  // ---- arena: [results that need zeroing .. | bucket (zeroed part first) | other results, inputs,
+  //              random][bf16 operand planes]
   size_t cursor = 0;
   std::vector<int> order;
-  for (int id : target->tensors)
-    if (needs_zero.count(id)) order.push_back(id);
-  const size_t n_zero = order.size();
-  for (int id : target->tensors) {
+  auto in_arena = [&](int id) {
     const TensorKind kind = prog->tdef(id).kind;
-    if (needs_zero.count(id)) continue;
-    if (kind == TensorKind::Result || kind == TensorKind::Input || kind == TensorKind::Random) order.push_back(id);
-  }
+    return kind == TensorKind::Result || kind == TensorKind::Input || kind == TensorKind::Random;
+  };
+  for (int id : target->tensors)
+    if (needs_zero.count(id) && !bucket.count(id)) order.push_back(id);
+  const size_t bucket_first = order.size();
+  for (int id : target->tensors)
+    if (needs_zero.count(id) && bucket.count(id)) order.push_back(id);
+  const size_t n_zero = order.size();
+  for (int id : target->tensors)
+    if (!needs_zero.count(id) && bucket.count(id)) order.push_back(id);
+  const size_t bucket_last = order.size();
+  for (int id : target->tensors)
+    if (!needs_zero.count(id) && !bucket.count(id) && in_arena(id)) order.push_back(id);
   std::map<int, size_t> offs;
   for (size_t i = 0; i < order.size(); ++i) {
     const int id = order[i];
@@ -256,11 +293,14 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
     if (sh == plan->shapes.end()) fail(EGB_ERR_SHAPE, "Missing shape for tensor%d", id - 1);
     for (auto d : sh->second)
       if (d < 0) fail(EGB_ERR_SHAPE, "tensor%d has a negative dimension %s", id - 1, shape_text(sh->second).c_str());
+    if (i == bucket_first) plan->bucket_off = cursor;
     offs[id] = cursor;
     cursor += align_up((size_t)shape_len(sh->second) * 4, 256);
     if (i + 1 == n_zero) plan->zero_bytes = cursor;
+    if (i + 1 == bucket_last) plan->bucket_bytes = cursor - plan->bucket_off;
   }
   if (n_zero == 0) plan->zero_bytes = 0;
+  if (bucket.empty()) plan->bucket_bytes = 0;
   plan->plane_off = cursor;
   plan->plane_bytes = plane_bytes;
   cursor += plane_bytes;
@@ -269,6 +309,7 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   if (e != cudaSuccess)
     fail(EGB_ERR_GPU, "cudaMalloc of %zu bytes for target %s failed: %s", plan->arena_bytes, target_name.c_str(),
          cudaGetErrorString(e));
+  EGB_CUDA(cudaMemsetAsync(plan->arena, 0, plan->arena_bytes, ctx->stream));  // deterministic padding
   for (int id : order) {
     DevTensor t;
     t.ptr = plan->arena + offs[id];
@@ -297,6 +338,10 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       break;
     case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
     case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st); break;
+    case Node::ALLREDUCE:
+      // the 256-byte alignment padding between bucket tensors travels with the payload (zeros)
+      comm_all_reduce_avg(m.comm, (float*)n.ptr, n.bytes / 4, st);
+      break;
     default: fail(EGB_ERR_RUNTIME, "internal: unknown plan node");
   }
 }

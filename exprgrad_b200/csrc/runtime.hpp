@@ -72,6 +72,8 @@ struct Plan {
   size_t zero_bytes = 0;              // leading part of the arena that must be zeroed before every run
   std::vector<KernelInfo> info;       // one per target kernel
   size_t plane_off = 0, plane_bytes = 0;  // bf16 operand-plane region of the arena
+  size_t bucket_off = 0, bucket_bytes = 0;  // contiguous parameter-gradient bucket (data parallel)
+  int bucket_before_kernel = -1;            // the all-reduce runs right before this target kernel
   std::vector<Node> nodes;
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
@@ -82,6 +84,8 @@ struct Plan {
 };
 
 struct CommHooks;  // data-parallel extension (dist.cu)
+void comm_all_reduce_avg(CommHooks* c, float* buf, size_t n, cudaStream_t st);
+int comm_world(CommHooks* c);
 
 struct Model {
   Context* ctx = nullptr;

@@ -49,6 +49,7 @@ typedef struct egb_buffer egb_buffer;
 typedef struct egb_kernel egb_kernel;
 typedef struct egb_program egb_program;
 typedef struct egb_model egb_model;
+typedef struct egb_comm egb_comm;
 
 /* Message of the last failing call on this thread. Never NULL. */
 const char* egb_last_error(void);
@@ -194,6 +195,22 @@ int egb_model_fit(egb_model* model, const char* target, int n_args, const char* 
                   int64_t* batches_run);
 /* Human-readable node list of the most recent call's launch plan. */
 int egb_model_describe_plan(egb_model* model, char* buf, size_t cap, size_t* needed);
+
+/* ---- 4. data parallel (no counterpart in the reference, which is single-device: cl.nim:95-99) ---- */
+
+/* One process per GPU. Rank 0 creates a 128-byte NCCL unique id and the host side distributes it
+ * (torch.distributed / MPI / a file); every rank then creates its communicator on its own context. */
+int egb_comm_unique_id(void* out, size_t cap);
+int egb_comm_create(egb_context* ctx, const void* unique_id, int rank, int world, egb_comm** out);
+int egb_comm_destroy(egb_comm* comm);
+int egb_comm_info(egb_comm* comm, int* rank, int* world, int* nccl_version);
+/* In-place average of n floats across all ranks on the context's stream (asynchronous). */
+int egb_comm_allreduce_avg_f32(egb_comm* comm, float* device_buf, size_t n);
+/* Make every target that has a backward pass data parallel: the gradients of all parameters are laid
+ * out as one contiguous bucket and averaged across ranks (one ncclAllReduce over NVLink) between the
+ * last adjoint kernel and the first optimizer kernel, inside the same CUDA graph. comm = NULL turns
+ * it off again. With equal-size batch shards this reproduces the reference's global-batch step. */
+int egb_model_set_data_parallel(egb_model* model, egb_comm* comm);
 
 #ifdef __cplusplus
 }

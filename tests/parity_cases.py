@@ -63,15 +63,32 @@ def gemm_f32(ctx, a, b, ta=0, tb=0, flags=0, c0=None, bias=None, alpha=1.0):
 
 
 def smoke_case():
-    """One small invocation of the hot path on cuda:0, checked against the oracle."""
+    """One small invocation of the hot path on cuda:0, checked against the oracle: a dense-net train
+    step (forward contractions on tcgen05, adjoints, SGD) through the model C-ABI."""
+    import oracle as o
+    from oracle import layers as OL
     import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, layers as PL
+    import graphs as G
+    sizes = (64, 48, 32, 10)
     ctx = eg.new_gpu_context()
-    rng = np.random.default_rng(0)
-    a = rng.uniform(-1, 1, (123, 100)).astype(np.float32)
-    b = rng.uniform(-1, 1, (100, 77)).astype(np.float32)
-    got = gemm_f32(ctx, a, b)
-    ref = oracle_matmul(a, b)
-    e = assert_close(got, ref, what="smoke matmul 123x100x77")
-    assert ctx.launch_count >= 3
-    print(f"smoke ok: matmul 123x100x77 normalised max err {e:.2e}, {ctx.launch_count} kernel launches")
+    om = o.compile(*G.dense_net(o, OL, sizes), seed=1)
+    pm = eg.compile(*G.dense_net(F, PL, sizes), gpu=ctx, seed=1)
+    x, y, params = G.dense_inputs(96, sizes)
+    for tid, v in zip(sorted(om.params), params):
+        om.params[tid][...] = v
+        pm.params[tid] = v
+    n0 = ctx.launch_count
+    for _ in range(2):
+        om.apply("train", {"x": x, "y": y})
+        pm.apply("train", {"x": x, "y": y})
+    worst = 0.0
+    for tid in sorted(om.params):
+        worst = max(worst, assert_close(pm.params[tid], om.params[tid], what=f"smoke: param tensor{tid - 1}"))
+    e = assert_close(pm.call("loss", {"x": x, "y": y}), om.call("loss", {"x": x, "y": y}), what="smoke: loss")
+    launches = ctx.launch_count - n0
+    assert launches >= 20, launches
+    print(f"smoke ok: dense {sizes} train step x2 vs oracle: params err {worst:.2e}, loss err {e:.2e}, "
+          f"{launches} kernel launches")
+    pm.free()
     ctx.destroy()
