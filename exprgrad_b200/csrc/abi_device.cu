@@ -341,7 +341,9 @@ int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const voi
   g.a_hi = (const __nv_bfloat16*)a_hi; g.a_mid = (const __nv_bfloat16*)a_mid; g.lda = (int)lda;
   g.b_hi = (const __nv_bfloat16*)b_hi; g.b_mid = (const __nv_bfloat16*)b_mid; g.ldb = (int)ldb;
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
-  g.C = C; g.ldc = (int)ldc; g.flags = flags; g.bias = bias; g.alpha = alpha; g.bn = bn;
+  g.a_mn = (flags & 16) != 0;
+  g.b_mn = (flags & 32) != 0;
+  g.C = C; g.ldc = (int)ldc; g.flags = flags & 7; g.bias = bias; g.alpha = alpha; g.bn = bn;
   launch_gemm_bf16x3(ctx->c, g, ctx->c.stream);
   EGB_CATCH
 }
@@ -353,23 +355,27 @@ int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t 
   if (M <= 0 || N <= 0) return EGB_OK;
   if (K <= 0) fail(EGB_ERR_GPU, "gemm: K must be positive");
   Context& c = ctx->c;
-  const int64_t kp = (K + 7) & ~int64_t(7);
-  const size_t a_plane = (size_t)M * kp * 2, b_plane = (size_t)N * kp * 2;
+  // bf16 planes of both operands. The tensor-core descriptors take either orientation (K-major or
+  // MN-major), so small operands are split exactly as stored; large MN-major ones get a transposed copy.
+  const bool a_copy = trans_a && prefer_transposed_copy(K, M);
+  const bool b_copy = !trans_b && prefer_transposed_copy(K, N);
+  const int64_t a_rows = trans_a ? K : M, a_cols = trans_a ? M : K;    // as stored
+  const int64_t b_rows = trans_b ? N : K, b_cols = trans_b ? K : N;
+  const int64_t a_prow = a_copy ? a_cols : a_rows, a_pcol = a_copy ? a_rows : a_cols;  // plane shape
+  const int64_t b_prow = b_copy ? b_cols : b_rows, b_pcol = b_copy ? b_rows : b_cols;
+  const int64_t a_ld = (a_pcol + 7) & ~int64_t(7), b_ld = (b_pcol + 7) & ~int64_t(7);
+  const size_t a_plane = (size_t)a_prow * a_ld * 2, b_plane = (size_t)b_prow * b_ld * 2;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   char* ws = (char*)c.ensure_scratch(2 * al(a_plane) + 2 * al(b_plane));
   __nv_bfloat16* a_hi = (__nv_bfloat16*)ws;
   __nv_bfloat16* a_mid = (__nv_bfloat16*)(ws + al(a_plane));
   __nv_bfloat16* b_hi = (__nv_bfloat16*)(ws + 2 * al(a_plane));
   __nv_bfloat16* b_mid = (__nv_bfloat16*)(ws + 2 * al(a_plane) + al(b_plane));
-  // A operand must be [M, K] K-contiguous; stored [K, M] when trans_a
-  if (trans_a) launch_split_bf16(c, A, (int)K, (int)M, (int)lda, true, a_hi, a_mid, (int)kp, 0, c.stream);
-  else launch_split_bf16(c, A, (int)M, (int)K, (int)lda, false, a_hi, a_mid, (int)kp, 0, c.stream);
-  // B operand must be [N, K] K-contiguous; stored [K, N] unless trans_b
-  if (trans_b) launch_split_bf16(c, B, (int)N, (int)K, (int)ldb, false, b_hi, b_mid, (int)kp, 0, c.stream);
-  else launch_split_bf16(c, B, (int)K, (int)N, (int)ldb, true, b_hi, b_mid, (int)kp, 0, c.stream);
+  launch_split_bf16(c, A, (int)a_rows, (int)a_cols, (int)lda, a_copy, a_hi, a_mid, (int)a_ld, 0, c.stream);
+  launch_split_bf16(c, B, (int)b_rows, (int)b_cols, (int)ldb, b_copy, b_hi, b_mid, (int)b_ld, 0, c.stream);
   GemmArgs g;
-  g.a_hi = a_hi; g.a_mid = a_mid; g.lda = (int)kp;
-  g.b_hi = b_hi; g.b_mid = b_mid; g.ldb = (int)kp;
+  g.a_hi = a_hi; g.a_mid = a_mid; g.lda = (int)a_ld; g.a_mn = trans_a != 0 && !a_copy;  // stored [K, M]
+  g.b_hi = b_hi; g.b_mid = b_mid; g.ldb = (int)b_ld; g.b_mn = trans_b == 0 && !b_copy;  // stored [K, N]
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.C = C; g.ldc = (int)ldc; g.flags = flags & 7; g.bias = bias; g.alpha = alpha;
   launch_gemm_bf16x3(c, g, c.stream);

@@ -101,10 +101,14 @@ enum GemmFlags {
 };
 
 struct GemmArgs {
-  // operands, both K-major bf16 planes: A is [M, lda] and B is [N, ldb], K contiguous
+  // operands as bf16 (hi, mid) planes. K-major (default): A is stored [M, lda], B is stored [N, ldb]
+  // with K contiguous. MN-major (a_mn / b_mn): A is stored [K, lda] with M contiguous, B is stored
+  // [K, ldb] with N contiguous - i.e. the row-major planes of a [K, M] / [K, N] matrix are used as
+  // they are, no transposed copy is needed (UMMA descriptor major bits 15/16).
   const __nv_bfloat16 *a_hi = nullptr, *a_mid = nullptr;
   const __nv_bfloat16 *b_hi = nullptr, *b_mid = nullptr;
   int lda = 0, ldb = 0;
+  bool a_mn = false, b_mn = false;
   int M = 0, N = 0, K = 0;
   float* C = nullptr;  // [M, ldc] fp32 output
   int ldc = 0;
@@ -119,5 +123,11 @@ struct GemmArgs {
 };
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
+
+// Large operands whose stored orientation is MN-major are better served by one transposing split
+// pass plus the K-major tensor-core path (measured on 4096^3: 0.330 ms vs 0.353 ms per GEMM).
+inline bool prefer_transposed_copy(int64_t k_extent, int64_t mn_extent) {
+  return k_extent * mn_extent >= (int64_t)1 << 22;
+}
 
 }  // namespace egb

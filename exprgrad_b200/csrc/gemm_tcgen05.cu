@@ -31,6 +31,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;                      // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int MN_GROUP_BYTES = BK * 128;    // MN-major: one group of 64 MN-elements x BK rows
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 constexpr int NUM_THREADS = 256;
@@ -49,6 +50,7 @@ struct KParams {
   int tiles_m, tiles_n;
   int flags;
   float alpha;
+  int a_mn, b_mn;  // operand is MN-major (stored [K, MN] row-major)
 };
 
 __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* mid, float v) {
@@ -117,16 +119,32 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           uint8_t* st = smem + s * stage_bytes;
           ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           const int k0 = kb * BK;
-          ptx::tma_load_2d(st, &tm_a_hi, &full_bar[s], k0, m0);
-          ptx::tma_load_2d(st + A_PLANE_BYTES, &tm_a_mid, &full_bar[s], k0, m0);
-          ptx::tma_load_2d(st + 2 * A_PLANE_BYTES, &tm_b_hi, &full_bar[s], k0, n0);
-          ptx::tma_load_2d(st + 2 * A_PLANE_BYTES + b_plane_bytes, &tm_b_mid, &full_bar[s], k0, n0);
+          if (!p.a_mn) {
+            ptx::tma_load_2d(st, &tm_a_hi, &full_bar[s], k0, m0);
+            ptx::tma_load_2d(st + A_PLANE_BYTES, &tm_a_mid, &full_bar[s], k0, m0);
+          } else {
+            // MN-major: one {64 (M), BK (K rows)} box per group of 64 M-elements
+            for (int g = 0; g < BM / 64; ++g) {
+              ptx::tma_load_2d(st + g * MN_GROUP_BYTES, &tm_a_hi, &full_bar[s], m0 + g * 64, k0);
+              ptx::tma_load_2d(st + A_PLANE_BYTES + g * MN_GROUP_BYTES, &tm_a_mid, &full_bar[s], m0 + g * 64, k0);
+            }
+          }
+          uint8_t* sb = st + 2 * A_PLANE_BYTES;
+          if (!p.b_mn) {
+            ptx::tma_load_2d(sb, &tm_b_hi, &full_bar[s], k0, n0);
+            ptx::tma_load_2d(sb + b_plane_bytes, &tm_b_mid, &full_bar[s], k0, n0);
+          } else {
+            for (int g = 0; g < p.BN / 64; ++g) {
+              ptx::tma_load_2d(sb + g * MN_GROUP_BYTES, &tm_b_hi, &full_bar[s], n0 + g * 64, k0);
+              ptx::tma_load_2d(sb + b_plane_bytes + g * MN_GROUP_BYTES, &tm_b_mid, &full_bar[s], n0 + g * 64, k0);
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN);
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN, p.a_mn != 0, p.b_mn != 0);
     uint32_t it = 0;
     uint32_t local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
@@ -142,18 +160,24 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t st = ptx::smem_u32(smem + s * stage_bytes);
-          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(st);
-          const uint64_t a_mid = ptx::make_kmajor_sw128_desc(st + A_PLANE_BYTES);
-          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(st + 2 * A_PLANE_BYTES);
-          const uint64_t b_mid = ptx::make_kmajor_sw128_desc(st + 2 * A_PLANE_BYTES + b_plane_bytes);
+          const uint32_t sb = st + 2 * A_PLANE_BYTES;
+          const uint64_t a_hi = p.a_mn ? ptx::make_mnmajor_sw128_desc(st, MN_GROUP_BYTES) : ptx::make_kmajor_sw128_desc(st);
+          const uint64_t a_mid = p.a_mn ? ptx::make_mnmajor_sw128_desc(st + A_PLANE_BYTES, MN_GROUP_BYTES)
+                                        : ptx::make_kmajor_sw128_desc(st + A_PLANE_BYTES);
+          const uint64_t b_hi = p.b_mn ? ptx::make_mnmajor_sw128_desc(sb, MN_GROUP_BYTES) : ptx::make_kmajor_sw128_desc(sb);
+          const uint64_t b_mid = p.b_mn ? ptx::make_mnmajor_sw128_desc(sb + b_plane_bytes, MN_GROUP_BYTES)
+                                        : ptx::make_kmajor_sw128_desc(sb + b_plane_bytes);
+          // advancing by UMMA_K = 16 along K: K-major: 32 bytes inside the 128-byte swizzle row;
+          // MN-major: 16 rows of 128 bytes (address field is in 16-byte units)
+          const uint64_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+          const uint64_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advancing 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the >>4 address field
-            const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
+            const uint64_t aa = a_step * k, ba = b_step * k;
             // small cross terms first, dominant hi*hi last
-            ptx::umma_f16<1>(d_tmem, a_mid + adv, b_hi + adv, idesc, (kb | k) != 0);
-            ptx::umma_f16<1>(d_tmem, a_hi + adv, b_mid + adv, idesc, 1);
-            ptx::umma_f16<1>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            ptx::umma_f16<1>(d_tmem, a_mid + aa, b_hi + ba, idesc, (kb | k) != 0);
+            ptx::umma_f16<1>(d_tmem, a_hi + aa, b_mid + ba, idesc, 1);
+            ptx::umma_f16<1>(d_tmem, a_hi + aa, b_hi + ba, idesc, 1);
           }
           ptx::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
           if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
@@ -252,13 +276,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   }
 }
 
-void encode_plane(Context& ctx, CUtensorMap* tm, const __nv_bfloat16* base, int rows, int K, int ld,
-                  int box_rows) {
+// K-major: the plane is [rows = MN extent, K] -> box {BK, box_rows}. MN-major: the plane is
+// [K, cols = MN extent] -> box {64, BK}.
+void encode_plane(Context& ctx, CUtensorMap* tm, const __nv_bfloat16* base, int mn, int K, int ld, int box_rows,
+                  bool mn_major) {
   if ((ld & 7) != 0) fail(EGB_ERR_GPU, "bf16 plane leading dimension %d is not a multiple of 8", ld);
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) fail(EGB_ERR_GPU, "bf16 plane is not 16-byte aligned");
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)mn};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  if (mn_major) {
+    dims[0] = (cuuint64_t)mn;
+    dims[1] = (cuuint64_t)K;
+    box[0] = 64;
+    box[1] = BK;
+  }
   cuuint32_t estr[2] = {1, 1};
   CUresult r = ctx.encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -266,12 +298,13 @@ void encode_plane(Context& ctx, CUtensorMap* tm, const __nv_bfloat16* base, int 
   if (r != CUDA_SUCCESS) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
 }
 
-int choose_bn(int M, int N, int sm_count) {
+int choose_bn(int M, int N, int sm_count, bool b_mn) {
   // Smallest tile count that still fills the machine wins; prefer wide tiles (more operand reuse).
   const int tiles_m = (M + BM - 1) / BM;
-  int best = 32;
+  const int step = b_mn ? 64 : 32;  // an MN-major B tile is made of 64-column groups
+  int best = step;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 32) {
+  for (int bn = 256; bn >= step; bn -= step) {
     const int tiles_n = (N + bn - 1) / bn;
     const long tiles = (long)tiles_m * tiles_n;
     const long waves = (tiles + sm_count - 1) / sm_count;
@@ -296,8 +329,11 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   p.ldc = a.ldc; p.ld_out = a.ld_out;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.flags = a.flags; p.alpha = a.alpha;
-  p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, ctx.sm_count);
+  p.a_mn = a.a_mn ? 1 : 0;
+  p.b_mn = a.b_mn ? 1 : 0;
+  p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, ctx.sm_count, a.b_mn);
   if (p.BN % 32 != 0 || p.BN < 32 || p.BN > 256) fail(EGB_ERR_GPU, "gemm: invalid BN %d", p.BN);
+  if (a.b_mn && p.BN % 64 != 0) fail(EGB_ERR_GPU, "gemm: BN must be a multiple of 64 for an MN-major B operand");
   p.tiles_m = (a.M + BM - 1) / BM;
   p.tiles_n = (a.N + p.BN - 1) / p.BN;
   const int stage_bytes = 2 * A_PLANE_BYTES + 2 * p.BN * BK * 2;
@@ -309,10 +345,10 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)stages * stage_bytes + bar_bytes;
 
   CUtensorMap tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid;
-  encode_plane(ctx, &tm_a_hi, a.a_hi, a.M, a.K, a.lda, BM);
-  encode_plane(ctx, &tm_a_mid, a.a_mid, a.M, a.K, a.lda, BM);
-  encode_plane(ctx, &tm_b_hi, a.b_hi, a.N, a.K, a.ldb, p.BN);
-  encode_plane(ctx, &tm_b_mid, a.b_mid, a.N, a.K, a.ldb, p.BN);
+  encode_plane(ctx, &tm_a_hi, a.a_hi, a.M, a.K, a.lda, BM, a.a_mn);
+  encode_plane(ctx, &tm_a_mid, a.a_mid, a.M, a.K, a.lda, BM, a.a_mn);
+  encode_plane(ctx, &tm_b_hi, a.b_hi, a.N, a.K, a.ldb, p.BN, a.b_mn);
+  encode_plane(ctx, &tm_b_mid, a.b_mid, a.N, a.K, a.ldb, p.BN, a.b_mn);
 
   static bool attr_set = false;
   if (!attr_set) {

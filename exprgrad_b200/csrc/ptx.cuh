@@ -230,14 +230,32 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major operand tile (CUTLASS canonical layout
+// "Major-MN, B128": ((T,8,m),(8,k)) : ((1,T,LBO),(8T,SBO)), T = 8 bf16): the tile is stored as K rows
+// of 64 MN-elements (128 bytes, 128B-swizzled in 8-row atoms = what TMA writes for a {64, rows} box
+// of a row-major [K, MN] matrix); groups of 64 MN-elements are `mn_group_bytes` apart (LBO), groups
+// of 8 K-rows are 1024 bytes apart (SBO).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t mn_group_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((mn_group_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 //   [4,6) c_format = 1 (F32); [7,10) a_format = 1 (BF16); [10,13) b_format = 1 (BF16)
 //   [15] a_major = 0 (K); [16] b_major = 0 (K); [17,23) N>>3; [24,29) M>>4
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16_f32(int M, int N) {
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16_f32(int M, int N, bool a_mn = false,
+                                                                 bool b_mn = false) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= 1u << 7;
   d |= 1u << 10;
+  if (a_mn) d |= 1u << 15;
+  if (b_mn) d |= 1u << 16;
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(M >> 4) << 24;
   return d;

@@ -107,28 +107,29 @@ void build_nodes_impl(Model& m, Plan& plan) {
   size_t plane_cursor = 0;
   char* plane_base = plan.arena + plan.plane_off;
   const size_t plane_cap = plan.plane_bytes;
-  auto get_planes = [&](int tensor, bool k_major_needs_transpose, int64_t rows, int64_t cols, int64_t ld,
-                        int64_t& out_ld) {
-    // rows x cols is the stored fp32 matrix; the planes are [rows, cols] or (transposed) [cols, rows]
-    const int64_t kdim = k_major_needs_transpose ? rows : cols;
-    const int64_t outer = k_major_needs_transpose ? cols : rows;
-    out_ld = (kdim + 7) & ~int64_t(7);
-    auto key = std::make_pair(tensor, k_major_needs_transpose ? 1 : 0);
+  // Planes of a stored [rows, cols] fp32 matrix: row-major as stored (the GEMM descriptors take either
+  // operand orientation, so one pair serves every contraction), or - only for large operands whose
+  // natural orientation is MN-major, where the K-major tensor-core path is ~7% faster and the extra
+  // streaming pass is cheap by comparison - an explicitly transposed copy.
+  auto get_planes = [&](int tensor, bool transposed, int64_t rows, int64_t cols, int64_t ld, int64_t& out_ld) {
+    const int64_t prow = transposed ? cols : rows, pcol = transposed ? rows : cols;
+    out_ld = (pcol + 7) & ~int64_t(7);
+    auto key = std::make_pair(tensor, transposed ? 1 : 0);
     auto it = planes.find(key);
     if (it != planes.end()) return it->second;
-    const size_t bytes = align_up((size_t)outer * out_ld * 2, 256);
+    const size_t bytes = align_up((size_t)prow * out_ld * 2, 256);
     if (plane_cursor + 2 * bytes > plane_cap) fail(EGB_ERR_RUNTIME, "internal: operand plane arena exhausted");
     auto* hi = (__nv_bfloat16*)(plane_base + plane_cursor);
     auto* mid = (__nv_bfloat16*)(plane_base + plane_cursor + bytes);
     plane_cursor += 2 * bytes;
     Node n;
     n.kind = Node::SPLIT;
-    n.label = "split tensor" + std::to_string(tensor - 1) + (k_major_needs_transpose ? " (transposed)" : "");
+    n.label = "split tensor" + std::to_string(tensor - 1) + (transposed ? " (transposed)" : "");
     n.split_src = (const float*)ptrs[tensor];
     n.split_rows = (int)rows;
     n.split_cols = (int)cols;
     n.split_ld = (int)ld;
-    n.split_transpose = k_major_needs_transpose;
+    n.split_transpose = transposed;
     n.split_hi = hi;
     n.split_mid = mid;
     n.split_dst_ld = (int)out_ld;
@@ -155,14 +156,15 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.label = "gemm tensor" + std::to_string(g.c_tensor - 1);
       n.kernel_index = (int)ki;
       int64_t lda = 0, ldb = 0;
-      // A operand must be [M, K] with K contiguous: stored [M,K] (no transpose) or [K,M] (transpose)
-      auto pa = g.trans_a ? get_planes(g.a_tensor, true, g.K, g.M, g.lda, lda)
+      // A stored [M,K] is K-major, stored [K,M] is MN-major; B stored [N,K] is K-major, [K,N] MN-major
+      const bool a_copy = g.trans_a && prefer_transposed_copy(g.K, g.M);
+      const bool b_copy = !g.trans_b && prefer_transposed_copy(g.K, g.N);
+      auto pa = g.trans_a ? get_planes(g.a_tensor, a_copy, g.K, g.M, g.lda, lda)
                           : get_planes(g.a_tensor, false, g.M, g.K, g.lda, lda);
-      // B operand must be [N, K] with K contiguous: stored [N,K] (no transpose) or [K,N] (transpose)
       auto pb = g.trans_b ? get_planes(g.b_tensor, false, g.N, g.K, g.ldb, ldb)
-                          : get_planes(g.b_tensor, true, g.K, g.N, g.ldb, ldb);
-      n.gemm.a_hi = pa.first; n.gemm.a_mid = pa.second; n.gemm.lda = (int)lda;
-      n.gemm.b_hi = pb.first; n.gemm.b_mid = pb.second; n.gemm.ldb = (int)ldb;
+                          : get_planes(g.b_tensor, b_copy, g.K, g.N, g.ldb, ldb);
+      n.gemm.a_hi = pa.first; n.gemm.a_mid = pa.second; n.gemm.lda = (int)lda; n.gemm.a_mn = g.trans_a && !a_copy;
+      n.gemm.b_hi = pb.first; n.gemm.b_mid = pb.second; n.gemm.ldb = (int)ldb; n.gemm.b_mn = !g.trans_b && !b_copy;
       n.gemm.M = (int)g.M; n.gemm.N = (int)g.N; n.gemm.K = (int)g.K;
       n.gemm.C = (float*)ptrs[g.c_tensor];
       n.gemm.ldc = (int)g.ldc;
@@ -239,8 +241,11 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
     written.insert(wt);
     if (inf.is_gemm) {
       const GemmPattern& g = inf.gemm;
-      const size_t kp = (size_t)((g.K + 7) & ~int64_t(7));
-      plane_bytes += 2 * align_up((size_t)g.M * kp * 2, 256) + 2 * align_up((size_t)g.N * kp * 2, 256);
+      auto pad8 = [](int64_t v) { return (size_t)((v + 7) & ~int64_t(7)); };
+      // upper bound over both possible orientations of each operand
+      const size_t a_bytes = std::max((size_t)g.K * pad8(g.M), (size_t)g.M * pad8(g.K)) * 2;
+      const size_t b_bytes = std::max((size_t)g.N * pad8(g.K), (size_t)g.K * pad8(g.N)) * 2;
+      plane_bytes += 2 * align_up(a_bytes, 256) + 2 * align_up(b_bytes, 256);
     }
   }
   for (int id : target->tensors)

@@ -123,8 +123,10 @@ int egb_buffer_read_into(egb_buffer* buf, void* data, size_t bytes);
 int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, const float* A,
                  int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int flags,
                  const float* bias, float alpha);
-/* Same contraction on operands already split into bf16 (hi, mid) K-major planes. bn = 0 lets the
- * library choose the N tile. Used by the benchmark to time the tensor-core kernel alone. */
+/* Same contraction on operands already split into bf16 (hi, mid) planes. By default both are K-major
+ * (A stored [M, lda], B stored [N, ldb], K contiguous); flags bit 16: A is MN-major (stored [K, lda], M
+ * contiguous), bit 32: B is MN-major (stored [K, ldb], N contiguous). bn = 0 lets the library choose the
+ * N tile. */
 int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_mid,
                     int64_t lda, const void* b_hi, const void* b_mid, int64_t ldb, float* C, int64_t ldc,
                     int flags, const float* bias, float alpha, int bn);
