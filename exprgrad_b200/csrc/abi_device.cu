@@ -343,7 +343,8 @@ int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const voi
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.a_mn = (flags & 16) != 0;
   g.b_mn = (flags & 32) != 0;
-  g.C = C; g.ldc = (int)ldc; g.flags = flags & 7; g.bias = bias; g.alpha = alpha; g.bn = bn;
+  g.C = C; g.ldc = (int)ldc; g.flags = flags & 3; g.bias = bias; g.alpha = alpha; g.bn = bn;
+  if (flags & 4) { g.epi = EPI_RELU; g.D = C; }
   launch_gemm_bf16x3(ctx->c, g, ctx->c.stream);
   EGB_CATCH
 }
@@ -377,7 +378,8 @@ int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t 
   g.a_hi = a_hi; g.a_mid = a_mid; g.lda = (int)a_ld; g.a_mn = trans_a != 0 && !a_copy;  // stored [K, M]
   g.b_hi = b_hi; g.b_mid = b_mid; g.ldb = (int)b_ld; g.b_mn = trans_b == 0 && !b_copy;  // stored [K, N]
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
-  g.C = C; g.ldc = (int)ldc; g.flags = flags & 7; g.bias = bias; g.alpha = alpha;
+  g.C = C; g.ldc = (int)ldc; g.flags = flags & 3; g.bias = bias; g.alpha = alpha;
+  if (flags & 4) { g.epi = EPI_RELU; g.D = C; }
   launch_gemm_bf16x3(c, g, c.stream);
   EGB_CATCH
 }

@@ -76,6 +76,21 @@ int egb_program_serialize(egb_program* p, char* buf, size_t cap, size_t* needed)
   EGB_CATCH
 }
 
+int egb_program_describe(egb_program* p, const char* target, char* buf, size_t cap, size_t* needed) {
+  EGB_TRY
+  Target* t = p->p->find_target(target);
+  if (!t) fail(EGB_ERR_RUNTIME, "%s is not a target of the model", target);
+  std::string s;
+  for (size_t i = 0; i < t->kernels.size(); ++i) {
+    const Kernel& k = *t->kernels[i];
+    s += std::to_string(i) + ": T" + std::to_string(k.write.tensor) + " <-";
+    for (auto& r : k.reads) s += " T" + std::to_string(r.tensor);
+    s += " | " + describe_kernel(k) + "\n";
+  }
+  copy_out(s, buf, cap, needed);
+  EGB_CATCH
+}
+
 int egb_program_free(egb_program* p) {
   EGB_TRY
   delete p;
@@ -167,6 +182,13 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
     m->m->strict = value != 0;
   } else if (k == "graphs") {
     m->m->use_graphs = value != 0;
+  } else if (k == "fuse") {
+    if (m->m->fuse != (value != 0)) {
+      EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
+      m->m->plans.clear();
+      m->m->last_plan = nullptr;
+    }
+    m->m->fuse = value != 0;
   } else if (k == "epoch") {
     m->m->epoch = value;
   } else {

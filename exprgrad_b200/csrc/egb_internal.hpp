@@ -96,8 +96,18 @@ void launch_fill_u32(Context& ctx, uint32_t* dst, uint32_t value, size_t n, cuda
 enum GemmFlags {
   GEMM_ACCUMULATE = 1,  // C += alpha*acc  (reference `++=` on a tensor that already holds data)
   GEMM_BIAS = 2,        // + bias[col]     (row-broadcast add, reference dnn.nim:22-24)
-  GEMM_RELU = 4,        // out = select(0 <= v, v, 0) (reference dnn.nim:26-27); pre-activation goes to C_pre
-  GEMM_SPLIT_OUT = 8,   // additionally emit bf16 hi/mid planes of the (activated) output
+  GEMM_RELU = 4,        // (raw entry point only) shorthand for epi = EPI_RELU with D = C
+  GEMM_SPLIT_OUT = 8,   // additionally emit bf16 hi/mid planes of the final value
+};
+
+// Second epilogue stage: one reference kernel fused behind the contraction. v = value stored to C.
+enum EpiMode {
+  EPI_NONE = 0,
+  EPI_RELU = 1,        // D = select(0 <= v, v, 0)                      (dnn.nim:26-27)
+  EPI_LEAKY = 2,       // D = select(0 <= v, 1, leak) * v               (dnn.nim:29-30)
+  EPI_MASK_RELU = 3,   // D = select(0 <= H, v, 0)                      (adjoint of relu, passes.nim:471-476)
+  EPI_MASK_LEAKY = 4,  // D = v * select(0 <= H, 1, leak)               (adjoint of leakyRelu)
+  EPI_SGD = 5,         // D += (0 - v) * rate                           (base.nim:37-38)
 };
 
 struct GemmArgs {
@@ -112,8 +122,12 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0;
   float* C = nullptr;  // [M, ldc] fp32 output
   int ldc = 0;
-  float* C_pre = nullptr;  // optional pre-activation output (same layout as C) when GEMM_RELU
   const float* bias = nullptr;
+  int epi = EPI_NONE;
+  float epi_param = 0.0f;       // leak or rate
+  float* D = nullptr;           // second-stage output (same layout as C)
+  const float* H = nullptr;     // mask source (same layout as C)
+  float* colsum = nullptr;      // [N] column sums of the final value, accumulated atomically
   float alpha = 1.0f;
   int flags = 0;
   __nv_bfloat16 *out_hi = nullptr, *out_mid = nullptr;  // GEMM_SPLIT_OUT: [M, ld_out] planes

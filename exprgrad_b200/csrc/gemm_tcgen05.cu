@@ -40,11 +40,15 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct KParams {
   float* C;
-  float* C_pre;
   const float* bias;
+  float* D;            // second output: activation / masked gradient / updated parameter (same layout as C)
+  const float* H;      // EPI_MASK_*: pre-activation the mask is computed from (same layout as C)
+  float* colsum;       // += column sums of the final value (atomic)
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_mid;
   int ldc, ld_out;
+  int epi;             // EpiMode
+  float epi_param;     // leak (leaky relu) or rate (SGD)
   int M, N, K;
   int BN, stages;
   int tiles_m, tiles_n;
@@ -187,9 +191,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue
+    // Thread t of warp q owns accumulator row (q*32 + t); it walks the tile 32 columns at a time:
+    //   v = acc [+ bias[c]] [+ C_old]          -> C   (the contraction's own output tensor)
+    //   w = second stage (activation / gradient mask / SGD update) of v   -> D
+    //   [bf16 hi/mid planes of w]  [column sums of w -> colsum]
+    // Every stage restates one reference kernel that would otherwise run as a separate launch
+    // (bias: dnn.nim:22-24, relu/leakyRelu: dnn.nim:26-30 and their derive()d adjoints,
+    // gradientDescent: base.nim:37-38); arithmetic is kept un-contracted (__fmul_rn/__fadd_rn).
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t local_tile = 0;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.H) & 15) == 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const uint32_t acc = local_tile & 1;
       const uint32_t use = local_tile >> 1;
@@ -204,62 +216,133 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
         ptx::tmem_ld_wait();
         const int col0 = n0 + c;
-        if (row < p.M && col0 < p.N) {
-          float* crow = p.C + (size_t)row * p.ldc + col0;
-          const int ncols = min(32, p.N - col0);
-          float v[32];
+        if (col0 >= p.N) break;  // warp-uniform
+        const int ncols = min(32, p.N - col0);
+        const bool row_ok = row < p.M;
+        const bool full = vec_ok && ncols == 32;
+        const size_t off = (size_t)row * p.ldc + col0;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          if (p.flags & GEMM_BIAS) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.flags & GEMM_BIAS) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
-          }
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.bias + col0 + j));
+        }
+        if (row_ok) {
           if (p.flags & GEMM_ACCUMULATE) {
-            if (vec_ok && ncols == 32) {
+            if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                float4 o = *reinterpret_cast<const float4*>(crow + j);
+                const float4 o = *reinterpret_cast<const float4*>(p.C + off + j);
                 v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] += crow[j];
+                if (j < ncols) v[j] += p.C[off + j];
             }
           }
-          if (p.flags & GEMM_RELU) {
-            if (p.C_pre) {
-              float* prow = p.C_pre + (size_t)row * p.ldc + col0;
-              if (vec_ok && ncols == 32) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(prow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncols) prow[j] = v[j];
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (0.0f <= v[j]) ? v[j] : 0.0f;
-          }
-          if (vec_ok && ncols == 32) {
+          if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              *reinterpret_cast<float4*>(p.C + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < ncols) crow[j] = v[j];
+              if (j < ncols) p.C[off + j] = v[j];
+          }
+          // ---- second stage
+          if (p.epi == EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (0.0f <= v[j]) ? v[j] : 0.0f;
+          } else if (p.epi == EPI_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fmul_rn((0.0f <= v[j]) ? 1.0f : p.epi_param, v[j]);
+          } else if (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY) {
+            float h[32];
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(p.H + off + j);
+                h[j] = o.x; h[j + 1] = o.y; h[j + 2] = o.z; h[j + 3] = o.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) h[j] = (j < ncols) ? p.H[off + j] : 0.0f;
+            }
+            if (p.epi == EPI_MASK_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (0.0f <= h[j]) ? v[j] : 0.0f;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], (0.0f <= h[j]) ? 1.0f : p.epi_param);
+            }
+          } else if (p.epi == EPI_SGD) {
+            // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(p.D + off + j);
+                v[j] = __fadd_rn(o.x, __fmul_rn(0.0f - v[j], p.epi_param));
+                v[j + 1] = __fadd_rn(o.y, __fmul_rn(0.0f - v[j + 1], p.epi_param));
+                v[j + 2] = __fadd_rn(o.z, __fmul_rn(0.0f - v[j + 2], p.epi_param));
+                v[j + 3] = __fadd_rn(o.w, __fmul_rn(0.0f - v[j + 3], p.epi_param));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] = __fadd_rn(p.D[off + j], __fmul_rn(0.0f - v[j], p.epi_param));
+            }
+          }
+          if (p.epi != EPI_NONE) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(p.D + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) p.D[off + j] = v[j];
+            }
           }
           if (p.flags & GEMM_SPLIT_OUT) {
             __nv_bfloat16* hrow = p.out_hi + (size_t)row * p.ld_out + col0;
             __nv_bfloat16* mrow = p.out_mid + (size_t)row * p.ld_out + col0;
+            if (ncols == 32 && (p.ld_out & 7) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) split_store(hrow + j, mrow + j, v[j]);
+              for (int j = 0; j < 32; j += 8) {
+                __align__(16) __nv_bfloat16 hv[8];
+                __align__(16) __nv_bfloat16 mv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_store(&hv[e], &mv[e], v[j + e]);
+                *reinterpret_cast<uint4*>(hrow + j) = *reinterpret_cast<const uint4*>(hv);
+                *reinterpret_cast<uint4*>(mrow + j) = *reinterpret_cast<const uint4*>(mv);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) split_store(hrow + j, mrow + j, v[j]);
+            }
           }
+        }
+        if (p.colsum) {
+          // column sums over the 32 rows this warp holds: butterfly transpose-reduce (31 shuffles);
+          // afterwards lane j holds the sum of column j. Rows outside the matrix contribute zero.
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (!row_ok || j >= ncols) v[j] = 0.0f;
+#pragma unroll
+          for (int offw = 16; offw >= 1; offw >>= 1) {
+            const bool upper = (lane & offw) != 0;
+#pragma unroll
+            for (int j = 0; j < offw; ++j) {
+              const float send = upper ? v[j] : v[j + offw];
+              const float keep = upper ? v[j + offw] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, offw);
+            }
+          }
+          if (lane < ncols) atomicAdd(p.colsum + col0 + lane, v[0]);
         }
       }
       ptx::tc_fence_before();
@@ -325,7 +408,14 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   if (a.K <= 0) fail(EGB_ERR_GPU, "gemm: K must be positive");
   if (!ctx.encode_tiled) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled entry point not available");
   KParams p;
-  p.C = a.C; p.C_pre = a.C_pre; p.bias = a.bias; p.out_hi = a.out_hi; p.out_mid = a.out_mid;
+  p.C = a.C; p.bias = a.bias; p.out_hi = a.out_hi; p.out_mid = a.out_mid;
+  p.D = a.D; p.H = a.H; p.colsum = a.colsum;
+  p.epi = a.epi; p.epi_param = a.epi_param;
+  if (a.flags & GEMM_RELU) {  // legacy flag of the raw entry point: relu written in place of C
+    fail(EGB_ERR_GPU, "gemm: use epi = EPI_RELU with a second output instead of GEMM_RELU");
+  }
+  if (a.epi != EPI_NONE && !a.D) fail(EGB_ERR_GPU, "gemm: fused second stage needs an output tensor");
+  if ((a.epi == EPI_MASK_RELU || a.epi == EPI_MASK_LEAKY) && !a.H) fail(EGB_ERR_GPU, "gemm: mask stage needs H");
   p.ldc = a.ldc; p.ld_out = a.ld_out;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.flags = a.flags; p.alpha = a.alpha;

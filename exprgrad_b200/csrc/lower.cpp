@@ -421,6 +421,46 @@ bool covers_whole_tensor(const Kernel& k, const ShapeTable& shapes) {
   return true;
 }
 
+bool kernel_loops_full(const Kernel& k, const ShapeTable& shapes) {
+  Lowerer lw(k, shapes, 0);
+  std::vector<IpInstr> scratch;
+  lw.sink = &scratch;
+  for (auto& l : k.loops) {
+    Val v;
+    v.kind = V_DEV;
+    v.ty = T_INDEX;
+    v.slot = lw.new_slot();
+    lw.env[l.iter] = v;
+  }
+  try {
+    for (auto& l : k.loops) {
+      if (!l.has_bounds) return false;
+      int64_t extent = -1;
+      auto visit = [&](const TensorOp& op) {
+        if (extent >= 0) return;
+        auto sh = shapes.find(op.tensor);
+        if (sh == shapes.end()) return;
+        for (size_t d = 0; d < op.dims.size(); ++d) {
+          if (op.dims[d].only_register() != l.iter) continue;
+          if (op.is_raw) {
+            extent = 1;
+            for (auto s : sh->second) extent *= s;
+          } else if (d < sh->second.size()) {
+            extent = sh->second[d];
+          }
+          return;
+        }
+      };
+      visit(k.write);
+      for (auto& r : k.reads) visit(r);
+      if (extent < 0 || !full_range(lw, l, extent)) return false;
+    }
+  } catch (const Error&) {
+    return false;
+  }
+  return true;
+}
+
 Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<int, void*>& ptrs, int64_t epoch,
                      bool strict, bool overwrite, int sm_count) {
   Lowerer lw(k, shapes, epoch);

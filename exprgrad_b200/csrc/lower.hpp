@@ -23,6 +23,8 @@ Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<i
                      bool strict, bool overwrite, int sm_count);
 
 bool covers_whole_tensor(const Kernel& k, const ShapeTable& shapes);
+// Every loop runs over the full extent [0, size) of a tensor dimension it indexes alone.
+bool kernel_loops_full(const Kernel& k, const ShapeTable& shapes);
 
 struct GemmPattern {
   int a_tensor = 0, b_tensor = 0, c_tensor = 0;

@@ -509,13 +509,71 @@ std::string serialize_program(const Program& prog) {
   return w.ss.str();
 }
 
-std::string describe_kernel(const Kernel& k) {
+// Canonical text of a kernel: iterator-space, tensor accesses and the value expression as a tree.
+// Reads are named R0, R1, ... in read order, loop iterators I0, I1, ... in loop order; independent
+// loops are marked with '!'. The planner matches these strings against the shapes the reference's
+// layer library produces (exprgrad/layers/base.nim, dnn.nim) to pick fused device kernels.
+static std::string index_text(const LinearIndex& li, const std::map<int, int>& loop_pos) {
   std::ostringstream ss;
-  ss << "t" << k.write.tensor << (k.write.is_raw ? "{" : "[");
-  for (size_t i = 0; i < k.write.dims.size(); ++i) ss << (i ? "," : "") << "d";
-  ss << (k.write.is_raw ? "}" : "]") << " ++= f(";
-  for (size_t i = 0; i < k.reads.size(); ++i) ss << (i ? "," : "") << "t" << k.reads[i].tensor;
-  ss << ") loops=" << k.loops.size() << " instrs=" << k.instrs.size();
+  bool first = true;
+  for (auto& kv : li.factors) {
+    if (!first) ss << "+";
+    first = false;
+    if (kv.second != 1) ss << kv.second << "*";
+    auto it = loop_pos.find(kv.first);
+    if (it != loop_pos.end()) ss << "I" << it->second;
+    else ss << "r" << kv.first;
+  }
+  if (li.constant != 0 || first) ss << (first ? "" : "+") << li.constant;
+  return ss.str();
+}
+
+static std::string access_text(const TensorOp& op, const std::map<int, int>& loop_pos) {
+  std::ostringstream ss;
+  ss << (op.is_raw ? "{" : "[");
+  for (size_t i = 0; i < op.dims.size(); ++i) ss << (i ? "," : "") << index_text(op.dims[i], loop_pos);
+  ss << (op.is_raw ? "}" : "]");
+  return ss.str();
+}
+
+std::string expr_text(const Kernel& k, int reg, int depth) {
+  if (depth > 64) return "?";
+  for (size_t i = 0; i < k.reads.size(); ++i)
+    if (k.reads[i].data == reg) return "R" + std::to_string(i);
+  for (size_t i = 0; i < k.loops.size(); ++i)
+    if (k.loops[i].iter == reg) return "I" + std::to_string(i);
+  for (auto& ins : k.instrs) {
+    if (ins.res != reg) continue;
+    char buf[64];
+    switch (ins.op) {
+      case Op::Scalar: snprintf(buf, sizeof(buf), "%.17g", ins.scalar); return buf;
+      case Op::Index: return "i" + std::to_string(ins.index);
+      case Op::Boolean: return ins.index ? "true" : "false";
+      case Op::Shape: return "shape(T" + std::to_string(ins.tensor) + "," + std::to_string(ins.dim) + ")";
+      case Op::Len: return "len(T" + std::to_string(ins.tensor) + ")";
+      case Op::ShapeLen: return "rank(T" + std::to_string(ins.tensor) + ")";
+      default: break;
+    }
+    std::string s = op_name(ins.op);
+    for (auto& c : s) c = (char)tolower(c);
+    s += "(";
+    for (size_t i = 0; i < ins.args.size(); ++i) s += (i ? "," : "") + expr_text(k, ins.args[i], depth + 1);
+    return s + ")";
+  }
+  return "r" + std::to_string(reg);
+}
+
+std::string describe_kernel(const Kernel& k) {
+  std::map<int, int> loop_pos;
+  std::ostringstream ss;
+  ss << "loops=";
+  for (size_t i = 0; i < k.loops.size(); ++i) {
+    loop_pos[k.loops[i].iter] = (int)i;
+    ss << (k.loops[i].mode >= 1 ? "!" : ".");
+  }
+  ss << " W" << access_text(k.write, loop_pos);
+  for (size_t i = 0; i < k.reads.size(); ++i) ss << " R" << i << access_text(k.reads[i], loop_pos);
+  ss << " : " << expr_text(k, k.write.data, 0);
   return ss.str();
 }
 

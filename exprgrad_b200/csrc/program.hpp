@@ -163,5 +163,6 @@ typedef std::map<int, std::vector<int64_t>> ShapeTable;
 ShapeTable infer_shapes(const Program& prog, const Target& target, const ShapeTable& inputs);
 
 std::string describe_kernel(const Kernel& k);
+std::string expr_text(const Kernel& k, int reg, int depth = 0);
 
 }  // namespace egb

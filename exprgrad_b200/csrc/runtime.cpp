@@ -141,6 +141,7 @@ void build_nodes_impl(Model& m, Plan& plan) {
   for (size_t ki = 0; ki < target.kernels.size(); ++ki) {
     const Kernel& k = *target.kernels[ki];
     const KernelInfo& inf = info[ki];
+    if (inf.absorbed_by >= 0) continue;  // runs inside the epilogue of its contraction
     if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes) {
       Node n;
       n.kind = Node::ALLREDUCE;
@@ -170,7 +171,29 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.gemm.ldc = (int)g.ldc;
       n.gemm.flags = inf.overwrite ? 0 : GEMM_ACCUMULATE;
       n.gemm.alpha = 1.0f;
+      if (inf.bias_tensor) {
+        n.gemm.flags |= GEMM_BIAS;
+        n.gemm.bias = (const float*)ptrs[inf.bias_tensor];
+      }
+      n.gemm.epi = inf.epi;
+      n.gemm.epi_param = inf.epi_param;
+      if (inf.d_tensor) n.gemm.D = (float*)ptrs[inf.d_tensor];
+      if (inf.h_tensor) n.gemm.H = (const float*)ptrs[inf.h_tensor];
+      if (inf.colsum_tensor) n.gemm.colsum = (float*)ptrs[inf.colsum_tensor];
+      if (!inf.absorbed.empty()) n.label += " +" + std::to_string(inf.absorbed.size()) + " fused";
+      if (inf.emit_planes) {
+        // the epilogue writes the operand planes of its final value: later contractions find them in the cache
+        const int64_t cols = g.N, out_ld = (cols + 7) & ~int64_t(7);
+        const size_t bytes = align_up((size_t)g.M * out_ld * 2, 256);
+        if (plane_cursor + 2 * bytes > plane_cap) fail(EGB_ERR_RUNTIME, "internal: operand plane arena exhausted");
+        n.gemm.out_hi = (__nv_bfloat16*)(plane_base + plane_cursor);
+        n.gemm.out_mid = (__nv_bfloat16*)(plane_base + plane_cursor + bytes);
+        n.gemm.ld_out = (int)out_ld;
+        n.gemm.flags |= GEMM_SPLIT_OUT;
+        plane_cursor += 2 * bytes;
+      }
       plan.nodes.push_back(n);
+      if (inf.emit_planes) planes[std::make_pair(inf.final_tensor, 0)] = std::make_pair(n.gemm.out_hi, n.gemm.out_mid);
     } else {
       Lowered lw = lower_kernel(k, plan.shapes, ptrs, m.epoch, m.strict, inf.overwrite, ctx.sm_count);
       Node n;
@@ -185,9 +208,14 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.kernel_index = (int)ki;
       plan.nodes.push_back(n);
     }
-    // the written tensor's cached planes are stale now
-    for (auto it = planes.begin(); it != planes.end();)
-      it = it->first.first == k.write.tensor ? planes.erase(it) : std::next(it);
+    // cached planes of every tensor this unit wrote are stale now (except the ones it just produced)
+    std::vector<int> wrote = {k.write.tensor};
+    for (int kj : inf.absorbed) wrote.push_back(target.kernels[kj]->write.tensor);
+    for (int wtensor : wrote) {
+      if (inf.emit_planes && wtensor == inf.final_tensor && inf.is_gemm && !m.strict) continue;
+      for (auto it = planes.begin(); it != planes.end();)
+        it = it->first.first == wtensor ? planes.erase(it) : std::next(it);
+    }
   }
   for (auto& n : plan.nodes)
     if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
@@ -220,20 +248,48 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   for (auto& kv : state) plan->shapes[kv.first] = kv.second.shape;
 
   // ---- classify kernels, decide overwrite vs accumulate and which results need zero-filling
-  plan->info.resize(target->kernels.size());
+  const size_t nk = target->kernels.size();
+  plan->info.resize(nk);
   std::set<int> written, read_first, needs_zero;
   size_t plane_bytes = 0;
-  for (size_t ki = 0; ki < target->kernels.size(); ++ki) {
+  const bool dp = comm && comm_world(comm) > 1;
+  std::vector<std::string> text(nk);
+  for (size_t ki = 0; ki < nk; ++ki) {
+    if (target->kernels[ki]->is_generator())
+      fail(EGB_ERR_GENERATOR, "program still contains generator kernels; compile it first");
+    text[ki] = describe_kernel(*target->kernels[ki]);
+  }
+  auto same_shape = [&](int a, int b) {
+    auto x = plan->shapes.find(a), y = plan->shapes.find(b);
+    return x != plan->shapes.end() && y != plan->shapes.end() && x->second == y->second;
+  };
+  auto is_fresh = [&](int t) {
+    return prog->tdef(t).kind == TensorKind::Result && !written.count(t) && !read_first.count(t) && t != 0;
+  };
+  // "prefix<number>suffix" -> number
+  auto parse_param = [](const std::string& s, const std::string& prefix, const std::string& suffix, float& out) {
+    if (s.size() <= prefix.size() + suffix.size()) return false;
+    if (s.compare(0, prefix.size(), prefix) != 0) return false;
+    if (s.compare(s.size() - suffix.size(), suffix.size(), suffix) != 0) return false;
+    const std::string num = s.substr(prefix.size(), s.size() - prefix.size() - suffix.size());
+    char* end = nullptr;
+    const double v = strtod(num.c_str(), &end);
+    if (!end || *end) return false;
+    out = (float)v;
+    return true;
+  };
+
+  for (size_t ki = 0; ki < nk; ++ki) {
     const Kernel& k = *target->kernels[ki];
-    if (k.is_generator()) fail(EGB_ERR_GENERATOR, "program still contains generator kernels; compile it first");
     KernelInfo& inf = plan->info[ki];
+    if (inf.absorbed_by >= 0) continue;  // accounted for at the position of its contraction
     for (auto& r : k.reads) {
       if (!plan->shapes.count(r.tensor)) fail(EGB_ERR_SHAPE, "Missing shape for tensor%d", r.tensor - 1);
       if (!written.count(r.tensor)) read_first.insert(r.tensor);
     }
     inf.is_gemm = !strict && match_gemm(k, plan->shapes, inf.gemm);
     const int wt = k.write.tensor;
-    const bool fresh = prog->tdef(wt).kind == TensorKind::Result && !written.count(wt) && !read_first.count(wt);
+    const bool fresh = is_fresh(wt);
     bool reads_self = false;
     for (auto& r : k.reads) reads_self = reads_self || r.tensor == wt;
     inf.overwrite = fresh && !reads_self && (inf.is_gemm || covers_whole_tensor(k, plan->shapes));
@@ -246,6 +302,90 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
       const size_t a_bytes = std::max((size_t)g.K * pad8(g.M), (size_t)g.M * pad8(g.K)) * 2;
       const size_t b_bytes = std::max((size_t)g.N * pad8(g.K), (size_t)g.K * pad8(g.N)) * 2;
       plane_bytes += 2 * align_up(a_bytes, 256) + 2 * align_up(b_bytes, 256);
+    }
+    inf.final_tensor = wt;
+    if (!(inf.is_gemm && inf.overwrite && fuse)) continue;
+
+    // ---- epilogue fusion: look ahead for kernels that post-process this contraction's output
+    const int C = wt;
+    std::set<int> touched_r, touched_w;  // tensors used by kernels that stay between ki and the candidate
+    bool has_bias = false, has_stage = false, has_colsum = false;
+    for (size_t kj = ki + 1; kj < nk; ++kj) {
+      const Kernel& c = *target->kernels[kj];
+      KernelInfo& cinf = plan->info[kj];
+      if (cinf.absorbed_by >= 0) continue;  // already runs earlier, inside another contraction
+      bool conflict = touched_r.count(c.write.tensor) || touched_w.count(c.write.tensor);
+      for (auto& r : c.reads) conflict = conflict || touched_w.count(r.tensor);
+      bool take = false;
+      const std::string& t = text[kj];
+      const int final_t = inf.final_tensor;
+      if (!conflict && kernel_loops_full(c, plan->shapes)) {
+        float param = 0.0f;
+        if (!has_bias && !has_stage && !has_colsum && t == "loops=!! W[I0,I1] R0[I1] : R0" && c.write.tensor == C &&
+            c.reads[0].tensor != C) {
+          inf.bias_tensor = c.reads[0].tensor;
+          has_bias = take = true;
+        } else if (!has_stage && !has_colsum && c.reads.size() == 1 && c.reads[0].tensor == C &&
+                   is_fresh(c.write.tensor) && same_shape(c.write.tensor, C) &&
+                   (t == "loops=! W{I0} R0{I0} : select(le(0,R0),R0,0)" ||
+                    parse_param(t, "loops=! W{I0} R0{I0} : mul(select(le(0,R0),1,", "),R0)", param))) {
+          inf.epi = t.find("mul(") != std::string::npos ? EPI_LEAKY : EPI_RELU;
+          inf.epi_param = param;
+          inf.d_tensor = c.write.tensor;
+          has_stage = take = true;
+        } else if (!has_stage && !has_colsum && c.reads.size() == 2 && c.reads[1].tensor == C &&
+                   c.reads[0].tensor != C && is_fresh(c.write.tensor) && same_shape(c.write.tensor, C) &&
+                   same_shape(c.reads[0].tensor, C) && !touched_w.count(c.reads[0].tensor) &&
+                   (t == "loops=! W{I0} R0{I0} R1{I0} : select(le(0,R0),R1,0)" ||
+                    parse_param(t, "loops=! W{I0} R0{I0} R1{I0} : mul(R1,select(le(0,R0),1,", "))", param))) {
+          inf.epi = t.find("mul(") != std::string::npos ? EPI_MASK_LEAKY : EPI_MASK_RELU;
+          inf.epi_param = param;
+          inf.d_tensor = c.write.tensor;
+          inf.h_tensor = c.reads[0].tensor;
+          has_stage = take = true;
+        } else if (!has_colsum && t == "loops=.! W[I1] R0[I0,I1] : R0" && c.reads[0].tensor == final_t &&
+                   is_fresh(c.write.tensor)) {
+          inf.colsum_tensor = c.write.tensor;
+          has_colsum = take = true;
+        } else if (!dp && !has_stage && !has_colsum && c.reads.size() == 1 && c.reads[0].tensor == C &&
+                   prog->tdef(c.write.tensor).kind == TensorKind::Param && same_shape(c.write.tensor, C) &&
+                   parse_param(t, "loops=! W{I0} R0{I0} : mul(negate(R0),", ")", param)) {
+          inf.epi = EPI_SGD;
+          inf.epi_param = param;
+          inf.d_tensor = c.write.tensor;
+          has_stage = take = true;
+        }
+      }
+      if (take) {
+        cinf.absorbed_by = (int)ki;
+        inf.absorbed.push_back((int)kj);
+        if (inf.epi != EPI_SGD && inf.d_tensor) inf.final_tensor = inf.d_tensor;
+        if (inf.colsum_tensor == c.write.tensor) needs_zero.insert(c.write.tensor);  // accumulated atomically
+        written.insert(c.write.tensor);
+        continue;
+      }
+      touched_w.insert(c.write.tensor);
+      for (auto& r : c.reads) touched_r.insert(r.tensor);
+    }
+  }
+  // does a later contraction consume a fused epilogue's final value as an operand? then emit its planes
+  for (size_t ki = 0; ki < nk; ++ki) {
+    KernelInfo& inf = plan->info[ki];
+    if (!inf.is_gemm || inf.absorbed_by >= 0 || !inf.overwrite || inf.epi == EPI_SGD) continue;
+    for (size_t kj = ki + 1; kj < nk && !inf.emit_planes; ++kj) {
+      const KernelInfo& c = plan->info[kj];
+      if (c.absorbed_by >= 0) continue;
+      if (c.is_gemm) {
+        const GemmPattern& g = c.gemm;
+        const bool a_copy = g.trans_a && prefer_transposed_copy(g.K, g.M);
+        const bool b_copy = !g.trans_b && prefer_transposed_copy(g.K, g.N);
+        if ((g.a_tensor == inf.final_tensor && !a_copy) || (g.b_tensor == inf.final_tensor && !b_copy)) inf.emit_planes = true;
+      }
+      if (target->kernels[kj]->write.tensor == inf.final_tensor) break;  // rewritten before any use
+    }
+    if (inf.emit_planes) {
+      const auto& sh = plan->shapes.at(inf.final_tensor);
+      plane_bytes += 2 * align_up((size_t)sh[0] * (size_t)((sh[1] + 7) & ~int64_t(7)) * 2, 256);
     }
   }
   for (int id : target->tensors)

@@ -58,6 +58,16 @@ struct KernelInfo {
   bool is_gemm = false;
   GemmPattern gemm;
   bool overwrite = false;  // first writer of a zero-initialised result that it covers completely
+  // Epilogue fusion: kernels that follow a contraction and only post-process its output element by
+  // element (bias add, relu / leakyRelu, their adjoint masks, bias-gradient column sums, the SGD
+  // update) run inside the contraction's epilogue instead of as separate launches.
+  int absorbed_by = -1;       // >= 0: this kernel runs inside the epilogue of that contraction kernel
+  std::vector<int> absorbed;  // (contraction) kernels fused behind this one
+  int bias_tensor = 0, d_tensor = 0, h_tensor = 0, colsum_tensor = 0;
+  int epi = EPI_NONE;
+  float epi_param = 0.0f;
+  int final_tensor = 0;       // tensor that holds the final epilogue value (C or D)
+  bool emit_planes = false;   // the epilogue also writes bf16 operand planes of the final value
 };
 
 struct Plan {
@@ -96,6 +106,7 @@ struct Model {
   uint64_t rng_counter = 0;
   bool strict = false;      // bit-exact mode: sequential accumulation everywhere, no tensor cores
   bool use_graphs = true;
+  bool fuse = true;         // epilogue fusion of contraction + elementwise / column-sum / SGD kernels
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   CommHooks* comm = nullptr;

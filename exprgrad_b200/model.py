@@ -39,6 +39,13 @@ class Program:
         check(lib.egb_program_serialize(self.handle, buf, need.value, ctypes.byref(need)))
         return buf.value.decode("utf-8")
 
+    def describe(self, target: str) -> str:
+        need = ctypes.c_size_t(0)
+        check(lib.egb_program_describe(self.handle, target.encode(), None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        check(lib.egb_program_describe(self.handle, target.encode(), buf, need.value, ctypes.byref(need)))
+        return buf.value.decode()
+
     def tensor_count(self) -> int:
         n = ctypes.c_int(0)
         check(lib.egb_program_tensor_count(self.handle, ctypes.byref(n)))

@@ -149,6 +149,9 @@ int egb_program_compile(egb_program* program);
 /* Text form of the current program state (used by the tests to compare the native passes with the
  * oracle's). Two-call protocol: *needed receives the size including the terminating NUL. */
 int egb_program_serialize(egb_program* program, char* buf, size_t cap, size_t* needed);
+/* One line per kernel of a target: tensors read/written and the canonical text of the kernel
+ * (iteration space, accesses, value expression) that the planner matches fused kernels against. */
+int egb_program_describe(egb_program* program, const char* target, char* buf, size_t cap, size_t* needed);
 int egb_program_free(egb_program* program);
 int egb_program_tensor_count(egb_program* program, int* count);
 /* kind: 0 result, 1 input, 2 param, 3 cache, 4 random (exprgrad/ir.nim:222-233). dims has room for

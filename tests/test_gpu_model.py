@@ -65,8 +65,29 @@ def test_dense_net_plan_uses_tensor_cores_and_graph(ctx):
     plan = pm.describe_plan()
     assert plan.count("\n  gemm ") == 8, plan  # 3 forward + 2 dX + 3 dW contractions
     assert "graph yes" in plan
-    assert ctx.launch_count - n0 >= 2 * 30
+    assert plan.count("fused") >= 6, plan     # bias/relu, relu-adjoint/colsum and SGD stages run in GEMM epilogues
+    assert ctx.launch_count - n0 >= 2 * 15
     pm.free()
+
+
+def test_fused_and_unfused_plans_agree(ctx):
+    """Epilogue fusion must not change results beyond summation order of the bias-gradient column sums."""
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    x, y, params = G.dense_inputs(300)
+    outs = []
+    for fuse in (1, 0):
+        pm = M.compile(*G.dense_net(F, PL), gpu=ctx, seed=0)
+        pm.set_option("fuse", fuse)
+        for tid, v in zip(pm.params.ids(), params):
+            pm.params[tid] = v
+        for _ in range(2):
+            pm.apply("train", {"x": x, "y": y})
+        assert ("fused" in pm.describe_plan()) == bool(fuse)
+        outs.append([pm.params[t] for t in pm.params.ids()])
+        pm.free()
+    for a, b, v in zip(outs[0], outs[1], params):
+        assert_close(a, b, tol=1e-6, what="fused vs unfused params")
+        assert_close(a - v, b - v, tol=1e-3, what="fused vs unfused update")
 
 
 def test_strict_mode_is_bit_exact_for_non_transcendental_kernels(ctx):
