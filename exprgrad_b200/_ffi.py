@@ -52,6 +52,7 @@ _SIGS = {
     "egb_context_synchronize": (I, [P]),
     "egb_context_stream": (P, [P]),
     "egb_context_launch_count": (I64, [P]),
+    "egb_context_set_option": (I, [P, S, I64]),
     "egb_context_set_timing": (I, [P, I]),
     "egb_context_kernel_time": (I, [P, I, ctypes.POINTER(D), PI64]),
     "egb_event_create": (I, [P, PP]),

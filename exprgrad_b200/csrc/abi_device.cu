@@ -1,5 +1,6 @@
 // C-ABI group 1 + 2: device runtime (mirror of exprgrad/runtimes/gpu.nim:25-52 as implemented for
 // OpenCL in exprgrad/runtimes/cl.nim:83-207) and the raw operator entry points.
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -143,6 +144,7 @@ int egb_context_create(int device, egb_context** out) {
   EGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (qres != cudaDriverEntryPointSuccess || !fn) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled not found in driver");
   ctx->c.encode_tiled = (PFN_encodeTiled)fn;
+  if (const char* e = getenv("EGB_PDL")) ctx->c.pdl = atoi(e) != 0;
   *out = ctx;
   EGB_CATCH
 }
@@ -170,6 +172,14 @@ int egb_context_synchronize(egb_context* ctx) {
 }
 
 void* egb_context_stream(egb_context* ctx) { return (void*)ctx->c.stream; }
+
+int egb_context_set_option(egb_context* ctx, const char* key, int64_t value) {
+  EGB_TRY
+  const std::string k(key);
+  if (k == "pdl") ctx->c.pdl = value != 0;
+  else fail(EGB_ERR_GPU, "unknown context option '%s'", key);
+  EGB_CATCH
+}
 
 int egb_context_set_timing(egb_context* ctx, int enabled) {
   EGB_TRY

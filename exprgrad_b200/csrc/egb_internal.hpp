@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <stdexcept>
 #include <string>
@@ -49,6 +50,11 @@ struct Context {
   size_t launches = 0;  // number of kernel launches issued through this context
   void* ensure_scratch(size_t bytes);
 
+  // Programmatic dependent launch: every kernel is launched with the programmatic-stream-serialization
+  // attribute and begins with griddepcontrol.wait, so that the launch latency and prologue of kernel
+  // N+1 overlap the tail of kernel N (also inside captured CUDA graphs).
+  bool pdl = true;
+
   // Optional per-kernel-class device timing (bench.py's live roofline measurement): when enabled,
   // every launch is bracketed by CUDA events on the launching stream.
   bool timing = false;
@@ -61,6 +67,31 @@ struct Context {
 // Kernel classes for the timing interface (egb_context_kernel_time).
 enum KernelClass { KC_GEMM = 0, KC_SPLIT = 1, KC_FILL = 2, KC_INTERP = 3, KC_REDUCE = 4, KC_ELTWISE = 5,
                    KC_CONV = 6, KC_OTHER = 7, KC_COUNT = 8 };
+
+// Kernel launch through cudaLaunchKernelEx so that the PDL attribute can be attached.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(Context& ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx.pdl ? 1 : 0;
+  EGB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
+// Device side of PDL: wait for the prerequisite grid (no-op when launched without the attribute) and
+// allow the dependent grid to start its own prologue.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // RAII bracket around one kernel launch: counts it and, if timing is on, records events.
 struct Launch {

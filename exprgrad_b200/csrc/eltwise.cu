@@ -4,6 +4,8 @@
 namespace egb {
 namespace {
 __global__ void fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t value, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (n >> 2) : 0;
@@ -16,6 +18,8 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t value, size
 // Counter-based: element i of call c is a hash of (seed, c, i), so a run is reproducible.
 __global__ void fill_uniform_kernel(float* __restrict__ dst, size_t n, float lo, float hi, uint64_t seed,
                                     uint64_t counter) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint64_t z = seed * 0x9e3779b97f4a7c15ull + counter * 0xd1342543de82ef95ull + i + 1;
@@ -36,7 +40,7 @@ void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi,
   if (blocks > cap) blocks = cap;
   {
     Launch l(ctx, KC_FILL, st);
-    fill_uniform_kernel<<<(int)blocks, 256, 0, st>>>(dst, n, lo, hi, seed, counter);
+    launch_kernel(ctx, fill_uniform_kernel, dim3((int)blocks), dim3(256), 0, st, dst, n, lo, hi, seed, counter);
   }
   EGB_CUDA(cudaGetLastError());
 }
@@ -48,7 +52,7 @@ void launch_fill_u32(Context& ctx, uint32_t* dst, uint32_t value, size_t n, cuda
   if (blocks > cap) blocks = cap;
   {
     Launch l(ctx, KC_FILL, st);
-    fill_u32_kernel<<<(int)blocks, 256, 0, st>>>(dst, value, n);
+    launch_kernel(ctx, fill_u32_kernel, dim3((int)blocks), dim3(256), 0, st, dst, value, n);
   }
   EGB_CUDA(cudaGetLastError());
 }

@@ -109,9 +109,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
+      // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the
+      // previous kernel; operand planes written by it may only be read from here on. Every other role
+      // is ordered behind these loads through the mbarrier pipeline.
+      pdl_wait();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % p.tiles_m) * BM;
@@ -449,7 +454,8 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   const int grid = tiles < ctx.sm_count ? tiles : ctx.sm_count;
   {
     Launch l(ctx, KC_GEMM, st);
-    gemm_bf16x3_kernel<<<grid, NUM_THREADS, smem, st>>>(tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p);
+    launch_kernel(ctx, gemm_bf16x3_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid,
+                  p);
   }
   EGB_CUDA(cudaGetLastError());
 }

@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constan
   const int rl = points_fast ? t / pb : t % rb;  // reduction slice
   const int64_t nblocks = (p.npoints + pb - 1) / pb;
   float* const out = reinterpret_cast<float*>(p.write.base);
+  pdl_launch_dependents();
   for (int i = 0; i < p.nlits; ++i) s[p.lit_slot[i]].u = p.lits[i];
+  pdl_wait();
 
   for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const int64_t point = blk * pb + pl;
@@ -182,8 +184,8 @@ void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int poin
   const int grid = (int)(nblocks < cap ? nblocks : cap);
   {
     Launch l(ctx, KC_INTERP, st);
-    if (strict) interp_kernel<true><<<grid, IP_THREADS, 0, st>>>(prog, pb, rb, points_fast);
-    else interp_kernel<false><<<grid, IP_THREADS, 0, st>>>(prog, pb, rb, points_fast);
+    if (strict) launch_kernel(ctx, interp_kernel<true>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
+    else launch_kernel(ctx, interp_kernel<false>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
   }
   EGB_CUDA(cudaGetLastError());
 }

@@ -21,6 +21,8 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& h, __nv_bfloat16&
 __global__ void split_rows_kernel(const float* __restrict__ src, int rows, int cols, int ld,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid, int dst_ld,
                                   int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunks = (cols + 7) >> 3;
   const long total = (long)rows * chunks;
   const bool vec = ((ld & 3) == 0) && ((dst_ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -52,6 +54,8 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, 
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                                        int dst_ld, int act) {
   __shared__ float tile[64][65];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tiles_c = (cols + 63) >> 6;
   const int tiles_r = (rows + 63) >> 6;
   const int tx = threadIdx.x & 63;  // 256 threads: 64 x 4
@@ -90,14 +94,15 @@ void launch_split_bf16(Context& ctx, const float* src, int rows, int cols, int l
     const long cap = (long)ctx.sm_count * 8;
     if (blocks > cap) blocks = cap;
     Launch l(ctx, KC_SPLIT, st);
-    split_rows_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, ld, hi, mid, dst_ld, act);
+    launch_kernel(ctx, split_rows_kernel, dim3((int)blocks), dim3(256), 0, st, src, rows, cols, ld, hi, mid, dst_ld, act);
   } else {
     const long tiles = (long)((rows + 63) >> 6) * ((cols + 63) >> 6);
     long blocks = tiles;
     const long cap = (long)ctx.sm_count * 8;
     if (blocks > cap) blocks = cap;
     Launch l(ctx, KC_SPLIT, st);
-    split_transpose_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, ld, hi, mid, dst_ld, act);
+    launch_kernel(ctx, split_transpose_kernel, dim3((int)blocks), dim3(256), 0, st, src, rows, cols, ld, hi, mid, dst_ld,
+                  act);
   }
   EGB_CUDA(cudaGetLastError());
 }

@@ -76,6 +76,9 @@ void* egb_context_stream(egb_context* ctx);
 /* Number of CUDA kernels launched through this context so far (graph replays count their nodes). */
 int64_t egb_context_launch_count(egb_context* ctx);
 
+/* Context options: "pdl" 0/1 - programmatic dependent launch of consecutive kernels (default 1; the
+ * environment variable EGB_PDL overrides the default). */
+int egb_context_set_option(egb_context* ctx, const char* key, int64_t value);
 /* Device timing for benchmarks. set_timing(1) clears the record and brackets every subsequent kernel
  * launch with CUDA events on the context's stream; kernel_time sums the device time of the launches
  * of one kernel class (EGB_KC_*, -1 = all) recorded since. */
