@@ -1,0 +1,393 @@
+// Direct fp32 kernels for the reference's `conv2` layer (exprgrad/layers/dnn.nim:45-49: NHWC images,
+// filters [filter, dy, dx, chan], valid padding, stride 1) and the two adjoint kernels `derive`
+// generates for it (exprgrad/passes.nim:519-549):
+//
+//   forward    out[n,y,x,f]        += img[n,y+dy,x+dx,c] * w[f,dy,dx,c]
+//   d_filters  dw[f,dy,dx,c]       += dout[n,y,x,f]      * img[n,y+dy,x+dx,c]      (reduction over n,y,x)
+//   d_images   dimg[n,y+dy,x+dx,c] += dout[n,y,x,f]      * w[f,dy,dx,c]            (scatter in the reference,
+//                                                                                   gathered per input pixel here)
+//
+// At BASELINE config 4 (256x224x224x3 images, 64 3x3x3 filters) the arithmetic intensity is ~13 flop/B:
+// all three kernels are bound by streaming the 3.2 GB output / output-gradient tensor through HBM, and
+// K = 27 is far too short for tensor-core tiles to pay off, so they run on the fp32 CUDA cores with
+// register tiling (4 pixels x 8 filters per thread), shared-memory staging of the input rows and filter
+// bank, and 128-bit coalesced loads/stores of the big tensor. Filters are processed in chunks of 64.
+#include "egb_internal.hpp"
+
+namespace egb {
+
+namespace {
+
+constexpr int FC = 64;        // filters per chunk
+constexpr int TX_FWD = 128;   // output pixels per block (forward)
+constexpr int TX_BWD = 64;    // pixels per block (both adjoint kernels)
+constexpr int MAX_CC = 4;     // channels per pass
+
+struct ConvDims {
+  int N, H, W, C, F, KH, KW, OH, OW;
+};
+
+// ------------------------------------------------------------------ forward
+// block: 256 threads = 8 filter groups (8 filters each) x 32 pixel quads (4 consecutive x each).
+template <int KW_T>
+__global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                        float* __restrict__ out, ConvDims d, int accumulate) {
+  extern __shared__ float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int KW = KW_T > 0 ? KW_T : d.KW;
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, tq = tid >> 3;
+  const int fchunks = (d.F + FC - 1) / FC;
+  const int n = blockIdx.z / fchunks, f0 = (blockIdx.z % fchunks) * FC;
+  const int y = blockIdx.y, x0 = blockIdx.x * TX_FWD;
+  const int in_w = TX_FWD + KW - 1;                 // staged input pixels per row
+  float* in_s = smem;                               // [KH][in_w * cc]
+  float* w_s = smem + d.KH * in_w * MAX_CC;         // [KH*KW*cc][FC]
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.0f;
+
+  for (int c0 = 0; c0 < d.C; c0 += MAX_CC) {
+    const int cc = min(MAX_CC, d.C - c0);
+    __syncthreads();
+    for (int i = tid; i < d.KH * in_w * cc; i += 256) {
+      const int dy = i / (in_w * cc), r = i % (in_w * cc);
+      const int px = r / cc, ch = r % cc;
+      const int gx = x0 + px;
+      in_s[i] = gx < d.W ? __ldg(img + (((size_t)n * d.H + y + dy) * d.W + gx) * d.C + c0 + ch) : 0.0f;
+    }
+    for (int i = tid; i < d.KH * KW * cc * FC; i += 256) {
+      const int f = i % FC, k = i / FC;
+      const int ch = k % cc, dx = (k / cc) % KW, dy = k / (cc * KW);
+      w_s[i] = (f0 + f) < d.F ? __ldg(w + (((size_t)(f0 + f) * d.KH + dy) * KW + dx) * d.C + c0 + ch) : 0.0f;
+    }
+    __syncthreads();
+    for (int dy = 0; dy < d.KH; ++dy) {
+      const float* row = in_s + dy * in_w * cc + tq * 4 * cc;
+      if (KW_T > 0) {
+        for (int ch = 0; ch < cc; ++ch) {
+          float iv[4 + (KW_T > 0 ? KW_T : 1) - 1];
+#pragma unroll
+          for (int t = 0; t < 4 + KW_T - 1; ++t) iv[t] = row[t * cc + ch];
+#pragma unroll
+          for (int dx = 0; dx < KW_T; ++dx) {
+            const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW_T + dx) * cc + ch) * FC + tx * 8);
+            const float4 w0 = wp[0], w1 = wp[1];
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv[p + dx], wv[j], acc[p][j]);
+          }
+        }
+      } else {
+        for (int dx = 0; dx < KW; ++dx)
+          for (int ch = 0; ch < cc; ++ch) {
+            const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW + dx) * cc + ch) * FC + tx * 8);
+            const float4 w0 = wp[0], w1 = wp[1];
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const float iv = row[(p + dx) * cc + ch];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv, wv[j], acc[p][j]);
+            }
+          }
+      }
+    }
+  }
+  const int fb = f0 + tx * 8;
+  const bool vec = (d.F & 3) == 0 && fb + 8 <= d.F;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int x = x0 + tq * 4 + p;
+    if (x >= d.OW) continue;
+    float* o = out + (((size_t)n * d.OH + y) * d.OW + x) * d.F + fb;
+    if (vec) {
+      float4 a = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+      float4 b = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+      if (accumulate) {
+        const float4 oa = *reinterpret_cast<const float4*>(o), ob = *reinterpret_cast<const float4*>(o + 4);
+        a.x += oa.x; a.y += oa.y; a.z += oa.z; a.w += oa.w;
+        b.x += ob.x; b.y += ob.y; b.z += ob.z; b.w += ob.w;
+      }
+      *reinterpret_cast<float4*>(o) = a;
+      *reinterpret_cast<float4*>(o + 4) = b;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (fb + j < d.F) o[j] = accumulate ? o[j] + acc[p][j] : acc[p][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ d_filters
+// Persistent blocks; a work item is (n, y, 64-pixel chunk of the output row). 256 threads = 4 pixel
+// sets x (16 filter groups of 4) x (4 k groups); a thread accumulates 4 filters x 8 filter taps
+// (k = kc*32 + kg + 4*i) in registers over all its work items, the block reduces the 4 pixel sets
+// through shared memory and flushes once with atomicAdd.
+__global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__ img, const float* __restrict__ dout,
+                                                       float* __restrict__ dw, ConvDims d) {
+  extern __shared__ float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int K = d.KH * d.KW * d.C;
+  const int kchunks = (K + 31) / 32, fchunks = (d.F + FC - 1) / FC;
+  const int kc = blockIdx.y % kchunks, f0 = (blockIdx.y / kchunks) * FC;
+  const int tid = threadIdx.x;
+  const int ps = tid >> 6, r = tid & 63, fg = r & 15, kg = r >> 4;
+  const int in_w = (TX_BWD + d.KW - 1) * d.C;       // staged floats per input row (all channels)
+  float* dout_s = smem;                              // [TX_BWD][FC]
+  float* img_s = smem + TX_BWD * FC;                 // [KH][in_w]
+  (void)fchunks;
+  int koff[8];
+  bool kval[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = kc * 32 + kg + 4 * i;
+    kval[i] = k < K;
+    const int kk = kval[i] ? k : 0;
+    const int ch = kk % d.C, dx = (kk / d.C) % d.KW, dy = kk / (d.C * d.KW);
+    koff[i] = dy * in_w + dx * d.C + ch;
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  const int xchunks = (d.OW + TX_BWD - 1) / TX_BWD;
+  const long items = (long)d.N * d.OH * xchunks;
+  for (long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int xc = (int)(it % xchunks);
+    const int y = (int)((it / xchunks) % d.OH);
+    const int n = (int)(it / ((long)xchunks * d.OH));
+    const int x0 = xc * TX_BWD;
+    __syncthreads();
+    for (int i = tid; i < TX_BWD * (FC / 4); i += 256) {
+      const int px = i / (FC / 4), f4 = (i % (FC / 4)) * 4;
+      const int x = x0 + px;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x < d.OW) {
+        const float* src = dout + (((size_t)n * d.OH + y) * d.OW + x) * d.F + f0 + f4;
+        if ((d.F & 3) == 0 && f0 + f4 + 4 <= d.F) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          if (f0 + f4 + 0 < d.F) v.x = __ldg(src + 0);
+          if (f0 + f4 + 1 < d.F) v.y = __ldg(src + 1);
+          if (f0 + f4 + 2 < d.F) v.z = __ldg(src + 2);
+          if (f0 + f4 + 3 < d.F) v.w = __ldg(src + 3);
+        }
+      }
+      *reinterpret_cast<float4*>(dout_s + px * FC + f4) = v;
+    }
+    for (int i = tid; i < d.KH * in_w; i += 256) {
+      const int dy = i / in_w, rr = i % in_w;
+      const int gx = x0 + rr / d.C;
+      img_s[i] = gx < d.W ? __ldg(img + (((size_t)n * d.H + y + dy) * d.W + x0) * d.C + rr) : 0.0f;
+    }
+    __syncthreads();
+    const int npx = min(TX_BWD, d.OW - x0);
+    for (int px = ps; px < npx; px += 4) {
+      const float4 dv = *reinterpret_cast<const float4*>(dout_s + px * FC + fg * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float iv = img_s[koff[i] + px * d.C];
+        acc[i][0] = fmaf(iv, dv.x, acc[i][0]);
+        acc[i][1] = fmaf(iv, dv.y, acc[i][1]);
+        acc[i][2] = fmaf(iv, dv.z, acc[i][2]);
+        acc[i][3] = fmaf(iv, dv.w, acc[i][3]);
+      }
+    }
+  }
+  // reduce the 4 pixel sets, then one atomic per (filter, tap) and block
+  __syncthreads();
+  float* red = smem;  // [4 sets][64 threads][32 values]
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(ps * 64 + r) * 33 + i * 4 + j] = acc[i][j];
+  __syncthreads();
+  if (ps == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!kval[i]) continue;
+      const int k = kc * 32 + kg + 4 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = f0 + fg * 4 + j;
+        if (f >= d.F) continue;
+        const float s = red[(0 * 64 + r) * 33 + i * 4 + j] + red[(1 * 64 + r) * 33 + i * 4 + j] +
+                        red[(2 * 64 + r) * 33 + i * 4 + j] + red[(3 * 64 + r) * 33 + i * 4 + j];
+        atomicAdd(dw + (size_t)f * K + k, s);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ d_images
+// block = (n, input row iy, strip of 64 input pixels). 256 threads = 16 pixel quads x 16 filter slices
+// (4 filters each); a thread gathers, for its 4 pixels and up to 4 channels, the contributions of its
+// 4 filters over all (dy, dx); the 16 slices are combined with xor-shuffles.
+template <int KW_T>
+__global__ void __launch_bounds__(256) conv2_dimg_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                                         float* __restrict__ dimg, ConvDims d, int accumulate) {
+  extern __shared__ float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int KW = KW_T;
+  const int tid = threadIdx.x;
+  const int q = tid >> 4, fs = tid & 15;
+  const int n = blockIdx.z, iy = blockIdx.y, ix0 = blockIdx.x * TX_BWD;
+  const int tw = TX_BWD + KW - 1;                    // staged dout pixels per row
+  float* dout_s = smem;                              // [KH][tw][FC]
+  float* w_s = smem + d.KH * tw * FC;                // [KH][KW][FC][4 channels]
+  const int fchunks = (d.F + FC - 1) / FC;
+  for (int c0 = 0; c0 < d.C; c0 += MAX_CC) {
+    const int cc = min(MAX_CC, d.C - c0);
+    float acc[4][MAX_CC];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < MAX_CC; ++c) acc[p][c] = 0.0f;
+    for (int fchunk = 0; fchunk < fchunks; ++fchunk) {
+      const int f0 = fchunk * FC;
+      __syncthreads();
+      // dout rows iy-dy, pixels ix0-(KW-1) .. ix0+63
+      for (int i = tid; i < d.KH * tw * (FC / 4); i += 256) {
+        const int f4 = (i % (FC / 4)) * 4, t = (i / (FC / 4)) % tw, dy = i / ((FC / 4) * tw);
+        const int oy = iy - dy, ox = ix0 - (KW - 1) + t;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (oy >= 0 && oy < d.OH && ox >= 0 && ox < d.OW) {
+          const float* src = dout + (((size_t)n * d.OH + oy) * d.OW + ox) * d.F + f0 + f4;
+          if ((d.F & 3) == 0 && f0 + f4 + 4 <= d.F) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            if (f0 + f4 + 0 < d.F) v.x = __ldg(src + 0);
+            if (f0 + f4 + 1 < d.F) v.y = __ldg(src + 1);
+            if (f0 + f4 + 2 < d.F) v.z = __ldg(src + 2);
+            if (f0 + f4 + 3 < d.F) v.w = __ldg(src + 3);
+          }
+        }
+        *reinterpret_cast<float4*>(dout_s + (dy * tw + t) * FC + f4) = v;
+      }
+      for (int i = tid; i < d.KH * KW * FC * MAX_CC; i += 256) {
+        const int c = i % MAX_CC, f = (i / MAX_CC) % FC, dx = (i / (MAX_CC * FC)) % KW, dy = i / (MAX_CC * FC * KW);
+        w_s[i] = (c < cc && f0 + f < d.F) ? __ldg(w + (((size_t)(f0 + f) * d.KH + dy) * KW + dx) * d.C + c0 + c) : 0.0f;
+      }
+      __syncthreads();
+      for (int dy = 0; dy < d.KH; ++dy) {
+        // pixel ix = ix0 + q*4 + p receives dout[.., ix - dx, ..]: staged column t = q*4 + p - dx + KW-1
+        float4 e[4 + KW - 1];
+#pragma unroll
+        for (int t = 0; t < 4 + KW - 1; ++t)
+          e[t] = *reinterpret_cast<const float4*>(dout_s + (dy * tw + q * 4 + t) * FC + fs * 4);
+#pragma unroll
+        for (int dx = 0; dx < KW; ++dx) {
+          const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW + dx) * FC + fs * 4) * MAX_CC);
+          const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];  // filters fs*4+0..3, 4 channels each
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float4 ev = e[p - dx + KW - 1];
+            acc[p][0] = fmaf(ev.x, w0.x, fmaf(ev.y, w1.x, fmaf(ev.z, w2.x, fmaf(ev.w, w3.x, acc[p][0]))));
+            acc[p][1] = fmaf(ev.x, w0.y, fmaf(ev.y, w1.y, fmaf(ev.z, w2.y, fmaf(ev.w, w3.y, acc[p][1]))));
+            acc[p][2] = fmaf(ev.x, w0.z, fmaf(ev.y, w1.z, fmaf(ev.z, w2.z, fmaf(ev.w, w3.z, acc[p][2]))));
+            acc[p][3] = fmaf(ev.x, w0.w, fmaf(ev.y, w1.w, fmaf(ev.z, w2.w, fmaf(ev.w, w3.w, acc[p][3]))));
+          }
+        }
+      }
+    }
+    // combine the 16 filter slices (lanes differing in the low 4 bits)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < MAX_CC; ++c) {
+        float v = acc[p][c];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        acc[p][c] = v;
+      }
+    if (fs == 0) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int ix = ix0 + q * 4 + p;
+        if (ix >= d.W) continue;
+        float* o = dimg + (((size_t)n * d.H + iy) * d.W + ix) * d.C + c0;
+#pragma unroll
+        for (int c = 0; c < MAX_CC; ++c)
+          if (c < cc) o[c] = accumulate ? o[c] + acc[p][c] : acc[p][c];
+      }
+    }
+  }
+}
+
+void check_dims(const ConvDims& d) {
+  if (d.N <= 0 || d.OH <= 0 || d.OW <= 0 || d.F <= 0 || d.C <= 0) fail(EGB_ERR_GPU, "conv2: empty tensor");
+  if (d.OH != d.H - d.KH + 1 || d.OW != d.W - d.KW + 1) fail(EGB_ERR_GPU, "conv2: inconsistent shapes");
+  if (d.OH > 65535 || (long)d.N * ((d.F + FC - 1) / FC) > 65535 || d.H > 65535)
+    fail(EGB_ERR_GPU, "conv2: tensor too large for the launch grid");
+}
+
+}  // namespace
+
+void launch_conv2_fwd(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
+                      int KH, int KW, bool accumulate, cudaStream_t st) {
+  ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
+  check_dims(d);
+  const int cc = C < MAX_CC ? C : MAX_CC;
+  const size_t smem = ((size_t)KH * (TX_FWD + KW - 1) * MAX_CC + (size_t)KH * KW * cc * FC) * sizeof(float);
+  dim3 grid((d.OW + TX_FWD - 1) / TX_FWD, d.OH, N * ((F + FC - 1) / FC));
+  Launch l(ctx, KC_CONV, st);
+  if (KW == 3) {
+    EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(ctx, conv2_fwd_kernel<3>, grid, dim3(256), smem, st, img, w, out, d, accumulate ? 1 : 0);
+  } else {
+    EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(ctx, conv2_fwd_kernel<0>, grid, dim3(256), smem, st, img, w, out, d, accumulate ? 1 : 0);
+  }
+}
+
+void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* dw, int N, int H, int W, int C, int F,
+                     int KH, int KW, cudaStream_t st) {
+  ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
+  check_dims(d);
+  const int K = KH * KW * C;
+  const size_t stage = ((size_t)TX_BWD * FC + (size_t)KH * (TX_BWD + KW - 1) * C) * sizeof(float);
+  const size_t red = (size_t)4 * 64 * 33 * sizeof(float);
+  const size_t smem = stage > red ? stage : red;
+  dim3 grid(ctx.sm_count * 2, ((K + 31) / 32) * ((F + FC - 1) / FC));
+  EGB_CUDA(cudaFuncSetAttribute(conv2_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  Launch l(ctx, KC_CONV, st);
+  launch_kernel(ctx, conv2_dw_kernel, grid, dim3(256), smem, st, img, dout, dw, d);
+}
+
+void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* dimg, int N, int H, int W, int C, int F,
+                       int KH, int KW, bool accumulate, cudaStream_t st) {
+  ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
+  check_dims(d);
+  const size_t smem = ((size_t)KH * (TX_BWD + KW - 1) * FC + (size_t)KH * KW * FC * MAX_CC) * sizeof(float);
+  dim3 grid((W + TX_BWD - 1) / TX_BWD, H, N);
+  Launch l(ctx, KC_CONV, st);
+#define EGB_DIMG(KWT)                                                                                       \
+  EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_kernel<KWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  launch_kernel(ctx, conv2_dimg_kernel<KWT>, grid, dim3(256), smem, st, dout, w, dimg, d, accumulate ? 1 : 0);
+  switch (KW) {
+    case 1: EGB_DIMG(1) break;
+    case 2: EGB_DIMG(2) break;
+    case 3: EGB_DIMG(3) break;
+    case 4: EGB_DIMG(4) break;
+    case 5: EGB_DIMG(5) break;
+    case 7: EGB_DIMG(7) break;
+    default: fail(EGB_ERR_GPU, "conv2 d_images: unsupported filter width %d", KW);
+  }
+#undef EGB_DIMG
+}
+
+bool conv2_dimg_supported(int KW) { return KW == 1 || KW == 2 || KW == 3 || KW == 4 || KW == 5 || KW == 7; }
+
+}  // namespace egb

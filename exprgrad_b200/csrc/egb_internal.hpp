@@ -169,6 +169,15 @@ struct GemmArgs {
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
 
+// Direct fp32 conv2 kernels (conv2.cu): NHWC images, filters [F, KH, KW, C], valid, stride 1.
+void launch_conv2_fwd(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
+                      int KH, int KW, bool accumulate, cudaStream_t st);
+void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* dw, int N, int H, int W, int C, int F,
+                     int KH, int KW, cudaStream_t st);
+void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* dimg, int N, int H, int W, int C, int F,
+                       int KH, int KW, bool accumulate, cudaStream_t st);
+bool conv2_dimg_supported(int KW);
+
 // Large operands whose stored orientation is MN-major are better served by one transposing split
 // pass plus the K-major tensor-core path (measured on 4096^3: 0.330 ms vs 0.353 ms per GEMM).
 inline bool prefer_transposed_copy(int64_t k_extent, int64_t mn_extent) {

@@ -684,4 +684,73 @@ bool match_gemm(const Kernel& k, const ShapeTable& shapes, GemmPattern& g) {
   return true;
 }
 
+// ------------------------------------------------------------------ conv2 pattern
+
+bool match_conv2(const Kernel& k, const ShapeTable& shapes, ConvPattern& c) {
+  if (k.loops.size() != 7 || k.reads.size() != 2 || k.instrs.size() != 1) return false;
+  const Instr& mul = k.instrs[0];
+  if (mul.op != Op::Mul || k.write.data != mul.res) return false;
+  if (!((mul.args[0] == k.reads[0].data && mul.args[1] == k.reads[1].data) ||
+        (mul.args[0] == k.reads[1].data && mul.args[1] == k.reads[0].data)))
+    return false;
+  const TensorOp* ops[3] = {&k.write, &k.reads[0], &k.reads[1]};
+  const TensorOp* img = nullptr;
+  std::vector<const TensorOp*> plain;
+  for (auto* op : ops) {
+    if (op->is_raw || op->dims.size() != 4) return false;
+    bool all_single = true;
+    for (auto& d : op->dims) all_single = all_single && d.only_register() != 0;
+    if (all_single) {
+      plain.push_back(op);
+    } else {
+      if (img) return false;
+      img = op;
+    }
+  }
+  if (!img || plain.size() != 2) return false;
+  // image role: [n, y+dy, x+dx, c]
+  auto pair_of = [](const LinearIndex& li, int& a, int& b) {
+    if (li.constant != 0 || !li.setup.empty() || li.factors.size() != 2) return false;
+    auto it = li.factors.begin();
+    if (it->second != 1) return false;
+    a = it->first;
+    ++it;
+    if (it->second != 1) return false;
+    b = it->first;
+    return true;
+  };
+  const int n = img->dims[0].only_register(), ch = img->dims[3].only_register();
+  int a1, b1, a2, b2;
+  if (!n || !ch || !pair_of(img->dims[1], a1, b1) || !pair_of(img->dims[2], a2, b2)) return false;
+  // filter role: [f, dy, dx, c]; output role: [n, y, x, f]
+  const TensorOp *fil = nullptr, *out = nullptr;
+  for (auto* op : plain) {
+    if (op->dims[3].only_register() == ch && op->dims[0].only_register() != n) fil = op;
+    else if (op->dims[0].only_register() == n) out = op;
+  }
+  if (!fil || !out) return false;
+  const int f = fil->dims[0].only_register(), dy = fil->dims[1].only_register(), dx = fil->dims[2].only_register();
+  if ((dy != a1 && dy != b1) || (dx != a2 && dx != b2)) return false;
+  const int y = dy == a1 ? b1 : a1, x = dx == a2 ? b2 : a2;
+  if (out->dims[1].only_register() != y || out->dims[2].only_register() != x || out->dims[3].only_register() != f)
+    return false;
+  std::set<int> regs = {n, ch, f, dy, dx, y, x};
+  if (regs.size() != 7) return false;
+  if (img->tensor == fil->tensor || img->tensor == out->tensor || fil->tensor == out->tensor) return false;
+  auto si = shapes.find(img->tensor), sf = shapes.find(fil->tensor), so = shapes.find(out->tensor);
+  if (si == shapes.end() || sf == shapes.end() || so == shapes.end()) return false;
+  if (si->second.size() != 4 || sf->second.size() != 4 || so->second.size() != 4) return false;
+  c.N = (int)si->second[0]; c.H = (int)si->second[1]; c.W = (int)si->second[2]; c.C = (int)si->second[3];
+  c.F = (int)sf->second[0]; c.KH = (int)sf->second[1]; c.KW = (int)sf->second[2];
+  if (sf->second[3] != c.C || so->second[0] != c.N || so->second[1] != c.H - c.KH + 1 ||
+      so->second[2] != c.W - c.KW + 1 || so->second[3] != c.F)
+    return false;
+  if (!kernel_loops_full(k, shapes)) return false;
+  c.img_tensor = img->tensor;
+  c.fil_tensor = fil->tensor;
+  c.out_tensor = out->tensor;
+  c.kind = &k.write == out ? ConvPattern::FORWARD : &k.write == fil ? ConvPattern::D_FILTERS : ConvPattern::D_IMAGES;
+  return true;
+}
+
 }  // namespace egb

@@ -35,4 +35,13 @@ struct GemmPattern {
 // (exprgrad/layers/base.nim:27-28 and its adjoints, passes.nim:519-549).
 bool match_gemm(const Kernel& k, const ShapeTable& shapes, GemmPattern& g);
 
+struct ConvPattern {
+  enum Kind { FORWARD, D_FILTERS, D_IMAGES } kind = FORWARD;
+  int img_tensor = 0, fil_tensor = 0, out_tensor = 0;  // roles: [N,H,W,C], [F,KH,KW,C], [N,OH,OW,F]
+  int N = 0, H = 0, W = 0, C = 0, F = 0, KH = 0, KW = 0;
+};
+// out[n,y,x,f] += img[n,y+dy,x+dx,c] * w[f,dy,dx,c] (exprgrad/layers/dnn.nim:45-49) or one of its two
+// adjoints (the written tensor decides which).
+bool match_conv2(const Kernel& k, const ShapeTable& shapes, ConvPattern& c);
+
 }  // namespace egb

@@ -194,6 +194,30 @@ void build_nodes_impl(Model& m, Plan& plan) {
       }
       plan.nodes.push_back(n);
       if (inf.emit_planes) planes[std::make_pair(inf.final_tensor, 0)] = std::make_pair(n.gemm.out_hi, n.gemm.out_mid);
+    } else if (inf.is_conv && !m.strict) {
+      const ConvPattern& cv = inf.conv;
+      Node n;
+      n.kind = Node::CONV;
+      n.conv = cv;
+      n.kernel_index = (int)ki;
+      n.conv_accumulate = !inf.overwrite;
+      if (cv.kind == ConvPattern::FORWARD) {
+        n.label = "conv2 forward -> tensor" + std::to_string(cv.out_tensor - 1);
+        n.conv_a = (const float*)ptrs[cv.img_tensor];
+        n.conv_b = (const float*)ptrs[cv.fil_tensor];
+        n.conv_out = (float*)ptrs[cv.out_tensor];
+      } else if (cv.kind == ConvPattern::D_FILTERS) {
+        n.label = "conv2 d_filters -> tensor" + std::to_string(cv.fil_tensor - 1);
+        n.conv_a = (const float*)ptrs[cv.img_tensor];
+        n.conv_b = (const float*)ptrs[cv.out_tensor];
+        n.conv_out = (float*)ptrs[cv.fil_tensor];
+      } else {
+        n.label = "conv2 d_images -> tensor" + std::to_string(cv.img_tensor - 1);
+        n.conv_a = (const float*)ptrs[cv.out_tensor];
+        n.conv_b = (const float*)ptrs[cv.fil_tensor];
+        n.conv_out = (float*)ptrs[cv.img_tensor];
+      }
+      plan.nodes.push_back(n);
     } else {
       Lowered lw = lower_kernel(k, plan.shapes, ptrs, m.epoch, m.strict, inf.overwrite, ctx.sm_count);
       Node n;
@@ -288,11 +312,17 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
       if (!written.count(r.tensor)) read_first.insert(r.tensor);
     }
     inf.is_gemm = !strict && match_gemm(k, plan->shapes, inf.gemm);
+    inf.is_conv = !strict && !inf.is_gemm && match_conv2(k, plan->shapes, inf.conv) &&
+                  (inf.conv.kind != ConvPattern::D_IMAGES || conv2_dimg_supported(inf.conv.KW));
     const int wt = k.write.tensor;
     const bool fresh = is_fresh(wt);
     bool reads_self = false;
     for (auto& r : k.reads) reads_self = reads_self || r.tensor == wt;
-    inf.overwrite = fresh && !reads_self && (inf.is_gemm || covers_whole_tensor(k, plan->shapes));
+    // a convolution (forward / d_images) produces every element of its output; d_filters accumulates
+    // with atomics and therefore always needs a zeroed destination
+    const bool conv_covers = inf.is_conv && inf.conv.kind != ConvPattern::D_FILTERS;
+    inf.overwrite = fresh && !reads_self && (inf.is_gemm || conv_covers ||
+                                             (!inf.is_conv && covers_whole_tensor(k, plan->shapes)));
     if (prog->tdef(wt).kind == TensorKind::Result && !written.count(wt) && !inf.overwrite) needs_zero.insert(wt);
     written.insert(wt);
     if (inf.is_gemm) {
@@ -483,6 +513,16 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       break;
     case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
     case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st); break;
+    case Node::CONV: {
+      const ConvPattern& cv = n.conv;
+      if (cv.kind == ConvPattern::FORWARD)
+        launch_conv2_fwd(ctx, n.conv_a, n.conv_b, n.conv_out, cv.N, cv.H, cv.W, cv.C, cv.F, cv.KH, cv.KW, n.conv_accumulate, st);
+      else if (cv.kind == ConvPattern::D_FILTERS)
+        launch_conv2_dw(ctx, n.conv_a, n.conv_b, n.conv_out, cv.N, cv.H, cv.W, cv.C, cv.F, cv.KH, cv.KW, st);
+      else
+        launch_conv2_dimg(ctx, n.conv_a, n.conv_b, n.conv_out, cv.N, cv.H, cv.W, cv.C, cv.F, cv.KH, cv.KW, n.conv_accumulate, st);
+      break;
+    }
     case Node::ALLREDUCE:
       // the 256-byte alignment padding between bucket tensors travels with the payload (zeros)
       comm_all_reduce_avg(m.comm, (float*)n.ptr, n.bytes / 4, st);

@@ -30,7 +30,7 @@ struct DevTensor {
 };
 
 struct Node {
-  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, FUSED } kind = INTERP;
+  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV } kind = INTERP;
   std::string label;
   // INTERP
   IpProgram ip;
@@ -45,6 +45,11 @@ struct Node {
   int split_rows = 0, split_cols = 0, split_ld = 0, split_dst_ld = 0, split_act = 0;
   bool split_transpose = false;
   __nv_bfloat16 *split_hi = nullptr, *split_mid = nullptr;
+  // CONV
+  ConvPattern conv;
+  const float *conv_a = nullptr, *conv_b = nullptr;
+  float* conv_out = nullptr;
+  bool conv_accumulate = false;
   // MEMSET / RANDOM / ALLREDUCE
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -58,6 +63,8 @@ struct KernelInfo {
   bool is_gemm = false;
   GemmPattern gemm;
   bool overwrite = false;  // first writer of a zero-initialised result that it covers completely
+  bool is_conv = false;
+  ConvPattern conv;
   // Epilogue fusion: kernels that follow a contraction and only post-process its output element by
   // element (bias add, relu / leakyRelu, their adjoint masks, bias-gradient column sums, the SGD
   // update) run inside the contraction's epilogue instead of as separate launches.

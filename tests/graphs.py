@@ -46,9 +46,9 @@ def xor_net(d, L, rate=0.1, ct="gpu"):
     return [loss.backprop(L.gradient_descent(rate)).target("train", ct)]
 
 
-def conv2_net(d, L, ct="gpu"):
+def conv2_net(d, L, ct="gpu", filters=(4, 3, 3, 3)):
     """benchmarks/conv2 style: NHWC valid convolution forward + backward to filters and images."""
-    img = d.input("img"); w = d.param([4, 3, 3, 3], name="filters")
+    img = d.input("img"); w = d.param(list(filters), name="filters")
     out = L.conv2(img, w)
     loss = d.Fun(); it = d.Iter("it")
     loss[0] += d.sq(out.raw[it])

@@ -150,6 +150,57 @@ def test_conv2_forward_backward(ctx, shape):
     pm.free()
 
 
+@pytest.mark.parametrize("shape,filters", [((2, 20, 150, 3), (64, 3, 3, 3)), ((1, 12, 70, 5), (70, 3, 5, 5)),
+                                           ((3, 9, 9, 1), (8, 2, 2, 1)), ((2, 40, 40, 3), (64, 3, 3, 3))])
+def test_conv2_direct_kernels(ctx, shape, filters):
+    """The dedicated conv2 kernels (csrc/conv2.cu) on shapes that exercise pixel-chunk tails, more than
+    one filter chunk, channel chunks and other filter sizes; U(-2,2) filters like benchmarks/conv2."""
+    om, pm = both("conv2_net", ctx, filters=filters)
+    w = np.random.default_rng(1).uniform(-2, 2, filters).astype(np.float32)
+    sync_params(om, pm, [w])
+    img = np.random.default_rng(0).uniform(0, 1, shape).astype(np.float32)
+    for target in ("conv", "dw", "dimg"):
+        got, ref = pm.call(target, {"img": img}), om.call(target, {"img": img})
+        assert "conv conv2" in pm.describe_plan(), pm.describe_plan()
+        assert_close(got, ref, what=f"{target} {shape} {filters}")
+    pm.free()
+
+
+def test_conv2_full_size_properties(ctx):
+    """BASELINE config 4 at full size (256x224x224x3 images, 64 3x3x3 filters): the oracle would need
+    minutes, so check size-independent properties: an all-ones image turns every output into the
+    filter's tap sum, d_filters of loss = sum(out^2) on that image is 2 * sum(out) per tap, and the
+    first image equals a single-image run checked against the oracle."""
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    import oracle as o
+    from oracle import layers as OL
+    filters = (64, 3, 3, 3)
+    pm = M.compile(*G.conv2_net(F, PL, filters=filters), gpu=ctx, seed=0)
+    w = np.random.default_rng(1).uniform(-2, 2, filters).astype(np.float32)
+    pm.params[pm.params.ids()[0]] = w
+    img = np.ones((256, 224, 224, 3), np.float32)
+    out = pm.call("conv", {"img": img})
+    assert out.shape == (256, 222, 222, 64)
+    taps = w.reshape(64, -1).astype(np.float64).sum(1)
+    assert np.abs(out[::37, ::11, ::13] - taps).max() / np.abs(taps).max() < 1e-5
+    assert np.abs(out[-1, -1, -1] - taps).max() / np.abs(taps).max() < 1e-5
+    dw = pm.call("dw", {"img": img}).astype(np.float64)          # d/dw sum(out^2) = 2 * sum_pixels out[f] * 1
+    want = 2.0 * taps * 256 * 222 * 222
+    assert np.abs(dw - want[:, None, None, None]).max() / np.abs(want).max() < 1e-4
+    dimg = pm.call("dimg", {"img": img})
+    inner = (2.0 * taps[:, None, None, None] * w.astype(np.float64)).sum((0, 1, 2))   # interior pixels see all 9 taps
+    assert np.abs(dimg[5, 100, 100] - inner).max() / np.abs(inner).max() < 1e-4
+    corner = (2.0 * taps * w[:, 0, 0, :].T.astype(np.float64)).sum(1)                 # pixel (0,0) only sees tap (0,0)
+    assert np.abs(dimg[0, 0, 0] - corner).max() / np.abs(inner).max() < 1e-4
+    # one random image against the oracle
+    rnd = np.random.default_rng(0).uniform(0, 1, (1, 224, 224, 3)).astype(np.float32)
+    om = o.compile(*G.conv2_net(o, OL, ct="threads", filters=filters), seed=0)
+    om.params[sorted(om.params)[0]][...] = w
+    for target in ("conv", "dw", "dimg"):
+        assert_close(pm.call(target, {"img": rnd}), om.call(target, {"img": rnd}), what=f"full-width {target}")
+    pm.free()
+
+
 def test_fashion_net_adam_fit(ctx):
     """'next' rows: conv + leakyRelu + maxpool2 (customGrad) + reshape + dense + softmax + adam with
     caches and epoch(), trained with Model.fit over two epochs."""
