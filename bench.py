@@ -353,6 +353,71 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None):
     return out
 
 
+# ------------------------------------------------------------------------------ conv2 forward + backward
+CONV_IMG = (256, 224, 224, 3)
+CONV_FIL = (64, 3, 3, 3)
+CONV_NAME = "benchmarks/conv2: NHWC 256x224x224x3 images, 64 3x3x3 filters, valid, fp32 forward + d_filters + d_images (BASELINE configs[3])"
+
+
+def run_conv2(args, ctx, timer, rank, world):
+    """Times the three conv2 kernels inside their targets (forward; loss=sum(out^2) -> d_filters, d_images)."""
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, gpu as G, layers as PL
+    peaks = load_peaks()
+    model = eg.compile(*GR.conv2_net(F, PL, filters=CONV_FIL), gpu=ctx, seed=0)
+    w = np.random.default_rng(1).uniform(-2, 2, CONV_FIL).astype(np.float32)   # conv2.nim:337-338 ranges
+    model.params[model.params.ids()[0]] = w
+    n, h, wd, c = CONV_IMG
+    f, kh, kw, _ = CONV_FIL
+    oh, ow = h - kh + 1, wd - kw + 1
+    himg = G.pinned_empty(CONV_IMG)
+    himg[...] = np.random.default_rng(0).uniform(0, 1, CONV_IMG).astype(np.float32)
+    dimg = eg.alloc_tensor(ctx, CONV_IMG)
+    dimg.write(himg)
+    out_bytes, in_bytes = n * oh * ow * f * 4, n * h * wd * c * 4
+    flop = 2.0 * n * oh * ow * f * kh * kw * c
+    res = {}
+    steps = max(3, min(args.steps, 10))
+    for target, alg_bytes in (("conv", in_bytes + out_bytes), ("dw", in_bytes + out_bytes), ("dimg", out_bytes + in_bytes)):
+        fn = lambda: model.apply(target, {"img": dimg}, sync=False)
+        fn(); ctx.synchronize()
+        ms, _ = timer.run(fn, steps, 2)
+        G.set_timing(ctx, True)
+        for _ in range(steps):
+            fn()
+        k_ms, k_n = G.kernel_time(ctx, "conv")
+        all_ms, _ = G.kernel_time(ctx, "all")
+        G.set_timing(ctx, False)
+        # every target re-runs the forward convolution first; the kernel of interest is the last conv launch
+        per_target = int(round(k_n / steps))
+        res[target] = {"target_ms": ms / steps, "conv_kernels_per_run": per_target, "conv_kernels_ms": k_ms / steps,
+                       "all_kernels_ms": all_ms / steps, "algorithmic_bytes": alg_bytes}
+    fwd_ms = res["conv"]["conv_kernels_ms"]
+    dw_ms = res["dw"]["conv_kernels_ms"] - fwd_ms
+    di_ms = res["dimg"]["conv_kernels_ms"] - fwd_ms
+    e2e_fn = lambda: model.call("conv", {"img": himg})
+    e2e_ms, _ = timer.run(e2e_fn, 2, 1)
+    kern = {"forward": fwd_ms, "d_filters": dw_ms, "d_images": di_ms}
+    total = fwd_ms + dw_ms + di_ms
+    out = {"metric": "conv2_fwd_bwd_images_per_s", "value": world * n / (total * 1e-3), "unit": "images/s",
+           "n_gpus": world, "ms_per_step": total, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+           "data": "synthetic", "config": {"workload": CONV_NAME, "parallelism": f"replicas x{world}"},
+           "kernels_ms": kern,
+           "roofline": {"bound": "hbm", "kernel": "conv2_fwd_kernel / conv2_dw_kernel / conv2_dimg_kernel",
+                        "achieved": 3 * (in_bytes + out_bytes) / (total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": 3 * (in_bytes + out_bytes) / (total * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                        "per_kernel_frac": {k: (in_bytes + out_bytes) / (v * 1e-3) / 1e9 / peaks["hbm_gbs"] for k, v in kern.items()},
+                        "tflops_fp32": {k: flop / (v * 1e-3) / 1e12 for k, v in kern.items()},
+                        "peak_source": peaks["source"]},
+           "targets": res,
+           "e2e": {"value": world * n / (e2e_ms / 2 * 1e-3), "unit": "images/s (forward only)", "h2d_bytes_per_step": in_bytes,
+                   "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / 2,
+                   "api": "model.call('conv', {img}) with a pinned host image batch; D2H of the 3.2 GB output"}}
+    model.free()
+    dimg.buffer.dealloc()
+    return out
+
+
 # ------------------------------------------------------------------------------ entry points
 def run_reference(args, rank, world):
     if rank != 0:
@@ -384,7 +449,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="matmul", choices=["matmul", "dense"])
+    ap.add_argument("--workload", default="matmul", choices=["matmul", "dense", "conv2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense_train block of the matmul line")
     args = ap.parse_args()
@@ -414,6 +479,11 @@ def main():
         out = run_matmul(args, ctx, timer, rank, world, sampler)
         if not args.no_dense:
             out["dense_train"] = run_dense(args, ctx, timer, rank, world, comm)
+    elif args.workload == "conv2":
+        out = run_conv2(args, ctx, timer, rank, world)
+        out["warmup"] = args.warmup
+        out["vs_baseline"] = None
+        out["clocks"] = sampler.stop() if sampler else None
     else:
         out = run_dense(args, ctx, timer, rank, world, comm, sampler)
         out["warmup"] = args.warmup
@@ -424,7 +494,7 @@ def main():
                 out["cpu_baseline"], _ = cpu_matmul_sample()
                 if "dense_train" in out:
                     out["dense_train"]["cpu_baseline"], _ = cpu_dense_sample()
-            else:
+            elif args.workload == "dense":
                 out["cpu_baseline"], _ = cpu_dense_sample()
         print(json.dumps(out), flush=True)
     if comm is not None:

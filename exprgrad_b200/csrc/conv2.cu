@@ -19,7 +19,6 @@ namespace egb {
 namespace {
 
 constexpr int FC = 64;        // filters per chunk
-constexpr int TX_FWD = 128;   // output pixels per block (forward)
 constexpr int TX_BWD = 64;    // pixels per block (both adjoint kernels)
 constexpr int MAX_CC = 4;     // channels per pass
 
@@ -28,98 +27,122 @@ struct ConvDims {
 };
 
 // ------------------------------------------------------------------ forward
-// block: 256 threads = 8 filter groups (8 filters each) x 32 pixel quads (4 consecutive x each).
+// block: 8 filter groups (8 filters each) x TQ pixel quads (4 consecutive x each), TQ <= 32 chosen by
+// the host so that the strips divide the output row evenly. A block walks ROWS_FWD consecutive output
+// rows of its strip: the filter bank is staged once, the KH input rows live in a ring buffer so that
+// every new output row stages only one new input row.
+constexpr int ROWS_FWD = 8;
+
 template <int KW_T>
 __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                                        float* __restrict__ out, ConvDims d, int accumulate) {
+                                                        float* __restrict__ out, ConvDims d, int accumulate, int tq_n) {
   extern __shared__ float smem[];
   pdl_launch_dependents();
   pdl_wait();
   const int KW = KW_T > 0 ? KW_T : d.KW;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   const int tx = tid & 7, tq = tid >> 3;
   const int fchunks = (d.F + FC - 1) / FC;
   const int n = blockIdx.z / fchunks, f0 = (blockIdx.z % fchunks) * FC;
-  const int y = blockIdx.y, x0 = blockIdx.x * TX_FWD;
-  const int in_w = TX_FWD + KW - 1;                 // staged input pixels per row
-  float* in_s = smem;                               // [KH][in_w * cc]
+  const int y0 = blockIdx.y * ROWS_FWD, x0 = blockIdx.x * tq_n * 4;
+  const int y1 = min(y0 + ROWS_FWD, d.OH);
+  const int in_w = tq_n * 4 + KW - 1;               // staged input pixels per row
+  float* in_s = smem;                               // ring: [KH][in_w * cc]
   float* w_s = smem + d.KH * in_w * MAX_CC;         // [KH*KW*cc][FC]
-  float acc[4][8];
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[p][j] = 0.0f;
+  const int fb = f0 + tx * 8;
+  const bool vec = (d.F & 3) == 0 && fb + 8 <= d.F;
 
   for (int c0 = 0; c0 < d.C; c0 += MAX_CC) {
     const int cc = min(MAX_CC, d.C - c0);
+    const int row_len = in_w * cc;
     __syncthreads();
-    for (int i = tid; i < d.KH * in_w * cc; i += 256) {
-      const int dy = i / (in_w * cc), r = i % (in_w * cc);
-      const int px = r / cc, ch = r % cc;
-      const int gx = x0 + px;
-      in_s[i] = gx < d.W ? __ldg(img + (((size_t)n * d.H + y + dy) * d.W + gx) * d.C + c0 + ch) : 0.0f;
-    }
-    for (int i = tid; i < d.KH * KW * cc * FC; i += 256) {
+    for (int i = tid; i < d.KH * KW * cc * FC; i += nthreads) {
       const int f = i % FC, k = i / FC;
       const int ch = k % cc, dx = (k / cc) % KW, dy = k / (cc * KW);
       w_s[i] = (f0 + f) < d.F ? __ldg(w + (((size_t)(f0 + f) * d.KH + dy) * KW + dx) * d.C + c0 + ch) : 0.0f;
     }
-    __syncthreads();
-    for (int dy = 0; dy < d.KH; ++dy) {
-      const float* row = in_s + dy * in_w * cc + tq * 4 * cc;
-      if (KW_T > 0) {
-        for (int ch = 0; ch < cc; ++ch) {
-          float iv[4 + (KW_T > 0 ? KW_T : 1) - 1];
-#pragma unroll
-          for (int t = 0; t < 4 + KW_T - 1; ++t) iv[t] = row[t * cc + ch];
-#pragma unroll
-          for (int dx = 0; dx < KW_T; ++dx) {
-            const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW_T + dx) * cc + ch) * FC + tx * 8);
-            const float4 w0 = wp[0], w1 = wp[1];
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv[p + dx], wv[j], acc[p][j]);
+    for (int y = y0; y < y1; ++y) {
+      // stage input rows y .. y+KH-1 into ring slots (row % KH); after the first output row only the
+      // newest input row is missing
+      __syncthreads();
+      for (int r = (y == y0 ? 0 : d.KH - 1); r < d.KH; ++r) {
+        const int iy = y + r;
+        float* dst = in_s + (iy % d.KH) * row_len;
+        const float* src = img + (((size_t)n * d.H + iy) * d.W + x0) * d.C + c0;
+        if (cc == d.C) {
+          const int valid = min(in_w, d.W - x0) * cc;   // contiguous run
+          for (int j = tid; j < row_len; j += nthreads) dst[j] = j < valid ? __ldg(src + j) : 0.0f;
+        } else {
+          for (int j = tid; j < row_len; j += nthreads) {
+            const int px = j / cc, ch = j % cc;
+            dst[j] = (x0 + px) < d.W ? __ldg(src + (size_t)px * d.C + ch) : 0.0f;
           }
         }
-      } else {
-        for (int dx = 0; dx < KW; ++dx)
-          for (int ch = 0; ch < cc; ++ch) {
-            const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW + dx) * cc + ch) * FC + tx * 8);
-            const float4 w0 = wp[0], w1 = wp[1];
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      }
+      __syncthreads();
+      float acc[4][8];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const float iv = row[(p + dx) * cc + ch];
+      for (int p = 0; p < 4; ++p)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv, wv[j], acc[p][j]);
+        for (int j = 0; j < 8; ++j) acc[p][j] = 0.0f;
+      if (tq < tq_n) {
+        for (int dy = 0; dy < d.KH; ++dy) {
+          const float* row = in_s + ((y + dy) % d.KH) * row_len + tq * 4 * cc;
+          if (KW_T > 0) {
+            for (int ch = 0; ch < cc; ++ch) {
+              float iv[4 + (KW_T > 0 ? KW_T : 1) - 1];
+#pragma unroll
+              for (int t = 0; t < 4 + KW_T - 1; ++t) iv[t] = row[t * cc + ch];
+#pragma unroll
+              for (int dx = 0; dx < KW_T; ++dx) {
+                const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW_T + dx) * cc + ch) * FC + tx * 8);
+                const float4 w0 = wp[0], w1 = wp[1];
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv[p + dx], wv[j], acc[p][j]);
+              }
             }
+          } else {
+            for (int dx = 0; dx < KW; ++dx)
+              for (int ch = 0; ch < cc; ++ch) {
+                const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW + dx) * cc + ch) * FC + tx * 8);
+                const float4 w0 = wp[0], w1 = wp[1];
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                  const float iv = row[(p + dx) * cc + ch];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv, wv[j], acc[p][j]);
+                }
+              }
           }
-      }
-    }
-  }
-  const int fb = f0 + tx * 8;
-  const bool vec = (d.F & 3) == 0 && fb + 8 <= d.F;
+        }
+        // channel chunks after the first accumulate into what the first one stored
+        const bool acc_out = accumulate || c0 > 0;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int x = x0 + tq * 4 + p;
-    if (x >= d.OW) continue;
-    float* o = out + (((size_t)n * d.OH + y) * d.OW + x) * d.F + fb;
-    if (vec) {
-      float4 a = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
-      float4 b = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
-      if (accumulate) {
-        const float4 oa = *reinterpret_cast<const float4*>(o), ob = *reinterpret_cast<const float4*>(o + 4);
-        a.x += oa.x; a.y += oa.y; a.z += oa.z; a.w += oa.w;
-        b.x += ob.x; b.y += ob.y; b.z += ob.z; b.w += ob.w;
-      }
-      *reinterpret_cast<float4*>(o) = a;
-      *reinterpret_cast<float4*>(o + 4) = b;
-    } else {
+        for (int p = 0; p < 4; ++p) {
+          const int x = x0 + tq * 4 + p;
+          if (x >= d.OW) continue;
+          float* o = out + (((size_t)n * d.OH + y) * d.OW + x) * d.F + fb;
+          if (vec) {
+            float4 a = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+            float4 b = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+            if (acc_out) {
+              const float4 oa = *reinterpret_cast<const float4*>(o), ob = *reinterpret_cast<const float4*>(o + 4);
+              a.x += oa.x; a.y += oa.y; a.z += oa.z; a.w += oa.w;
+              b.x += ob.x; b.y += ob.y; b.z += ob.z; b.w += ob.w;
+            }
+            *reinterpret_cast<float4*>(o) = a;
+            *reinterpret_cast<float4*>(o + 4) = b;
+          } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (fb + j < d.F) o[j] = accumulate ? o[j] + acc[p][j] : acc[p][j];
+            for (int j = 0; j < 8; ++j)
+              if (fb + j < d.F) o[j] = acc_out ? o[j] + acc[p][j] : acc[p][j];
+          }
+        }
+      }
     }
   }
 }
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
 // (k = kc*32 + kg + 4*i) in registers over all its work items, the block reduces the 4 pixel sets
 // through shared memory and flushes once with atomicAdd.
 __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__ img, const float* __restrict__ dout,
-                                                       float* __restrict__ dw, ConvDims d) {
+                                                       float* __restrict__ dw, ConvDims d, int txw) {
   extern __shared__ float smem[];
   pdl_launch_dependents();
   pdl_wait();
@@ -139,8 +162,8 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
   const int kc = blockIdx.y % kchunks, f0 = (blockIdx.y / kchunks) * FC;
   const int tid = threadIdx.x;
   const int ps = tid >> 6, r = tid & 63, fg = r & 15, kg = r >> 4;
-  const int in_w = (TX_BWD + d.KW - 1) * d.C;       // staged floats per input row (all channels)
-  float* dout_s = smem;                              // [TX_BWD][FC]
+  const int in_w = (txw + d.KW - 1) * d.C;          // staged floats per input row (all channels)
+  float* dout_s = smem;                              // [txw][FC]
   float* img_s = smem + TX_BWD * FC;                 // [KH][in_w]
   (void)fchunks;
   int koff[8];
@@ -159,15 +182,15 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  const int xchunks = (d.OW + TX_BWD - 1) / TX_BWD;
+  const int xchunks = (d.OW + txw - 1) / txw;
   const long items = (long)d.N * d.OH * xchunks;
   for (long it = blockIdx.x; it < items; it += gridDim.x) {
     const int xc = (int)(it % xchunks);
     const int y = (int)((it / xchunks) % d.OH);
     const int n = (int)(it / ((long)xchunks * d.OH));
-    const int x0 = xc * TX_BWD;
+    const int x0 = xc * txw;
     __syncthreads();
-    for (int i = tid; i < TX_BWD * (FC / 4); i += 256) {
+    for (int i = tid; i < txw * (FC / 4); i += 256) {
       const int px = i / (FC / 4), f4 = (i % (FC / 4)) * 4;
       const int x = x0 + px;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -190,7 +213,7 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
       img_s[i] = gx < d.W ? __ldg(img + (((size_t)n * d.H + y + dy) * d.W + x0) * d.C + rr) : 0.0f;
     }
     __syncthreads();
-    const int npx = min(TX_BWD, d.OW - x0);
+    const int npx = min(txw, d.OW - x0);
     for (int px = ps; px < npx; px += 4) {
       const float4 dv = *reinterpret_cast<const float4*>(dout_s + px * FC + fg * 4);
 #pragma unroll
@@ -229,98 +252,115 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------ d_images
-// block = (n, input row iy, strip of 64 input pixels). 256 threads = 16 pixel quads x 16 filter slices
-// (4 filters each); a thread gathers, for its 4 pixels and up to 4 channels, the contributions of its
-// 4 filters over all (dy, dx); the 16 slices are combined with xor-shuffles.
+// block = (n, ROWS_DIMG consecutive input rows, strip of TQ*4 input pixels); threads = TQ pixel quads x
+// 16 filter slices (4 filters each). The KH rows of dout that feed an input row live in a ring buffer,
+// so every new input row stages one new dout row. A thread gathers, for its 4 pixels and up to 4
+// channels, the contributions of its 4 filters over all (dy, dx); the 16 slices are combined with
+// xor-shuffles.
+constexpr int ROWS_DIMG = 8;
+
 template <int KW_T>
 __global__ void __launch_bounds__(256) conv2_dimg_kernel(const float* __restrict__ dout, const float* __restrict__ w,
-                                                         float* __restrict__ dimg, ConvDims d, int accumulate) {
+                                                         float* __restrict__ dimg, ConvDims d, int accumulate, int tq_n) {
   extern __shared__ float smem[];
   pdl_launch_dependents();
   pdl_wait();
   constexpr int KW = KW_T;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   const int q = tid >> 4, fs = tid & 15;
-  const int n = blockIdx.z, iy = blockIdx.y, ix0 = blockIdx.x * TX_BWD;
-  const int tw = TX_BWD + KW - 1;                    // staged dout pixels per row
-  float* dout_s = smem;                              // [KH][tw][FC]
-  float* w_s = smem + d.KH * tw * FC;                // [KH][KW][FC][4 channels]
+  const int n = blockIdx.z, iy0 = blockIdx.y * ROWS_DIMG, ix0 = blockIdx.x * tq_n * 4;
+  const int iy1 = min(iy0 + ROWS_DIMG, d.H);
+  const int tw = tq_n * 4 + KW - 1;                  // staged dout pixels per row
+  float* dout_s = smem;                              // ring: [KH][tw][FC]
+  float* w_s = smem + d.KH * tw * FC;                // [KH][KW][4 filters of a slice][16 slices][4 channels]
   const int fchunks = (d.F + FC - 1) / FC;
   for (int c0 = 0; c0 < d.C; c0 += MAX_CC) {
     const int cc = min(MAX_CC, d.C - c0);
-    float acc[4][MAX_CC];
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int c = 0; c < MAX_CC; ++c) acc[p][c] = 0.0f;
     for (int fchunk = 0; fchunk < fchunks; ++fchunk) {
       const int f0 = fchunk * FC;
       __syncthreads();
-      // dout rows iy-dy, pixels ix0-(KW-1) .. ix0+63
-      for (int i = tid; i < d.KH * tw * (FC / 4); i += 256) {
-        const int f4 = (i % (FC / 4)) * 4, t = (i / (FC / 4)) % tw, dy = i / ((FC / 4) * tw);
-        const int oy = iy - dy, ox = ix0 - (KW - 1) + t;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (oy >= 0 && oy < d.OH && ox >= 0 && ox < d.OW) {
-          const float* src = dout + (((size_t)n * d.OH + oy) * d.OW + ox) * d.F + f0 + f4;
-          if ((d.F & 3) == 0 && f0 + f4 + 4 <= d.F) {
-            v = __ldg(reinterpret_cast<const float4*>(src));
-          } else {
-            if (f0 + f4 + 0 < d.F) v.x = __ldg(src + 0);
-            if (f0 + f4 + 1 < d.F) v.y = __ldg(src + 1);
-            if (f0 + f4 + 2 < d.F) v.z = __ldg(src + 2);
-            if (f0 + f4 + 3 < d.F) v.w = __ldg(src + 3);
+      for (int i = tid; i < d.KH * KW * FC * MAX_CC; i += nthreads) {
+        const int c = i % MAX_CC, sl = (i / MAX_CC) % 16, j = (i / (MAX_CC * 16)) % 4;
+        const int dx = (i / (MAX_CC * FC)) % KW, dy = i / (MAX_CC * FC * KW);
+        const int f = f0 + sl * 4 + j;
+        w_s[i] = (c < cc && f < d.F) ? __ldg(w + (((size_t)f * d.KH + dy) * KW + dx) * d.C + c0 + c) : 0.0f;
+      }
+      for (int iy = iy0; iy < iy1; ++iy) {
+        // ring slot of dout row oy is oy mod KH; rows iy-KH+1 .. iy are needed, only row iy is new
+        __syncthreads();
+        for (int r = (iy == iy0 ? 0 : d.KH - 1); r < d.KH; ++r) {
+          const int oy = iy - (d.KH - 1) + r;
+          float* dst = dout_s + (((oy % d.KH) + d.KH) % d.KH) * tw * FC;
+          const bool row_ok = oy >= 0 && oy < d.OH;
+          for (int i = tid; i < tw * (FC / 4); i += nthreads) {
+            const int f4 = (i % (FC / 4)) * 4, t = i / (FC / 4);
+            const int ox = ix0 - (KW - 1) + t;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok && ox >= 0 && ox < d.OW) {
+              const float* src = dout + (((size_t)n * d.OH + oy) * d.OW + ox) * d.F + f0 + f4;
+              if ((d.F & 3) == 0 && f0 + f4 + 4 <= d.F) {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+              } else {
+                if (f0 + f4 + 0 < d.F) v.x = __ldg(src + 0);
+                if (f0 + f4 + 1 < d.F) v.y = __ldg(src + 1);
+                if (f0 + f4 + 2 < d.F) v.z = __ldg(src + 2);
+                if (f0 + f4 + 3 < d.F) v.w = __ldg(src + 3);
+              }
+            }
+            *reinterpret_cast<float4*>(dst + t * FC + f4) = v;
           }
         }
-        *reinterpret_cast<float4*>(dout_s + (dy * tw + t) * FC + f4) = v;
-      }
-      for (int i = tid; i < d.KH * KW * FC * MAX_CC; i += 256) {
-        const int c = i % MAX_CC, f = (i / MAX_CC) % FC, dx = (i / (MAX_CC * FC)) % KW, dy = i / (MAX_CC * FC * KW);
-        w_s[i] = (c < cc && f0 + f < d.F) ? __ldg(w + (((size_t)(f0 + f) * d.KH + dy) * KW + dx) * d.C + c0 + c) : 0.0f;
-      }
-      __syncthreads();
-      for (int dy = 0; dy < d.KH; ++dy) {
-        // pixel ix = ix0 + q*4 + p receives dout[.., ix - dx, ..]: staged column t = q*4 + p - dx + KW-1
-        float4 e[4 + KW - 1];
+        __syncthreads();
+        float acc[4][MAX_CC];
 #pragma unroll
-        for (int t = 0; t < 4 + KW - 1; ++t)
-          e[t] = *reinterpret_cast<const float4*>(dout_s + (dy * tw + q * 4 + t) * FC + fs * 4);
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int dx = 0; dx < KW; ++dx) {
-          const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW + dx) * FC + fs * 4) * MAX_CC);
-          const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];  // filters fs*4+0..3, 4 channels each
+          for (int c = 0; c < MAX_CC; ++c) acc[p][c] = 0.0f;
+        for (int dy = 0; dy < d.KH; ++dy) {
+          const int oy = iy - dy;
+          const float* rowp = dout_s + (((oy % d.KH) + d.KH) % d.KH) * tw * FC;
+          // pixel ix = ix0 + q*4 + p receives dout[.., ix - dx, ..]: staged column t = q*4 + p - dx + KW-1
+          float4 e[4 + KW - 1];
+#pragma unroll
+          for (int t = 0; t < 4 + KW - 1; ++t) e[t] = *reinterpret_cast<const float4*>(rowp + (q * 4 + t) * FC + fs * 4);
+#pragma unroll
+          for (int dx = 0; dx < KW; ++dx) {
+            const float4* wp = reinterpret_cast<const float4*>(w_s + (size_t)(dy * KW + dx) * FC * MAX_CC) + fs;
+            const float4 w0 = wp[0], w1 = wp[16], w2 = wp[32], w3 = wp[48];  // filters fs*4+0..3, 4 channels each
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const float4 ev = e[p - dx + KW - 1];
+              acc[p][0] = fmaf(ev.x, w0.x, fmaf(ev.y, w1.x, fmaf(ev.z, w2.x, fmaf(ev.w, w3.x, acc[p][0]))));
+              acc[p][1] = fmaf(ev.x, w0.y, fmaf(ev.y, w1.y, fmaf(ev.z, w2.y, fmaf(ev.w, w3.y, acc[p][1]))));
+              acc[p][2] = fmaf(ev.x, w0.z, fmaf(ev.y, w1.z, fmaf(ev.z, w2.z, fmaf(ev.w, w3.z, acc[p][2]))));
+              acc[p][3] = fmaf(ev.x, w0.w, fmaf(ev.y, w1.w, fmaf(ev.z, w2.w, fmaf(ev.w, w3.w, acc[p][3]))));
+            }
+          }
+        }
+        // combine the 16 filter slices (lanes differing in the low 4 bits)
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int c = 0; c < MAX_CC; ++c) {
+            float v = acc[p][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            acc[p][c] = v;
+          }
+        if (fs == 0) {
+          const bool acc_out = accumulate || fchunk > 0;   // later filter chunks add to the first one's result
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            const float4 ev = e[p - dx + KW - 1];
-            acc[p][0] = fmaf(ev.x, w0.x, fmaf(ev.y, w1.x, fmaf(ev.z, w2.x, fmaf(ev.w, w3.x, acc[p][0]))));
-            acc[p][1] = fmaf(ev.x, w0.y, fmaf(ev.y, w1.y, fmaf(ev.z, w2.y, fmaf(ev.w, w3.y, acc[p][1]))));
-            acc[p][2] = fmaf(ev.x, w0.z, fmaf(ev.y, w1.z, fmaf(ev.z, w2.z, fmaf(ev.w, w3.z, acc[p][2]))));
-            acc[p][3] = fmaf(ev.x, w0.w, fmaf(ev.y, w1.w, fmaf(ev.z, w2.w, fmaf(ev.w, w3.w, acc[p][3]))));
+            const int ix = ix0 + q * 4 + p;
+            if (ix >= d.W) continue;
+            float* o = dimg + (((size_t)n * d.H + iy) * d.W + ix) * d.C + c0;
+#pragma unroll
+            for (int c = 0; c < MAX_CC; ++c)
+              if (c < cc) o[c] = acc_out ? o[c] + acc[p][c] : acc[p][c];
           }
         }
-      }
-    }
-    // combine the 16 filter slices (lanes differing in the low 4 bits)
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int c = 0; c < MAX_CC; ++c) {
-        float v = acc[p][c];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        acc[p][c] = v;
-      }
-    if (fs == 0) {
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int ix = ix0 + q * 4 + p;
-        if (ix >= d.W) continue;
-        float* o = dimg + (((size_t)n * d.H + iy) * d.W + ix) * d.C + c0;
-#pragma unroll
-        for (int c = 0; c < MAX_CC; ++c)
-          if (c < cc) o[c] = accumulate ? o[c] + acc[p][c] : acc[p][c];
       }
     }
   }
@@ -335,20 +375,29 @@ void check_dims(const ConvDims& d) {
 
 }  // namespace
 
+// Pixel quads per block: the smallest block count that covers the row, then the smallest strip that
+// still covers it with that many blocks (e.g. OW = 222 -> 2 strips of 28 quads instead of 32 + 24).
+static int quads_per_block(int pixels, int max_quads) {
+  const int quads = (pixels + 3) / 4;
+  const int blocks = (quads + max_quads - 1) / max_quads;
+  return (quads + blocks - 1) / blocks;
+}
+
 void launch_conv2_fwd(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
                       int KH, int KW, bool accumulate, cudaStream_t st) {
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
   const int cc = C < MAX_CC ? C : MAX_CC;
-  const size_t smem = ((size_t)KH * (TX_FWD + KW - 1) * MAX_CC + (size_t)KH * KW * cc * FC) * sizeof(float);
-  dim3 grid((d.OW + TX_FWD - 1) / TX_FWD, d.OH, N * ((F + FC - 1) / FC));
+  const int tq = quads_per_block(d.OW, 32);
+  const size_t smem = ((size_t)KH * (tq * 4 + KW - 1) * MAX_CC + (size_t)KH * KW * cc * FC) * sizeof(float);
+  dim3 grid((d.OW + tq * 4 - 1) / (tq * 4), (d.OH + ROWS_FWD - 1) / ROWS_FWD, N * ((F + FC - 1) / FC));
   Launch l(ctx, KC_CONV, st);
   if (KW == 3) {
     EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_kernel(ctx, conv2_fwd_kernel<3>, grid, dim3(256), smem, st, img, w, out, d, accumulate ? 1 : 0);
+    launch_kernel(ctx, conv2_fwd_kernel<3>, grid, dim3(tq * 8), smem, st, img, w, out, d, accumulate ? 1 : 0, tq);
   } else {
     EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_kernel(ctx, conv2_fwd_kernel<0>, grid, dim3(256), smem, st, img, w, out, d, accumulate ? 1 : 0);
+    launch_kernel(ctx, conv2_fwd_kernel<0>, grid, dim3(tq * 8), smem, st, img, w, out, d, accumulate ? 1 : 0, tq);
   }
 }
 
@@ -357,25 +406,27 @@ void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* d
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
   const int K = KH * KW * C;
-  const size_t stage = ((size_t)TX_BWD * FC + (size_t)KH * (TX_BWD + KW - 1) * C) * sizeof(float);
+  const int txw = quads_per_block(d.OW, TX_BWD / 4) * 4;   // even chunks of the output row, <= 64 pixels
+  const size_t stage = ((size_t)TX_BWD * FC + (size_t)KH * (txw + KW - 1) * C) * sizeof(float);
   const size_t red = (size_t)4 * 64 * 33 * sizeof(float);
   const size_t smem = stage > red ? stage : red;
-  dim3 grid(ctx.sm_count * 2, ((K + 31) / 32) * ((F + FC - 1) / FC));
+  dim3 grid(ctx.sm_count * 3, ((K + 31) / 32) * ((F + FC - 1) / FC));
   EGB_CUDA(cudaFuncSetAttribute(conv2_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   Launch l(ctx, KC_CONV, st);
-  launch_kernel(ctx, conv2_dw_kernel, grid, dim3(256), smem, st, img, dout, dw, d);
+  launch_kernel(ctx, conv2_dw_kernel, grid, dim3(256), smem, st, img, dout, dw, d, txw);
 }
 
 void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* dimg, int N, int H, int W, int C, int F,
                        int KH, int KW, bool accumulate, cudaStream_t st) {
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
-  const size_t smem = ((size_t)KH * (TX_BWD + KW - 1) * FC + (size_t)KH * KW * FC * MAX_CC) * sizeof(float);
-  dim3 grid((W + TX_BWD - 1) / TX_BWD, H, N);
+  const int tq = quads_per_block(W, 16);
+  const size_t smem = ((size_t)KH * (tq * 4 + KW - 1) * FC + (size_t)KH * KW * FC * MAX_CC) * sizeof(float);
+  dim3 grid((W + tq * 4 - 1) / (tq * 4), (H + ROWS_DIMG - 1) / ROWS_DIMG, N);
   Launch l(ctx, KC_CONV, st);
 #define EGB_DIMG(KWT)                                                                                       \
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_kernel<KWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-  launch_kernel(ctx, conv2_dimg_kernel<KWT>, grid, dim3(256), smem, st, dout, w, dimg, d, accumulate ? 1 : 0);
+  launch_kernel(ctx, conv2_dimg_kernel<KWT>, grid, dim3(tq * 16), smem, st, dout, w, dimg, d, accumulate ? 1 : 0, tq);
   switch (KW) {
     case 1: EGB_DIMG(1) break;
     case 2: EGB_DIMG(2) break;
