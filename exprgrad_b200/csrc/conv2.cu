@@ -163,8 +163,6 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
   const int tid = threadIdx.x;
   const int ps = tid >> 6, r = tid & 63, fg = r & 15, kg = r >> 4;
   const int in_w = (txw + d.KW - 1) * d.C;          // staged floats per input row (all channels)
-  float* dout_s = smem;                              // [txw][FC]
-  float* img_s = smem + TX_BWD * FC;                 // [KH][in_w]
   (void)fchunks;
   int koff[8];
   bool kval[8];
@@ -184,47 +182,68 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
 
   const int xchunks = (d.OW + txw - 1) / txw;
   const long items = (long)d.N * d.OH * xchunks;
-  for (long it = blockIdx.x; it < items; it += gridDim.x) {
+  const int buf_floats = (TX_BWD * FC + d.KH * in_w + 3) & ~3;   // one staging buffer: dout tile + input rows
+  const bool f_vec = (d.F & 3) == 0;
+  // cp.async double buffering: the tile of work item i+1 streams in while item i is being reduced
+  auto stage = [&](long it, int buf) {
     const int xc = (int)(it % xchunks);
     const int y = (int)((it / xchunks) % d.OH);
     const int n = (int)(it / ((long)xchunks * d.OH));
     const int x0 = xc * txw;
-    __syncthreads();
+    float* dsm = smem + buf * buf_floats;
+    float* ism = dsm + TX_BWD * FC;
     for (int i = tid; i < txw * (FC / 4); i += 256) {
       const int px = i / (FC / 4), f4 = (i % (FC / 4)) * 4;
       const int x = x0 + px;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (x < d.OW) {
-        const float* src = dout + (((size_t)n * d.OH + y) * d.OW + x) * d.F + f0 + f4;
-        if ((d.F & 3) == 0 && f0 + f4 + 4 <= d.F) {
-          v = __ldg(reinterpret_cast<const float4*>(src));
-        } else {
-          if (f0 + f4 + 0 < d.F) v.x = __ldg(src + 0);
-          if (f0 + f4 + 1 < d.F) v.y = __ldg(src + 1);
-          if (f0 + f4 + 2 < d.F) v.z = __ldg(src + 2);
-          if (f0 + f4 + 3 < d.F) v.w = __ldg(src + 3);
-        }
+      float* dst = dsm + px * FC + f4;
+      const float* src = dout + (((size_t)n * d.OH + y) * d.OW + min(x, d.OW - 1)) * d.F + f0 + f4;
+      if (f_vec && f0 + f4 + 4 <= d.F) {
+        const unsigned bytes = x < d.OW ? 16u : 0u;   // zero-fill outside the row
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
+                     "r"(bytes) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = (x < d.OW && f0 + f4 + j < d.F) ? __ldg(src + j) : 0.0f;
       }
-      *reinterpret_cast<float4*>(dout_s + px * FC + f4) = v;
     }
     for (int i = tid; i < d.KH * in_w; i += 256) {
       const int dy = i / in_w, rr = i % in_w;
       const int gx = x0 + rr / d.C;
-      img_s[i] = gx < d.W ? __ldg(img + (((size_t)n * d.H + y + dy) * d.W + x0) * d.C + rr) : 0.0f;
+      const float* src = img + (((size_t)n * d.H + y + dy) * d.W + x0) * d.C + (gx < d.W ? rr : 0);
+      const unsigned bytes = gx < d.W ? 4u : 0u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(ism + i)), "l"(src),
+                   "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if ((long)blockIdx.x < items) stage(blockIdx.x, 0);
+  for (long it = blockIdx.x; it < items; it += gridDim.x) {
+    const long next = it + gridDim.x;
+    if (next < items) {
+      stage(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* dout_c = smem + buf * buf_floats;
+    const float* img_c = dout_c + TX_BWD * FC;
+    const int x0 = (int)(it % xchunks) * txw;
     const int npx = min(txw, d.OW - x0);
     for (int px = ps; px < npx; px += 4) {
-      const float4 dv = *reinterpret_cast<const float4*>(dout_s + px * FC + fg * 4);
+      const float4 dv = *reinterpret_cast<const float4*>(dout_c + px * FC + fg * 4);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float iv = img_s[koff[i] + px * d.C];
+        const float iv = img_c[koff[i] + px * d.C];
         acc[i][0] = fmaf(iv, dv.x, acc[i][0]);
         acc[i][1] = fmaf(iv, dv.y, acc[i][1]);
         acc[i][2] = fmaf(iv, dv.z, acc[i][2]);
         acc[i][3] = fmaf(iv, dv.w, acc[i][3]);
       }
     }
+    __syncthreads();   // everyone is done with this buffer before it is refilled
+    buf ^= 1;
   }
   // reduce the 4 pixel sets, then one atomic per (filter, tap) and block
   __syncthreads();
@@ -407,7 +426,7 @@ void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* d
   check_dims(d);
   const int K = KH * KW * C;
   const int txw = quads_per_block(d.OW, TX_BWD / 4) * 4;   // even chunks of the output row, <= 64 pixels
-  const size_t stage = ((size_t)TX_BWD * FC + (size_t)KH * (txw + KW - 1) * C) * sizeof(float);
+  const size_t stage = 2 * (((size_t)TX_BWD * FC + (size_t)KH * (txw + KW - 1) * C + 3) & ~size_t(3)) * sizeof(float);
   const size_t red = (size_t)4 * 64 * 33 * sizeof(float);
   const size_t smem = stage > red ? stage : red;
   dim3 grid(ctx.sm_count * 3, ((K + 31) / 32) * ((F + FC - 1) / FC));
