@@ -27,7 +27,7 @@ struct ConvDims {
 };
 
 // ------------------------------------------------------------------ forward
-// block: 8 filter groups (8 filters each) x TQ pixel quads (4 consecutive x each), TQ <= 32 chosen by
+// block: 8 filter groups (filters g*4..g*4+3 and 32+g*4..32+g*4+3) x TQ pixel quads (4 consecutive x each), TQ <= 32 chosen by
 // the host so that the strips divide the output row evenly. A block walks ROWS_FWD consecutive output
 // rows of its strip: the filter bank is staged once, the KH input rows live in a ring buffer so that
 // every new output row stages only one new input row.
@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
   const int in_w = tq_n * 4 + KW - 1;               // staged input pixels per row
   float* in_s = smem;                               // ring: [KH][in_w * cc]
   float* w_s = smem + d.KH * in_w * MAX_CC;         // [KH*KW*cc][FC]
-  const int fb = f0 + tx * 8;
-  const bool vec = (d.F & 3) == 0 && fb + 8 <= d.F;
+  const int fb = f0 + tx * 4;                       // this thread's filters: fb..fb+3 and fb+32..fb+35
+  const bool vec = (d.F & 3) == 0 && fb + 36 <= d.F;
 
   for (int c0 = 0; c0 < d.C; c0 += MAX_CC) {
     const int cc = min(MAX_CC, d.C - c0);
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
               for (int t = 0; t < 4 + KW_T - 1; ++t) iv[t] = row[t * cc + ch];
 #pragma unroll
               for (int dx = 0; dx < KW_T; ++dx) {
-                const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW_T + dx) * cc + ch) * FC + tx * 8);
-                const float4 w0 = wp[0], w1 = wp[1];
+                const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW_T + dx) * cc + ch) * FC) + tx;
+                const float4 w0 = wp[0], w1 = wp[8];   // filters tx*4.. and 32+tx*4..: conflict-free 128-byte rows
                 const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
           } else {
             for (int dx = 0; dx < KW; ++dx)
               for (int ch = 0; ch < cc; ++ch) {
-                const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW + dx) * cc + ch) * FC + tx * 8);
-                const float4 w0 = wp[0], w1 = wp[1];
+                const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW + dx) * cc + ch) * FC) + tx;
+                const float4 w0 = wp[0], w1 = wp[8];
                 const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
@@ -130,16 +130,18 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
             float4 a = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
             float4 b = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
             if (acc_out) {
-              const float4 oa = *reinterpret_cast<const float4*>(o), ob = *reinterpret_cast<const float4*>(o + 4);
+              const float4 oa = *reinterpret_cast<const float4*>(o), ob = *reinterpret_cast<const float4*>(o + 32);
               a.x += oa.x; a.y += oa.y; a.z += oa.z; a.w += oa.w;
               b.x += ob.x; b.y += ob.y; b.z += ob.z; b.w += ob.w;
             }
             *reinterpret_cast<float4*>(o) = a;
-            *reinterpret_cast<float4*>(o + 4) = b;
+            *reinterpret_cast<float4*>(o + 32) = b;
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (fb + j < d.F) o[j] = acc_out ? o[j] + acc[p][j] : acc[p][j];
+            for (int j = 0; j < 8; ++j) {
+              const int fo = (j & 3) + (j >> 2) * 32;
+              if (fb + fo < d.F) o[fo] = acc_out ? o[fo] + acc[p][j] : acc[p][j];
+            }
           }
         }
       }

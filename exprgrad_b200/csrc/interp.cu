@@ -173,11 +173,126 @@ __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ 4-wide streaming fast path
+// Pure elementwise kernels (one unit-stride loop, fp32/boolean expression): every thread evaluates the
+// register program on 4 consecutive elements at a time, with 128-bit loads and stores where the
+// access is 16-byte aligned. Same opcode semantics as above, lane by lane.
+struct V4 {
+  float x, y, z, w;
+};
+__device__ __forceinline__ float b2f(bool b) { return __uint_as_float(b ? 1u : 0u); }
+__device__ __forceinline__ bool f2b(float f) { return __float_as_uint(f) != 0u; }
+
+#define EGB_V4_BIN(expr)                                    \
+  {                                                         \
+    const V4 a = s[in.a], b = s[in.b];                      \
+    r.x = expr(a.x, b.x); r.y = expr(a.y, b.y); r.z = expr(a.z, b.z); r.w = expr(a.w, b.w); \
+  }
+#define EGB_V4_UN(expr)                                     \
+  {                                                         \
+    const V4 a = s[in.a];                                   \
+    r.x = expr(a.x); r.y = expr(a.y); r.z = expr(a.z); r.w = expr(a.w); \
+  }
+
+__global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_constant__ IpProgram p) {
+  V4 s[64];
+  pdl_launch_dependents();
+  for (int i = 0; i < p.nlits; ++i) {
+    const float f = __uint_as_float((uint32_t)p.lits[i]);
+    s[p.lit_slot[i]] = V4{f, f, f, f};
+  }
+  pdl_wait();
+  const int64_t n = p.loops[0].count, start = p.loops[0].start;
+  float* const out = reinterpret_cast<float*>(p.write.base) + p.write.offset + start;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += stride) {
+    const bool full = i4 + 3 < n;
+    for (int k = 0; k < p.nreads; ++k) {
+      const IpTensorOp& op = p.reads[k];
+      const float* src = reinterpret_cast<const float*>(op.base) + op.offset;
+      V4 v;
+      if (!op.streaming) {
+        const float f = __ldg(src);
+        v = V4{f, f, f, f};
+      } else {
+        src += start + i4;
+        if (full && op.aligned16) {
+          const float4 t = *reinterpret_cast<const float4*>(src);
+          v = V4{t.x, t.y, t.z, t.w};
+        } else {
+          v.x = src[0];
+          v.y = i4 + 1 < n ? src[1] : 0.0f;
+          v.z = i4 + 2 < n ? src[2] : 0.0f;
+          v.w = i4 + 3 < n ? src[3] : 0.0f;
+        }
+      }
+      s[op.dst] = v;
+    }
+    for (int k = 0; k < p.ninstrs; ++k) {
+      const IpInstr in = p.instrs[k];
+      V4 r = V4{0.f, 0.f, 0.f, 0.f};
+      switch (in.op) {
+        case IP_FADD: EGB_V4_BIN([](float a, float b) { return a + b; }) break;
+        case IP_FSUB: EGB_V4_BIN([](float a, float b) { return a - b; }) break;
+        case IP_FMUL: EGB_V4_BIN([](float a, float b) { return a * b; }) break;
+        case IP_FDIV: EGB_V4_BIN(__fdiv_rn) break;
+        case IP_FNEG: EGB_V4_UN([](float a) { return 0.0f - a; }) break;
+        case IP_SIN: EGB_V4_UN(sinf) break;
+        case IP_COS: EGB_V4_UN(cosf) break;
+        case IP_EXP: EGB_V4_UN(expf) break;
+        case IP_LN: EGB_V4_UN(logf) break;
+        case IP_SQRT: EGB_V4_UN(__fsqrt_rn) break;
+        case IP_POW: EGB_V4_BIN(powf) break;
+        case IP_LOG10: EGB_V4_UN(log10f) break;
+        case IP_LOG2: EGB_V4_UN(log2f) break;
+        case IP_LOGB: EGB_V4_BIN([](float a, float b) { return __fdiv_rn(logf(a), logf(b)); }) break;
+        case IP_FEQ: EGB_V4_BIN([](float a, float b) { return b2f(a == b); }) break;
+        case IP_FLT: EGB_V4_BIN([](float a, float b) { return b2f(a < b); }) break;
+        case IP_FLE: EGB_V4_BIN([](float a, float b) { return b2f(a <= b); }) break;
+        case IP_BEQ: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) == f2b(b)); }) break;
+        case IP_AND: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) && f2b(b)); }) break;
+        case IP_OR: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) || f2b(b)); }) break;
+        case IP_SELECT: {
+          const V4 c = s[in.a], a = s[in.b], b = s[in.c];
+          r.x = f2b(c.x) ? a.x : b.x; r.y = f2b(c.y) ? a.y : b.y; r.z = f2b(c.z) ? a.z : b.z; r.w = f2b(c.w) ? a.w : b.w;
+          break;
+        }
+        default: break;
+      }
+      s[in.dst] = r;
+    }
+    V4 v = s[p.write.dst];
+    float* o = out + i4;
+    if (full && p.write.aligned16) {
+      if (p.accumulate) {
+        const float4 t = *reinterpret_cast<const float4*>(o);
+        v.x = t.x + v.x; v.y = t.y + v.y; v.z = t.z + v.z; v.w = t.w + v.w;
+      }
+      *reinterpret_cast<float4*>(o) = make_float4(v.x, v.y, v.z, v.w);
+    } else {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      for (int j = 0; j < 4; ++j)
+        if (i4 + j < n) o[j] = p.accumulate ? o[j] + vv[j] : vv[j];
+    }
+  }
+}
+
 }  // namespace
 
 void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
                    cudaStream_t st) {
   if (prog.npoints <= 0 || prog.nred <= 0) return;
+  if (prog.vec4 && !strict) {
+    const int64_t groups = (prog.npoints + 3) / 4;
+    const int64_t nb = (groups + IP_THREADS - 1) / IP_THREADS;
+    const int64_t capb = (int64_t)ctx.sm_count * 16;
+    {
+      Launch l(ctx, KC_ELTWISE, st);
+      launch_kernel(ctx, interp_vec4_kernel, dim3((int)(nb < capb ? nb : capb)), dim3(IP_THREADS), 0, st, prog);
+    }
+    EGB_CUDA(cudaGetLastError());
+    return;
+  }
   if (pb * rb != IP_THREADS) fail(EGB_ERR_GPU, "interp: PB*RB must be %d", IP_THREADS);
   const int64_t nblocks = (prog.npoints + pb - 1) / pb;
   const int64_t cap = (int64_t)ctx.sm_count * 8;

@@ -47,7 +47,9 @@ struct IpTensorOp {
   uint8_t slot[IP_MAX_TERMS];
   uint8_t nterms;
   uint8_t dst;                       // reads: destination slot; write: value slot
-  uint8_t pad[6];
+  uint8_t streaming;                 // vec4 path: index = offset + loop iterator (else: loop-invariant)
+  uint8_t aligned16;                 // vec4 path: element (offset + loop start) is 16-byte aligned
+  uint8_t pad[4];
 };
 
 struct IpLoop {
@@ -72,6 +74,7 @@ struct IpProgram {
   uint8_t nloops, npar, nreads, ninstrs, nindex_instrs, nlits;
   uint8_t accumulate;                // 1: out += value (InstrWrite), 0: out = value (InstrOverwrite)
   uint8_t scatter;                   // write index depends on a reduction loop: read-modify-write per iteration
+  uint8_t vec4;                      // pure streaming elementwise kernel: eligible for the 4-wide fast path
 };
 
 }  // namespace egb

@@ -238,7 +238,21 @@ struct Lowerer {
       case Op::Log10: res = emit(IP_LOG10, T_SCALAR, {v[0]}); break;
       case Op::Log2: res = emit(IP_LOG2, T_SCALAR, {v[0]}); break;
       case Op::Log: res = emit(IP_LOGB, T_SCALAR, {v[0], v[1]}); break;
-      case Op::ToScalar: res = emit(IP_TOSCALAR, T_SCALAR, {v[0]}); break;
+      case Op::ToScalar:
+        if (v[0]->kind != V_DEV) {
+          // host-known index (shape / len / literal): (float)i is what the reference computes at run
+          // time with sitofp; materialise it as a scalar literal (not foldable further, like there)
+          const float f = (float)v[0]->i;
+          uint32_t b;
+          memcpy(&b, &f, 4);
+          res.kind = V_DEV;
+          res.ty = T_SCALAR;
+          res.slot = literal(T_SCALAR, b);
+          res.deps = 0;
+          break;
+        }
+        res = emit(IP_TOSCALAR, T_SCALAR, {v[0]});
+        break;
       case Op::ToIndex: res = emit(IP_TOINDEX, T_INDEX, {v[0]}); break;
       case Op::Shape: {
         const auto& shape = shape_of(ins.tensor);
@@ -567,6 +581,33 @@ Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<i
     ++pos;
   }
   ip.accumulate = (overwrite && !ip.scatter) ? 0 : 1;
+
+  // 4-wide fast path: one unit-stride loop, every access either streams with it or is loop-invariant,
+  // and the expression only uses fp32 / boolean operations
+  {
+    bool ok = nloops == 1 && ip.npar == 1 && k.loops[0].step == 1 && !ip.scatter && ip.nindex_instrs == 0 &&
+              lw.nslots <= 64;
+    auto classify = [&](IpTensorOp& op, bool must_stream) {
+      if (op.nterms == 1 && op.coef[0] == 1 && op.slot[0] == iter_slot[0]) op.streaming = 1;
+      else if (op.nterms == 0 && !must_stream) op.streaming = 0;
+      else ok = false;
+      const int64_t first = op.offset + (op.streaming ? start[0] : 0);
+      op.aligned16 = (((op.base >> 2) + (uint64_t)first) & 3) == 0 && (op.base & 3) == 0;
+    };
+    if (ok) {
+      classify(ip.write, true);
+      for (int r = 0; r < ip.nreads; ++r) classify(ip.reads[r], false);
+      for (int i = 0; i < ip.ninstrs && ok; ++i) {
+        const uint8_t op = ip.instrs[i].op;
+        const bool fp = (op >= IP_FADD && op <= IP_LOGB) || op == IP_FEQ || op == IP_FLT || op == IP_FLE ||
+                        op == IP_BEQ || op == IP_AND || op == IP_OR || op == IP_SELECT;
+        ok = ok && fp;
+      }
+      // index-typed literals cannot be splatted into fp32 lanes; they are only present if unused
+      for (int i = 0; i < ip.nlits && ok; ++i) ok = ok && (ip.lits[i] >> 32) == 0;
+    }
+    ip.vec4 = ok ? 1 : 0;
+  }
 
   Lowered out;
   out.uses_epoch = lw.uses_epoch;
