@@ -68,6 +68,13 @@ _SIGS = {
     "egb_buffer_write": (I, [P, P, SZ]),
     "egb_buffer_fill": (I, [P, P, SZ]),
     "egb_buffer_read_into": (I, [P, P, SZ]),
+    "egb_compile": (I, [P, S, S, PP]),
+    "egb_kernel_free": (I, [P]),
+    "egb_kernel_arg_count": (I, [P, PI]),
+    "egb_kernel_arg_buffer": (I, [P, I, P]),
+    "egb_kernel_arg_shape": (I, [P, I, I, PI64]),
+    "egb_kernel_arg_index": (I, [P, I, I64]),
+    "egb_kernel_run": (I, [P, I, PI64, PI64]),
     "egb_gemm_f32": (I, [P, I, I, I64, I64, I64, P, I64, P, I64, P, I64, I, P, F]),
     "egb_gemm_planes": (I, [P, I64, I64, I64, P, P, I64, P, P, I64, P, I64, I, P, F, I]),
     "egb_split_bf16": (I, [P, P, I64, I64, I64, I, P, P, I64, I]),

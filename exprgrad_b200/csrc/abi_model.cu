@@ -149,6 +149,114 @@ int egb_program_infer_shapes(egb_program* p, const char* target, int n_args, con
   EGB_CATCH
 }
 
+// ---- compile / arg / run: the per-kernel launch interface of exprgrad/runtimes/gpu.nim:46-50 --------
+// (cl.nim:149-207). `source` is not OpenCL C but the text of a compiled program with one target
+// (the kernels the JIT'd host code would launch one by one); arguments are the target's tensors in
+// `target.tensors` order. The reference passes shapes to its OpenCL kernels as captured Index registers
+// (llvmgen.nim:474-486); here they are attached per tensor with egb_kernel_arg_shape.
+struct egb_kernel {
+  egb_context* ctx = nullptr;
+  std::shared_ptr<Program> prog;
+  Target* target = nullptr;
+  std::map<int, void*> ptrs;   // tensor id -> device pointer
+  ShapeTable shapes;
+  int64_t epoch = 0;
+};
+
+int egb_compile(egb_context* ctx, const char* name, const char* source, egb_kernel** out) {
+  EGB_TRY
+  auto k = std::make_unique<egb_kernel>();
+  k->ctx = ctx;
+  try {
+    k->prog = parse_program(source);
+  } catch (const Error& e) {
+    fail(EGB_ERR_GPU, "Failed to build program: %s", e.what());  // cl.nim:163-171
+  }
+  if (!k->prog->compiled) compile_program(*k->prog);
+  if (k->prog->f64) fail(EGB_ERR_GPU, "Failed to build program: float64 kernels are not supported");
+  k->target = k->prog->find_target(name);
+  if (!k->target) fail(EGB_ERR_GPU, "Failed to build program: no target named %s", name);
+  *out = k.release();
+  EGB_CATCH
+}
+
+int egb_kernel_free(egb_kernel* k) {
+  EGB_TRY
+  delete k;
+  EGB_CATCH
+}
+
+int egb_kernel_arg_count(egb_kernel* k, int* count) {
+  EGB_TRY
+  *count = (int)k->target->tensors.size();
+  EGB_CATCH
+}
+
+static int kernel_tensor(egb_kernel* k, int index) {
+  if (index < 0 || index >= (int)k->target->tensors.size())
+    fail(EGB_ERR_GPU, "kernel argument %d out of range (the kernel has %zu tensor arguments)", index,
+         k->target->tensors.size());
+  return k->target->tensors[index];
+}
+
+int egb_kernel_arg_buffer(egb_kernel* k, int index, egb_buffer* buf) {
+  EGB_TRY
+  k->ptrs[kernel_tensor(k, index)] = buf->ptr;
+  EGB_CATCH
+}
+
+int egb_kernel_arg_shape(egb_kernel* k, int index, int rank, const int64_t* dims) {
+  EGB_TRY
+  k->shapes[kernel_tensor(k, index)] = std::vector<int64_t>(dims, dims + rank);
+  EGB_CATCH
+}
+
+int egb_kernel_arg_index(egb_kernel* k, int index, int64_t value) {
+  EGB_TRY
+  if (index != -1) fail(EGB_ERR_GPU, "index arguments other than the epoch (-1) are derived from the tensor shapes");
+  k->epoch = value;
+  EGB_CATCH
+}
+
+int egb_kernel_run(egb_kernel* k, int work_dims, const int64_t* group_size, const int64_t* local_size) {
+  EGB_TRY
+  (void)group_size;
+  (void)local_size;
+  if (work_dims <= 0) fail(EGB_ERR_GPU, "Group size must have at least one dimension");  // cl.nim:191-192
+  Context& c = k->ctx->c;
+  EGB_CUDA(cudaSetDevice(c.device));
+  for (int id : k->target->tensors) {
+    if (!k->ptrs.count(id)) fail(EGB_ERR_GPU, "kernel argument for tensor%d has not been set", id - 1);
+    if (!k->shapes.count(id)) fail(EGB_ERR_GPU, "shape of tensor%d has not been set", id - 1);
+  }
+  // launch geometry is the library's; every kernel accumulates into its destination like the
+  // reference's generated `+=` (clgen.nim:116-125) - the caller zero-fills results (model.nim:302-318)
+  for (auto& kp : k->target->kernels) {
+    const Kernel& kern = *kp;
+    GemmPattern g;
+    ConvPattern cv;
+    if (match_gemm(kern, k->shapes, g)) {
+      int st = egb_gemm_f32(k->ctx, g.trans_a, g.trans_b, g.M, g.N, g.K, (const float*)k->ptrs[g.a_tensor], g.lda,
+                            (const float*)k->ptrs[g.b_tensor], g.ldb, (float*)k->ptrs[g.c_tensor], g.ldc, 1, nullptr, 1.0f);
+      if (st != EGB_OK) return st;
+    } else if (match_conv2(kern, k->shapes, cv) && (cv.kind != ConvPattern::D_IMAGES || conv2_dimg_supported(cv.KW))) {
+      const float* img = (const float*)k->ptrs[cv.img_tensor];
+      const float* fil = (const float*)k->ptrs[cv.fil_tensor];
+      const float* out_t = (const float*)k->ptrs[cv.out_tensor];
+      if (cv.kind == ConvPattern::FORWARD)
+        launch_conv2_fwd(c, img, fil, (float*)out_t, cv.N, cv.H, cv.W, cv.C, cv.F, cv.KH, cv.KW, true, c.stream);
+      else if (cv.kind == ConvPattern::D_FILTERS)
+        launch_conv2_dw(c, img, out_t, (float*)fil, cv.N, cv.H, cv.W, cv.C, cv.F, cv.KH, cv.KW, c.stream);
+      else
+        launch_conv2_dimg(c, out_t, fil, (float*)img, cv.N, cv.H, cv.W, cv.C, cv.F, cv.KH, cv.KW, true, c.stream);
+    } else {
+      Lowered lw = lower_kernel(kern, k->shapes, k->ptrs, k->epoch, false, false, c.sm_count);
+      launch_interp(c, lw.ip, lw.pb, lw.rb, lw.points_fast, false, c.stream);
+    }
+  }
+  EGB_CATCH
+}
+
 int egb_model_create(egb_context* ctx, egb_program* program, uint64_t seed, egb_model** out) {
   EGB_TRY
   EGB_CUDA(cudaSetDevice(ctx->c.device));

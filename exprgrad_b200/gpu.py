@@ -96,6 +96,9 @@ class GpuBuffer:
 class GpuContext:
     """cl.nim:22-25, 83-99: one device, one in-order queue (= one CUDA stream)."""
 
+    def compile(self, name: str, source: str) -> "GpuKernel":  # gpu.nim:46
+        return GpuKernel(self, name, source)
+
     def __init__(self, device: GpuDevice = None):
         h = ctypes.c_void_p()
         check(lib.egb_context_create(-1 if device is None else device.index, ctypes.byref(h)))
@@ -120,6 +123,52 @@ class GpuContext:
         if self.handle:
             check(lib.egb_context_destroy(self.handle))
             self.handle = None
+
+
+class GpuKernel:
+    """cl.nim:37-39, 149-207: compile / arg / run. `source` is the text of a compiled program (see
+    egb_compile in include/egb200.h); arguments are the target's tensors in order."""
+
+    def __init__(self, ctx: GpuContext, name: str, source: str):
+        h = ctypes.c_void_p()
+        check(lib.egb_compile(ctx.handle, name.encode(), source.encode(), ctypes.byref(h)))
+        self.handle = h
+        self.ctx = ctx
+
+    @property
+    def arg_count(self) -> int:
+        n = ctypes.c_int(0)
+        check(lib.egb_kernel_arg_count(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def arg(self, index: int, value, shape=None) -> "GpuKernel":
+        if isinstance(value, GpuTensor):
+            shape, value = value.shape, value.buffer
+        if isinstance(value, GpuBuffer):
+            check(lib.egb_kernel_arg_buffer(self.handle, index, value.handle))
+            if shape is not None:
+                dims = (ctypes.c_int64 * max(len(shape), 1))(*[int(d) for d in shape])
+                check(lib.egb_kernel_arg_shape(self.handle, index, len(shape), dims))
+        else:
+            check(lib.egb_kernel_arg_index(self.handle, index, int(value)))
+        return self
+
+    def run(self, group_size: Sequence[int], local_size: Sequence[int]):
+        if len(group_size) != len(local_size) and len(group_size) > 0:
+            raise GpuError("Dimension of group size must equal dimension of local size")  # cl.nim:193-194
+        n = len(group_size)
+        g = (ctypes.c_int64 * max(n, 1))(*group_size)
+        l = (ctypes.c_int64 * max(n, 1))(*local_size)
+        check(lib.egb_kernel_run(self.handle, n, g, l))
+
+    def free(self):
+        if self.handle:
+            check(lib.egb_kernel_free(self.handle))
+            self.handle = None
+
+
+def compile_kernel(ctx: GpuContext, name: str, source: str) -> GpuKernel:  # gpu.nim:46
+    return GpuKernel(ctx, name, source)
 
 
 def new_gpu_context(device: GpuDevice = None) -> GpuContext:  # cl.nim:83-99

@@ -117,6 +117,27 @@ int egb_buffer_fill(egb_buffer* buf, const void* value, size_t elem_size);
  * ("Buffer size is not equal to target size"). */
 int egb_buffer_read_into(egb_buffer* buf, void* data, size_t bytes);
 
+/* compile(ctx, name, source) / compile(ctx, GpuKernelSource) (gpu.nim:46-47, cl.nim:149-179). `source`
+ * is not OpenCL C: it is the text of a compiled program (same grammar as egb_program_parse) and `name`
+ * selects the target whose kernels this GpuKernel launches; build problems are reported like the
+ * reference's "Failed to build program: <log>" (cl.nim:163-171). */
+int egb_compile(egb_context* ctx, const char* name, const char* source, egb_kernel** out);
+int egb_kernel_free(egb_kernel* k);
+/* Number of tensor arguments (= the target's tensors, in `target.tensors` order). */
+int egb_kernel_arg_count(egb_kernel* k, int* count);
+/* arg(kernel, index, buffer) (gpu.nim:49, cl.nim:186-188): binds tensor argument `index`. */
+int egb_kernel_arg_buffer(egb_kernel* k, int index, egb_buffer* buf);
+/* The reference hands shapes to its OpenCL kernels as captured Index registers (llvmgen.nim:474-486);
+ * here the shape of tensor argument `index` is attached directly. */
+int egb_kernel_arg_shape(egb_kernel* k, int index, int rank, const int64_t* dims);
+/* arg[T](kernel, index, value) (gpu.nim:48, cl.nim:181-184): only index -1 (the epoch) is accepted. */
+int egb_kernel_arg_index(egb_kernel* k, int index, int64_t value);
+/* run(kernel, groupSize, localSize) (gpu.nim:50, cl.nim:190-207): asynchronous; the launch geometry is
+ * chosen by the library, the arguments are validated like the reference ("Group size must have at least
+ * one dimension"). Every kernel accumulates into its destination (`+=`, clgen.nim:116-125), so results
+ * must be zero-filled by the caller exactly as model.nim:302-318 does. */
+int egb_kernel_run(egb_kernel* k, int work_dims, const int64_t* group_size, const int64_t* local_size);
+
 /* ---- 2. operator kernels on raw device pointers ---------------------------------------------- */
 
 /* C[M,N] (+)= alpha * op(A)[M,K] * op(B)[K,N] (+ bias[n]) (relu). fp32 in/out, row-major.

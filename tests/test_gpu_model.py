@@ -257,3 +257,51 @@ def test_dropout_random_tensor(ctx):
         assert abs((out != 0).mean() - 0.75) < 0.02
     assert not np.array_equal(a, b)
     pm.free()
+
+
+def test_device_api_compile_arg_run(ctx):
+    """The per-kernel launch interface of exprgrad/runtimes/gpu.nim:46-50 (what the JIT'd host code of a
+    CompileGpu target drives, llvmgen.nim:461-500), as in tests/test_gpu.nim:62-68, 201-208, 241-246:
+    64x64 matmul, conv1 and leaky relu against host results with the reference's (loose) bound."""
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, gpu as GP
+    from exprgrad_b200.model import Program
+    rng = np.random.default_rng(0)
+
+    def run(graph, name, host):
+        prog = Program.from_graphs([graph]).compile()
+        k = ctx.compile(name, prog.serialize())
+        order = [prog.tensor_info(t) for t in range(1, prog.tensor_count() + 1)]
+        assert k.arg_count == len(host)
+        tensors = []
+        # arguments follow target.tensors order, which for these one-kernel programs is reads then write
+        for i in range(k.arg_count):
+            arr = host[i]
+            t = eg.alloc_tensor(ctx, arr.shape)
+            t.write(arr)
+            k.arg(i, t)
+            tensors.append(t)
+        with pytest.raises(eg.GpuError):
+            k.run([], [])
+        k.run([1], [16])
+        out = tensors[-1].read()
+        k.free()
+        return out
+
+    a = rng.uniform(0, 1, (64, 64)).astype(np.float32); b = rng.uniform(0, 1, (64, 64)).astype(np.float32)
+    c = F.Fun(); y, x, it = F.Iter("y"), F.Iter("x"), F.Iter("it")
+    c[y, x] += F.input("a")[y, it] * F.input("b")[it, x]
+    got = run(c.target("c", "gpu"), "c", [a, b, np.zeros((64, 64), np.float32)])
+    assert float(((got - a @ b) ** 2).sum()) < 0.1
+
+    img = rng.uniform(0, 1, (68,)).astype(np.float32); fil = rng.uniform(-1, 1, (5,)).astype(np.float32)
+    r = F.Fun(); x, dx = F.Iter("x"), F.Iter("dx")
+    r[x] += F.input("image")[x + dx] * F.input("filter")[dx]
+    got = run(r.target("res", "gpu"), "res", [img, fil, np.zeros((64,), np.float32)])
+    assert float(((got - np.correlate(img, fil, "valid")) ** 2).sum()) < 0.1
+
+    xs = np.array([[1, 2, -1], [-2, 0, 3]], np.float32)
+    yv = F.Fun(); it = F.Iter("it"); xin = F.input("x")
+    yv.raw[it] += F.select(xin.raw[it] > 0.0, xin.raw[it], 0.01 * xin.raw[it])
+    got = run(yv.target("y", "gpu"), "y", [xs, np.zeros((2, 3), np.float32)])
+    assert np.array_equal(got, np.array([[1, 2, -0.01], [-0.02, 0, 3]], np.float32))
