@@ -215,6 +215,10 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
     passes = 3
     t_kernel = k_ms / max(k_n, 1) * 1e-3
     achieved = passes * flop / t_kernel / 1e12
+    # a >50 ms back-to-back region runs under the 1 kW power cap: the sustained cuBLAS figure is the
+    # denominator (B200_PROFILING.md); short runs (--steps <= 100) compare against the burst figure
+    sustained = ms > 50.0
+    peak = peaks["bf16_sustained"] if sustained else peaks["bf16_burst"]
     out = {
         "metric": "matmul_gflops", "value": world * flop / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -226,11 +230,13 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
                    "api": "exprgrad_b200.compile(c.target('c')).apply('c', {a, b}) -> egb_model_call"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel", "achieved": achieved,
-                     "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "frac_of_burst_peak": achieved / peaks["bf16_burst"],
                      "traffic": 578.0e6, "traffic_source": "profiles/r01a_ncu_full.txt (dram read+write per launch)",
                      "passes": passes, "algorithmic_tflops": flop / t_kernel / 1e12, "kernel_ms": t_kernel * 1e3,
                      "kernel_share_of_step": k_ms / max(all_ms, 1e-9),
-                     "peak_source": peaks["source"] + ", burst bf16 figure (kernel timed per launch)",
+                     "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a %.0f ms back-to-back region)" % ms
+                                                       if sustained else ", burst bf16 figure (short timed region)"),
                      "note": "achieved = passes x 2MNK / kernel time = tensor-pipe rate of the 3-pass fp32 scheme; "
                              "algorithmic_tflops = 2MNK / kernel time; fp32-equivalent ceiling = peak / 3"},
         "e2e": {"value": world * flop / (e2e_ms / e2e_steps * 1e-3) / 1e9, "unit": "GFLOP/s",

@@ -20,6 +20,8 @@
 //   warps 4-7   epilogue: tcgen05.ld -> registers -> alpha / bias / relu / accumulate -> global
 // Pipelines: smem full/empty mbarriers between TMA and MMA; TMEM full/empty between MMA and epilogue,
 // so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdlib.h>
+
 #include "egb_internal.hpp"
 #include "ptx.cuh"
 
@@ -63,6 +65,9 @@ __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* mi
   *mid = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// kFused = false: plain contraction epilogue (C (+)= alpha * acc), the 4096^3 benchmark path;
+// kFused = true: bias / second stage / operand planes / column sums fused behind the contraction.
+template <bool kFused>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_mid,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_mid,
@@ -229,7 +234,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (p.flags & GEMM_BIAS) {
+        if (kFused && (p.flags & GEMM_BIAS)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.bias + col0 + j));
@@ -258,7 +263,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               if (j < ncols) p.C[off + j] = v[j];
           }
           // ---- second stage
-          if (p.epi == EPI_RELU) {
+          if (!kFused) {
+          } else if (p.epi == EPI_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (0.0f <= v[j]) ? v[j] : 0.0f;
           } else if (p.epi == EPI_LEAKY) {
@@ -300,7 +306,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 if (j < ncols) v[j] = __fadd_rn(p.D[off + j], __fmul_rn(0.0f - v[j], p.epi_param));
             }
           }
-          if (p.epi != EPI_NONE) {
+          if (kFused && p.epi != EPI_NONE) {
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -311,7 +317,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 if (j < ncols) p.D[off + j] = v[j];
             }
           }
-          if (p.flags & GEMM_SPLIT_OUT) {
+          if (kFused && (p.flags & GEMM_SPLIT_OUT)) {
             __nv_bfloat16* hrow = p.out_hi + (size_t)row * p.ld_out + col0;
             __nv_bfloat16* mrow = p.out_mid + (size_t)row * p.ld_out + col0;
             if (ncols == 32 && (p.ld_out & 7) == 0) {
@@ -331,7 +337,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
         }
-        if (p.colsum) {
+        if (kFused && p.colsum) {
           // column sums over the 32 rows this warp holds: butterfly transpose-reduce (31 shuffles);
           // afterwards lane j holds the sum of column j. Rows outside the matrix contribute zero.
 #pragma unroll
@@ -447,15 +453,22 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    EGB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    EGB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    EGB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
+  static const bool force_fused = getenv("EGB_GEMM_FUSED_ALWAYS") != nullptr;
+  const bool fused = force_fused || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.epi != EPI_NONE || a.colsum;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < ctx.sm_count ? tiles : ctx.sm_count;
   {
     Launch l(ctx, KC_GEMM, st);
-    launch_kernel(ctx, gemm_bf16x3_kernel, dim3(grid), dim3(NUM_THREADS), smem, st, tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid,
-                  p);
+    if (fused)
+      launch_kernel(ctx, gemm_bf16x3_kernel<true>, dim3(grid), dim3(NUM_THREADS), smem, st, tm_a_hi, tm_a_mid, tm_b_hi,
+                    tm_b_mid, p);
+    else
+      launch_kernel(ctx, gemm_bf16x3_kernel<false>, dim3(grid), dim3(NUM_THREADS), smem, st, tm_a_hi, tm_a_mid, tm_b_hi,
+                    tm_b_mid, p);
   }
   EGB_CUDA(cudaGetLastError());
 }
