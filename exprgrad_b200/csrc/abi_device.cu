@@ -155,6 +155,9 @@ int egb_context_destroy(egb_context* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   if (ctx->c.scratch) cudaFree(ctx->c.scratch);
+  for (auto st : ctx->c.aux_stream)
+    if (st) cudaStreamDestroy(st);
+  for (auto e : ctx->c.fork_events) cudaEventDestroy(e);
   for (auto& s : ctx->c.spans) {
     cudaEventDestroy(s.a);
     cudaEventDestroy(s.b);

@@ -290,6 +290,11 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
     m->m->strict = value != 0;
   } else if (k == "graphs") {
     m->m->use_graphs = value != 0;
+  } else if (k == "concurrent") {
+    if (m->m->concurrent != (value != 0)) {
+      for (auto& p : m->m->plans) p->graph_valid = false;
+    }
+    m->m->concurrent = value != 0;
   } else if (k == "fuse") {
     if (m->m->fuse != (value != 0)) {
       EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
@@ -469,7 +474,7 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
          (p.graph_valid ? "yes" : "no") + "\n";
     static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv"};
     for (auto& n : p.nodes) {
-      s += std::string("  ") + kinds[n.kind] + " " + n.label;
+      s += std::string("  L") + std::to_string(n.level) + " " + kinds[n.kind] + " " + n.label;
       if (n.kind == Node::INTERP)
         s += " points=" + std::to_string(n.ip.npoints) + " red=" + std::to_string(n.ip.nred) + " pb=" +
              std::to_string(n.pb) + " rb=" + std::to_string(n.rb) + (n.ip.accumulate ? " +=" : " =") +

@@ -50,6 +50,10 @@ struct Context {
   size_t launches = 0;  // number of kernel launches issued through this context
   void* ensure_scratch(size_t bytes);
 
+  // auxiliary streams + events used to capture independent plan nodes as parallel graph branches
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> fork_events;
+
   // Programmatic dependent launch: every kernel is launched with the programmatic-stream-serialization
   // attribute and begins with griddepcontrol.wait, so that the launch latency and prologue of kernel
   // N+1 overlap the tail of kernel N (also inside captured CUDA graphs).

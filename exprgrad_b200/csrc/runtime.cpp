@@ -79,12 +79,15 @@ void build_nodes_impl(Model& m, Plan& plan) {
   for (auto& kv : plan.shapes)
     if (!ptrs.count(kv.first)) ptrs[kv.first] = tensor_ptr(m, plan, kv.first);
 
+  auto plane_key = [](int tensor, int orientation) { return -(int64_t)(2 * tensor + orientation + 1); };
   if (plan.zero_bytes) {
     Node n;
     n.kind = Node::MEMSET;
     n.label = "zero results";
     n.ptr = plan.arena;
     n.bytes = plan.zero_bytes;
+    for (auto& kv : plan.tensors)
+      if ((char*)kv.second.ptr < plan.arena + plan.zero_bytes) n.writes.push_back(kv.first);
     plan.nodes.push_back(n);
   }
   for (int id : target.tensors) {
@@ -98,6 +101,7 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.lo = (float)td.range_lo;
       n.hi = (float)td.range_hi;
       n.tensor = id;
+      n.writes.push_back(id);
       plan.nodes.push_back(n);
     }
   }
@@ -133,6 +137,8 @@ void build_nodes_impl(Model& m, Plan& plan) {
     n.split_hi = hi;
     n.split_mid = mid;
     n.split_dst_ld = (int)out_ld;
+    n.reads.push_back(tensor);
+    n.writes.push_back(plane_key(tensor, transposed ? 1 : 0));
     plan.nodes.push_back(n);
     planes[key] = std::make_pair(hi, mid);
     return planes[key];
@@ -148,6 +154,13 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.label = "all-reduce(avg) parameter-gradient bucket";
       n.ptr = plan.arena + plan.bucket_off;
       n.bytes = plan.bucket_bytes;
+      for (auto& kv : plan.tensors) {
+        const char* p0 = (const char*)kv.second.ptr;
+        if (p0 >= plan.arena + plan.bucket_off && p0 < plan.arena + plan.bucket_off + plan.bucket_bytes) {
+          n.reads.push_back(kv.first);
+          n.writes.push_back(kv.first);
+        }
+      }
       plan.nodes.push_back(n);
     }
     if (inf.is_gemm && !m.strict) {
@@ -166,6 +179,21 @@ void build_nodes_impl(Model& m, Plan& plan) {
                           : get_planes(g.b_tensor, b_copy, g.K, g.N, g.ldb, ldb);
       n.gemm.a_hi = pa.first; n.gemm.a_mid = pa.second; n.gemm.lda = (int)lda; n.gemm.a_mn = g.trans_a && !a_copy;
       n.gemm.b_hi = pb.first; n.gemm.b_mid = pb.second; n.gemm.ldb = (int)ldb; n.gemm.b_mn = !g.trans_b && !b_copy;
+      n.reads.push_back(plane_key(g.a_tensor, a_copy ? 1 : 0));
+      n.reads.push_back(plane_key(g.b_tensor, b_copy ? 1 : 0));
+      n.writes.push_back(g.c_tensor);
+      if (!inf.overwrite) n.reads.push_back(g.c_tensor);
+      if (inf.bias_tensor) n.reads.push_back(inf.bias_tensor);
+      if (inf.h_tensor) n.reads.push_back(inf.h_tensor);
+      if (inf.d_tensor) {
+        n.writes.push_back(inf.d_tensor);
+        if (inf.epi == EPI_SGD) n.reads.push_back(inf.d_tensor);
+      }
+      if (inf.colsum_tensor) {
+        n.writes.push_back(inf.colsum_tensor);
+        n.reads.push_back(inf.colsum_tensor);
+      }
+      if (inf.emit_planes) n.writes.push_back(plane_key(inf.final_tensor, 0));
       n.gemm.M = (int)g.M; n.gemm.N = (int)g.N; n.gemm.K = (int)g.K;
       n.gemm.C = (float*)ptrs[g.c_tensor];
       n.gemm.ldc = (int)g.ldc;
@@ -217,6 +245,9 @@ void build_nodes_impl(Model& m, Plan& plan) {
         n.conv_b = (const float*)ptrs[cv.fil_tensor];
         n.conv_out = (float*)ptrs[cv.img_tensor];
       }
+      for (auto& r : k.reads) n.reads.push_back(r.tensor);
+      n.writes.push_back(k.write.tensor);
+      n.reads.push_back(k.write.tensor);
       plan.nodes.push_back(n);
     } else {
       Lowered lw = lower_kernel(k, plan.shapes, ptrs, m.epoch, m.strict, inf.overwrite, ctx.sm_count);
@@ -230,6 +261,9 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.strict = m.strict;
       n.uses_epoch = lw.uses_epoch;
       n.kernel_index = (int)ki;
+      for (auto& r : k.reads) n.reads.push_back(r.tensor);
+      n.writes.push_back(k.write.tensor);
+      if (lw.ip.accumulate) n.reads.push_back(k.write.tensor);
       plan.nodes.push_back(n);
     }
     // cached planes of every tensor this unit wrote are stale now (except the ones it just produced)
@@ -240,6 +274,24 @@ void build_nodes_impl(Model& m, Plan& plan) {
       for (auto it = planes.begin(); it != planes.end();)
         it = it->first.first == wtensor ? planes.erase(it) : std::next(it);
     }
+  }
+  // levels: a node's level is one more than the highest level among the earlier nodes it conflicts
+  // with (read-after-write, write-after-read, write-after-write); nodes of one level are independent
+  for (size_t i = 0; i < plan.nodes.size(); ++i) {
+    Node& ni = plan.nodes[i];
+    int level = 0;
+    auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+      for (auto x : a)
+        for (auto y : b)
+          if (x == y) return true;
+      return false;
+    };
+    for (size_t j = 0; j < i; ++j) {
+      const Node& nj = plan.nodes[j];
+      if (hits(nj.writes, ni.reads) || hits(nj.writes, ni.writes) || hits(nj.reads, ni.writes))
+        level = std::max(level, nj.level + 1);
+    }
+    ni.level = level;
   }
   for (auto& n : plan.nodes)
     if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
@@ -531,6 +583,61 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
   }
 }
 
+// Issue the plan's nodes into the capturing stream level by level; within a level the nodes are
+// spread over the main stream and two auxiliary streams (fork / join with events), which the capture
+// turns into parallel branches of the CUDA graph.
+static void capture_levels(Model& m, Plan& plan) {
+  Context& c = *m.ctx;
+  int max_level = 0;
+  size_t widest = 1;
+  for (auto& n : plan.nodes) max_level = std::max(max_level, n.level);
+  std::vector<std::vector<Node*>> levels(max_level + 1);
+  for (auto& n : plan.nodes) levels[n.level].push_back(&n);
+  for (auto& l : levels) widest = std::max(widest, l.size());
+  if (!m.concurrent || widest == 1) {
+    for (auto& n : plan.nodes) launch_node(m, n, c.stream);
+    return;
+  }
+  for (auto& st : c.aux_stream)
+    if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  size_t ev = 0;
+  auto next_event = [&]() {
+    if (ev == c.fork_events.size()) {
+      cudaEvent_t e;
+      EGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c.fork_events.push_back(e);
+    }
+    return c.fork_events[ev++];
+  };
+  for (auto& level : levels) {
+    if (level.size() == 1) {
+      launch_node(m, *level[0], c.stream);
+      continue;
+    }
+    // NCCL and memset nodes stay on the main stream; the rest round-robin over 3 streams
+    cudaStream_t streams[3] = {c.stream, c.aux_stream[0], c.aux_stream[1]};
+    bool used[3] = {true, false, false};
+    cudaEvent_t fork = next_event();
+    EGB_CUDA(cudaEventRecord(fork, c.stream));
+    size_t rr = 0;
+    for (Node* n : level) {
+      int s = 0;
+      if (n->kind != Node::ALLREDUCE && n->kind != Node::MEMSET) s = (int)(rr++ % 3);
+      if (s != 0 && !used[s]) {
+        EGB_CUDA(cudaStreamWaitEvent(streams[s], fork, 0));
+        used[s] = true;
+      }
+      launch_node(m, *n, streams[s]);
+    }
+    for (int s = 1; s < 3; ++s) {
+      if (!used[s]) continue;
+      cudaEvent_t join = next_event();
+      EGB_CUDA(cudaEventRecord(join, streams[s]));
+      EGB_CUDA(cudaStreamWaitEvent(c.stream, join, 0));
+    }
+  }
+}
+
 void Model::run(Plan& plan) {
   Context& c = *ctx;
   bool has_random = false, uses_epoch = false;
@@ -550,7 +657,7 @@ void Model::run(Plan& plan) {
       cudaGraph_t graph = nullptr;
       EGB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
       try {
-        for (auto& n : plan.nodes) launch_node(*this, n, c.stream);
+        capture_levels(*this, plan);
       } catch (...) {
         cudaStreamEndCapture(c.stream, &graph);
         if (graph) cudaGraphDestroy(graph);

@@ -50,6 +50,10 @@ struct Node {
   const float *conv_a = nullptr, *conv_b = nullptr;
   float* conv_out = nullptr;
   bool conv_accumulate = false;
+  // dependency bookkeeping for concurrent scheduling inside the CUDA graph: buffers read / written
+  // (tensor id, or -(2*tensor + orientation + 1) for a bf16 operand-plane pair) and the resulting level
+  std::vector<int64_t> reads, writes;
+  int level = 0;
   // MEMSET / RANDOM / ALLREDUCE
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -114,6 +118,7 @@ struct Model {
   bool strict = false;      // bit-exact mode: sequential accumulation everywhere, no tensor cores
   bool use_graphs = true;
   bool fuse = true;         // epilogue fusion of contraction + elementwise / column-sum / SGD kernels
+  bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   CommHooks* comm = nullptr;

@@ -63,7 +63,7 @@ def test_dense_net_plan_uses_tensor_cores_and_graph(ctx):
     pm.apply("train", {"x": x, "y": y})
     pm.apply("train", {"x": x, "y": y})
     plan = pm.describe_plan()
-    assert plan.count("\n  gemm ") == 8, plan  # 3 forward + 2 dX + 3 dW contractions
+    assert plan.count(" gemm gemm tensor") == 8, plan  # 3 forward + 2 dX + 3 dW contractions
     assert "graph yes" in plan
     assert plan.count("fused") >= 6, plan     # bias/relu, relu-adjoint/colsum and SGD stages run in GEMM epilogues
     assert ctx.launch_count - n0 >= 2 * 15
