@@ -295,6 +295,13 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
       for (auto& p : m->m->plans) p->graph_valid = false;
     }
     m->m->concurrent = value != 0;
+  } else if (k == "rowchain") {
+    if (m->m->rowchain != (value != 0)) {
+      EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
+      m->m->plans.clear();
+      m->m->last_plan = nullptr;
+    }
+    m->m->rowchain = value != 0;
   } else if (k == "fuse") {
     if (m->m->fuse != (value != 0)) {
       EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
@@ -472,7 +479,7 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
     s += "target " + p.target_name + ": " + std::to_string(p.nodes.size()) + " nodes, arena " +
          std::to_string(p.arena_bytes) + " bytes (zeroed per run: " + std::to_string(p.zero_bytes) + "), graph " +
          (p.graph_valid ? "yes" : "no") + "\n";
-    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv"};
+    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain"};
     for (auto& n : p.nodes) {
       s += std::string("  L") + std::to_string(n.level) + " " + kinds[n.kind] + " " + n.label;
       if (n.kind == Node::INTERP)

@@ -173,6 +173,74 @@ __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ row-chain kernel
+// A run of small kernels that only couple elements of the same row (softmax sums -> normalise ->
+// cross-entropy adjoints ..., exprgrad/layers/dnn.nim:90-94, base.nim:66-67 and their derive()d
+// kernels) executes in ONE launch: each warp owns rows and runs the whole chain for its row,
+// exchanging intermediate tensors through global memory with only __syncwarp() in between.
+// Programs are in "row form": loops[0] is the row loop (start 0, step 1).
+__global__ void __launch_bounds__(IP_THREADS) interp_rowchain_kernel(const IpProgram* __restrict__ progs, int nprogs,
+                                                                     int64_t rows) {
+  Slot s[IP_MAX_SLOTS];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp; row < rows; row += nwarps) {
+    for (int k = 0; k < nprogs; ++k) {
+      const IpProgram& p = progs[k];
+      float* const out = reinterpret_cast<float*>(p.write.base);
+      for (int i = 0; i < p.nlits; ++i) s[p.lit_slot[i]].u = p.lits[i];
+      s[p.loops[0].slot].i = row;
+      const int64_t pts = p.npoints / rows;  // points of this row
+      if (pts == 1 && p.nred > 1) {
+        // one output per row: the lanes share the reduction
+        decode(p, 1, p.npar, 0, s);
+        float acc = 0.0f;
+        for (int64_t r = lane; r < p.nred; r += 32) {
+          decode(p, p.npar, p.nloops, r, s);
+          run_instrs(p.index_instrs, p.nindex_instrs, s, p);
+          for (int q = 0; q < p.nreads; ++q) {
+            const IpTensorOp& op = p.reads[q];
+            s[op.dst].u = 0;
+            s[op.dst].f = reinterpret_cast<const float*>(op.base)[flat_index(op, s)];
+          }
+          run_instrs(p.instrs, p.ninstrs, s, p);
+          acc += s[p.write.dst].f;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+          decode(p, p.npar, p.nloops, 0, s);
+          run_instrs(p.index_instrs, p.nindex_instrs, s, p);
+          const int64_t w = flat_index(p.write, s);
+          out[w] = p.accumulate ? out[w] + acc : acc;
+        }
+      } else {
+        for (int64_t pt = lane; pt < pts; pt += 32) {
+          decode(p, 1, p.npar, pt, s);
+          float acc = 0.0f;
+          for (int64_t r = 0; r < p.nred; ++r) {
+            decode(p, p.npar, p.nloops, r, s);
+            run_instrs(p.index_instrs, p.nindex_instrs, s, p);
+            for (int q = 0; q < p.nreads; ++q) {
+              const IpTensorOp& op = p.reads[q];
+              s[op.dst].u = 0;
+              s[op.dst].f = reinterpret_cast<const float*>(op.base)[flat_index(op, s)];
+            }
+            run_instrs(p.instrs, p.ninstrs, s, p);
+            acc += s[p.write.dst].f;
+          }
+          const int64_t w = flat_index(p.write, s);
+          out[w] = p.accumulate ? out[w] + acc : acc;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ 4-wide streaming fast path
 // Pure elementwise kernels (one unit-stride loop, fp32/boolean expression): every thread evaluates the
 // register program on 4 consecutive elements at a time, with 128-bit loads and stores where the
@@ -278,6 +346,19 @@ __global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_co
 }
 
 }  // namespace
+
+void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int64_t rows, cudaStream_t st) {
+  if (rows <= 0 || nprogs <= 0) return;
+  const int64_t warps_per_block = IP_THREADS / 32;
+  const int64_t nb = (rows + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = (int64_t)ctx.sm_count * 8;
+  {
+    Launch l(ctx, KC_INTERP, st);
+    launch_kernel(ctx, interp_rowchain_kernel, dim3((int)(nb < cap ? nb : cap)), dim3(IP_THREADS), 0, st, dev_progs, nprogs,
+                  rows);
+  }
+  EGB_CUDA(cudaGetLastError());
+}
 
 void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
                    cudaStream_t st) {

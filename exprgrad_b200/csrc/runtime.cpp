@@ -43,6 +43,7 @@ struct SplitMix {
 }  // namespace
 
 Plan::~Plan() {
+  for (void* b : chain_bufs) cudaFree(b);
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (arena) cudaFree(arena);
 }
@@ -68,12 +69,234 @@ void* tensor_ptr(Model& m, Plan& plan, int id) {
   return nullptr;
 }
 
+// levels: a node's level is one more than the highest level among the earlier nodes it conflicts
+// with (read-after-write, write-after-read, write-after-write); nodes of one level are independent
+void compute_levels(Plan& plan) {
+  auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+    for (auto x : a)
+      for (auto y : b)
+        if (x == y) return true;
+    return false;
+  };
+  for (size_t i = 0; i < plan.nodes.size(); ++i) {
+    Node& ni = plan.nodes[i];
+    int level = 0;
+    for (size_t j = 0; j < i; ++j) {
+      const Node& nj = plan.nodes[j];
+      if (hits(nj.writes, ni.reads) || hits(nj.writes, ni.writes) || hits(nj.reads, ni.writes))
+        level = std::max(level, nj.level + 1);
+    }
+    ni.level = level;
+  }
+}
+
+// Rewrite a lowered program so that loops[0] is a row loop of `rows` iterations and check that every
+// access to a tensor written inside the group stays within the row (see interp_rowchain_kernel).
+bool to_row_form(IpProgram& p, int64_t rows, const std::map<uint64_t, int64_t>& row_stride) {
+  if (p.scatter || p.npar == 0 || rows <= 0) return false;
+  auto out_stride = row_stride.find(p.write.base);
+  if (out_stride == row_stride.end()) return false;
+  auto coef_of = [](const IpTensorOp& op, int slot) {
+    int64_t c = 0;
+    for (int t = 0; t < op.nterms; ++t)
+      if (op.slot[t] == slot) c = op.coef[t];
+    return c;
+  };
+  int row = -1;
+  for (int l = 0; l < p.npar; ++l)
+    if (p.loops[l].count == rows && p.loops[l].start == 0 && p.loops[l].step == 1 &&
+        coef_of(p.write, p.loops[l].slot) == out_stride->second && row < 0)
+      row = l;
+  if (row < 0) {
+    // a single raw loop over rows * width elements: split it into (row, column)
+    if (p.nloops != 1 || p.loops[0].start != 0 || p.loops[0].step != 1 || p.loops[0].count % rows != 0) return false;
+    const int64_t width = p.loops[0].count / rows;
+    if (width != out_stride->second) return false;
+    const int old = p.loops[0].slot;
+    auto arity = [](uint8_t op) {
+      switch (op) {
+        case IP_FNEG: case IP_SIN: case IP_COS: case IP_EXP: case IP_LN: case IP_SQRT: case IP_LOG10: case IP_LOG2:
+        case IP_INEG: case IP_TOSCALAR: case IP_TOINDEX: case IP_ARRAY_READ: return 1;
+        case IP_SELECT: return 3;
+        default: return 2;
+      }
+    };
+    for (int i = 0; i < p.ninstrs; ++i) {  // the iterator must not be used as a value
+      const IpInstr& in = p.instrs[i];
+      const int n = arity(in.op);
+      if (in.a == old || (n >= 2 && in.b == old) || (n >= 3 && in.c == old)) return false;
+    }
+    if (p.nindex_instrs) return false;
+    // find an unused slot for the row iterator
+    bool used[IP_MAX_SLOTS] = {false};
+    used[old] = true;
+    for (int i = 0; i < p.ninstrs; ++i) used[p.instrs[i].dst] = used[p.instrs[i].a] = used[p.instrs[i].b] = used[p.instrs[i].c] = true;
+    for (int i = 0; i < p.nlits; ++i) used[p.lit_slot[i]] = true;
+    for (int q = 0; q < p.nreads; ++q) used[p.reads[q].dst] = true;
+    used[p.write.dst] = true;
+    int rs = -1;
+    for (int i = 0; i < IP_MAX_SLOTS && rs < 0; ++i)
+      if (!used[i]) rs = i;
+    if (rs < 0) return false;
+    auto split = [&](IpTensorOp& op) {
+      const int64_t c = coef_of(op, old);
+      if (c == 0) return true;
+      if (op.nterms >= IP_MAX_TERMS) return false;
+      op.slot[op.nterms] = (uint8_t)rs;
+      op.coef[op.nterms] = c * width;
+      op.nterms++;
+      return true;
+    };
+    for (int q = 0; q < p.nreads; ++q)
+      if (!split(p.reads[q])) return false;
+    if (!split(p.write)) return false;
+    p.loops[1] = p.loops[0];
+    p.loops[1].count = width;
+    p.loops[0].slot = (uint8_t)rs;
+    p.loops[0].start = 0;
+    p.loops[0].step = 1;
+    p.loops[0].count = rows;
+    p.nloops = 2;
+    p.npar = 2;
+  } else if (row != 0) {
+    const IpLoop r = p.loops[row];
+    for (int l = row; l > 0; --l) p.loops[l] = p.loops[l - 1];
+    p.loops[0] = r;
+  }
+  // row locality of every access to a tensor the group writes
+  const int rslot = p.loops[0].slot;
+  auto local = [&](const IpTensorOp& op) {
+    auto st = row_stride.find(op.base);
+    if (st == row_stride.end()) return true;  // external tensor: read-only for the whole group
+    if (coef_of(op, rslot) != st->second) return false;
+    int64_t lo = op.offset, hi = op.offset;
+    for (int t = 0; t < op.nterms; ++t) {
+      if (op.slot[t] == rslot) continue;
+      int l = -1;
+      for (int q = 0; q < p.nloops; ++q)
+        if (p.loops[q].slot == op.slot[t]) l = q;
+      if (l < 0) return false;  // index computed by per-point instructions: range unknown
+      const int64_t first = p.loops[l].start, last = p.loops[l].start + p.loops[l].step * (p.loops[l].count - 1);
+      const int64_t a = op.coef[t] * first, b = op.coef[t] * last;
+      lo += std::min(a, b);
+      hi += std::max(a, b);
+    }
+    return lo >= 0 && hi < st->second;
+  };
+  for (int q = 0; q < p.nreads; ++q)
+    if (!local(p.reads[q])) return false;
+  return local(p.write);
+}
+
+// Replace runs of consecutive levels that consist only of small row-local generic kernels by one
+// ROWCHAIN node each. Returns true if anything was fused.
+bool fuse_row_chains(Model& m, Plan& plan) {
+  int max_level = 0;
+  for (auto& n : plan.nodes) max_level = std::max(max_level, n.level);
+  std::vector<std::vector<int>> by_level(max_level + 1);
+  for (size_t i = 0; i < plan.nodes.size(); ++i) by_level[plan.nodes[i].level].push_back((int)i);
+  auto tensor_len = [&](int64_t id) {
+    int64_t len = 1;
+    auto sh = plan.shapes.find((int)id);
+    if (sh == plan.shapes.end()) return (int64_t)-1;
+    for (auto d : sh->second) len *= d;
+    return len;
+  };
+  std::set<int> remove;
+  std::vector<std::pair<int, Node>> insert;  // (position of the first fused node, chain node)
+  int l = 0;
+  while (l <= max_level) {
+    auto level_ok = [&](int lv) {
+      if (by_level[lv].empty()) return false;
+      for (int i : by_level[lv]) {
+        const Node& n = plan.nodes[i];
+        if (n.kind != Node::INTERP || n.ip.scatter || n.uses_epoch || n.ip.npoints * n.ip.nred > (1 << 22)) return false;
+      }
+      return true;
+    };
+    if (!level_ok(l)) {
+      ++l;
+      continue;
+    }
+    // candidate rows: taken from the first node
+    std::vector<int> members;
+    int64_t rows = -1;
+    int end = l;
+    for (; end <= max_level && level_ok(end); ++end) {
+      std::vector<int> trial = members;
+      for (int i : by_level[end]) trial.push_back(i);
+      // rows = leading dimension shared by all written tensors of the trial group
+      int64_t r = -1;
+      bool ok = true;
+      std::map<uint64_t, int64_t> stride;
+      for (int i : trial) {
+        const Node& n = plan.nodes[i];
+        const int wt = (int)n.writes[0];
+        auto sh = plan.shapes.find(wt);
+        if (sh == plan.shapes.end() || sh->second.empty()) { ok = false; break; }
+        if (r < 0) r = sh->second[0];
+        if (sh->second[0] != r || r <= 1) { ok = false; break; }
+        stride[n.ip.write.base] = tensor_len(wt) / r;
+      }
+      if (ok) {
+        for (int i : trial) {
+          IpProgram p = plan.nodes[i].ip;
+          if (!to_row_form(p, r, stride)) { ok = false; break; }
+        }
+      }
+      if (!ok) break;
+      members = trial;
+      rows = r;
+    }
+    if (members.size() >= 2) {
+      std::map<uint64_t, int64_t> stride;
+      for (int i : members) stride[plan.nodes[i].ip.write.base] = tensor_len(plan.nodes[i].writes[0]) / rows;
+      std::vector<IpProgram> progs;
+      Node chain;
+      chain.kind = Node::ROWCHAIN;
+      chain.label = "row chain of " + std::to_string(members.size()) + " kernels:";
+      for (int i : members) {
+        IpProgram p = plan.nodes[i].ip;
+        to_row_form(p, rows, stride);
+        progs.push_back(p);
+        chain.label += " " + std::to_string(plan.nodes[i].kernel_index);
+        for (auto r : plan.nodes[i].reads) chain.reads.push_back(r);
+        for (auto w : plan.nodes[i].writes) chain.writes.push_back(w);
+        remove.insert(i);
+      }
+      void* dev = nullptr;
+      EGB_CUDA(cudaMalloc(&dev, progs.size() * sizeof(IpProgram)));
+      plan.chain_bufs.push_back(dev);
+      EGB_CUDA(cudaMemcpyAsync(dev, progs.data(), progs.size() * sizeof(IpProgram), cudaMemcpyHostToDevice, m.ctx->stream));
+      EGB_CUDA(cudaStreamSynchronize(m.ctx->stream));  // `progs` is a local
+      chain.chain_progs = (IpProgram*)dev;
+      chain.chain_n = (int)progs.size();
+      chain.chain_rows = rows;
+      insert.emplace_back(*std::min_element(members.begin(), members.end()), chain);
+      l = end;
+    } else {
+      ++l;
+    }
+  }
+  if (insert.empty()) return false;
+  std::vector<Node> out;
+  for (size_t i = 0; i < plan.nodes.size(); ++i) {
+    for (auto& ins : insert)
+      if (ins.first == (int)i) out.push_back(ins.second);
+    if (!remove.count((int)i)) out.push_back(plan.nodes[i]);
+  }
+  plan.nodes = out;
+  return true;
+}
+
 void build_nodes_impl(Model& m, Plan& plan) {
   const std::vector<KernelInfo>& info = plan.info;
   const Target& target = *plan.target;
   Context& ctx = *m.ctx;
   plan.nodes.clear();
   plan.launches_per_run = 0;
+  for (void* b : plan.chain_bufs) cudaFree(b);
+  plan.chain_bufs.clear();
   std::map<int, void*> ptrs;
   for (int id : target.tensors) ptrs[id] = tensor_ptr(m, plan, id);
   for (auto& kv : plan.shapes)
@@ -275,23 +498,12 @@ void build_nodes_impl(Model& m, Plan& plan) {
         it = it->first.first == wtensor ? planes.erase(it) : std::next(it);
     }
   }
-  // levels: a node's level is one more than the highest level among the earlier nodes it conflicts
-  // with (read-after-write, write-after-read, write-after-write); nodes of one level are independent
-  for (size_t i = 0; i < plan.nodes.size(); ++i) {
-    Node& ni = plan.nodes[i];
-    int level = 0;
-    auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
-      for (auto x : a)
-        for (auto y : b)
-          if (x == y) return true;
-      return false;
-    };
-    for (size_t j = 0; j < i; ++j) {
-      const Node& nj = plan.nodes[j];
-      if (hits(nj.writes, ni.reads) || hits(nj.writes, ni.writes) || hits(nj.reads, ni.writes))
-        level = std::max(level, nj.level + 1);
-    }
-    ni.level = level;
+  compute_levels(plan);
+  // level order is a topological order: sorting by it makes every run of consecutive levels contiguous
+  // (needed by the row-chain fusion) and keeps sequential (eager) execution valid
+  std::stable_sort(plan.nodes.begin(), plan.nodes.end(), [](const Node& a, const Node& b) { return a.level < b.level; });
+  if (m.rowchain && !m.strict) {
+    if (fuse_row_chains(m, plan)) compute_levels(plan);
   }
   for (auto& n : plan.nodes)
     if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
@@ -565,6 +777,7 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       break;
     case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
     case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st); break;
+    case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_rows, st); break;
     case Node::CONV: {
       const ConvPattern& cv = n.conv;
       if (cv.kind == ConvPattern::FORWARD)

@@ -30,7 +30,7 @@ struct DevTensor {
 };
 
 struct Node {
-  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV } kind = INTERP;
+  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN } kind = INTERP;
   std::string label;
   // INTERP
   IpProgram ip;
@@ -45,6 +45,10 @@ struct Node {
   int split_rows = 0, split_cols = 0, split_ld = 0, split_dst_ld = 0, split_act = 0;
   bool split_transpose = false;
   __nv_bfloat16 *split_hi = nullptr, *split_mid = nullptr;
+  // ROWCHAIN: several row-local INTERP programs executed by one launch
+  IpProgram* chain_progs = nullptr;  // device array (owned by the plan)
+  int chain_n = 0;
+  int64_t chain_rows = 0;
   // CONV
   ConvPattern conv;
   const float *conv_a = nullptr, *conv_b = nullptr;
@@ -96,6 +100,7 @@ struct Plan {
   size_t bucket_off = 0, bucket_bytes = 0;  // contiguous parameter-gradient bucket (data parallel)
   int bucket_before_kernel = -1;            // the all-reduce runs right before this target kernel
   std::vector<Node> nodes;
+  std::vector<void*> chain_bufs;      // device copies of row-chain programs
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
   int64_t epoch_built = -1;
@@ -119,6 +124,7 @@ struct Model {
   bool use_graphs = true;
   bool fuse = true;         // epilogue fusion of contraction + elementwise / column-sum / SGD kernels
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
+  bool rowchain = true;     // runs of small row-local kernels execute in one launch
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   CommHooks* comm = nullptr;
@@ -135,6 +141,7 @@ std::unique_ptr<Model> new_model(Context& ctx, std::shared_ptr<Program> prog, ui
 // kernels (host launchers)
 void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
                    cudaStream_t st);
+void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int64_t rows, cudaStream_t st);
 void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi, uint64_t seed, uint64_t counter,
                          cudaStream_t st);
 
