@@ -295,6 +295,13 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
       for (auto& p : m->m->plans) p->graph_valid = false;
     }
     m->m->concurrent = value != 0;
+  } else if (k == "splitk") {
+    if (m->m->splitk != (value != 0)) {
+      EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
+      m->m->plans.clear();
+      m->m->last_plan = nullptr;
+    }
+    m->m->splitk = value != 0;
   } else if (k == "rowchain") {
     if (m->m->rowchain != (value != 0)) {
       EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));

@@ -168,8 +168,11 @@ struct GemmArgs {
   __nv_bfloat16 *out_hi = nullptr, *out_mid = nullptr;  // GEMM_SPLIT_OUT: [M, ld_out] planes
   int ld_out = 0;
   int bn = 0;        // 0 = choose
-  int split_k = 0;   // 0/1 = none (reserved)
+  int splits = 1;    // split-K factor (> 1 needs `counters` and a C that is zero-filled or accumulated onto)
+  int* counters = nullptr;  // one int per output tile, zero before the first launch (self-resetting)
 };
+
+void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* splits, int* tiles);
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
 

@@ -57,6 +57,11 @@ struct KParams {
   int flags;
   float alpha;
   int a_mn, b_mn;  // operand is MN-major (stored [K, MN] row-major)
+  // split-K (kFused kernel only): every output tile is computed by `splits` CTAs over disjoint
+  // k-block ranges; partial tiles are added into C with RED.ADD and the CTA that arrives last at the
+  // tile's counter re-reads the sum and runs the fused epilogue stages.
+  int splits, kb_per_split;
+  int* counters;
 };
 
 __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* mid, float v) {
@@ -82,6 +87,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const int stage_bytes = 2 * A_PLANE_BYTES + 2 * b_plane_bytes;
   const int num_kb = (p.K + BK - 1) / BK;
   const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_units = num_tiles * p.splits;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -123,10 +129,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       // is ordered behind these loads through the mbarrier pipeline.
       pdl_wait();
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit / p.splits;
+        const int kb0 = (unit % p.splits) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int m0 = (tile % p.tiles_m) * BM;
         const int n0 = (tile / p.tiles_m) * p.BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
@@ -161,13 +169,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN, p.a_mn != 0, p.b_mn != 0);
     uint32_t it = 0;
     uint32_t local_tile = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local_tile) {
       const uint32_t acc = local_tile & 1;
       const uint32_t use = local_tile >> 1;
+      const int kb0 = (unit % p.splits) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
       ptx::mbar_wait(&tmem_empty[acc], (use & 1) ^ 1, 2);  // epilogue drained this accumulator
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
         ptx::mbar_wait(&full_bar[s], ph, 3);  // TMA bytes have landed
@@ -189,12 +198,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t aa = a_step * k, ba = b_step * k;
             // small cross terms first, dominant hi*hi last
-            ptx::umma_f16<1>(d_tmem, a_mid + aa, b_hi + ba, idesc, (kb | k) != 0);
+            ptx::umma_f16<1>(d_tmem, a_mid + aa, b_hi + ba, idesc, (kb != kb0) || (k != 0));
             ptx::umma_f16<1>(d_tmem, a_hi + aa, b_mid + ba, idesc, 1);
             ptx::umma_f16<1>(d_tmem, a_hi + aa, b_hi + ba, idesc, 1);
           }
           ptx::umma_commit(&empty_bar[s]);                          // smem slot free when these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
         }
         __syncwarp();
       }
@@ -212,7 +221,137 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     uint32_t local_tile = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.H) & 15) == 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    // one 32-column chunk of one accumulator row through the fused stages; `v` holds alpha * acc, or
+    // (split-K, last CTA of the tile) the complete sum read back from C
+    auto finish_chunk = [&](float (&v)[32], const int row, const int col0, const bool from_memory) {
+      const int ncols = min(32, p.N - col0);
+      const bool row_ok = row < p.M;
+      const bool full = vec_ok && ncols == 32;
+      const size_t off = (size_t)row * p.ldc + col0;
+        if (kFused && (p.flags & GEMM_BIAS)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.bias + col0 + j));
+      }
+      if (row_ok) {
+        if (!from_memory && (p.flags & GEMM_ACCUMULATE)) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(p.C + off + j);
+              v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] += p.C[off + j];
+          }
+        }
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(p.C + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) p.C[off + j] = v[j];
+        }
+        // ---- second stage
+        if (!kFused) {
+        } else if (p.epi == EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (0.0f <= v[j]) ? v[j] : 0.0f;
+        } else if (p.epi == EPI_LEAKY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fmul_rn((0.0f <= v[j]) ? 1.0f : p.epi_param, v[j]);
+        } else if (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY) {
+          float h[32];
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(p.H + off + j);
+              h[j] = o.x; h[j + 1] = o.y; h[j + 2] = o.z; h[j + 3] = o.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = (j < ncols) ? p.H[off + j] : 0.0f;
+          }
+          if (p.epi == EPI_MASK_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (0.0f <= h[j]) ? v[j] : 0.0f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], (0.0f <= h[j]) ? 1.0f : p.epi_param);
+          }
+        } else if (p.epi == EPI_SGD) {
+          // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(p.D + off + j);
+              v[j] = __fadd_rn(o.x, __fmul_rn(0.0f - v[j], p.epi_param));
+              v[j + 1] = __fadd_rn(o.y, __fmul_rn(0.0f - v[j + 1], p.epi_param));
+              v[j + 2] = __fadd_rn(o.z, __fmul_rn(0.0f - v[j + 2], p.epi_param));
+              v[j + 3] = __fadd_rn(o.w, __fmul_rn(0.0f - v[j + 3], p.epi_param));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] = __fadd_rn(p.D[off + j], __fmul_rn(0.0f - v[j], p.epi_param));
+          }
+        }
+        if (kFused && p.epi != EPI_NONE) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.D + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) p.D[off + j] = v[j];
+          }
+        }
+        if (kFused && (p.flags & GEMM_SPLIT_OUT)) {
+          __nv_bfloat16* hrow = p.out_hi + (size_t)row * p.ld_out + col0;
+          __nv_bfloat16* mrow = p.out_mid + (size_t)row * p.ld_out + col0;
+          if (ncols == 32 && (p.ld_out & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __align__(16) __nv_bfloat16 hv[8];
+              __align__(16) __nv_bfloat16 mv[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split_store(&hv[e], &mv[e], v[j + e]);
+              *reinterpret_cast<uint4*>(hrow + j) = *reinterpret_cast<const uint4*>(hv);
+              *reinterpret_cast<uint4*>(mrow + j) = *reinterpret_cast<const uint4*>(mv);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) split_store(hrow + j, mrow + j, v[j]);
+          }
+        }
+      }
+      if (kFused && p.colsum) {
+        // column sums over the 32 rows this warp holds: butterfly transpose-reduce (31 shuffles);
+        // afterwards lane j holds the sum of column j. Rows outside the matrix contribute zero.
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (!row_ok || j >= ncols) v[j] = 0.0f;
+#pragma unroll
+        for (int offw = 16; offw >= 1; offw >>= 1) {
+          const bool upper = (lane & offw) != 0;
+#pragma unroll
+          for (int j = 0; j < offw; ++j) {
+            const float send = upper ? v[j] : v[j + offw];
+            const float keep = upper ? v[j + offw] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, offw);
+          }
+        }
+        if (lane < ncols) atomicAdd(p.colsum + col0 + lane, v[0]);
+      }
+    };
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local_tile) {
+      const int tile = unit / p.splits;
       const uint32_t acc = local_tile & 1;
       const uint32_t use = local_tile >> 1;
       const int m0 = (tile % p.tiles_m) * BM;
@@ -221,144 +360,65 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       ptx::tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+      const bool split = kFused && p.splits > 1;
       for (int c = 0; c < p.BN; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
         ptx::tmem_ld_wait();
         const int col0 = n0 + c;
         if (col0 >= p.N) break;  // warp-uniform
-        const int ncols = min(32, p.N - col0);
-        const bool row_ok = row < p.M;
-        const bool full = vec_ok && ncols == 32;
-        const size_t off = (size_t)row * p.ldc + col0;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (kFused && (p.flags & GEMM_BIAS)) {
+        if (!split) {
+          finish_chunk(v, row, col0, false);
+        } else if (row < p.M) {
+          // partial tile: add into C (zero-filled or holding the value to accumulate onto)
+          float* crow = p.C + (size_t)row * p.ldc + col0;
+          const int ncols = min(32, p.N - col0);
+          if (vec_ok && ncols == 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.bias + col0 + j));
-        }
-        if (row_ok) {
-          if (p.flags & GEMM_ACCUMULATE) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 o = *reinterpret_cast<const float4*>(p.C + off + j);
-                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] += p.C[off + j];
-            }
-          }
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.C + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: 4x fewer L2 atomic operations
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j), "f"(v[j]), "f"(v[j + 1]),
+                           "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < ncols) p.C[off + j] = v[j];
+              if (j < ncols) atomicAdd(crow + j, v[j]);
           }
-          // ---- second stage
-          if (!kFused) {
-          } else if (p.epi == EPI_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (0.0f <= v[j]) ? v[j] : 0.0f;
-          } else if (p.epi == EPI_LEAKY) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fmul_rn((0.0f <= v[j]) ? 1.0f : p.epi_param, v[j]);
-          } else if (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY) {
-            float h[32];
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 o = *reinterpret_cast<const float4*>(p.H + off + j);
-                h[j] = o.x; h[j + 1] = o.y; h[j + 2] = o.z; h[j + 3] = o.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) h[j] = (j < ncols) ? p.H[off + j] : 0.0f;
-            }
-            if (p.epi == EPI_MASK_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (0.0f <= h[j]) ? v[j] : 0.0f;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], (0.0f <= h[j]) ? 1.0f : p.epi_param);
-            }
-          } else if (p.epi == EPI_SGD) {
-            // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 o = *reinterpret_cast<const float4*>(p.D + off + j);
-                v[j] = __fadd_rn(o.x, __fmul_rn(0.0f - v[j], p.epi_param));
-                v[j + 1] = __fadd_rn(o.y, __fmul_rn(0.0f - v[j + 1], p.epi_param));
-                v[j + 2] = __fadd_rn(o.z, __fmul_rn(0.0f - v[j + 2], p.epi_param));
-                v[j + 3] = __fadd_rn(o.w, __fmul_rn(0.0f - v[j + 3], p.epi_param));
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] = __fadd_rn(p.D[off + j], __fmul_rn(0.0f - v[j], p.epi_param));
-            }
-          }
-          if (kFused && p.epi != EPI_NONE) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(p.D + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) p.D[off + j] = v[j];
-            }
-          }
-          if (kFused && (p.flags & GEMM_SPLIT_OUT)) {
-            __nv_bfloat16* hrow = p.out_hi + (size_t)row * p.ld_out + col0;
-            __nv_bfloat16* mrow = p.out_mid + (size_t)row * p.ld_out + col0;
-            if (ncols == 32 && (p.ld_out & 7) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __align__(16) __nv_bfloat16 hv[8];
-                __align__(16) __nv_bfloat16 mv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split_store(&hv[e], &mv[e], v[j + e]);
-                *reinterpret_cast<uint4*>(hrow + j) = *reinterpret_cast<const uint4*>(hv);
-                *reinterpret_cast<uint4*>(mrow + j) = *reinterpret_cast<const uint4*>(mv);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) split_store(hrow + j, mrow + j, v[j]);
-            }
-          }
-        }
-        if (kFused && p.colsum) {
-          // column sums over the 32 rows this warp holds: butterfly transpose-reduce (31 shuffles);
-          // afterwards lane j holds the sum of column j. Rows outside the matrix contribute zero.
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (!row_ok || j >= ncols) v[j] = 0.0f;
-#pragma unroll
-          for (int offw = 16; offw >= 1; offw >>= 1) {
-            const bool upper = (lane & offw) != 0;
-#pragma unroll
-            for (int j = 0; j < offw; ++j) {
-              const float send = upper ? v[j] : v[j + offw];
-              const float keep = upper ? v[j + offw] : v[j];
-              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, offw);
-            }
-          }
-          if (lane < ncols) atomicAdd(p.colsum + col0 + lane, v[0]);
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (split) {
+        // the CTA that increments the tile counter last owns the complete sum
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const int prev = atomicAdd(p.counters + tile, 1);
+          const bool last = prev == p.splits - 1;
+          if (last) p.counters[tile] = 0;  // self-resetting for the next launch
+          tmem_slot[1] = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool last = tmem_slot[1] != 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag may be rewritten by the next unit
+        if (last) {
+          __threadfence();
+          for (int c = 0; c < p.BN; c += 32) {
+            const int col0 = n0 + c;
+            if (col0 >= p.N) break;
+            float v[32];
+            const int ncols = min(32, p.N - col0);
+            const float* crow = p.C + (size_t)row * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (row < p.M && j < ncols) ? __ldcg(crow + j) : 0.0f;
+            finish_chunk(v, row, col0, true);
+          }
+        }
+      }
     }
   }
 
@@ -414,6 +474,22 @@ int choose_bn(int M, int N, int sm_count, bool b_mn) {
 
 }  // namespace
 
+void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* splits, int* tiles) {
+  *bn = choose_bn(M, N, sm_count, b_mn);
+  *tiles = ((M + BM - 1) / BM) * ((N + *bn - 1) / *bn);
+  const int num_kb = (K + BK - 1) / BK;
+  int s = 1;
+  // few tiles and a long reduction: one SM per tile would stream its whole K extent at the per-SM TMA
+  // rate (~100 GB/s) while the rest of the machine idles - split the reduction instead
+  if (*tiles * 2 <= sm_count && num_kb >= 4) {
+    s = sm_count / *tiles;
+    if (s > num_kb / 2) s = num_kb / 2;
+    if (s > 8) s = 8;
+    if (s < 1) s = 1;
+  }
+  *splits = s;
+}
+
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return;
   if (a.K <= 0) fail(EGB_ERR_GPU, "gemm: K must be positive");
@@ -432,6 +508,7 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   p.flags = a.flags; p.alpha = a.alpha;
   p.a_mn = a.a_mn ? 1 : 0;
   p.b_mn = a.b_mn ? 1 : 0;
+  p.counters = a.counters;
   p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, ctx.sm_count, a.b_mn);
   if (p.BN % 32 != 0 || p.BN < 32 || p.BN > 256) fail(EGB_ERR_GPU, "gemm: invalid BN %d", p.BN);
   if (a.b_mn && p.BN % 64 != 0) fail(EGB_ERR_GPU, "gemm: BN must be a multiple of 64 for an MN-major B operand");
@@ -458,9 +535,15 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   static const bool force_fused = getenv("EGB_GEMM_FUSED_ALWAYS") != nullptr;
-  const bool fused = force_fused || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.epi != EPI_NONE || a.colsum;
   const int tiles = p.tiles_m * p.tiles_n;
-  const int grid = tiles < ctx.sm_count ? tiles : ctx.sm_count;
+  const int num_kb = (a.K + BK - 1) / BK;
+  int splits = (a.splits > 1 && a.counters) ? a.splits : 1;
+  if (splits > num_kb) splits = num_kb;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  const int units = tiles * p.splits;
+  const bool fused = force_fused || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.epi != EPI_NONE || a.colsum || p.splits > 1;
+  const int grid = units < ctx.sm_count ? units : ctx.sm_count;
   {
     Launch l(ctx, KC_GEMM, st);
     if (fused)

@@ -422,6 +422,15 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.gemm.ldc = (int)g.ldc;
       n.gemm.flags = inf.overwrite ? 0 : GEMM_ACCUMULATE;
       n.gemm.alpha = 1.0f;
+      n.gemm.bn = inf.bn;
+      if (inf.splits > 1) {
+        const size_t cbytes = align_up((size_t)inf.tiles * sizeof(int), 256);
+        if (plane_cursor + cbytes > plane_cap) fail(EGB_ERR_RUNTIME, "internal: operand plane arena exhausted");
+        n.gemm.counters = (int*)(plane_base + plane_cursor);  // zero since arena creation, self-resetting
+        plane_cursor += cbytes;
+        n.gemm.splits = inf.splits;
+        n.label += " splitK=" + std::to_string(inf.splits);
+      }
       if (inf.bias_tensor) {
         n.gemm.flags |= GEMM_BIAS;
         n.gemm.bias = (const float*)ptrs[inf.bias_tensor];
@@ -596,6 +605,15 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
       const size_t a_bytes = std::max((size_t)g.K * pad8(g.M), (size_t)g.M * pad8(g.K)) * 2;
       const size_t b_bytes = std::max((size_t)g.N * pad8(g.K), (size_t)g.K * pad8(g.N)) * 2;
       plane_bytes += 2 * align_up(a_bytes, 256) + 2 * align_up(b_bytes, 256);
+      const bool b_copy = !g.trans_b && prefer_transposed_copy(g.K, g.N);
+      gemm_choose_config((int)g.M, (int)g.N, (int)g.K, !g.trans_b && !b_copy, ctx->sm_count, &inf.bn, &inf.splits,
+                         &inf.tiles);
+      if (!splitk) inf.splits = 1;
+      if (inf.splits > 1) {
+        plane_bytes += align_up((size_t)inf.tiles * sizeof(int), 256);  // tile counters
+        // partial tiles are added into C: it must start from zero unless it is accumulated onto anyway
+        if (inf.overwrite) needs_zero.insert(wt);
+      }
     }
     inf.final_tensor = wt;
     if (!(inf.is_gemm && inf.overwrite && fuse)) continue;

@@ -83,6 +83,7 @@ struct KernelInfo {
   float epi_param = 0.0f;
   int final_tensor = 0;       // tensor that holds the final epilogue value (C or D)
   bool emit_planes = false;   // the epilogue also writes bf16 operand planes of the final value
+  int bn = 0, splits = 1, tiles = 0;  // tile width, split-K factor and tile count of a contraction
 };
 
 struct Plan {
@@ -125,6 +126,10 @@ struct Model {
   bool fuse = true;         // epilogue fusion of contraction + elementwise / column-sum / SGD kernels
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   bool rowchain = true;     // runs of small row-local kernels execute in one launch
+  // split-K for contractions with few output tiles (RED.ADD partial tiles + last-arriver epilogue).
+  // Measured on the dense step it loses to the unsplit kernel (161 vs 150 us: zero-filling C, L2
+  // atomics and the re-read cost more than the shorter k-loops save), so it is off by default.
+  bool splitk = false;
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   CommHooks* comm = nullptr;
