@@ -27,11 +27,12 @@ struct ConvDims {
 };
 
 // ------------------------------------------------------------------ forward
-// block: 8 filter groups (filters g*4..g*4+3 and 32+g*4..32+g*4+3) x TQ pixel quads (4 consecutive x each), TQ <= 32 chosen by
+// block: 8 filter groups (filters g*4..g*4+3 and 32+g*4..32+g*4+3) x TQ pixel groups (PXT consecutive x each), TQ <= 32 chosen by
 // the host so that the strips divide the output row evenly. A block walks ROWS_FWD consecutive output
 // rows of its strip: the filter bank is staged once, the KH input rows live in a ring buffer so that
 // every new output row stages only one new input row.
 constexpr int ROWS_FWD = 8;
+constexpr int PXT = 4;          // output pixels per thread (forward; 8 was measured slower: 1.88 vs 1.63 ms)
 
 template <int KW_T>
 __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
@@ -44,9 +45,9 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
   const int tx = tid & 7, tq = tid >> 3;
   const int fchunks = (d.F + FC - 1) / FC;
   const int n = blockIdx.z / fchunks, f0 = (blockIdx.z % fchunks) * FC;
-  const int y0 = blockIdx.y * ROWS_FWD, x0 = blockIdx.x * tq_n * 4;
+  const int y0 = blockIdx.y * ROWS_FWD, x0 = blockIdx.x * tq_n * PXT;
   const int y1 = min(y0 + ROWS_FWD, d.OH);
-  const int in_w = tq_n * 4 + KW - 1;               // staged input pixels per row
+  const int in_w = tq_n * PXT + KW - 1;             // staged input pixels per row
   float* in_s = smem;                               // ring: [KH][in_w * cc]
   float* w_s = smem + d.KH * in_w * MAX_CC;         // [KH*KW*cc][FC]
   const int fb = f0 + tx * 4;                       // this thread's filters: fb..fb+3 and fb+32..fb+35
@@ -80,26 +81,26 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
         }
       }
       __syncthreads();
-      float acc[4][8];
+      float acc[PXT][8];
 #pragma unroll
-      for (int p = 0; p < 4; ++p)
+      for (int p = 0; p < PXT; ++p)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[p][j] = 0.0f;
       if (tq < tq_n) {
         for (int dy = 0; dy < d.KH; ++dy) {
-          const float* row = in_s + ((y + dy) % d.KH) * row_len + tq * 4 * cc;
+          const float* row = in_s + ((y + dy) % d.KH) * row_len + tq * PXT * cc;
           if (KW_T > 0) {
             for (int ch = 0; ch < cc; ++ch) {
-              float iv[4 + (KW_T > 0 ? KW_T : 1) - 1];
+              float iv[PXT + (KW_T > 0 ? KW_T : 1) - 1];
 #pragma unroll
-              for (int t = 0; t < 4 + KW_T - 1; ++t) iv[t] = row[t * cc + ch];
+              for (int t = 0; t < PXT + KW_T - 1; ++t) iv[t] = row[t * cc + ch];
 #pragma unroll
               for (int dx = 0; dx < KW_T; ++dx) {
                 const float4* wp = reinterpret_cast<const float4*>(w_s + ((dy * KW_T + dx) * cc + ch) * FC) + tx;
                 const float4 w0 = wp[0], w1 = wp[8];   // filters tx*4.. and 32+tx*4..: conflict-free 128-byte rows
                 const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int p = 0; p < 4; ++p)
+                for (int p = 0; p < PXT; ++p)
 #pragma unroll
                   for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv[p + dx], wv[j], acc[p][j]);
               }
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
                 const float4 w0 = wp[0], w1 = wp[8];
                 const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
+                for (int p = 0; p < PXT; ++p) {
                   const float iv = row[(p + dx) * cc + ch];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(iv, wv[j], acc[p][j]);
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
         // channel chunks after the first accumulate into what the first one stored
         const bool acc_out = accumulate || c0 > 0;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int x = x0 + tq * 4 + p;
+        for (int p = 0; p < PXT; ++p) {
+          const int x = x0 + tq * PXT + p;
           if (x >= d.OW) continue;
           float* o = out + (((size_t)n * d.OH + y) * d.OW + x) * d.F + fb;
           if (vec) {
@@ -150,10 +151,10 @@ __global__ void __launch_bounds__(256) conv2_fwd_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------ d_filters
-// Persistent blocks; a work item is (n, y, 64-pixel chunk of the output row). 256 threads = 4 pixel
-// sets x (16 filter groups of 4) x (4 k groups); a thread accumulates 4 filters x 8 filter taps
-// (k = kc*32 + kg + 4*i) in registers over all its work items, the block reduces the 4 pixel sets
-// through shared memory and flushes once with atomicAdd.
+// Persistent blocks; a work item is (n, y, <=64-pixel chunk of the output row). 256 threads = 8 pixel
+// sets x (8 filter groups: filters g*4..g*4+3 and 32+g*4..32+g*4+3) x (4 tap groups); a thread
+// accumulates 8 filters x 8 filter taps (k = kc*32 + kg + 4*i) in registers over all its work items,
+// the block reduces the 8 pixel sets through shared memory and flushes once with atomicAdd.
 __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__ img, const float* __restrict__ dout,
                                                        float* __restrict__ dw, ConvDims d, int txw) {
   extern __shared__ float smem[];
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
   const int kchunks = (K + 31) / 32, fchunks = (d.F + FC - 1) / FC;
   const int kc = blockIdx.y % kchunks, f0 = (blockIdx.y / kchunks) * FC;
   const int tid = threadIdx.x;
-  const int ps = tid >> 6, r = tid & 63, fg = r & 15, kg = r >> 4;
+  const int ps = tid >> 5, r = tid & 31, fg = r & 7, kg = r >> 3;
   const int in_w = (txw + d.KW - 1) * d.C;          // staged floats per input row (all channels)
   (void)fchunks;
   int koff[8];
@@ -176,11 +177,11 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
     const int ch = kk % d.C, dx = (kk / d.C) % d.KW, dy = kk / (d.C * d.KW);
     koff[i] = dy * in_w + dx * d.C + ch;
   }
-  float acc[8][4];
+  float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
 
   const int xchunks = (d.OW + txw - 1) / txw;
   const long items = (long)d.N * d.OH * xchunks;
@@ -233,42 +234,45 @@ __global__ void __launch_bounds__(256) conv2_dw_kernel(const float* __restrict__
     const float* img_c = dout_c + TX_BWD * FC;
     const int x0 = (int)(it % xchunks) * txw;
     const int npx = min(txw, d.OW - x0);
-    for (int px = ps; px < npx; px += 4) {
-      const float4 dv = *reinterpret_cast<const float4*>(dout_c + px * FC + fg * 4);
+    for (int px = ps; px < npx; px += 8) {
+      const float4 d0 = *reinterpret_cast<const float4*>(dout_c + px * FC + fg * 4);
+      const float4 d1 = *reinterpret_cast<const float4*>(dout_c + px * FC + 32 + fg * 4);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float iv = img_c[koff[i] + px * d.C];
-        acc[i][0] = fmaf(iv, dv.x, acc[i][0]);
-        acc[i][1] = fmaf(iv, dv.y, acc[i][1]);
-        acc[i][2] = fmaf(iv, dv.z, acc[i][2]);
-        acc[i][3] = fmaf(iv, dv.w, acc[i][3]);
+        acc[i][0] = fmaf(iv, d0.x, acc[i][0]);
+        acc[i][1] = fmaf(iv, d0.y, acc[i][1]);
+        acc[i][2] = fmaf(iv, d0.z, acc[i][2]);
+        acc[i][3] = fmaf(iv, d0.w, acc[i][3]);
+        acc[i][4] = fmaf(iv, d1.x, acc[i][4]);
+        acc[i][5] = fmaf(iv, d1.y, acc[i][5]);
+        acc[i][6] = fmaf(iv, d1.z, acc[i][6]);
+        acc[i][7] = fmaf(iv, d1.w, acc[i][7]);
       }
     }
     __syncthreads();   // everyone is done with this buffer before it is refilled
     buf ^= 1;
   }
-  // reduce the 4 pixel sets, then one atomic per (filter, tap) and block
+  // reduce the 8 pixel sets, then one atomic per (filter, tap) and block
   __syncthreads();
-  float* red = smem;  // [4 sets][64 threads][32 values]
+  float* red = smem;  // [8 sets][32 threads][64 values (+1 pad)]
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[(ps * 64 + r) * 33 + i * 4 + j] = acc[i][j];
+    for (int j = 0; j < 8; ++j) red[(ps * 32 + r) * 65 + i * 8 + j] = acc[i][j];
   __syncthreads();
-  if (ps == 0) {
+  // 32 threads x 64 values = 2048 sums: every thread of the block takes 8 of them
+  for (int e = tid; e < 32 * 64; e += 256) {
+    const int rr = e >> 6, idx = e & 63;
+    const int i = idx >> 3, j = idx & 7;
+    const int kg2 = rr >> 3, fg2 = rr & 7;
+    const int k = kc * 32 + kg2 + 4 * i;
+    const int f = f0 + (j & 3) + (j >> 2) * 32 + fg2 * 4;
+    if (k >= K || f >= d.F) continue;
+    float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (!kval[i]) continue;
-      const int k = kc * 32 + kg + 4 * i;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int f = f0 + fg * 4 + j;
-        if (f >= d.F) continue;
-        const float s = red[(0 * 64 + r) * 33 + i * 4 + j] + red[(1 * 64 + r) * 33 + i * 4 + j] +
-                        red[(2 * 64 + r) * 33 + i * 4 + j] + red[(3 * 64 + r) * 33 + i * 4 + j];
-        atomicAdd(dw + (size_t)f * K + k, s);
-      }
-    }
+    for (int set = 0; set < 8; ++set) s += red[(set * 32 + rr) * 65 + idx];
+    atomicAdd(dw + (size_t)f * K + k, s);
   }
 }
 
@@ -292,8 +296,8 @@ __global__ void __launch_bounds__(256) conv2_dimg_kernel(const float* __restrict
   const int n = blockIdx.z, iy0 = blockIdx.y * ROWS_DIMG, ix0 = blockIdx.x * tq_n * 4;
   const int iy1 = min(iy0 + ROWS_DIMG, d.H);
   const int tw = tq_n * 4 + KW - 1;                  // staged dout pixels per row
-  float* dout_s = smem;                              // ring: [KH][tw][FC]
-  float* w_s = smem + d.KH * tw * FC;                // [KH][KW][4 filters of a slice][16 slices][4 channels]
+  float* dout_s = smem;                              // ring: [KH+1][tw][FC]
+  float* w_s = smem + (d.KH + 1) * tw * FC;          // [KH][KW][4 filters of a slice][16 slices][4 channels]
   const int fchunks = (d.F + FC - 1) / FC;
   for (int c0 = 0; c0 < d.C; c0 += MAX_CC) {
     const int cc = min(MAX_CC, d.C - c0);
@@ -306,30 +310,40 @@ __global__ void __launch_bounds__(256) conv2_dimg_kernel(const float* __restrict
         const int f = f0 + sl * 4 + j;
         w_s[i] = (c < cc && f < d.F) ? __ldg(w + (((size_t)f * d.KH + dy) * KW + dx) * d.C + c0 + c) : 0.0f;
       }
-      for (int iy = iy0; iy < iy1; ++iy) {
-        // ring slot of dout row oy is oy mod KH; rows iy-KH+1 .. iy are needed, only row iy is new
-        __syncthreads();
-        for (int r = (iy == iy0 ? 0 : d.KH - 1); r < d.KH; ++r) {
-          const int oy = iy - (d.KH - 1) + r;
-          float* dst = dout_s + (((oy % d.KH) + d.KH) % d.KH) * tw * FC;
-          const bool row_ok = oy >= 0 && oy < d.OH;
-          for (int i = tid; i < tw * (FC / 4); i += nthreads) {
-            const int f4 = (i % (FC / 4)) * 4, t = i / (FC / 4);
-            const int ox = ix0 - (KW - 1) + t;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok && ox >= 0 && ox < d.OW) {
-              const float* src = dout + (((size_t)n * d.OH + oy) * d.OW + ox) * d.F + f0 + f4;
-              if ((d.F & 3) == 0 && f0 + f4 + 4 <= d.F) {
-                v = __ldg(reinterpret_cast<const float4*>(src));
-              } else {
-                if (f0 + f4 + 0 < d.F) v.x = __ldg(src + 0);
-                if (f0 + f4 + 1 < d.F) v.y = __ldg(src + 1);
-                if (f0 + f4 + 2 < d.F) v.z = __ldg(src + 2);
-                if (f0 + f4 + 3 < d.F) v.w = __ldg(src + 3);
-              }
-            }
-            *reinterpret_cast<float4*>(dst + t * FC + f4) = v;
+      // ring of KH+1 dout rows (slot = oy mod (KH+1)): row iy+1 streams in with cp.async while row iy is
+      // being processed
+      const int ring = d.KH + 1;
+      const bool f_vec = (d.F & 3) == 0;
+      auto stage_row = [&](int oy) {
+        float* dst = dout_s + (((oy % ring) + ring) % ring) * tw * FC;
+        const bool row_ok = oy >= 0 && oy < d.OH;
+        const int oyc = min(max(oy, 0), d.OH - 1);
+        for (int i = tid; i < tw * (FC / 4); i += nthreads) {
+          const int f4 = (i % (FC / 4)) * 4, t = i / (FC / 4);
+          const int ox = ix0 - (KW - 1) + t;
+          const bool ok = row_ok && ox >= 0 && ox < d.OW;
+          const int oxc = min(max(ox, 0), d.OW - 1);
+          const float* src = dout + (((size_t)n * d.OH + oyc) * d.OW + oxc) * d.F + f0 + f4;
+          float* o = dst + t * FC + f4;
+          if (f_vec && f0 + f4 + 4 <= d.F) {
+            const unsigned bytes = ok ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(o)), "l"(src),
+                         "r"(bytes) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = (ok && f0 + f4 + j < d.F) ? __ldg(src + j) : 0.0f;
           }
+        }
+      };
+      for (int r = 0; r < d.KH; ++r) stage_row(iy0 - (d.KH - 1) + r);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      for (int iy = iy0; iy < iy1; ++iy) {
+        if (iy + 1 < iy1) {
+          stage_row(iy + 1);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         float acc[4][MAX_CC];
@@ -339,7 +353,7 @@ __global__ void __launch_bounds__(256) conv2_dimg_kernel(const float* __restrict
           for (int c = 0; c < MAX_CC; ++c) acc[p][c] = 0.0f;
         for (int dy = 0; dy < d.KH; ++dy) {
           const int oy = iy - dy;
-          const float* rowp = dout_s + (((oy % d.KH) + d.KH) % d.KH) * tw * FC;
+          const float* rowp = dout_s + (((oy % ring) + ring) % ring) * tw * FC;
           // pixel ix = ix0 + q*4 + p receives dout[.., ix - dx, ..]: staged column t = q*4 + p - dx + KW-1
           float4 e[4 + KW - 1];
 #pragma unroll
@@ -382,6 +396,7 @@ __global__ void __launch_bounds__(256) conv2_dimg_kernel(const float* __restrict
               if (c < cc) o[c] = acc_out ? o[c] + acc[p][c] : acc[p][c];
           }
         }
+        __syncthreads();   // the ring slot of the oldest row is refilled next
       }
     }
   }
@@ -398,20 +413,21 @@ void check_dims(const ConvDims& d) {
 
 // Pixel quads per block: the smallest block count that covers the row, then the smallest strip that
 // still covers it with that many blocks (e.g. OW = 222 -> 2 strips of 28 quads instead of 32 + 24).
-static int quads_per_block(int pixels, int max_quads) {
-  const int quads = (pixels + 3) / 4;
-  const int blocks = (quads + max_quads - 1) / max_quads;
-  return (quads + blocks - 1) / blocks;
+static int groups_per_block(int pixels, int group, int max_groups) {
+  const int groups = (pixels + group - 1) / group;
+  const int blocks = (groups + max_groups - 1) / max_groups;
+  return (groups + blocks - 1) / blocks;
 }
+static int quads_per_block(int pixels, int max_quads) { return groups_per_block(pixels, 4, max_quads); }
 
 void launch_conv2_fwd(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
                       int KH, int KW, bool accumulate, cudaStream_t st) {
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
   const int cc = C < MAX_CC ? C : MAX_CC;
-  const int tq = quads_per_block(d.OW, 32);
-  const size_t smem = ((size_t)KH * (tq * 4 + KW - 1) * MAX_CC + (size_t)KH * KW * cc * FC) * sizeof(float);
-  dim3 grid((d.OW + tq * 4 - 1) / (tq * 4), (d.OH + ROWS_FWD - 1) / ROWS_FWD, N * ((F + FC - 1) / FC));
+  const int tq = groups_per_block(d.OW, PXT, 32);
+  const size_t smem = ((size_t)KH * (tq * PXT + KW - 1) * MAX_CC + (size_t)KH * KW * cc * FC) * sizeof(float);
+  dim3 grid((d.OW + tq * PXT - 1) / (tq * PXT), (d.OH + ROWS_FWD - 1) / ROWS_FWD, N * ((F + FC - 1) / FC));
   Launch l(ctx, KC_CONV, st);
   if (KW == 3) {
     EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -429,7 +445,7 @@ void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* d
   const int K = KH * KW * C;
   const int txw = quads_per_block(d.OW, TX_BWD / 4) * 4;   // even chunks of the output row, <= 64 pixels
   const size_t stage = 2 * (((size_t)TX_BWD * FC + (size_t)KH * (txw + KW - 1) * C + 3) & ~size_t(3)) * sizeof(float);
-  const size_t red = (size_t)4 * 64 * 33 * sizeof(float);
+  const size_t red = (size_t)8 * 32 * 65 * sizeof(float);
   const size_t smem = stage > red ? stage : red;
   dim3 grid(ctx.sm_count * 3, ((K + 31) / 32) * ((F + FC - 1) / FC));
   EGB_CUDA(cudaFuncSetAttribute(conv2_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -442,7 +458,7 @@ void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* d
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
   const int tq = quads_per_block(W, 16);
-  const size_t smem = ((size_t)KH * (tq * 4 + KW - 1) * FC + (size_t)KH * KW * FC * MAX_CC) * sizeof(float);
+  const size_t smem = ((size_t)(KH + 1) * (tq * 4 + KW - 1) * FC + (size_t)KH * KW * FC * MAX_CC) * sizeof(float);
   dim3 grid((W + tq * 4 - 1) / (tq * 4), (H + ROWS_DIMG - 1) / ROWS_DIMG, N);
   Launch l(ctx, KC_CONV, st);
 #define EGB_DIMG(KWT)                                                                                       \
