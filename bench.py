@@ -13,6 +13,8 @@ Workloads (BASELINE.json `configs`), both driven through the public model API
                       NCCL all-reduce of the parameter-gradient bucket (metric train samples/s).
                       Reported inside the same JSON line under "dense_train" (or as the primary line
                       with --workload dense).
+  conv2   configs[3]  NHWC 256x224x224x3 images, 64 3x3x3 filters: forward, d_filters and d_images kernels
+                      (HBM-bound; reported under "conv2_fwd_bwd" at N=1, or with --workload conv2).
 A "step" is one pass of the hot path over one batch of synthetic input.
 
 `value`    device-resident throughput (inputs already in HBM when the timed region starts)
@@ -458,6 +460,7 @@ def main():
     ap.add_argument("--workload", default="matmul", choices=["matmul", "dense", "conv2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense_train block of the matmul line")
+    ap.add_argument("--no-conv", action="store_true", help="skip the conv2_fwd_bwd block of the matmul line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -485,6 +488,8 @@ def main():
         out = run_matmul(args, ctx, timer, rank, world, sampler)
         if not args.no_dense:
             out["dense_train"] = run_dense(args, ctx, timer, rank, world, comm)
+        if not args.no_conv and world == 1:
+            out["conv2_fwd_bwd"] = run_conv2(args, ctx, timer, rank, world)
     elif args.workload == "conv2":
         out = run_conv2(args, ctx, timer, rank, world)
         out["warmup"] = args.warmup
