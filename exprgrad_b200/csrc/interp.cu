@@ -179,10 +179,21 @@ __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constan
 // kernels) executes in ONE launch: each warp owns rows and runs the whole chain for its row,
 // exchanging intermediate tensors through global memory with only __syncwarp() in between.
 // Programs are in "row form": loops[0] is the row loop (start 0, step 1).
-__global__ void __launch_bounds__(IP_THREADS) interp_rowchain_kernel(const IpProgram* __restrict__ progs, int nprogs,
+__global__ void __launch_bounds__(IP_THREADS) interp_rowchain_kernel(const IpProgram* __restrict__ gprogs, int nprogs,
                                                                      int64_t rows) {
+  // the programs are staged into shared memory once per block: fetching them field by field from
+  // global memory costs an L2 round trip per cache line on every warp's critical path
+  extern __shared__ __align__(16) unsigned char chain_smem[];
+  IpProgram* progs = reinterpret_cast<IpProgram*>(chain_smem);
   Slot s[IP_MAX_SLOTS];
   pdl_launch_dependents();
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(gprogs);
+    uint4* dst = reinterpret_cast<uint4*>(chain_smem);
+    const int n16 = (int)(nprogs * sizeof(IpProgram) / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);  // written before the graph ran
+  }
+  __syncthreads();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -354,7 +365,8 @@ void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs
   const int64_t cap = (int64_t)ctx.sm_count * 8;
   {
     Launch l(ctx, KC_INTERP, st);
-    launch_kernel(ctx, interp_rowchain_kernel, dim3((int)(nb < cap ? nb : cap)), dim3(IP_THREADS), 0, st, dev_progs, nprogs,
+    const size_t smem = (size_t)nprogs * sizeof(IpProgram);
+    launch_kernel(ctx, interp_rowchain_kernel, dim3((int)(nb < cap ? nb : cap)), dim3(IP_THREADS), smem, st, dev_progs, nprogs,
                   rows);
   }
   EGB_CUDA(cudaGetLastError());

@@ -58,7 +58,7 @@ struct IpLoop {
   uint8_t pad[7];
 };
 
-struct IpProgram {
+struct alignas(16) IpProgram {
   // loops[0 .. npar) are the independent loops (thread-mapped, last one fastest);
   // loops[npar .. nloops) are reduction loops in the reference's nesting order (outermost first).
   IpLoop loops[IP_MAX_LOOPS];
@@ -76,5 +76,8 @@ struct IpProgram {
   uint8_t scatter;                   // write index depends on a reduction loop: read-modify-write per iteration
   uint8_t vec4;                      // pure streaming elementwise kernel: eligible for the 4-wide fast path
 };
+
+static_assert(sizeof(IpProgram) % 16 == 0, "IpProgram is copied in 16-byte units");
+static_assert(sizeof(IpProgram) <= 4000, "IpProgram travels as a kernel parameter");
 
 }  // namespace egb

@@ -225,6 +225,7 @@ bool fuse_row_chains(Model& m, Plan& plan) {
     for (; end <= max_level && level_ok(end); ++end) {
       std::vector<int> trial = members;
       for (int i : by_level[end]) trial.push_back(i);
+      if (trial.size() * sizeof(IpProgram) > 44 * 1024) break;  // the chain's programs live in shared memory
       // rows = leading dimension shared by all written tensors of the trial group
       int64_t r = -1;
       bool ok = true;
