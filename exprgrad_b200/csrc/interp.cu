@@ -13,6 +13,8 @@
 // accumulation order (bit-exact mode).
 #include <math.h>
 
+#include <type_traits>
+
 #include "egb_internal.hpp"
 #include "interp.hpp"
 
@@ -27,7 +29,20 @@ union Slot {
 
 constexpr int IP_THREADS = 256;
 
-__device__ __forceinline__ void run_instrs(const IpInstr* __restrict__ ins, int n, Slot* s, const IpProgram& p) {
+// The register file of the interpreted program. In local memory every first touch of a slot is a
+// cache miss on the thread's stack (the dominant cost of small kernels: ~5 us for a ten-instruction
+// program); programs that fit IP_SMEM_SLOTS keep it in shared memory instead, laid out [slot][thread].
+struct LocalSlots {
+  Slot* s;
+  __device__ __forceinline__ Slot& operator[](int i) const { return s[i]; }
+};
+struct SharedSlots {
+  Slot* base;  // already offset by the thread index
+  __device__ __forceinline__ Slot& operator[](int i) const { return base[i * IP_THREADS]; }
+};
+
+template <class S>
+__device__ __forceinline__ void run_instrs(const IpInstr* __restrict__ ins, int n, S s, const IpProgram& p) {
   for (int k = 0; k < n; ++k) {
     const IpInstr in = ins[k];
     Slot r;
@@ -77,14 +92,16 @@ __device__ __forceinline__ void run_instrs(const IpInstr* __restrict__ ins, int 
   }
 }
 
-__device__ __forceinline__ int64_t flat_index(const IpTensorOp& op, const Slot* s) {
+template <class S>
+__device__ __forceinline__ int64_t flat_index(const IpTensorOp& op, S s) {
   int64_t idx = op.offset;
   for (int t = 0; t < op.nterms; ++t) idx += op.coef[t] * s[op.slot[t]].i;
   return idx;
 }
 
 // Decode a linear index into the iterators of loops [lo, hi) (last loop fastest).
-__device__ __forceinline__ void decode(const IpProgram& p, int lo, int hi, int64_t lin, Slot* s) {
+template <class S>
+__device__ __forceinline__ void decode(const IpProgram& p, int lo, int hi, int64_t lin, S s) {
   if (lin < 0x7fffffffLL) {
     uint32_t v = (uint32_t)lin;
     for (int l = hi - 1; l >= lo; --l) {
@@ -104,11 +121,15 @@ __device__ __forceinline__ void decode(const IpProgram& p, int lo, int hi, int64
   }
 }
 
-template <bool kStrict>
+template <bool kStrict, bool kSmemSlots>
 __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constant__ IpProgram p, int pb, int rb,
                                                             int points_fast) {
   __shared__ float partial[IP_THREADS];
-  Slot s[IP_MAX_SLOTS];
+  extern __shared__ __align__(16) unsigned char slot_smem[];
+  Slot local_slots[kSmemSlots ? 1 : IP_MAX_SLOTS];
+  typename std::conditional<kSmemSlots, SharedSlots, LocalSlots>::type s;
+  if constexpr (kSmemSlots) s.base = reinterpret_cast<Slot*>(slot_smem) + threadIdx.x;
+  else s.s = local_slots;
   const int t = threadIdx.x;
   const int pl = points_fast ? t % pb : t / rb;  // point within the block
   const int rl = points_fast ? t / pb : t % rb;  // reduction slice
@@ -185,7 +206,8 @@ __global__ void __launch_bounds__(IP_THREADS) interp_rowchain_kernel(const IpPro
   // global memory costs an L2 round trip per cache line on every warp's critical path
   extern __shared__ __align__(16) unsigned char chain_smem[];
   IpProgram* progs = reinterpret_cast<IpProgram*>(chain_smem);
-  Slot s[IP_MAX_SLOTS];
+  SharedSlots s;  // register file in shared memory, behind the programs (the host guarantees that it fits)
+  s.base = reinterpret_cast<Slot*>(chain_smem + (size_t)nprogs * sizeof(IpProgram)) + threadIdx.x;
   pdl_launch_dependents();
   {
     const uint4* src = reinterpret_cast<const uint4*>(gprogs);
@@ -358,14 +380,20 @@ __global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_co
 
 }  // namespace
 
-void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int64_t rows, cudaStream_t st) {
+void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int max_slots, int64_t rows,
+                            cudaStream_t st) {
   if (rows <= 0 || nprogs <= 0) return;
   const int64_t warps_per_block = IP_THREADS / 32;
   const int64_t nb = (rows + warps_per_block - 1) / warps_per_block;
   const int64_t cap = (int64_t)ctx.sm_count * 8;
   {
     Launch l(ctx, KC_INTERP, st);
-    const size_t smem = (size_t)nprogs * sizeof(IpProgram);
+    const size_t smem = (size_t)nprogs * sizeof(IpProgram) + (size_t)max_slots * IP_THREADS * sizeof(Slot);
+    static bool attr_set = false;
+    if (!attr_set) {
+      EGB_CUDA(cudaFuncSetAttribute(interp_rowchain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
     launch_kernel(ctx, interp_rowchain_kernel, dim3((int)(nb < cap ? nb : cap)), dim3(IP_THREADS), smem, st, dev_progs, nprogs,
                   rows);
   }
@@ -392,8 +420,15 @@ void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int poin
   const int grid = (int)(nblocks < cap ? nblocks : cap);
   {
     Launch l(ctx, KC_INTERP, st);
-    if (strict) launch_kernel(ctx, interp_kernel<true>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
-    else launch_kernel(ctx, interp_kernel<false>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
+    const bool smem_slots = prog.nslots <= IP_SMEM_SLOTS;
+    const size_t smem = smem_slots ? (size_t)prog.nslots * IP_THREADS * sizeof(Slot) : 0;
+    if (strict) {
+      if (smem_slots) launch_kernel(ctx, interp_kernel<true, true>, dim3(grid), dim3(IP_THREADS), smem, st, prog, pb, rb, points_fast);
+      else launch_kernel(ctx, interp_kernel<true, false>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
+    } else {
+      if (smem_slots) launch_kernel(ctx, interp_kernel<false, true>, dim3(grid), dim3(IP_THREADS), smem, st, prog, pb, rb, points_fast);
+      else launch_kernel(ctx, interp_kernel<false, false>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
+    }
   }
   EGB_CUDA(cudaGetLastError());
 }

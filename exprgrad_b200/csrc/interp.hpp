@@ -17,6 +17,7 @@ constexpr int IP_MAX_OPS = 12;     // reads
 constexpr int IP_MAX_TERMS = 8;    // (slot, coefficient) terms of one flattened tensor index
 constexpr int IP_MAX_INSTRS = 160;
 constexpr int IP_MAX_SLOTS = 192;
+constexpr int IP_SMEM_SLOTS = 22;  // 22 slots x 256 threads x 8 B = 44 KB of shared memory
 
 enum IpOp : uint8_t {
   IP_NOP = 0,
@@ -75,6 +76,7 @@ struct alignas(16) IpProgram {
   uint8_t accumulate;                // 1: out += value (InstrWrite), 0: out = value (InstrOverwrite)
   uint8_t scatter;                   // write index depends on a reduction loop: read-modify-write per iteration
   uint8_t vec4;                      // pure streaming elementwise kernel: eligible for the 4-wide fast path
+  uint8_t nslots;                    // registers used (<= IP_SMEM_SLOTS: the register file lives in shared memory)
 };
 
 static_assert(sizeof(IpProgram) % 16 == 0, "IpProgram is copied in 16-byte units");

@@ -608,6 +608,7 @@ Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<i
     }
     ip.vec4 = ok ? 1 : 0;
   }
+  ip.nslots = (uint8_t)std::min(lw.nslots, 255);
 
   Lowered out;
   out.uses_epoch = lw.uses_epoch;

@@ -225,7 +225,10 @@ bool fuse_row_chains(Model& m, Plan& plan) {
     for (; end <= max_level && level_ok(end); ++end) {
       std::vector<int> trial = members;
       for (int i : by_level[end]) trial.push_back(i);
-      if (trial.size() * sizeof(IpProgram) > 44 * 1024) break;  // the chain's programs live in shared memory
+      // the chain's programs and its register file live in shared memory (<= 96 KB)
+      int trial_slots = 1;
+      for (int i : trial) trial_slots = std::max(trial_slots, (int)plan.nodes[i].ip.nslots + 1);  // +1: row iterator
+      if (trial.size() * sizeof(IpProgram) + (size_t)trial_slots * 256 * 8 > 92 * 1024) break;
       // rows = leading dimension shared by all written tensors of the trial group
       int64_t r = -1;
       bool ok = true;
@@ -272,6 +275,11 @@ bool fuse_row_chains(Model& m, Plan& plan) {
       EGB_CUDA(cudaStreamSynchronize(m.ctx->stream));  // `progs` is a local
       chain.chain_progs = (IpProgram*)dev;
       chain.chain_n = (int)progs.size();
+      for (auto& pr : progs) {
+        int used = 0;   // highest slot index referenced + 1 (to_row_form may have added the row iterator)
+        for (int q = 0; q < pr.nloops; ++q) used = std::max(used, pr.loops[q].slot + 1);
+        chain.chain_slots = std::max(chain.chain_slots, std::max(used, (int)pr.nslots));
+      }
       chain.chain_rows = rows;
       insert.emplace_back(*std::min_element(members.begin(), members.end()), chain);
       l = end;
@@ -796,7 +804,7 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       break;
     case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
     case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st); break;
-    case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_rows, st); break;
+    case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_slots, n.chain_rows, st); break;
     case Node::CONV: {
       const ConvPattern& cv = n.conv;
       if (cv.kind == ConvPattern::FORWARD)

@@ -47,7 +47,7 @@ struct Node {
   __nv_bfloat16 *split_hi = nullptr, *split_mid = nullptr;
   // ROWCHAIN: several row-local INTERP programs executed by one launch
   IpProgram* chain_progs = nullptr;  // device array (owned by the plan)
-  int chain_n = 0;
+  int chain_n = 0, chain_slots = 0;
   int64_t chain_rows = 0;
   // CONV
   ConvPattern conv;
@@ -146,7 +146,8 @@ std::unique_ptr<Model> new_model(Context& ctx, std::shared_ptr<Program> prog, ui
 // kernels (host launchers)
 void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
                    cudaStream_t st);
-void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int64_t rows, cudaStream_t st);
+void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int max_slots, int64_t rows,
+                            cudaStream_t st);
 void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi, uint64_t seed, uint64_t counter,
                          cudaStream_t st);
 
