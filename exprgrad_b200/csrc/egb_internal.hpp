@@ -172,6 +172,9 @@ struct GemmArgs {
   int* counters = nullptr;  // one int per output tile, zero before the first launch (self-resetting)
 };
 
+// 2-CTA (cta_group::2) variant for large K-major problems with a plain epilogue (gemm_tcgen05_2cta.cu)
+bool gemm_2cta_eligible(const GemmArgs& a);
+void launch_gemm_bf16x3_2cta(Context& ctx, const GemmArgs& a, cudaStream_t st);
 void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* splits, int* tiles);
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);

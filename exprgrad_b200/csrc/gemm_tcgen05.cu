@@ -494,6 +494,10 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return;
   if (a.K <= 0) fail(EGB_ERR_GPU, "gemm: K must be positive");
   if (!ctx.encode_tiled) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled entry point not available");
+  if (a.bn == 0 && gemm_2cta_eligible(a)) {
+    launch_gemm_bf16x3_2cta(ctx, a, st);
+    return;
+  }
   KParams p;
   p.C = a.C; p.bias = a.bias; p.out_hi = a.out_hi; p.out_mid = a.out_mid;
   p.D = a.D; p.H = a.H; p.colsum = a.colsum;

@@ -431,8 +431,8 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.gemm.ldc = (int)g.ldc;
       n.gemm.flags = inf.overwrite ? 0 : GEMM_ACCUMULATE;
       n.gemm.alpha = 1.0f;
-      n.gemm.bn = inf.bn;
       if (inf.splits > 1) {
+        n.gemm.bn = inf.bn;  // the tile count the counters were sized for
         const size_t cbytes = align_up((size_t)inf.tiles * sizeof(int), 256);
         if (plane_cursor + cbytes > plane_cap) fail(EGB_ERR_RUNTIME, "internal: operand plane arena exhausted");
         n.gemm.counters = (int*)(plane_base + plane_cursor);  // zero since arena creation, self-resetting
