@@ -48,8 +48,9 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int rows, int c
   }
 }
 
-// Transposing variant: src [rows, cols] -> planes [cols, rows]. 64x64 tiles through shared memory so
-// both the fp32 reads (along cols) and the bf16 writes (along rows) are coalesced.
+// Transposing variant: src [rows, cols] -> planes [cols, rows]. 64x64 tiles through shared memory:
+// 128-bit loads along the source rows, then every thread converts 8 consecutive source rows of one
+// source column and writes them as one 16-byte store per plane (the output row is contiguous in r).
 __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, int cols, int ld,
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                                        int dst_ld, int act) {
@@ -58,26 +59,55 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, 
   pdl_wait();
   const int tiles_c = (cols + 63) >> 6;
   const int tiles_r = (rows + 63) >> 6;
-  const int tx = threadIdx.x & 63;  // 256 threads: 64 x 4
-  const int ty = threadIdx.x >> 6;
+  const bool vec_in = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const bool vec_out = ((dst_ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(hi) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(mid) & 15) == 0);
   for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
     const int r0 = (t / tiles_c) << 6;
     const int c0 = (t % tiles_c) << 6;
     __syncthreads();
-#pragma unroll 4
-    for (int j = ty; j < 64; j += 4) {
-      const int r = r0 + j, c = c0 + tx;
-      tile[j][tx] = (r < rows && c < cols) ? __ldg(src + (size_t)r * ld + c) : 0.0f;
+    // load: 64 rows x 16 float4 = 1024 vector loads, 4 per thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      const int rr = idx >> 4, c4 = (idx & 15) << 2;
+      const int r = r0 + rr, c = c0 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        const float* p = src + (size_t)r * ld + c;
+        if (vec_in && c + 4 <= cols) {
+          v = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (c + 0 < cols) v.x = __ldg(p + 0);
+          if (c + 1 < cols) v.y = __ldg(p + 1);
+          if (c + 2 < cols) v.z = __ldg(p + 2);
+          if (c + 3 < cols) v.w = __ldg(p + 3);
+        }
+      }
+      tile[rr][c4 + 0] = v.x; tile[rr][c4 + 1] = v.y; tile[rr][c4 + 2] = v.z; tile[rr][c4 + 3] = v.w;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int j = ty; j < 64; j += 4) {
-      const int c = c0 + j, r = r0 + tx;  // output row = source column
-      if (c < cols && r < rows) {
-        __nv_bfloat16 h, m;
-        split2(apply_act(tile[tx][j], act), h, m);
-        hi[(size_t)c * dst_ld + r] = h;
-        mid[(size_t)c * dst_ld + r] = m;
+    // store: 64 output rows (source columns) x 8 groups of 8 source rows = 512 items, 2 per thread
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      const int g = idx & 7, cc = idx >> 3;    // 8 neighbouring lanes write one contiguous 128-byte output row segment
+      const int c = c0 + cc, r = r0 + g * 8;
+      if (c >= cols || r >= rows) continue;
+      __align__(16) __nv_bfloat16 hv[8];
+      __align__(16) __nv_bfloat16 mv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split2(apply_act(tile[g * 8 + e][cc], act), hv[e], mv[e]);
+      __nv_bfloat16* h = hi + (size_t)c * dst_ld + r;
+      __nv_bfloat16* m = mid + (size_t)c * dst_ld + r;
+      if (vec_out && r + 8 <= rows) {
+        *reinterpret_cast<uint4*>(h) = *reinterpret_cast<const uint4*>(hv);
+        *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(mv);
+      } else {
+        for (int e = 0; e < 8 && r + e < rows; ++e) {
+          h[e] = hv[e];
+          m[e] = mv[e];
+        }
       }
     }
   }
