@@ -234,7 +234,7 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_2cta_kernel (cta_group::2 tcgen05, 256x256 pair tiles)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "frac_of_burst_peak": achieved / peaks["bf16_burst"], "frac_of_sustained_peak": achieved / peaks["bf16_sustained"],
-                     "traffic": 578.0e6, "traffic_source": "profiles/r01a_ncu_full.txt (dram read+write per launch)",
+                     "traffic": 390.0e6, "traffic_source": "profiles/r01i_ncu_full.txt (dram read+write per launch: 335 + 55 MB)",
                      "passes": passes, "algorithmic_tflops": flop / t_kernel / 1e12, "kernel_ms": t_kernel * 1e3,
                      "kernel_share_of_step": k_ms / max(all_ms, 1e-9),
                      "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a %.0f ms back-to-back region)" % ms

@@ -828,54 +828,85 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
 // turns into parallel branches of the CUDA graph.
 static void capture_levels(Model& m, Plan& plan) {
   Context& c = *m.ctx;
+  const int n = (int)plan.nodes.size();
   int max_level = 0;
-  size_t widest = 1;
-  for (auto& n : plan.nodes) max_level = std::max(max_level, n.level);
-  std::vector<std::vector<Node*>> levels(max_level + 1);
-  for (auto& n : plan.nodes) levels[n.level].push_back(&n);
-  for (auto& l : levels) widest = std::max(widest, l.size());
-  if (!m.concurrent || widest == 1) {
-    for (auto& n : plan.nodes) launch_node(m, n, c.stream);
+  std::vector<int> width;
+  for (auto& nd : plan.nodes) max_level = std::max(max_level, nd.level);
+  width.assign(max_level + 1, 0);
+  bool parallel = false;
+  for (auto& nd : plan.nodes) parallel = parallel || ++width[nd.level] > 1;
+  if (!m.concurrent || !parallel) {
+    for (auto& nd : plan.nodes) launch_node(m, nd, c.stream);
     return;
   }
+  // Dependency-exact capture: every node waits (through events) only for the earlier nodes it really
+  // conflicts with, so e.g. the weight-gradient contraction of layer l overlaps the input-gradient
+  // chain of the layers below it. Nodes are issued in level order on four streams; a node goes to a
+  // stream whose last node is one of its predecessors (no false ordering), else to an idle one.
+  constexpr int NS = 4;
   for (auto& st : c.aux_stream)
     if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  size_t ev = 0;
-  auto next_event = [&]() {
-    if (ev == c.fork_events.size()) {
-      cudaEvent_t e;
-      EGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      c.fork_events.push_back(e);
-    }
-    return c.fork_events[ev++];
-  };
-  for (auto& level : levels) {
-    if (level.size() == 1) {
-      launch_node(m, *level[0], c.stream);
-      continue;
-    }
-    // NCCL and memset nodes stay on the main stream; the rest round-robin over 3 streams
-    cudaStream_t streams[3] = {c.stream, c.aux_stream[0], c.aux_stream[1]};
-    bool used[3] = {true, false, false};
-    cudaEvent_t fork = next_event();
-    EGB_CUDA(cudaEventRecord(fork, c.stream));
-    size_t rr = 0;
-    for (Node* n : level) {
-      int s = 0;
-      if (n->kind != Node::ALLREDUCE && n->kind != Node::MEMSET) s = (int)(rr++ % 3);
-      if (s != 0 && !used[s]) {
-        EGB_CUDA(cudaStreamWaitEvent(streams[s], fork, 0));
-        used[s] = true;
-      }
-      launch_node(m, *n, streams[s]);
-    }
-    for (int s = 1; s < 3; ++s) {
-      if (!used[s]) continue;
-      cudaEvent_t join = next_event();
-      EGB_CUDA(cudaEventRecord(join, streams[s]));
-      EGB_CUDA(cudaStreamWaitEvent(c.stream, join, 0));
-    }
+  static cudaStream_t extra = nullptr;  // a fourth stream, shared by all contexts of the process
+  if (!extra) EGB_CUDA(cudaStreamCreateWithFlags(&extra, cudaStreamNonBlocking));
+  cudaStream_t streams[NS] = {c.stream, c.aux_stream[0], c.aux_stream[1], extra};
+  while ((int)c.fork_events.size() < n + 1) {
+    cudaEvent_t e;
+    EGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c.fork_events.push_back(e);
   }
+  auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+    for (auto x : a)
+      for (auto y : b)
+        if (x == y) return true;
+    return false;
+  };
+  std::vector<std::vector<int>> preds(n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) {
+      const Node &a2 = plan.nodes[j], &b2 = plan.nodes[i];
+      if (hits(a2.writes, b2.reads) || hits(a2.writes, b2.writes) || hits(a2.reads, b2.writes)) preds[i].push_back(j);
+    }
+  cudaEvent_t start = c.fork_events[n];
+  EGB_CUDA(cudaEventRecord(start, c.stream));
+  int tail[NS] = {-1, -1, -1, -1};
+  bool forked[NS] = {true, false, false, false};
+  std::vector<int> stream_of(n, 0);
+  for (int i = 0; i < n; ++i) {
+    Node& nd = plan.nodes[i];
+    int s = -1;
+    if (nd.kind == Node::ALLREDUCE || nd.kind == Node::MEMSET) {
+      s = 0;  // NCCL and memset stay on the main stream
+    } else {
+      // 1. a stream whose tail is a predecessor (prefer the latest one)
+      int best = -1;
+      for (int q = 0; q < NS; ++q)
+        if (tail[q] >= 0 && std::find(preds[i].begin(), preds[i].end(), tail[q]) != preds[i].end() && tail[q] > best) {
+          best = tail[q];
+          s = q;
+        }
+      // 2. an unused stream
+      for (int q = 0; q < NS && s < 0; ++q)
+        if (tail[q] < 0) s = q;
+      // 3. the stream whose tail is the oldest node
+      if (s < 0) {
+        s = 0;
+        for (int q = 1; q < NS; ++q)
+          if (tail[q] < tail[s]) s = q;
+      }
+    }
+    if (!forked[s]) {
+      EGB_CUDA(cudaStreamWaitEvent(streams[s], start, 0));
+      forked[s] = true;
+    }
+    for (int pj : preds[i])
+      if (stream_of[pj] != s) EGB_CUDA(cudaStreamWaitEvent(streams[s], c.fork_events[pj], 0));
+    launch_node(m, nd, streams[s]);
+    EGB_CUDA(cudaEventRecord(c.fork_events[i], streams[s]));
+    tail[s] = i;
+    stream_of[i] = s;
+  }
+  for (int q = 1; q < NS; ++q)
+    if (forked[q] && tail[q] >= 0) EGB_CUDA(cudaStreamWaitEvent(c.stream, c.fork_events[tail[q]], 0));
 }
 
 void Model::run(Plan& plan) {
