@@ -381,19 +381,21 @@ void build_nodes_impl(Model& m, Plan& plan) {
     const KernelInfo& inf = info[ki];
     if (inf.absorbed_by >= 0) continue;  // runs inside the epilogue of its contraction
     if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes) {
-      Node n;
-      n.kind = Node::ALLREDUCE;
-      n.label = "all-reduce(avg) parameter-gradient bucket";
-      n.ptr = plan.arena + plan.bucket_off;
-      n.bytes = plan.bucket_bytes;
-      for (auto& kv : plan.tensors) {
-        const char* p0 = (const char*)kv.second.ptr;
-        if (p0 >= plan.arena + plan.bucket_off && p0 < plan.arena + plan.bucket_off + plan.bucket_bytes) {
-          n.reads.push_back(kv.first);
-          n.writes.push_back(kv.first);
+      for (auto& seg : plan.bucket_segments) {
+        Node n;
+        n.kind = Node::ALLREDUCE;
+        n.label = "all-reduce(avg) gradient bucket segment, " + std::to_string(seg.second) + " bytes";
+        n.ptr = plan.arena + seg.first;
+        n.bytes = seg.second;
+        for (auto& kv : plan.tensors) {
+          const char* p0 = (const char*)kv.second.ptr;
+          if (p0 >= plan.arena + seg.first && p0 < plan.arena + seg.first + seg.second) {
+            n.reads.push_back(kv.first);
+            n.writes.push_back(kv.first);
+          }
         }
+        plan.nodes.push_back(n);
       }
-      plan.nodes.push_back(n);
     }
     if (inf.is_gemm && !m.strict) {
       const GemmPattern& g = inf.gemm;
@@ -732,6 +734,20 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
       if (plan->bucket_before_kernel < 0) bucket.clear();
     }
   }
+  // The bucket is laid out in the order in which the gradients become ready (position of the unit that
+  // writes them last) and cut into segments of >= 256 KB: every segment is one all-reduce that can
+  // start as soon as its gradients exist and overlaps the adjoint kernels of the layers below it.
+  std::vector<int> bucket_order(bucket.begin(), bucket.end());
+  {
+    std::map<int, int> ready;
+    for (size_t ki = 0; ki < nk; ++ki) {
+      const int pos = plan->info[ki].absorbed_by >= 0 ? plan->info[ki].absorbed_by : (int)ki;
+      const int wt = target->kernels[ki]->write.tensor;
+      if (bucket.count(wt)) ready[wt] = std::max(ready.count(wt) ? ready[wt] : -1, pos);
+    }
+    std::stable_sort(bucket_order.begin(), bucket_order.end(), [&](int a, int b) { return ready[a] < ready[b]; });
+    for (int id : bucket_order) needs_zero.insert(id);  // keeps the bucket contiguous inside the zeroed region
+  }
 
   // ---- arena: [results that need zeroing .. | bucket (zeroed part first) | other results, inputs,
   //              random][bf16 operand planes]
@@ -744,11 +760,8 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   for (int id : target->tensors)
     if (needs_zero.count(id) && !bucket.count(id)) order.push_back(id);
   const size_t bucket_first = order.size();
-  for (int id : target->tensors)
-    if (needs_zero.count(id) && bucket.count(id)) order.push_back(id);
+  for (int id : bucket_order) order.push_back(id);
   const size_t n_zero = order.size();
-  for (int id : target->tensors)
-    if (!needs_zero.count(id) && bucket.count(id)) order.push_back(id);
   const size_t bucket_last = order.size();
   for (int id : target->tensors)
     if (!needs_zero.count(id) && !bucket.count(id) && in_arena(id)) order.push_back(id);
@@ -764,6 +777,12 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
     cursor += align_up((size_t)shape_len(sh->second) * 4, 256);
     if (i + 1 == n_zero) plan->zero_bytes = cursor;
     if (i + 1 == bucket_last) plan->bucket_bytes = cursor - plan->bucket_off;
+    if (i >= bucket_first && i < bucket_last) {
+      // close a segment once it holds >= 256 KB (the last one takes the remainder)
+      if (plan->bucket_segments.empty() || plan->bucket_segments.back().second >= (256u << 10))
+        plan->bucket_segments.emplace_back(offs[id], 0);
+      plan->bucket_segments.back().second = cursor - plan->bucket_segments.back().first;
+    }
   }
   if (n_zero == 0) plan->zero_bytes = 0;
   if (bucket.empty()) plan->bucket_bytes = 0;

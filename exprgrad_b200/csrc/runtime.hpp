@@ -99,6 +99,7 @@ struct Plan {
   std::vector<KernelInfo> info;       // one per target kernel
   size_t plane_off = 0, plane_bytes = 0;  // bf16 operand-plane region of the arena
   size_t bucket_off = 0, bucket_bytes = 0;  // contiguous parameter-gradient bucket (data parallel)
+  std::vector<std::pair<size_t, size_t>> bucket_segments;  // (arena offset, bytes), in order of readiness
   int bucket_before_kernel = -1;            // the all-reduce runs right before this target kernel
   std::vector<Node> nodes;
   std::vector<void*> chain_bufs;      // device copies of row-chain programs
