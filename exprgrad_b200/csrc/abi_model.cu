@@ -486,7 +486,7 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
     s += "target " + p.target_name + ": " + std::to_string(p.nodes.size()) + " nodes, arena " +
          std::to_string(p.arena_bytes) + " bytes (zeroed per run: " + std::to_string(p.zero_bytes) + "), graph " +
          (p.graph_valid ? "yes" : "no") + "\n";
-    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain"};
+    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain", "softmax_xent"};
     for (auto& n : p.nodes) {
       s += std::string("  L") + std::to_string(n.level) + " " + kinds[n.kind] + " " + n.label;
       if (n.kind == Node::INTERP)

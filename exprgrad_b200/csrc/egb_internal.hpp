@@ -179,6 +179,11 @@ void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, i
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
 
+// Fused softmax + crossEntropy forward/adjoint row kernel (fused_rows.cu)
+bool softmax_xent_supported(int64_t cols);
+void launch_softmax_xent_rows(Context& ctx, const float* H, const float* Y, const float* DL, float* S, float* P, float* DP,
+                              float* DH, float* DS, int rows, int cols, cudaStream_t st);
+
 // Direct fp32 conv2 kernels (conv2.cu): NHWC images, filters [F, KH, KW, C], valid, stride 1.
 void launch_conv2_fwd(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
                       int KH, int KW, bool accumulate, cudaStream_t st);

@@ -252,6 +252,71 @@ bool fuse_row_chains(Model& m, Plan& plan) {
       members = trial;
       rows = r;
     }
+    if (members.size() >= 6) {
+      // the reference's softmax + crossEntropy head and its adjoints, in exactly this wiring?
+      const Target& target = *plan.target;
+      auto K = [&](int m) -> const Kernel& { return *target.kernels[plan.nodes[members[m]].kernel_index]; };
+      auto text = [&](int m) { return describe_kernel(K(m)); };
+      auto acc = [&](int m) { return (int)plan.nodes[members[m]].ip.accumulate; };
+      bool ok = members.size() == 6;
+      for (int m2 = 0; ok && m2 < 6; ++m2) ok = plan.nodes[members[m2]].kernel_index >= 0;
+      if (ok) {
+        const std::string t2 = text(2);
+        const std::string pre = "loops=! W{I0} R0{I0} R1{I0} R2[0] : div(mul(negate(div(R2,toscalar(shape(T", post = ",0)))),R0),R1)";
+        ok = text(0) == "loops=!. W[I0] R0[I0,I1] : exp(R0)" && text(1) == "loops=!! W[I0,I1] R0[I0,I1] R1[I0] : div(exp(R0),R1)" &&
+             t2.compare(0, pre.size(), pre) == 0 && t2.size() > pre.size() + post.size() &&
+             t2.compare(t2.size() - post.size(), post.size(), post) == 0 &&
+             text(3) == "loops=!! W[I0,I1] R0[I0,I1] R1[I0] R2[I0,I1] : mul(div(R2,R1),exp(R0))" &&
+             text(4) == "loops=!. W[I0] R0[I0,I1] R1[I0] R2[I0,I1] : mul(negate(exp(R0)),div(R2,mul(R1,R1)))" &&
+             text(5) == "loops=!! W[I0,I1] R0[I0,I1] R1[I0] : mul(R1,exp(R0))" && acc(0) == 0 && acc(1) == 0 &&
+             acc(2) == 0 && acc(3) == 0 && acc(4) == 0 && acc(5) == 1;
+      }
+      if (ok) {
+        const int H = K(0).reads[0].tensor, S = K(0).write.tensor, P = K(1).write.tensor;
+        const int Y = K(2).reads[0].tensor, DL = K(2).reads[2].tensor, DP = K(2).write.tensor;
+        const int DH = K(3).write.tensor, DS = K(4).write.tensor;
+        const std::string shape_of = "T" + std::to_string(P) + ",";
+        ok = K(1).reads[0].tensor == H && K(1).reads[1].tensor == S && K(2).reads[1].tensor == P &&
+             text(2).find("shape(" + shape_of) != std::string::npos && K(3).reads[0].tensor == H &&
+             K(3).reads[1].tensor == S && K(3).reads[2].tensor == DP && K(4).reads[0].tensor == H &&
+             K(4).reads[1].tensor == S && K(4).reads[2].tensor == DP && K(5).reads[0].tensor == H &&
+             K(5).reads[1].tensor == DS && K(5).write.tensor == DH;
+        std::set<int> distinct = {H, S, P, Y, DL, DP, DH, DS};
+        const auto& hs = plan.shapes.at(H);
+        ok = ok && distinct.size() == 8 && hs.size() == 2 && softmax_xent_supported(hs[1]) && plan.shapes.at(Y) == hs &&
+             plan.shapes.at(P) == hs && plan.shapes.at(DP) == hs && plan.shapes.at(DH) == hs && tensor_len(DL) == 1 &&
+             tensor_len(S) == hs[0] && tensor_len(DS) == hs[0];
+        if (ok) {
+          Node fx;
+          fx.kind = Node::SOFTMAX_XENT;
+          fx.label = "softmax + crossEntropy forward/adjoint rows (kernels";
+          for (int i : members) {
+            fx.label += " " + std::to_string(plan.nodes[i].kernel_index);
+            for (auto r : plan.nodes[i].reads) fx.reads.push_back(r);
+            for (auto w : plan.nodes[i].writes) fx.writes.push_back(w);
+            remove.insert(i);
+          }
+          fx.label += ")";
+          auto ptr = [&](int tensor) {
+            for (int i : members) {
+              const IpProgram& ip = plan.nodes[i].ip;
+              if (plan.nodes[i].writes[0] == tensor) return (float*)ip.write.base;
+              const Kernel& kk = *target.kernels[plan.nodes[i].kernel_index];
+              for (size_t q = 0; q < kk.reads.size(); ++q)
+                if (kk.reads[q].tensor == tensor) return (float*)ip.reads[q].base;
+            }
+            return (float*)nullptr;
+          };
+          fx.sx_h = ptr(H); fx.sx_y = ptr(Y); fx.sx_dl = ptr(DL);
+          fx.sx_s = ptr(S); fx.sx_p = ptr(P); fx.sx_dp = ptr(DP); fx.sx_dh = ptr(DH); fx.sx_ds = ptr(DS);
+          fx.sx_rows = (int)hs[0];
+          fx.sx_cols = (int)hs[1];
+          insert.emplace_back(*std::min_element(members.begin(), members.end()), fx);
+          l = end;
+          continue;
+        }
+      }
+    }
     if (members.size() >= 2) {
       std::map<uint64_t, int64_t> stride;
       for (int i : members) stride[plan.nodes[i].ip.write.base] = tensor_len(plan.nodes[i].writes[0]) / rows;
@@ -823,6 +888,9 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       break;
     case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
     case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st); break;
+    case Node::SOFTMAX_XENT:
+      launch_softmax_xent_rows(ctx, n.sx_h, n.sx_y, n.sx_dl, n.sx_s, n.sx_p, n.sx_dp, n.sx_dh, n.sx_ds, n.sx_rows, n.sx_cols, st);
+      break;
     case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_slots, n.chain_rows, st); break;
     case Node::CONV: {
       const ConvPattern& cv = n.conv;

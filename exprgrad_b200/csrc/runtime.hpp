@@ -30,7 +30,7 @@ struct DevTensor {
 };
 
 struct Node {
-  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN } kind = INTERP;
+  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN, SOFTMAX_XENT } kind = INTERP;
   std::string label;
   // INTERP
   IpProgram ip;
@@ -49,6 +49,10 @@ struct Node {
   IpProgram* chain_progs = nullptr;  // device array (owned by the plan)
   int chain_n = 0, chain_slots = 0;
   int64_t chain_rows = 0;
+  // SOFTMAX_XENT: H, Y, DL -> S, P, DP, DH, DS (fused_rows.cu)
+  const float *sx_h = nullptr, *sx_y = nullptr, *sx_dl = nullptr;
+  float *sx_s = nullptr, *sx_p = nullptr, *sx_dp = nullptr, *sx_dh = nullptr, *sx_ds = nullptr;
+  int sx_rows = 0, sx_cols = 0;
   // CONV
   ConvPattern conv;
   const float *conv_a = nullptr, *conv_b = nullptr;

@@ -90,6 +90,30 @@ def test_fused_and_unfused_plans_agree(ctx):
         assert_close(a - v, b - v, tol=1e-3, what="fused vs unfused update")
 
 
+@pytest.mark.parametrize("opts", [dict(concurrent=0), dict(rowchain=0), dict(graphs=0), dict(splitk=1),
+                                  dict(fuse=0, rowchain=0, concurrent=0), dict(splitk=1, fuse=0)])
+def test_planner_options_do_not_change_results(ctx, opts):
+    """Every planner feature (epilogue fusion, row chains, concurrent graph branches, CUDA graphs, split-K)
+    is an execution detail: turning it off (or on) must reproduce the default plan's train step."""
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    x, y, params = G.dense_inputs(200)
+    outs = []
+    for o in (dict(), opts):
+        pm = M.compile(*G.dense_net(F, PL), gpu=ctx, seed=0)
+        for k, v in o.items():
+            pm.set_option(k, v)
+        for tid, v in zip(pm.params.ids(), params):
+            pm.params[tid] = v
+        for _ in range(2):
+            pm.apply("train", {"x": x, "y": y})
+        outs.append(([pm.params[t] for t in pm.params.ids()], pm.call("loss", {"x": x, "y": y})))
+        pm.free()
+    for a, b, v in zip(outs[0][0], outs[1][0], params):
+        assert_close(a, b, tol=1e-6, what=f"params under {opts}")
+        assert_close(a - v, b - v, tol=1e-3, what=f"update under {opts}")
+    assert_close(outs[0][1], outs[1][1], tol=1e-6, what=f"loss under {opts}")
+
+
 def test_strict_mode_is_bit_exact_for_non_transcendental_kernels(ctx):
     """Strict mode restates the reference's sequential fp32 accumulation: the matmul + bias + relu part
     of the net (no exp/log) must equal the oracle bit for bit."""
