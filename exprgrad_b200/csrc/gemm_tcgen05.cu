@@ -481,7 +481,9 @@ void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, i
   int s = 1;
   // few tiles and a long reduction: one SM per tile would stream its whole K extent at the per-SM TMA
   // rate (~100 GB/s) while the rest of the machine idles - split the reduction instead
-  if (*tiles * 2 <= sm_count && num_kb >= 4) {
+  // (measured on the dense step: splitting pays only when very few SMs would be busy - the zero fill,
+  // L2 reductions and re-read of C cost more than a 2x shorter k-loop saves on mid-sized grids)
+  if (*tiles * 8 <= sm_count && num_kb >= 4) {
     s = sm_count / *tiles;
     if (s > num_kb / 2) s = num_kb / 2;
     if (s > 8) s = 8;

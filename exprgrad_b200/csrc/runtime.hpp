@@ -132,8 +132,9 @@ struct Model {
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   bool rowchain = true;     // runs of small row-local kernels execute in one launch
   // split-K for contractions with few output tiles (RED.ADD partial tiles + last-arriver epilogue).
-  // Measured on the dense step it loses to the unsplit kernel (161 vs 150 us: zero-filling C, L2
-  // atomics and the re-read cost more than the shorter k-loops save), so it is off by default.
+  // Measured on the dense step it loses both when applied to every half-empty grid (161 vs 150 us) and
+  // when restricted to grids of <= 18 tiles (115.6 vs 111.4 us): zero-filling C, the L2 reductions, the
+  // tile-counter handshake and the re-read cost more than the shorter k-loops save. Off by default.
   bool splitk = false;
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
