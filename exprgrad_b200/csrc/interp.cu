@@ -123,7 +123,7 @@ __device__ __forceinline__ void decode(const IpProgram& p, int lo, int hi, int64
 
 template <bool kStrict, bool kSmemSlots>
 __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constant__ IpProgram p, int pb, int rb,
-                                                            int points_fast) {
+                                                            int points_fast, int rsplit) {
   __shared__ float partial[IP_THREADS];
   extern __shared__ __align__(16) unsigned char slot_smem[];
   Slot local_slots[kSmemSlots ? 1 : IP_MAX_SLOTS];
@@ -155,7 +155,15 @@ __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constan
         }
         if (kStrict && p.accumulate && p.nred > 0) acc = out[widx];
       }
-      for (int64_t r = rl; r < p.nred; r += rb) {
+      // long reductions with few outputs are additionally split over blockIdx.y; the partial sums of
+      // the splits meet in the output through atomicAdd (the output then always accumulates)
+      int64_t r_begin = 0, r_end = p.nred;
+      if (rsplit > 1) {
+        const int64_t chunk = ((p.nred + rsplit - 1) / rsplit + rb - 1) / rb * rb;
+        r_begin = (int64_t)blockIdx.y * chunk;
+        r_end = min(p.nred, r_begin + chunk);
+      }
+      for (int64_t r = r_begin + rl; r < r_end; r += rb) {
         decode(p, p.npar, p.nloops, r, s);
         run_instrs(p.index_instrs, p.nindex_instrs, s, p);
         for (int k = 0; k < p.nreads; ++k) {
@@ -189,6 +197,7 @@ __global__ void __launch_bounds__(IP_THREADS) interp_kernel(const __grid_constan
     }
     if (active && rl == 0 && p.nred > 0) {
       if (kStrict) out[widx] = acc;
+      else if (rsplit > 1) atomicAdd(out + widx, acc);
       else out[widx] = p.accumulate ? out[widx] + acc : acc;
     }
   }
@@ -303,29 +312,49 @@ __global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_co
     s[p.lit_slot[i]] = V4{f, f, f, f};
   }
   pdl_wait();
-  const int64_t n = p.loops[0].count, start = p.loops[0].start;
-  float* const out = reinterpret_cast<float*>(p.write.base) + p.write.offset + start;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-  for (int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += stride) {
+  const int inner = p.npar - 1;
+  const int64_t n = p.loops[inner].count;              // row length (innermost loop)
+  const int64_t groups = (n + 3) >> 2;                 // 4-element groups per row
+  const int64_t total = (p.npoints / n) * groups;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+    const int64_t rowi = item / groups;
+    const int64_t i4 = (item - rowi * groups) << 2;
+    // iterators: outer loops decoded from the row index, the inner one starts at i4
+    int64_t it[IP_MAX_LOOPS];
+    {
+      int64_t v = rowi;
+      for (int l = inner - 1; l >= 0; --l) {
+        const int64_t c = p.loops[l].count;
+        const int64_t q = v / c;
+        it[l] = p.loops[l].start + p.loops[l].step * (v - q * c);
+        v = q;
+      }
+      it[inner] = p.loops[inner].start + i4;
+    }
+    auto flat = [&](const IpTensorOp& op) {
+      int64_t idx = op.offset;
+      for (int t = 0; t < op.nterms; ++t)
+        for (int l = 0; l <= inner; ++l)
+          if (p.loops[l].slot == op.slot[t]) idx += op.coef[t] * it[l];
+      return idx;
+    };
     const bool full = i4 + 3 < n;
     for (int k = 0; k < p.nreads; ++k) {
       const IpTensorOp& op = p.reads[k];
-      const float* src = reinterpret_cast<const float*>(op.base) + op.offset;
+      const float* src = reinterpret_cast<const float*>(op.base) + flat(op);
       V4 v;
       if (!op.streaming) {
         const float f = __ldg(src);
         v = V4{f, f, f, f};
+      } else if (full && op.aligned16) {
+        const float4 t = *reinterpret_cast<const float4*>(src);
+        v = V4{t.x, t.y, t.z, t.w};
       } else {
-        src += start + i4;
-        if (full && op.aligned16) {
-          const float4 t = *reinterpret_cast<const float4*>(src);
-          v = V4{t.x, t.y, t.z, t.w};
-        } else {
-          v.x = src[0];
-          v.y = i4 + 1 < n ? src[1] : 0.0f;
-          v.z = i4 + 2 < n ? src[2] : 0.0f;
-          v.w = i4 + 3 < n ? src[3] : 0.0f;
-        }
+        v.x = src[0];
+        v.y = i4 + 1 < n ? src[1] : 0.0f;
+        v.z = i4 + 2 < n ? src[2] : 0.0f;
+        v.w = i4 + 3 < n ? src[3] : 0.0f;
       }
       s[op.dst] = v;
     }
@@ -363,7 +392,7 @@ __global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_co
       s[in.dst] = r;
     }
     V4 v = s[p.write.dst];
-    float* o = out + i4;
+    float* o = reinterpret_cast<float*>(p.write.base) + flat(p.write);
     if (full && p.write.aligned16) {
       if (p.accumulate) {
         const float4 t = *reinterpret_cast<const float4*>(o);
@@ -400,11 +429,23 @@ void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs
   EGB_CUDA(cudaGetLastError());
 }
 
+int interp_reduction_splits(const IpProgram& prog, int pb, int rb, bool strict, int sm_count) {
+  if (strict || prog.scatter || prog.vec4 || prog.nred < (1 << 16)) return 1;
+  const int64_t nblocks = (prog.npoints + pb - 1) / pb;
+  if (nblocks >= 2 * sm_count) return 1;
+  int64_t s = (4 * (int64_t)sm_count) / nblocks;
+  const int64_t max_s = prog.nred / ((int64_t)rb * 64);
+  if (s > max_s) s = max_s;
+  if (s > 1024) s = 1024;
+  return s < 2 ? 1 : (int)s;
+}
+
 void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
-                   cudaStream_t st) {
+                   cudaStream_t st, int rsplit) {
   if (prog.npoints <= 0 || prog.nred <= 0) return;
   if (prog.vec4 && !strict) {
-    const int64_t groups = (prog.npoints + 3) / 4;
+    const int64_t row_len = prog.loops[prog.npar - 1].count;
+    const int64_t groups = (prog.npoints / row_len) * ((row_len + 3) / 4);
     const int64_t nb = (groups + IP_THREADS - 1) / IP_THREADS;
     const int64_t capb = (int64_t)ctx.sm_count * 16;
     {
@@ -418,16 +459,18 @@ void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int poin
   const int64_t nblocks = (prog.npoints + pb - 1) / pb;
   const int64_t cap = (int64_t)ctx.sm_count * 8;
   const int grid = (int)(nblocks < cap ? nblocks : cap);
+  if (rsplit > 1 && !prog.accumulate) fail(EGB_ERR_GPU, "interp: a split reduction needs an accumulating output");
+  const dim3 grid3(grid, rsplit > 1 ? rsplit : 1);
   {
     Launch l(ctx, KC_INTERP, st);
     const bool smem_slots = prog.nslots <= IP_SMEM_SLOTS;
     const size_t smem = smem_slots ? (size_t)prog.nslots * IP_THREADS * sizeof(Slot) : 0;
     if (strict) {
-      if (smem_slots) launch_kernel(ctx, interp_kernel<true, true>, dim3(grid), dim3(IP_THREADS), smem, st, prog, pb, rb, points_fast);
-      else launch_kernel(ctx, interp_kernel<true, false>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
+      if (smem_slots) launch_kernel(ctx, interp_kernel<true, true>, grid3, dim3(IP_THREADS), smem, st, prog, pb, rb, points_fast, 1);
+      else launch_kernel(ctx, interp_kernel<true, false>, grid3, dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast, 1);
     } else {
-      if (smem_slots) launch_kernel(ctx, interp_kernel<false, true>, dim3(grid), dim3(IP_THREADS), smem, st, prog, pb, rb, points_fast);
-      else launch_kernel(ctx, interp_kernel<false, false>, dim3(grid), dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast);
+      if (smem_slots) launch_kernel(ctx, interp_kernel<false, true>, grid3, dim3(IP_THREADS), smem, st, prog, pb, rb, points_fast, rsplit);
+      else launch_kernel(ctx, interp_kernel<false, false>, grid3, dim3(IP_THREADS), 0, st, prog, pb, rb, points_fast, rsplit);
     }
   }
   EGB_CUDA(cudaGetLastError());

@@ -582,17 +582,32 @@ Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<i
   }
   ip.accumulate = (overwrite && !ip.scatter) ? 0 : 1;
 
-  // 4-wide fast path: one unit-stride loop, every access either streams with it or is loop-invariant,
-  // and the expression only uses fp32 / boolean operations
+  // 4-wide fast path: no reduction, the innermost independent loop has unit stride, every access either
+  // streams with it (coefficient 1) or does not depend on it (broadcast along the row), and the
+  // expression only uses fp32 / boolean operations. Outer iterators only enter the address arithmetic.
   {
-    bool ok = nloops == 1 && ip.npar == 1 && k.loops[0].step == 1 && !ip.scatter && ip.nindex_instrs == 0 &&
-              lw.nslots <= 64;
+    bool ok = ip.npar >= 1 && ip.npar == nloops && !ip.scatter && ip.nindex_instrs == 0 && lw.nslots <= 64 &&
+              ip.loops[ip.npar - 1].step == 1 && ip.npoints > 0;
+    const int inner_slot = ok ? ip.loops[ip.npar - 1].slot : -1;
+    const int64_t inner_start = ok ? ip.loops[ip.npar - 1].start : 0;
     auto classify = [&](IpTensorOp& op, bool must_stream) {
-      if (op.nterms == 1 && op.coef[0] == 1 && op.slot[0] == iter_slot[0]) op.streaming = 1;
-      else if (op.nterms == 0 && !must_stream) op.streaming = 0;
+      int64_t inner_coef = 0;
+      bool outer_mult4 = true;
+      for (int t = 0; t < op.nterms; ++t) {
+        if (op.slot[t] == inner_slot) {
+          inner_coef = op.coef[t];
+        } else {
+          bool is_loop = false;
+          for (int l = 0; l < ip.npar; ++l) is_loop = is_loop || ip.loops[l].slot == op.slot[t];
+          if (!is_loop) ok = false;
+          outer_mult4 = outer_mult4 && (op.coef[t] % 4 == 0);
+        }
+      }
+      if (inner_coef == 1) op.streaming = 1;
+      else if (inner_coef == 0 && !must_stream) op.streaming = 0;
       else ok = false;
-      const int64_t first = op.offset + (op.streaming ? start[0] : 0);
-      op.aligned16 = (((op.base >> 2) + (uint64_t)first) & 3) == 0 && (op.base & 3) == 0;
+      const int64_t first = op.offset + (op.streaming ? inner_start : 0);
+      op.aligned16 = outer_mult4 && (((op.base >> 2) + (uint64_t)first) & 3) == 0 && (op.base & 3) == 0;
     };
     if (ok) {
       classify(ip.write, true);

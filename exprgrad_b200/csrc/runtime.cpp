@@ -210,7 +210,8 @@ bool fuse_row_chains(Model& m, Plan& plan) {
       if (by_level[lv].empty()) return false;
       for (int i : by_level[lv]) {
         const Node& n = plan.nodes[i];
-        if (n.kind != Node::INTERP || n.ip.scatter || n.uses_epoch || n.ip.npoints * n.ip.nred > (1 << 22)) return false;
+        // chains are for latency-bound small kernels; larger ones run faster as separate (4-wide) launches
+        if (n.kind != Node::INTERP || n.ip.scatter || n.uses_epoch || n.ip.npoints * n.ip.nred > (1 << 16)) return false;
       }
       return true;
     };
@@ -571,7 +572,20 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.kernel_index = (int)ki;
       for (auto& r : k.reads) n.reads.push_back(r.tensor);
       n.writes.push_back(k.write.tensor);
-      if (lw.ip.accumulate) n.reads.push_back(k.write.tensor);
+      n.rsplit = interp_reduction_splits(n.ip, n.pb, n.rb, m.strict, ctx.sm_count);
+      if (n.rsplit > 1 && !n.ip.accumulate) {
+        // the splits accumulate into the output, so an overwriting kernel first gets its (completely
+        // covered) output tensor cleared
+        Node z;
+        z.kind = Node::MEMSET;
+        z.label = "zero tensor" + std::to_string(k.write.tensor - 1) + " (split reduction)";
+        z.ptr = ptrs[k.write.tensor];
+        z.bytes = (size_t)shape_len(plan.shapes.at(k.write.tensor)) * 4;
+        z.writes.push_back(k.write.tensor);
+        plan.nodes.push_back(z);
+        n.ip.accumulate = 1;
+      }
+      if (n.ip.accumulate) n.reads.push_back(k.write.tensor);
       plan.nodes.push_back(n);
     }
     // cached planes of every tensor this unit wrote are stale now (except the ones it just produced)
@@ -887,7 +901,7 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
                         n.split_mid, n.split_dst_ld, n.split_act, st);
       break;
     case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
-    case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st); break;
+    case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st, n.rsplit); break;
     case Node::SOFTMAX_XENT:
       launch_softmax_xent_rows(ctx, n.sx_h, n.sx_y, n.sx_dl, n.sx_s, n.sx_p, n.sx_dp, n.sx_dh, n.sx_ds, n.sx_rows, n.sx_cols, st);
       break;

@@ -37,6 +37,7 @@ struct Node {
   int pb = 256, rb = 1, points_fast = 1;
   bool strict = false;
   bool uses_epoch = false;
+  int rsplit = 1;  // long reduction split over blockIdx.y (partials meet through atomicAdd)
   int kernel_index = -1;  // index into target.kernels (for re-lowering when the epoch changes)
   // GEMM
   GemmArgs gemm;
@@ -151,7 +152,8 @@ std::unique_ptr<Model> new_model(Context& ctx, std::shared_ptr<Program> prog, ui
 
 // kernels (host launchers)
 void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int points_fast, bool strict,
-                   cudaStream_t st);
+                   cudaStream_t st, int rsplit = 1);
+int interp_reduction_splits(const IpProgram& prog, int pb, int rb, bool strict, int sm_count);
 void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int max_slots, int64_t rows,
                             cudaStream_t st);
 void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi, uint64_t seed, uint64_t counter,
