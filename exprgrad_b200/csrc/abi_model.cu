@@ -489,10 +489,14 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
     static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain", "softmax_xent"};
     for (auto& n : p.nodes) {
       s += std::string("  L") + std::to_string(n.level) + " " + kinds[n.kind] + " " + n.label;
-      if (n.kind == Node::INTERP)
-        s += " points=" + std::to_string(n.ip.npoints) + " red=" + std::to_string(n.ip.nred) + " pb=" +
-             std::to_string(n.pb) + " rb=" + std::to_string(n.rb) + (n.ip.accumulate ? " +=" : " =") +
-             (n.ip.scatter ? " scatter" : "");
+      if (n.kind == Node::INTERP) {
+        static const char* paths[] = {"", " 4wide-eltwise", " 4wide-stream-reduce", " 4wide-point-reduce"};
+        s += " points=" + std::to_string(n.ip.npoints) + " red=" + std::to_string(n.ip.nred) + " loops=" +
+             std::to_string(n.ip.nloops);
+        if (n.ip.vec4 && !n.strict) s += paths[n.ip.vec4 & 3];
+        else s += " pb=" + std::to_string(n.pb) + " rb=" + std::to_string(n.rb) + " rsplit=" + std::to_string(n.rsplit);
+        s += std::string(n.ip.accumulate ? " +=" : " =") + (n.ip.scatter ? " scatter" : "");
+      }
       if (n.kind == Node::GEMM)
         s += " M=" + std::to_string(n.gemm.M) + " N=" + std::to_string(n.gemm.N) + " K=" + std::to_string(n.gemm.K) +
              ((n.gemm.flags & GEMM_ACCUMULATE) ? " +=" : " =");

@@ -304,96 +304,171 @@ __device__ __forceinline__ bool f2b(float f) { return __float_as_uint(f) != 0u; 
     r.x = expr(a.x); r.y = expr(a.y); r.z = expr(a.z); r.w = expr(a.w); \
   }
 
-__global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_constant__ IpProgram p) {
-  V4 s[64];
-  pdl_launch_dependents();
-  for (int i = 0; i < p.nlits; ++i) {
-    const float f = __uint_as_float((uint32_t)p.lits[i]);
-    s[p.lit_slot[i]] = V4{f, f, f, f};
+// register file of the 4-wide paths: shared memory ([slot][thread], 16 bytes per thread) when it fits,
+// else local memory
+struct V4Local {
+  V4* s;
+  __device__ __forceinline__ V4& operator[](int i) const { return s[i]; }
+};
+struct V4Shared {
+  V4* base;
+  __device__ __forceinline__ V4& operator[](int i) const { return base[i * IP_THREADS]; }
+};
+
+template <class S>
+__device__ __forceinline__ void run_v4(const IpProgram& p, S s) {
+  for (int k = 0; k < p.ninstrs; ++k) {
+    const IpInstr in = p.instrs[k];
+    V4 r = V4{0.f, 0.f, 0.f, 0.f};
+    switch (in.op) {
+      case IP_FADD: EGB_V4_BIN([](float a, float b) { return a + b; }) break;
+      case IP_FSUB: EGB_V4_BIN([](float a, float b) { return a - b; }) break;
+      case IP_FMUL: EGB_V4_BIN([](float a, float b) { return a * b; }) break;
+      case IP_FDIV: EGB_V4_BIN(__fdiv_rn) break;
+      case IP_FNEG: EGB_V4_UN([](float a) { return 0.0f - a; }) break;
+      case IP_SIN: EGB_V4_UN(sinf) break;
+      case IP_COS: EGB_V4_UN(cosf) break;
+      case IP_EXP: EGB_V4_UN(expf) break;
+      case IP_LN: EGB_V4_UN(logf) break;
+      case IP_SQRT: EGB_V4_UN(__fsqrt_rn) break;
+      case IP_POW: EGB_V4_BIN(powf) break;
+      case IP_LOG10: EGB_V4_UN(log10f) break;
+      case IP_LOG2: EGB_V4_UN(log2f) break;
+      case IP_LOGB: EGB_V4_BIN([](float a, float b) { return __fdiv_rn(logf(a), logf(b)); }) break;
+      case IP_FEQ: EGB_V4_BIN([](float a, float b) { return b2f(a == b); }) break;
+      case IP_FLT: EGB_V4_BIN([](float a, float b) { return b2f(a < b); }) break;
+      case IP_FLE: EGB_V4_BIN([](float a, float b) { return b2f(a <= b); }) break;
+      case IP_BEQ: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) == f2b(b)); }) break;
+      case IP_AND: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) && f2b(b)); }) break;
+      case IP_OR: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) || f2b(b)); }) break;
+      case IP_SELECT: {
+        const V4 c = s[in.a], a = s[in.b], b = s[in.c];
+        r.x = f2b(c.x) ? a.x : b.x; r.y = f2b(c.y) ? a.y : b.y; r.z = f2b(c.z) ? a.z : b.z; r.w = f2b(c.w) ? a.w : b.w;
+        break;
+      }
+      default: break;
+    }
+    s[in.dst] = r;
   }
+}
+
+// The 4-wide kernels keep iterator values in a small array indexed by SLOT (the loop iterators own the
+// first slots of a lowered kernel), so the flat element index of an access is a dot product of its terms.
+__device__ __forceinline__ int64_t flat_v4(const IpTensorOp& op, const int64_t* itv) {
+  int64_t idx = op.offset;
+  for (int t = 0; t < op.nterms; ++t) idx += op.coef[t] * itv[op.slot[t]];
+  return idx;
+}
+
+// q = a / b, a -= q * b with a 32-bit divide when both fit (they almost always do; 64-bit division is a
+// ~100-instruction subroutine)
+__device__ __forceinline__ int64_t divmod(int64_t& a, int64_t b) {
+  int64_t q;
+  if (((uint64_t)a | (uint64_t)b) >> 32 == 0) q = (int64_t)((uint32_t)a / (uint32_t)b);
+  else q = a / b;
+  a -= q * b;
+  return q;
+}
+
+// iterator values of loops [first, last] from a linear index (last loop fastest)
+__device__ __forceinline__ void decode_loops(const IpProgram& p, int first, int last, int64_t v, int64_t* itv) {
+  for (int l = last; l >= first; --l) {
+    const int64_t c = p.loops[l].count;
+    int64_t r = v;
+    v = l > first ? divmod(r, c) : 0;
+    itv[p.loops[l].slot] = p.loops[l].start + p.loops[l].step * r;
+  }
+}
+
+// the 4 consecutive elements (along the streaming loop) of one read
+__device__ __forceinline__ V4 load_one_v4(const IpTensorOp& op, const int64_t* itv, int64_t i4, int64_t n) {
+  const float* src = reinterpret_cast<const float*>(op.base) + flat_v4(op, itv);
+  V4 v;
+  if (!op.streaming) {
+    const float f = __ldg(src);
+    v = V4{f, f, f, f};
+  } else if (i4 + 3 < n && op.aligned16) {
+    const float4 t = *reinterpret_cast<const float4*>(src);
+    v = V4{t.x, t.y, t.z, t.w};
+  } else {
+    v.x = src[0];
+    v.y = i4 + 1 < n ? src[1] : 0.0f;
+    v.z = i4 + 2 < n ? src[2] : 0.0f;
+    v.w = i4 + 3 < n ? src[3] : 0.0f;
+  }
+  return v;
+}
+
+// Software pipeline: the first IP_V4_PRE reads of the NEXT work item are fetched into registers while the
+// current item is evaluated, so every thread keeps loads in flight during the interpretive part.
+constexpr int IP_V4_PRE = 4;
+__device__ __forceinline__ void prefetch_v4(const IpProgram& p, const int64_t* itv, int64_t i4, int64_t n, V4 (&pre)[IP_V4_PRE]) {
+#pragma unroll
+  for (int k = 0; k < IP_V4_PRE; ++k)
+    if (k < p.nreads) pre[k] = load_one_v4(p.reads[k], itv, i4, n);
+}
+template <class S>
+__device__ __forceinline__ void commit_v4(const IpProgram& p, S s, const V4 (&pre)[IP_V4_PRE]) {
+#pragma unroll
+  for (int k = 0; k < IP_V4_PRE; ++k)
+    if (k < p.nreads) s[p.reads[k].dst] = pre[k];
+}
+template <class S>
+__device__ __forceinline__ void load_rest_v4(const IpProgram& p, S s, const int64_t* itv, int64_t i4, int64_t n) {
+  for (int k = IP_V4_PRE; k < p.nreads; ++k) s[p.reads[k].dst] = load_one_v4(p.reads[k], itv, i4, n);
+}
+
+#define EGB_V4_SLOTS(s)                                                               \
+  extern __shared__ __align__(16) unsigned char v4_smem[];                              \
+  V4 v4_local[kSmem ? 1 : 64];                                                          \
+  typename std::conditional<kSmem, V4Shared, V4Local>::type s;                          \
+  if constexpr (kSmem) s.base = reinterpret_cast<V4*>(v4_smem) + (threadIdx.x + threadIdx.y * blockDim.x); \
+  else s.s = v4_local;                                                                  \
+  for (int i = 0; i < p.nlits; ++i) {                                                   \
+    const float f = __uint_as_float((uint32_t)p.lits[i]);                               \
+    s[p.lit_slot[i]] = V4{f, f, f, f};                                                  \
+  }
+
+// mode 1, elementwise: no reduction loop, the innermost independent loop streams
+template <bool kSmem>
+__global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_constant__ IpProgram p) {
+  pdl_launch_dependents();
+  EGB_V4_SLOTS(s)
   pdl_wait();
   const int inner = p.npar - 1;
+  const int inner_slot = p.loops[inner].slot;
   const int64_t n = p.loops[inner].count;              // row length (innermost loop)
   const int64_t groups = (n + 3) >> 2;                 // 4-element groups per row
   const int64_t total = (p.npoints / n) * groups;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
-    const int64_t rowi = item / groups;
-    const int64_t i4 = (item - rowi * groups) << 2;
-    // iterators: outer loops decoded from the row index, the inner one starts at i4
-    int64_t it[IP_MAX_LOOPS];
-    {
-      int64_t v = rowi;
-      for (int l = inner - 1; l >= 0; --l) {
-        const int64_t c = p.loops[l].count;
-        const int64_t q = v / c;
-        it[l] = p.loops[l].start + p.loops[l].step * (v - q * c);
-        v = q;
-      }
-      it[inner] = p.loops[inner].start + i4;
+  int64_t itv[IP_MAX_LOOPS];
+  V4 pre[IP_V4_PRE];
+  auto locate = [&](int64_t item) {                    // iterator values of a work item; returns i4
+    int64_t g = item;
+    const int64_t rowi = divmod(g, groups);
+    if (inner > 0) decode_loops(p, 0, inner - 1, rowi, itv);
+    itv[inner_slot] = p.loops[inner].start + (g << 2);
+    return g << 2;
+  };
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i4 = 0;
+  if (item < total) {
+    i4 = locate(item);
+    prefetch_v4(p, itv, i4, n, pre);
+  }
+  while (item < total) {
+    commit_v4(p, s, pre);
+    load_rest_v4(p, s, itv, i4, n);
+    float* o = reinterpret_cast<float*>(p.write.base) + flat_v4(p.write, itv);
+    const int64_t cur_i4 = i4;
+    item += stride;
+    if (item < total) {
+      i4 = locate(item);
+      prefetch_v4(p, itv, i4, n, pre);
     }
-    auto flat = [&](const IpTensorOp& op) {
-      int64_t idx = op.offset;
-      for (int t = 0; t < op.nterms; ++t)
-        for (int l = 0; l <= inner; ++l)
-          if (p.loops[l].slot == op.slot[t]) idx += op.coef[t] * it[l];
-      return idx;
-    };
-    const bool full = i4 + 3 < n;
-    for (int k = 0; k < p.nreads; ++k) {
-      const IpTensorOp& op = p.reads[k];
-      const float* src = reinterpret_cast<const float*>(op.base) + flat(op);
-      V4 v;
-      if (!op.streaming) {
-        const float f = __ldg(src);
-        v = V4{f, f, f, f};
-      } else if (full && op.aligned16) {
-        const float4 t = *reinterpret_cast<const float4*>(src);
-        v = V4{t.x, t.y, t.z, t.w};
-      } else {
-        v.x = src[0];
-        v.y = i4 + 1 < n ? src[1] : 0.0f;
-        v.z = i4 + 2 < n ? src[2] : 0.0f;
-        v.w = i4 + 3 < n ? src[3] : 0.0f;
-      }
-      s[op.dst] = v;
-    }
-    for (int k = 0; k < p.ninstrs; ++k) {
-      const IpInstr in = p.instrs[k];
-      V4 r = V4{0.f, 0.f, 0.f, 0.f};
-      switch (in.op) {
-        case IP_FADD: EGB_V4_BIN([](float a, float b) { return a + b; }) break;
-        case IP_FSUB: EGB_V4_BIN([](float a, float b) { return a - b; }) break;
-        case IP_FMUL: EGB_V4_BIN([](float a, float b) { return a * b; }) break;
-        case IP_FDIV: EGB_V4_BIN(__fdiv_rn) break;
-        case IP_FNEG: EGB_V4_UN([](float a) { return 0.0f - a; }) break;
-        case IP_SIN: EGB_V4_UN(sinf) break;
-        case IP_COS: EGB_V4_UN(cosf) break;
-        case IP_EXP: EGB_V4_UN(expf) break;
-        case IP_LN: EGB_V4_UN(logf) break;
-        case IP_SQRT: EGB_V4_UN(__fsqrt_rn) break;
-        case IP_POW: EGB_V4_BIN(powf) break;
-        case IP_LOG10: EGB_V4_UN(log10f) break;
-        case IP_LOG2: EGB_V4_UN(log2f) break;
-        case IP_LOGB: EGB_V4_BIN([](float a, float b) { return __fdiv_rn(logf(a), logf(b)); }) break;
-        case IP_FEQ: EGB_V4_BIN([](float a, float b) { return b2f(a == b); }) break;
-        case IP_FLT: EGB_V4_BIN([](float a, float b) { return b2f(a < b); }) break;
-        case IP_FLE: EGB_V4_BIN([](float a, float b) { return b2f(a <= b); }) break;
-        case IP_BEQ: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) == f2b(b)); }) break;
-        case IP_AND: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) && f2b(b)); }) break;
-        case IP_OR: EGB_V4_BIN([](float a, float b) { return b2f(f2b(a) || f2b(b)); }) break;
-        case IP_SELECT: {
-          const V4 c = s[in.a], a = s[in.b], b = s[in.c];
-          r.x = f2b(c.x) ? a.x : b.x; r.y = f2b(c.y) ? a.y : b.y; r.z = f2b(c.z) ? a.z : b.z; r.w = f2b(c.w) ? a.w : b.w;
-          break;
-        }
-        default: break;
-      }
-      s[in.dst] = r;
-    }
+    run_v4(p, s);
     V4 v = s[p.write.dst];
-    float* o = reinterpret_cast<float*>(p.write.base) + flat(p.write);
-    if (full && p.write.aligned16) {
+    if (cur_i4 + 3 < n && p.write.aligned16) {
       if (p.accumulate) {
         const float4 t = *reinterpret_cast<const float4*>(o);
         v.x = t.x + v.x; v.y = t.y + v.y; v.z = t.z + v.z; v.w = t.w + v.w;
@@ -402,7 +477,136 @@ __global__ void __launch_bounds__(IP_THREADS) interp_vec4_kernel(const __grid_co
     } else {
       const float vv[4] = {v.x, v.y, v.z, v.w};
       for (int j = 0; j < 4; ++j)
-        if (i4 + j < n) o[j] = p.accumulate ? o[j] + vv[j] : vv[j];
+        if (cur_i4 + j < n) o[j] = p.accumulate ? o[j] + vv[j] : vv[j];
+    }
+  }
+}
+
+// mode 2, streaming reduction: exactly one reduction loop (unit stride, loops[npar]) that the reads stream
+// along; blockIdx.y walks the output points, the blocks along x share one point's reduction range;
+// 128-bit loads, per-lane fp32 partial sums, warp-shuffle + shared-memory block reduction, one
+// atomicAdd per block.
+template <bool kSmem>
+__global__ void __launch_bounds__(IP_THREADS) interp_vec4_reduce_kernel(const __grid_constant__ IpProgram p) {
+  __shared__ float warp_sums[IP_THREADS / 32];
+  pdl_launch_dependents();
+  EGB_V4_SLOTS(s)
+  pdl_wait();
+  const int red = p.npar;                               // index of the reduction loop
+  const int red_slot = p.loops[red].slot;
+  const int64_t n = p.loops[red].count;
+  const int64_t groups = (n + 3) >> 2;
+  const int64_t chunk = (groups + gridDim.x - 1) / gridDim.x;
+  const int64_t g_begin = (int64_t)blockIdx.x * chunk, g_end = min(groups, g_begin + chunk);
+  float* const out = reinterpret_cast<float*>(p.write.base);
+  int64_t itv[IP_MAX_LOOPS];
+  V4 pre[IP_V4_PRE];
+  for (int64_t point = blockIdx.y; point < p.npoints; point += gridDim.y) {
+    if (red > 0) decode_loops(p, 0, red - 1, point, itv);
+    V4 acc = V4{0.f, 0.f, 0.f, 0.f};
+    int64_t g = g_begin + threadIdx.x;
+    if (g < g_end) {
+      itv[red_slot] = p.loops[red].start + (g << 2);
+      prefetch_v4(p, itv, g << 2, n, pre);
+    }
+    while (g < g_end) {
+      const int64_t i4 = g << 2;
+      commit_v4(p, s, pre);
+      load_rest_v4(p, s, itv, i4, n);
+      g += IP_THREADS;
+      if (g < g_end) {
+        itv[red_slot] = p.loops[red].start + (g << 2);
+        prefetch_v4(p, itv, g << 2, n, pre);
+      }
+      run_v4(p, s);
+      const V4 v = s[p.write.dst];
+      acc.x += v.x;
+      if (i4 + 1 < n) acc.y += v.y;
+      if (i4 + 2 < n) acc.z += v.z;
+      if (i4 + 3 < n) acc.w += v.w;
+    }
+    float t = (acc.x + acc.y) + (acc.z + acc.w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float total = 0.0f;
+      for (int w = 0; w < IP_THREADS / 32; ++w) total += warp_sums[w];
+      atomicAdd(out + flat_v4(p.write, itv), total);
+    }
+    __syncthreads();
+  }
+}
+
+// mode 3, reduction with streaming output points (column sums, naive contractions): the innermost
+// independent loop streams (4 outputs per thread, 128-bit loads along it), one reduction loop with
+// arbitrary strides. blockDim = (GX point groups) x (GY reduction lanes), blockIdx.y splits the
+// reduction range; partial sums meet in shared memory and leave with one atomicAdd per output.
+template <bool kSmem>
+__global__ void __launch_bounds__(IP_THREADS) interp_vec4_pointsum_kernel(const __grid_constant__ IpProgram p) {
+  __shared__ V4 partial[IP_THREADS];
+  pdl_launch_dependents();
+  EGB_V4_SLOTS(s)
+  pdl_wait();
+  const int inner = p.npar - 1, red = p.npar;
+  const int inner_slot = p.loops[inner].slot, red_slot = p.loops[red].slot;
+  const int64_t n = p.loops[inner].count;
+  const int64_t groups = (n + 3) >> 2;
+  const int64_t total = (p.npoints / n) * groups;
+  const int64_t R = p.loops[red].count;
+  const int64_t chunk = (R + gridDim.y - 1) / gridDim.y;
+  const int64_t r_begin = (int64_t)blockIdx.y * chunk, r_end = min(R, r_begin + chunk);
+  const int gx = blockDim.x, gy = blockDim.y, tid = threadIdx.x + threadIdx.y * gx;
+  float* const out = reinterpret_cast<float*>(p.write.base);
+  int64_t itv[IP_MAX_LOOPS];
+  V4 pre[IP_V4_PRE];
+  for (int64_t base = (int64_t)blockIdx.x * gx; base < total; base += (int64_t)gridDim.x * gx) {
+    const int64_t item = base + threadIdx.x;
+    const bool valid = item < total;
+    V4 acc = V4{0.f, 0.f, 0.f, 0.f};
+    int64_t i4 = 0;
+    if (valid) {
+      int64_t g = item;
+      const int64_t rowi = divmod(g, groups);
+      if (inner > 0) decode_loops(p, 0, inner - 1, rowi, itv);
+      i4 = g << 2;
+      itv[inner_slot] = p.loops[inner].start + i4;
+      int64_t r = r_begin + threadIdx.y;
+      if (r < r_end) {
+        itv[red_slot] = p.loops[red].start + p.loops[red].step * r;
+        prefetch_v4(p, itv, i4, n, pre);
+      }
+      while (r < r_end) {
+        commit_v4(p, s, pre);
+        load_rest_v4(p, s, itv, i4, n);
+        r += gy;
+        if (r < r_end) {
+          itv[red_slot] = p.loops[red].start + p.loops[red].step * r;
+          prefetch_v4(p, itv, i4, n, pre);
+        }
+        run_v4(p, s);
+        const V4 v = s[p.write.dst];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (gy > 1) {
+      partial[tid] = acc;
+      __syncthreads();
+      if (threadIdx.y == 0) {
+        for (int j = 1; j < gy; ++j) {
+          const V4 o = partial[threadIdx.x + j * gx];
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+      }
+      __syncthreads();
+    }
+    if (valid && threadIdx.y == 0) {
+      float* o = out + flat_v4(p.write, itv);   // the write has no term on the reduction loop
+      atomicAdd(o, acc.x);
+      if (i4 + 1 < n) atomicAdd(o + 1, acc.y);
+      if (i4 + 2 < n) atomicAdd(o + 2, acc.z);
+      if (i4 + 3 < n) atomicAdd(o + 3, acc.w);
     }
   }
 }
@@ -430,7 +634,9 @@ void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs
 }
 
 int interp_reduction_splits(const IpProgram& prog, int pb, int rb, bool strict, int sm_count) {
-  if (strict || prog.scatter || prog.vec4 || prog.nred < (1 << 16)) return 1;
+  if (strict || prog.scatter) return 1;
+  if (prog.vec4 >= 2) return 2;  // the 4-wide reductions always combine their blocks with atomicAdd
+  if (prog.vec4 || prog.nred < (1 << 16)) return 1;
   const int64_t nblocks = (prog.npoints + pb - 1) / pb;
   if (nblocks >= 2 * sm_count) return 1;
   int64_t s = (4 * (int64_t)sm_count) / nblocks;
@@ -444,13 +650,52 @@ void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int poin
                    cudaStream_t st, int rsplit) {
   if (prog.npoints <= 0 || prog.nred <= 0) return;
   if (prog.vec4 && !strict) {
-    const int64_t row_len = prog.loops[prog.npar - 1].count;
-    const int64_t groups = (prog.npoints / row_len) * ((row_len + 3) / 4);
-    const int64_t nb = (groups + IP_THREADS - 1) / IP_THREADS;
-    const int64_t capb = (int64_t)ctx.sm_count * 16;
-    {
+    const bool smem_slots = prog.nslots <= 24;   // 24 slots x 256 threads x 16 B = 96 KB
+    const size_t smem = smem_slots ? (size_t)prog.nslots * IP_THREADS * sizeof(V4) : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      EGB_CUDA(cudaFuncSetAttribute(interp_vec4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      EGB_CUDA(cudaFuncSetAttribute(interp_vec4_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      EGB_CUDA(cudaFuncSetAttribute(interp_vec4_pointsum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    if (prog.vec4 == 1) {
+      const int64_t row_len = prog.loops[prog.npar - 1].count;
+      const int64_t groups = (prog.npoints / row_len) * ((row_len + 3) / 4);
+      const int64_t nb = (groups + IP_THREADS - 1) / IP_THREADS;
+      const int64_t capb = (int64_t)ctx.sm_count * 16;
+      const dim3 grid((int)(nb < capb ? nb : capb));
       Launch l(ctx, KC_ELTWISE, st);
-      launch_kernel(ctx, interp_vec4_kernel, dim3((int)(nb < capb ? nb : capb)), dim3(IP_THREADS), 0, st, prog);
+      if (smem_slots) launch_kernel(ctx, interp_vec4_kernel<true>, grid, dim3(IP_THREADS), smem, st, prog);
+      else launch_kernel(ctx, interp_vec4_kernel<false>, grid, dim3(IP_THREADS), 0, st, prog);
+    } else if (prog.vec4 == 2) {
+      if (!prog.accumulate) fail(EGB_ERR_GPU, "interp: a streaming reduction needs an accumulating output");
+      const int64_t groups = (prog.nred + 3) / 4;
+      int64_t by = prog.npoints < 65535 ? prog.npoints : 65535;
+      int64_t bx = (8 * (int64_t)ctx.sm_count + by - 1) / by;            // ~8 blocks per SM in total
+      const int64_t max_bx = (groups + IP_THREADS * 4 - 1) / (IP_THREADS * 4);  // >= 4 groups per thread
+      if (bx > max_bx) bx = max_bx;
+      if (bx < 1) bx = 1;
+      Launch l(ctx, KC_REDUCE, st);
+      if (smem_slots) launch_kernel(ctx, interp_vec4_reduce_kernel<true>, dim3((int)bx, (int)by), dim3(IP_THREADS), smem, st, prog);
+      else launch_kernel(ctx, interp_vec4_reduce_kernel<false>, dim3((int)bx, (int)by), dim3(IP_THREADS), 0, st, prog);
+    } else {
+      if (!prog.accumulate) fail(EGB_ERR_GPU, "interp: a split reduction needs an accumulating output");
+      const int64_t row_len = prog.loops[prog.npar - 1].count;
+      const int64_t items = (prog.npoints / row_len) * ((row_len + 3) / 4);
+      int gx = 8;                                        // >= 8 lanes x 16 B: whole 128-byte lines
+      while (gx < IP_THREADS && gx < items) gx *= 2;
+      const int gy = IP_THREADS / gx;
+      int64_t bx = (items + gx - 1) / gx;
+      if (bx > 65535) bx = 65535;
+      int64_t by = (8 * (int64_t)ctx.sm_count + bx - 1) / bx;            // ~8 blocks per SM in total
+      const int64_t max_by = prog.nred / ((int64_t)gy * 8);              // >= 8 steps per thread
+      if (by > max_by) by = max_by;
+      if (by > 65535) by = 65535;
+      if (by < 1) by = 1;
+      Launch l(ctx, KC_REDUCE, st);
+      if (smem_slots) launch_kernel(ctx, interp_vec4_pointsum_kernel<true>, dim3((int)bx, (int)by), dim3(gx, gy), smem, st, prog);
+      else launch_kernel(ctx, interp_vec4_pointsum_kernel<false>, dim3((int)bx, (int)by), dim3(gx, gy), 0, st, prog);
     }
     EGB_CUDA(cudaGetLastError());
     return;

@@ -475,6 +475,104 @@ bool kernel_loops_full(const Kernel& k, const ShapeTable& shapes) {
   return true;
 }
 
+// Loop-nest simplification for the large generic kernels (nothing but the index arithmetic sees the
+// iterators): every loop becomes 0 .. count with unit step (start and step folded into the accesses),
+// loops of one iteration disappear, and adjacent loops of the same kind whose accesses are contiguous
+// across them (coefficient of the outer == coefficient of the inner x count of the inner, for every
+// access) merge into one. A [N,H,W,F] elementwise kernel becomes one flat loop; sum over (n, y, x) of
+// t[n,y,x,f] becomes one reduction loop of stride F.
+static void simplify_loops(IpProgram& ip) {
+  auto arity = [](uint8_t op) {
+    switch (op) {
+      case IP_FNEG: case IP_SIN: case IP_COS: case IP_EXP: case IP_LN: case IP_SQRT: case IP_LOG10: case IP_LOG2:
+      case IP_INEG: case IP_TOSCALAR: case IP_TOINDEX: case IP_ARRAY_READ: return 1;
+      case IP_SELECT: return 3;
+      default: return 2;
+    }
+  };
+  bool as_value[256] = {false};
+  for (int i = 0; i < ip.ninstrs; ++i) {
+    const IpInstr& in = ip.instrs[i];
+    const int n = arity(in.op);
+    as_value[in.a] = true;
+    if (n >= 2) as_value[in.b] = true;
+    if (n >= 3) as_value[in.c] = true;
+  }
+  for (int i = 0; i < ip.ninstrs; ++i)
+    if (ip.instrs[i].op == IP_ARRAY_READ) return;   // array elements are referenced through a slot table
+  std::vector<IpTensorOp*> ops;
+  for (int r = 0; r < ip.nreads; ++r) ops.push_back(&ip.reads[r]);
+  ops.push_back(&ip.write);
+  auto loop_of_slot = [&](int slot) {
+    for (int l = 0; l < ip.nloops; ++l)
+      if (ip.loops[l].slot == slot) return l;
+    return -1;
+  };
+  for (auto* op : ops)
+    for (int t = 0; t < op->nterms; ++t)
+      if (loop_of_slot(op->slot[t]) < 0) return;   // an index term that is not a loop iterator
+  for (int l = 0; l < ip.nloops; ++l)
+    if (as_value[ip.loops[l].slot]) return;         // an iterator used as data
+  // canonical terms: one per loop, zero coefficients dropped, start/step folded
+  auto coef_of = [&](const IpTensorOp& op, int slot) {
+    int64_t c = 0;
+    for (int t = 0; t < op.nterms; ++t)
+      if (op.slot[t] == slot) c += op.coef[t];
+    return c;
+  };
+  for (auto* op : ops) {
+    int64_t coef[IP_MAX_LOOPS];
+    for (int l = 0; l < ip.nloops; ++l) {
+      const int64_t c = coef_of(*op, ip.loops[l].slot);
+      op->offset += c * ip.loops[l].start;
+      coef[l] = c * ip.loops[l].step;
+    }
+    op->nterms = 0;
+    for (int l = 0; l < ip.nloops; ++l)
+      if (coef[l] != 0 && ip.loops[l].count > 1) {
+        op->coef[op->nterms] = coef[l];
+        op->slot[op->nterms] = ip.loops[l].slot;
+        ++op->nterms;
+      }
+  }
+  for (int l = 0; l < ip.nloops; ++l) {
+    ip.loops[l].start = 0;
+    ip.loops[l].step = 1;
+  }
+  auto erase_loop = [&](int l) {
+    for (int j = l; j + 1 < ip.nloops; ++j) ip.loops[j] = ip.loops[j + 1];
+    if (l < ip.npar) --ip.npar;
+    --ip.nloops;
+  };
+  for (int l = ip.nloops - 1; l >= 0; --l)
+    if (ip.loops[l].count == 1 && ip.nloops > 1) erase_loop(l);
+  bool changed = true;
+  while (changed) {
+    changed = false;
+    for (int l = 0; l + 1 < ip.nloops && !changed; ++l) {
+      const bool same_kind = (l + 1 < ip.npar) || (l >= ip.npar);
+      if (!same_kind) continue;
+      const int so = ip.loops[l].slot, si = ip.loops[l + 1].slot;
+      bool ok = true;
+      for (auto* op : ops) ok = ok && coef_of(*op, so) == coef_of(*op, si) * ip.loops[l + 1].count;
+      if (!ok) continue;
+      for (auto* op : ops) {
+        int w = 0;
+        for (int t = 0; t < op->nterms; ++t)
+          if (op->slot[t] != so) {
+            op->coef[w] = op->coef[t];
+            op->slot[w] = op->slot[t];
+            ++w;
+          }
+        op->nterms = (uint8_t)w;
+      }
+      ip.loops[l + 1].count *= ip.loops[l].count;
+      erase_loop(l);
+      changed = true;
+    }
+  }
+}
+
 Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<int, void*>& ptrs, int64_t epoch,
                      bool strict, bool overwrite, int sm_count) {
   Lowerer lw(k, shapes, epoch);
@@ -581,13 +679,17 @@ Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<i
     ++pos;
   }
   ip.accumulate = (overwrite && !ip.scatter) ? 0 : 1;
+  // small kernels keep their loop structure (row chains look for the batch loop)
+  if (!strict && ip.nindex_instrs == 0 && ip.npoints * ip.nred > (1 << 16)) simplify_loops(ip);
+  bool iter_slots_small = true;   // the 4-wide kernels index iterator values by slot
+  for (int l = 0; l < ip.nloops; ++l) iter_slots_small = iter_slots_small && ip.loops[l].slot < IP_MAX_LOOPS;
 
   // 4-wide fast path: no reduction, the innermost independent loop has unit stride, every access either
   // streams with it (coefficient 1) or does not depend on it (broadcast along the row), and the
   // expression only uses fp32 / boolean operations. Outer iterators only enter the address arithmetic.
   {
-    bool ok = ip.npar >= 1 && ip.npar == nloops && !ip.scatter && ip.nindex_instrs == 0 && lw.nslots <= 64 &&
-              ip.loops[ip.npar - 1].step == 1 && ip.npoints > 0;
+    bool ok = ip.npar >= 1 && ip.npar == ip.nloops && !ip.scatter && ip.nindex_instrs == 0 && lw.nslots <= 64 &&
+              iter_slots_small && ip.loops[ip.npar - 1].step == 1 && ip.npoints > 0;
     const int inner_slot = ok ? ip.loops[ip.npar - 1].slot : -1;
     const int64_t inner_start = ok ? ip.loops[ip.npar - 1].start : 0;
     auto classify = [&](IpTensorOp& op, bool must_stream) {
@@ -623,6 +725,98 @@ Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<i
     }
     ip.vec4 = ok ? 1 : 0;
   }
+  // streaming reduction (vec4 == 2): exactly one reduction loop with unit stride and a long range, every
+  // read streams with it or ignores it, fp32 / boolean expression; outer iterators only address
+  if (!ip.vec4) {
+    bool ok = ip.nloops == ip.npar + 1 && !ip.scatter && ip.nindex_instrs == 0 && lw.nslots <= 64 &&
+              iter_slots_small && ip.loops[ip.npar].step == 1 && ip.loops[ip.npar].count >= 4096 && ip.npoints > 0;
+    const int red_slot = ok ? ip.loops[ip.npar].slot : -1;
+    const int64_t red_start = ok ? ip.loops[ip.npar].start : 0;
+    auto classify = [&](IpTensorOp& op, bool is_write) {
+      int64_t c_red = 0;
+      bool outer_mult4 = true;
+      for (int t = 0; t < op.nterms; ++t) {
+        if (op.slot[t] == red_slot) {
+          c_red = op.coef[t];
+        } else {
+          bool is_loop = false;
+          for (int l = 0; l < ip.npar; ++l) is_loop = is_loop || ip.loops[l].slot == op.slot[t];
+          if (!is_loop) ok = false;
+          outer_mult4 = outer_mult4 && (op.coef[t] % 4 == 0);
+        }
+      }
+      if (is_write) {
+        if (c_red != 0) ok = false;
+        return;
+      }
+      if (c_red == 1) op.streaming = 1;
+      else if (c_red == 0) op.streaming = 0;
+      else ok = false;
+      const int64_t first = op.offset + (op.streaming ? red_start : 0);
+      op.aligned16 = outer_mult4 && (((op.base >> 2) + (uint64_t)first) & 3) == 0 && (op.base & 3) == 0;
+    };
+    if (ok) {
+      classify(ip.write, true);
+      bool any_stream = false;
+      for (int r = 0; r < ip.nreads; ++r) {
+        classify(ip.reads[r], false);
+        any_stream = any_stream || ip.reads[r].streaming;
+      }
+      ok = ok && any_stream;
+      for (int i = 0; i < ip.ninstrs && ok; ++i) {
+        const uint8_t op = ip.instrs[i].op;
+        const bool fp = (op >= IP_FADD && op <= IP_LOGB) || op == IP_FEQ || op == IP_FLT || op == IP_FLE ||
+                        op == IP_BEQ || op == IP_AND || op == IP_OR || op == IP_SELECT;
+        ok = ok && fp;
+      }
+      for (int i = 0; i < ip.nlits && ok; ++i) ok = ok && (ip.lits[i] >> 32) == 0;
+    }
+    if (ok) ip.vec4 = 2;
+  }
+  // reduction with streaming output points (vec4 == 3): one reduction loop with arbitrary strides, the
+  // innermost independent loop has unit stride and the write and every read either stream with it or
+  // ignore it
+  if (!ip.vec4) {
+    bool ok = ip.npar >= 1 && ip.nloops == ip.npar + 1 && !ip.scatter && ip.nindex_instrs == 0 && lw.nslots <= 64 &&
+              iter_slots_small && ip.loops[ip.npar - 1].step == 1 && ip.loops[ip.npar - 1].count >= 4 &&
+              ip.nred >= 64 && ip.npoints * ip.nred > (1 << 16);
+    const int inner_slot = ok ? ip.loops[ip.npar - 1].slot : -1;
+    const int64_t inner_start = ok ? ip.loops[ip.npar - 1].start : 0;
+    auto classify = [&](IpTensorOp& op, bool is_write) {
+      int64_t inner_coef = 0;
+      bool other_mult4 = true;
+      for (int t = 0; t < op.nterms; ++t) {
+        if (op.slot[t] == inner_slot) {
+          inner_coef = op.coef[t];
+        } else {
+          bool is_loop = false;
+          for (int l = 0; l < ip.nloops; ++l) is_loop = is_loop || ip.loops[l].slot == op.slot[t];
+          if (!is_loop) ok = false;
+          int64_t step = 1, start = 0;
+          for (int l = 0; l < ip.nloops; ++l)
+            if (ip.loops[l].slot == op.slot[t]) { step = ip.loops[l].step; start = ip.loops[l].start; }
+          other_mult4 = other_mult4 && ((op.coef[t] * step) % 4 == 0) && ((op.coef[t] * start) % 4 == 0);
+        }
+      }
+      if (inner_coef == 1) op.streaming = 1;
+      else if (inner_coef == 0 && !is_write) op.streaming = 0;
+      else ok = false;
+      const int64_t first = op.offset + (op.streaming ? inner_start : 0);
+      op.aligned16 = other_mult4 && (((op.base >> 2) + (uint64_t)first) & 3) == 0 && (op.base & 3) == 0;
+    };
+    if (ok) {
+      classify(ip.write, true);
+      for (int r = 0; r < ip.nreads; ++r) classify(ip.reads[r], false);
+      for (int i = 0; i < ip.ninstrs && ok; ++i) {
+        const uint8_t op = ip.instrs[i].op;
+        const bool fp = (op >= IP_FADD && op <= IP_LOGB) || op == IP_FEQ || op == IP_FLT || op == IP_FLE ||
+                        op == IP_BEQ || op == IP_AND || op == IP_OR || op == IP_SELECT;
+        ok = ok && fp;
+      }
+      for (int i = 0; i < ip.nlits && ok; ++i) ok = ok && (ip.lits[i] >> 32) == 0;
+    }
+    if (ok) ip.vec4 = 3;
+  }
   ip.nslots = (uint8_t)std::min(lw.nslots, 255);
 
   Lowered out;
@@ -648,12 +842,19 @@ Lowered lower_kernel(const Kernel& k, const ShapeTable& shapes, const std::map<i
           }
       return best;
     };
-    if (par.empty()) {
+    if (ip.npar == 0) {
       points_fast = 0;
     } else {
-      const int64_t cp = min_read_coef(iter_slot[par.back()]);
-      const int64_t cr = red.empty() ? INT64_MAX : min_read_coef(iter_slot[red.back()]);
+      const int64_t cp = min_read_coef(ip.loops[ip.npar - 1].slot);
+      const int64_t cr = ip.nloops == ip.npar ? INT64_MAX : min_read_coef(ip.loops[ip.nloops - 1].slot);
       points_fast = cp <= cr ? 1 : 0;
+    }
+    // when neighbouring lanes walk the output points (contiguous reads along the points), keep at
+    // least a full warp of points per block: wider parallelism then comes from splitting the reduction
+    // over blocks (interp_reduction_splits), not from shrinking the coalesced dimension
+    if (points_fast && pb < 32 && ip.npoints >= 32) {
+      pb = 32;
+      rb = 8;
     }
   }
   out.pb = pb;

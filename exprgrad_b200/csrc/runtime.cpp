@@ -578,7 +578,7 @@ void build_nodes_impl(Model& m, Plan& plan) {
         // covered) output tensor cleared
         Node z;
         z.kind = Node::MEMSET;
-        z.label = "zero tensor" + std::to_string(k.write.tensor - 1) + " (split reduction)";
+        z.label = "zero tensor" + std::to_string(k.write.tensor - 1) + " (reduction combined with atomics)";
         z.ptr = ptrs[k.write.tensor];
         z.bytes = (size_t)shape_len(plan.shapes.at(k.write.tensor)) * 4;
         z.writes.push_back(k.write.tensor);

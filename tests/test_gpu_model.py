@@ -360,5 +360,47 @@ def test_generic_kernel_fast_paths_match_numpy(ctx):
     got2 = pm.call("loss", {"p": p, "t": t})       # the zero fill of the split reduction must repeat every call
     assert abs(float(got2[0]) - want) / want < 1e-5
     mm = rng.uniform(-1, 1, (70000, 300)).astype(np.float32)
-    assert_close(pm.call("colsum", {"m": mm}), mm.astype(np.float64).sum(0), tol=1e-5, what="tall column sum")
+    for _ in range(2):
+        assert_close(pm.call("colsum", {"m": mm}), mm.astype(np.float64).sum(0), tol=1e-5, what="tall column sum")
+    assert "4wide-point-reduce" in pm.describe_plan()
+    mm = rng.uniform(-1, 1, (9001, 37)).astype(np.float32)       # ragged width: unaligned rows, tail lanes
+    assert_close(pm.call("colsum", {"m": mm}), mm.astype(np.float64).sum(0), tol=1e-5, what="ragged column sum")
+    pm.free()
+    # loops that merge: [N,H,W,F] elementwise with a broadcast over the merged (n,y,x) loop, and the bias-gradient sum
+    act = F.Fun(); n_, y, x, f = F.Iter("n"), F.Iter("y"), F.Iter("x"), F.Iter("f")
+    act[n_, y, x, f] += F.input("t")[n_, y, x, f] * 2.0 + F.input("bias")[f]
+    db = F.Fun(); n_, y, x, f = F.Iter("n"), F.Iter("y"), F.Iter("x"), F.Iter("f")
+    db[f] += F.input("t")[n_, y, x, f]
+    pm = M.compile(act.target("act", "gpu"), db.target("dbias", "gpu"), gpu=ctx)
+    t4 = rng.uniform(-1, 1, (6, 31, 29, 24)).astype(np.float32); bb = rng.uniform(-1, 1, (24,)).astype(np.float32)
+    assert np.array_equal(pm.call("act", {"t": t4, "bias": bb}), t4 * np.float32(2.0) + bb)
+    assert "loops=2" in pm.describe_plan()
+    assert_close(pm.call("dbias", {"t": t4}), t4.astype(np.float64).sum((0, 1, 2)), tol=1e-5, what="bias gradient sum")
+    assert "4wide-point-reduce" in pm.describe_plan() and "loops=2" in pm.describe_plan()
+    pm.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols", [(7, 4099), (300, 8192), (1, 1 << 20), (3, 65537)])
+def test_streaming_reductions_match_numpy(ctx, rows, cols):
+    """Row-wise reductions long enough for the 4-wide streaming reduction: ragged row lengths (tail lanes,
+    unaligned rows), a broadcast operand inside the reduced expression, repeated calls (the output is
+    cleared before the blocks combine with atomics) and the plan text naming the path."""
+    from exprgrad_b200 import frontend as F, model as M
+    rng = np.random.default_rng(rows * 31 + cols)
+    rs = F.Fun(); y, x = F.Iter("y"), F.Iter("x")
+    rs[y] += F.input("a")[y, x] * F.input("w")[x] + F.input("c")[y]
+    dot = F.Fun(); y, x = F.Iter("y"), F.Iter("x")
+    dot[0] += F.sq(F.input("a")[y, x])
+    pm = M.compile(rs.target("rowsum", "gpu"), dot.target("sumsq", "gpu"), gpu=ctx)
+    a = rng.uniform(-1, 1, (rows, cols)).astype(np.float32)
+    w = rng.uniform(-1, 1, (cols,)).astype(np.float32)
+    c = rng.uniform(-1, 1, (rows,)).astype(np.float32)
+    want = (a.astype(np.float64) * w).sum(1) + c.astype(np.float64) * cols
+    for _ in range(2):
+        assert_close(pm.call("rowsum", {"a": a, "w": w, "c": c}), want, tol=2e-5, what="row sums")
+    assert "4wide-stream-reduce" in pm.describe_plan()
+    want2 = (a.astype(np.float64) ** 2).sum()
+    got2 = pm.call("sumsq", {"a": a})
+    assert abs(float(got2[0]) - want2) / want2 < 1e-5
     pm.free()
