@@ -243,7 +243,8 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
                              "algorithmic_tflops = 2MNK / kernel time; fp32-equivalent ceiling = peak / 3"},
         "e2e": {"value": world * flop / (e2e_ms / e2e_steps * 1e-3) / 1e9, "unit": "GFLOP/s",
                 "h2d_bytes_per_step": 2 * n * n * 4, "d2h_bytes_per_step": n * n * 4, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "model.call('c', {a, b}) with pinned host arrays: H2D a, b; split+GEMM; D2H c"},
+                "api": "model.call('c', {a, b}, out=c) with pinned host arrays -> egb_model_call_read: H2D of b, then a in "
+                       "2 MiB row blocks; split + GEMM per block; D2H of each c block - copies and tensor cores overlap on three streams"},
         "clocks": clocks,
     }
     model.free()

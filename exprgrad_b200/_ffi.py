@@ -96,6 +96,7 @@ _SIGS = {
     "egb_model_tensor_shape": (I, [P, I, PI, PI64]),
     "egb_model_tensor_device_ptr": (I, [P, I, PP]),
     "egb_model_call": (I, [P, S, I, ctypes.POINTER(S), PP, PI, PI64, PI, PI, PI64]),
+    "egb_model_call_read": (I, [P, S, I, ctypes.POINTER(S), PP, PI, PI64, PI, P, SZ, PI, PI64]),
     "egb_model_read_output": (I, [P, P, SZ]),
     "egb_model_fit": (I, [P, S, I, ctypes.POINTER(S), PP, PI, PI64, I64, PI64]),
     "egb_model_describe_plan": (I, [P, P, SZ, ctypes.POINTER(SZ)]),

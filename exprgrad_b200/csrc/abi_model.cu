@@ -4,6 +4,7 @@
 //   Model.fit             exprgrad/model.nim:413-454  (egb_model_fit)
 //   model.params/caches   exprgrad/model.nim:37-38    (egb_model_write_tensor / read_tensor)
 //   inferShapes           exprgrad/passes.nim:1386-1436 (egb_program_infer_shapes)
+#include <stdlib.h>
 #include <string.h>
 
 #include "abi_model.hpp"
@@ -418,6 +419,189 @@ int egb_model_call(egb_model* m, const char* target, int n_args, const char* con
     } else {
       *out_rank = -1;
     }
+  }
+  EGB_CATCH
+}
+
+// ---- Model.call with a host destination (model.nim:392-406: run the target, then readOutput) -------
+// A target that is one plain contraction of host operands (benchmarks/matmul/matmul_gpu.nim:28-75 times
+// exactly this: upload, multiply, read back) is limited by the PCIe copies, not by the tensor cores. Its
+// rows are independent (`y` is a parallel loop of c[y,x] ++= a[y,it]*b[it,x]), so the call is streamed:
+// B is uploaded first, then A in row blocks; each block is split into bf16 planes, multiplied and copied
+// back while the next block is still arriving - H2D, tensor cores and D2H overlap on three streams.
+namespace {
+
+struct RowStream {
+  Node* split_a = nullptr;
+  Node* split_b = nullptr;
+  Node* gemm = nullptr;
+  Node* memset = nullptr;
+  int a_id = 0, b_id = 0;
+};
+
+bool find_row_stream(Plan& plan, const Args& a, const int* on_device, RowStream& rs) {
+  std::vector<Node*> splits;
+  for (auto& n : plan.nodes) {
+    if (n.kind == Node::SPLIT) splits.push_back(&n);
+    else if (n.kind == Node::GEMM && !rs.gemm) rs.gemm = &n;
+    else if (n.kind == Node::MEMSET && !rs.memset) rs.memset = &n;
+    else return false;
+  }
+  if (!rs.gemm || splits.size() != 2) return false;
+  const GemmArgs& g = rs.gemm->gemm;
+  const int out = plan.target->output;
+  if (!out || g.flags != 0 || g.epi != EPI_NONE || g.bias || g.colsum || g.a_mn || g.splits > 1 || g.alpha != 1.0f) return false;
+  auto ot = plan.tensors.find(out);
+  if (ot == plan.tensors.end() || g.C != ot->second.ptr || g.ldc != g.N) return false;
+  for (Node* s : splits) {
+    if (s->split_hi == g.a_hi) rs.split_a = s;
+    else if (s->split_hi == g.b_hi) rs.split_b = s;
+  }
+  if (!rs.split_a || !rs.split_b || rs.split_a->split_transpose || rs.split_a->split_act || rs.split_a->split_rows != g.M) return false;
+  // both operands must be inputs of this call; A has to come from the host
+  for (size_t i = 0; i < a.ids.size(); ++i) {
+    auto t = plan.tensors.find(a.ids[i]);
+    if (t == plan.tensors.end()) continue;
+    const bool dev = on_device && on_device[i];
+    if (!dev && t->second.ptr == rs.split_a->split_src) rs.a_id = a.ids[i];
+    if (t->second.ptr == rs.split_b->split_src || (dev && plan.bound[a.ids[i]] == rs.split_b->split_src)) rs.b_id = a.ids[i];
+  }
+  return rs.a_id != 0 && rs.b_id != 0 && (int64_t)g.M * g.K >= ((int64_t)1 << 20);
+}
+
+struct StreamEvents {
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t get(size_t i) {
+    while (ev.size() <= i) {
+      cudaEvent_t e;
+      EGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev.push_back(e);
+    }
+    return ev[i];
+  }
+};
+
+void run_row_stream(Model& model, Context& c, Plan& plan, const RowStream& rs, const Args& a, const void* const* data,
+                    const int* on_device, char* out_host) {
+  static thread_local StreamEvents events;
+  for (auto& st : c.aux_stream)
+    if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaStream_t h2d = c.aux_stream[0], d2h = c.aux_stream[1], comp = c.stream;
+  const GemmArgs& g = rs.gemm->gemm;
+  const Node& sa = *rs.split_a;
+  // everything queued on the main stream so far (earlier calls) is ordered before the copies
+  cudaEvent_t e_start = events.get(0);
+  EGB_CUDA(cudaEventRecord(e_start, comp));
+  EGB_CUDA(cudaStreamWaitEvent(h2d, e_start, 0));
+  EGB_CUDA(cudaStreamWaitEvent(d2h, e_start, 0));
+  const char* a_host = nullptr;
+  for (size_t i = 0; i < a.ids.size(); ++i) {
+    auto t = plan.tensors.find(a.ids[i]);
+    if (t == plan.tensors.end()) continue;
+    if (a.ids[i] == rs.a_id) {
+      a_host = (const char*)data[i];
+      continue;
+    }
+    if (!(on_device && on_device[i]) && t->second.bytes)
+      EGB_CUDA(cudaMemcpyAsync(t->second.ptr, data[i], t->second.bytes, cudaMemcpyHostToDevice, h2d));
+  }
+  cudaEvent_t e_b = events.get(1);
+  EGB_CUDA(cudaEventRecord(e_b, h2d));
+  EGB_CUDA(cudaStreamWaitEvent(comp, e_b, 0));
+  if (rs.memset) EGB_CUDA(cudaMemsetAsync(rs.memset->ptr, 0, rs.memset->bytes, comp));
+  {
+    const Node& sb = *rs.split_b;
+    launch_split_bf16(c, sb.split_src, sb.split_rows, sb.split_cols, sb.split_ld, sb.split_transpose, sb.split_hi,
+                      sb.split_mid, sb.split_dst_ld, sb.split_act, comp);
+  }
+  // row blocks of about 2 MiB of A (multiples of the 128-row MMA tile)
+  const size_t row_bytes = (size_t)sa.split_cols * 4;
+  static const char* blk_env = getenv("EGB_STREAM_BLOCK_KIB");
+  const size_t blk_bytes = blk_env ? (size_t)atol(blk_env) << 10 : (size_t)2 << 20;
+  int64_t rows_per = (int64_t)(blk_bytes / std::max<size_t>(row_bytes, 1)) / 128 * 128;
+  if (rows_per < 128) rows_per = 128;
+  size_t ei = 2;
+  for (int64_t r0 = 0; r0 < g.M; r0 += rows_per) {
+    const int rc = (int)std::min<int64_t>(rows_per, g.M - r0);
+    char* a_dev = (char*)const_cast<float*>(sa.split_src) + (size_t)r0 * sa.split_ld * 4;
+    if ((size_t)sa.split_ld * 4 == row_bytes)
+      EGB_CUDA(cudaMemcpyAsync(a_dev, a_host + (size_t)r0 * row_bytes, (size_t)rc * row_bytes, cudaMemcpyHostToDevice, h2d));
+    else
+      EGB_CUDA(cudaMemcpy2DAsync(a_dev, (size_t)sa.split_ld * 4, a_host + (size_t)r0 * row_bytes, row_bytes, row_bytes, rc,
+                                 cudaMemcpyHostToDevice, h2d));
+    cudaEvent_t e_a = events.get(ei++);
+    EGB_CUDA(cudaEventRecord(e_a, h2d));
+    EGB_CUDA(cudaStreamWaitEvent(comp, e_a, 0));
+    launch_split_bf16(c, sa.split_src + (size_t)r0 * sa.split_ld, rc, sa.split_cols, sa.split_ld, false,
+                      sa.split_hi + (size_t)r0 * sa.split_dst_ld, sa.split_mid + (size_t)r0 * sa.split_dst_ld, sa.split_dst_ld, 0, comp);
+    GemmArgs gc = g;
+    gc.a_hi = g.a_hi + (size_t)r0 * g.lda;
+    gc.a_mid = g.a_mid + (size_t)r0 * g.lda;
+    gc.M = rc;
+    gc.C = g.C + (size_t)r0 * g.ldc;
+    gc.bn = 0;
+    launch_gemm_bf16x3(c, gc, comp);
+    cudaEvent_t e_c = events.get(ei++);
+    EGB_CUDA(cudaEventRecord(e_c, comp));
+    EGB_CUDA(cudaStreamWaitEvent(d2h, e_c, 0));
+    EGB_CUDA(cudaMemcpyAsync(out_host + (size_t)r0 * g.ldc * 4, gc.C, (size_t)rc * g.ldc * 4, cudaMemcpyDeviceToHost, d2h));
+  }
+  cudaEvent_t e_done = events.get(ei++);
+  EGB_CUDA(cudaEventRecord(e_done, d2h));
+  EGB_CUDA(cudaStreamWaitEvent(comp, e_done, 0));
+  EGB_CUDA(cudaStreamSynchronize(comp));
+  plan.runs++;
+  model.last_plan = &plan;
+}
+
+}  // namespace
+
+int egb_model_call_read(egb_model* m, const char* target, int n_args, const char* const* names, const void* const* data,
+                        const int* ranks, const int64_t* dims, const int* on_device, void* out_host, size_t out_bytes,
+                        int* out_rank, int64_t* out_dims) {
+  EGB_TRY
+  Model& model = *m->m;
+  Context& c = m->ctx->c;
+  EGB_CUDA(cudaSetDevice(c.device));
+  if (!model.prog->find_target(target)) fail(EGB_ERR_RUNTIME, "%s is not a target of the model", target);
+  Args a = resolve_args(*model.prog, n_args, names, ranks, dims);
+  Plan& plan = model.get_plan(target, a.ids, a.shapes);
+  const int out = plan.target->output;
+  if (!out) fail(EGB_ERR_RUNTIME, "target %s has no output tensor", target);
+  const auto& shape = plan.shapes.at(out);
+  if (shape.size() > EGB_MAX_RANK) fail(EGB_ERR_SHAPE, "rank %zu exceeds EGB_MAX_RANK", shape.size());
+  if (out_rank) {
+    *out_rank = (int)shape.size();
+    for (size_t i = 0; i < shape.size(); ++i) out_dims[i] = shape[i];
+  }
+  if ((size_t)shape_len(shape) * 4 != out_bytes) fail(EGB_ERR_GPU, "Buffer size is not equal to target size");  // cl.nim:134-135
+  bool rebind = false;
+  for (int i = 0; i < n_args; ++i) {
+    const int id = a.ids[i];
+    if (plan.tensors.find(id) == plan.tensors.end()) continue;
+    const void* want = (on_device && on_device[i]) ? data[i] : nullptr;
+    auto b = plan.bound.find(id);
+    const void* have = b == plan.bound.end() ? nullptr : b->second;
+    if (want != have) {
+      plan.bound[id] = want;
+      rebind = true;
+    }
+  }
+  if (rebind) model.build_nodes(plan);
+  RowStream rs;
+  if (!model.strict && !c.timing && find_row_stream(plan, a, on_device, rs)) {
+    run_row_stream(model, c, plan, rs, a, data, on_device, (char*)out_host);
+  } else {
+    for (int i = 0; i < n_args; ++i) {
+      auto t = plan.tensors.find(a.ids[i]);
+      if (t == plan.tensors.end()) continue;
+      if (!(on_device && on_device[i]) && t->second.bytes)
+        EGB_CUDA(cudaMemcpyAsync(t->second.ptr, data[i], t->second.bytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    model.run(plan);
+    DevTensor* t = find_tensor(m, out);
+    if (out_bytes) EGB_CUDA(cudaMemcpyAsync(out_host, t->ptr, out_bytes, cudaMemcpyDeviceToHost, c.stream));
+    EGB_CUDA(cudaStreamSynchronize(c.stream));
   }
   EGB_CATCH
 }

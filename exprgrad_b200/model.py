@@ -201,6 +201,15 @@ class Model:
         n, names, data, ranks, dims, on_dev, keep = self._pack(args or {})
         out_rank = ctypes.c_int(0)
         out_dims = (ctypes.c_int64 * MAX_RANK)()
+        if out is not None and isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]:
+            # Model.call into a caller-provided host tensor: one blocking ABI call (streams H2D / compute /
+            # D2H for single-contraction targets); a wrong-sized buffer raises GpuError like cl.nim:134-135
+            check(lib.egb_model_call_read(self.handle, target.encode(), n, names, data, ranks, dims, on_dev,
+                                          out.ctypes.data, out.nbytes, ctypes.byref(out_rank), out_dims))
+            shape = [out_dims[i] for i in range(out_rank.value)]
+            if list(out.shape) != shape:
+                raise RuntimeError_(f"output buffer has shape {list(out.shape)}, the target produces {shape}")
+            return out
         check(lib.egb_model_call(self.handle, target.encode(), n, names, data, ranks, dims, on_dev,
                                  ctypes.byref(out_rank), out_dims))
         if out_rank.value < 0:

@@ -215,6 +215,14 @@ int egb_model_tensor_device_ptr(egb_model* model, int tensor_id, void** ptr);
 int egb_model_call(egb_model* model, const char* target, int n_args, const char* const* names,
                    const void* const* data, const int* ranks, const int64_t* dims, const int* on_device,
                    int* out_rank, int64_t* out_dims);
+/* Model.call as the reference defines it (exprgrad/model.nim:392-406): run the target and return its
+ * output in HOST memory (`out_host`, `out_bytes` must equal the output's size - use
+ * egb_program_infer_shapes to size it). Blocking. When the target is a single plain contraction of host
+ * operands (benchmarks/matmul/matmul_gpu.nim:28-75) the call is streamed in row blocks so that the H2D
+ * copies, the tensor-core work and the D2H copy overlap; every other target runs call + readOutput. */
+int egb_model_call_read(egb_model* model, const char* target, int n_args, const char* const* names,
+                        const void* const* data, const int* ranks, const int64_t* dims, const int* on_device,
+                        void* out_host, size_t out_bytes, int* out_rank, int64_t* out_dims);
 /* readOutput (exprgrad/model.nim:370-376): blocking D2H of the last call's output tensor. */
 int egb_model_read_output(egb_model* model, void* dst, size_t bytes);
 /* Model.fit (exprgrad/model.nim:413-454): shapes inferred once with dim 0 = batch_size, epoch += 1,

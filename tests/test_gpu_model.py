@@ -268,6 +268,35 @@ def test_device_resident_inputs_and_shape_changes(ctx):
     pm.free()
 
 
+@pytest.mark.parametrize("m,k,n", [(2048, 1024, 512), (1300, 1024, 200), (1100, 1000, 136)])
+def test_call_into_host_buffer_streams_row_blocks(ctx, m, k, n):
+    """Model.call with a host destination (model.nim:392-406) on a single-contraction target runs as a
+    row-block pipeline (H2D / tensor cores / D2H on three streams); the result must equal the plain
+    call + readOutput path, including a ragged last block and repeated calls with new data."""
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, gpu as GP, layers as PL, model as M
+    pm = M.compile(*G.matmul(F, PL), gpu=ctx)
+    rng = np.random.default_rng(7)
+    out = GP.pinned_empty((m, n))
+    for rep in range(2):
+        a = rng.uniform(-1, 1, (m, k)).astype(np.float32); b = rng.uniform(-1, 1, (k, n)).astype(np.float32)
+        ref = a.astype(np.float64) @ b.astype(np.float64)
+        got = pm.call("c", {"a": a, "b": b}, out=out)
+        assert got is out
+        assert_close(out, ref, what=f"streamed call rep {rep}")
+        plain = pm.call("c", {"a": a, "b": b})
+        assert_close(plain, ref, what="plain call")
+        # same operand planes, same kernels: blocks of rows do not change any value
+        assert np.array_equal(plain, out)
+        db = eg.alloc_tensor(ctx, b.shape); db.write(b)
+        out[...] = 0
+        pm.call("c", {"a": a, "b": db}, out=out)
+        assert np.array_equal(plain, out)
+    with pytest.raises(eg.GpuError):
+        pm.call("c", {"a": a, "b": b}, out=np.empty((m, n + 1), np.float32))
+    pm.free()
+
+
 def test_dropout_random_tensor(ctx):
     """TensorRandom (model.nim:310-314): refilled U(0,1) on every call; dropout keeps ~(1-p) of the
     inputs scaled by 1/(1-p) (exprgrad/layers/dnn.nim:96-100)."""
