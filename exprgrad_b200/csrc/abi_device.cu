@@ -145,6 +145,10 @@ int egb_context_create(int device, egb_context** out) {
   if (qres != cudaDriverEntryPointSuccess || !fn) fail(EGB_ERR_GPU, "cuTensorMapEncodeTiled not found in driver");
   ctx->c.encode_tiled = (PFN_encodeTiled)fn;
   if (const char* e = getenv("EGB_PDL")) ctx->c.pdl = atoi(e) != 0;
+  if (getenv("EGB_GEMM_TRACE")) {
+    EGB_CUDA(cudaHostAlloc((void**)&ctx->c.trace, (size_t)TRACE_SLOTS * TRACE_SLOT_WORDS * 8, cudaHostAllocMapped));
+    memset(ctx->c.trace, 0, (size_t)TRACE_SLOTS * TRACE_SLOT_WORDS * 8);
+  }
   *out = ctx;
   EGB_CATCH
 }
@@ -154,6 +158,17 @@ int egb_context_destroy(egb_context* ctx) {
   if (!ctx) return EGB_OK;
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
+  if (ctx->c.trace) {
+    if (FILE* f = fopen(getenv("EGB_GEMM_TRACE") ? getenv("EGB_GEMM_TRACE") : "/dev/null", "w")) {
+      const unsigned long long n = ctx->c.trace[0] < TRACE_SLOTS - 1 ? ctx->c.trace[0] : TRACE_SLOTS - 1;
+      for (unsigned long long i = 1; i <= n; ++i) {
+        for (int w = 0; w < TRACE_SLOT_WORDS; ++w) fprintf(f, "%llu ", ctx->c.trace[i * TRACE_SLOT_WORDS + w]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    cudaFreeHost(ctx->c.trace);
+  }
   if (ctx->c.scratch) cudaFree(ctx->c.scratch);
   for (auto st : ctx->c.aux_stream)
     if (st) cudaStreamDestroy(st);
@@ -356,7 +371,8 @@ int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const voi
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.a_mn = (flags & 16) != 0;
   g.b_mn = (flags & 32) != 0;
-  g.C = C; g.ldc = (int)ldc; g.flags = flags & 3; g.bias = bias; g.alpha = alpha; g.bn = bn;
+  g.C = C; g.ldc = (int)ldc; g.flags = flags & 3; g.bias = bias; g.alpha = alpha; g.bn = bn & 0xffff;
+  g.cluster_k = (bn >> 16) & 0xff;  // probing: bn | cluster split-K factor << 16
   if (flags & 4) { g.epi = EPI_RELU; g.D = C; }
   launch_gemm_bf16x3(ctx->c, g, ctx->c.stream);
   EGB_CATCH

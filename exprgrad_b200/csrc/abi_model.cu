@@ -450,7 +450,7 @@ bool find_row_stream(Plan& plan, const Args& a, const int* on_device, RowStream&
   if (!rs.gemm || splits.size() != 2) return false;
   const GemmArgs& g = rs.gemm->gemm;
   const int out = plan.target->output;
-  if (!out || g.flags != 0 || g.epi != EPI_NONE || g.bias || g.colsum || g.a_mn || g.splits > 1 || g.alpha != 1.0f) return false;
+  if (!out || g.flags != 0 || g.epi != EPI_NONE || g.bias || g.colsum || g.a_mn || g.alpha != 1.0f) return false;
   auto ot = plan.tensors.find(out);
   if (ot == plan.tensors.end() || g.C != ot->second.ptr || g.ldc != g.N) return false;
   for (Node* s : splits) {

@@ -66,7 +66,14 @@ struct Context {
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
   cudaEvent_t get_event();
+
+  // Debug timeline (EGB_GEMM_TRACE=<file>): CTA 0 of every contraction launch records globaltimer /
+  // clock64 stamps at its phase boundaries into this pinned, device-mapped buffer (slot 0 = cursor);
+  // dumped as text when the context is destroyed. Null in normal operation.
+  unsigned long long* trace = nullptr;
 };
+constexpr int TRACE_SLOT_WORDS = 24;
+constexpr int TRACE_SLOTS = 4096;
 
 // Kernel classes for the timing interface (egb_context_kernel_time).
 enum KernelClass { KC_GEMM = 0, KC_SPLIT = 1, KC_FILL = 2, KC_INTERP = 3, KC_REDUCE = 4, KC_ELTWISE = 5,
@@ -168,14 +175,13 @@ struct GemmArgs {
   __nv_bfloat16 *out_hi = nullptr, *out_mid = nullptr;  // GEMM_SPLIT_OUT: [M, ld_out] planes
   int ld_out = 0;
   int bn = 0;        // 0 = choose
-  int splits = 1;    // split-K factor (> 1 needs `counters` and a C that is zero-filled or accumulated onto)
-  int* counters = nullptr;  // one int per output tile, zero before the first launch (self-resetting)
+  int cluster_k = 0; // cluster split-K factor: 0 = choose, 1 = off, 2/4/8 = CTAs per output tile
 };
 
 // 2-CTA (cta_group::2) variant for large K-major problems with a plain epilogue (gemm_tcgen05_2cta.cu)
 bool gemm_2cta_eligible(const GemmArgs& a);
 void launch_gemm_bf16x3_2cta(Context& ctx, const GemmArgs& a, cudaStream_t st);
-void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* splits, int* tiles);
+void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* tiles);
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
 

@@ -57,12 +57,48 @@ struct KParams {
   int flags;
   float alpha;
   int a_mn, b_mn;  // operand is MN-major (stored [K, MN] row-major)
-  // split-K (kFused kernel only): every output tile is computed by `splits` CTAs over disjoint
-  // k-block ranges; partial tiles are added into C with RED.ADD and the CTA that arrives last at the
-  // tile's counter re-reads the sum and runs the fused epilogue stages.
+  // cluster split-K: the `ck` CTAs of a thread-block cluster each accumulate a disjoint k-block range of
+  // ONE output tile in their own TMEM, stage the partial tile in shared memory and reduce it through
+  // distributed shared memory; CTA r then runs the fused epilogue on rows [r*128/ck, (r+1)*128/ck).
+  // No atomics, no zero fill, fixed summation order. (splits == ck > 1: one unit per CTA.)
+  int ck;
   int splits, kb_per_split;
-  int* counters;
+  int exp;  // timing experiments (EGB_GEMM_EXP)
+  unsigned long long* trace;  // debug timeline (Context::trace) or null
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// slot words: 0 gtime entry, 1 clk entry, 2 clk setup done, 3 clk pdl_wait passed, 4 clk first operands landed,
+// 5 clk accumulator complete, 6 clk epilogue done, 7 clk exit, 8 gtime exit, 9 M, 10 N, 11 K, 12 BN, 13 ck, 14 grid
+// Stamps are collected in shared memory and copied out once at kernel exit: a store to the host-mapped
+// trace buffer in the middle of a phase stalls the warp's later stores behind a PCIe write (observer effect).
+#define EGB_TRACE(word)                                                        \
+  do {                                                                         \
+    if (trace_slot) trace_sm[word] = (unsigned long long)clock64();            \
+  } while (0)
+
+constexpr int STAGING_PAD = 4;  // floats; keeps 16-byte row-strided accesses conflict-free
+constexpr int WSTAGE_LD = 32 + STAGING_PAD;               // row stride of a warp's 32 x 32 transposition buffer
+constexpr int WSTAGE_BYTES = 4 * 32 * WSTAGE_LD * 4;      // four epilogue warps
+constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 32 + TRACE_SLOT_WORDS * 8;  // mbarriers, TMEM slot, trace pointer + stamps
+
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta_rank) {
+  float4 v;
+  asm volatile(
+      "{\n"
+      ".reg .b32 remote;\n"
+      "mapa.shared::cluster.u32 remote, %4, %5;\n"
+      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [remote];\n"
+      "}\n"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(local_addr), "r"(cta_rank)
+      : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* mid, float v) {
   __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -94,6 +130,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  unsigned long long** trace_slot_shp = reinterpret_cast<unsigned long long**>(tmem_slot + 4);
+  unsigned long long* trace_sm = reinterpret_cast<unsigned long long*>(tmem_slot + 8);  // TRACE_SLOT_WORDS stamps
+  if (threadIdx.x == 0) {
+    unsigned long long* slot = nullptr;
+    if (p.trace && blockIdx.x == 0) {
+      const unsigned long long i = atomicAdd(p.trace, 1ull) + 1;
+      if (i < TRACE_SLOTS) {
+        slot = p.trace + i * TRACE_SLOT_WORDS;
+        for (int w = 0; w < TRACE_SLOT_WORDS; ++w) trace_sm[w] = 0;
+        trace_sm[0] = globaltimer_ns(); trace_sm[1] = (unsigned long long)clock64();
+        trace_sm[9] = p.M; trace_sm[10] = p.N; trace_sm[11] = p.K; trace_sm[12] = p.BN; trace_sm[13] = p.ck; trace_sm[14] = gridDim.x;
+      }
+    }
+    *trace_slot_shp = slot;
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a_hi);
@@ -119,54 +170,74 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  unsigned long long* const trace_slot = *trace_slot_shp;
+  if (threadIdx.x == 0) EGB_TRACE(2);
 
   pdl_launch_dependents();
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the
-      // previous kernel; operand planes written by it may only be read from here on. Every other role
-      // is ordered behind these loads through the mbarrier pipeline.
-      pdl_wait();
-      uint32_t it = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        const int tile = unit / p.splits;
-        const int kb0 = (unit % p.splits) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-        const int m0 = (tile % p.tiles_m) * BM;
-        const int n0 = (tile / p.tiles_m) * p.BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
-          uint8_t* st = smem + s * stage_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-          const int k0 = kb * BK;
-          if (!p.a_mn) {
-            ptx::tma_load_2d(st, &tm_a_hi, &full_bar[s], k0, m0);
-            ptx::tma_load_2d(st + A_PLANE_BYTES, &tm_a_mid, &full_bar[s], k0, m0);
-          } else {
-            // MN-major: one {64 (M), BK (K rows)} box per group of 64 M-elements
-            for (int g = 0; g < BM / 64; ++g) {
-              ptx::tma_load_2d(st + g * MN_GROUP_BYTES, &tm_a_hi, &full_bar[s], m0 + g * 64, k0);
-              ptx::tma_load_2d(st + A_PLANE_BYTES + g * MN_GROUP_BYTES, &tm_a_mid, &full_bar[s], m0 + g * 64, k0);
-            }
-          }
-          uint8_t* sb = st + 2 * A_PLANE_BYTES;
-          if (!p.b_mn) {
-            ptx::tma_load_2d(sb, &tm_b_hi, &full_bar[s], k0, n0);
-            ptx::tma_load_2d(sb + b_plane_bytes, &tm_b_mid, &full_bar[s], k0, n0);
-          } else {
-            for (int g = 0; g < p.BN / 64; ++g) {
-              ptx::tma_load_2d(sb + g * MN_GROUP_BYTES, &tm_b_hi, &full_bar[s], n0 + g * 64, k0);
-              ptx::tma_load_2d(sb + b_plane_bytes + g * MN_GROUP_BYTES, &tm_b_mid, &full_bar[s], n0 + g * 64, k0);
-            }
+    // The whole warp walks the loop convergently and `elect.sync` guards the issue: with `if (lane == 0)`
+    // around the loop nvcc feeds every uniform-register operand of UTMALDG / UTCHMMA through an
+    // ELECT / R2UR / BRA.U.ANY waterfall (~100 cycles per instruction: small contractions were
+    // issue-bound at 0.62 us per 64-deep k-block); under elect.sync it emits them back to back.
+    // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the
+    // previous kernel; operand planes written by it may only be read from here on. Every other role
+    // is ordered behind these loads through the mbarrier pipeline.
+    pdl_wait();
+    if (lane == 0) EGB_TRACE(3);
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int tile = unit / p.splits;
+      const int kb0 = (unit % p.splits) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+      const int m0 = (tile % p.tiles_m) * BM;
+      const int n0 = (tile / p.tiles_m) * p.BN;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        uint8_t* st = smem + s * stage_bytes;
+        const int k0 = kb * BK;
+        if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+        if (!p.a_mn) {
+          ptx::tma_load_2d(st, &tm_a_hi, &full_bar[s], k0, m0);
+          ptx::tma_load_2d(st + A_PLANE_BYTES, &tm_a_mid, &full_bar[s], k0, m0);
+        } else {
+          // MN-major: one {64 (M), BK (K rows)} box per group of 64 M-elements
+#pragma unroll
+          for (int g = 0; g < BM / 64; ++g) {
+            ptx::tma_load_2d(st + g * MN_GROUP_BYTES, &tm_a_hi, &full_bar[s], m0 + g * 64, k0);
+            ptx::tma_load_2d(st + A_PLANE_BYTES + g * MN_GROUP_BYTES, &tm_a_mid, &full_bar[s], m0 + g * 64, k0);
           }
         }
+        uint8_t* sb = st + 2 * A_PLANE_BYTES;
+        if (!p.b_mn) {
+          ptx::tma_load_2d(sb, &tm_b_hi, &full_bar[s], k0, n0);
+          ptx::tma_load_2d(sb + b_plane_bytes, &tm_b_mid, &full_bar[s], k0, n0);
+        } else {
+          for (int g = 0; g < p.BN / 64; ++g) {
+            ptx::tma_load_2d(sb + g * MN_GROUP_BYTES, &tm_b_hi, &full_bar[s], n0 + g * 64, k0);
+            ptx::tma_load_2d(sb + b_plane_bytes + g * MN_GROUP_BYTES, &tm_b_mid, &full_bar[s], n0 + g * 64, k0);
+          }
+        }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
+    // ===================================================== MMA issuer (convergent warp, lane 0 issues)
     const uint32_t idesc = ptx::make_idesc_bf16_f32(BM, p.BN, p.a_mn != 0, p.b_mn != 0);
+    // advancing by UMMA_K = 16 along K: K-major: 32 bytes inside the 128-byte swizzle row;
+    // MN-major: 16 rows of 128 bytes (address field is in 16-byte units)
+    const uint64_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+    const uint64_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+    // descriptors of stage 0; a stage / plane offset only moves the 14-bit start-address field
+    const uint32_t smem0 = ptx::smem_u32(smem);
+    const uint64_t a_desc0 = p.a_mn ? ptx::make_mnmajor_sw128_desc(smem0, MN_GROUP_BYTES) : ptx::make_kmajor_sw128_desc(smem0);
+    const uint64_t b_desc0 = p.b_mn ? ptx::make_mnmajor_sw128_desc(smem0, MN_GROUP_BYTES) : ptx::make_kmajor_sw128_desc(smem0);
+    const uint64_t a_mid_off = (uint64_t)(A_PLANE_BYTES >> 4);
+    const uint64_t b_off = (uint64_t)((2 * A_PLANE_BYTES) >> 4);
+    const uint64_t b_mid_off = b_off + (uint64_t)(b_plane_bytes >> 4);
     uint32_t it = 0;
     uint32_t local_tile = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local_tile) {
@@ -181,19 +252,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const uint32_t ph = (it / p.stages) & 1;
         ptx::mbar_wait(&full_bar[s], ph, 3);  // TMA bytes have landed
         ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t st = ptx::smem_u32(smem + s * stage_bytes);
-          const uint32_t sb = st + 2 * A_PLANE_BYTES;
-          const uint64_t a_hi = p.a_mn ? ptx::make_mnmajor_sw128_desc(st, MN_GROUP_BYTES) : ptx::make_kmajor_sw128_desc(st);
-          const uint64_t a_mid = p.a_mn ? ptx::make_mnmajor_sw128_desc(st + A_PLANE_BYTES, MN_GROUP_BYTES)
-                                        : ptx::make_kmajor_sw128_desc(st + A_PLANE_BYTES);
-          const uint64_t b_hi = p.b_mn ? ptx::make_mnmajor_sw128_desc(sb, MN_GROUP_BYTES) : ptx::make_kmajor_sw128_desc(sb);
-          const uint64_t b_mid = p.b_mn ? ptx::make_mnmajor_sw128_desc(sb + b_plane_bytes, MN_GROUP_BYTES)
-                                        : ptx::make_kmajor_sw128_desc(sb + b_plane_bytes);
-          // advancing by UMMA_K = 16 along K: K-major: 32 bytes inside the 128-byte swizzle row;
-          // MN-major: 16 rows of 128 bytes (address field is in 16-byte units)
-          const uint64_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-          const uint64_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+        if (it == 0 && lane == 0) EGB_TRACE(4);
+        const uint64_t so = (uint64_t)((uint32_t)(s * stage_bytes) >> 4);
+        const uint64_t a_hi = a_desc0 + so, a_mid = a_hi + a_mid_off;
+        const uint64_t b_hi = b_desc0 + so + b_off, b_mid = b_desc0 + so + b_mid_off;
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t aa = a_step * k, ba = b_step * k;
@@ -210,146 +273,159 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue
-    // Thread t of warp q owns accumulator row (q*32 + t); it walks the tile 32 columns at a time:
-    //   v = acc [+ bias[c]] [+ C_old]          -> C   (the contraction's own output tensor)
+    // Warp q owns accumulator rows q*32 .. q*32+31 (its TMEM lane quarter). tcgen05.ld hands thread t
+    // row t with 32 consecutive columns - a layout in which every global access of a warp would touch
+    // 32 different rows (32 LSU wavefronts per instruction; measured 3 us per 32-column chunk). Each
+    // 32 x 32 block is therefore transposed through a warp-private padded staging buffer into the
+    // "coalesced layout": thread t holds rows (t>>3) + 4i, i = 0..7, columns 4*(t&7) .. +3, so one warp
+    // instruction covers 4 rows x 128 contiguous bytes. All fused stages run in that layout:
+    //   v = alpha * acc [+ bias[c]] [+ C_old]   -> C   (the contraction's own output tensor)
     //   w = second stage (activation / gradient mask / SGD update) of v   -> D
     //   [bf16 hi/mid planes of w]  [column sums of w -> colsum]
     // Every stage restates one reference kernel that would otherwise run as a separate launch
     // (bias: dnn.nim:22-24, relu/leakyRelu: dnn.nim:26-30 and their derive()d adjoints,
     // gradientDescent: base.nim:37-38); arithmetic is kept un-contracted (__fmul_rn/__fadd_rn).
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint32_t local_tile = 0;
+    const int q = warp & 3;
+    float* wstage = reinterpret_cast<float*>(smem + p.stages * stage_bytes + BAR_BYTES) + q * (32 * WSTAGE_LD);
+    const int lr = lane >> 3;         // row of this thread inside a group of 4 rows
+    const int c4 = (lane & 7) * 4;    // first of its 4 columns inside the 32-column block
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.H) & 15) == 0);
-    // one 32-column chunk of one accumulator row through the fused stages; `v` holds alpha * acc, or
-    // (split-K, last CTA of the tile) the complete sum read back from C
-    auto finish_chunk = [&](float (&v)[32], const int row, const int col0, const bool from_memory) {
+    const bool planes_vec = ((p.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 7) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.out_mid) & 7) == 0);
+    // One 32-row x 32-column block in the coalesced layout: v[i] = alpha * acc of row row0 + lr + 4i.
+    auto finish_block = [&](float4 (&v)[8], const int row0, const int nrows, const int col0) {
       const int ncols = min(32, p.N - col0);
-      const bool row_ok = row < p.M;
-      const bool full = vec_ok && ncols == 32;
-      const size_t off = (size_t)row * p.ldc + col0;
-        if (kFused && (p.flags & GEMM_BIAS)) {
+      const int cnt = max(0, min(4, ncols - c4));  // valid columns of this thread
+      const bool full = vec_ok && cnt == 4;
+      if (kFused && (p.flags & GEMM_BIAS)) {
+        float b[4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.bias + col0 + j));
+        for (int e = 0; e < 4; ++e) b[e] = (e < cnt && p.exp != 1) ? __ldg(p.bias + col0 + c4 + e) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i].x = __fadd_rn(v[i].x, b[0]); v[i].y = __fadd_rn(v[i].y, b[1]);
+          v[i].z = __fadd_rn(v[i].z, b[2]); v[i].w = __fadd_rn(v[i].w, b[3]);
+        }
       }
-      if (row_ok) {
-        if (!from_memory && (p.flags & GEMM_ACCUMULATE)) {
-          if (full) {
+      float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      // Phase 1: every global read of the block is issued before the first store. The pointers may alias
+      // as far as the compiler knows, so loads interleaved with stores would serialise into one L2 round
+      // trip per row group (measured: 8 round trips per chunk, 7 us epilogues).
+      const bool need_c = (p.flags & GEMM_ACCUMULATE) != 0;
+      const bool need_h = kFused && (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY);
+      const bool need_d = kFused && p.epi == EPI_SGD;
+      float4 oldc[8], aux[8];  // aux: H (mask source) or the parameter the SGD stage updates
+      uint32_t valid = 0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 o = *reinterpret_cast<const float4*>(p.C + off + j);
-              v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+      for (int i = 0; i < 8; ++i) {
+        const int r = lr + 4 * i;
+        const int row = row0 + r;
+        oldc[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        aux[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (r >= nrows || row >= p.M || cnt == 0) continue;
+        valid |= 1u << i;
+        const size_t off = (size_t)row * p.ldc + col0 + c4;
+        const float* auxp = need_h ? p.H : p.D;
+        if (full) {
+          if (need_c) oldc[i] = *reinterpret_cast<const float4*>(p.C + off);
+          if (need_h || need_d) aux[i] = *reinterpret_cast<const float4*>(auxp + off);
+        } else {
+          float o[4] = {0.0f, 0.0f, 0.0f, 0.0f}, a2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < cnt) {
+              if (need_c) o[e] = p.C[off + e];
+              if (need_h || need_d) a2[e] = auxp[off + e];
             }
-          } else {
+          oldc[i] = make_float4(o[0], o[1], o[2], o[3]);
+          aux[i] = make_float4(a2[0], a2[1], a2[2], a2[3]);
+        }
+      }
+      // Phase 2: arithmetic and stores
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] += p.C[off + j];
-          }
+      for (int i = 0; i < 8; ++i) {
+        if (!((valid >> i) & 1u) || p.exp == 2) continue;
+        const int row = row0 + lr + 4 * i;
+        const size_t off = (size_t)row * p.ldc + col0 + c4;
+        float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        if (need_c) {
+          x[0] += oldc[i].x; x[1] += oldc[i].y; x[2] += oldc[i].z; x[3] += oldc[i].w;
         }
         if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(p.C + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          *reinterpret_cast<float4*>(p.C + off) = make_float4(x[0], x[1], x[2], x[3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) p.C[off + j] = v[j];
+          for (int e = 0; e < 4; ++e)
+            if (e < cnt) p.C[off + e] = x[e];
         }
-        // ---- second stage
-        if (!kFused) {
-        } else if (p.epi == EPI_RELU) {
+        if (kFused) {
+          // ---- second stage
+          const float a2[4] = {aux[i].x, aux[i].y, aux[i].z, aux[i].w};
+          if (p.epi == EPI_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (0.0f <= v[j]) ? v[j] : 0.0f;
-        } else if (p.epi == EPI_LEAKY) {
+            for (int e = 0; e < 4; ++e) x[e] = (0.0f <= x[e]) ? x[e] : 0.0f;
+          } else if (p.epi == EPI_LEAKY) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __fmul_rn((0.0f <= v[j]) ? 1.0f : p.epi_param, v[j]);
-        } else if (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY) {
-          float h[32];
-          if (full) {
+            for (int e = 0; e < 4; ++e) x[e] = __fmul_rn((0.0f <= x[e]) ? 1.0f : p.epi_param, x[e]);
+          } else if (p.epi == EPI_MASK_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 o = *reinterpret_cast<const float4*>(p.H + off + j);
-              h[j] = o.x; h[j + 1] = o.y; h[j + 2] = o.z; h[j + 3] = o.w;
+            for (int e = 0; e < 4; ++e) x[e] = (0.0f <= a2[e]) ? x[e] : 0.0f;
+          } else if (p.epi == EPI_MASK_LEAKY) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __fmul_rn(x[e], (0.0f <= a2[e]) ? 1.0f : p.epi_param);
+          } else if (p.epi == EPI_SGD) {
+            // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __fadd_rn(a2[e], __fmul_rn(0.0f - x[e], p.epi_param));
+          }
+          if (p.epi != EPI_NONE) {
+            if (full) {
+              *reinterpret_cast<float4*>(p.D + off) = make_float4(x[0], x[1], x[2], x[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < cnt) p.D[off + e] = x[e];
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = (j < ncols) ? p.H[off + j] : 0.0f;
           }
-          if (p.epi == EPI_MASK_RELU) {
+          if (p.flags & GEMM_SPLIT_OUT) {
+            __nv_bfloat16* hrow = p.out_hi + (size_t)row * p.ld_out + col0 + c4;
+            __nv_bfloat16* mrow = p.out_mid + (size_t)row * p.ld_out + col0 + c4;
+            __align__(8) __nv_bfloat16 hv[4];
+            __align__(8) __nv_bfloat16 mv[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (0.0f <= h[j]) ? v[j] : 0.0f;
-          } else {
+            for (int e = 0; e < 4; ++e) split_store(&hv[e], &mv[e], x[e]);
+            if (planes_vec && cnt == 4) {
+              *reinterpret_cast<uint2*>(hrow) = *reinterpret_cast<const uint2*>(hv);
+              *reinterpret_cast<uint2*>(mrow) = *reinterpret_cast<const uint2*>(mv);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], (0.0f <= h[j]) ? 1.0f : p.epi_param);
-          }
-        } else if (p.epi == EPI_SGD) {
-          // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 o = *reinterpret_cast<const float4*>(p.D + off + j);
-              v[j] = __fadd_rn(o.x, __fmul_rn(0.0f - v[j], p.epi_param));
-              v[j + 1] = __fadd_rn(o.y, __fmul_rn(0.0f - v[j + 1], p.epi_param));
-              v[j + 2] = __fadd_rn(o.z, __fmul_rn(0.0f - v[j + 2], p.epi_param));
-              v[j + 3] = __fadd_rn(o.w, __fmul_rn(0.0f - v[j + 3], p.epi_param));
+              for (int e = 0; e < 4; ++e)
+                if (e < cnt) { hrow[e] = hv[e]; mrow[e] = mv[e]; }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] = __fadd_rn(p.D[off + j], __fmul_rn(0.0f - v[j], p.epi_param));
           }
-        }
-        if (kFused && p.epi != EPI_NONE) {
-          if (full) {
+          if (p.colsum) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.D + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) p.D[off + j] = v[j];
-          }
-        }
-        if (kFused && (p.flags & GEMM_SPLIT_OUT)) {
-          __nv_bfloat16* hrow = p.out_hi + (size_t)row * p.ld_out + col0;
-          __nv_bfloat16* mrow = p.out_mid + (size_t)row * p.ld_out + col0;
-          if (ncols == 32 && (p.ld_out & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __align__(16) __nv_bfloat16 hv[8];
-              __align__(16) __nv_bfloat16 mv[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) split_store(&hv[e], &mv[e], v[j + e]);
-              *reinterpret_cast<uint4*>(hrow + j) = *reinterpret_cast<const uint4*>(hv);
-              *reinterpret_cast<uint4*>(mrow + j) = *reinterpret_cast<const uint4*>(mv);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) split_store(hrow + j, mrow + j, v[j]);
+            for (int e = 0; e < 4; ++e)
+              if (e < cnt) cs[e] += x[e];
           }
         }
       }
       if (kFused && p.colsum) {
-        // column sums over the 32 rows this warp holds: butterfly transpose-reduce (31 shuffles);
-        // afterwards lane j holds the sum of column j. Rows outside the matrix contribute zero.
+        // the 4 lanes that share a column quad (lane ^ 8, lane ^ 16) hold the other rows
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (!row_ok || j >= ncols) v[j] = 0.0f;
-#pragma unroll
-        for (int offw = 16; offw >= 1; offw >>= 1) {
-          const bool upper = (lane & offw) != 0;
-#pragma unroll
-          for (int j = 0; j < offw; ++j) {
-            const float send = upper ? v[j] : v[j + offw];
-            const float keep = upper ? v[j + offw] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, offw);
-          }
+        for (int e = 0; e < 4; ++e) {
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
         }
-        if (lane < ncols) atomicAdd(p.colsum + col0 + lane, v[0]);
+        if (lane < 8) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < cnt) atomicAdd(p.colsum + col0 + c4 + e, cs[e]);
+        }
       }
     };
+    uint32_t local_tile = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local_tile) {
       const int tile = unit / p.splits;
       const uint32_t acc = local_tile & 1;
@@ -358,75 +434,113 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int n0 = (tile / p.tiles_m) * p.BN;
       ptx::mbar_wait(&tmem_full[acc], use & 1, 4);
       ptx::tc_fence_after();
-      const int row = m0 + q * 32 + lane;
+      if (local_tile == 0 && threadIdx.x == 128) EGB_TRACE(5);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
-      const bool split = kFused && p.splits > 1;
+      if (p.ck > 1) {
+        // cluster split-K: park the raw partial accumulator in shared memory (the operand stages are idle:
+        // tmem_full means every MMA of this CTA has retired and this CTA loads nothing else)
+        float* stage_row = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * (p.BN + STAGING_PAD);
+        for (int c = 0; c < p.BN; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c, r);
+          ptx::tmem_ld_wait();
+          if (n0 + c >= p.N) break;  // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stage_row + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+        ptx::tc_fence_before();
+        break;  // exactly one unit per CTA
+      }
       for (int c = 0; c < p.BN; c += 32) {
+        const int col0 = n0 + c;
+        if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
         ptx::tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        float v[32];
+        if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(15);
+        float* mine = wstage + lane * WSTAGE_LD;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (!split) {
-          finish_chunk(v, row, col0, false);
-        } else if (row < p.M) {
-          // partial tile: add into C (zero-filled or holding the value to accumulate onto)
-          float* crow = p.C + (size_t)row * p.ldc + col0;
-          const int ncols = min(32, p.N - col0);
-          if (vec_ok && ncols == 32) {
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(mine + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        float4 v[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: 4x fewer L2 atomic operations
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j), "f"(v[j]), "f"(v[j + 1]),
-                           "f"(v[j + 2]), "f"(v[j + 3])
-                           : "memory");
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(crow + j, v[j]);
-          }
+        for (int i = 0; i < 8; ++i) {
+          v[i] = *reinterpret_cast<const float4*>(wstage + (lr + 4 * i) * WSTAGE_LD + c4);
+          v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha;
         }
+        __syncwarp();  // the staging block is rewritten by the next chunk
+        if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(16);
+        finish_block(v, m0 + q * 32, 32, col0);
+        if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(17);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      if (split) {
-        // the CTA that increments the tile counter last owns the complete sum
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 128) {
-          const int prev = atomicAdd(p.counters + tile, 1);
-          const bool last = prev == p.splits - 1;
-          if (last) p.counters[tile] = 0;  // self-resetting for the next launch
-          tmem_slot[1] = last ? 1u : 0u;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const bool last = tmem_slot[1] != 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // flag may be rewritten by the next unit
-        if (last) {
-          __threadfence();
-          for (int c = 0; c < p.BN; c += 32) {
-            const int col0 = n0 + c;
-            if (col0 >= p.N) break;
-            float v[32];
-            const int ncols = min(32, p.N - col0);
-            const float* crow = p.C + (size_t)row * p.ldc + col0;
+    }
+    if (p.ck > 1) {
+      __syncwarp();
+      ptx::cluster_sync_all();  // every CTA of the cluster has staged its partial tile
+      const int tile = blockIdx.x / p.ck;
+      const int m0 = (tile % p.tiles_m) * BM;
+      const int n0 = (tile / p.tiles_m) * p.BN;
+      const uint32_t crank = ptx::cluster_ctarank();
+      const int rows_per = BM / p.ck;                 // rows of the tile this CTA finishes
+      const int groups = (rows_per + 31) / 32;
+      const int nchunks = p.BN / 32;
+      const uint32_t stage_base = ptx::smem_u32(smem);
+      for (int u = q; u < groups * nchunks; u += 4) {
+        const int g = u / nchunks, c = (u % nchunks) * 32;
+        const int col0 = n0 + c;
+        if (col0 >= p.N) continue;  // warp-uniform
+        const int nrows = min(32, rows_per - g * 32);
+        const int trow0 = (int)crank * rows_per + g * 32;
+        float4 v[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (row < p.M && j < ncols) ? __ldcg(crow + j) : 0.0f;
-            finish_chunk(v, row, col0, true);
+        for (int i = 0; i < 8; ++i) v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int peer = 0; peer < p.ck; ++peer) {   // ascending k ranges: fixed summation order
+          // all eight loads of a peer are in flight before the first add (a DSMEM round trip each otherwise)
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = min(lr + 4 * i, nrows - 1);  // rows past the block repeat the last one (not used)
+            const uint32_t addr = stage_base + (uint32_t)(((trow0 + r) * (p.BN + STAGING_PAD) + c + c4) * 4);
+            t[i] = ld_dsmem_f4(addr, (uint32_t)peer);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w;
           }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha;
+        }
+        finish_block(v, m0 + trow0, nrows, col0);
       }
+      __syncwarp();
+      ptx::cluster_sync_all();  // peers may still be reading this CTA's staging buffer until here
     }
   }
 
+  if (threadIdx.x == 128) EGB_TRACE(6);
+  if (p.ck > 1 && warp < 4) {
+    // non-epilogue warps take part in the two cluster barriers of the split-K reduction
+    __syncwarp();
+    ptx::cluster_sync_all();
+    ptx::cluster_sync_all();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<1>(tmem_base, TMEM_COLS);
+  }
+  if (trace_slot && threadIdx.x == 0) {
+    trace_sm[7] = (unsigned long long)clock64();
+    trace_sm[8] = globaltimer_ns();
+    for (int w = 0; w < TRACE_SLOT_WORDS; ++w) trace_slot[w] = trace_sm[w];
   }
 }
 
@@ -472,24 +586,47 @@ int choose_bn(int M, int N, int sm_count, bool b_mn) {
   return best;
 }
 
+// Tile width and cluster split-K factor for problems that cannot fill the machine with 128 x 256 tiles.
+// Cost model from the device timeline (tools/gemm_trace.py, EGB_GEMM_TRACE): a CTA spends ~1.2 us in
+// prologue + first TMA round trip, then ~(0.40 + 0.0017 bn) us per 64-deep k-block (12 SS-mode MMAs
+// whose operand reads from shared memory, not the tensor pipe, set the pace at these tile widths), then
+// ~0.6 us per 32-column chunk of fused epilogue. Spreading the k-blocks of a tile over `ck` CTAs of a
+// cluster divides the first and the last term by ck and adds one DSMEM reduction.
+void choose_small_config(int M, int N, int K, int sm_count, bool b_mn, int* bn_out, int* ck_out) {
+  const int tiles_m = (M + BM - 1) / BM;
+  const int num_kb = (K + BK - 1) / BK;
+  const int step = b_mn ? 64 : 32;
+  double best = 1e30;
+  *bn_out = choose_bn(M, N, sm_count, b_mn);
+  *ck_out = 1;
+  for (int bn = 256; bn >= step; bn -= step) {
+    if (bn > step && bn - step >= N) continue;  // a narrower tile already covers N
+    const int tiles = tiles_m * ((N + bn - 1) / bn);
+    for (int ck = 1; ck <= 8; ck *= 2) {
+      if (ck > 1 && tiles * ck > sm_count) break;   // clusters must be co-resident in one wave
+      const int kbps = (num_kb + ck - 1) / ck;
+      if (ck > 1 && (ck - 1) * kbps >= num_kb) break;  // an empty k range
+      const double waves = (double)((tiles * ck + sm_count - 1) / sm_count);
+      const double t_main = waves * kbps * (0.40 + 0.0017 * bn);
+      const double chunks = (double)((N < bn ? N : bn) + 31) / 32;
+      const double t_epi = waves * 0.6 * chunks / ck;
+      const double t_red = ck > 1 ? 0.8 + 0.004 * bn : 0.0;
+      const double cost = t_main + t_epi + t_red;
+      if (cost < best - 1e-9) {
+        best = cost;
+        *bn_out = bn;
+        *ck_out = ck;
+      }
+    }
+  }
+}
+
 }  // namespace
 
-void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* splits, int* tiles) {
+void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* tiles) {
+  (void)K;
   *bn = choose_bn(M, N, sm_count, b_mn);
   *tiles = ((M + BM - 1) / BM) * ((N + *bn - 1) / *bn);
-  const int num_kb = (K + BK - 1) / BK;
-  int s = 1;
-  // few tiles and a long reduction: one SM per tile would stream its whole K extent at the per-SM TMA
-  // rate (~100 GB/s) while the rest of the machine idles - split the reduction instead
-  // (measured on the dense step: splitting pays only when very few SMs would be busy - the zero fill,
-  // L2 reductions and re-read of C cost more than a 2x shorter k-loop saves on mid-sized grids)
-  if (*tiles * 8 <= sm_count && num_kb >= 4) {
-    s = sm_count / *tiles;
-    if (s > num_kb / 2) s = num_kb / 2;
-    if (s > 8) s = 8;
-    if (s < 1) s = 1;
-  }
-  *splits = s;
 }
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
@@ -514,14 +651,20 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   p.flags = a.flags; p.alpha = a.alpha;
   p.a_mn = a.a_mn ? 1 : 0;
   p.b_mn = a.b_mn ? 1 : 0;
-  p.counters = a.counters;
+  p.trace = ctx.trace;
+  static const int exp_mode = getenv("EGB_GEMM_EXP") ? atoi(getenv("EGB_GEMM_EXP")) : 0;
+  p.exp = exp_mode;
   p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, ctx.sm_count, a.b_mn);
+  int ck = a.cluster_k > 0 ? a.cluster_k : 1;
+  static const bool no_cluster = getenv("EGB_GEMM_NO_CLUSTER_SPLITK") != nullptr;
+  if (a.bn == 0 && a.cluster_k == 0 && !no_cluster && ((a.M + BM - 1) / BM) * ((a.N + 255) / 256) * 2 <= ctx.sm_count)
+    choose_small_config(a.M, a.N, a.K, ctx.sm_count, a.b_mn, &p.BN, &ck);
   if (p.BN % 32 != 0 || p.BN < 32 || p.BN > 256) fail(EGB_ERR_GPU, "gemm: invalid BN %d", p.BN);
   if (a.b_mn && p.BN % 64 != 0) fail(EGB_ERR_GPU, "gemm: BN must be a multiple of 64 for an MN-major B operand");
   p.tiles_m = (a.M + BM - 1) / BM;
   p.tiles_n = (a.N + p.BN - 1) / p.BN;
   const int stage_bytes = 2 * A_PLANE_BYTES + 2 * p.BN * BK * 2;
-  const int bar_bytes = (2 * MAX_STAGES + 4) * 8 + 16;
+  const int bar_bytes = BAR_BYTES + WSTAGE_BYTES;  // barriers + the epilogue warps' transposition buffers
   int stages = (SMEM_LIMIT - 1024 - bar_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) fail(EGB_ERR_GPU, "gemm: tile does not fit shared memory");
@@ -543,14 +686,42 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   static const bool force_fused = getenv("EGB_GEMM_FUSED_ALWAYS") != nullptr;
   const int tiles = p.tiles_m * p.tiles_n;
   const int num_kb = (a.K + BK - 1) / BK;
-  int splits = (a.splits > 1 && a.counters) ? a.splits : 1;
+  int splits = 1;
+  if (ck > 1) {
+    while (ck > 1 && (ck - 1) * ((num_kb + ck - 1) / ck) >= num_kb) ck /= 2;  // every CTA needs k-blocks
+    if ((size_t)BM * (p.BN + STAGING_PAD) * 4 > (size_t)stages * stage_bytes) ck = 1;
+    if (ck != 1 && ck != 2 && ck != 4 && ck != 8) fail(EGB_ERR_GPU, "gemm: invalid cluster split-K factor %d", ck);
+  }
+  if (ck > 1) splits = ck;
   if (splits > num_kb) splits = num_kb;
   p.kb_per_split = (num_kb + splits - 1) / splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  p.ck = ck > 1 ? p.splits : 1;
   const int units = tiles * p.splits;
   const bool fused = force_fused || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.epi != EPI_NONE || a.colsum || p.splits > 1;
-  const int grid = units < ctx.sm_count ? units : ctx.sm_count;
-  {
+  const int grid = (p.ck > 1 || units < ctx.sm_count) ? units : ctx.sm_count;
+  if (p.ck > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.ck;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx.pdl ? 2 : 1;
+    Launch l(ctx, KC_GEMM, st);
+    if (fused)
+      EGB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true>, tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p));
+    else
+      EGB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<false>, tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p));
+  } else {
     Launch l(ctx, KC_GEMM, st);
     if (fused)
       launch_kernel(ctx, gemm_bf16x3_kernel<true>, dim3(grid), dim3(NUM_THREADS), smem, st, tm_a_hi, tm_a_mid, tm_b_hi,

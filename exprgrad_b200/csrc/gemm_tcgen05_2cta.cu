@@ -223,7 +223,7 @@ bool gemm_2cta_eligible(const GemmArgs& a) {
   static const bool disabled = getenv("EGB_GEMM_NO_2CTA") != nullptr;
   if (disabled) return false;
   if (a.a_mn || a.b_mn) return false;
-  if (a.epi != EPI_NONE || a.colsum || a.bias || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.splits > 1) return false;
+  if (a.epi != EPI_NONE || a.colsum || a.bias || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.cluster_k > 1) return false;
   if ((a.lda & 7) || (a.ldb & 7)) return false;
   // worth it only when there are enough 256 x 256 pair tiles to fill the machine
   const long pair_tiles = (long)((a.M + 255) / 256) * ((a.N + 255) / 256);

@@ -499,15 +499,7 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.gemm.ldc = (int)g.ldc;
       n.gemm.flags = inf.overwrite ? 0 : GEMM_ACCUMULATE;
       n.gemm.alpha = 1.0f;
-      if (inf.splits > 1) {
-        n.gemm.bn = inf.bn;  // the tile count the counters were sized for
-        const size_t cbytes = align_up((size_t)inf.tiles * sizeof(int), 256);
-        if (plane_cursor + cbytes > plane_cap) fail(EGB_ERR_RUNTIME, "internal: operand plane arena exhausted");
-        n.gemm.counters = (int*)(plane_base + plane_cursor);  // zero since arena creation, self-resetting
-        plane_cursor += cbytes;
-        n.gemm.splits = inf.splits;
-        n.label += " splitK=" + std::to_string(inf.splits);
-      }
+      if (!m.splitk) n.gemm.cluster_k = 1;  // option: no cluster split-K
       if (inf.bias_tensor) {
         n.gemm.flags |= GEMM_BIAS;
         n.gemm.bias = (const float*)ptrs[inf.bias_tensor];
@@ -696,14 +688,7 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
       const size_t b_bytes = std::max((size_t)g.N * pad8(g.K), (size_t)g.K * pad8(g.N)) * 2;
       plane_bytes += 2 * align_up(a_bytes, 256) + 2 * align_up(b_bytes, 256);
       const bool b_copy = !g.trans_b && prefer_transposed_copy(g.K, g.N);
-      gemm_choose_config((int)g.M, (int)g.N, (int)g.K, !g.trans_b && !b_copy, ctx->sm_count, &inf.bn, &inf.splits,
-                         &inf.tiles);
-      if (!splitk) inf.splits = 1;
-      if (inf.splits > 1) {
-        plane_bytes += align_up((size_t)inf.tiles * sizeof(int), 256);  // tile counters
-        // partial tiles are added into C: it must start from zero unless it is accumulated onto anyway
-        if (inf.overwrite) needs_zero.insert(wt);
-      }
+      gemm_choose_config((int)g.M, (int)g.N, (int)g.K, !g.trans_b && !b_copy, ctx->sm_count, &inf.bn, &inf.tiles);
     }
     inf.final_tensor = wt;
     if (!(inf.is_gemm && inf.overwrite && fuse)) continue;
@@ -942,14 +927,15 @@ static void capture_levels(Model& m, Plan& plan) {
   }
   // Dependency-exact capture: every node waits (through events) only for the earlier nodes it really
   // conflicts with, so e.g. the weight-gradient contraction of layer l overlaps the input-gradient
-  // chain of the layers below it. Nodes are issued in level order on four streams; a node goes to a
+  // chain of the layers below it. Nodes are issued in level order on eight streams; a node goes to a
   // stream whose last node is one of its predecessors (no false ordering), else to an idle one.
-  constexpr int NS = 4;
+  constexpr int NS = 8;
   for (auto& st : c.aux_stream)
     if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  static cudaStream_t extra = nullptr;  // a fourth stream, shared by all contexts of the process
-  if (!extra) EGB_CUDA(cudaStreamCreateWithFlags(&extra, cudaStreamNonBlocking));
-  cudaStream_t streams[NS] = {c.stream, c.aux_stream[0], c.aux_stream[1], extra};
+  static cudaStream_t extra[NS - 3] = {};  // further capture streams, shared by all contexts of the process
+  for (auto& st : extra)
+    if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaStream_t streams[NS] = {c.stream, c.aux_stream[0], c.aux_stream[1], extra[0], extra[1], extra[2], extra[3], extra[4]};
   while ((int)c.fork_events.size() < n + 1) {
     cudaEvent_t e;
     EGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -967,10 +953,22 @@ static void capture_levels(Model& m, Plan& plan) {
       const Node &a2 = plan.nodes[j], &b2 = plan.nodes[i];
       if (hits(a2.writes, b2.reads) || hits(a2.writes, b2.writes) || hits(a2.reads, b2.writes)) preds[i].push_back(j);
     }
+  // transitive ancestors: a node may follow any of them on a stream without adding a dependency
+  std::vector<std::vector<char>> anc(n, std::vector<char>(n, 0));
+  for (int i = 0; i < n; ++i)
+    for (int pj : preds[i]) {
+      anc[i][pj] = 1;
+      for (int a2 = 0; a2 < pj; ++a2)
+        if (anc[pj][a2]) anc[i][a2] = 1;
+    }
   cudaEvent_t start = c.fork_events[n];
   EGB_CUDA(cudaEventRecord(start, c.stream));
-  int tail[NS] = {-1, -1, -1, -1};
-  bool forked[NS] = {true, false, false, false};
+  int tail[NS];
+  bool forked[NS];
+  for (int q = 0; q < NS; ++q) {
+    tail[q] = -1;
+    forked[q] = q == 0;
+  }
   std::vector<int> stream_of(n, 0);
   for (int i = 0; i < n; ++i) {
     Node& nd = plan.nodes[i];
@@ -985,10 +983,13 @@ static void capture_levels(Model& m, Plan& plan) {
           best = tail[q];
           s = q;
         }
-      // 2. an unused stream
+      // 2. a stream whose tail is an ancestor anyway (stream order adds no false dependency)
+      for (int q = 0; q < NS && s < 0; ++q)
+        if (tail[q] >= 0 && anc[i][tail[q]]) s = q;
+      // 3. an unused stream
       for (int q = 0; q < NS && s < 0; ++q)
         if (tail[q] < 0) s = q;
-      // 3. the stream whose tail is the oldest node
+      // 4. the stream whose tail is the oldest node (a false dependency; only when all streams are busy)
       if (s < 0) {
         s = 0;
         for (int q = 1; q < NS; ++q)

@@ -88,7 +88,7 @@ struct KernelInfo {
   float epi_param = 0.0f;
   int final_tensor = 0;       // tensor that holds the final epilogue value (C or D)
   bool emit_planes = false;   // the epilogue also writes bf16 operand planes of the final value
-  int bn = 0, splits = 1, tiles = 0;  // tile width, split-K factor and tile count of a contraction
+  int bn = 0, tiles = 0;  // tile width and tile count of a contraction
 };
 
 struct Plan {
@@ -132,11 +132,11 @@ struct Model {
   bool fuse = true;         // epilogue fusion of contraction + elementwise / column-sum / SGD kernels
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   bool rowchain = true;     // runs of small row-local kernels execute in one launch
-  // split-K for contractions with few output tiles (RED.ADD partial tiles + last-arriver epilogue).
-  // Measured on the dense step it loses both when applied to every half-empty grid (161 vs 150 us) and
-  // when restricted to grids of <= 18 tiles (115.6 vs 111.4 us): zero-filling C, the L2 reductions, the
-  // tile-counter handshake and the re-read cost more than the shorter k-loops save. Off by default.
-  bool splitk = false;
+  // cluster split-K: contractions with few output tiles spread each tile's reduction over the CTAs of a
+  // thread-block cluster (partial tiles meet through distributed shared memory, gemm_tcgen05.cu).
+  // (An earlier global-memory variant - RED.ADD partial tiles + last-arriver epilogue - lost on the dense
+  // step, 115.6 vs 111.4 us, and was removed.)
+  bool splitk = true;
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   CommHooks* comm = nullptr;

@@ -77,3 +77,48 @@ def test_full_size_checksum_properties(ctx):
         if seed == 0:
             c2 = gemm_f32(ctx, a * np.float32(2), b).astype(np.float64)  # exact scaling by 2
             assert np.array_equal(c2, 2 * c)
+
+
+def _bf16_planes(x):
+    """hi = bf16(x), mid = bf16(x - hi) with round-to-nearest-even (what split.cu computes), as uint16."""
+    def rn(v):
+        bits = v.astype(np.float32).view(np.uint32).astype(np.uint64)
+        return (((bits + 0x7FFF + ((bits >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+    hi = rn(x)
+    hi_f = (hi.astype(np.uint32) << 16).view(np.float32)
+    return hi, rn(x - hi_f)
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(1024, 512, 784, 0, 0), (1024, 512, 784, 0, 1), (512, 10, 1024, 1, 1),
+                                             (300, 200, 520, 0, 0), (784, 512, 1024, 1, 1), (128, 64, 128, 0, 0)])
+@pytest.mark.parametrize("bn,ck", [(64, 2), (128, 4), (256, 8), (64, 8)])
+def test_cluster_split_k_configurations(ctx, M, N, K, a_mn, b_mn, bn, ck):
+    """Forced tile width x cluster split-K factor (egb_gemm_planes): each CTA of a cluster reduces a k
+    range of one tile and the partial tiles meet through distributed shared memory."""
+    import ctypes
+    from exprgrad_b200._ffi import check, lib
+    rng = np.random.default_rng(M + N + K + bn + ck)
+    a = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    b = rng.uniform(-1, 1, (K, N)).astype(np.float32)
+    pad8 = lambda v: (v + 7) // 8 * 8
+    a_st = np.ascontiguousarray(a.T) if a_mn else a          # stored [K, M] (MN-major) or [M, K]
+    b_st = b if b_mn else np.ascontiguousarray(b.T)          # stored [K, N] (MN-major) or [N, K]
+    bufs = []
+    def upload(mat):
+        ld = pad8(mat.shape[1])
+        padded = np.zeros((mat.shape[0], ld), np.float32); padded[:, :mat.shape[1]] = mat
+        out = []
+        for plane in _bf16_planes(padded):
+            buf = ctx.alloc_buffer(plane.nbytes); buf.write(plane); bufs.append(buf); out.append(buf.device_ptr)
+        return out, ld
+    (a_hi, a_mid), lda = upload(a_st)
+    (b_hi, b_mid), ldb = upload(b_st)
+    c = ctx.alloc_buffer(M * N * 4); bufs.append(c)
+    c.fill(0.0)
+    flags = (16 if a_mn else 0) | (32 if b_mn else 0)
+    check(lib.egb_gemm_planes(ctx.handle, M, N, K, a_hi, a_mid, lda, b_hi, b_mid, ldb, c.device_ptr, N, flags, None,
+                              ctypes.c_float(1.0), bn | (ck << 16)))
+    got = c.read().reshape(M, N)
+    assert_close(got, a.astype(np.float64) @ b.astype(np.float64), what=f"bn{bn} ck{ck}")
+    for x in bufs:
+        x.dealloc()

@@ -32,9 +32,13 @@ def run(M, N, K, a_mn, b_mn, bn, iters=300):
     return us
 for (M, N, K, a_mn, b_mn, name) in [(1024, 512, 784, 0, 1, "fwd1 h=x.W1 (B MN-major)"), (1024, 512, 784, 0, 0, "fwd1 with K-major B"),
                                      (1024, 512, 512, 0, 0, "da1 = dh.W^T (K-major B)"), (512, 512, 1024, 1, 1, "dW2 = a^T.dh (both MN-major)"),
-                                     (784, 512, 1024, 1, 1, "dW1"), (1024, 10, 512, 0, 1, "fwd3 N=10"), (512, 10, 1024, 1, 1, "dW3 N=10")]:
+                                     (784, 512, 1024, 1, 1, "dW1"), (1024, 10, 512, 0, 1, "fwd3 N=10"), (512, 10, 1024, 1, 1, "dW3 N=10"), (1024, 512, 10, 0, 0, "da2 K=10")]:
     res = []
+    res.append(f"auto:{run(M, N, K, a_mn, b_mn, 0):.1f}")
     for bn in ([32, 64, 128, 256] if not b_mn else [64, 128, 256]):
         if bn > max(64, N) * 2: continue
-        res.append(f"bn{bn}:{run(M, N, K, a_mn, b_mn, bn):.1f}")
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+        for ck in (1, 2, 4, 8):
+            if ck > 1 and (tiles * ck > 148 or ck * 2 > (K + 63) // 64): continue
+            res.append(f"bn{bn}x{ck}:{run(M, N, K, a_mn, b_mn, bn | (ck << 16)):.1f}")
     print(f"{name:34s} M={M} N={N} K={K}  " + "  ".join(res), flush=True)
