@@ -671,8 +671,21 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
          std::to_string(p.arena_bytes) + " bytes (zeroed per run: " + std::to_string(p.zero_bytes) + "), graph " +
          (p.graph_valid ? "yes" : "no") + "\n";
     static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain", "softmax_xent"};
+    auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+      for (auto x : a)
+        for (auto y : b)
+          if (x == y) return true;
+      return false;
+    };
+    int node_index = 0;
     for (auto& n : p.nodes) {
-      s += std::string("  L") + std::to_string(n.level) + " " + kinds[n.kind] + " " + n.label;
+      s += std::string("  #") + std::to_string(node_index) + " L" + std::to_string(n.level) + " " + kinds[n.kind] + " " + n.label;
+      s += " <-";
+      for (int j = 0; j < node_index; ++j) {
+        const Node& a2 = p.nodes[j];
+        if (hits(a2.writes, n.reads) || hits(a2.writes, n.writes) || hits(a2.reads, n.writes)) s += " #" + std::to_string(j);
+      }
+      ++node_index;
       if (n.kind == Node::INTERP) {
         static const char* paths[] = {"", " 4wide-eltwise", " 4wide-stream-reduce", " 4wide-point-reduce"};
         s += " points=" + std::to_string(n.ip.npoints) + " red=" + std::to_string(n.ip.nred) + " loops=" +

@@ -71,6 +71,7 @@ struct Context {
   // clock64 stamps at its phase boundaries into this pinned, device-mapped buffer (slot 0 = cursor);
   // dumped as text when the context is destroyed. Null in normal operation.
   unsigned long long* trace = nullptr;
+  unsigned long long trace_next = 0;
 };
 constexpr int TRACE_SLOT_WORDS = 24;
 constexpr int TRACE_SLOTS = 4096;
@@ -176,6 +177,7 @@ struct GemmArgs {
   int ld_out = 0;
   int bn = 0;        // 0 = choose
   int cluster_k = 0; // cluster split-K factor: 0 = choose, 1 = off, 2/4/8 = CTAs per output tile
+  int sm_budget = 0; // SMs this launch may plan for (0 = all): contractions that run concurrently share the machine
 };
 
 // 2-CTA (cta_group::2) variant for large K-major problems with a plain epilogue (gemm_tcgen05_2cta.cu)

@@ -36,7 +36,7 @@ constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int MN_GROUP_BYTES = BK * 128;    // MN-major: one group of 64 MN-elements x BK rows
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // TMA, MMA, TMEM-allocator, idle warp + 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -65,6 +65,7 @@ struct KParams {
   int splits, kb_per_split;
   int exp;  // timing experiments (EGB_GEMM_EXP)
   unsigned long long* trace;  // debug timeline (Context::trace) or null
+  int trace_index;            // slot of this launch
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -82,8 +83,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   } while (0)
 
 constexpr int STAGING_PAD = 4;  // floats; keeps 16-byte row-strided accesses conflict-free
-constexpr int WSTAGE_LD = 32 + STAGING_PAD;               // row stride of a warp's 32 x 32 transposition buffer
-constexpr int WSTAGE_BYTES = 4 * 32 * WSTAGE_LD * 4;      // four epilogue warps
+constexpr int UNIT_COLS = 16;                             // an epilogue work unit is 32 rows x 16 columns
+constexpr int WSTAGE_LD = UNIT_COLS + STAGING_PAD;        // row stride of a warp's transposition buffer
+constexpr int EPI_WARPS = 8;
+constexpr int WSTAGE_BYTES = EPI_WARPS * 32 * WSTAGE_LD * 4;
 constexpr int BAR_BYTES = (2 * MAX_STAGES + 4) * 8 + 32 + TRACE_SLOT_WORDS * 8;  // mbarriers, TMEM slot, trace pointer + stamps
 
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta_rank) {
@@ -135,8 +138,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   if (threadIdx.x == 0) {
     unsigned long long* slot = nullptr;
     if (p.trace && blockIdx.x == 0) {
-      const unsigned long long i = atomicAdd(p.trace, 1ull) + 1;
-      if (i < TRACE_SLOTS) {
+      const unsigned long long i = (unsigned long long)p.trace_index;  // fixed per launch site: graph replays overwrite
+      if (p.trace[0] < i) p.trace[0] = i;  // (only CTA 0 of each launch writes: per-CTA atomics on the host-mapped
+                                           // buffer delay kernel completion by > 100 us - observer effect)
+      {
         slot = p.trace + i * TRACE_SLOT_WORDS;
         for (int w = 0; w < TRACE_SLOT_WORDS; ++w) trace_sm[w] = 0;
         trace_sm[0] = globaltimer_ns(); trace_sm[1] = (unsigned long long)clock64();
@@ -159,7 +164,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -173,7 +178,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   unsigned long long* const trace_slot = *trace_slot_shp;
   if (threadIdx.x == 0) EGB_TRACE(2);
 
-  pdl_launch_dependents();
   if (warp == 0) {
     // ===================================================== TMA producer
     // The whole warp walks the loop convergently and `elect.sync` guards the issue: with `if (lane == 0)`
@@ -261,6 +265,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t aa = a_step * k, ba = b_step * k;
             // small cross terms first, dominant hi*hi last
+            if (p.exp == 3) {  // timing experiment: one product instead of three
+              ptx::umma_f16<1>(d_tmem, a_hi + aa, b_hi + ba, idesc, (kb != kb0) || (k != 0));
+              continue;
+            }
             ptx::umma_f16<1>(d_tmem, a_mid + aa, b_hi + ba, idesc, (kb != kb0) || (k != 0));
             ptx::umma_f16<1>(d_tmem, a_hi + aa, b_mid + ba, idesc, 1);
             ptx::umma_f16<1>(d_tmem, a_hi + aa, b_hi + ba, idesc, 1);
@@ -272,54 +280,54 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue
-    // Warp q owns accumulator rows q*32 .. q*32+31 (its TMEM lane quarter). tcgen05.ld hands thread t
-    // row t with 32 consecutive columns - a layout in which every global access of a warp would touch
-    // 32 different rows (32 LSU wavefronts per instruction; measured 3 us per 32-column chunk). Each
-    // 32 x 32 block is therefore transposed through a warp-private padded staging buffer into the
-    // "coalesced layout": thread t holds rows (t>>3) + 4i, i = 0..7, columns 4*(t&7) .. +3, so one warp
-    // instruction covers 4 rows x 128 contiguous bytes. All fused stages run in that layout:
+    // ===================================================== epilogue (8 warps)
+    // Warps q and q + 4 of this group share TMEM lane quarter q (accumulator rows q*32 .. q*32+31) and
+    // alternate over its 16-column units. tcgen05.ld hands thread t row t with consecutive columns - a
+    // layout in which every global access of a warp touches 32 different rows (32 LSU wavefronts per
+    // instruction). Each 32 x 16 unit is therefore transposed through a warp-private padded buffer into
+    // the "coalesced layout": thread t holds rows (t>>2) + 8i, i = 0..3, columns 4*(t&3) .. +3, so one
+    // warp instruction covers 8 rows x 64 contiguous bytes (whole 32-byte sectors). All fused stages run
+    // in that layout:
     //   v = alpha * acc [+ bias[c]] [+ C_old]   -> C   (the contraction's own output tensor)
     //   w = second stage (activation / gradient mask / SGD update) of v   -> D
     //   [bf16 hi/mid planes of w]  [column sums of w -> colsum]
     // Every stage restates one reference kernel that would otherwise run as a separate launch
     // (bias: dnn.nim:22-24, relu/leakyRelu: dnn.nim:26-30 and their derive()d adjoints,
     // gradientDescent: base.nim:37-38); arithmetic is kept un-contracted (__fmul_rn/__fadd_rn).
+    // Eight warps rather than four: the epilogue is a long dependent instruction stream, and a single
+    // warp per scheduler ran it at ~5 cycles per instruction (timeline: 3 us per 32 x 32 block).
     const int q = warp & 3;
-    float* wstage = reinterpret_cast<float*>(smem + p.stages * stage_bytes + BAR_BYTES) + q * (32 * WSTAGE_LD);
-    const int lr = lane >> 3;         // row of this thread inside a group of 4 rows
-    const int c4 = (lane & 7) * 4;    // first of its 4 columns inside the 32-column block
+    const int ew = warp - 4;          // 0..7
+    const int eh = ew >> 2;           // which of the two warps of the lane quarter
+    float* wstage = reinterpret_cast<float*>(smem + p.stages * stage_bytes + BAR_BYTES) + ew * (32 * WSTAGE_LD);
+    const int lr = lane >> 2;         // row of this thread inside a group of 8 rows
+    const int c4 = (lane & 3) * 4;    // first of its 4 columns inside the 16-column unit
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.H) & 15) == 0);
     const bool planes_vec = ((p.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 7) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.out_mid) & 7) == 0);
-    // One 32-row x 32-column block in the coalesced layout: v[i] = alpha * acc of row row0 + lr + 4i.
-    auto finish_block = [&](float4 (&v)[8], const int row0, const int nrows, const int col0) {
-      const int ncols = min(32, p.N - col0);
+    const bool need_c = (p.flags & GEMM_ACCUMULATE) != 0;
+    const bool need_h = kFused && (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY);
+    const bool need_d = kFused && p.epi == EPI_SGD;
+    // One 32-row x 16-column unit in the coalesced layout: v[i] = alpha * acc of row row0 + lr + 8i.
+    auto finish_unit = [&](float4 (&v)[4], const int row0, const int nrows, const int col0) {
+      const int ncols = min(UNIT_COLS, p.N - col0);
       const int cnt = max(0, min(4, ncols - c4));  // valid columns of this thread
       const bool full = vec_ok && cnt == 4;
-      if (kFused && (p.flags & GEMM_BIAS)) {
-        float b[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) b[e] = (e < cnt && p.exp != 1) ? __ldg(p.bias + col0 + c4 + e) : 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i].x = __fadd_rn(v[i].x, b[0]); v[i].y = __fadd_rn(v[i].y, b[1]);
-          v[i].z = __fadd_rn(v[i].z, b[2]); v[i].w = __fadd_rn(v[i].w, b[3]);
-        }
-      }
-      float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      // Phase 1: every global read of the block is issued before the first store. The pointers may alias
+      // Phase 1: every global read of the unit is issued before the first store. The pointers may alias
       // as far as the compiler knows, so loads interleaved with stores would serialise into one L2 round
-      // trip per row group (measured: 8 round trips per chunk, 7 us epilogues).
-      const bool need_c = (p.flags & GEMM_ACCUMULATE) != 0;
-      const bool need_h = kFused && (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY);
-      const bool need_d = kFused && p.epi == EPI_SGD;
-      float4 oldc[8], aux[8];  // aux: H (mask source) or the parameter the SGD stage updates
+      // trip per row group.
+      float b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (kFused && (p.flags & GEMM_BIAS)) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < cnt) b[e] = __ldg(p.bias + col0 + c4 + e);
+      }
+      float4 oldc[4], aux[4];  // aux: H (mask source) or the parameter the SGD stage updates
       uint32_t valid = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = lr + 4 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int r = lr + 8 * i;
         const int row = row0 + r;
         oldc[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         aux[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -343,12 +351,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
       // Phase 2: arithmetic and stores
+      float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (!((valid >> i) & 1u) || p.exp == 2) continue;
-        const int row = row0 + lr + 4 * i;
+      for (int i = 0; i < 4; ++i) {
+        if (!((valid >> i) & 1u)) continue;
+        const int row = row0 + lr + 8 * i;
         const size_t off = (size_t)row * p.ldc + col0 + c4;
         float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        if (kFused && (p.flags & GEMM_BIAS)) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = __fadd_rn(x[e], b[e]);
+        }
         if (need_c) {
           x[0] += oldc[i].x; x[1] += oldc[i].y; x[2] += oldc[i].z; x[3] += oldc[i].w;
         }
@@ -412,13 +425,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
       if (kFused && p.colsum) {
-        // the 4 lanes that share a column quad (lane ^ 8, lane ^ 16) hold the other rows
+        // the 8 lanes that share a column quad (lane ^ 4, ^ 8, ^ 16) hold the other rows
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+          cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 4);
           cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
           cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
         }
-        if (lane < 8) {
+        if (lane < 4) {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             if (e < cnt) atomicAdd(p.colsum + col0 + c4 + e, cs[e]);
@@ -434,45 +448,50 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int n0 = (tile / p.tiles_m) * p.BN;
       ptx::mbar_wait(&tmem_full[acc], use & 1, 4);
       ptx::tc_fence_after();
+      // Programmatic dependent launch, triggered late: the dependent grid may be scheduled once every CTA
+      // has reached its LAST epilogue, so that its launch latency (~4.5 us as a full graph edge) overlaps
+      // this epilogue. Triggering at kernel start instead parks the dependents' CTAs - one whole SM each -
+      // in griddepcontrol.wait and starves the contractions of the parallel branches (measured).
+      if (unit + (int)gridDim.x >= num_units) pdl_launch_dependents();
       if (local_tile == 0 && threadIdx.x == 128) EGB_TRACE(5);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
       if (p.ck > 1) {
         // cluster split-K: park the raw partial accumulator in shared memory (the operand stages are idle:
         // tmem_full means every MMA of this CTA has retired and this CTA loads nothing else)
         float* stage_row = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * (p.BN + STAGING_PAD);
-        for (int c = 0; c < p.BN; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(t_row + c, r);
-          ptx::tmem_ld_wait();
+        for (int c = eh * UNIT_COLS; c < p.BN; c += 2 * UNIT_COLS) {
           if (n0 + c >= p.N) break;  // warp-uniform
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(t_row + c, r);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
+          for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<uint4*>(stage_row + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         }
         ptx::tc_fence_before();
         break;  // exactly one unit per CTA
       }
-      for (int c = 0; c < p.BN; c += 32) {
+      for (int c = eh * UNIT_COLS; c < p.BN; c += 2 * UNIT_COLS) {
         const int col0 = n0 + c;
         if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(t_row + c, r);
         ptx::tmem_ld_wait();
         if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(15);
         float* mine = wstage + lane * WSTAGE_LD;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
+        for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<uint4*>(mine + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         __syncwarp();
-        float4 v[8];
+        float4 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i] = *reinterpret_cast<const float4*>(wstage + (lr + 4 * i) * WSTAGE_LD + c4);
+        for (int i = 0; i < 4; ++i) {
+          v[i] = *reinterpret_cast<const float4*>(wstage + (lr + 8 * i) * WSTAGE_LD + c4);
           v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha;
         }
-        __syncwarp();  // the staging block is rewritten by the next chunk
+        __syncwarp();  // the staging block is rewritten by the next unit
         if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(16);
-        finish_block(v, m0 + q * 32, 32, col0);
+        finish_unit(v, m0 + q * 32, 32, col0);
         if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(17);
       }
       ptx::tc_fence_before();
@@ -482,45 +501,68 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     if (p.ck > 1) {
       __syncwarp();
       ptx::cluster_sync_all();  // every CTA of the cluster has staged its partial tile
+      if (threadIdx.x == 128) EGB_TRACE(15);
       const int tile = blockIdx.x / p.ck;
       const int m0 = (tile % p.tiles_m) * BM;
       const int n0 = (tile / p.tiles_m) * p.BN;
       const uint32_t crank = ptx::cluster_ctarank();
       const int rows_per = BM / p.ck;                 // rows of the tile this CTA finishes
       const int groups = (rows_per + 31) / 32;
-      const int nchunks = p.BN / 32;
+      const int nunits = p.BN / UNIT_COLS;
       const uint32_t stage_base = ptx::smem_u32(smem);
-      for (int u = q; u < groups * nchunks; u += 4) {
-        const int g = u / nchunks, c = (u % nchunks) * 32;
-        const int col0 = n0 + c;
-        if (col0 >= p.N) continue;  // warp-uniform
+      // This warp's units: all partial sums are read first; the cluster is then told that this warp is done
+      // with its peers' staging buffers (arrive) before the fused stages run, so no CTA waits for another
+      // one's epilogue - only for its reads.
+      constexpr int MAX_U = 4;  // (BN / 16 units) * (rows_per / 32 groups) / 8 warps <= 4 for ck >= 2
+      float4 v[MAX_U][4];
+      const int total_u = groups * nunits;
+#pragma unroll
+      for (int k = 0; k < MAX_U; ++k) {
+        const int u = ew + k * EPI_WARPS;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[k][i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (u >= total_u) continue;
+        const int g = u / nunits, c = (u % nunits) * UNIT_COLS;
+        if (n0 + c >= p.N) continue;  // warp-uniform
         const int nrows = min(32, rows_per - g * 32);
         const int trow0 = (int)crank * rows_per + g * 32;
-        float4 v[8];
+        for (int peer = 0; peer < p.ck; peer += 2) {   // ascending k ranges: fixed summation order
+          // the loads of two peers are in flight before the first add (a DSMEM round trip each otherwise)
+          float4 t[2][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        for (int peer = 0; peer < p.ck; ++peer) {   // ascending k ranges: fixed summation order
-          // all eight loads of a peer are in flight before the first add (a DSMEM round trip each otherwise)
-          float4 t[8];
+          for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = min(lr + 4 * i, nrows - 1);  // rows past the block repeat the last one (not used)
-            const uint32_t addr = stage_base + (uint32_t)(((trow0 + r) * (p.BN + STAGING_PAD) + c + c4) * 4);
-            t[i] = ld_dsmem_f4(addr, (uint32_t)peer);
-          }
+            for (int i = 0; i < 4; ++i) {
+              const int r = min(lr + 8 * i, nrows - 1);  // rows past the block repeat the last one (not used)
+              const uint32_t addr = stage_base + (uint32_t)(((trow0 + r) * (p.BN + STAGING_PAD) + c + c4) * 4);
+              t[pp][i] = ld_dsmem_f4(addr, (uint32_t)(peer + pp));   // ck is even
+            }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w;
-          }
+          for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              v[k][i].x += t[pp][i].x; v[k][i].y += t[pp][i].y; v[k][i].z += t[pp][i].z; v[k][i].w += t[pp][i].w;
+            }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i].x *= p.alpha; v[i].y *= p.alpha; v[i].z *= p.alpha; v[i].w *= p.alpha;
-        }
-        finish_block(v, m0 + trow0, nrows, col0);
       }
       __syncwarp();
-      ptx::cluster_sync_all();  // peers may still be reading this CTA's staging buffer until here
+      ptx::cluster_arrive();
+      if (threadIdx.x == 128) EGB_TRACE(16);
+#pragma unroll
+      for (int k = 0; k < MAX_U; ++k) {
+        const int u = ew + k * EPI_WARPS;
+        if (u >= total_u) continue;
+        const int g = u / nunits, c = (u % nunits) * UNIT_COLS;
+        const int col0 = n0 + c;
+        if (col0 >= p.N) continue;  // warp-uniform
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[k][i].x *= p.alpha; v[k][i].y *= p.alpha; v[k][i].z *= p.alpha; v[k][i].w *= p.alpha;
+        }
+        finish_unit(v[k], m0 + (int)crank * rows_per + g * 32, min(32, rows_per - g * 32), col0);
+      }
+      __syncwarp();
+      ptx::cluster_wait();  // peers may still be reading this CTA's staging buffer until here
     }
   }
 
@@ -529,7 +571,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // non-epilogue warps take part in the two cluster barriers of the split-K reduction
     __syncwarp();
     ptx::cluster_sync_all();
-    ptx::cluster_sync_all();
+    ptx::cluster_arrive();
+    ptx::cluster_wait();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -540,8 +583,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   if (trace_slot && threadIdx.x == 0) {
     trace_sm[7] = (unsigned long long)clock64();
     trace_sm[8] = globaltimer_ns();
-    for (int w = 0; w < TRACE_SLOT_WORDS; ++w) trace_slot[w] = trace_sm[w];
+    for (int w = 0; w < 18; ++w) trace_slot[w] = trace_sm[w];
   }
+
 }
 
 // K-major: the plane is [rows = MN extent, K] -> box {BK, box_rows}. MN-major: the plane is
@@ -587,12 +631,16 @@ int choose_bn(int M, int N, int sm_count, bool b_mn) {
 }
 
 // Tile width and cluster split-K factor for problems that cannot fill the machine with 128 x 256 tiles.
-// Cost model from the device timeline (tools/gemm_trace.py, EGB_GEMM_TRACE): a CTA spends ~1.2 us in
-// prologue + first TMA round trip, then ~(0.40 + 0.0017 bn) us per 64-deep k-block (12 SS-mode MMAs
-// whose operand reads from shared memory, not the tensor pipe, set the pace at these tile widths), then
-// ~0.6 us per 32-column chunk of fused epilogue. Spreading the k-blocks of a tile over `ck` CTAs of a
-// cluster divides the first and the last term by ck and adds one DSMEM reduction.
-void choose_small_config(int M, int N, int K, int sm_count, bool b_mn, int* bn_out, int* ck_out) {
+// Cost model fitted to the device timeline (tools/gemm_trace.py, EGB_GEMM_TRACE), in microseconds:
+//   * ~2.1 fixed: prologue, first TMA round trip, exit;
+//   * main loop: shared-memory bandwidth sets the pace at these tile widths - per 64-deep k-block TMA
+//     writes (128 + bn) * 256 B and the 12 SS-mode MMAs read 3 * (128 + bn) * 128 B, at 128 B/clk
+//     (measured 0.45 / 0.49 / 0.62 us at bn = 32 / 64 / 128; one product instead of three: 0.32 us);
+//   * epilogue: ~1.5 per 32 x 16 unit a warp finishes (8 warps; one L2 round trip + the fused stages);
+//   * cluster split-K: k-blocks and epilogue rows are divided by ck, plus staging + two cluster barriers
+//     (~1.7 + 0.25 ck of skew) and the DSMEM reduction, which moves only ~20 B/clk per SM - wide tiles
+//     with deep splits (bn = 256, ck = 8: 13 us epilogues) lose to narrow tiles with ck = 2.
+void choose_small_config(int M, int N, int K, int sm_count, bool b_mn, int max_ck, int* bn_out, int* ck_out) {
   const int tiles_m = (M + BM - 1) / BM;
   const int num_kb = (K + BK - 1) / BK;
   const int step = b_mn ? 64 : 32;
@@ -602,16 +650,24 @@ void choose_small_config(int M, int N, int K, int sm_count, bool b_mn, int* bn_o
   for (int bn = 256; bn >= step; bn -= step) {
     if (bn > step && bn - step >= N) continue;  // a narrower tile already covers N
     const int tiles = tiles_m * ((N + bn - 1) / bn);
-    for (int ck = 1; ck <= 8; ck *= 2) {
+    const double t_kb = (128.0 + bn) * 640.0 / 128.0 / 1900.0;   // bytes through shared memory / (128 B/clk)
+    const int units = ((N < bn ? N : bn) + UNIT_COLS - 1) / UNIT_COLS;  // 16-column units with data
+    for (int ck = 1; ck <= max_ck; ck *= 2) {
       if (ck > 1 && tiles * ck > sm_count) break;   // clusters must be co-resident in one wave
       const int kbps = (num_kb + ck - 1) / ck;
       if (ck > 1 && (ck - 1) * kbps >= num_kb) break;  // an empty k range
       const double waves = (double)((tiles * ck + sm_count - 1) / sm_count);
-      const double t_main = waves * kbps * (0.40 + 0.0017 * bn);
-      const double chunks = (double)((N < bn ? N : bn) + 31) / 32;
-      const double t_epi = waves * 0.6 * chunks / ck;
-      const double t_red = ck > 1 ? 0.8 + 0.004 * bn : 0.0;
-      const double cost = t_main + t_epi + t_red;
+      double cost = 2.1 + waves * kbps * t_kb;
+      if (ck == 1) {
+        cost += waves * 1.5 * ((units + 1) / 2);        // two warps share a lane quarter
+      } else {
+        const int groups = (BM / ck + 31) / 32;
+        const int upw = (groups * units + EPI_WARPS - 1) / EPI_WARPS;
+        if (upw > 4) continue;
+        // DSMEM moves ~20 B/clk per SM: the (ck - 1) remote partial slices of this CTA's rows
+        const double t_dsmem = 0.3 + (double)(BM / ck) * bn * 4.0 * (ck - 1) / 20.0 / 1900.0;
+        cost += 0.7 + t_dsmem + upw * 1.5 + 1.0 + 0.25 * ck;   // staging + barrier, reduction, stages, exit skew
+      }
       if (cost < best - 1e-9) {
         best = cost;
         *bn_out = bn;
@@ -652,13 +708,18 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   p.a_mn = a.a_mn ? 1 : 0;
   p.b_mn = a.b_mn ? 1 : 0;
   p.trace = ctx.trace;
+  p.trace_index = ctx.trace ? 1 + (int)(ctx.trace_next++ % (TRACE_SLOTS - 1)) : 0;
   static const int exp_mode = getenv("EGB_GEMM_EXP") ? atoi(getenv("EGB_GEMM_EXP")) : 0;
   p.exp = exp_mode;
-  p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, ctx.sm_count, a.b_mn);
+  const int sms = (a.sm_budget > 0 && a.sm_budget < ctx.sm_count) ? a.sm_budget : ctx.sm_count;
+  p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, sms, a.b_mn);
   int ck = a.cluster_k > 0 ? a.cluster_k : 1;
   static const bool no_cluster = getenv("EGB_GEMM_NO_CLUSTER_SPLITK") != nullptr;
-  if (a.bn == 0 && a.cluster_k == 0 && !no_cluster && ((a.M + BM - 1) / BM) * ((a.N + 255) / 256) * 2 <= ctx.sm_count)
-    choose_small_config(a.M, a.N, a.K, ctx.sm_count, a.b_mn, &p.BN, &ck);
+  if (a.bn == 0 && ((a.M + BM - 1) / BM) * ((a.N + 255) / 256) * 2 <= ctx.sm_count) {
+    int ck_auto = 1;
+    choose_small_config(a.M, a.N, a.K, sms, a.b_mn, a.cluster_k == 1 || no_cluster ? 1 : 8, &p.BN, &ck_auto);
+    if (a.cluster_k == 0) ck = ck_auto;
+  }
   if (p.BN % 32 != 0 || p.BN < 32 || p.BN > 256) fail(EGB_ERR_GPU, "gemm: invalid BN %d", p.BN);
   if (a.b_mn && p.BN % 64 != 0) fail(EGB_ERR_GPU, "gemm: BN must be a multiple of 64 for an MN-major B operand");
   p.tiles_m = (a.M + BM - 1) / BM;
@@ -699,7 +760,7 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   p.ck = ck > 1 ? p.splits : 1;
   const int units = tiles * p.splits;
   const bool fused = force_fused || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.epi != EPI_NONE || a.colsum || p.splits > 1;
-  const int grid = (p.ck > 1 || units < ctx.sm_count) ? units : ctx.sm_count;
+  const int grid = (p.ck > 1 || units < sms) ? units : sms;
   if (p.ck > 1) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -596,6 +596,27 @@ void build_nodes_impl(Model& m, Plan& plan) {
   if (m.rowchain && !m.strict) {
     if (fuse_row_chains(m, plan)) compute_levels(plan);
   }
+  // Contractions of one level run concurrently (parallel graph branches). Each needs a whole SM per CTA
+  // (shared memory), so grids that together exceed the machine run in two waves and the level takes twice
+  // as long (timeline: 256 CTAs at level 7 of the dense step). Give every contraction of a level an SM
+  // budget proportional to its work; its tile width / cluster split-K factor is then chosen inside it.
+  if (m.concurrent) {
+    std::map<int, double> level_work;
+    std::map<int, int> level_gemms;
+    for (auto& n : plan.nodes)
+      if (n.kind == Node::GEMM) {
+        level_work[n.level] += (double)n.gemm.M * n.gemm.N * n.gemm.K;
+        level_gemms[n.level]++;
+      }
+    for (auto& n : plan.nodes)
+      if (n.kind == Node::GEMM && level_gemms[n.level] > 1) {
+        const double share = (double)n.gemm.M * n.gemm.N * n.gemm.K / level_work[n.level];
+        int budget = (int)(m.ctx->sm_count * share) / 8 * 8;
+        if (budget < 16) budget = 16;
+        n.gemm.sm_budget = budget;
+        n.label += " sm<=" + std::to_string(budget);
+      }
+  }
   for (auto& n : plan.nodes)
     if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
   plan.epoch_built = m.epoch;
@@ -961,6 +982,47 @@ static void capture_levels(Model& m, Plan& plan) {
       for (int a2 = 0; a2 < pj; ++a2)
         if (anc[pj][a2]) anc[i][a2] = 1;
     }
+  // Critical path (longest chain by a rough cost): its nodes are issued back to back on the main stream,
+  // where consecutive kernel launches become *programmatic* graph edges (the next kernel's launch latency
+  // and prologue overlap the previous kernel; measured 4.5 us per full kernel -> kernel edge otherwise).
+  // Everything else forks onto side streams.
+  std::vector<double> cost(n), longest(n);
+  std::vector<int> via(n, -1);
+  for (int i = 0; i < n; ++i) {
+    const Node& nd = plan.nodes[i];
+    switch (nd.kind) {
+      case Node::GEMM: cost[i] = 8.0 + 3e-9 * (double)nd.gemm.M * nd.gemm.N * nd.gemm.K; break;
+      case Node::CONV: cost[i] = 50.0; break;
+      case Node::MEMSET: cost[i] = 1.0; break;
+      case Node::ALLREDUCE: cost[i] = 30.0; break;
+      default: cost[i] = 4.0;
+    }
+    longest[i] = cost[i];
+    for (int pj : preds[i])
+      if (longest[pj] + cost[i] > longest[i]) {
+        longest[i] = longest[pj] + cost[i];
+        via[i] = pj;
+      }
+  }
+  std::vector<char> critical(n, 0);
+  {
+    int end = 0;
+    for (int i = 1; i < n; ++i)
+      if (longest[i] > longest[end]) end = i;
+    for (int i = end; i >= 0; i = via[i]) critical[i] = 1;
+    // A kernel with any cross-stream (full) dependency loses its programmatic edge as well (observed:
+    // stream capture downgrades mixed dependencies), so the cheap ancestors of the critical path - operand
+    // splits, seeds - are issued on the main stream too; a few serialised 2 us kernels at the start cost
+    // less than a full-edge latency in front of every contraction of the chain.
+    for (int i = 0; i < n; ++i) {
+      if (critical[i] || cost[i] > 4.0) continue;
+      for (int j = i + 1; j < n; ++j)
+        if (critical[j] == 1 && anc[j][i]) {
+          critical[i] = 2;
+          break;
+        }
+    }
+  }
   cudaEvent_t start = c.fork_events[n];
   EGB_CUDA(cudaEventRecord(start, c.stream));
   int tail[NS];
@@ -973,26 +1035,26 @@ static void capture_levels(Model& m, Plan& plan) {
   for (int i = 0; i < n; ++i) {
     Node& nd = plan.nodes[i];
     int s = -1;
-    if (nd.kind == Node::ALLREDUCE || nd.kind == Node::MEMSET) {
-      s = 0;  // NCCL and memset stay on the main stream
+    if (nd.kind == Node::ALLREDUCE || nd.kind == Node::MEMSET || critical[i]) {
+      s = 0;  // NCCL, memset and the critical path stay on the main stream
     } else {
-      // 1. a stream whose tail is a predecessor (prefer the latest one)
+      // 1. a side stream whose tail is a predecessor (prefer the latest one)
       int best = -1;
-      for (int q = 0; q < NS; ++q)
+      for (int q = 1; q < NS; ++q)
         if (tail[q] >= 0 && std::find(preds[i].begin(), preds[i].end(), tail[q]) != preds[i].end() && tail[q] > best) {
           best = tail[q];
           s = q;
         }
-      // 2. a stream whose tail is an ancestor anyway (stream order adds no false dependency)
-      for (int q = 0; q < NS && s < 0; ++q)
+      // 2. a side stream whose tail is an ancestor anyway (stream order adds no false dependency)
+      for (int q = 1; q < NS && s < 0; ++q)
         if (tail[q] >= 0 && anc[i][tail[q]]) s = q;
-      // 3. an unused stream
-      for (int q = 0; q < NS && s < 0; ++q)
+      // 3. an unused side stream
+      for (int q = 1; q < NS && s < 0; ++q)
         if (tail[q] < 0) s = q;
-      // 4. the stream whose tail is the oldest node (a false dependency; only when all streams are busy)
+      // 4. the side stream whose tail is the oldest node (a false dependency; only when all streams are busy)
       if (s < 0) {
-        s = 0;
-        for (int q = 1; q < NS; ++q)
+        s = 1;
+        for (int q = 2; q < NS; ++q)
           if (tail[q] < tail[s]) s = q;
       }
     }
