@@ -431,19 +431,31 @@ int egb_model_call(egb_model* m, const char* target, int n_args, const char* con
 // back while the next block is still arriving - H2D, tensor cores and D2H overlap on three streams.
 namespace {
 
+struct SplitOp {   // one operand split of the plan (a SPLIT node or one job of a merged one)
+  const float* split_src = nullptr;
+  __nv_bfloat16 *split_hi = nullptr, *split_mid = nullptr;
+  int split_rows = 0, split_cols = 0, split_ld = 0, split_dst_ld = 0, split_act = 0;
+  bool split_transpose = false;
+};
+
 struct RowStream {
-  Node* split_a = nullptr;
-  Node* split_b = nullptr;
+  SplitOp sa, sb;
+  SplitOp* split_a = nullptr;
+  SplitOp* split_b = nullptr;
   Node* gemm = nullptr;
   Node* memset = nullptr;
   int a_id = 0, b_id = 0;
 };
 
 bool find_row_stream(Plan& plan, const Args& a, const int* on_device, RowStream& rs) {
-  std::vector<Node*> splits;
+  std::vector<SplitOp> splits;
   for (auto& n : plan.nodes) {
-    if (n.kind == Node::SPLIT) splits.push_back(&n);
-    else if (n.kind == Node::GEMM && !rs.gemm) rs.gemm = &n;
+    if (n.kind == Node::SPLIT && !n.split_jobs.empty()) {
+      for (auto& j : n.split_jobs) splits.push_back(SplitOp{j.src, j.hi, j.mid, j.rows, j.cols, j.ld, j.dst_ld, j.act, false});
+    } else if (n.kind == Node::SPLIT) {
+      splits.push_back(SplitOp{n.split_src, n.split_hi, n.split_mid, n.split_rows, n.split_cols, n.split_ld, n.split_dst_ld,
+                               n.split_act, n.split_transpose});
+    } else if (n.kind == Node::GEMM && !rs.gemm) rs.gemm = &n;
     else if (n.kind == Node::MEMSET && !rs.memset) rs.memset = &n;
     else return false;
   }
@@ -453,9 +465,9 @@ bool find_row_stream(Plan& plan, const Args& a, const int* on_device, RowStream&
   if (!out || g.flags != 0 || g.epi != EPI_NONE || g.bias || g.colsum || g.a_mn || g.alpha != 1.0f) return false;
   auto ot = plan.tensors.find(out);
   if (ot == plan.tensors.end() || g.C != ot->second.ptr || g.ldc != g.N) return false;
-  for (Node* s : splits) {
-    if (s->split_hi == g.a_hi) rs.split_a = s;
-    else if (s->split_hi == g.b_hi) rs.split_b = s;
+  for (auto& s : splits) {
+    if (s.split_hi == g.a_hi) { rs.sa = s; rs.split_a = &rs.sa; }
+    else if (s.split_hi == g.b_hi) { rs.sb = s; rs.split_b = &rs.sb; }
   }
   if (!rs.split_a || !rs.split_b || rs.split_a->split_transpose || rs.split_a->split_act || rs.split_a->split_rows != g.M) return false;
   // both operands must be inputs of this call; A has to come from the host
@@ -488,7 +500,7 @@ void run_row_stream(Model& model, Context& c, Plan& plan, const RowStream& rs, c
     if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   cudaStream_t h2d = c.aux_stream[0], d2h = c.aux_stream[1], comp = c.stream;
   const GemmArgs& g = rs.gemm->gemm;
-  const Node& sa = *rs.split_a;
+  const SplitOp& sa = *rs.split_a;
   // everything queued on the main stream so far (earlier calls) is ordered before the copies
   cudaEvent_t e_start = events.get(0);
   EGB_CUDA(cudaEventRecord(e_start, comp));
@@ -510,7 +522,7 @@ void run_row_stream(Model& model, Context& c, Plan& plan, const RowStream& rs, c
   EGB_CUDA(cudaStreamWaitEvent(comp, e_b, 0));
   if (rs.memset) EGB_CUDA(cudaMemsetAsync(rs.memset->ptr, 0, rs.memset->bytes, comp));
   {
-    const Node& sb = *rs.split_b;
+    const SplitOp& sb = *rs.split_b;
     launch_split_bf16(c, sb.split_src, sb.split_rows, sb.split_cols, sb.split_ld, sb.split_transpose, sb.split_hi,
                       sb.split_mid, sb.split_dst_ld, sb.split_act, comp);
   }

@@ -134,6 +134,20 @@ struct Launch {
 void launch_split_bf16(Context& ctx, const float* src, int rows, int cols, int ld, bool transpose,
                        __nv_bfloat16* hi, __nv_bfloat16* mid, int dst_ld, int act, cudaStream_t st);
 
+// Several non-transposing splits in one launch (split.cu)
+struct SplitJob {
+  const float* src;
+  __nv_bfloat16 *hi, *mid;
+  int rows, cols, ld, dst_ld, act;
+};
+struct SplitBatch {
+  static constexpr int MAX_JOBS = 8;
+  SplitJob jobs[MAX_JOBS];
+  long first_chunk[MAX_JOBS + 1];
+  int n;
+};
+void launch_split_batch(Context& ctx, const SplitJob* jobs, int n, cudaStream_t st);
+
 void launch_fill_u32(Context& ctx, uint32_t* dst, uint32_t value, size_t n, cudaStream_t st);
 
 enum GemmFlags {
@@ -189,8 +203,10 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
 
 // Fused softmax + crossEntropy forward/adjoint row kernel (fused_rows.cu)
 bool softmax_xent_supported(int64_t cols);
+// colsum (zeroed by the caller, may be null): += column sums of DH; out_hi/out_mid (may be null): bf16 planes of DH
 void launch_softmax_xent_rows(Context& ctx, const float* H, const float* Y, const float* DL, float* S, float* P, float* DP,
-                              float* DH, float* DS, int rows, int cols, cudaStream_t st);
+                              float* DH, float* DS, int rows, int cols, float* colsum, __nv_bfloat16* out_hi,
+                              __nv_bfloat16* out_mid, int ld_out, cudaStream_t st);
 
 // Direct fp32 conv2 kernels (conv2.cu): NHWC images, filters [F, KH, KW, C], valid, stride 1.
 void launch_conv2_fwd(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,

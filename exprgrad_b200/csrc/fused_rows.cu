@@ -20,9 +20,15 @@ __global__ void __launch_bounds__(256) softmax_xent_rows_kernel(const float* __r
                                                                 const float* __restrict__ DL, float* __restrict__ S,
                                                                 float* __restrict__ P, float* __restrict__ DP,
                                                                 float* __restrict__ DH, float* __restrict__ DS, int rows,
-                                                                int cols) {
+                                                                int cols, float* __restrict__ colsum,
+                                                                __nv_bfloat16* __restrict__ out_hi,
+                                                                __nv_bfloat16* __restrict__ out_mid, int ld_out) {
+  __shared__ float colpart[8][32 * MAX_PER_LANE];
   pdl_launch_dependents();
   pdl_wait();
+  float colacc[MAX_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) colacc[i] = 0.0f;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -63,7 +69,30 @@ __global__ void __launch_bounds__(256) softmax_xent_rows_kernel(const float* __r
 #pragma unroll
     for (int i = 0; i < MAX_PER_LANE; ++i) {
       const int x = lane + 32 * i;
-      if (x < cols) DH[(size_t)r * cols + x] = __fadd_rn(t[i], __fmul_rn(dsum, e[i]));
+      if (x < cols) {
+        const float dh = __fadd_rn(t[i], __fmul_rn(dsum, e[i]));
+        DH[(size_t)r * cols + x] = dh;
+        colacc[i] += dh;
+        if (out_hi) {  // bf16 operand planes of dh for the adjoint contractions (split.cu's arithmetic)
+          const __nv_bfloat16 hi = __float2bfloat16_rn(dh);
+          out_hi[(size_t)r * ld_out + x] = hi;
+          out_mid[(size_t)r * ld_out + x] = __float2bfloat16_rn(dh - __bfloat162float(hi));
+        }
+      }
+    }
+  }
+  if (colsum) {
+    // bias gradient db[x] += sum_y dh[y,x] (the reference's column-sum kernel behind the head, dnn.nim:22-24
+    // adjoint): per-warp partial sums meet in shared memory, one atomic per column and block
+    const int w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i) colpart[w][lane + 32 * i] = colacc[i];
+    __syncthreads();
+    for (int x = threadIdx.x; x < cols; x += blockDim.x) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) sum += colpart[ww][x];
+      atomicAdd(colsum + x, sum);
     }
   }
 }
@@ -73,14 +102,15 @@ __global__ void __launch_bounds__(256) softmax_xent_rows_kernel(const float* __r
 bool softmax_xent_supported(int64_t cols) { return cols >= 1 && cols <= 32 * MAX_PER_LANE; }
 
 void launch_softmax_xent_rows(Context& ctx, const float* H, const float* Y, const float* DL, float* S, float* P, float* DP,
-                              float* DH, float* DS, int rows, int cols, cudaStream_t st) {
+                              float* DH, float* DS, int rows, int cols, float* colsum, __nv_bfloat16* out_hi,
+                              __nv_bfloat16* out_mid, int ld_out, cudaStream_t st) {
   if (rows <= 0) return;
   const int blocks = (rows + 7) / 8;
   const int cap = ctx.sm_count * 8;
   {
     Launch l(ctx, KC_REDUCE, st);
     launch_kernel(ctx, softmax_xent_rows_kernel, dim3(blocks < cap ? blocks : cap), dim3(256), 0, st, H, Y, DL, S, P, DP, DH, DS,
-                  rows, cols);
+                  rows, cols, colsum, out_hi, out_mid, ld_out);
   }
   EGB_CUDA(cudaGetLastError());
 }

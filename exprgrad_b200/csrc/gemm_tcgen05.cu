@@ -638,7 +638,7 @@ int choose_bn(int M, int N, int sm_count, bool b_mn) {
 //     (measured 0.45 / 0.49 / 0.62 us at bn = 32 / 64 / 128; one product instead of three: 0.32 us);
 //   * epilogue: ~1.5 per 32 x 16 unit a warp finishes (8 warps; one L2 round trip + the fused stages);
 //   * cluster split-K: k-blocks and epilogue rows are divided by ck, plus staging + two cluster barriers
-//     (~1.7 + 0.25 ck of skew) and the DSMEM reduction, which moves only ~20 B/clk per SM - wide tiles
+//     (~0.7 + up to 2 us of skew on a full machine) and the DSMEM reduction, which moves only ~20 B/clk per SM - wide tiles
 //     with deep splits (bn = 256, ck = 8: 13 us epilogues) lose to narrow tiles with ck = 2.
 void choose_small_config(int M, int N, int K, int sm_count, bool b_mn, int max_ck, int* bn_out, int* ck_out) {
   const int tiles_m = (M + BM - 1) / BM;
@@ -666,7 +666,8 @@ void choose_small_config(int M, int N, int K, int sm_count, bool b_mn, int max_c
         if (upw > 4) continue;
         // DSMEM moves ~20 B/clk per SM: the (ck - 1) remote partial slices of this CTA's rows
         const double t_dsmem = 0.3 + (double)(BM / ck) * bn * 4.0 * (ck - 1) / 20.0 / 1900.0;
-        cost += 0.7 + t_dsmem + upw * 1.5 + 1.0 + 0.25 * ck;   // staging + barrier, reduction, stages, exit skew
+        // staging + barrier, reduction, fused stages, exit skew (grows with the share of the machine in use)
+        cost += 0.7 + t_dsmem + upw * 1.5 + 2.0 * (double)(tiles * ck) / sm_count;
       }
       if (cost < best - 1e-9) {
         best = cost;

@@ -312,7 +312,56 @@ bool fuse_row_chains(Model& m, Plan& plan) {
           fx.sx_s = ptr(S); fx.sx_p = ptr(P); fx.sx_dp = ptr(DP); fx.sx_dh = ptr(DH); fx.sx_ds = ptr(DS);
           fx.sx_rows = (int)hs[0];
           fx.sx_cols = (int)hs[1];
-          insert.emplace_back(*std::min_element(members.begin(), members.end()), fx);
+          // The two nodes that follow the head in a dense net consume DH only: the bias-gradient column sum
+          // (db[x] = sum_y dh[y,x]) and the bf16 operand split for the adjoint contractions. Both run inside
+          // the row kernel (one level less on the critical path); the column sums meet through atomics, so
+          // their tensor is zeroed by a memset node first.
+          const int first_member = *std::min_element(members.begin(), members.end());
+          for (int j = 0; j < (int)plan.nodes.size(); ++j) {
+            if (remove.count(j) || std::find(members.begin(), members.end(), j) != members.end()) continue;
+            Node& nj = plan.nodes[j];
+            if (j < first_member) continue;
+            // nothing between the head and this node may touch what it writes
+            bool clean = true;
+            for (int k2 = first_member; k2 < j && clean; ++k2) {
+              if (remove.count(k2) || std::find(members.begin(), members.end(), k2) != members.end()) continue;
+              for (auto w : nj.writes)
+                for (auto r : plan.nodes[k2].reads) clean = clean && r != w;
+              for (auto w : nj.writes)
+                for (auto w2 : plan.nodes[k2].writes) clean = clean && w2 != w;
+            }
+            if (!clean) continue;
+            auto drop = [&](int idx) {   // a fused node must not join a later row chain
+              auto& lv = by_level[plan.nodes[idx].level];
+              lv.erase(std::remove(lv.begin(), lv.end(), idx), lv.end());
+              remove.insert(idx);
+            };
+            if (nj.kind == Node::SPLIT && nj.split_src == fx.sx_dh && !nj.split_transpose && nj.split_act == 0 && !fx.sx_out_hi &&
+                nj.split_rows == fx.sx_rows && nj.split_cols == fx.sx_cols && nj.split_ld == fx.sx_cols) {
+              fx.sx_out_hi = nj.split_hi;
+              fx.sx_out_mid = nj.split_mid;
+              fx.sx_ld_out = nj.split_dst_ld;
+              for (auto w : nj.writes) fx.writes.push_back(w);
+              fx.label += " + operand planes";
+              drop(j);
+            } else if (nj.kind == Node::INTERP && nj.kernel_index >= 0 && !fx.sx_colsum && !nj.ip.accumulate &&
+                       describe_kernel(*target.kernels[nj.kernel_index]) == "loops=.! W[I1] R0[I0,I1] : R0" &&
+                       target.kernels[nj.kernel_index]->reads[0].tensor == DH && tensor_len((int)nj.writes[0]) == hs[1]) {
+              fx.sx_colsum = (float*)nj.ip.write.base;
+              Node z;
+              z.kind = Node::MEMSET;
+              z.label = "zero column sums of tensor" + std::to_string((int)nj.writes[0] - 1);
+              z.ptr = fx.sx_colsum;
+              z.bytes = (size_t)hs[1] * 4;
+              z.writes.push_back(nj.writes[0]);
+              insert.emplace_back(first_member, z);
+              for (auto w : nj.writes) fx.writes.push_back(w);
+              fx.reads.push_back(nj.writes[0]);
+              fx.label += " + column sums (kernel " + std::to_string(nj.kernel_index) + ")";
+              drop(j);
+            }
+          }
+          insert.emplace_back(first_member, fx);
           l = end;
           continue;
         }
@@ -593,6 +642,36 @@ void build_nodes_impl(Model& m, Plan& plan) {
   // level order is a topological order: sorting by it makes every run of consecutive levels contiguous
   // (needed by the row-chain fusion) and keeps sequential (eager) execution valid
   std::stable_sort(plan.nodes.begin(), plan.nodes.end(), [](const Node& a, const Node& b) { return a.level < b.level; });
+  // The operand splits that depend on nothing inside the plan (input batch, parameters) run as ONE launch:
+  // they sit in front of the first contraction on the critical path.
+  if (m.fuse) {
+    std::vector<int> roots;
+    for (int i = 0; i < (int)plan.nodes.size(); ++i) {
+      const Node& n = plan.nodes[i];
+      if (n.kind == Node::SPLIT && n.level == 0 && !n.split_transpose && (int)roots.size() < SplitBatch::MAX_JOBS) roots.push_back(i);
+    }
+    if (roots.size() >= 2) {
+      Node& first = plan.nodes[roots[0]];
+      std::string merged_label = "split";
+      for (int i : roots) {
+        const Node& n = plan.nodes[i];
+        first.split_jobs.push_back(SplitJob{n.split_src, n.split_hi, n.split_mid, n.split_rows, n.split_cols, n.split_ld,
+                                            n.split_dst_ld, n.split_act});
+        const size_t tpos = n.label.find("tensor");
+        merged_label += " " + (tpos == std::string::npos ? n.label : n.label.substr(tpos));
+        if (i != roots[0]) {
+          for (auto r : n.reads) first.reads.push_back(r);
+          for (auto w : n.writes) first.writes.push_back(w);
+        }
+      }
+      first.label = merged_label + " (one launch)";
+      std::vector<Node> kept;
+      for (int i = 0; i < (int)plan.nodes.size(); ++i)
+        if (i == roots[0] || std::find(roots.begin(), roots.end(), i) == roots.end()) kept.push_back(plan.nodes[i]);
+      plan.nodes = kept;
+      compute_levels(plan);
+    }
+  }
   if (m.rowchain && !m.strict) {
     if (fuse_row_chains(m, plan)) compute_levels(plan);
   }
@@ -903,13 +982,18 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       launch_fill_uniform(ctx, (float*)n.ptr, n.bytes / 4, n.lo, n.hi, m.seed, m.rng_counter, st);
       break;
     case Node::SPLIT:
+      if (!n.split_jobs.empty()) {
+        launch_split_batch(ctx, n.split_jobs.data(), (int)n.split_jobs.size(), st);
+        break;
+      }
       launch_split_bf16(ctx, n.split_src, n.split_rows, n.split_cols, n.split_ld, n.split_transpose, n.split_hi,
                         n.split_mid, n.split_dst_ld, n.split_act, st);
       break;
     case Node::GEMM: launch_gemm_bf16x3(ctx, n.gemm, st); break;
     case Node::INTERP: launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, st, n.rsplit); break;
     case Node::SOFTMAX_XENT:
-      launch_softmax_xent_rows(ctx, n.sx_h, n.sx_y, n.sx_dl, n.sx_s, n.sx_p, n.sx_dp, n.sx_dh, n.sx_ds, n.sx_rows, n.sx_cols, st);
+      launch_softmax_xent_rows(ctx, n.sx_h, n.sx_y, n.sx_dl, n.sx_s, n.sx_p, n.sx_dp, n.sx_dh, n.sx_ds, n.sx_rows, n.sx_cols,
+                               n.sx_colsum, n.sx_out_hi, n.sx_out_mid, n.sx_ld_out, st);
       break;
     case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_slots, n.chain_rows, st); break;
     case Node::CONV: {

@@ -46,6 +46,7 @@ struct Node {
   int split_rows = 0, split_cols = 0, split_ld = 0, split_dst_ld = 0, split_act = 0;
   bool split_transpose = false;
   __nv_bfloat16 *split_hi = nullptr, *split_mid = nullptr;
+  std::vector<SplitJob> split_jobs;  // non-empty: several row splits merged into this node (one launch)
   // ROWCHAIN: several row-local INTERP programs executed by one launch
   IpProgram* chain_progs = nullptr;  // device array (owned by the plan)
   int chain_n = 0, chain_slots = 0;
@@ -54,6 +55,9 @@ struct Node {
   const float *sx_h = nullptr, *sx_y = nullptr, *sx_dl = nullptr;
   float *sx_s = nullptr, *sx_p = nullptr, *sx_dp = nullptr, *sx_dh = nullptr, *sx_ds = nullptr;
   int sx_rows = 0, sx_cols = 0;
+  float* sx_colsum = nullptr;                                   // fused bias-gradient column sum of DH (zeroed first)
+  __nv_bfloat16 *sx_out_hi = nullptr, *sx_out_mid = nullptr;    // fused operand planes of DH
+  int sx_ld_out = 0;
   // CONV
   ConvPattern conv;
   const float *conv_a = nullptr, *conv_b = nullptr;

@@ -48,6 +48,42 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int rows, int c
   }
 }
 
+// Several row splits in one launch (the operand planes every step needs before its first contraction:
+// the input batch and the parameters). Work items are 8-column chunks, numbered job after job.
+__global__ void split_rows_batch_kernel(const SplitBatch b) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long total = b.first_chunk[b.n];
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int j = 0;
+#pragma unroll
+    for (int q = 1; q < SplitBatch::MAX_JOBS; ++q)
+      if (q < b.n && i >= b.first_chunk[q]) j = q;
+    const SplitJob& job = b.jobs[j];
+    const long li = i - b.first_chunk[j];
+    const int chunks = (job.cols + 7) >> 3;
+    const int r = (int)(li / chunks);
+    const int c0 = (int)(li % chunks) << 3;
+    const bool vec = ((job.ld & 3) == 0) && ((job.dst_ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(job.src) & 15) == 0);
+    const float* s = job.src + (size_t)r * job.ld + c0;
+    __nv_bfloat16* h = job.hi + (size_t)r * job.dst_ld + c0;
+    __nv_bfloat16* m = job.mid + (size_t)r * job.dst_ld + c0;
+    if (vec && c0 + 8 <= job.cols) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(s));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(s) + 1);
+      const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      __align__(16) __nv_bfloat16 hv[8];
+      __align__(16) __nv_bfloat16 mv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) split2(apply_act(xs[q], job.act), hv[q], mv[q]);
+      *reinterpret_cast<uint4*>(h) = *reinterpret_cast<const uint4*>(hv);
+      *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(mv);
+    } else {
+      for (int q = 0; q < 8 && c0 + q < job.cols; ++q) split2(apply_act(s[q], job.act), h[q], m[q]);
+    }
+  }
+}
+
 // Transposing variant: src [rows, cols] -> planes [cols, rows]. 64x64 tiles through shared memory:
 // 128-bit loads along the source rows, then every thread converts 8 consecutive source rows of one
 // source column and writes them as one 16-byte store per plane (the output row is contiguous in r).
@@ -114,6 +150,28 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, 
 }
 
 }  // namespace
+
+void launch_split_batch(Context& ctx, const SplitJob* jobs, int n, cudaStream_t st) {
+  if (n <= 0) return;
+  if (n > SplitBatch::MAX_JOBS) fail(EGB_ERR_GPU, "split batch of %d jobs exceeds %d", n, SplitBatch::MAX_JOBS);
+  SplitBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = n;
+  long total = 0;
+  for (int j = 0; j < n; ++j) {
+    b.jobs[j] = jobs[j];
+    b.first_chunk[j] = total;
+    total += (long)jobs[j].rows * ((jobs[j].cols + 7) >> 3);
+  }
+  b.first_chunk[n] = total;
+  if (total == 0) return;
+  long blocks = (total + 255) / 256;
+  const long cap = (long)ctx.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  Launch l(ctx, KC_SPLIT, st);
+  launch_kernel(ctx, split_rows_batch_kernel, dim3((int)blocks), dim3(256), 0, st, b);
+  EGB_CUDA(cudaGetLastError());
+}
 
 void launch_split_bf16(Context& ctx, const float* src, int rows, int cols, int ld, bool transpose,
                        __nv_bfloat16* hi, __nv_bfloat16* mid, int dst_ld, int act, cudaStream_t st) {

@@ -66,7 +66,7 @@ def test_dense_net_plan_uses_tensor_cores_and_graph(ctx):
     assert plan.count(" gemm gemm tensor") == 8, plan  # 3 forward + 2 dX + 3 dW contractions
     assert "graph yes" in plan
     assert plan.count("fused") >= 6, plan     # bias/relu, relu-adjoint/colsum and SGD stages run in GEMM epilogues
-    assert ctx.launch_count - n0 >= 2 * 15
+    assert ctx.launch_count - n0 >= 2 * 12     # 8 contractions, merged root splits, fused head, bias updates
     pm.free()
 
 
