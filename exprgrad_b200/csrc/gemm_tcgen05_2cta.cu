@@ -91,7 +91,8 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs)
-    if (lane == 0) {
+    // convergent warp, elect.sync-guarded issue (no R2UR waterfall around UTMALDG, see gemm_tcgen05.cu)
+    {
       pdl_wait();
       uint32_t it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -102,12 +103,15 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           const uint32_t ph = (it / STAGES2) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
           uint8_t* st = smem + s * STAGE_BYTES;
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], 2u * STAGE_BYTES);
           const int k0 = kb * BK;
-          ptx::tma_load_2d_cta2(st, &tm_a_hi, &full_bar[s], k0, m0);
-          ptx::tma_load_2d_cta2(st + PLANE_BYTES, &tm_a_mid, &full_bar[s], k0, m0);
-          ptx::tma_load_2d_cta2(st + 2 * PLANE_BYTES, &tm_b_hi, &full_bar[s], k0, n0);
-          ptx::tma_load_2d_cta2(st + 3 * PLANE_BYTES, &tm_b_mid, &full_bar[s], k0, n0);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], 2u * STAGE_BYTES);
+            ptx::tma_load_2d_cta2(st, &tm_a_hi, &full_bar[s], k0, m0);
+            ptx::tma_load_2d_cta2(st + PLANE_BYTES, &tm_a_mid, &full_bar[s], k0, m0);
+            ptx::tma_load_2d_cta2(st + 2 * PLANE_BYTES, &tm_b_hi, &full_bar[s], k0, n0);
+            ptx::tma_load_2d_cta2(st + 3 * PLANE_BYTES, &tm_b_mid, &full_bar[s], k0, n0);
+          }
+          __syncwarp();
         }
       }
     }
@@ -128,7 +132,7 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           const uint32_t ph = (it / STAGES2) & 1;
           ptx::mbar_wait(&full_bar[s], ph, 3);   // the planes of both CTAs have landed
           ptx::tc_fence_after();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             const uint32_t st = ptx::smem_u32(smem + s * STAGE_BYTES);
             const uint64_t a_hi = ptx::make_kmajor_sw128_desc(st);
             const uint64_t a_mid = ptx::make_kmajor_sw128_desc(st + PLANE_BYTES);
