@@ -424,6 +424,10 @@ void launch_conv2_fwd(Context& ctx, const float* img, const float* w, float* out
                       int KH, int KW, bool accumulate, cudaStream_t st) {
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
+  if (conv2_fwd_tc_supported(out, C, F, KH, KW)) {
+    launch_conv2_fwd_tc(ctx, img, w, out, N, H, W, C, F, KH, KW, accumulate, st);
+    return;
+  }
   const int cc = C < MAX_CC ? C : MAX_CC;
   const int tq = groups_per_block(d.OW, PXT, 32);
   const size_t smem = ((size_t)KH * (tq * PXT + KW - 1) * MAX_CC + (size_t)KH * KW * cc * FC) * sizeof(float);

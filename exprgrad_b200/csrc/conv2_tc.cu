@@ -1,0 +1,266 @@
+// conv2 forward on the 5th-gen tensor cores (sm_100a) as an implicit GEMM:
+//
+//   out[n,y,x,f] (+)= sum_{dy,dx,c} img[n,y+dy,x+dx,c] * w[f,dy,dx,c]          (exprgrad/layers/dnn.nim:45-49)
+//
+// seen as  OUT[p, f] = sum_k A[p, k] * W[f, k]  with p = (n,y,x) linearised, k = (dy,dx,c): M = 128 output
+// pixels per tile, N = F filters, K = KH*KW*C <= 32 taps. The CUDA-core kernel (conv2.cu) is issue-bound
+// at 0.32 of the HBM roofline (ncu: FMA pipe 43 %, issue 68 %); here the multiply-adds run as six
+// tcgen05.mma per tile and the SM's instruction budget goes to building operand tiles and streaming the
+// 3.2 GB output.
+//
+// fp32 accuracy on bf16 tensor cores (same bf16x3 scheme as gemm_tcgen05.cu): every operand is split
+// into hi = bf16(x), mid = bf16(x - hi). One 128-byte shared-memory row per pixel holds
+// [hi(32 taps) | mid(32 taps)] in the K-major SWIZZLE_128B layout (written by the producer threads, not
+// by TMA: the im2col row of a pixel is KH runs of KW*C contiguous floats), so that
+//     A' x B1,  B1 = [w_hi | w_hi]  (K = 64)   gives  hi*hi + mid*hi
+//     A' x B2,  B2 = [w_mid]        (K = 32)   gives  hi*mid
+// accumulate into one fp32 TMEM tile.
+//
+// Roles (320 threads, two CTAs per SM, persistent over pixel tiles):
+//   warps 0-3  producers: one pixel each - KH*KW*C loads, split, 8 swizzled 16-byte stores
+//   warp  4    MMA issuer (elect.sync-guarded, convergent warp)
+//   warp  5    TMEM allocator
+//   warps 6-9  epilogue: tcgen05.ld -> padded staging -> 512-byte coalesced stores (a warp's 32 pixels x F
+//              floats are one contiguous 8 KB run of the NHWC output)
+#include <stdlib.h>
+
+#include "egb_internal.hpp"
+#include "ptx.cuh"
+
+namespace egb {
+namespace {
+
+constexpr int TILE_P = 128;            // pixels per tile = MMA M
+constexpr int KPAD = 32;               // taps padded to 32 (two k-steps of 16)
+constexpr int A_BYTES = TILE_P * 128;  // one operand tile: 128 rows of [hi(32) | mid(32)] bf16
+constexpr int STAGES = 3;
+constexpr int THREADS = 320;
+constexpr int OUT_PAD = 4;
+
+struct TcParams {
+  const float* img;
+  const float* w;
+  float* out;
+  int N, H, W, C, F, OH, OW;
+  long total;   // output pixels
+  int ntiles;
+  int accumulate;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// byte offset of 16-byte chunk `c` of row `r` in a K-major SWIZZLE_128B tile (rows of 128 bytes)
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+template <int KH, int KWC>
+__global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int F = p.F;
+  const int b_bytes = F * 128;
+  uint8_t* sB1 = smem;
+  uint8_t* sB2 = smem + b_bytes;
+  uint8_t* sA = smem + 2 * b_bytes;                              // STAGES operand tiles (b_bytes is a multiple of 1024)
+  float* sOut = reinterpret_cast<float*>(sA + STAGES * A_BYTES);  // 4 warps x 32 x (F + OUT_PAD)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sOut + 4 * 32 * (F + OUT_PAD));
+  uint64_t* a_empty = a_full + STAGES;
+  uint64_t* tmem_full = a_empty + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const uint32_t tmem_cols = F <= 16 ? 32 : (F <= 32 ? 64 : (F <= 64 ? 128 : (F <= 128 ? 256 : 512)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&a_full[s], TILE_P);  // every producer thread arrives
+      ptx::mbar_init(&a_empty[s], 1);      // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 5) ptx::tmem_alloc<1>(tmem_slot, tmem_cols);
+  pdl_wait();
+  pdl_launch_dependents();
+  // filter tiles, built once per CTA: B1 row f = [w_hi | w_hi], B2 row f = [w_mid | 0]
+  constexpr int K = KH * KWC;
+  for (int i = threadIdx.x; i < F * 8; i += THREADS) {
+    const int f = i >> 3, c = i & 7;        // 16-byte chunk c of row f holds taps 8*(c&3) .. +7
+    uint32_t h[4], m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k0 = 8 * (c & 3) + 2 * e;
+      const float x0 = k0 < K ? __ldg(p.w + (size_t)f * K + k0) : 0.0f;
+      const float x1 = k0 + 1 < K ? __ldg(p.w + (size_t)f * K + k0 + 1) : 0.0f;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      h[e] = pack_bf16(h0, h1);
+      m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(sB1 + sw128(f, c)) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(sB2 + sw128(f, c)) = c < 4 ? make_uint4(m[0], m[1], m[2], m[3]) : make_uint4(0, 0, 0, 0);
+  }
+  ptx::fence_proxy_async();   // generic-proxy writes above are read by the tensor core (async proxy)
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================================================== producers: one im2col row per thread
+    const int row = threadIdx.x;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      float v[KPAD];
+#pragma unroll
+      for (int k = 0; k < KPAD; ++k) v[k] = 0.0f;
+      const long pix = (long)tile * TILE_P + row;
+      if (pix < p.total) {
+        const int x = (int)(pix % p.OW);
+        const long t = pix / p.OW;
+        const int y = (int)(t % p.OH);
+        const int n = (int)(t / p.OH);
+        const float* base = p.img + (((size_t)n * p.H + y) * p.W + x) * p.C;
+#pragma unroll
+        for (int dy = 0; dy < KH; ++dy)
+#pragma unroll
+          for (int j = 0; j < KWC; ++j) v[dy * KWC + j] = __ldg(base + (size_t)dy * p.W * p.C + j);
+      }
+      uint32_t h[16], m[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+        h[e] = pack_bf16(h0, h1);
+        m[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)),
+                         __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+      }
+      ptx::mbar_wait(&a_empty[s], ph ^ 1, 11);   // the MMAs that read this stage have retired
+      uint8_t* a = sA + s * A_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(a + sw128(row, c)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+        *reinterpret_cast<uint4*>(a + sw128(row, c + 4)) = make_uint4(m[4 * c], m[4 * c + 1], m[4 * c + 2], m[4 * c + 3]);
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 4) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(TILE_P, F);
+    const uint64_t a_desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA));
+    const uint64_t b1_desc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB1));
+    const uint64_t b2_desc = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sB2));
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      const uint32_t acc = it & 1;
+      ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 12);
+      ptx::mbar_wait(&a_full[s], ph, 13);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)F;
+        const uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)(s * A_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // [hi | mid] x [w_hi | w_hi]; 16 taps = 32 bytes per step
+          ptx::umma_f16<1>(d_tmem, a_desc + 2 * k, b1_desc + 2 * k, idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)   // hi x w_mid
+          ptx::umma_f16<1>(d_tmem, a_desc + 2 * k, b2_desc + 2 * k, idesc, 1);
+        ptx::umma_commit(&a_empty[s]);
+        ptx::umma_commit(&tmem_full[acc]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 6) {
+    // ===================================================== epilogue
+    const int q = warp & 3;   // TMEM lane quarter of this warp: pixels q*32 .. q*32+31 of the tile
+    float* stage = sOut + q * 32 * (F + OUT_PAD);
+    const int f4 = F >> 2;    // float4 per pixel
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1, 14);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)F;
+      for (int c = 0; c < F; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_wait();
+        float* mine = stage + lane * (F + OUT_PAD) + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(mine + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);   // the accumulator is free while the tile streams out
+      const long pix0 = (long)tile * TILE_P + q * 32;
+      const long left = p.total - pix0;
+      const int nrows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+      float* dst = p.out + (size_t)pix0 * F;   // nrows * F contiguous floats
+      for (int i = lane; i < nrows * f4; i += 32) {
+        const int rr = i / f4, cc = (i - rr * f4) << 2;
+        float4 x = *reinterpret_cast<const float4*>(stage + rr * (F + OUT_PAD) + cc);
+        if (p.accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(dst + (size_t)i * 4);
+          x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+        }
+        *reinterpret_cast<float4*>(dst + (size_t)i * 4) = x;
+      }
+      __syncwarp();   // the staging rows are rewritten by the next tile
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, tmem_cols);
+  }
+}
+
+size_t tc_smem_bytes(int F) {
+  return 1024 + 2 * (size_t)F * 128 + (size_t)STAGES * A_BYTES + (size_t)4 * 32 * (F + OUT_PAD) * 4 + (2 * STAGES + 4) * 8 + 16;
+}
+
+}  // namespace
+
+bool conv2_fwd_tc_supported(const float* out, int C, int F, int KH, int KW) {
+  static const bool disabled = getenv("EGB_CONV_NO_TC") != nullptr;
+  if (disabled) return false;
+  // taps fit one 32-wide row, F is a legal MMA N with whole 32-column TMEM chunks and 1024-byte filter tiles
+  return KH == 3 && KW == 3 && (C == 3 || C == 1) && (F == 32 || F == 64 || F == 128) &&
+         (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+
+void launch_conv2_fwd_tc(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
+                         int KH, int KW, bool accumulate, cudaStream_t st) {
+  TcParams p;
+  p.img = img; p.w = w; p.out = out;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.F = F;
+  p.OH = H - KH + 1; p.OW = W - KW + 1;
+  p.total = (long)N * p.OH * p.OW;
+  if (p.total <= 0) return;
+  p.ntiles = (int)((p.total + TILE_P - 1) / TILE_P);
+  p.accumulate = accumulate ? 1 : 0;
+  const size_t smem = tc_smem_bytes(F);
+  int grid = ctx.sm_count * 2;
+  if (grid > p.ntiles) grid = p.ntiles;
+  Launch l(ctx, KC_CONV, st);
+  if (C == 3) {
+    EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_tc_kernel<3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(ctx, conv2_fwd_tc_kernel<3, 9>, dim3(grid), dim3(THREADS), smem, st, p);
+  } else {
+    EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_tc_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_kernel(ctx, conv2_fwd_tc_kernel<3, 3>, dim3(grid), dim3(THREADS), smem, st, p);
+  }
+  EGB_CUDA(cudaGetLastError());
+}
+
+}  // namespace egb

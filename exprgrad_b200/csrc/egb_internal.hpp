@@ -216,6 +216,10 @@ void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* d
 void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* dimg, int N, int H, int W, int C, int F,
                        int KH, int KW, bool accumulate, cudaStream_t st);
 bool conv2_dimg_supported(int KW);
+// Tensor-core implicit-GEMM forward (conv2_tc.cu) for 3x3 filters on 1- or 3-channel images, F in {32, 64, 128}
+bool conv2_fwd_tc_supported(const float* out, int C, int F, int KH, int KW);
+void launch_conv2_fwd_tc(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
+                         int KH, int KW, bool accumulate, cudaStream_t st);
 
 // Large operands whose stored orientation is MN-major are better served by one transposing split
 // pass plus the K-major tensor-core path (measured on 4096^3: 0.330 ms vs 0.353 ms per GEMM).
