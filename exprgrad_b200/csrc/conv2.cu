@@ -461,6 +461,10 @@ void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* d
                        int KH, int KW, bool accumulate, cudaStream_t st) {
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
+  if (conv2_dimg_tc_supported(dout, C, F, KH, KW)) {
+    launch_conv2_dimg_tc(ctx, dout, w, dimg, N, H, W, C, F, KH, KW, accumulate, st);
+    return;
+  }
   const int tq = quads_per_block(W, 16);
   const size_t smem = ((size_t)(KH + 1) * (tq * 4 + KW - 1) * FC + (size_t)KH * KW * FC * MAX_CC) * sizeof(float);
   dim3 grid((W + tq * 4 - 1) / (tq * 4), (H + ROWS_DIMG - 1) / ROWS_DIMG, N);

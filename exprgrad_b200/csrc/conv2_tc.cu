@@ -225,6 +225,218 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// d_images: dimg[n,y+dy,x+dx,c] += sum_f dout[n,y,x,f] * w[f,dy,dx,c]   (derive()d adjoint of conv2,
+// exprgrad/passes.nim:519-549; the reference scatters, only n and c are independent loops).
+// Per tile of 128 output pixels of one output row:  T[p, k] = sum_f dout[p, f] * w[f, k]  (M = 128,
+// N = 32 taps, K = F = 64) on the tensor cores, then col2im: every input-row segment the tile touches
+// (3 rows x 130 pixels x 3 channels) is gathered from T in shared memory (3 adds per element, no atomics
+// inside the tile) and added to dimg with one coalesced RED per element - tiles overlap by dy and by
+// the 2-pixel halo, so the image must be zeroed (or hold the value to accumulate onto) beforehand.
+constexpr int DI_THREADS = 448;   // 8 producer warps, MMA, TMEM allocator, 4 epilogue warps
+constexpr int DI_STAGES = 4;
+constexpr int DI_TLD = 33;        // row stride of the T tile in shared memory (floats)
+
+struct DimgParams {
+  const float* dout;
+  const float* w;
+  float* dimg;
+  int N, H, W, OH, OW;
+  int tiles_per_row, ntiles;
+  int vec4;   // image rows are 16-byte multiples and the image is 16-byte aligned: vector REDs
+};
+
+// fp32 -> (hi, mid) bf16 of 32 consecutive floats of one row, written as chunks c0..c0+3 of the row
+__device__ __forceinline__ void split_store_32(const float4 (&x)[8], uint8_t* a_hi, uint8_t* a_mid, int row, int c0) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float v[8] = {x[2 * i].x, x[2 * i].y, x[2 * i].z, x[2 * i].w, x[2 * i + 1].x, x[2 * i + 1].y, x[2 * i + 1].z, x[2 * i + 1].w};
+    uint32_t h[4], m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+      h[e] = pack_bf16(h0, h1);
+      m[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(a_hi + sw128(row, c0 + i)) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_mid + sw128(row, c0 + i)) = make_uint4(m[0], m[1], m[2], m[3]);
+  }
+}
+
+__global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const DimgParams p) {
+  constexpr int KH = 3, KW = 3, C = 3, F = 64, K = KH * KW * C, NT = 32;
+  constexpr int SEG = (TILE_P + KW - 1) * C;   // floats of one input-row segment a tile touches (390)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* sWhi = smem;                       // [32 taps][64 f] bf16, K-major (K = f)
+  uint8_t* sWmid = smem + NT * 128;
+  uint8_t* sA = smem + 2 * NT * 128;          // DI_STAGES x (A_hi, A_mid), 16 KB each
+  float* sT = reinterpret_cast<float*>(sA + DI_STAGES * 2 * A_BYTES);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sT + TILE_P * DI_TLD + 1);
+  a_full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(a_full) + 7) & ~uintptr_t(7));
+  uint64_t* a_empty = a_full + DI_STAGES;
+  uint64_t* tmem_full = a_empty + DI_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DI_STAGES; ++s) {
+      ptx::mbar_init(&a_full[s], 256);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 9) ptx::tmem_alloc<1>(tmem_slot, 64);
+  pdl_wait();
+  pdl_launch_dependents();
+  // filter tiles: row k (tap), 64 f along K; rows >= 27 are zero
+  for (int i = threadIdx.x; i < NT * 8; i += DI_THREADS) {
+    const int k = i >> 3, c = i & 7;
+    uint32_t h[4], m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f0 = 8 * c + 2 * e;
+      const float x0 = k < K ? __ldg(p.w + (size_t)f0 * K + k) : 0.0f;
+      const float x1 = k < K ? __ldg(p.w + (size_t)(f0 + 1) * K + k) : 0.0f;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      h[e] = pack_bf16(h0, h1);
+      m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(sWhi + sw128(k, c)) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(sWmid + sw128(k, c)) = make_uint4(m[0], m[1], m[2], m[3]);
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================================================== producers: half a dout row (32 filters) per thread
+    const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % DI_STAGES;
+      const uint32_t ph = (it / DI_STAGES) & 1;
+      const int x0 = (tile % p.tiles_per_row) * TILE_P;
+      const long ny = tile / p.tiles_per_row;   // n * OH + y
+      float4 x[8];
+      if (x0 + row < p.OW) {
+        const float4* src = reinterpret_cast<const float4*>(p.dout + ((size_t)ny * p.OW + x0 + row) * F + half * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ldg(src + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+      ptx::mbar_wait(&a_empty[s], ph ^ 1, 21);
+      uint8_t* a_hi = sA + s * 2 * A_BYTES;
+      split_store_32(x, a_hi, a_hi + A_BYTES, row, half * 4);
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(TILE_P, NT);
+    const uint64_t a_desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sA));
+    const uint64_t wh = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWhi));
+    const uint64_t wm = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWmid));
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % DI_STAGES;
+      const uint32_t ph = (it / DI_STAGES) & 1;
+      const uint32_t acc = it & 1;
+      ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 22);
+      ptx::mbar_wait(&a_full[s], ph, 23);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * NT;
+        const uint64_t ah = a_desc0 + (uint64_t)((uint32_t)(s * 2 * A_BYTES) >> 4);
+        const uint64_t am = ah + (uint64_t)(A_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < F / 16; ++k) {
+          ptx::umma_f16<1>(d_tmem, am + 2 * k, wh + 2 * k, idesc, k != 0);
+          ptx::umma_f16<1>(d_tmem, ah + 2 * k, wm + 2 * k, idesc, 1);
+          ptx::umma_f16<1>(d_tmem, ah + 2 * k, wh + 2 * k, idesc, 1);
+        }
+        ptx::umma_commit(&a_empty[s]);
+        ptx::umma_commit(&tmem_full[acc]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 10) {
+    // ===================================================== epilogue: T -> shared memory -> col2im gather -> RED
+    const int q = warp & 3;
+    const int et = q * 32 + lane;   // 0..127: accumulator row handled by this thread / gather thread id
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      const int x0 = (tile % p.tiles_per_row) * TILE_P;
+      const long ny = tile / p.tiles_per_row;
+      const int y = (int)(ny % p.OH);
+      const long n = ny / p.OH;
+      ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1, 24);
+      ptx::tc_fence_after();
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT, r);
+      ptx::tmem_ld_wait();
+      const bool live = x0 + et < p.OW;   // rows past the end of the output row carry zeros anyway
+#pragma unroll
+      for (int j = 0; j < K; ++j) sT[et * DI_TLD + j] = live ? __uint_as_float(r[j]) : 0.0f;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps: T is complete
+      auto gather = [&](int dy, int j) {   // element j of the input-row segment y + dy
+        const int X = j / C, c = j - X * C;
+        float sum = 0.0f;
+#pragma unroll
+        for (int dx = 0; dx < KW; ++dx) {
+          const int xx = X - dx;
+          if (xx >= 0 && xx < TILE_P) sum += sT[xx * DI_TLD + (dy * KW + dx) * C + c];
+        }
+        return sum;
+      };
+      const int seg_len = min(SEG, (p.W - x0) * C);   // the segment ends with the image row
+      if (p.vec4) {
+        // rows and segments start 16-byte aligned: one 16-byte RED per four elements
+        constexpr int Q = (SEG + 3) / 4;
+        for (int idx = et; idx < KH * Q; idx += 128) {
+          const int dy = idx / Q, j = (idx - dy * Q) * 4;
+          if (j >= seg_len) continue;
+          float* dst = p.dimg + (((size_t)n * p.H + y + dy) * p.W + x0) * C + j;
+          if (j + 4 <= seg_len) {
+            const float s0 = gather(dy, j), s1 = gather(dy, j + 1), s2 = gather(dy, j + 2), s3 = gather(dy, j + 3);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(s0), "f"(s1), "f"(s2), "f"(s3) : "memory");
+          } else {
+            for (int e = 0; j + e < seg_len; ++e) atomicAdd(dst + e, gather(dy, j + e));
+          }
+        }
+      } else {
+        for (int idx = et; idx < KH * SEG; idx += 128) {
+          const int dy = idx / SEG, j = idx - dy * SEG;
+          if (j >= seg_len) continue;
+          atomicAdd(p.dimg + (((size_t)n * p.H + y + dy) * p.W + x0) * C + j, gather(dy, j));
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // T is rewritten by the next tile
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, 64);
+  }
+}
+
 size_t tc_smem_bytes(int F) {
   return 1024 + 2 * (size_t)F * 128 + (size_t)STAGES * A_BYTES + (size_t)4 * 32 * (F + OUT_PAD) * 4 + (2 * STAGES + 4) * 8 + 16;
 }
@@ -237,6 +449,37 @@ bool conv2_fwd_tc_supported(const float* out, int C, int F, int KH, int KW) {
   // taps fit one 32-wide row, F is a legal MMA N with whole 32-column TMEM chunks and 1024-byte filter tiles
   return KH == 3 && KW == 3 && (C == 3 || C == 1) && (F == 32 || F == 64 || F == 128) &&
          (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+
+bool conv2_dimg_tc_supported(const float* dout, int C, int F, int KH, int KW) {
+  static const bool disabled = getenv("EGB_CONV_NO_TC") != nullptr;
+  return !disabled && KH == 3 && KW == 3 && C == 3 && F == 64 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
+}
+
+void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float* dimg, int N, int H, int W, int C, int F,
+                          int KH, int KW, bool accumulate, cudaStream_t st) {
+  (void)C; (void)F;
+  DimgParams p;
+  p.dout = dout; p.w = w; p.dimg = dimg;
+  p.N = N; p.H = H; p.W = W;
+  p.OH = H - KH + 1; p.OW = W - KW + 1;
+  if (N <= 0 || p.OH <= 0 || p.OW <= 0) return;
+  p.tiles_per_row = (p.OW + TILE_P - 1) / TILE_P;
+  const long tiles = (long)N * p.OH * p.tiles_per_row;
+  if (tiles > 0x7fffffffL) fail(EGB_ERR_GPU, "conv2 d_images: too many tiles");
+  p.ntiles = (int)tiles;
+  p.vec4 = ((W * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(dimg) & 15) == 0) ? 1 : 0;
+  // the tiles overlap (rows by dy, columns by the halo) and meet through RED: start from zero unless the
+  // caller accumulates onto existing data
+  if (!accumulate) EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
+  const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)(TILE_P * DI_TLD + 4) * 4 +
+                      (2 * DI_STAGES + 4) * 8 + 32;
+  int grid = ctx.sm_count;
+  if (grid > p.ntiles) grid = p.ntiles;
+  EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  Launch l(ctx, KC_CONV, st);
+  launch_kernel(ctx, conv2_dimg_tc_kernel, dim3(grid), dim3(DI_THREADS), smem, st, p);
+  EGB_CUDA(cudaGetLastError());
 }
 
 void launch_conv2_fwd_tc(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,

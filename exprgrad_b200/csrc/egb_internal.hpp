@@ -218,6 +218,9 @@ void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* d
 bool conv2_dimg_supported(int KW);
 // Tensor-core implicit-GEMM forward (conv2_tc.cu) for 3x3 filters on 1- or 3-channel images, F in {32, 64, 128}
 bool conv2_fwd_tc_supported(const float* out, int C, int F, int KH, int KW);
+bool conv2_dimg_tc_supported(const float* dout, int C, int F, int KH, int KW);
+void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float* dimg, int N, int H, int W, int C, int F,
+                          int KH, int KW, bool accumulate, cudaStream_t st);
 void launch_conv2_fwd_tc(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
                          int KH, int KW, bool accumulate, cudaStream_t st);
 
