@@ -446,6 +446,10 @@ void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* d
                      int KH, int KW, cudaStream_t st) {
   ConvDims d = {N, H, W, C, F, KH, KW, H - KH + 1, W - KW + 1};
   check_dims(d);
+  if (conv2_dw_tc_supported(dout, C, F, KH, KW)) {
+    launch_conv2_dw_tc(ctx, img, dout, dw, N, H, W, C, F, KH, KW, st);
+    return;
+  }
   const int K = KH * KW * C;
   const int txw = quads_per_block(d.OW, TX_BWD / 4) * 4;   // even chunks of the output row, <= 64 pixels
   const size_t stage = 2 * (((size_t)TX_BWD * FC + (size_t)KH * (txw + KW - 1) * C + 3) & ~size_t(3)) * sizeof(float);

@@ -113,15 +113,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
   if (warp < 4) {
     // ===================================================== producers: one im2col row per thread
     const int row = threadIdx.x;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      float v[KPAD];
-#pragma unroll
-      for (int k = 0; k < KPAD; ++k) v[k] = 0.0f;
+    // Software pipeline: the taps of the NEXT tile are in flight while this one is converted and stored
+    // (ncu on the first version: 4.8 long-scoreboard stalls per issue - one exposed HBM/L2 round trip per
+    // tile and thread, since the shared-memory stages are filled by the same threads one after another).
+    auto load_taps = [&](int tile, float (&v)[K]) {
       const long pix = (long)tile * TILE_P + row;
-      if (pix < p.total) {
+      if (tile < p.ntiles && pix < p.total) {
         const int x = (int)(pix % p.OW);
         const long t = pix / p.OW;
         const int y = (int)(t % p.OH);
@@ -131,21 +128,36 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
         for (int dy = 0; dy < KH; ++dy)
 #pragma unroll
           for (int j = 0; j < KWC; ++j) v[dy * KWC + j] = __ldg(base + (size_t)dy * p.W * p.C + j);
-      }
-      uint32_t h[16], m[16];
+      } else {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
-        h[e] = pack_bf16(h0, h1);
-        m[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)),
-                         __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+        for (int k = 0; k < K; ++k) v[k] = 0.0f;
       }
+    };
+    float v[K], nv[K];
+    load_taps(blockIdx.x, nv);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+#pragma unroll
+      for (int k = 0; k < K; ++k) v[k] = nv[k];
+      load_taps(tile + gridDim.x, nv);
       ptx::mbar_wait(&a_empty[s], ph ^ 1, 11);   // the MMAs that read this stage have retired
       uint8_t* a = sA + s * A_BYTES;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        *reinterpret_cast<uint4*>(a + sw128(row, c)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
-        *reinterpret_cast<uint4*>(a + sw128(row, c + 4)) = make_uint4(m[4 * c], m[4 * c + 1], m[4 * c + 2], m[4 * c + 3]);
+      for (int c = 0; c < 4; ++c) {   // chunk c: taps 8c .. 8c+7 (hi) and the same taps' mid in chunk c + 4
+        uint32_t h[4], m[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k0 = 8 * c + 2 * e;
+          const float x0 = k0 < K ? v[k0 < K ? k0 : 0] : 0.0f;
+          const float x1 = k0 + 1 < K ? v[k0 + 1 < K ? k0 + 1 : 0] : 0.0f;
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+          h[e] = pack_bf16(h0, h1);
+          m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+        }
+        *reinterpret_cast<uint4*>(a + sw128(row, c)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(a + sw128(row, c + 4)) = make_uint4(m[0], m[1], m[2], m[3]);
       }
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&a_full[s]);
@@ -437,6 +449,181 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// d_filters: dw[f,dy,dx,c] += sum_{n,y,x} dout[n,y,x,f] * img[n,y+dy,x+dx,c]   (derive()d adjoint of conv2;
+// a reduction over all 12.6 M output pixels). As one MMA shape per 16 pixels:
+//     D[128 x 64] += [dout_hi ; dout_mid]^T (M = 2 x 64 filters, MN-major)  x  [a_hi | a_mid] (N = 2 x 32 taps, MN-major)
+// i.e. both operands are used exactly as the other two kernels build them (one 128-byte row per pixel),
+// only described to the tensor core as MN-major with the pixel as K. Rows 0-63 of D hold hi*hi | hi*mid,
+// rows 64-127 mid*hi | (mid*mid, unused): dw[f,k] = D[f,k] + D[f,32+k] + D[64+f,k].
+// The tensor core's fp32 accumulation truncates, so D is drained into registers every DW_FLUSH tiles
+// (512 pixels) and summed there with rounded adds; the CTAs meet in dw through atomics at the very end.
+constexpr int DW_THREADS = 448;   // 8 producer warps, MMA, TMEM allocator, 4 epilogue warps
+constexpr int DW_STAGES = 3;
+constexpr int DW_FLUSH = 4;
+
+struct DwParams {
+  const float* img;
+  const float* dout;
+  float* dw;
+  int N, H, W, OH, OW;
+  long total;
+  int ntiles;
+};
+
+__global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwParams p) {
+  constexpr int KH = 3, KWC = 9, C = 3, F = 64, K = KH * KWC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* sS = smem;   // DW_STAGES x (dout_hi, dout_mid, im2col), 16 KB each
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sS + DW_STAGES * 3 * A_BYTES);
+  uint64_t* a_empty = a_full + DW_STAGES;
+  uint64_t* tmem_full = a_empty + DW_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DW_STAGES; ++s) {
+      ptx::mbar_init(&a_full[s], 256);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 9) ptx::tmem_alloc<1>(tmem_slot, 128);
+  pdl_wait();
+  pdl_launch_dependents();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) ++my_tiles;
+  const int my_groups = (my_tiles + DW_FLUSH - 1) / DW_FLUSH;
+
+  if (warp < 8) {
+    // ===================================================== producers: half a dout row + half an im2col row
+    const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % DW_STAGES;
+      const uint32_t ph = (it / DW_STAGES) & 1;
+      const long pix = (long)tile * TILE_P + row;
+      float4 x[8];
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = 0.0f;
+      if (pix < p.total) {
+        const float4* src = reinterpret_cast<const float4*>(p.dout + (size_t)pix * F + half * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ldg(src + i);
+        const int xo = (int)(pix % p.OW);
+        const long t = pix / p.OW;
+        const int y = (int)(t % p.OH);
+        const long n = t / p.OH;
+        const float* base = p.img + (((size_t)n * p.H + y) * p.W + xo) * C;
+        if (half == 0) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = __ldg(base + (size_t)(k / KWC) * p.W * C + (k % KWC));
+        } else {
+#pragma unroll
+          for (int k = 16; k < K; ++k) v[k - 16] = __ldg(base + (size_t)(k / KWC) * p.W * C + (k % KWC));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+      ptx::mbar_wait(&a_empty[s], ph ^ 1, 31);
+      uint8_t* d_hi = sS + s * 3 * A_BYTES;
+      split_store_32(x, d_hi, d_hi + A_BYTES, row, half * 4);
+      uint8_t* a = d_hi + 2 * A_BYTES;   // im2col row: chunks 0-3 hi, 4-7 mid; this thread owns taps 16*half .. +15
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t h[4], m[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = v[8 * c + 2 * e], x1 = v[8 * c + 2 * e + 1];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+          h[e] = pack_bf16(h0, h1);
+          m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+        }
+        *reinterpret_cast<uint4*>(a + sw128(row, half * 2 + c)) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(a + sw128(row, 4 + half * 2 + c)) = make_uint4(m[0], m[1], m[2], m[3]);
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, true, true);
+    // A: two groups of 64 M-elements (dout_hi tile, dout_mid tile), A_BYTES apart; B: one group of 64 N-elements
+    const uint64_t a_desc0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(sS), A_BYTES);
+    const uint64_t b_desc0 = ptx::make_mnmajor_sw128_desc(ptx::smem_u32(sS + 2 * A_BYTES), A_BYTES);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % DW_STAGES;
+      const uint32_t ph = (it / DW_STAGES) & 1;
+      const uint32_t group = it / DW_FLUSH, in_group = it % DW_FLUSH;
+      const uint32_t acc = group & 1;
+      if (in_group == 0) ptx::mbar_wait(&tmem_empty[acc], ((group >> 1) & 1) ^ 1, 32);
+      ptx::mbar_wait(&a_full[s], ph, 33);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        const uint64_t so = (uint64_t)((uint32_t)(s * 3 * A_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < TILE_P / 16; ++k)   // 16 pixels = 16 rows of 128 bytes per step
+          ptx::umma_f16<1>(d_tmem, a_desc0 + so + 128 * k, b_desc0 + so + 128 * k, idesc, (in_group | k) != 0);
+        ptx::umma_commit(&a_empty[s]);
+        if (in_group == DW_FLUSH - 1 || (int)it == my_tiles - 1) ptx::umma_commit(&tmem_full[acc]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 10) {
+    // ===================================================== epilogue: drain D every DW_FLUSH tiles, sum in registers
+    const int q = warp & 3;
+    const int drow = q * 32 + lane;   // row of D: filter drow (hi) or drow - 64 (mid)
+    float sum[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) sum[j] = 0.0f;
+    for (int g = 0; g < my_groups; ++g) {
+      const uint32_t acc = g & 1;
+      ptx::mbar_wait(&tmem_full[acc], (g >> 1) & 1, 34);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[c + j] += __uint_as_float(r[j]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+    const int f = drow & 63;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float val = drow < 64 ? sum[k] + sum[32 + k] : sum[k];
+      atomicAdd(p.dw + (size_t)f * K + k, val);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, 128);
+  }
+}
+
 size_t tc_smem_bytes(int F) {
   return 1024 + 2 * (size_t)F * 128 + (size_t)STAGES * A_BYTES + (size_t)4 * 32 * (F + OUT_PAD) * 4 + (2 * STAGES + 4) * 8 + 16;
 }
@@ -479,6 +666,31 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   Launch l(ctx, KC_CONV, st);
   launch_kernel(ctx, conv2_dimg_tc_kernel, dim3(grid), dim3(DI_THREADS), smem, st, p);
+  EGB_CUDA(cudaGetLastError());
+}
+
+bool conv2_dw_tc_supported(const float* dout, int C, int F, int KH, int KW) {
+  static const bool disabled = getenv("EGB_CONV_NO_TC") != nullptr;
+  return !disabled && KH == 3 && KW == 3 && C == 3 && F == 64 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
+}
+
+// dw must be zero (or hold the value to accumulate onto): the CTAs add their partial sums atomically
+void launch_conv2_dw_tc(Context& ctx, const float* img, const float* dout, float* dw, int N, int H, int W, int C, int F,
+                        int KH, int KW, cudaStream_t st) {
+  (void)C; (void)F;
+  DwParams p;
+  p.img = img; p.dout = dout; p.dw = dw;
+  p.N = N; p.H = H; p.W = W;
+  p.OH = H - KH + 1; p.OW = W - KW + 1;
+  p.total = (long)N * p.OH * p.OW;
+  if (p.total <= 0) return;
+  p.ntiles = (int)((p.total + TILE_P - 1) / TILE_P);
+  const size_t smem = 1024 + (size_t)DW_STAGES * 3 * A_BYTES + (2 * DW_STAGES + 4) * 8 + 32;
+  int grid = ctx.sm_count;
+  if (grid > p.ntiles) grid = p.ntiles;
+  EGB_CUDA(cudaFuncSetAttribute(conv2_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  Launch l(ctx, KC_CONV, st);
+  launch_kernel(ctx, conv2_dw_tc_kernel, dim3(grid), dim3(DW_THREADS), smem, st, p);
   EGB_CUDA(cudaGetLastError());
 }
 

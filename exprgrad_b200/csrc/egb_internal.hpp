@@ -221,6 +221,9 @@ bool conv2_fwd_tc_supported(const float* out, int C, int F, int KH, int KW);
 bool conv2_dimg_tc_supported(const float* dout, int C, int F, int KH, int KW);
 void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float* dimg, int N, int H, int W, int C, int F,
                           int KH, int KW, bool accumulate, cudaStream_t st);
+bool conv2_dw_tc_supported(const float* dout, int C, int F, int KH, int KW);
+void launch_conv2_dw_tc(Context& ctx, const float* img, const float* dout, float* dw, int N, int H, int W, int C, int F,
+                        int KH, int KW, cudaStream_t st);
 void launch_conv2_fwd_tc(Context& ctx, const float* img, const float* w, float* out, int N, int H, int W, int C, int F,
                          int KH, int KW, bool accumulate, cudaStream_t st);
 
