@@ -234,7 +234,7 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_2cta_kernel (cta_group::2 tcgen05, 256x256 pair tiles)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "frac_of_burst_peak": achieved / peaks["bf16_burst"], "frac_of_sustained_peak": achieved / peaks["bf16_sustained"],
-                     "traffic": 390.0e6, "traffic_source": "profiles/r01i_ncu_full.txt (dram read+write per launch: 335 + 55 MB)",
+                     "traffic": 390.0e6, "traffic_source": "profiles/r01l_ncu_full.txt (dram read+write per launch: 336 + 54 MB)",
                      "passes": passes, "algorithmic_tflops": flop / t_kernel / 1e12, "kernel_ms": t_kernel * 1e3,
                      "kernel_share_of_step": k_ms / max(all_ms, 1e-9),
                      "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a %.0f ms back-to-back region)" % ms
@@ -344,7 +344,7 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None):
                    "l2": "working set (~40 MB) is L2-resident by design; every step rewrites all activations and parameters",
                    "numerics": "contractions bf16x3 on tcgen05; everything else fp32"},
         "gpu_launches": int(launches), "plan_nodes": plan.count("\n  "), "cuda_graph": "graph yes" in plan,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel (8 contractions per step)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel (8 contractions per step; cluster split-K, fused epilogues)",
                      "achieved": 3 * flop / max(g["ms_per_step"], 1e-9) / 1e9, "peak": peaks["bf16_sustained"],
                      "unit": "TFLOP/s", "frac": 3 * flop / max(g["ms_per_step"], 1e-9) / 1e9 / peaks["bf16_sustained"],
                      "traffic": None, "passes": 3,
@@ -412,7 +412,7 @@ def run_conv2(args, ctx, timer, rank, world):
            "n_gpus": world, "ms_per_step": total, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
            "data": "synthetic", "config": {"workload": CONV_NAME, "parallelism": f"replicas x{world}"},
            "kernels_ms": kern,
-           "roofline": {"bound": "hbm", "kernel": "conv2_fwd_kernel / conv2_dw_kernel / conv2_dimg_kernel",
+           "roofline": {"bound": "hbm", "kernel": "conv2_fwd_tc_kernel / conv2_dw_tc_kernel / conv2_dimg_tc_kernel (tcgen05 implicit GEMM)",
                         "achieved": 3 * (in_bytes + out_bytes) / (total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": 3 * (in_bytes + out_bytes) / (total * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
                         "per_kernel_frac": {k: (in_bytes + out_bytes) / (v * 1e-3) / 1e9 / peaks["hbm_gbs"] for k, v in kern.items()},

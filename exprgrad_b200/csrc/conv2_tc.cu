@@ -658,7 +658,10 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
   p.vec4 = ((W * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(dimg) & 15) == 0) ? 1 : 0;
   // the tiles overlap (rows by dy, columns by the halo) and meet through RED: start from zero unless the
   // caller accumulates onto existing data
-  if (!accumulate) EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
+  if (!accumulate) {
+    Launch lz(ctx, KC_CONV, st);   // counted (and timed) with the kernel it belongs to
+    EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
+  }
   const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)(TILE_P * DI_TLD + 4) * 4 +
                       (2 * DI_STAGES + 4) * 8 + 32;
   int grid = ctx.sm_count;
