@@ -275,6 +275,37 @@ __device__ __forceinline__ void split_store_32(const float4 (&x)[8], uint8_t* a_
   }
 }
 
+// Raw fp32 dout tile [128 pixels x 64 filters] (as the bulk copy delivered it) -> swizzled hi / mid bf16
+// tiles. 256 threads; a warp converts 4 rows per step: lane l takes the 8 filters of chunk l % 8 of row
+// l / 8 (32 contiguous bytes per lane, 256 per row: conflict-free reads and swizzled 16-byte writes).
+// Rows >= valid_rows (tail tile / end of an output row) become zeros.
+__device__ __forceinline__ void convert_dout_tile(const float* raw, uint8_t* a_hi, uint8_t* a_mid, int t, int valid_rows) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = j * 32 + (t >> 3), c = t & 7;
+    float v[8];
+    if (row < valid_rows) {
+      const float4 x0 = *reinterpret_cast<const float4*>(raw + row * 64 + c * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(raw + row * 64 + c * 8 + 4);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+    }
+    uint32_t h[4], m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+      h[e] = pack_bf16(h0, h1);
+      m[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+    }
+    *reinterpret_cast<uint4*>(a_hi + sw128(row, c)) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_mid + sw128(row, c)) = make_uint4(m[0], m[1], m[2], m[3]);
+  }
+}
+constexpr int RAW_BYTES = TILE_P * 64 * 4;   // one raw fp32 dout tile
+constexpr int RAW_STAGES = 3;
+
 __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const DimgParams p) {
   constexpr int KH = 3, KW = 3, C = 3, F = 64, K = KH * KW * C, NT = 32;
   constexpr int SEG = (TILE_P + KW - 1) * C;   // floats of one input-row segment a tile touches (390)
@@ -459,7 +490,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
 // The tensor core's fp32 accumulation truncates, so D is drained into registers every DW_FLUSH tiles
 // (512 pixels) and summed there with rounded adds; the CTAs meet in dw through atomics at the very end.
 constexpr int DW_THREADS = 448;   // 8 producer warps, MMA, TMEM allocator, 4 epilogue warps
-constexpr int DW_STAGES = 3;
+constexpr int DW_STAGES = 2;
 constexpr int DW_FLUSH = 4;
 
 struct DwParams {
@@ -478,16 +509,23 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* sS = smem;   // DW_STAGES x (dout_hi, dout_mid, im2col), 16 KB each
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sS + DW_STAGES * 3 * A_BYTES);
+  uint8_t* sRaw = sS + DW_STAGES * 3 * A_BYTES;   // RAW_STAGES raw fp32 dout tiles (bulk-copy ring)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sRaw + RAW_STAGES * RAW_BYTES);
   uint64_t* a_empty = a_full + DW_STAGES;
   uint64_t* tmem_full = a_empty + DW_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* raw_full = tmem_empty + 2;
+  uint64_t* raw_empty = raw_full + RAW_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RAW_STAGES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < DW_STAGES; ++s) {
       ptx::mbar_init(&a_full[s], 256);
       ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int r = 0; r < RAW_STAGES; ++r) {
+      ptx::mbar_init(&raw_full[r], 1);      // the loader's arrive.expect_tx
+      ptx::mbar_init(&raw_empty[r], 256);   // every converter thread
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
@@ -507,21 +545,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
   const int my_groups = (my_tiles + DW_FLUSH - 1) / DW_FLUSH;
 
   if (warp < 8) {
-    // ===================================================== producers: half a dout row + half an im2col row
+    // ===================================================== producers: convert the raw dout tile + half an im2col row
+    // (dout arrives through the loader warp's bulk-copy ring, RAW_STAGES tiles ahead: with per-thread
+    // global loads ncu showed 8.7 long-scoreboard stalls per issue and issue slots 23 % busy)
     const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % DW_STAGES;
       const uint32_t ph = (it / DW_STAGES) & 1;
+      const int rs = it % RAW_STAGES;
+      const uint32_t rph = (it / RAW_STAGES) & 1;
       const long pix = (long)tile * TILE_P + row;
-      float4 x[8];
       float v[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = 0.0f;
       if (pix < p.total) {
-        const float4* src = reinterpret_cast<const float4*>(p.dout + (size_t)pix * F + half * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __ldg(src + i);
         const int xo = (int)(pix % p.OW);
         const long t = pix / p.OW;
         const int y = (int)(t % p.OH);
@@ -534,13 +572,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
 #pragma unroll
           for (int k = 16; k < K; ++k) v[k - 16] = __ldg(base + (size_t)(k / KWC) * p.W * C + (k % KWC));
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
       ptx::mbar_wait(&a_empty[s], ph ^ 1, 31);
       uint8_t* d_hi = sS + s * 3 * A_BYTES;
-      split_store_32(x, d_hi, d_hi + A_BYTES, row, half * 4);
+      ptx::mbar_wait(&raw_full[rs], rph, 35);
+      const long left = p.total - (long)tile * TILE_P;
+      convert_dout_tile(reinterpret_cast<const float*>(sRaw + rs * RAW_BYTES), d_hi, d_hi + A_BYTES, threadIdx.x,
+                        left >= TILE_P ? TILE_P : (int)left);
+      ptx::mbar_arrive(&raw_empty[rs]);
       uint8_t* a = d_hi + 2 * A_BYTES;   // im2col row: chunks 0-3 hi, 4-7 mid; this thread owns taps 16*half .. +15
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -557,6 +596,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
       }
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 9) {
+    // ===================================================== loader: bulk copies of the raw dout tiles
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int rs = it % RAW_STAGES;
+      const uint32_t rph = (it / RAW_STAGES) & 1;
+      ptx::mbar_wait(&raw_empty[rs], rph ^ 1, 36);
+      if (ptx::elect_one()) {
+        const long left = p.total - (long)tile * TILE_P;
+        const uint32_t bytes = (uint32_t)(left >= TILE_P ? TILE_P : left) * 64 * 4;
+        ptx::mbar_arrive_expect_tx(&raw_full[rs], bytes);
+        ptx::bulk_load(sRaw + rs * RAW_BYTES, p.dout + (size_t)tile * TILE_P * 64, bytes, &raw_full[rs]);
+      }
+      __syncwarp();
     }
   } else if (warp == 8) {
     // ===================================================== MMA issuer
@@ -688,7 +742,8 @@ void launch_conv2_dw_tc(Context& ctx, const float* img, const float* dout, float
   p.total = (long)N * p.OH * p.OW;
   if (p.total <= 0) return;
   p.ntiles = (int)((p.total + TILE_P - 1) / TILE_P);
-  const size_t smem = 1024 + (size_t)DW_STAGES * 3 * A_BYTES + (2 * DW_STAGES + 4) * 8 + 32;
+  const size_t smem = 1024 + (size_t)DW_STAGES * 3 * A_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
+                      (2 * DW_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
