@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
 // inside the tile) and added to dimg with one coalesced RED per element - tiles overlap by dy and by
 // the 2-pixel halo, so the image must be zeroed (or hold the value to accumulate onto) beforehand.
 constexpr int DI_THREADS = 448;   // 8 producer warps, MMA, TMEM allocator, 4 epilogue warps
-constexpr int DI_STAGES = 4;
+constexpr int DI_STAGES = 2;
 constexpr int DI_TLD = 33;        // row stride of the T tile in shared memory (floats)
 
 struct DimgParams {
@@ -316,18 +316,25 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   uint8_t* sWhi = smem;                       // [32 taps][64 f] bf16, K-major (K = f)
   uint8_t* sWmid = smem + NT * 128;
   uint8_t* sA = smem + 2 * NT * 128;          // DI_STAGES x (A_hi, A_mid), 16 KB each
-  float* sT = reinterpret_cast<float*>(sA + DI_STAGES * 2 * A_BYTES);
+  uint8_t* sRaw = sA + DI_STAGES * 2 * A_BYTES;   // RAW_STAGES raw fp32 dout tiles (bulk-copy ring)
+  float* sT = reinterpret_cast<float*>(sRaw + RAW_STAGES * RAW_BYTES);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sT + TILE_P * DI_TLD + 1);
   a_full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(a_full) + 7) & ~uintptr_t(7));
   uint64_t* a_empty = a_full + DI_STAGES;
   uint64_t* tmem_full = a_empty + DI_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* raw_full = tmem_empty + 2;
+  uint64_t* raw_empty = raw_full + RAW_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RAW_STAGES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < DI_STAGES; ++s) {
       ptx::mbar_init(&a_full[s], 256);
       ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int r = 0; r < RAW_STAGES; ++r) {
+      ptx::mbar_init(&raw_full[r], 1);
+      ptx::mbar_init(&raw_empty[r], 256);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
@@ -361,28 +368,38 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 8) {
-    // ===================================================== producers: half a dout row (32 filters) per thread
-    const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
+    // ===================================================== producers: convert the raw dout tile of the ring
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % DI_STAGES;
       const uint32_t ph = (it / DI_STAGES) & 1;
+      const int rs = it % RAW_STAGES;
+      const uint32_t rph = (it / RAW_STAGES) & 1;
       const int x0 = (tile % p.tiles_per_row) * TILE_P;
-      const long ny = tile / p.tiles_per_row;   // n * OH + y
-      float4 x[8];
-      if (x0 + row < p.OW) {
-        const float4* src = reinterpret_cast<const float4*>(p.dout + ((size_t)ny * p.OW + x0 + row) * F + half * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __ldg(src + i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      }
       ptx::mbar_wait(&a_empty[s], ph ^ 1, 21);
+      ptx::mbar_wait(&raw_full[rs], rph, 25);
       uint8_t* a_hi = sA + s * 2 * A_BYTES;
-      split_store_32(x, a_hi, a_hi + A_BYTES, row, half * 4);
+      convert_dout_tile(reinterpret_cast<const float*>(sRaw + rs * RAW_BYTES), a_hi, a_hi + A_BYTES, threadIdx.x,
+                        min(TILE_P, p.OW - x0));
+      ptx::mbar_arrive(&raw_empty[rs]);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 9) {
+    // ===================================================== loader: bulk copies of the raw dout row segments
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int rs = it % RAW_STAGES;
+      const uint32_t rph = (it / RAW_STAGES) & 1;
+      ptx::mbar_wait(&raw_empty[rs], rph ^ 1, 26);
+      if (ptx::elect_one()) {
+        const int x0 = (tile % p.tiles_per_row) * TILE_P;
+        const long ny = tile / p.tiles_per_row;   // n * OH + y
+        const uint32_t bytes = (uint32_t)min(TILE_P, p.OW - x0) * F * 4;
+        ptx::mbar_arrive_expect_tx(&raw_full[rs], bytes);
+        ptx::bulk_load(sRaw + rs * RAW_BYTES, p.dout + ((size_t)ny * p.OW + x0) * F, bytes, &raw_full[rs]);
+      }
+      __syncwarp();
     }
   } else if (warp == 8) {
     // ===================================================== MMA issuer
@@ -716,8 +733,8 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
     Launch lz(ctx, KC_CONV, st);   // counted (and timed) with the kernel it belongs to
     EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
   }
-  const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)(TILE_P * DI_TLD + 4) * 4 +
-                      (2 * DI_STAGES + 4) * 8 + 32;
+  const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
+                      (size_t)(TILE_P * DI_TLD + 4) * 4 + (2 * DI_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
