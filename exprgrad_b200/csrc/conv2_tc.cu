@@ -51,6 +51,17 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// (x0, x1) -> packed bf16x2 hi and mid words: hi = bf16(x), mid = bf16(x - hi). One cvt.rn.bf16x2.f32 per pair
+// (the scalar conversions are the producers' most expensive instructions).
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& h, uint32_t& m) {
+  const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+  h = *reinterpret_cast<const uint32_t*>(&hp);
+  const float r0 = x0 - __uint_as_float(h << 16);           // low half = x0's bf16 bits
+  const float r1 = x1 - __uint_as_float(h & 0xffff0000u);
+  const __nv_bfloat162 mp = __floats2bfloat162_rn(r0, r1);
+  m = *reinterpret_cast<const uint32_t*>(&mp);
+}
+
 // byte offset of 16-byte chunk `c` of row `r` in a K-major SWIZZLE_128B tile (rows of 128 bytes)
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -97,9 +108,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
       const int k0 = 8 * (c & 3) + 2 * e;
       const float x0 = k0 < K ? __ldg(p.w + (size_t)f * K + k0) : 0.0f;
       const float x1 = k0 + 1 < K ? __ldg(p.w + (size_t)f * K + k0 + 1) : 0.0f;
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-      h[e] = pack_bf16(h0, h1);
-      m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+      split_pair(x0, x1, h[e], m[e]);
     }
     *reinterpret_cast<uint4*>(sB1 + sw128(f, c)) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(sB2 + sw128(f, c)) = c < 4 ? make_uint4(m[0], m[1], m[2], m[3]) : make_uint4(0, 0, 0, 0);
@@ -152,9 +161,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
           const int k0 = 8 * c + 2 * e;
           const float x0 = k0 < K ? v[k0 < K ? k0 : 0] : 0.0f;
           const float x1 = k0 + 1 < K ? v[k0 + 1 < K ? k0 + 1 : 0] : 0.0f;
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-          h[e] = pack_bf16(h0, h1);
-          m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+          split_pair(x0, x1, h[e], m[e]);
         }
         *reinterpret_cast<uint4*>(a + sw128(row, c)) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(a + sw128(row, c + 4)) = make_uint4(m[0], m[1], m[2], m[3]);
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
 // (3 rows x 130 pixels x 3 channels) is gathered from T in shared memory (3 adds per element, no atomics
 // inside the tile) and added to dimg with one coalesced RED per element - tiles overlap by dy and by
 // the 2-pixel halo, so the image must be zeroed (or hold the value to accumulate onto) beforehand.
-constexpr int DI_THREADS = 448;   // 8 producer warps, MMA, TMEM allocator, 4 epilogue warps
+constexpr int DI_THREADS = 576;   // 8 converter warps, MMA, loader/TMEM allocator, 2 x 4 epilogue warps
 constexpr int DI_STAGES = 2;
 constexpr int DI_TLD = 33;        // row stride of the T tile in shared memory (floats)
 
@@ -266,9 +273,7 @@ __device__ __forceinline__ void split_store_32(const float4 (&x)[8], uint8_t* a_
     uint32_t h[4], m[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
-      h[e] = pack_bf16(h0, h1);
-      m[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+      split_pair(v[2 * e], v[2 * e + 1], h[e], m[e]);
     }
     *reinterpret_cast<uint4*>(a_hi + sw128(row, c0 + i)) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(a_mid + sw128(row, c0 + i)) = make_uint4(m[0], m[1], m[2], m[3]);
@@ -295,9 +300,7 @@ __device__ __forceinline__ void convert_dout_tile(const float* raw, uint8_t* a_h
     uint32_t h[4], m[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
-      h[e] = pack_bf16(h0, h1);
-      m[e] = pack_bf16(__float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1)));
+      split_pair(v[2 * e], v[2 * e + 1], h[e], m[e]);
     }
     *reinterpret_cast<uint4*>(a_hi + sw128(row, c)) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(a_mid + sw128(row, c)) = make_uint4(m[0], m[1], m[2], m[3]);
@@ -317,8 +320,8 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   uint8_t* sWmid = smem + NT * 128;
   uint8_t* sA = smem + 2 * NT * 128;          // DI_STAGES x (A_hi, A_mid), 16 KB each
   uint8_t* sRaw = sA + DI_STAGES * 2 * A_BYTES;   // RAW_STAGES raw fp32 dout tiles (bulk-copy ring)
-  float* sT = reinterpret_cast<float*>(sRaw + RAW_STAGES * RAW_BYTES);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sT + TILE_P * DI_TLD + 1);
+  float* sT0 = reinterpret_cast<float*>(sRaw + RAW_STAGES * RAW_BYTES);   // one T tile per epilogue group
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sT0 + 2 * TILE_P * DI_TLD + 1);
   a_full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(a_full) + 7) & ~uintptr_t(7));
   uint64_t* a_empty = a_full + DI_STAGES;
   uint64_t* tmem_full = a_empty + DI_STAGES;
@@ -354,9 +357,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       const int f0 = 8 * c + 2 * e;
       const float x0 = k < K ? __ldg(p.w + (size_t)f0 * K + k) : 0.0f;
       const float x1 = k < K ? __ldg(p.w + (size_t)(f0 + 1) * K + k) : 0.0f;
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-      h[e] = pack_bf16(h0, h1);
-      m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+      split_pair(x0, x1, h[e], m[e]);
     }
     *reinterpret_cast<uint4*>(sWhi + sw128(k, c)) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(sWmid + sw128(k, c)) = make_uint4(m[0], m[1], m[2], m[3]);
@@ -432,10 +433,14 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
     }
   } else if (warp >= 10) {
     // ===================================================== epilogue: T -> shared memory -> col2im gather -> RED
+    // Two groups of four warps: group g finishes the tiles whose accumulator is g (every other tile), so
+    // two col2im gathers are in flight per SM.
     const int q = warp & 3;
+    const int grp = (warp - 10) >> 2;
+    float* sT = sT0 + grp * TILE_P * DI_TLD;
     const int et = q * 32 + lane;   // 0..127: accumulator row handled by this thread / gather thread id
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    uint32_t it = grp;
+    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < p.ntiles; tile += 2 * (int)gridDim.x, it += 2) {
       const uint32_t acc = it & 1;
       const int x0 = (tile % p.tiles_per_row) * TILE_P;
       const long ny = tile / p.tiles_per_row;
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps: T is complete
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the four warps of the group: T is complete
       auto gather = [&](int dy, int j) {   // element j of the input-row segment y + dy
         const int X = j / C, c = j - X * C;
         float sum = 0.0f;
@@ -485,7 +490,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
           atomicAdd(p.dimg + (((size_t)n * p.H + y + dy) * p.W + x0) * C + j, gather(dy, j));
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // T is rewritten by the next tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // T is rewritten by the group's next tile
     }
   }
 
@@ -604,9 +609,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float x0 = v[8 * c + 2 * e], x1 = v[8 * c + 2 * e + 1];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-          h[e] = pack_bf16(h0, h1);
-          m[e] = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+          split_pair(x0, x1, h[e], m[e]);
         }
         *reinterpret_cast<uint4*>(a + sw128(row, half * 2 + c)) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(a + sw128(row, 4 + half * 2 + c)) = make_uint4(m[0], m[1], m[2], m[3]);
@@ -734,7 +737,7 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
     EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
   }
   const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
-                      (size_t)(TILE_P * DI_TLD + 4) * 4 + (2 * DI_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
+                      (size_t)(2 * TILE_P * DI_TLD + 4) * 4 + (2 * DI_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
