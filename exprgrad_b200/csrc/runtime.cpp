@@ -1119,26 +1119,31 @@ static void capture_levels(Model& m, Plan& plan) {
   for (int i = 0; i < n; ++i) {
     Node& nd = plan.nodes[i];
     int s = -1;
-    if (nd.kind == Node::ALLREDUCE || nd.kind == Node::MEMSET || critical[i]) {
-      s = 0;  // NCCL, memset and the critical path stay on the main stream
+    if (nd.kind == Node::ALLREDUCE) {
+      // all collectives on one dedicated stream, in plan order (every rank issues them in the same order, and
+      // never two at a time); off the main stream, so that the all-reduce of an early bucket segment
+      // overlaps the remaining adjoint contractions instead of sitting between them
+      s = NS - 1;
+    } else if (nd.kind == Node::MEMSET || critical[i]) {
+      s = 0;  // memset and the critical path stay on the main stream
     } else {
       // 1. a side stream whose tail is a predecessor (prefer the latest one)
       int best = -1;
-      for (int q = 1; q < NS; ++q)
+      for (int q = 1; q < NS - 1; ++q)
         if (tail[q] >= 0 && std::find(preds[i].begin(), preds[i].end(), tail[q]) != preds[i].end() && tail[q] > best) {
           best = tail[q];
           s = q;
         }
       // 2. a side stream whose tail is an ancestor anyway (stream order adds no false dependency)
-      for (int q = 1; q < NS && s < 0; ++q)
+      for (int q = 1; q < NS - 1 && s < 0; ++q)
         if (tail[q] >= 0 && anc[i][tail[q]]) s = q;
       // 3. an unused side stream
-      for (int q = 1; q < NS && s < 0; ++q)
+      for (int q = 1; q < NS - 1 && s < 0; ++q)
         if (tail[q] < 0) s = q;
       // 4. the side stream whose tail is the oldest node (a false dependency; only when all streams are busy)
       if (s < 0) {
         s = 1;
-        for (int q = 2; q < NS; ++q)
+        for (int q = 2; q < NS - 1; ++q)
           if (tail[q] < tail[s]) s = q;
       }
     }

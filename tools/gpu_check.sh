@@ -11,7 +11,7 @@ echo "== bench" ; timeout 600 python bench.py 2>gpurun_out/${TAG}_bench.err | te
 echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>>gpurun_out/${TAG}_bench.err | tee gpurun_out/${TAG}_bench_ref.json
 echo "== ncu launches"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu --no-conv > gpurun_out/${TAG}_ncu_bench.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu --no-conv --no-dense --no-e2e > gpurun_out/${TAG}_ncu_bench.log 2>&1
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 3 -c 2 -f -o gpurun_out/${TAG}_prof \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-conv --no-dense > gpurun_out/${TAG}_ncu_full.log 2>&1
