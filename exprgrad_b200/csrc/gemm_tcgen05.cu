@@ -63,7 +63,6 @@ struct KParams {
   // No atomics, no zero fill, fixed summation order. (splits == ck > 1: one unit per CTA.)
   int ck;
   int splits, kb_per_split;
-  int exp;  // timing experiments (EGB_GEMM_EXP)
   unsigned long long* trace;  // debug timeline (Context::trace) or null
   int trace_index;            // slot of this launch
 };
@@ -265,10 +264,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t aa = a_step * k, ba = b_step * k;
             // small cross terms first, dominant hi*hi last
-            if (p.exp == 3) {  // timing experiment: one product instead of three
-              ptx::umma_f16<1>(d_tmem, a_hi + aa, b_hi + ba, idesc, (kb != kb0) || (k != 0));
-              continue;
-            }
             ptx::umma_f16<1>(d_tmem, a_mid + aa, b_hi + ba, idesc, (kb != kb0) || (k != 0));
             ptx::umma_f16<1>(d_tmem, a_hi + aa, b_mid + ba, idesc, 1);
             ptx::umma_f16<1>(d_tmem, a_hi + aa, b_hi + ba, idesc, 1);
@@ -710,8 +705,6 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   p.b_mn = a.b_mn ? 1 : 0;
   p.trace = ctx.trace;
   p.trace_index = ctx.trace ? 1 + (int)(ctx.trace_next++ % (TRACE_SLOTS - 1)) : 0;
-  static const int exp_mode = getenv("EGB_GEMM_EXP") ? atoi(getenv("EGB_GEMM_EXP")) : 0;
-  p.exp = exp_mode;
   const int sms = (a.sm_budget > 0 && a.sm_budget < ctx.sm_count) ? a.sm_budget : ctx.sm_count;
   p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, sms, a.b_mn);
   int ck = a.cluster_k > 0 ? a.cluster_k : 1;

@@ -175,7 +175,11 @@ def test_conv2_forward_backward(ctx, shape):
 
 
 @pytest.mark.parametrize("shape,filters", [((2, 20, 150, 3), (64, 3, 3, 3)), ((1, 12, 70, 5), (70, 3, 5, 5)),
-                                           ((3, 9, 9, 1), (8, 2, 2, 1)), ((2, 40, 40, 3), (64, 3, 3, 3))])
+                                           ((3, 9, 9, 1), (8, 2, 2, 1)), ((2, 40, 40, 3), (64, 3, 3, 3)),
+                                           # tensor-core forward at its other widths / channel counts, and a single
+                                           # partial tile (adjoints of these shapes run on the CUDA-core kernels)
+                                           ((2, 17, 33, 3), (32, 3, 3, 3)), ((1, 30, 141, 1), (128, 3, 3, 1)),
+                                           ((1, 5, 6, 3), (64, 3, 3, 3)), ((2, 3, 131, 3), (64, 3, 3, 3))])
 def test_conv2_direct_kernels(ctx, shape, filters):
     """The dedicated conv2 kernels (csrc/conv2.cu) on shapes that exercise pixel-chunk tails, more than
     one filter chunk, channel chunks and other filter sizes; U(-2,2) filters like benchmarks/conv2."""
