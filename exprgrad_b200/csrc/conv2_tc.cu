@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
 #pragma unroll
       for (int k = 0; k < K; ++k) v[k] = nv[k];
       load_taps(tile + gridDim.x, nv);
-      ptx::mbar_wait(&a_empty[s], ph ^ 1, 11);   // the MMAs that read this stage have retired
+      ptx::mbar_wait_sleepy(&a_empty[s], ph ^ 1, 11);   // the MMAs that read this stage have retired
       uint8_t* a = sA + s * A_BYTES;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {   // chunk c: taps 8c .. 8c+7 (hi) and the same taps' mid in chunk c + 4
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       const uint32_t acc = it & 1;
-      ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 12);
-      ptx::mbar_wait(&a_full[s], ph, 13);
+      ptx::mbar_wait_sleepy(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 12);
+      ptx::mbar_wait_sleepy(&a_full[s], ph, 13);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)F;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
-      ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1, 14);
+      ptx::mbar_wait_sleepy(&tmem_full[acc], (it >> 1) & 1, 14);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)F;
       for (int c = 0; c < F; c += 32) {
@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       const int rs = it % RAW_STAGES;
       const uint32_t rph = (it / RAW_STAGES) & 1;
       const int x0 = (tile % p.tiles_per_row) * TILE_P;
-      ptx::mbar_wait(&a_empty[s], ph ^ 1, 21);
-      ptx::mbar_wait(&raw_full[rs], rph, 25);
+      ptx::mbar_wait_sleepy(&a_empty[s], ph ^ 1, 21);
+      ptx::mbar_wait_sleepy(&raw_full[rs], rph, 25);
       uint8_t* a_hi = sA + s * 2 * A_BYTES;
       convert_dout_tile(reinterpret_cast<const float*>(sRaw + rs * RAW_BYTES), a_hi, a_hi + A_BYTES, threadIdx.x,
                         min(TILE_P, p.OW - x0));
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int rs = it % RAW_STAGES;
       const uint32_t rph = (it / RAW_STAGES) & 1;
-      ptx::mbar_wait(&raw_empty[rs], rph ^ 1, 26);
+      ptx::mbar_wait_sleepy(&raw_empty[rs], rph ^ 1, 26);
       if (ptx::elect_one()) {
         const int x0 = (tile % p.tiles_per_row) * TILE_P;
         const long ny = tile / p.tiles_per_row;   // n * OH + y
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       const int s = it % DI_STAGES;
       const uint32_t ph = (it / DI_STAGES) & 1;
       const uint32_t acc = it & 1;
-      ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 22);
-      ptx::mbar_wait(&a_full[s], ph, 23);
+      ptx::mbar_wait_sleepy(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 22);
+      ptx::mbar_wait_sleepy(&a_full[s], ph, 23);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * NT;
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       const long ny = tile / p.tiles_per_row;
       const int y = (int)(ny % p.OH);
       const long n = ny / p.OH;
-      ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1, 24);
+      ptx::mbar_wait_sleepy(&tmem_full[acc], (it >> 1) & 1, 24);
       ptx::tc_fence_after();
       uint32_t r[32];
       ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT, r);
@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
           for (int k = 16; k < K; ++k) v[k - 16] = __ldg(base + (size_t)(k / KWC) * p.W * C + (k % KWC));
         }
       }
-      ptx::mbar_wait(&a_empty[s], ph ^ 1, 31);
+      ptx::mbar_wait_sleepy(&a_empty[s], ph ^ 1, 31);
       uint8_t* d_hi = sS + s * 3 * A_BYTES;
-      ptx::mbar_wait(&raw_full[rs], rph, 35);
+      ptx::mbar_wait_sleepy(&raw_full[rs], rph, 35);
       const long left = p.total - (long)tile * TILE_P;
       convert_dout_tile(reinterpret_cast<const float*>(sRaw + rs * RAW_BYTES), d_hi, d_hi + A_BYTES, threadIdx.x,
                         left >= TILE_P ? TILE_P : (int)left);
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int rs = it % RAW_STAGES;
       const uint32_t rph = (it / RAW_STAGES) & 1;
-      ptx::mbar_wait(&raw_empty[rs], rph ^ 1, 36);
+      ptx::mbar_wait_sleepy(&raw_empty[rs], rph ^ 1, 36);
       if (ptx::elect_one()) {
         const long left = p.total - (long)tile * TILE_P;
         const uint32_t bytes = (uint32_t)(left >= TILE_P ? TILE_P : left) * 64 * 4;
@@ -644,8 +644,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
       const uint32_t ph = (it / DW_STAGES) & 1;
       const uint32_t group = it / DW_FLUSH, in_group = it % DW_FLUSH;
       const uint32_t acc = group & 1;
-      if (in_group == 0) ptx::mbar_wait(&tmem_empty[acc], ((group >> 1) & 1) ^ 1, 32);
-      ptx::mbar_wait(&a_full[s], ph, 33);
+      if (in_group == 0) ptx::mbar_wait_sleepy(&tmem_empty[acc], ((group >> 1) & 1) ^ 1, 32);
+      ptx::mbar_wait_sleepy(&a_full[s], ph, 33);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * 64;
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
     for (int j = 0; j < 64; ++j) sum[j] = 0.0f;
     for (int g = 0; g < my_groups; ++g) {
       const uint32_t acc = g & 1;
-      ptx::mbar_wait(&tmem_full[acc], (g >> 1) & 1, 34);
+      ptx::mbar_wait_sleepy(&tmem_full[acc], (g >> 1) & 1, 34);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
 #pragma unroll
