@@ -627,7 +627,21 @@ void build_nodes_impl(Model& m, Plan& plan) {
         n.ip.accumulate = 1;
       }
       if (n.ip.accumulate) n.reads.push_back(k.write.tensor);
-      plan.nodes.push_back(n);
+      // A kernel that reads nothing and overwrites a result no other kernel of the target writes (the adjoint
+      // seed `dL = 1`, passes.nim:614-636) produces the same values on every run: it is launched once, here,
+      // and stays out of the plan - in the dense step it sat on the critical path in front of the head.
+      bool constant = m.fuse && !m.strict && k.reads.empty() && !n.uses_epoch && !n.ip.accumulate && n.rsplit <= 1 &&
+                      m.prog->tdef(k.write.tensor).kind == TensorKind::Result;
+      if (constant) {
+        int writers = 0;
+        for (auto& other : target.kernels) writers += other->write.tensor == k.write.tensor;
+        constant = writers == 1;
+      }
+      if (constant) {
+        launch_interp(ctx, n.ip, n.pb, n.rb, n.points_fast, n.strict, ctx.stream, n.rsplit);
+      } else {
+        plan.nodes.push_back(n);
+      }
     }
     // cached planes of every tensor this unit wrote are stale now (except the ones it just produced)
     std::vector<int> wrote = {k.write.tensor};
