@@ -305,20 +305,29 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const bool need_h = kFused && (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY);
     const bool need_d = kFused && p.epi == EPI_SGD;
     // One 32-row x 16-column unit in the coalesced layout: v[i] = alpha * acc of row row0 + lr + 8i.
-    auto finish_unit = [&](float4 (&v)[4], const int row0, const int nrows, const int col0) {
+    // Phase 1 of a unit: every global read (bias, old C, mask source / parameter) is issued before the first
+    // store - the pointers may alias as far as the compiler knows, so loads interleaved with stores would
+    // serialise into one L2 round trip per row group. For the first unit of a warp these loads are issued
+    // even before the accumulator is complete (they do not depend on it).
+    struct UnitLoads {
+      float b[4];
+      float4 oldc[4], aux[4];  // aux: H (mask source) or the parameter the SGD stage updates
+      uint32_t valid;
+    };
+    auto unit_loads = [&](UnitLoads& L, const int row0, const int nrows, const int col0) {
       const int ncols = min(UNIT_COLS, p.N - col0);
       const int cnt = max(0, min(4, ncols - c4));  // valid columns of this thread
       const bool full = vec_ok && cnt == 4;
-      // Phase 1: every global read of the unit is issued before the first store. The pointers may alias
-      // as far as the compiler knows, so loads interleaved with stores would serialise into one L2 round
-      // trip per row group.
-      float b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      float (&b)[4] = L.b;
+      float4 (&oldc)[4] = L.oldc;
+      float4 (&aux)[4] = L.aux;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) b[e] = 0.0f;
       if (kFused && (p.flags & GEMM_BIAS)) {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (e < cnt) b[e] = __ldg(p.bias + col0 + c4 + e);
       }
-      float4 oldc[4], aux[4];  // aux: H (mask source) or the parameter the SGD stage updates
       uint32_t valid = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -345,7 +354,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           aux[i] = make_float4(a2[0], a2[1], a2[2], a2[3]);
         }
       }
-      // Phase 2: arithmetic and stores
+      L.valid = valid;
+    };
+    // Phase 2 of a unit in the coalesced layout: v[i] = alpha * acc of row row0 + lr + 8i.
+    auto finish_unit = [&](float4 (&v)[4], const UnitLoads& L, const int row0, const int col0) {
+      const int ncols = min(UNIT_COLS, p.N - col0);
+      const int cnt = max(0, min(4, ncols - c4));  // valid columns of this thread
+      const bool full = vec_ok && cnt == 4;
+      const float (&b)[4] = L.b;
+      const float4 (&oldc)[4] = L.oldc;
+      const float4 (&aux)[4] = L.aux;
+      const uint32_t valid = L.valid;
       float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -434,6 +453,30 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
     };
+    // Loads of this warp's first unit, issued while the main loop is still running. They read tensors that
+    // earlier kernels produced, so the warp first joins the programmatic-launch dependency.
+    UnitLoads pre;
+    bool have_pre = false;
+    pdl_wait();
+    if ((int)blockIdx.x < num_units) {
+      const int tile = blockIdx.x / p.splits;
+      const int m0 = (tile % p.tiles_m) * BM;
+      const int n0 = (tile / p.tiles_m) * p.BN;
+      if (p.ck > 1) {
+        const int rows_per = BM / p.ck, nunits = p.BN / UNIT_COLS;
+        const int groups = (rows_per + 31) / 32;
+        if (ew < groups * nunits) {
+          const int g = ew / nunits, c = (ew % nunits) * UNIT_COLS;
+          if (n0 + c < p.N) {
+            unit_loads(pre, m0 + (int)ptx::cluster_ctarank() * rows_per + g * 32, min(32, rows_per - g * 32), n0 + c);
+            have_pre = true;
+          }
+        }
+      } else if (eh * UNIT_COLS < p.BN && n0 + eh * UNIT_COLS < p.N) {
+        unit_loads(pre, m0 + q * 32, 32, n0 + eh * UNIT_COLS);
+        have_pre = true;
+      }
+    }
     uint32_t local_tile = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local_tile) {
       const int tile = unit / p.splits;
@@ -486,7 +529,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
         __syncwarp();  // the staging block is rewritten by the next unit
         if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(16);
-        finish_unit(v, m0 + q * 32, 32, col0);
+        if (!(have_pre && local_tile == 0 && c == eh * UNIT_COLS)) unit_loads(pre, m0 + q * 32, 32, col0);
+        finish_unit(v, pre, m0 + q * 32, col0);
         if (local_tile == 0 && c == 0 && threadIdx.x == 128) EGB_TRACE(17);
       }
       ptx::tc_fence_before();
@@ -554,7 +598,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         for (int i = 0; i < 4; ++i) {
           v[k][i].x *= p.alpha; v[k][i].y *= p.alpha; v[k][i].z *= p.alpha; v[k][i].w *= p.alpha;
         }
-        finish_unit(v[k], m0 + (int)crank * rows_per + g * 32, min(32, rows_per - g * 32), col0);
+        if (!(have_pre && k == 0)) unit_loads(pre, m0 + (int)crank * rows_per + g * 32, min(32, rows_per - g * 32), col0);
+        finish_unit(v[k], pre, m0 + (int)crank * rows_per + g * 32, col0);
       }
       __syncwarp();
       ptx::cluster_wait();  // peers may still be reading this CTA's staging buffer until here

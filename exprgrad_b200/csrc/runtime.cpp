@@ -348,13 +348,16 @@ bool fuse_row_chains(Model& m, Plan& plan) {
                        describe_kernel(*target.kernels[nj.kernel_index]) == "loops=.! W[I1] R0[I0,I1] : R0" &&
                        target.kernels[nj.kernel_index]->reads[0].tensor == DH && tensor_len((int)nj.writes[0]) == hs[1]) {
               fx.sx_colsum = (float*)nj.ip.write.base;
-              Node z;
-              z.kind = Node::MEMSET;
-              z.label = "zero column sums of tensor" + std::to_string((int)nj.writes[0] - 1);
-              z.ptr = fx.sx_colsum;
-              z.bytes = (size_t)hs[1] * 4;
-              z.writes.push_back(nj.writes[0]);
-              insert.emplace_back(first_member, z);
+              const bool prezeroed = (char*)fx.sx_colsum >= plan.arena && (char*)fx.sx_colsum < plan.arena + plan.zero_bytes;
+              if (!prezeroed) {   // (normally it lies in the region the plan's first node zeroes)
+                Node z;
+                z.kind = Node::MEMSET;
+                z.label = "zero column sums of tensor" + std::to_string((int)nj.writes[0] - 1);
+                z.ptr = fx.sx_colsum;
+                z.bytes = (size_t)hs[1] * 4;
+                z.writes.push_back(nj.writes[0]);
+                insert.emplace_back(first_member, z);
+              }
               for (auto w : nj.writes) fx.writes.push_back(w);
               fx.reads.push_back(nj.writes[0]);
               fx.label += " + column sums (kernel " + std::to_string(nj.kernel_index) + ")";
@@ -793,6 +796,11 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
     inf.overwrite = fresh && !reads_self && (inf.is_gemm || conv_covers ||
                                              (!inf.is_conv && covers_whole_tensor(k, plan->shapes)));
     if (prog->tdef(wt).kind == TensorKind::Result && !written.count(wt) && !inf.overwrite) needs_zero.insert(wt);
+    // a plain column sum (bias gradient) may be fused into the classification head, where the partial sums meet
+    // through atomics: keep its (small) result in the zeroed region so that no extra memset node is needed
+    if (fuse && !strict && prog->tdef(wt).kind == TensorKind::Result && !written.count(wt) && inf.overwrite && !inf.is_gemm &&
+        !inf.is_conv && describe_kernel(k) == "loops=.! W[I1] R0[I0,I1] : R0")
+      needs_zero.insert(wt);
     written.insert(wt);
     if (inf.is_gemm) {
       const GemmPattern& g = inf.gemm;
