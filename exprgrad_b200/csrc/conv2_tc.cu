@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
     const int q = warp & 3;   // TMEM lane quarter of this warp: pixels q*32 .. q*32+31 of the tile
     float* stage = sOut + q * 32 * (F + OUT_PAD);
     const int f4 = F >> 2;    // float4 per pixel
+    const int f4_shift = 31 - __clz(f4);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
@@ -223,8 +224,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
       const long left = p.total - pix0;
       const int nrows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
       float* dst = p.out + (size_t)pix0 * F;   // nrows * F contiguous floats
-      for (int i = lane; i < nrows * f4; i += 32) {
-        const int rr = i / f4, cc = (i - rr * f4) << 2;
+      const int total4 = nrows * f4;
+      // F is a power of two: row / column of float4 i by shift and mask; four independent copies in flight
+#pragma unroll 4
+      for (int i = lane; i < total4; i += 32) {
+        const int rr = i >> f4_shift, cc = (i & (f4 - 1)) << 2;
         float4 x = *reinterpret_cast<const float4*>(stage + rr * (F + OUT_PAD) + cc);
         if (p.accumulate) {
           const float4 o = *reinterpret_cast<const float4*>(dst + (size_t)i * 4);
