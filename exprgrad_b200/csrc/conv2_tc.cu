@@ -254,11 +254,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
 // Per tile of 128 output pixels of one output row:  T[p, k] = sum_f dout[p, f] * w[f, k]  (M = 128,
 // N = 32 taps, K = F = 64) on the tensor cores, then col2im: every input-row segment the tile touches
 // (3 rows x 130 pixels x 3 channels) is gathered from T in shared memory (3 adds per element, no atomics
-// inside the tile) and added to dimg with one coalesced RED per element - tiles overlap by dy and by
-// the 2-pixel halo, so the image must be zeroed (or hold the value to accumulate onto) beforehand.
+// inside the tile), accumulated in a three-row ring across the vertically adjacent tiles of a CTA and added
+// to dimg with 16-byte REDs once per row - runs of different CTAs and the 2-pixel halo of neighbouring
+// column tiles still overlap, so the image must be zeroed (or hold the value to accumulate onto) beforehand.
 constexpr int DI_THREADS = 576;   // 8 converter warps, MMA, loader/TMEM allocator, 2 x 4 epilogue warps
 constexpr int DI_STAGES = 2;
 constexpr int DI_TLD = 33;        // row stride of the T tile in shared memory (floats)
+constexpr int RING_LD = 392;      // one input-row segment of a tile: (128 + 2) pixels x 3 channels, padded to 16 bytes
 
 struct DimgParams {
   const float* dout;
@@ -324,8 +326,10 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   uint8_t* sWmid = smem + NT * 128;
   uint8_t* sA = smem + 2 * NT * 128;          // DI_STAGES x (A_hi, A_mid), 16 KB each
   uint8_t* sRaw = sA + DI_STAGES * 2 * A_BYTES;   // RAW_STAGES raw fp32 dout tiles (bulk-copy ring)
-  float* sT0 = reinterpret_cast<float*>(sRaw + RAW_STAGES * RAW_BYTES);   // one T tile per epilogue group
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sT0 + 2 * TILE_P * DI_TLD + 1);
+  float* sT = reinterpret_cast<float*>(sRaw + RAW_STAGES * RAW_BYTES);   // T tile [128][DI_TLD]
+  float* sRing = sT + TILE_P * DI_TLD + 3;                                 // three input-row segments (16-byte aligned)
+  sRing = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sRing) + 15) & ~uintptr_t(15));
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sRing + 3 * RING_LD);
   a_full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(a_full) + 7) & ~uintptr_t(7));
   uint64_t* a_empty = a_full + DI_STAGES;
   uint64_t* tmem_full = a_empty + DI_STAGES;
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);
+      ptx::mbar_init(&tmem_empty[a], 8);   // the eight epilogue warps
     }
     ptx::fence_barrier_init();
   }
@@ -371,16 +375,26 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Tiles are numbered (n, x-tile, y) with y fastest and every CTA takes one contiguous range, so that the
+  // tiles a CTA processes one after another are vertically adjacent (see the row ring in the epilogue).
+  const int t0 = (int)((long)blockIdx.x * p.ntiles / gridDim.x), t1 = (int)((long)(blockIdx.x + 1) * p.ntiles / gridDim.x);
+  auto decode = [&](int tile, int& x0, long& ny) {   // -> first output column, n * OH + y
+    const int y = tile % p.OH, col = tile / p.OH;
+    x0 = (col % p.tiles_per_row) * TILE_P;
+    ny = (long)(col / p.tiles_per_row) * p.OH + y;
+  };
 
   if (warp < 8) {
     // ===================================================== producers: convert the raw dout tile of the ring
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = t0; tile < t1; ++tile, ++it) {
       const int s = it % DI_STAGES;
       const uint32_t ph = (it / DI_STAGES) & 1;
       const int rs = it % RAW_STAGES;
       const uint32_t rph = (it / RAW_STAGES) & 1;
-      const int x0 = (tile % p.tiles_per_row) * TILE_P;
+      int x0;
+      long ny;
+      decode(tile, x0, ny);
       ptx::mbar_wait_sleepy(&a_empty[s], ph ^ 1, 21);
       ptx::mbar_wait_sleepy(&raw_full[rs], rph, 25);
       uint8_t* a_hi = sA + s * 2 * A_BYTES;
@@ -393,13 +407,14 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   } else if (warp == 9) {
     // ===================================================== loader: bulk copies of the raw dout row segments
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = t0; tile < t1; ++tile, ++it) {
       const int rs = it % RAW_STAGES;
       const uint32_t rph = (it / RAW_STAGES) & 1;
       ptx::mbar_wait_sleepy(&raw_empty[rs], rph ^ 1, 26);
       if (ptx::elect_one()) {
-        const int x0 = (tile % p.tiles_per_row) * TILE_P;
-        const long ny = tile / p.tiles_per_row;   // n * OH + y
+        int x0;
+        long ny;
+        decode(tile, x0, ny);
         const uint32_t bytes = (uint32_t)min(TILE_P, p.OW - x0) * F * 4;
         ptx::mbar_arrive_expect_tx(&raw_full[rs], bytes);
         ptx::bulk_load(sRaw + rs * RAW_BYTES, p.dout + ((size_t)ny * p.OW + x0) * F, bytes, &raw_full[rs]);
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
     const uint64_t wh = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWhi));
     const uint64_t wm = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sWmid));
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = t0; tile < t1; ++tile, ++it) {
       const int s = it % DI_STAGES;
       const uint32_t ph = (it / DI_STAGES) & 1;
       const uint32_t acc = it & 1;
@@ -436,65 +451,79 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       __syncwarp();
     }
   } else if (warp >= 10) {
-    // ===================================================== epilogue: T -> shared memory -> col2im gather -> RED
-    // Two groups of four warps: group g finishes the tiles whose accumulator is g (every other tile), so
-    // two col2im gathers are in flight per SM.
+    // ===================================================== epilogue: T -> shared memory -> col2im -> row ring -> RED
+    // Eight warps. The col2im contributions of a tile go to three input rows (y + dy); consecutive tiles of
+    // this CTA are vertically adjacent, so the rows are accumulated in a three-slot ring in shared memory
+    // and an input row is added to the image once (one 16-byte RED per four elements) when the last tile
+    // that touches it inside this CTA's run has been processed - instead of three REDs per element.
+    // Partial rows at the ends of a run simply meet the neighbouring CTA's part in memory.
+    const int et = threadIdx.x - 320;   // 0..255
     const int q = warp & 3;
-    const int grp = (warp - 10) >> 2;
-    float* sT = sT0 + grp * TILE_P * DI_TLD;
-    const int et = q * 32 + lane;   // 0..127: accumulator row handled by this thread / gather thread id
-    uint32_t it = grp;
-    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < p.ntiles; tile += 2 * (int)gridDim.x, it += 2) {
+    const bool loads_tmem = warp < 14;  // warps 10..13 cover the four TMEM lane quarters
+    for (int i = et; i < 3 * RING_LD; i += 256) sRing[i] = 0.0f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t it = 0;
+    for (int tile = t0; tile < t1; ++tile, ++it) {
       const uint32_t acc = it & 1;
-      const int x0 = (tile % p.tiles_per_row) * TILE_P;
-      const long ny = tile / p.tiles_per_row;
+      int x0;
+      long ny;
+      decode(tile, x0, ny);
       const int y = (int)(ny % p.OH);
       const long n = ny / p.OH;
-      ptx::mbar_wait_sleepy(&tmem_full[acc], (it >> 1) & 1, 24);
-      ptx::tc_fence_after();
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT, r);
-      ptx::tmem_ld_wait();
-      const bool live = x0 + et < p.OW;   // rows past the end of the output row carry zeros anyway
+      {
+        // two warps per TMEM lane quarter, 16 columns (taps) each
+        ptx::mbar_wait_sleepy(&tmem_full[acc], (it >> 1) & 1, 24);
+        ptx::tc_fence_after();
+        const int chalf = loads_tmem ? 0 : 16;
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT + chalf, r);
+        ptx::tmem_ld_wait();
+        const int trow = q * 32 + lane;
+        const bool live = x0 + trow < p.OW;   // rows past the end of the output row carry zeros anyway
 #pragma unroll
-      for (int j = 0; j < K; ++j) sT[et * DI_TLD + j] = live ? __uint_as_float(r[j]) : 0.0f;
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the four warps of the group: T is complete
-      auto gather = [&](int dy, int j) {   // element j of the input-row segment y + dy
-        const int X = j / C, c = j - X * C;
-        float sum = 0.0f;
+        for (int j = 0; j < 16; ++j)
+          if (chalf + j < K) sT[trow * DI_TLD + chalf + j] = live ? __uint_as_float(r[j]) : 0.0f;
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // T is complete
+      constexpr int XS = TILE_P + KW - 1;   // input pixels of a row segment
+      for (int idx = et; idx < KH * XS; idx += 256) {   // one (dy, input pixel) per thread: 9 taps -> 3 channels
+        const int dy = idx / XS, X = idx - dy * XS;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
         for (int dx = 0; dx < KW; ++dx) {
           const int xx = X - dx;
-          if (xx >= 0 && xx < TILE_P) sum += sT[xx * DI_TLD + (dy * KW + dx) * C + c];
-        }
-        return sum;
-      };
-      const int seg_len = min(SEG, (p.W - x0) * C);   // the segment ends with the image row
-      if (p.vec4) {
-        // rows and segments start 16-byte aligned: one 16-byte RED per four elements
-        constexpr int Q = (SEG + 3) / 4;
-        for (int idx = et; idx < KH * Q; idx += 128) {
-          const int dy = idx / Q, j = (idx - dy * Q) * 4;
-          if (j >= seg_len) continue;
-          float* dst = p.dimg + (((size_t)n * p.H + y + dy) * p.W + x0) * C + j;
-          if (j + 4 <= seg_len) {
-            const float s0 = gather(dy, j), s1 = gather(dy, j + 1), s2 = gather(dy, j + 2), s3 = gather(dy, j + 3);
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(s0), "f"(s1), "f"(s2), "f"(s3) : "memory");
-          } else {
-            for (int e = 0; j + e < seg_len; ++e) atomicAdd(dst + e, gather(dy, j + e));
+          if (xx >= 0 && xx < TILE_P) {
+            const float* t = sT + xx * DI_TLD + (dy * KW + dx) * C;
+            s0 += t[0]; s1 += t[1]; s2 += t[2];
           }
         }
-      } else {
-        for (int idx = et; idx < KH * SEG; idx += 128) {
-          const int dy = idx / SEG, j = idx - dy * SEG;
-          if (j >= seg_len) continue;
-          atomicAdd(p.dimg + (((size_t)n * p.H + y + dy) * p.W + x0) * C + j, gather(dy, j));
+        float* ring = sRing + ((y + dy) % 3) * RING_LD + X * C;
+        ring[0] += s0; ring[1] += s1; ring[2] += s2;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the ring holds this tile
+      // input row y is complete as far as this run goes; at the end of a column / of the run also y+1, y+2
+      const int nflush = (y == p.OH - 1 || tile == t1 - 1) ? 3 : 1;
+      const int seg_len = min(SEG, (p.W - x0) * C);   // the segment ends with the image row
+      constexpr int Q = (SEG + 3) / 4;
+      for (int idx = et; idx < nflush * Q; idx += 256) {
+        const int fr = idx / Q, j = (idx - fr * Q) * 4;
+        float* ring = sRing + ((y + fr) % 3) * RING_LD + j;
+        const float4 val = *reinterpret_cast<const float4*>(ring);
+        *reinterpret_cast<float4*>(ring) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (j >= seg_len) continue;
+        float* dst = p.dimg + (((size_t)n * p.H + y + fr) * p.W + x0) * C + j;
+        if (p.vec4 && j + 4 <= seg_len) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w)
+                       : "memory");
+        } else {
+          const float e[4] = {val.x, val.y, val.z, val.w};
+          for (int k2 = 0; k2 < 4 && j + k2 < seg_len; ++k2) atomicAdd(dst + k2, e[k2]);
         }
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // T is rewritten by the group's next tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // ring slots and T are reused by the next tile
     }
   }
 
@@ -741,7 +770,7 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
     EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
   }
   const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
-                      (size_t)(2 * TILE_P * DI_TLD + 4) * 4 + (2 * DI_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
+                      (size_t)(TILE_P * DI_TLD + 8 + 3 * RING_LD) * 4 + (2 * DI_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
