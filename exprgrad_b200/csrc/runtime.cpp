@@ -748,7 +748,9 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   plan->info.resize(nk);
   std::set<int> written, read_first, needs_zero;
   size_t plane_bytes = 0;
-  const bool dp = comm && comm_world(comm) > 1;
+  // (EGB_DP_FORCE: lay the plan out for data parallelism on a single rank - timing studies of the DP plan)
+  static const bool dp_force = getenv("EGB_DP_FORCE") != nullptr;
+  const bool dp = comm && (comm_world(comm) > 1 || dp_force);
   std::vector<std::string> text(nk);
   for (size_t ki = 0; ki < nk; ++ki) {
     if (target->kernels[ki]->is_generator())
@@ -903,7 +905,7 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   // ---- data parallel: the gradients of the parameters form one contiguous bucket that is
   // all-reduced right before the first optimizer kernel (the first kernel that writes a param/cache)
   std::set<int> bucket;
-  if (comm && comm_world(comm) > 1) {
+  if (comm && (comm_world(comm) > 1 || dp_force)) {
     auto gt = prog->grad_tensors.find(target_name);
     if (gt != prog->grad_tensors.end()) {
       for (int pid : prog->params) {
