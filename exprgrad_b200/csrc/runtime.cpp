@@ -1144,10 +1144,13 @@ static void capture_levels(Model& m, Plan& plan) {
     Node& nd = plan.nodes[i];
     int s = -1;
     if (nd.kind == Node::ALLREDUCE) {
-      // all collectives on one dedicated stream, in plan order (every rank issues them in the same order, and
-      // never two at a time); off the main stream, so that the all-reduce of an early bucket segment
-      // overlaps the remaining adjoint contractions instead of sitting between them
-      s = NS - 1;
+      // Up to 4 ranks: all collectives on one dedicated stream, in plan order (every rank issues them in the
+      // same order, and never two at a time), so that the all-reduce of an early bucket segment overlaps the
+      // remaining adjoint contractions instead of sitting between them (2 GPUs: 131.8 -> 119.1 us per step).
+      // At 8 ranks NCCL's kernels use many more CTAs and must be co-resident on every rank, while the
+      // contractions hold one SM per CTA: the overlapped variant measured 298 us per step there against
+      // ~210 us with the collectives in stream order - so they stay on the main stream.
+      s = comm_world(m.comm) <= 4 ? NS - 1 : 0;
     } else if (nd.kind == Node::MEMSET || critical[i]) {
       s = 0;  // memset and the critical path stay on the main stream
     } else {
