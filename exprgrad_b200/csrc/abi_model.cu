@@ -450,6 +450,7 @@ struct RowStream {
 bool find_row_stream(Plan& plan, const Args& a, const int* on_device, RowStream& rs) {
   std::vector<SplitOp> splits;
   for (auto& n : plan.nodes) {
+    if (n.kind == Node::SPLIT && n.bytes) return false;   // the split launch also clears results: not streamable
     if (n.kind == Node::SPLIT && !n.split_jobs.empty()) {
       for (auto& j : n.split_jobs) splits.push_back(SplitOp{j.src, j.hi, j.mid, j.rows, j.cols, j.ld, j.dst_ld, j.act, false});
     } else if (n.kind == Node::SPLIT) {

@@ -145,8 +145,11 @@ struct SplitBatch {
   SplitJob jobs[MAX_JOBS];
   long first_chunk[MAX_JOBS + 1];
   int n;
+  uint4* zero_ptr;      // optional: a region to clear in the same launch (the plan's zero-initialised results)
+  size_t zero_vec16;    // its size in 16-byte units
 };
-void launch_split_batch(Context& ctx, const SplitJob* jobs, int n, cudaStream_t st);
+void launch_split_batch(Context& ctx, const SplitJob* jobs, int n, cudaStream_t st, void* zero_ptr = nullptr,
+                        size_t zero_bytes = 0);
 
 void launch_fill_u32(Context& ctx, uint32_t* dst, uint32_t value, size_t n, cudaStream_t st);
 

@@ -682,9 +682,22 @@ void build_nodes_impl(Model& m, Plan& plan) {
         }
       }
       first.label = merged_label + " (one launch)";
+      // the plan's leading memset (zero-initialised results) rides along: one node less in front of the first
+      // contraction. Its region is 16-byte aligned by construction (arena base, 256-byte tensor alignment).
+      int zero_node = -1;
+      for (int i = 0; i < (int)plan.nodes.size(); ++i) {
+        const Node& n = plan.nodes[i];
+        if (n.kind == Node::MEMSET && n.level == 0 && n.ptr == plan.arena && n.bytes == plan.zero_bytes && n.bytes % 16 == 0) zero_node = i;
+      }
+      if (zero_node >= 0) {
+        first.ptr = plan.nodes[zero_node].ptr;
+        first.bytes = plan.nodes[zero_node].bytes;
+        for (auto w : plan.nodes[zero_node].writes) first.writes.push_back(w);
+        first.label += " + zero results";
+      }
       std::vector<Node> kept;
       for (int i = 0; i < (int)plan.nodes.size(); ++i)
-        if (i == roots[0] || std::find(roots.begin(), roots.end(), i) == roots.end()) kept.push_back(plan.nodes[i]);
+        if (i != zero_node && (i == roots[0] || std::find(roots.begin(), roots.end(), i) == roots.end())) kept.push_back(plan.nodes[i]);
       plan.nodes = kept;
       compute_levels(plan);
     }
@@ -1007,7 +1020,7 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       break;
     case Node::SPLIT:
       if (!n.split_jobs.empty()) {
-        launch_split_batch(ctx, n.split_jobs.data(), (int)n.split_jobs.size(), st);
+        launch_split_batch(ctx, n.split_jobs.data(), (int)n.split_jobs.size(), st, n.ptr, n.bytes);
         break;
       }
       launch_split_bf16(ctx, n.split_src, n.split_rows, n.split_cols, n.split_ld, n.split_transpose, n.split_hi,

@@ -53,6 +53,10 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int rows, int c
 __global__ void split_rows_batch_kernel(const SplitBatch b) {
   pdl_launch_dependents();
   pdl_wait();
+  // the plan's zero-initialised results (a few KB; the gradient bucket under data parallelism) are cleared
+  // here instead of by a memset node in front of this kernel on the critical path
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.zero_vec16; i += (size_t)gridDim.x * blockDim.x)
+    b.zero_ptr[i] = make_uint4(0, 0, 0, 0);
   const long total = b.first_chunk[b.n];
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int j = 0;
@@ -151,8 +155,9 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int rows, 
 
 }  // namespace
 
-void launch_split_batch(Context& ctx, const SplitJob* jobs, int n, cudaStream_t st) {
+void launch_split_batch(Context& ctx, const SplitJob* jobs, int n, cudaStream_t st, void* zero_ptr, size_t zero_bytes) {
   if (n <= 0) return;
+  if ((reinterpret_cast<uintptr_t>(zero_ptr) & 15) || (zero_bytes & 15)) fail(EGB_ERR_GPU, "split batch: unaligned zero region");
   if (n > SplitBatch::MAX_JOBS) fail(EGB_ERR_GPU, "split batch of %d jobs exceeds %d", n, SplitBatch::MAX_JOBS);
   SplitBatch b;
   memset(&b, 0, sizeof(b));
@@ -164,7 +169,9 @@ void launch_split_batch(Context& ctx, const SplitJob* jobs, int n, cudaStream_t 
     total += (long)jobs[j].rows * ((jobs[j].cols + 7) >> 3);
   }
   b.first_chunk[n] = total;
-  if (total == 0) return;
+  b.zero_ptr = (uint4*)zero_ptr;
+  b.zero_vec16 = zero_bytes / 16;
+  if (total == 0 && zero_bytes == 0) return;
   long blocks = (total + 255) / 256;
   const long cap = (long)ctx.sm_count * 8;
   if (blocks > cap) blocks = cap;
