@@ -361,6 +361,13 @@ int egb_split_bf16(egb_context* ctx, const float* src, int64_t rows, int64_t col
   EGB_CATCH
 }
 
+int egb_gemm_plan(int64_t M, int64_t N, int64_t K, int b_mn_major, int sms, int* bn, int* cluster_k) {
+  EGB_TRY
+  if (M <= 0 || N <= 0 || K <= 0 || sms <= 0) fail(EGB_ERR_GPU, "gemm plan: sizes must be positive");
+  gemm_plan((int)M, (int)N, (int)K, b_mn_major != 0, sms, 148, 8, bn, cluster_k);
+  EGB_CATCH
+}
+
 int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_mid,
                     int64_t lda, const void* b_hi, const void* b_mid, int64_t ldb, float* C, int64_t ldc,
                     int flags, const float* bias, float alpha, int bn) {

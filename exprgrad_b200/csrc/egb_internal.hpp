@@ -203,6 +203,7 @@ void launch_gemm_bf16x3_2cta(Context& ctx, const GemmArgs& a, cudaStream_t st);
 void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* tiles);
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
+void gemm_plan(int M, int N, int K, bool b_mn, int sms, int machine_sms, int max_ck, int* bn, int* ck);  // host-only
 
 // Fused softmax + crossEntropy forward/adjoint row kernel (fused_rows.cu)
 bool softmax_xent_supported(int64_t cols);

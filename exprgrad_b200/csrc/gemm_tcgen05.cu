@@ -720,6 +720,16 @@ void choose_small_config(int M, int N, int K, int sm_count, bool b_mn, int max_c
 
 }  // namespace
 
+// What launch_gemm_bf16x3 does when the caller leaves the tile width open: `sms` SMs to plan for on a machine of
+// `machine_sms`, cluster split-K factors up to max_ck.
+void gemm_plan(int M, int N, int K, bool b_mn, int sms, int machine_sms, int max_ck, int* bn, int* ck) {
+  *bn = choose_bn(M, N, sms, b_mn);
+  *ck = 1;
+  if (((M + BM - 1) / BM) * ((N + 255) / 256) * 2 <= machine_sms) choose_small_config(M, N, K, sms, b_mn, max_ck, bn, ck);
+  const int num_kb = (K + BK - 1) / BK;
+  while (*ck > 1 && (*ck - 1) * ((num_kb + *ck - 1) / *ck) >= num_kb) *ck /= 2;
+}
+
 void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* tiles) {
   (void)K;
   *bn = choose_bn(M, N, sm_count, b_mn);
@@ -751,12 +761,12 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   p.trace = ctx.trace;
   p.trace_index = ctx.trace ? 1 + (int)(ctx.trace_next++ % (TRACE_SLOTS - 1)) : 0;
   const int sms = (a.sm_budget > 0 && a.sm_budget < ctx.sm_count) ? a.sm_budget : ctx.sm_count;
-  p.BN = a.bn > 0 ? a.bn : choose_bn(a.M, a.N, sms, a.b_mn);
+  p.BN = a.bn;
   int ck = a.cluster_k > 0 ? a.cluster_k : 1;
   static const bool no_cluster = getenv("EGB_GEMM_NO_CLUSTER_SPLITK") != nullptr;
-  if (a.bn == 0 && ((a.M + BM - 1) / BM) * ((a.N + 255) / 256) * 2 <= ctx.sm_count) {
+  if (a.bn == 0) {
     int ck_auto = 1;
-    choose_small_config(a.M, a.N, a.K, sms, a.b_mn, a.cluster_k == 1 || no_cluster ? 1 : 8, &p.BN, &ck_auto);
+    gemm_plan(a.M, a.N, a.K, a.b_mn, sms, ctx.sm_count, a.cluster_k == 1 || no_cluster ? 1 : 8, &p.BN, &ck_auto);
     if (a.cluster_k == 0) ck = ck_auto;
   }
   if (p.BN % 32 != 0 || p.BN < 32 || p.BN > 256) fail(EGB_ERR_GPU, "gemm: invalid BN %d", p.BN);

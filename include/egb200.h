@@ -147,10 +147,15 @@ int egb_kernel_run(egb_kernel* k, int work_dims, const int64_t* group_size, cons
 int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, const float* A,
                  int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int flags,
                  const float* bias, float alpha);
+/* The tile width (multiple of 32; 64 for an MN-major B) and cluster split-K factor (1, 2, 4 or 8 CTAs per output
+ * tile, reduced through distributed shared memory) the library would pick for an M x N x K contraction that may
+ * plan for `sms` SMs. Pure host arithmetic (no device needed): exposed so that the planner's cost model can be
+ * checked without a GPU. */
+int egb_gemm_plan(int64_t M, int64_t N, int64_t K, int b_mn_major, int sms, int* bn, int* cluster_k);
 /* Same contraction on operands already split into bf16 (hi, mid) planes. By default both are K-major
  * (A stored [M, lda], B stored [N, ldb], K contiguous); flags bit 16: A is MN-major (stored [K, lda], M
  * contiguous), bit 32: B is MN-major (stored [K, ldb], N contiguous). bn = 0 lets the library choose the
- * N tile. */
+ * N tile; bits 16-23 of bn force the cluster split-K factor (probing / tests). */
 int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_mid,
                     int64_t lda, const void* b_hi, const void* b_mid, int64_t ldb, float* C, int64_t ldc,
                     int flags, const float* bias, float alpha, int bn);

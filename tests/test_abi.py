@@ -41,3 +41,32 @@ def test_no_device_is_reported_not_crashed():
     if len(eg.list_devices()) == 0:
         with pytest.raises(eg.GpuError):
             eg.new_gpu_context()
+
+
+def test_contraction_planner_invariants():
+    """egb_gemm_plan is pure host arithmetic: tile width and cluster split-K factor of the contraction kernel
+    (csrc/gemm_tcgen05.cu) must always describe a launchable configuration."""
+    import ctypes
+    from exprgrad_b200._ffi import check, lib
+    shapes = [(1024, 512, 784), (1024, 512, 512), (1024, 10, 512), (512, 10, 1024), (1024, 512, 10), (512, 512, 1024),
+              (784, 512, 1024), (128, 4096, 4096), (1, 1, 1), (130, 70, 9), (300, 200, 129), (2048, 2048, 64), (64, 4000, 7000)]
+    for (m, n, k) in shapes:
+        for b_mn in (0, 1):
+            for sms in (148, 72, 16):
+                bn, ck = ctypes.c_int(0), ctypes.c_int(0)
+                check(lib.egb_gemm_plan(m, n, k, b_mn, sms, ctypes.byref(bn), ctypes.byref(ck)))
+                bn, ck = bn.value, ck.value
+                assert 32 <= bn <= 256 and bn % (64 if b_mn else 32) == 0, (m, n, k, b_mn, sms, bn)
+                assert ck in (1, 2, 4, 8)
+                tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+                kb = (k + 63) // 64
+                if ck > 1:
+                    assert tiles * ck <= sms, "clusters of a split contraction must be co-resident in one wave"
+                    assert (ck - 1) * ((kb + ck - 1) // ck) < kb, "every CTA of a cluster needs k-blocks"
+                    assert 128 * (bn + 4) * 4 <= 192 * 1024, "the partial tile must fit the operand stages"
+    # the dense-net adjoints: long reductions with few tiles are split, wide short ones are not
+    bn, ck = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib.egb_gemm_plan(512, 10, 1024, 1, 148, ctypes.byref(bn), ctypes.byref(ck)))
+    assert ck.value >= 4
+    check(lib.egb_gemm_plan(1024, 512, 10, 0, 148, ctypes.byref(bn), ctypes.byref(ck)))
+    assert ck.value == 1
