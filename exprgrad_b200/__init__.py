@@ -6,5 +6,5 @@ Importing it requires the built library - there is no CPU fallback."""
 from ._ffi import (GpuError, RuntimeError_, ShapeError, ParserError, GradientError, GeneratorError, ValueError_,
                    LIB_PATH)
 from .gpu import (GpuBuffer, GpuContext, GpuDevice, GpuTensor, alloc_tensor, list_devices, new_gpu_context)
-from .model import Model, Program, compile
+from .model import Model, Program, compile, load_model
 from . import frontend, layers, dist

@@ -8,7 +8,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import frontend
-from ._ffi import RuntimeError_, check, lib
+from ._ffi import RuntimeError_, ShapeError, ValueError_, check, lib
 from .gpu import GpuContext, new_gpu_context
 
 MAX_RANK = 8
@@ -119,11 +119,14 @@ class _StateTable:
         return [(t, self[t]) for t in self.ids()]
 
 
+MODEL_MAGIC = b"EGB200-MODEL-1\n"
+
+
 class Model:
     def __init__(self, graphs: Sequence[frontend.Fun], gpu: Optional[GpuContext] = None, seed: int = 0,
-                 strict: bool = False):
+                 strict: bool = False, program: Optional[Program] = None):
         self.ctx = gpu or new_gpu_context()
-        self.program = Program.from_graphs(graphs)
+        self.program = program if program is not None else Program.from_graphs(graphs)
         self.program.compile()
         h = ctypes.c_void_p()
         check(lib.egb_model_create(self.ctx.handle, self.program.handle, seed, ctypes.byref(h)))
@@ -240,10 +243,56 @@ class Model:
             print(f"{done.value}/{done.value}")
         return done.value
 
+    # -- checkpoint (exprgrad/io/serialize.nim:344-379: store(model) = program, params, caches)
+    def save(self, path: str):
+        """`model.save(path)`: the compiled program plus the parameter and cache tensors, read back from HBM the
+        way flushStateTensors(to = CompileCpu) does before the reference serialises (model.nim:326-345). The
+        container is this backend's own (the reference's is a Nim binary stream); the epoch is kept as well."""
+        import json
+        text = self.program.serialize().encode("utf-8")
+        tensors, blobs = [], []
+        for kind, table in (("param", self.params), ("cache", self.caches)):
+            for tid in table.ids():
+                arr = np.ascontiguousarray(table[tid], dtype=np.float32)
+                tensors.append({"id": tid, "kind": kind, "shape": list(arr.shape)})
+                blobs.append(arr.tobytes())
+        header = json.dumps({"program_bytes": len(text), "epoch": self.epoch, "tensors": tensors}).encode("utf-8")
+        with open(path, "wb") as f:
+            f.write(MODEL_MAGIC)
+            f.write(len(header).to_bytes(8, "little"))
+            f.write(header)
+            f.write(text)
+            for b in blobs:
+                f.write(b)
+
     def free(self):
         if self.handle:
             check(lib.egb_model_free(self.handle))
             self.handle = None
+
+
+def load_model(path: str, gpu: Optional[GpuContext] = None, strict: bool = False) -> Model:
+    """`loadModel[float32](path)` (exprgrad/io/serialize.nim:376-379) onto the device: parse the stored program
+    (already compiled: the passes are skipped), create the model and upload parameters and caches - the
+    flushStateTensors(to = CompileGpu) direction of model.nim:337-344."""
+    import json
+    with open(path, "rb") as f:
+        if f.read(len(MODEL_MAGIC)) != MODEL_MAGIC:
+            raise ValueError_(f"{path} is not an exprgrad_b200 model file")
+        header = json.loads(f.read(int.from_bytes(f.read(8), "little")).decode("utf-8"))
+        text = f.read(header["program_bytes"]).decode("utf-8")
+        model = Model([], gpu=gpu, strict=strict, program=Program(text))
+        for t in header["tensors"]:
+            n = int(np.prod(t["shape"])) if t["shape"] else 1
+            raw = f.read(4 * n)
+            if len(raw) != 4 * n:
+                raise ValueError_(f"{path} is truncated (tensor {t['id']})")
+            if model.tensor_shape(t["id"]) != list(t["shape"]):
+                raise ShapeError(f"tensor {t['id']} of {path} has shape {t['shape']}, the program declares "
+                                 f"{model.tensor_shape(t['id'])}")
+            model.write_tensor(t["id"], np.frombuffer(raw, np.float32).reshape(t["shape"]))
+        model.epoch = header.get("epoch", 0)
+    return model
 
 
 def compile(*graphs, gpu: Optional[GpuContext] = None, seed: int = 0, strict: bool = False) -> Model:

@@ -437,3 +437,36 @@ def test_streaming_reductions_match_numpy(ctx, rows, cols):
     got2 = pm.call("sumsq", {"a": a})
     assert abs(float(got2[0]) - want2) / want2 < 1e-5
     pm.free()
+
+
+def test_checkpoint_round_trip_with_device_resident_state(ctx, tmp_path):
+    """exprgrad/io/serialize.nim:344-379 (`save(model, path)` / `loadModel`): program + params + caches; the state
+    lives in HBM, so saving reads it back (flushStateTensors, model.nim:326-345) and loading uploads it. The
+    restored model must continue exactly like the original: adam caches and the epoch matter for that."""
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    pm = M.compile(*G.fashion_net(F, PL), gpu=ctx, seed=3)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, (8, 12, 12, 1)).astype(np.float32)
+    y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, 8)]
+    args = dict(zip(("x", "y"), (x, y)))
+    pm.fit("train", args, batch_size=4)
+    path = str(tmp_path / "model.egb")
+    pm.save(path)
+    pm2 = eg.load_model(path, gpu=ctx)
+    assert pm2.epoch == pm.epoch
+    assert pm2.params.ids() == pm.params.ids() and pm2.caches.ids() == pm.caches.ids()
+    for tid in pm.params.ids():
+        assert np.array_equal(pm.params[tid], pm2.params[tid])
+    for tid in pm.caches.ids():
+        assert np.array_equal(pm.caches[tid], pm2.caches[tid])
+    assert_close(pm2.call("predict", {"x": x}), pm.call("predict", {"x": x}), tol=1e-6, what="predict after load")
+    pm.fit("train", args, batch_size=4)
+    pm2.fit("train", args, batch_size=4)
+    for tid in pm.params.ids():
+        assert_close(pm2.params[tid], pm.params[tid], tol=1e-5, what=f"param {tid} one epoch after load")
+    with open(path, "r+b") as f:
+        f.write(b"garbage")
+    with pytest.raises(eg.ValueError_):
+        eg.load_model(path, gpu=ctx)
+    pm.free(); pm2.free()
