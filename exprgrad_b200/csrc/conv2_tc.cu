@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   uint8_t* sWmid = smem + NT * 128;
   uint8_t* sA = smem + 2 * NT * 128;          // DI_STAGES x (A_hi, A_mid), 16 KB each
   uint8_t* sRaw = sA + DI_STAGES * 2 * A_BYTES;   // RAW_STAGES raw fp32 dout tiles (bulk-copy ring)
-  float* sT = reinterpret_cast<float*>(sRaw + RAW_STAGES * RAW_BYTES);   // T tile [128][DI_TLD]
-  float* sRing = sT + TILE_P * DI_TLD + 3;                                 // three input-row segments (16-byte aligned)
+  float* sT0 = reinterpret_cast<float*>(sRaw + RAW_STAGES * RAW_BYTES);   // two T tiles [128][DI_TLD]
+  float* sRing = sT0 + 2 * TILE_P * DI_TLD + 3;                            // three input-row segments (16-byte aligned)
   sRing = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sRing) + 15) & ~uintptr_t(15));
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sRing + 3 * RING_LD);
   a_full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(a_full) + 7) & ~uintptr_t(7));
@@ -336,7 +336,9 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* raw_full = tmem_empty + 2;
   uint64_t* raw_empty = raw_full + RAW_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RAW_STAGES);
+  uint64_t* t_full = raw_empty + RAW_STAGES;   // T tile drained from TMEM -> gather warps
+  uint64_t* t_free = t_full + 2;               // gather warps done with a T tile -> drain warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_free + 2);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < DI_STAGES; ++s) {
@@ -349,7 +351,9 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 8);   // the eight epilogue warps
+      ptx::mbar_init(&tmem_empty[a], 4);   // the four drain warps
+      ptx::mbar_init(&t_full[a], 128);     // every drain thread
+      ptx::mbar_init(&t_free[a], 128);     // every gather thread
     }
     ptx::fence_barrier_init();
   }
@@ -452,78 +456,91 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
     }
   } else if (warp >= 10) {
     // ===================================================== epilogue: T -> shared memory -> col2im -> row ring -> RED
-    // Eight warps. The col2im contributions of a tile go to three input rows (y + dy); consecutive tiles of
-    // this CTA are vertically adjacent, so the rows are accumulated in a three-slot ring in shared memory
-    // and an input row is added to the image once (one 16-byte RED per four elements) when the last tile
-    // that touches it inside this CTA's run has been processed - instead of three REDs per element.
-    // Partial rows at the ends of a run simply meet the neighbouring CTA's part in memory.
-    const int et = threadIdx.x - 320;   // 0..255
-    const int q = warp & 3;
-    const bool loads_tmem = warp < 14;  // warps 10..13 cover the four TMEM lane quarters
-    for (int i = et; i < 3 * RING_LD; i += 256) sRing[i] = 0.0f;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    uint32_t it = 0;
-    for (int tile = t0; tile < t1; ++tile, ++it) {
-      const uint32_t acc = it & 1;
-      int x0;
-      long ny;
-      decode(tile, x0, ny);
-      const int y = (int)(ny % p.OH);
-      const long n = ny / p.OH;
-      {
-        // two warps per TMEM lane quarter, 16 columns (taps) each
+    // Two groups of four warps, decoupled by a double-buffered T tile: the DRAIN warps (one per TMEM lane
+    // quarter) move an accumulator into shared memory and free it for the next MMAs; the GATHER warps turn it
+    // into input-row contributions. The col2im contributions of a tile go to three input rows (y + dy);
+    // consecutive tiles of this CTA are vertically adjacent, so the rows are accumulated in a three-slot ring
+    // in shared memory and an input row is added to the image once (one 16-byte RED per four elements) when
+    // the last tile that touches it inside this CTA's run has been processed - instead of three REDs per
+    // element. Partial rows at the ends of a run simply meet the neighbouring CTA's part in memory.
+    if (warp < 14) {
+      // ---------------------------------------------------- drain warps (10..13 cover the four lane quarters)
+      const int q = warp & 3;
+      const int trow = q * 32 + lane;
+      uint32_t it = 0;
+      for (int tile = t0; tile < t1; ++tile, ++it) {
+        const uint32_t acc = it & 1, buf = it & 1;
+        int x0;
+        long ny;
+        decode(tile, x0, ny);
         ptx::mbar_wait_sleepy(&tmem_full[acc], (it >> 1) & 1, 24);
         ptx::tc_fence_after();
-        const int chalf = loads_tmem ? 0 : 16;
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT + chalf, r);
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * NT, r);
         ptx::tmem_ld_wait();
-        const int trow = q * 32 + lane;
-        const bool live = x0 + trow < p.OW;   // rows past the end of the output row carry zeros anyway
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (chalf + j < K) sT[trow * DI_TLD + chalf + j] = live ? __uint_as_float(r[j]) : 0.0f;
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // T is complete
-      constexpr int XS = TILE_P + KW - 1;   // input pixels of a row segment
-      for (int idx = et; idx < KH * XS; idx += 256) {   // one (dy, input pixel) per thread: 9 taps -> 3 channels
-        const int dy = idx / XS, X = idx - dy * XS;
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);   // the accumulator is free again
+        ptx::mbar_wait_sleepy(&t_free[buf], ((it >> 1) & 1) ^ 1, 27);   // the gather warps are done with this buffer
+        float* sT = sT0 + buf * TILE_P * DI_TLD;
+        const bool live = x0 + trow < p.OW;   // rows past the end of the output row carry zeros anyway
 #pragma unroll
-        for (int dx = 0; dx < KW; ++dx) {
-          const int xx = X - dx;
-          if (xx >= 0 && xx < TILE_P) {
-            const float* t = sT + xx * DI_TLD + (dy * KW + dx) * C;
-            s0 += t[0]; s1 += t[1]; s2 += t[2];
+        for (int j = 0; j < K; ++j) sT[trow * DI_TLD + j] = live ? __uint_as_float(r[j]) : 0.0f;
+        ptx::mbar_arrive(&t_full[buf]);
+      }
+    } else {
+      // ---------------------------------------------------- gather warps (14..17)
+      const int gt = threadIdx.x - 448;   // 0..127
+      for (int i = gt; i < 3 * RING_LD; i += 128) sRing[i] = 0.0f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      uint32_t it = 0;
+      for (int tile = t0; tile < t1; ++tile, ++it) {
+        const uint32_t buf = it & 1;
+        int x0;
+        long ny;
+        decode(tile, x0, ny);
+        const int y = (int)(ny % p.OH);
+        const long n = ny / p.OH;
+        const float* sT = sT0 + buf * TILE_P * DI_TLD;
+        ptx::mbar_wait_sleepy(&t_full[buf], (it >> 1) & 1, 28);
+        constexpr int XS = TILE_P + KW - 1;   // input pixels of a row segment
+        for (int idx = gt; idx < KH * XS; idx += 128) {   // one (dy, input pixel) per thread: 9 taps -> 3 channels
+          const int dy = idx / XS, X = idx - dy * XS;
+          float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+          for (int dx = 0; dx < KW; ++dx) {
+            const int xx = X - dx;
+            if (xx >= 0 && xx < TILE_P) {
+              const float* t = sT + xx * DI_TLD + (dy * KW + dx) * C;
+              s0 += t[0]; s1 += t[1]; s2 += t[2];
+            }
+          }
+          float* ring = sRing + ((y + dy) % 3) * RING_LD + X * C;
+          ring[0] += s0; ring[1] += s1; ring[2] += s2;
+        }
+        ptx::mbar_arrive(&t_free[buf]);                  // this thread no longer reads the T tile
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // the ring holds this tile
+        // input row y is complete as far as this run goes; at the end of a column / of the run also y+1, y+2
+        const int nflush = (y == p.OH - 1 || tile == t1 - 1) ? 3 : 1;
+        const int seg_len = min(SEG, (p.W - x0) * C);   // the segment ends with the image row
+        constexpr int Q = (SEG + 3) / 4;
+        for (int idx = gt; idx < nflush * Q; idx += 128) {
+          const int fr = idx / Q, j = (idx - fr * Q) * 4;
+          float* ring = sRing + ((y + fr) % 3) * RING_LD + j;
+          const float4 val = *reinterpret_cast<const float4*>(ring);
+          *reinterpret_cast<float4*>(ring) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (j >= seg_len) continue;
+          float* dst = p.dimg + (((size_t)n * p.H + y + fr) * p.W + x0) * C + j;
+          if (p.vec4 && j + 4 <= seg_len) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w)
+                         : "memory");
+          } else {
+            const float e[4] = {val.x, val.y, val.z, val.w};
+            for (int k2 = 0; k2 < 4 && j + k2 < seg_len; ++k2) atomicAdd(dst + k2, e[k2]);
           }
         }
-        float* ring = sRing + ((y + dy) % 3) * RING_LD + X * C;
-        ring[0] += s0; ring[1] += s1; ring[2] += s2;
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // ring slots are reused by the next tile
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the ring holds this tile
-      // input row y is complete as far as this run goes; at the end of a column / of the run also y+1, y+2
-      const int nflush = (y == p.OH - 1 || tile == t1 - 1) ? 3 : 1;
-      const int seg_len = min(SEG, (p.W - x0) * C);   // the segment ends with the image row
-      constexpr int Q = (SEG + 3) / 4;
-      for (int idx = et; idx < nflush * Q; idx += 256) {
-        const int fr = idx / Q, j = (idx - fr * Q) * 4;
-        float* ring = sRing + ((y + fr) % 3) * RING_LD + j;
-        const float4 val = *reinterpret_cast<const float4*>(ring);
-        *reinterpret_cast<float4*>(ring) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (j >= seg_len) continue;
-        float* dst = p.dimg + (((size_t)n * p.H + y + fr) * p.W + x0) * C + j;
-        if (p.vec4 && j + 4 <= seg_len) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w)
-                       : "memory");
-        } else {
-          const float e[4] = {val.x, val.y, val.z, val.w};
-          for (int k2 = 0; k2 < 4 && j + k2 < seg_len; ++k2) atomicAdd(dst + k2, e[k2]);
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // ring slots and T are reused by the next tile
     }
   }
 
@@ -770,7 +787,7 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
     EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
   }
   const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
-                      (size_t)(TILE_P * DI_TLD + 8 + 3 * RING_LD) * 4 + (2 * DI_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
+                      (size_t)(2 * TILE_P * DI_TLD + 8 + 3 * RING_LD) * 4 + (2 * DI_STAGES + 8 + 2 * RAW_STAGES) * 8 + 32;
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
