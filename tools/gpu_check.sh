@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: GPU tests, smoke, bench, ncu launch list and one full capture of the top kernel.
-# Usage (from the repo root, on the GPU box): bash tools/gpu_check.sh <tag> [kernel-regex]
+# Usage (from the repo root, on the GPU box): bash tools/gpu_check.sh <tag> [kernel-regex] [conv]
 TAG=${1:-r01}
 KREGEX=${2:-gemm_bf16x3}
 mkdir -p gpurun_out
@@ -15,4 +15,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 3 -c 2 -f -o gpurun_out/${TAG}_prof \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-conv --no-dense > gpurun_out/${TAG}_ncu_full.log 2>&1
+# optional third argument "conv": one full capture per tensor-core conv2 kernel as well
+if [ "$3" = "conv" ]; then
+  echo "== ncu full (conv2)"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv2_.*tc_kernel -c 6 -f -o gpurun_out/${TAG}_conv \
+      python bench.py --workload conv2 --no-cpu > gpurun_out/${TAG}_ncu_conv.log 2>&1
+fi
 ls -la gpurun_out | tail -20
