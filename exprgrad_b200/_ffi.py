@@ -101,6 +101,7 @@ _SIGS = {
     "egb_model_read_output": (I, [P, P, SZ]),
     "egb_model_fit": (I, [P, S, I, ctypes.POINTER(S), PP, PI, PI64, I64, PI64]),
     "egb_model_describe_plan": (I, [P, P, SZ, ctypes.POINTER(SZ)]),
+    "egb_model_plan_count": (I, [P, PI]),
     "egb_comm_unique_id": (I, [P, SZ]),
     "egb_comm_create": (I, [P, P, I, I, PP]),
     "egb_comm_destroy": (I, [P]),

@@ -317,6 +317,9 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
       m->m->last_plan = nullptr;
     }
     m->m->fuse = value != 0;
+  } else if (k == "plan_cache") {
+    if (value < 1) fail(EGB_ERR_RUNTIME, "plan_cache must be at least 1");
+    m->m->max_plans_per_target = (int)value;
   } else if (k == "epoch") {
     m->m->epoch = value;
   } else {
@@ -652,6 +655,12 @@ int egb_model_fit(egb_model* m, const char* target, int n_args, const char* cons
     row_bytes.push_back(shape_len(s) / batch_size * 4);
   }
   const int64_t batch_count = totals[0] / batch_size;
+  // every argument is sliced with viewFirst(b * batchSize, batchSize) (model.nim:443, tensors.nim:290-297): an
+  // argument with fewer rows than the batches cover would be read past its end
+  for (int i = 0; i < n_args; ++i)
+    if (totals[i] < batch_count * batch_size)
+      fail(EGB_ERR_SHAPE, "Model.fit: input %s has %lld rows, but %lld batches of %lld need %lld", names[i],
+           (long long)totals[i], (long long)batch_count, (long long)batch_size, (long long)(batch_count * batch_size));
   Plan& plan = model.get_plan(target, a.ids, a.shapes);
   bool rebind = false;
   for (auto& kv : plan.bound)
@@ -661,16 +670,93 @@ int egb_model_fit(egb_model* m, const char* target, int n_args, const char* cons
     }
   if (rebind) model.build_nodes(plan);
   model.epoch += 1;
-  for (int64_t b = 0; b < batch_count; ++b) {
-    for (int i = 0; i < n_args; ++i) {
-      auto t = plan.tensors.find(a.ids[i]);
-      if (t == plan.tensors.end() || !t->second.bytes) continue;
-      const char* src = (const char*)data[i] + (size_t)b * batch_size * row_bytes[i];
-      EGB_CUDA(cudaMemcpyAsync(t->second.ptr, src, t->second.bytes, cudaMemcpyHostToDevice, c.stream));
+  // The data set is uploaded ONCE per fit (in chunks of whole batches when it does not fit the staging budget,
+  // double buffered: the upload of chunk c+1 overlaps the training steps of chunk c) and every batch is a
+  // device-side slice of it - the device equivalent of the reference's zero-copy viewFirst. A batch reaches the
+  // plan's input tensors through a device-to-device copy on the compute stream (~1 us for a 3 MB batch), so the
+  // captured CUDA graph and its pointers stay valid; nothing crosses PCIe inside the batch loop.
+  std::vector<size_t> batch_bytes(n_args, 0), arg_off(n_args, 0);
+  size_t bytes_per_batch = 0;
+  for (int i = 0; i < n_args; ++i) {
+    auto t = plan.tensors.find(a.ids[i]);
+    if (t == plan.tensors.end() || !t->second.bytes) continue;
+    batch_bytes[i] = (size_t)batch_size * row_bytes[i];
+    arg_off[i] = bytes_per_batch;
+    bytes_per_batch += (batch_bytes[i] + 255) / 256 * 256;
+  }
+  if (batch_count > 0 && bytes_per_batch > 0) {
+    size_t free_b = 0, total_b = 0;
+    EGB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const char* budget_env = getenv("EGB_FIT_STAGE_MIB");  // (tests: forces chunked staging)
+    size_t budget = budget_env ? (size_t)atol(budget_env) << 20 : std::min<size_t>(free_b / 4, (size_t)4 << 30);
+    int64_t per_chunk = std::max<int64_t>(1, (int64_t)(budget / 2 / bytes_per_batch));
+    const bool single = per_chunk >= batch_count;
+    if (single) per_chunk = batch_count;
+    const int nbuf = single ? 1 : 2;
+    const size_t chunk_bytes = (size_t)per_chunk * bytes_per_batch;
+    char* stage[2] = {nullptr, nullptr};
+    cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    for (auto& st : c.aux_stream)
+      if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t h2d = c.aux_stream[0], comp = c.stream;
+    auto cleanup = [&]() {
+      cudaStreamSynchronize(h2d);
+      cudaStreamSynchronize(comp);
+      for (int q = 0; q < 2; ++q) {
+        if (stage[q]) cudaFree(stage[q]);
+        if (up[q]) cudaEventDestroy(up[q]);
+        if (done[q]) cudaEventDestroy(done[q]);
+      }
+    };
+    try {
+      for (int q = 0; q < nbuf; ++q) {
+        EGB_CUDA(cudaMalloc((void**)&stage[q], chunk_bytes));
+        EGB_CUDA(cudaEventCreateWithFlags(&up[q], cudaEventDisableTiming));
+        EGB_CUDA(cudaEventCreateWithFlags(&done[q], cudaEventDisableTiming));
+      }
+      // earlier work on the compute stream (parameter writes ...) is ordered before the first upload
+      EGB_CUDA(cudaEventRecord(done[0], comp));
+      EGB_CUDA(cudaStreamWaitEvent(h2d, done[0], 0));
+      int64_t chunk_index = 0;
+      for (int64_t b0 = 0; b0 < batch_count; b0 += per_chunk, ++chunk_index) {
+        const int q = (int)(chunk_index % nbuf);
+        const int64_t nb = std::min<int64_t>(per_chunk, batch_count - b0);
+        if (chunk_index >= nbuf) EGB_CUDA(cudaStreamWaitEvent(h2d, done[q], 0));  // steps of chunk c-2 are done with it
+        for (int i = 0; i < n_args; ++i) {
+          if (!batch_bytes[i]) continue;
+          // layout inside a chunk: [arg][batch] - one contiguous upload per argument
+          const char* src = (const char*)data[i] + (size_t)b0 * batch_bytes[i];
+          EGB_CUDA(cudaMemcpyAsync(stage[q] + arg_off[i] * (size_t)per_chunk, src, (size_t)nb * batch_bytes[i],
+                                   cudaMemcpyHostToDevice, h2d));
+        }
+        EGB_CUDA(cudaEventRecord(up[q], h2d));
+        EGB_CUDA(cudaStreamWaitEvent(comp, up[q], 0));
+        for (int64_t b = 0; b < nb; ++b) {
+          for (int i = 0; i < n_args; ++i) {
+            if (!batch_bytes[i]) continue;
+            auto t = plan.tensors.find(a.ids[i]);
+            EGB_CUDA(cudaMemcpyAsync(t->second.ptr, stage[q] + arg_off[i] * (size_t)per_chunk + (size_t)b * batch_bytes[i],
+                                     batch_bytes[i], cudaMemcpyDeviceToDevice, comp));
+          }
+          model.run(plan);
+        }
+        EGB_CUDA(cudaEventRecord(done[q], comp));
+      }
+    } catch (...) {
+      cleanup();
+      throw;
     }
-    model.run(plan);
+    cleanup();
+  } else {
+    for (int64_t b = 0; b < batch_count; ++b) model.run(plan);
   }
   if (batches_run) *batches_run = batch_count;
+  EGB_CATCH
+}
+
+int egb_model_plan_count(egb_model* m, int* count) {
+  EGB_TRY
+  *count = (int)m->m->plans.size();
   EGB_CATCH
 }
 

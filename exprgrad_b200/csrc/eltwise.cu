@@ -15,7 +15,8 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t value, size
   for (size_t j = (n4 << 2) + i; j < n; j += stride) dst[j] = value;
 }
 // U(lo, hi) fill for TensorRandom tensors (model.nim:286-294, 310-314: refilled on every call).
-// Counter-based: element i of call c is a hash of (seed, c, i), so a run is reproducible.
+// Counter-based: element i of tensor t in call c is a hash of (seed, c, t, i), so a run is reproducible and
+// every random tensor of a call draws its own sequence (the reference calls newRandTensor per tensor).
 __global__ void fill_uniform_kernel(float* __restrict__ dst, size_t n, float lo, float hi, uint64_t seed,
                                     uint64_t counter) {
   pdl_launch_dependents();
@@ -33,8 +34,15 @@ __global__ void fill_uniform_kernel(float* __restrict__ dst, size_t n, float lo,
 }  // namespace
 
 void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi, uint64_t seed, uint64_t counter,
-                         cudaStream_t st) {
+                         uint64_t tensor, cudaStream_t st) {
   if (n == 0) return;
+  // the tensor id selects an independent stream: folded into the seed with a full-avalanche mix
+  {
+    uint64_t z = seed + 0x9e3779b97f4a7c15ull * (tensor + 1);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    seed = z ^ (z >> 31);
+  }
   size_t blocks = (n + 255) / 256;
   const size_t cap = (size_t)ctx.sm_count * 8;
   if (blocks > cap) blocks = cap;

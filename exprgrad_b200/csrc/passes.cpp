@@ -496,7 +496,7 @@ void generate(Program& prog) {
             grad_kernels.insert(grad_kernels.end(), ks.begin(), ks.end());
           }
         }
-        prog.grad_tensors[target.name] = grad_tensors;
+        for (auto& gt : grad_tensors) prog.grad_tensors[target.name][gt.first] = gt.second;  // (several backwards() per target merge)
         target.kernels.erase(target.kernels.begin() + it);
         target.kernels.insert(target.kernels.begin() + it, grad_kernels.begin(), grad_kernels.end());
         it += grad_kernels.size();

@@ -315,7 +315,26 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
     for (int k = 0; k < nk; ++k) t->kernels.push_back(read_kernel(r));
     prog->targets.push_back(t);
   }
-  r.expect("end");
+  // optional: the loss-gradient table recorded by `generate` (target -> (tensor, gradient tensor) pairs). A
+  // compiled program that was serialised and parsed again (checkpoints, Model.save / load_model) keeps it, so the
+  // data-parallel runtime still finds the parameter-gradient bucket. Programs compiled by passes.nim do not
+  // carry it; the runtime then derives the bucket from the optimizer kernels (runtime.cpp).
+  std::string tail = r.next();
+  if (tail == "grads") {
+    const int ng = r.i32();
+    for (int i = 0; i < ng; ++i) {
+      r.expect("G");
+      const std::string name = r.str();
+      const int np = r.i32();
+      auto& table = prog->grad_tensors[name];
+      for (int q = 0; q < np; ++q) {
+        const int t = r.i32();
+        table[t] = r.i32();
+      }
+    }
+    tail = r.next();
+  }
+  if (tail != "end") fail(EGB_ERR_PARSER, "program text: expected 'end', got '%s'", tail.c_str());
   if (prog->compiled) {
     for (size_t i = 0; i < prog->tensors.size(); ++i) {
       const TensorDef& t = prog->tensors[i];
@@ -503,6 +522,21 @@ std::string serialize_program(const Program& prog) {
       w.nl();
     }
     for (auto& k : t->kernels) write_kernel(w, *k);
+  }
+  if (!prog.grad_tensors.empty()) {
+    w.tok("grads");
+    w.i((int64_t)prog.grad_tensors.size());
+    w.nl();
+    for (auto& kv : prog.grad_tensors) {
+      w.tok("G");
+      w.str(kv.first);
+      w.i((int64_t)kv.second.size());
+      for (auto& pr : kv.second) {
+        w.i(pr.first);
+        w.i(pr.second);
+      }
+      w.nl();
+    }
   }
   w.tok("end");
   w.nl();

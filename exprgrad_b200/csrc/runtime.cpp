@@ -736,6 +736,13 @@ void build_nodes_impl(Model& m, Plan& plan) {
 
 void Model::build_nodes(Plan& plan) { build_nodes_impl(*this, plan); }
 
+void Model::evict_plan(size_t index) {
+  if (index >= plans.size()) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);  // its graph / arena may still be in flight
+  if (last_plan == plans[index].get()) last_plan = nullptr;
+  plans.erase(plans.begin() + (long)index);
+}
+
 Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& ids,
                       const std::vector<std::vector<int64_t>>& in_shapes) {
   Target* target = prog->find_target(target_name);
@@ -744,7 +751,21 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   for (size_t i = 0; i < ids.size(); ++i) sig.emplace_back(ids[i], in_shapes[i]);
   std::sort(sig.begin(), sig.end());
   for (auto& p : plans)
-    if (p->target_name == target_name && p->input_sig == sig) return *p;
+    if (p->target_name == target_name && p->input_sig == sig) {
+      p->last_used = ++use_clock;
+      return *p;
+    }
+  // bound the cache: drop the least recently used plan(s) of this target
+  for (;;) {
+    int count = 0, lru = -1;
+    for (size_t i = 0; i < plans.size(); ++i)
+      if (plans[i]->target_name == target_name) {
+        ++count;
+        if (lru < 0 || plans[i]->last_used < plans[lru]->last_used) lru = (int)i;
+      }
+    if (count < std::max(1, max_plans_per_target) || lru < 0) break;
+    evict_plan((size_t)lru);
+  }
 
   // ---- run-time shape inference (passes.nim:1386-1436), once per input-shape signature
   ShapeTable inputs;
@@ -992,6 +1013,11 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   cursor += plane_bytes;
   plan->arena_bytes = std::max<size_t>(cursor, 256);
   cudaError_t e = cudaMalloc((void**)&plan->arena, plan->arena_bytes);
+  if (e != cudaSuccess && !plans.empty()) {
+    cudaGetLastError();  // out of memory: give back every cached plan and try once more
+    while (!plans.empty()) evict_plan(plans.size() - 1);
+    e = cudaMalloc((void**)&plan->arena, plan->arena_bytes);
+  }
   if (e != cudaSuccess)
     fail(EGB_ERR_GPU, "cudaMalloc of %zu bytes for target %s failed: %s", plan->arena_bytes, target_name.c_str(),
          cudaGetErrorString(e));
@@ -1004,6 +1030,7 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
     plan->tensors[id] = t;
   }
   Plan* raw = plan.get();
+  raw->last_used = ++use_clock;
   build_nodes(*raw);
   plans.push_back(std::move(plan));
   return *raw;
@@ -1016,7 +1043,7 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
   switch (n.kind) {
     case Node::MEMSET: EGB_CUDA(cudaMemsetAsync(n.ptr, 0, n.bytes, st)); break;
     case Node::RANDOM:
-      launch_fill_uniform(ctx, (float*)n.ptr, n.bytes / 4, n.lo, n.hi, m.seed, m.rng_counter, st);
+      launch_fill_uniform(ctx, (float*)n.ptr, n.bytes / 4, n.lo, n.hi, m.seed, m.rng_counter, (uint64_t)n.tensor, st);
       break;
     case Node::SPLIT:
       if (!n.split_jobs.empty()) {

@@ -116,6 +116,7 @@ struct Plan {
   bool graph_valid = false;
   int64_t epoch_built = -1;
   uint64_t runs = 0;
+  uint64_t last_used = 0;             // Model::use_clock stamp of the last get_plan hit (LRU eviction)
   size_t launches_per_run = 0;
   ~Plan();
 };
@@ -141,7 +142,14 @@ struct Model {
   // (An earlier global-memory variant - RED.ADD partial tiles + last-arriver epilogue - lost on the dense
   // step, 115.6 vs 111.4 us, and was removed.)
   bool splitk = true;
+  // Plan cache: one plan (arena, operand planes, CUDA graph) per target x input-shape signature. Bounded: at most
+  // `max_plans_per_target` signatures per target stay resident, the least recently used one is dropped first
+  // (the reference frees and reallocates when a shape changes, model.nim:311-317); an allocation failure evicts
+  // every other plan before giving up.
   std::vector<std::unique_ptr<Plan>> plans;
+  int max_plans_per_target = 4;
+  uint64_t use_clock = 0;
+  void evict_plan(size_t index);
   Plan* last_plan = nullptr;
   CommHooks* comm = nullptr;
   ~Model();
@@ -161,7 +169,7 @@ int interp_reduction_splits(const IpProgram& prog, int pb, int rb, bool strict, 
 void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs, int max_slots, int64_t rows,
                             cudaStream_t st);
 void launch_fill_uniform(Context& ctx, float* dst, size_t n, float lo, float hi, uint64_t seed, uint64_t counter,
-                         cudaStream_t st);
+                         uint64_t tensor, cudaStream_t st);
 
 // passes.cpp helpers reused by the planner
 int eval_index_instrs(const std::vector<Instr>& instrs, const ShapeTable& shapes, std::map<int, int64_t>& regs,

@@ -170,6 +170,11 @@ class Model:
         check(lib.egb_model_tensor_device_ptr(self.handle, tensor_id, ctypes.byref(p)))
         return p.value or 0
 
+    def plan_count(self) -> int:
+        n = ctypes.c_int(0)
+        check(lib.egb_model_plan_count(self.handle, ctypes.byref(n)))
+        return n.value
+
     def describe_plan(self) -> str:
         need = ctypes.c_size_t(0)
         check(lib.egb_model_describe_plan(self.handle, None, 0, ctypes.byref(need)))

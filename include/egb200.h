@@ -231,10 +231,17 @@ int egb_model_call_read(egb_model* model, const char* target, int n_args, const 
 /* readOutput (exprgrad/model.nim:370-376): blocking D2H of the last call's output tensor. */
 int egb_model_read_output(egb_model* model, void* dst, size_t bytes);
 /* Model.fit (exprgrad/model.nim:413-454): shapes inferred once with dim 0 = batch_size, epoch += 1,
- * one plan replay per full batch of host data (trailing partial batch dropped). */
+ * one plan replay per full batch (trailing partial batch dropped). The host data set is uploaded once per
+ * call (double-buffered chunks of whole batches when it exceeds the staging budget) and every batch is a
+ * device-side slice of it - the device form of viewFirst (exprgrad/tensors.nim:290-297); no host-to-device
+ * copy happens inside the batch loop. EGB_ERR_SHAPE if an argument has fewer rows than the batches cover.
+ * Blocking. */
 int egb_model_fit(egb_model* model, const char* target, int n_args, const char* const* names,
                   const void* const* data, const int* ranks, const int64_t* dims, int64_t batch_size,
                   int64_t* batches_run);
+/* Number of launch plans (one per target x input-shape signature, model.nim:347-355 re-allocates per call
+ * instead) the model currently caches; bounded by the "plan_cache" option (least recently used evicted). */
+int egb_model_plan_count(egb_model* model, int* count);
 /* Human-readable node list of the most recent call's launch plan. */
 int egb_model_describe_plan(egb_model* model, char* buf, size_t cap, size_t* needed);
 

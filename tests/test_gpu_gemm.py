@@ -79,6 +79,32 @@ def test_full_size_checksum_properties(ctx):
             assert np.array_equal(c2, 2 * c)
 
 
+@pytest.mark.parametrize("seed,lo", [(0, 0.0), (1, -1.0)])
+def test_full_size_matches_oracle_elementwise(ctx, seed, lo):
+    """BASELINE config 2 at full size, element by element: the whole 4096^3 product through the public model
+    API (benchmarks/matmul/matmul_gpu.nim:28-36, inputs as :69-70 plus the mixed-sign variant) against the
+    oracle's row-split loop nest on all host cores (about a second per product)."""
+    import oracle as o
+    from oracle import layers as OL
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, layers as PL
+    import graphs as G
+    n = 4096
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(lo, 1, (n, n)).astype(np.float32)
+    b = rng.uniform(lo, 1, (n, n)).astype(np.float32)
+    ref = o.compile(*G.matmul(o, OL, ct="threads")).call("c", {"a": a, "b": b})
+    pm = eg.compile(*G.matmul(F, PL), gpu=ctx)
+    got = pm.call("c", {"a": a, "b": b})
+    e = assert_close(got, ref, what=f"4096^3 U({lo},1) full product")
+    print(f"4096^3 U({lo},1): normalised max error vs oracle {e:.2e}")
+    # the streamed host-buffer form of the same call (what bench.py's e2e leg times)
+    out = np.empty((n, n), np.float32)
+    pm.call("c", {"a": a, "b": b}, out=out)
+    assert_close(out, ref, what="4096^3 streamed call")
+    pm.free()
+
+
 def _bf16_planes(x):
     """hi = bf16(x), mid = bf16(x - hi) with round-to-nearest-even (what split.cu computes), as uint16."""
     def rn(v):

@@ -229,6 +229,137 @@ def test_conv2_full_size_properties(ctx):
     pm.free()
 
 
+def test_conv2_full_size_matches_oracle(ctx):
+    """BASELINE config 4 at full size, element by element (benchmarks/conv2/conv2.nim:337-338 input ranges):
+    the forward convolution, d_filters and d_images of the whole 256x224x224x3 batch against the oracle's
+    threaded loop nests. The adjoint targets are compared on their own outputs; their loss = sum(out^2)
+    makes d_out = 2 * out, so all three tensor-core kernels see full-size data."""
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    import oracle as o
+    from oracle import layers as OL
+    filters = (64, 3, 3, 3)
+    w = np.random.default_rng(1).uniform(-2, 2, filters).astype(np.float32)
+    img = np.random.default_rng(0).uniform(0, 1, (256, 224, 224, 3)).astype(np.float32)
+    om = o.compile(*G.conv2_net(o, OL, ct="threads", filters=filters), seed=0)
+    om.params[sorted(om.params)[0]][...] = w
+    pm = M.compile(*G.conv2_net(F, PL, filters=filters), gpu=ctx, seed=0)
+    pm.params[pm.params.ids()[0]] = w
+    for target in ("conv", "dw", "dimg"):
+        ref = om.call(target, {"img": img})
+        got = pm.call(target, {"img": img})
+        assert "conv conv2" in pm.describe_plan()
+        e = assert_close(got, ref, what=f"full-size {target}")
+        print(f"conv2 256x224x224x3 {target}: normalised max error vs oracle {e:.2e}")
+        del ref, got
+    pm.free()
+
+
+def _small_layer_net(d, L, ct="gpu"):
+    """conv -> tanh -> avgpool2 -> upsample2 -> reshape -> dense -> sigmoid, binaryCrossEntropy, SGD:
+    the layers of exprgrad/layers/dnn.nim:35-40, 73-88 and base.nim:60-64 that no other graph uses."""
+    x = d.input("x", [-1, 10, 10, 2]); y = d.input("y", [-1, 6])
+    h = L.avgpool2(L.tanh(L.conv2_layer(x, 2, 3, 3, 4)))       # [N,8,8,4] -> [N,4,4,4]
+    h = L.upsample2(h)                                          # [N,8,8,4]
+    p = L.sigmoid(L.dense(h.reshape([-1, 256]), 256, 6))
+    loss = L.binary_cross_entropy(p, y)
+    return [h.target("features", ct), p.target("predict", ct), loss.target("loss", ct),
+            loss.backprop(L.gradient_descent(0.05)).target("train", ct)]
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_avgpool_upsample_tanh_bce_match_oracle(ctx, strict):
+    """'next' row f2: avgpool2, upsample2 (IndexDiv gather forward, scatter adjoint), tanh and
+    binaryCrossEntropy with their derive()d adjoints, forward values and three SGD steps against the oracle."""
+    import oracle as o
+    from oracle import layers as OL
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    om = o.compile(*_small_layer_net(o, OL), seed=4)
+    pm = M.compile(*_small_layer_net(F, PL), gpu=ctx, seed=4, strict=strict)
+    assert sorted(om.params) == pm.params.ids()
+    sync_params(om, pm)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (9, 10, 10, 2)).astype(np.float32)
+    y = rng.integers(0, 2, (9, 6)).astype(np.float32)
+    before = [om.params[t].copy() for t in sorted(om.params)]
+    for target, args in (("features", {"x": x}), ("predict", {"x": x}), ("loss", {"x": x, "y": y})):
+        got, ref = pm.call(target, args), om.call(target, args)
+        assert got.shape == ref.shape
+        assert_close(got, ref, tol=1e-5, what=f"{target} (strict={strict})")
+    for _ in range(3):
+        om.apply("train", {"x": x, "y": y})
+        pm.apply("train", {"x": x, "y": y})
+    for tid, v in zip(sorted(om.params), before):
+        assert_close(pm.params[tid], om.params[tid], what=f"param tensor{tid - 1} after 3 steps")
+        assert_close(pm.params[tid] - v, om.params[tid] - v, tol=2e-3, what=f"update of tensor{tid - 1}")
+    pm.free()
+
+
+def test_fit_slices_on_device_and_checks_rows(ctx):
+    """Model.fit (model.nim:413-454) uploads the data set once and slices batches on the device: the result
+    equals one apply per viewFirst slice, also when the data set is staged in several chunks, and an
+    argument with too few rows is refused (EGB_ERR_SHAPE) instead of being read past its end."""
+    import os
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    sizes = (20, 16, 5)
+    x, y, params = G.dense_inputs(70, sizes)
+    outs = []
+    for mode in ("apply", "fit", "fit-chunked"):
+        pm = M.compile(*G.dense_net(F, PL, sizes), gpu=ctx, seed=0)
+        for tid, v in zip(pm.params.ids(), params):
+            pm.params[tid] = v
+        if mode == "apply":
+            for b in range(70 // 16):
+                pm.apply("train", {"x": x[b * 16:(b + 1) * 16], "y": y[b * 16:(b + 1) * 16]})
+        else:
+            if mode == "fit-chunked":
+                os.environ["EGB_FIT_STAGE_MIB"] = "0"    # one batch per staging chunk, double buffered
+            try:
+                assert pm.fit("train", {"x": x, "y": y}, batch_size=16) == 4
+            finally:
+                os.environ.pop("EGB_FIT_STAGE_MIB", None)
+            assert pm.epoch == 1
+        outs.append([pm.params[t] for t in pm.params.ids()])
+        if mode == "fit":
+            with pytest.raises(eg.ShapeError):
+                pm.fit("train", {"x": x, "y": y[:40]}, batch_size=16)
+        pm.free()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+
+
+def test_random_tensors_of_one_call_are_independent(ctx):
+    """Every TensorRandom of a call draws its own sequence (newRandTensor per tensor, model.nim:310-314):
+    two random tensors of the same shape must differ, and each is refilled on the next call."""
+    from exprgrad_b200 import frontend as F, model as M
+    x = F.input("x")
+    a, b = F.rand(x, (0.0, 1.0)), F.rand(x, (0.0, 1.0))
+    r = F.Fun(); it = F.Iter("it")
+    r.raw[it] += a.raw[it] - b.raw[it]
+    r.copy_shape(x)
+    pm = M.compile(r.target("d", "gpu"), gpu=ctx, seed=11)
+    d1 = pm.call("d", {"x": np.zeros((64, 256), np.float32)})
+    d2 = pm.call("d", {"x": np.zeros((64, 256), np.float32)})
+    assert (d1 != 0).mean() > 0.99 and abs(d1.mean()) < 0.02 and abs(d1.std() - np.sqrt(1 / 6)) < 0.02
+    assert not np.array_equal(d1, d2)
+    pm.free()
+
+
+def test_plan_cache_is_bounded(ctx):
+    """One plan (arena + graph) per input-shape signature, least recently used dropped beyond the bound."""
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    pm = M.compile(*G.matmul(F, PL), gpu=ctx)
+    pm.set_option("plan_cache", 2)
+    rng = np.random.default_rng(2)
+    for rep in range(2):
+        for n in (8, 16, 24, 40, 8):
+            a = rng.uniform(-1, 1, (n, n)).astype(np.float32); b = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+            assert_close(pm.call("c", {"a": a, "b": b}), a.astype(np.float64) @ b.astype(np.float64), what=f"n={n}")
+    assert pm.plan_count() <= 2
+    pm.free()
+
+
 def test_fashion_net_adam_fit(ctx):
     """'next' rows: conv + leakyRelu + maxpool2 (customGrad) + reshape + dense + softmax + adam with
     caches and epoch(), trained with Model.fit over two epochs."""
