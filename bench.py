@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py - headline measurement of the exprgrad hot path on B200 (contract in the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload matmul|dense]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload auto|matmul|dense|conv2|eltwise]
 
-Workloads (BASELINE.json `configs`), both driven through the public model API
-(exprgrad_b200.compile(...).call/apply == exprgrad's compile[T] / Model.call / Model.apply):
-  matmul  configs[1]  benchmarks/matmul: c[y,x] ++= a[y,it]*b[it,x], 4096x4096x4096 fp32 - the primary
-                      JSON line (metric matmul GFLOP/s = 2MNK / t). A single contraction does not
-                      shard: --gpus N runs N independent replicas ("replicas only").
-  dense   configs[2]/[4]  784->512->512->10 dense+relu, softmax+crossEntropy, SGD: one full train step
-                      (fwd + bwd + update) on a batch of 1024 per GPU, data parallel over N GPUs with one
-                      NCCL all-reduce of the parameter-gradient bucket (metric train samples/s).
-                      Reported inside the same JSON line under "dense_train" (or as the primary line
-                      with --workload dense).
-  conv2   configs[3]  NHWC 256x224x224x3 images, 64 3x3x3 filters: forward, d_filters and d_images kernels
-                      (HBM-bound; reported under "conv2_fwd_bwd" at N=1, or with --workload conv2).
+Workloads (BASELINE.json `configs`), all driven through the public model API
+(exprgrad_b200.compile(...).call/apply/fit == exprgrad's compile[T] / Model.call / Model.apply / Model.fit):
+  matmul   configs[1]  benchmarks/matmul: c[y,x] ++= a[y,it]*b[it,x], 4096x4096x4096 fp32
+                       (metric matmul GFLOP/s = 2MNK / t). A single contraction does not shard: replicas only.
+  dense    configs[2]/[4]  784->512->512->10 dense+relu, softmax+crossEntropy, SGD: one full train step
+                       (fwd + bwd + update) on a batch of 1024 per GPU, data parallel over N GPUs: the
+                       parameter-gradient bucket is exchanged by one fused peer-memory kernel over NVLink
+                       (reduce-scatter + all-gather + SGD update), metric train samples/s, weak scaling;
+                       plus the strong-scaling point (global batch 8192 fixed, 8192/N per GPU).
+  conv2    configs[3]  NHWC 256x224x224x3 images, 64 3x3x3 filters: forward, d_filters and d_images (HBM-bound).
+  eltwise  the HBM-streaming elementwise / optimizer kernels the north star names (relu and its adjoint, bias add,
+           gradientDescent, adam) on 512 MiB tensors.
 A "step" is one pass of the hot path over one batch of synthetic input.
+
+Which workload is the primary JSON line (`--workload auto`): the configuration BASELINE.json's metric is quoted
+on when it fits one GPU - the 4096^3 matmul - on a single-GPU box; on a multi-GPU box (more than one GPU visible,
+or --gpus N > 1) the workload that actually shards, the data-parallel dense train step at EVERY N including 1, so
+that the per-N values of one scaling run are one metric and their ratio is the data-parallel curve. The other
+workloads ride along as extra keys of the same line (`dense_train`, `matmul_replicas`, `conv2_fwd_bwd`, `eltwise`).
 
 `value`    device-resident throughput (inputs already in HBM when the timed region starts)
 `e2e`      the same through the public API with HOST buffers: H2D of the step's inputs from pinned
@@ -24,11 +31,16 @@ A "step" is one pass of the hot path over one batch of synthetic input.
 `cpu_baseline` / `--impl reference`: the oracle's restatement of the reference's CPU (LLVM-JIT) path on
            this box's host cores (the reference itself needs Nim + LLVM 13, absent from this image).
 """
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -49,6 +61,35 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def visible_gpus():
+    """GPUs this process could use (no torch / CUDA initialisation: also called by the CPU arm)."""
+    env = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if env is not None and env.strip() != "":
+        return len([x for x in env.split(",") if x.strip()])
+    try:
+        r = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30)
+        return sum(1 for line in r.stdout.splitlines() if line.startswith("GPU "))
+    except (OSError, subprocess.TimeoutExpired):
+        return 0
+
+
+def resolve_workload(args, world):
+    if args.workload != "auto":
+        return args.workload
+    return "dense" if (world > 1 or args.gpus > 1 or visible_gpus() > 1) else "matmul"
+
+
+def oracle_threads(n=None):
+    """All host cores for the oracle's OpenMP loop nests, whatever OMP_NUM_THREADS the launcher exported."""
+    import ctypes
+    n = n or os.cpu_count() or 1
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+    return n
 
 
 # ------------------------------------------------------------------------------ clocks sampler
@@ -76,22 +117,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.perf_counter(), line.strip()))
 
-    def mark(self):
-        return time.perf_counter()
-
-    def stop(self, t0=None, t1=None):
+    def window(self, t0=None, t1=None):
+        """Clocks seen between two perf_counter stamps (all samples so far when none fall inside)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [s for (t, s) in self.samples if t0 is None or (t0 <= t <= t1 + 0.03)]
-        for s in inside or [s for (_, s) in self.samples]:
+        snap = list(self.samples)
+        inside = [s for (t, s) in snap if t0 is None or (t0 - 0.02 <= t <= t1 + 0.03)]
+        for s in inside or [s for (_, s) in snap]:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -103,7 +137,17 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "power_w_max": max(power) if power else None, "samples": len(sm)}
+                "reasons": sorted(reasons), "power_w_max": max(power) if power else None, "samples": len(sm),
+                "samples_inside_timed_region": len(inside)}
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
 
 
 class Timer:
@@ -118,7 +162,7 @@ class Timer:
             self.dist.barrier()
         self.ctx.synchronize()
 
-    def run(self, fn, steps, warmup, sampler=None):
+    def run(self, fn, steps, warmup):
         from exprgrad_b200 import gpu as G
         for _ in range(warmup):
             fn()
@@ -145,36 +189,49 @@ MATMUL_N = 4096
 MATMUL_NAME = "benchmarks/matmul c[y,x] ++= a[y,it]*b[it,x] 4096x4096x4096 fp32 (BASELINE configs[1])"
 
 
+def matmul_config(world):
+    return {"workload": MATMUL_NAME, "inputs": "A,B ~ U(0,1) seed 0 (matmul_gpu.nim:69-70)",
+            "parallelism": f"replicas only x{world}" if world > 1 else "1 GPU",
+            "l2": "fp32 operands + bf16 planes + output = 320 MiB touched per step, larger than the 126 MB L2",
+            "numerics": "fp32 in / fp32 out; device: bf16x3 split on tcgen05 (3 MMA passes); bar 1e-4 normalised max error",
+            "api": "compile(c.target('c')).apply('c', {a, b}) == exprgrad Model.apply"}
+
+
 def matmul_inputs(n=MATMUL_N):
     rng = np.random.default_rng(0)  # U(0,1) like benchmarks/matmul/matmul_gpu.nim:69-70
     return rng.uniform(0, 1, (n, n)).astype(np.float32), rng.uniform(0, 1, (n, n)).astype(np.float32)
 
 
-def cpu_matmul_sample(budget_s=12.0, steps=1):
-    """Oracle (port of the reference's CPU path) on a bounded sample of the 4096^3 workload: the first
-    `rows` rows of A against the full B (the reference parallelises over rows, so GFLOP/s on a row block
-    is representative of the whole product)."""
+def cpu_matmul_sample(budget_s=2.5, steps=1, warmup=1, keep_result=False):
+    """Oracle (port of the reference's CPU path) on the 4096^3 workload: the whole product when one step fits
+    `budget_s`, else the first `rows` rows of A against the full B (the reference parallelises over rows, so
+    GFLOP/s on a row block is representative of the whole product)."""
     import oracle as o
     from oracle import layers as OL
+    cores = oracle_threads()
     n = MATMUL_N
     a, b = matmul_inputs()
     m = o.compile(*GR.matmul(o, OL, ct="threads"))
-    cores = os.cpu_count() or 1
-    rows = max(cores, 16)
-    m.call("c", {"a": a[:rows], "b": b})  # warm-up + page-in
-    t0 = time.perf_counter(); m.call("c", {"a": a[:rows], "b": b}); t1 = time.perf_counter() - t0
-    rows = int(min(n, max(rows, budget_s / max(t1 / rows, 1e-9))))
-    rows = max(rows - rows % cores, cores)
+    probe = max(cores, 16) * 8
+    m.call("c", {"a": a[:probe], "b": b})  # page-in
+    t0 = time.perf_counter(); m.call("c", {"a": a[:probe], "b": b}); t1 = time.perf_counter() - t0
+    rows = n if t1 / probe * n <= budget_s else int(budget_s / max(t1 / probe, 1e-9))
+    rows = max(min(n, rows) - min(n, rows) % cores, cores)
+    out = None
+    for _ in range(warmup):
+        out = m.call("c", {"a": a[:rows], "b": b})
     times = []
     for _ in range(steps):
-        t0 = time.perf_counter(); m.call("c", {"a": a[:rows], "b": b}); times.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); out = m.call("c", {"a": a[:rows], "b": b}); times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
-    return {"value": 2.0 * rows * n * n / t / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-            "sample": f"first {rows} of {n} rows of A x full B (K=N={n}), oracle C loops y||,it,x "
-                      f"(gcc -O3 -march=native -ffp-contract=off), {cores} OpenMP threads, {t:.2f} s per step"}, t
+    cb = {"value": 2.0 * rows * n * n / t / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+          "sample": f"{'the whole product: all' if rows == n else 'first'} {rows} of {n} rows of A x full B (K=N={n}), "
+                    f"oracle C loops y||,it,x (gcc -O3 -march=native -ffp-contract=off), {cores} OpenMP threads, "
+                    f"{t:.2f} s per step, {steps} timed steps"}
+    return cb, t, (out if keep_result else None), rows
 
 
-def run_matmul(args, ctx, timer, rank, world, sampler):
+def run_matmul(args, ctx, timer, rank, world, sampler, cpu_check=True):
     import exprgrad_b200 as eg
     from exprgrad_b200 import frontend as F, gpu as G, layers as PL
     peaks = load_peaks()
@@ -195,9 +252,9 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
 
     step_device(); ctx.synchronize()
     l0 = ctx.launch_count
-    ms, span = timer.run(step_device, args.steps, args.warmup, sampler)
+    ms, span = timer.run(step_device, args.steps, args.warmup)
     launches = (ctx.launch_count - l0) * args.steps // (args.steps + args.warmup)
-    clocks = sampler.stop(*span) if sampler else None
+    clocks = sampler.window(*span) if sampler else None
 
     G.set_timing(ctx, True)  # dominant kernel, live, same stream, identical region
     for _ in range(args.steps):
@@ -212,9 +269,6 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
         e2e_ms = float("nan")
     else:
         e2e_ms, _ = timer.run(step_e2e, e2e_steps, 2)
-    # parity spot check of what was just timed (row sums in fp64, 1e-4 bar)
-    rows = a[:8].astype(np.float64) @ b.astype(np.float64).sum(1)
-    err = float(np.abs(hc[:8].astype(np.float64).sum(1) - rows).max() / np.abs(rows).max())
 
     flop = 2.0 * n * n * n
     ms_step = ms / args.steps
@@ -229,15 +283,10 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
         "metric": "matmul_gflops", "value": world * flop / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": MATMUL_NAME, "inputs": "A,B ~ U(0,1) seed 0, resident in HBM",
-                   "parallelism": f"replicas only x{world}" if world > 1 else "1 GPU",
-                   "l2": "fp32 operands + bf16 planes + output = 320 MiB touched per step, larger than the 126 MB L2",
-                   "numerics": f"bf16x3 split on tcgen05 (3 MMA passes); row-sum check vs fp64 {err:.1e} (bar 1e-4)",
-                   "api": "exprgrad_b200.compile(c.target('c')).apply('c', {a, b}) -> egb_model_call"},
+        "config": matmul_config(world),
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_2cta_kernel (cta_group::2 tcgen05, 256x256 pair tiles)", "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "frac_of_burst_peak": achieved / peaks["bf16_burst"], "frac_of_sustained_peak": achieved / peaks["bf16_sustained"],
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_2cta_kernel (cta_group::2 tcgen05, 256x256 pair tiles)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": 390.0e6, "traffic_source": "profiles/r01l_ncu_full.txt (dram read+write per launch: 336 + 54 MB)",
                      "passes": passes, "algorithmic_tflops": flop / t_kernel / 1e12, "kernel_ms": t_kernel * 1e3,
                      "kernel_share_of_step": k_ms / max(all_ms, 1e-9),
@@ -251,6 +300,17 @@ def run_matmul(args, ctx, timer, rank, world, sampler):
                        "2 MiB row blocks; split + GEMM per block; D2H of each c block - copies and tensor cores overlap on three streams"},
         "clocks": clocks,
     }
+    # parity of what was just timed: the e2e result (host buffer hc) against the oracle's product, element by element
+    if rank == 0 and cpu_check and not args.no_cpu:
+        cb, _, ref, rows = cpu_matmul_sample(keep_result=True)
+        out["cpu_baseline"] = cb
+        err = float(np.abs(hc[:rows].astype(np.float64) - ref.astype(np.float64)).max() / np.abs(ref).max())
+        out["numerics"] = {"normalised_max_error_vs_oracle": err, "rows_compared": int(rows), "of_rows": n, "bar": 1e-4,
+                           "what": "result of the timed e2e call vs the oracle product the cpu_baseline leg computed"}
+    else:
+        rows64 = a[:8].astype(np.float64) @ b.astype(np.float64).sum(1)
+        err = float(np.abs(hc[:8].astype(np.float64).sum(1) - rows64).max() / np.abs(rows64).max())
+        out["numerics"] = {"row_sum_error_vs_fp64": err, "bar": 1e-4, "what": "8 row sums (cpu leg skipped)"}
     model.free()
     for t in (da, db):
         t.buffer.dealloc()
@@ -263,31 +323,45 @@ DENSE_BATCH = 1024
 DENSE_NAME = "synthetic fashion_mnist dense net 784->512->512->10, relu, softmax+crossEntropy, SGD train step (BASELINE configs[2]/[4])"
 DENSE_FLOP_PER_SAMPLE = 3286237184 / 1024      # fwd + dW + dX (layer-1 dX is dead)
 DENSE_BYTES_PER_STEP = 38.7e6                  # minimal-fusion HBM traffic at batch 1024
+DENSE_BUCKET_BYTES = 669706 * 4                # parameter-gradient bucket exchanged per step
 
 
-def cpu_dense_sample(steps=5):
+def dense_config(world, batch=DENSE_BATCH):
+    return {"workload": DENSE_NAME, "batch_per_gpu": batch, "global_batch": batch * world,
+            "parallelism": (f"dp{world}: batch rows sharded, 669706-float gradient bucket averaged across ranks every step"
+                            if world > 1 else "1 GPU"),
+            "inputs": "x ~ U(0,1) seed 0, one-hot labels seed 1, params U(-0.1,0.1) seed 2, rate 0.01",
+            "l2": "working set (~40 MB) is L2-resident by design; every step rewrites all activations and parameters",
+            "numerics": "fp32 tensors; device contractions bf16x3 on tcgen05, everything else fp32; bar 1e-4 normalised max error"}
+
+
+def cpu_dense_sample(steps=5, warmup=1, batch=DENSE_BATCH):
     import oracle as o
     from oracle import layers as OL
+    cores = oracle_threads()
     m = o.compile(*GR.dense_net(o, OL, DENSE_SIZES, ct="threads"))
-    x, y, params = GR.dense_inputs(DENSE_BATCH, DENSE_SIZES)
+    x, y, params = GR.dense_inputs(batch, DENSE_SIZES)
     for tid, v in zip(sorted(m.params), params):
         m.params[tid][...] = v
-    m.apply("train", {"x": x, "y": y})
+    for _ in range(max(warmup, 1)):
+        m.apply("train", {"x": x, "y": y})
     times = []
     for _ in range(steps):
         t0 = time.perf_counter(); m.apply("train", {"x": x, "y": y}); times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
-    cores = os.cpu_count() or 1
-    return {"value": DENSE_BATCH / t, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} full train steps at batch {DENSE_BATCH}, oracle C loop nests (row-split OpenMP, {cores} threads), "
+    return {"value": batch / t, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} full train steps at batch {batch}, oracle C loop nests (row-split OpenMP, {cores} threads), "
                       f"{t * 1e3:.1f} ms per step"}, t
 
 
-def run_dense(args, ctx, timer, rank, world, comm, sampler=None):
+def run_dense(args, ctx, timer, rank, world, comm, sampler=None, batch=DENSE_BATCH, light=False, exact=False):
+    """One data-parallel train step per `step`: every rank holds `batch` rows of the global batch. `exact`: time
+    exactly --steps steps after --warmup warm-up steps (the primary line); otherwise at least 200 / 10."""
     import exprgrad_b200 as eg
     from exprgrad_b200 import dist as D, frontend as F, gpu as G, layers as PL
+    from exprgrad_b200._ffi import check, lib
     peaks = load_peaks()
-    B = DENSE_BATCH
+    B = batch
     model = eg.compile(*GR.dense_net(F, PL, DENSE_SIZES), gpu=ctx, seed=0)
     x, y, params = GR.dense_inputs(B * world, DENSE_SIZES)
     for tid, v in zip(model.params.ids(), params):
@@ -302,7 +376,6 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None):
     dev_args, host_args = {"x": dx, "y": dy}, {"x": hx, "y": hy}
     last_bias = model.params.ids()[-1]
     hb = G.pinned_empty((DENSE_SIZES[-1],))
-    from exprgrad_b200._ffi import check, lib
 
     def step_device():
         model.apply("train", dev_args, sync=False)
@@ -311,43 +384,45 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None):
         model.apply("train", host_args, sync=False)
         check(lib.egb_model_read_tensor(model.handle, last_bias, hb.ctypes.data, hb.nbytes))  # blocking D2H
 
-    steps = max(args.steps, 200)
+    steps = args.steps if exact else max(args.steps, 100 if light else 200)
+    warm = args.warmup if exact else max(args.warmup, 10)
     step_device(); ctx.synchronize()
     l0 = ctx.launch_count
-    ms, span = timer.run(step_device, steps, max(args.warmup, 10), sampler)
-    launches = (ctx.launch_count - l0) // (steps + max(args.warmup, 10))
-    clocks = sampler.stop(*span) if sampler else None
+    ms, span = timer.run(step_device, steps, warm)
+    launches = (ctx.launch_count - l0) // (steps + warm)
+    clocks = sampler.window(*span) if sampler else None
     plan = model.describe_plan()
+    ms_step = ms / steps
+    flop = DENSE_FLOP_PER_SAMPLE * B
+    out = {"metric": "dense_train_samples_per_s", "value": world * B / (ms_step * 1e-3), "unit": "samples/s",
+           "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": dense_config(world, B), "gpu_launches": int(launches)}
+    if light:
+        out["clocks"] = clocks
+        model.free()
+        return out
 
     # kernel-class breakdown, eager launches with events (graphs cannot carry the per-launch events)
+    reps = 20
     G.set_timing(ctx, True)
-    for _ in range(20):
+    for _ in range(reps):
         step_device()
     classes = {}
-    for c in ("gemm", "split", "interp", "fill", "other"):
+    for c in ("gemm", "split", "interp", "eltwise", "reduce", "fill", "exchange", "other"):
         t, k = G.kernel_time(ctx, c)
         if k:
-            classes[c] = {"ms_per_step": t / 20, "launches_per_step": k / 20}
+            classes[c] = {"ms_per_step": t / reps, "launches_per_step": k / reps}
     all_ms, _ = G.kernel_time(ctx, "all")
     G.set_timing(ctx, False)
 
     e2e_steps = 100
     e2e_ms, _ = timer.run(step_e2e, e2e_steps, 5)
-    ms_step = ms / steps
-    flop = DENSE_FLOP_PER_SAMPLE * B
     t_tensor = 3 * flop / (peaks["bf16_sustained"] * 1e12)
-    t_hbm = DENSE_BYTES_PER_STEP / (peaks["hbm_gbs"] * 1e9)
+    t_hbm = DENSE_BYTES_PER_STEP * (B / DENSE_BATCH) / (peaks["hbm_gbs"] * 1e9)
     g = classes.get("gemm", {"ms_per_step": 0.0, "launches_per_step": 0})
-    out = {
-        "metric": "dense_train_samples_per_s", "value": world * B / (ms_step * 1e-3), "unit": "samples/s",
-        "n_gpus": world, "steps": steps, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": DENSE_NAME, "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}: batch rows sharded, ncclAllReduce(avg) of the 669706-float gradient bucket"
-                                  if world > 1 else "1 GPU",
-                   "l2": "working set (~40 MB) is L2-resident by design; every step rewrites all activations and parameters",
-                   "numerics": "contractions bf16x3 on tcgen05; everything else fp32"},
-        "gpu_launches": int(launches), "plan_nodes": plan.count("\n  "), "cuda_graph": "graph yes" in plan,
+    out.update({
+        "plan_nodes": plan.count("\n  #"), "cuda_graph": "graph yes" in plan,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel (8 contractions per step; cluster split-K, fused epilogues)",
                      "achieved": 3 * flop / max(g["ms_per_step"], 1e-9) / 1e9, "peak": peaks["bf16_sustained"],
                      "unit": "TFLOP/s", "frac": 3 * flop / max(g["ms_per_step"], 1e-9) / 1e9 / peaks["bf16_sustained"],
@@ -355,13 +430,20 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None):
                      "step_roofline_us": {"tensor_3pass": t_tensor * 1e6, "hbm_min_fusion": t_hbm * 1e6},
                      "step_frac_of_roofline": max(t_tensor, t_hbm) / (ms_step * 1e-3),
                      "peak_source": peaks["source"] + ", sustained bf16 figure (kernels timed inside a long step)",
-                     "kernel_classes": classes, "eager_ms_per_step": all_ms / 20},
+                     "kernel_classes": classes, "eager_ms_per_step": all_ms / reps},
         "e2e": {"value": world * B / (e2e_ms / e2e_steps * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": int(hx.nbytes + hy.nbytes), "d2h_bytes_per_step": int(hb.nbytes),
                 "ms_per_step": e2e_ms / e2e_steps,
                 "api": "model.apply('train', {x, y}) with pinned host arrays + read of the updated output bias"},
         "clocks": clocks,
-    }
+    })
+    if world > 1:
+        ex = classes.get("exchange")
+        out["exchange"] = {"kernel": "dp_exchange_sgd_kernel: reduce-scatter + all-gather of the gradient bucket through "
+                                     "peer memory (NVLink 5 / NVSwitch) fused with the SGD update",
+                           "nvlink_bytes_per_rank_per_step": {"read_from_peers": int(DENSE_BUCKET_BYTES * (world - 1) / world),
+                                                              "written_to_peers": int(DENSE_BUCKET_BYTES * (world - 1) / world)},
+                           "eager_ms_per_step": ex["ms_per_step"] if ex else None}
     model.free()
     return out
 
@@ -372,8 +454,28 @@ CONV_FIL = (64, 3, 3, 3)
 CONV_NAME = "benchmarks/conv2: NHWC 256x224x224x3 images, 64 3x3x3 filters, valid, fp32 forward + d_filters + d_images (BASELINE configs[3])"
 
 
-def run_conv2(args, ctx, timer, rank, world):
-    """Times the three conv2 kernels inside their targets (forward; loss=sum(out^2) -> d_filters, d_images)."""
+def cpu_conv2_sample(images=4):
+    """Oracle loop nests (threads) for forward, d_filters and d_images on the first `images` images."""
+    import oracle as o
+    from oracle import layers as OL
+    cores = oracle_threads()
+    om = o.compile(*GR.conv2_net(o, OL, ct="threads", filters=CONV_FIL), seed=0)
+    om.params[sorted(om.params)[0]][...] = np.random.default_rng(1).uniform(-2, 2, CONV_FIL).astype(np.float32)
+    img = np.random.default_rng(0).uniform(0, 1, (images,) + CONV_IMG[1:]).astype(np.float32)
+    t = {}
+    for target in ("conv", "dw", "dimg"):
+        om.call(target, {"img": img})
+        t0 = time.perf_counter(); om.call(target, {"img": img}); t[target] = time.perf_counter() - t0
+    # the adjoint targets recompute the forward pass and the loss adjoint; count each kernel once
+    total = t["conv"] + (t["dw"] - t["conv"]) + (t["dimg"] - t["conv"])
+    return {"value": images / max(total, 1e-9), "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"first {images} of {CONV_IMG[0]} images: oracle forward {t['conv']:.2f} s, dw target {t['dw']:.2f} s, "
+                      f"dimg target {t['dimg']:.2f} s ({cores} OpenMP threads; only `image`/`chan` loops of d_images are independent)"}
+
+
+def run_conv2(args, ctx, timer, rank, world, cpu=True):
+    """Times the conv2 targets (forward; loss=sum(out^2) -> d_filters, d_images) and, inside them, the three
+    convolution kernels with their own CUDA events (timing classes conv_fwd / conv_dw / conv_dimg)."""
     import exprgrad_b200 as eg
     from exprgrad_b200 import frontend as F, gpu as G, layers as PL
     peaks = load_peaks()
@@ -389,70 +491,157 @@ def run_conv2(args, ctx, timer, rank, world):
     dimg.write(himg)
     out_bytes, in_bytes = n * oh * ow * f * 4, n * h * wd * c * 4
     flop = 2.0 * n * oh * ow * f * kh * kw * c
-    res = {}
     steps = max(3, min(args.steps, 10))
-    for target, alg_bytes in (("conv", in_bytes + out_bytes), ("dw", in_bytes + out_bytes), ("dimg", out_bytes + in_bytes)):
+    targets, kern = {}, {}
+    for target, cls in (("conv", "conv_fwd"), ("dw", "conv_dw"), ("dimg", "conv_dimg")):
         fn = lambda: model.apply(target, {"img": dimg}, sync=False)
         fn(); ctx.synchronize()
-        ms, _ = timer.run(fn, steps, 2)
+        ms, _ = timer.run(fn, steps, 3)
         G.set_timing(ctx, True)
         for _ in range(steps):
             fn()
-        k_ms, k_n = G.kernel_time(ctx, "conv")
-        all_ms, _ = G.kernel_time(ctx, "all")
+        k_ms, k_n = G.kernel_time(ctx, cls)
+        all_ms, all_n = G.kernel_time(ctx, "all")
         G.set_timing(ctx, False)
-        # every target re-runs the forward convolution first; the kernel of interest is the last conv launch
-        per_target = int(round(k_n / steps))
-        res[target] = {"target_ms": ms / steps, "conv_kernels_per_run": per_target, "conv_kernels_ms": k_ms / steps,
-                       "all_kernels_ms": all_ms / steps, "algorithmic_bytes": alg_bytes}
-    fwd_ms = res["conv"]["conv_kernels_ms"]
-    dw_ms = res["dw"]["conv_kernels_ms"] - fwd_ms
-    di_ms = res["dimg"]["conv_kernels_ms"] - fwd_ms
-    e2e_fn = lambda: model.call("conv", {"img": himg})
+        targets[target] = {"target_ms": ms / steps, "launches_per_run": all_n / steps, "all_kernels_ms": all_ms / steps}
+        kern[{"conv": "forward", "dw": "d_filters", "dimg": "d_images"}[target]] = k_ms / max(k_n, 1)
+    total = sum(kern.values())
+    hdw, hdi = np.empty(CONV_FIL, np.float32), G.pinned_empty(CONV_IMG)
+
+    def e2e_fn():
+        model.call("dw", {"img": himg}, out=hdw)
+        model.call("dimg", {"img": himg}, out=hdi)
     e2e_ms, _ = timer.run(e2e_fn, 2, 1)
-    kern = {"forward": fwd_ms, "d_filters": dw_ms, "d_images": di_ms}
-    total = fwd_ms + dw_ms + di_ms
+    alg = in_bytes + out_bytes
     out = {"metric": "conv2_fwd_bwd_images_per_s", "value": world * n / (total * 1e-3), "unit": "images/s",
-           "n_gpus": world, "ms_per_step": total, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
-           "data": "synthetic", "config": {"workload": CONV_NAME, "parallelism": f"replicas x{world}"},
+           "n_gpus": world, "steps": steps, "ms_per_step": total, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+           "data": "synthetic", "config": {"workload": CONV_NAME, "parallelism": f"replicas x{world}" if world > 1 else "1 GPU",
+                                           "l2": "3.2 GB output / output gradient per kernel, far larger than the L2"},
+           "value_definition": "images / (forward + d_filters + d_images kernel time), each kernel timed by its own CUDA events "
+                               "inside its target (timing classes conv_fwd / conv_dw / conv_dimg); whole-target times are in `targets`",
            "kernels_ms": kern,
            "roofline": {"bound": "hbm", "kernel": "conv2_fwd_tc_kernel / conv2_dw_tc_kernel / conv2_dimg_tc_kernel (tcgen05 implicit GEMM)",
-                        "achieved": 3 * (in_bytes + out_bytes) / (total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": 3 * (in_bytes + out_bytes) / (total * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                        "per_kernel_frac": {k: (in_bytes + out_bytes) / (v * 1e-3) / 1e9 / peaks["hbm_gbs"] for k, v in kern.items()},
+                        "achieved": 3 * alg / (total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": 3 * alg / (total * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                        "algorithmic_bytes_per_kernel": alg,
+                        "per_kernel_frac": {k: alg / (v * 1e-3) / 1e9 / peaks["hbm_gbs"] for k, v in kern.items()},
                         "tflops_fp32": {k: flop / (v * 1e-3) / 1e12 for k, v in kern.items()},
                         "peak_source": peaks["source"]},
-           "targets": res,
-           "e2e": {"value": world * n / (e2e_ms / 2 * 1e-3), "unit": "images/s (forward only)", "h2d_bytes_per_step": in_bytes,
-                   "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms / 2,
-                   "api": "model.call('conv', {img}) with a pinned host image batch; D2H of the 3.2 GB output"}}
+           "targets": targets,
+           "e2e": {"value": world * n / (e2e_ms / 2 * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 2 * in_bytes,
+                   "d2h_bytes_per_step": in_bytes + int(hdw.nbytes), "ms_per_step": e2e_ms / 2,
+                   "api": "model.call('dw', {img}, out) + model.call('dimg', {img}, out) with a pinned host image batch: "
+                          "forward + loss adjoint + d_filters, then forward + loss adjoint + d_images, gradients read back"}}
+    if cpu and rank == 0 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_conv2_sample()
     model.free()
     dimg.buffer.dealloc()
     return out
 
 
+# ------------------------------------------------------------------------------ streaming elementwise / optimizer kernels
+ELT_N = 1 << 27   # 512 MiB per fp32 tensor
+ELT_NAME = ("HBM-streaming elementwise / optimizer kernels on 512 MiB tensors: relu, relu adjoint, bias add, gradientDescent, adam "
+            "(layers/dnn.nim:22-27, layers/base.nim:37-53)")
+
+
+def _elt_graphs(F, PL, rows, cols):
+    n = rows * cols
+    x = F.input("x", [rows, cols]); g = F.input("g", [rows, cols])
+    relu = PL.relu(x)
+    radj = F.Fun(); it = F.Iter("it")
+    radj.raw[it] += F.select(x.raw[it] >= 0.0, g.raw[it], 0.0)      # derive() of relu (passes.nim:471-476)
+    radj.copy_shape(x)
+    b = F.param([cols], name="bias")
+    biased = F.Fun(); i, j = F.Iter("y"), F.Iter("x")
+    biased[i, j] += x[i, j]
+    i, j = F.Iter("y"), F.Iter("x")
+    biased[i, j] += b[j]
+    gflat = F.input("gflat", [n])
+    p1 = F.param([n], name="p_sgd"); e1 = F.Fun("Effect", effect=p1); PL.gradient_descent(0.01)(e1, gflat)
+    p2 = F.param([n], name="p_adam"); e2 = F.Fun("Effect", effect=p2); PL.adam(0.01)(e2, gflat)
+    return [relu.target("relu", "gpu"), radj.target("relu_adjoint", "gpu"), biased.target("bias_add", "gpu"),
+            e1.target("sgd", "gpu"), e2.target("adam", "gpu")]
+
+
+def run_eltwise(args, ctx, timer, rank, world):
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, gpu as G, layers as PL
+    peaks = load_peaks()
+    rows, cols = 16384, ELT_N // 16384
+    n = rows * cols
+    model = eg.compile(*_elt_graphs(F, PL, rows, cols), gpu=ctx, seed=0)
+    model.set_option("epoch", 1)
+    dxt, dgt = eg.alloc_tensor(ctx, (rows, cols)), eg.alloc_tensor(ctx, (rows, cols))
+    chunk = np.random.default_rng(0).uniform(-1, 1, (256, cols)).astype(np.float32)
+    big = np.tile(chunk, (rows // 256, 1))
+    dxt.write(big); dgt.write(big[::-1].copy())
+    dgflat = dgt.view((n,))
+    # bytes each target's kernels move (4 B x elements read + written)
+    cases = [("relu", {"x": dxt}, 8), ("relu_adjoint", {"x": dxt, "g": dgt}, 12), ("bias_add", {"x": dxt}, 16),
+             ("sgd", {"gflat": dgflat}, 12), ("adam", {"gflat": dgflat}, 40)]
+    steps = max(5, min(args.steps, 20))
+    res = {}
+    for target, targs, bpe in cases:
+        fn = lambda: model.apply(target, targs, sync=False)
+        fn(); ctx.synchronize()
+        ms, _ = timer.run(fn, steps, 3)
+        G.set_timing(ctx, True)
+        for _ in range(steps):
+            fn()
+        k_ms, k_n = G.kernel_time(ctx, "eltwise")
+        all_ms, all_n = G.kernel_time(ctx, "all")
+        G.set_timing(ctx, False)
+        plan = model.describe_plan()
+        gbs = bpe * n / (k_ms / steps * 1e-3) / 1e9
+        res[target] = {"target_ms": ms / steps, "kernels_ms": k_ms / steps, "launches": k_n / steps, "other_launches": (all_n - k_n) / steps,
+                       "algorithmic_bytes": bpe * n, "achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"],
+                       "specialised": "interp" not in plan}
+    # spot check: relu of the resident tensor
+    y = model.call("relu", {"x": dxt})
+    assert np.array_equal(y[:256], np.maximum(chunk, 0)), "relu result mismatch"
+    total_bytes = sum(v["algorithmic_bytes"] for v in res.values())
+    total_ms = sum(v["kernels_ms"] for v in res.values())
+    dom = res["sgd"]
+    out = {"metric": "eltwise_stream_gbs", "value": total_bytes / (total_ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
+           "steps": steps, "ms_per_step": total_ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+           "config": {"workload": ELT_NAME, "elements": n, "l2": "every tensor is 512 MiB, four times the L2"},
+           "roofline": {"bound": "hbm", "kernel": "elt_stream_kernel<sgd-axpy> (P += (0 - g) * rate, base.nim:37-38)",
+                        "achieved": dom["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dom["frac"],
+                        "traffic": None, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "peak_source": peaks["source"]},
+           "per_target": res}
+    model.free()
+    for t in (dxt, dgt):
+        t.buffer.dealloc()
+    return out
+
+
 # ------------------------------------------------------------------------------ entry points
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, workload):
+    """The reference's CPU path (restated by the oracle) on this box's host cores: W warm-up + K timed steps of
+    the same workload and config as our arm. Rank 0 only."""
     if rank != 0:
         return
-    if args.workload == "dense":
-        cb, t = cpu_dense_sample(steps=max(1, min(args.steps, 10)))
-        metric, name = "dense_train_samples_per_s", DENSE_NAME
+    if workload == "dense":
+        batch = DENSE_BATCH * world
+        cb, t = cpu_dense_sample(steps=args.steps, warmup=args.warmup, batch=batch)
+        metric, config = "dense_train_samples_per_s", dense_config(world)
+    elif workload == "conv2":
+        cb = cpu_conv2_sample()
+        t = 4 / cb["value"]
+        metric, config = "conv2_fwd_bwd_images_per_s", {"workload": CONV_NAME, "parallelism": "1 GPU",
+                                                         "l2": "3.2 GB output / output gradient per kernel, far larger than the L2"}
     else:
-        cb, t = cpu_matmul_sample(budget_s=8.0, steps=max(1, min(args.steps, 5)))
-        metric, name = "matmul_gflops", MATMUL_NAME
+        # keep the whole --steps K --warmup W run within a few minutes: one step is the whole product when it
+        # takes <= 2.5 s on this box, otherwise a row block of it
+        cb, t, _, _ = cpu_matmul_sample(budget_s=2.5, steps=args.steps, warmup=args.warmup)
+        metric, config = "matmul_gflops", matmul_config(world)
     out = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": cb["unit"], "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": name,
-                      "note": "reference CPU path restated by the oracle (Nim + LLVM 13 are not in this image), all host "
-                              "cores; runs on rank 0 only"},
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+           "note": "reference CPU path restated by the oracle (Nim + LLVM 13 are not in this image), all host cores; rank 0 only",
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if args.workload == "matmul" and not args.no_dense:
-        cd, td = cpu_dense_sample(steps=5)
-        out["dense_train"] = {"metric": "dense_train_samples_per_s", "value": cd["value"], "unit": cd["unit"],
-                              "ms_per_step": td * 1e3, "cpu_baseline": cd}
     print(json.dumps(out), flush=True)
 
 
@@ -462,19 +651,24 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="matmul", choices=["matmul", "dense", "conv2"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="auto", choices=["auto", "matmul", "dense", "conv2", "eltwise"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense_train block of the matmul line")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used for ncu launch lists of the timed region)")
-    ap.add_argument("--no-conv", action="store_true", help="skip the conv2_fwd_bwd block of the matmul line")
+    ap.add_argument("--no-conv", action="store_true", help="skip the conv2_fwd_bwd block")
+    ap.add_argument("--no-eltwise", action="store_true", help="skip the eltwise block")
+    ap.add_argument("--no-extras", action="store_true", help="primary workload only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = resolve_workload(args, world)
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, workload)
         return
     args.warmup = max(args.warmup, 3)
+    if args.no_extras:
+        args.no_dense = args.no_conv = args.no_eltwise = True
     import exprgrad_b200 as eg
     from exprgrad_b200 import dist as D
     dist = None
@@ -490,29 +684,42 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    if args.workload == "matmul":
+    if workload == "matmul":
         out = run_matmul(args, ctx, timer, rank, world, sampler)
         if not args.no_dense:
-            out["dense_train"] = run_dense(args, ctx, timer, rank, world, comm)
-        if not args.no_conv and world == 1:
+            out["dense_train"] = run_dense(args, ctx, timer, rank, world, comm, sampler)
+            if rank == 0 and not args.no_cpu:
+                out["dense_train"]["cpu_baseline"], _ = cpu_dense_sample()
+        if world == 1 and not args.no_conv:
             out["conv2_fwd_bwd"] = run_conv2(args, ctx, timer, rank, world)
-    elif args.workload == "conv2":
+        if world == 1 and not args.no_eltwise:
+            out["eltwise"] = run_eltwise(args, ctx, timer, rank, world)
+    elif workload == "dense":
+        out = run_dense(args, ctx, timer, rank, world, comm, sampler, exact=True)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            out["cpu_baseline"], _ = cpu_dense_sample()
+        if not args.no_extras:
+            # strong-scaling point of BASELINE configs[4]: global batch 8192 fixed, 8192 / N rows per GPU
+            if 8192 % world == 0:
+                strong = run_dense(args, ctx, timer, rank, world, comm, sampler, batch=8192 // world, light=True)
+                strong["scaling"] = "strong"
+                out["dense_strong"] = strong
+            mm = run_matmul(args, ctx, timer, rank, world, sampler, cpu_check=False)
+            out["matmul_replicas"] = {k: mm[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "numerics")}
+    elif workload == "conv2":
         out = run_conv2(args, ctx, timer, rank, world)
         out["warmup"] = args.warmup
         out["vs_baseline"] = None
-        out["clocks"] = sampler.stop() if sampler else None
+        out["clocks"] = sampler.window() if sampler else None
     else:
-        out = run_dense(args, ctx, timer, rank, world, comm, sampler)
+        out = run_eltwise(args, ctx, timer, rank, world)
         out["warmup"] = args.warmup
         out["vs_baseline"] = None
+        out["clocks"] = sampler.window() if sampler else None
+        out["gpu_launches"] = None
+    if sampler:
+        sampler.stop()
     if rank == 0:
-        if world == 1 and not args.no_cpu:
-            if args.workload == "matmul":
-                out["cpu_baseline"], _ = cpu_matmul_sample()
-                if "dense_train" in out:
-                    out["dense_train"]["cpu_baseline"], _ = cpu_dense_sample()
-            elif args.workload == "dense":
-                out["cpu_baseline"], _ = cpu_dense_sample()
         print(json.dumps(out), flush=True)
     if comm is not None:
         comm.destroy()

@@ -83,6 +83,7 @@ _SIGS = {
     "egb_program_compile": (I, [P]),
     "egb_program_serialize": (I, [P, P, SZ, ctypes.POINTER(SZ)]),
     "egb_program_describe": (I, [P, S, P, SZ, ctypes.POINTER(SZ)]),
+    "egb_program_classify": (I, [P, S, I, ctypes.POINTER(S), PI, PI64, P, SZ, ctypes.POINTER(SZ)]),
     "egb_program_free": (I, [P]),
     "egb_program_tensor_count": (I, [P, PI]),
     "egb_program_tensor_info": (I, [P, I, PI, PI, PI64, P, SZ]),

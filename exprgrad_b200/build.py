@@ -22,7 +22,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
           "--expt-relaxed-constexpr", "-I", os.path.join(os.path.dirname(HERE), "include")]
 # Kernels that restate the reference's strict fp32 arithmetic (separate fmul + fadd, llvmgen.nim:219-221)
 # must not be contracted into FMAs.
-STRICT = {"interp.cu", "eltwise.cu"}
+STRICT = {"interp.cu", "eltwise.cu", "eltwise_stream.cu"}
 
 
 def _sources():

@@ -92,6 +92,48 @@ int egb_program_describe(egb_program* p, const char* target, char* buf, size_t c
   EGB_CATCH
 }
 
+// Which device kernel family runs each IR kernel of a target at the given input shapes (host only: shape
+// inference + the structural matchers the planner uses). One line per kernel:
+//   "<index>: contraction M N K transA transB" | "conv2 forward|d_filters|d_images" |
+//   "eltwise <form> n=<elements> [row=<len>]" | "generic"
+int egb_program_classify(egb_program* p, const char* target, int n_args, const char* const* names, const int* ranks,
+                         const int64_t* dims, char* buf, size_t cap, size_t* needed) {
+  EGB_TRY
+  Program& prog = *p->p;
+  if (!prog.compiled) compile_program(prog);
+  Target* t = prog.find_target(target);
+  if (!t) fail(EGB_ERR_RUNTIME, "%s is not a target of the model", target);
+  Args a = resolve_args(prog, n_args, names, ranks, dims);
+  ShapeTable in;
+  for (size_t i = 0; i < a.ids.size(); ++i) in[a.ids[i]] = a.shapes[i];
+  ShapeTable shapes = infer_shapes(prog, *t, in);
+  for (int id : prog.params) shapes[id] = prog.tdef(id).shape;
+  for (int id : prog.caches) shapes[id] = prog.tdef(id).shape;
+  std::string s;
+  for (size_t i = 0; i < t->kernels.size(); ++i) {
+    const Kernel& k = *t->kernels[i];
+    GemmPattern g;
+    ConvPattern cv;
+    EltSpec es;
+    s += std::to_string(i) + ": ";
+    if (match_gemm(k, shapes, g)) {
+      s += "contraction " + std::to_string(g.M) + " " + std::to_string(g.N) + " " + std::to_string(g.K) + " " +
+           (g.trans_a ? "T" : "N") + (g.trans_b ? "T" : "N");
+    } else if (match_conv2(k, shapes, cv)) {
+      static const char* kinds[] = {"forward", "d_filters", "d_images"};
+      s += std::string("conv2 ") + kinds[(int)cv.kind];
+    } else if (match_eltwise(k, shapes, es)) {
+      s += std::string("eltwise ") + elt_kind_name(es.kind) + " n=" + std::to_string(es.n);
+      if (es.kind == ELT_BIAS_ROW) s += " row=" + std::to_string(es.row);
+    } else {
+      s += "generic";
+    }
+    s += "\n";
+  }
+  copy_out(s, buf, cap, needed);
+  EGB_CATCH
+}
+
 int egb_program_free(egb_program* p) {
   EGB_TRY
   delete p;
@@ -310,6 +352,13 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
       m->m->last_plan = nullptr;
     }
     m->m->rowchain = value != 0;
+  } else if (k == "eltwise") {
+    if (m->m->eltwise != (value != 0)) {
+      EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
+      m->m->plans.clear();
+      m->m->last_plan = nullptr;
+    }
+    m->m->eltwise = value != 0;
   } else if (k == "fuse") {
     if (m->m->fuse != (value != 0)) {
       EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
@@ -769,7 +818,7 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
     s += "target " + p.target_name + ": " + std::to_string(p.nodes.size()) + " nodes, arena " +
          std::to_string(p.arena_bytes) + " bytes (zeroed per run: " + std::to_string(p.zero_bytes) + "), graph " +
          (p.graph_valid ? "yes" : "no") + "\n";
-    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain", "softmax_xent"};
+    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain", "softmax_xent", "eltwise"};
     auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
       for (auto x : a)
         for (auto y : b)
@@ -798,6 +847,7 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
              ((n.gemm.flags & GEMM_ACCUMULATE) ? " +=" : " =");
       s += "\n";
     }
+    for (auto& note : p.notes) s += "  note: " + note + "\n";
   }
   copy_out(s, buf, cap, needed);
   EGB_CATCH

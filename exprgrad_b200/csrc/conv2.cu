@@ -457,7 +457,7 @@ void launch_conv2_dw(Context& ctx, const float* img, const float* dout, float* d
   const size_t smem = stage > red ? stage : red;
   dim3 grid(ctx.sm_count * 3, ((K + 31) / 32) * ((F + FC - 1) / FC));
   EGB_CUDA(cudaFuncSetAttribute(conv2_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  Launch l(ctx, KC_CONV, st);
+  Launch l(ctx, KC_CONV_DW, st);
   launch_kernel(ctx, conv2_dw_kernel, grid, dim3(256), smem, st, img, dout, dw, d, txw);
 }
 
@@ -472,7 +472,7 @@ void launch_conv2_dimg(Context& ctx, const float* dout, const float* w, float* d
   const int tq = quads_per_block(W, 16);
   const size_t smem = ((size_t)(KH + 1) * (tq * 4 + KW - 1) * FC + (size_t)KH * KW * FC * MAX_CC) * sizeof(float);
   dim3 grid((W + tq * 4 - 1) / (tq * 4), (H + ROWS_DIMG - 1) / ROWS_DIMG, N);
-  Launch l(ctx, KC_CONV, st);
+  Launch l(ctx, KC_CONV_DIMG, st);
 #define EGB_DIMG(KWT)                                                                                       \
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_kernel<KWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
   launch_kernel(ctx, conv2_dimg_kernel<KWT>, grid, dim3(tq * 16), smem, st, dout, w, dimg, d, accumulate ? 1 : 0, tq);

@@ -783,7 +783,7 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
   // the tiles overlap (rows by dy, columns by the halo) and meet through RED: start from zero unless the
   // caller accumulates onto existing data
   if (!accumulate) {
-    Launch lz(ctx, KC_CONV, st);   // counted (and timed) with the kernel it belongs to
+    Launch lz(ctx, KC_CONV_DIMG, st);   // counted (and timed) with the kernel it belongs to
     EGB_CUDA(cudaMemsetAsync(dimg, 0, (size_t)N * H * W * 3 * sizeof(float), st));
   }
   const size_t smem = 1024 + 2 * 32 * 128 + (size_t)DI_STAGES * 2 * A_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
@@ -791,7 +791,7 @@ void launch_conv2_dimg_tc(Context& ctx, const float* dout, const float* w, float
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dimg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  Launch l(ctx, KC_CONV, st);
+  Launch l(ctx, KC_CONV_DIMG, st);
   launch_kernel(ctx, conv2_dimg_tc_kernel, dim3(grid), dim3(DI_THREADS), smem, st, p);
   EGB_CUDA(cudaGetLastError());
 }
@@ -817,7 +817,7 @@ void launch_conv2_dw_tc(Context& ctx, const float* img, const float* dout, float
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  Launch l(ctx, KC_CONV, st);
+  Launch l(ctx, KC_CONV_DW, st);
   launch_kernel(ctx, conv2_dw_tc_kernel, dim3(grid), dim3(DW_THREADS), smem, st, p);
   EGB_CUDA(cudaGetLastError());
 }

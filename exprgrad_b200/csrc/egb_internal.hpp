@@ -78,7 +78,8 @@ constexpr int TRACE_SLOTS = 4096;
 
 // Kernel classes for the timing interface (egb_context_kernel_time).
 enum KernelClass { KC_GEMM = 0, KC_SPLIT = 1, KC_FILL = 2, KC_INTERP = 3, KC_REDUCE = 4, KC_ELTWISE = 5,
-                   KC_CONV = 6, KC_OTHER = 7, KC_COUNT = 8 };
+                   KC_CONV = 6 /* conv2 forward */, KC_OTHER = 7, KC_CONV_DW = 8, KC_CONV_DIMG = 9,
+                   KC_EXCHANGE = 10 /* data-parallel gradient exchange + optimizer */, KC_COUNT = 11 };
 
 // Kernel launch through cudaLaunchKernelEx so that the PDL attribute can be attached.
 template <typename... KArgs, typename... Args>
@@ -168,6 +169,8 @@ enum EpiMode {
   EPI_MASK_RELU = 3,   // D = select(0 <= H, v, 0)                      (adjoint of relu, passes.nim:471-476)
   EPI_MASK_LEAKY = 4,  // D = v * select(0 <= H, 1, leak)               (adjoint of leakyRelu)
   EPI_SGD = 5,         // D += (0 - v) * rate                           (base.nim:37-38)
+  EPI_SIGMOID = 6,     // D = 1 / (1 + exp(0 - v))                      (dnn.nim:32-33)
+  EPI_TANH = 7,        // D = (e - f) / (e + f), e = exp(v), f = exp(0 - v)   (dnn.nim:35-40)
 };
 
 struct GemmArgs {

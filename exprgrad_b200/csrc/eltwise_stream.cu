@@ -1,0 +1,195 @@
+// HBM-streaming map kernels for the fixed elementwise / optimizer forms of exprgrad's layer library:
+// activations and their adjoints (exprgrad/layers/dnn.nim:26-40 + derive, passes.nim:383-549), the optimizer
+// updates (gradientDescent base.nim:37-38, adam base.nim:40-53), tensor arithmetic (base.nim:19-25) and the
+// row-broadcast bias add (dnn.nim:22-24). They replace, for these forms, what the reference's OpenCL generator
+// emitted per kernel (clgen.nim:74-190: one work-item per element, scalar loads) and what interp.cu does as a
+// register interpreter (issue-bound at 0.37 of the HBM roofline, profiles/r01j_eltwise_ncu_full.txt).
+//
+// One template instance per form - no interpreter loop, no index arithmetic beyond a grid-stride counter:
+// every thread moves four independent 128-bit groups per tensor and iteration (all loads issued before the
+// first store), 256-thread blocks, a grid of a few CTAs per SM. Tensors that cannot stay in the 126 MB L2 are
+// read with ld.global.cs / written with st.global.cs (evict-first) so that they do not sweep the L2 contents
+// of their neighbours; small ones keep the default policy because the next kernel re-reads them from L2.
+// Arithmetic restates the IR expression operation by operation (file compiled with -fmad=false: the reference
+// emits separate fmul / fadd, llvmgen.nim:219-221; negate is 0 - x, llvm.nim:333-336; division and sqrt IEEE).
+#include "egb_internal.hpp"
+#include "pattern.hpp"
+#include "runtime.hpp"
+
+namespace egb {
+
+namespace {
+
+constexpr int ELT_THREADS = 256;
+constexpr int ELT_UNROLL = 4;
+
+struct EltArgs {
+  float* out;
+  const float* in0;
+  const float* in1;
+  float p0, p1, p2, p3;
+  long long n;     // elements
+  long long row;   // ELT_BIAS_ROW: row length (multiple of 4)
+  int accumulate;  // out += f(...) (InstrWrite) instead of out = f(...) (InstrOverwrite)
+  int streaming;   // evict-first loads / stores
+};
+
+template <int KIND>
+struct EltFn;
+
+#define EGB_ELT_FN(KIND_, NIN_, BODY)                                                  \
+  template <>                                                                          \
+  struct EltFn<KIND_> {                                                                \
+    static constexpr int kInputs = NIN_;                                               \
+    static __device__ __forceinline__ float apply(float x, float y, const EltArgs& a) { \
+      (void)x; (void)y; (void)a;                                                       \
+      BODY                                                                             \
+    }                                                                                  \
+  };
+
+EGB_ELT_FN(ELT_COPY, 1, return x;)
+EGB_ELT_FN(ELT_BIAS_ROW, 1, return x;)
+EGB_ELT_FN(ELT_RELU, 1, return (0.0f <= x) ? x : 0.0f;)
+EGB_ELT_FN(ELT_LEAKY, 1, return ((0.0f <= x) ? 1.0f : a.p0) * x;)
+EGB_ELT_FN(ELT_SIGMOID, 1, return __fdiv_rn(1.0f, 1.0f + expf(0.0f - x));)
+EGB_ELT_FN(ELT_TANH, 1, const float e = expf(x); const float f = expf(0.0f - x); return __fdiv_rn(e - f, e + f);)
+EGB_ELT_FN(ELT_SCALE, 1, return x * a.p0;)
+EGB_ELT_FN(ELT_SCALE_NEG, 1, return (0.0f - x) * a.p0;)
+EGB_ELT_FN(ELT_DIV_CONST, 1, return __fdiv_rn(x, a.p0);)
+EGB_ELT_FN(ELT_ADD, 2, return x + y;)
+EGB_ELT_FN(ELT_SUB, 2, return x - y;)
+EGB_ELT_FN(ELT_MUL, 2, return x * y;)
+EGB_ELT_FN(ELT_RELU_ADJ, 2, return (0.0f <= x) ? y : 0.0f;)
+EGB_ELT_FN(ELT_LEAKY_ADJ, 2, return y * ((0.0f <= x) ? 1.0f : a.p0);)
+// negate(mul(mul(negate(1), div(g, mul(s, s))), e)) with e = exp(negate(x)), s = add(1, e)
+EGB_ELT_FN(ELT_SIGMOID_ADJ, 2, const float e = expf(0.0f - x); const float s = 1.0f + e;
+           return 0.0f - ((-1.0f * __fdiv_rn(y, s * s)) * e);)
+// derive() of (e - f) / (e + f), e = exp(x), f = exp(negate(x)):
+//   t = negate(e - f) * (g / ((e + f) * (e + f)));  result = negate((t + negate(g / (e + f))) * f) + (t + g / (e + f)) * e
+EGB_ELT_FN(ELT_TANH_ADJ, 2, const float e = expf(x); const float f = expf(0.0f - x); const float s = e + f;
+           const float t = (0.0f - (e - f)) * __fdiv_rn(y, s * s); const float q = __fdiv_rn(y, s);
+           return (0.0f - ((t + (0.0f - q)) * f)) + ((t + q) * e);)
+EGB_ELT_FN(ELT_ADAM_M, 2, return (x * a.p0) + (a.p1 * y);)
+EGB_ELT_FN(ELT_ADAM_V, 2, return (x * a.p0) + (a.p1 * (y * y));)
+// div(mul(negate(eta), div(m, c1)), add(sqrt(div(v, c2)), eps)); c1 = 1 - pow(b1, epoch), c2 = 1 - pow(b2, epoch)
+EGB_ELT_FN(ELT_ADAM_STEP, 2, return __fdiv_rn(a.p0 * __fdiv_rn(x, a.p1), __fsqrt_rn(__fdiv_rn(y, a.p2)) + a.p3);)
+
+template <bool kStream>
+__device__ __forceinline__ float4 ld4(const float* p) {
+  if constexpr (kStream) return __ldcs(reinterpret_cast<const float4*>(p));
+  else return *reinterpret_cast<const float4*>(p);
+}
+template <bool kStream>
+__device__ __forceinline__ void st4(float* p, float4 v) {
+  if constexpr (kStream) __stcs(reinterpret_cast<float4*>(p), v);
+  else *reinterpret_cast<float4*>(p) = v;
+}
+
+// column of flat element i in a row-major [rows, row] tensor (32-bit divide when it fits)
+__device__ __forceinline__ long long row_offset(long long i, const EltArgs& a) {
+  if ((a.n >> 31) == 0) return (long long)((unsigned)i % (unsigned)a.row);
+  return i % a.row;
+}
+
+template <int KIND, bool kStream>
+__global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArgs a) {
+  using Fn = EltFn<KIND>;
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n4 = a.n >> 2;
+  const long long stride = (long long)gridDim.x * ELT_THREADS;
+  const long long first = (long long)blockIdx.x * ELT_THREADS + threadIdx.x;
+  // in-place forms (adam: m += f(m, g)) read the destination as an operand already
+  const bool alias0 = KIND != ELT_BIAS_ROW && a.in0 == a.out;
+  for (long long base = first; base < n4; base += stride * ELT_UNROLL) {
+    float4 x[ELT_UNROLL], y[ELT_UNROLL], o[ELT_UNROLL];
+    // phase 1: every load of this iteration
+#pragma unroll
+    for (int u = 0; u < ELT_UNROLL; ++u) {
+      const long long g = base + (long long)u * stride;
+      x[u] = y[u] = o[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < n4) {
+        if constexpr (KIND == ELT_BIAS_ROW) x[u] = *reinterpret_cast<const float4*>(a.in0 + row_offset(g << 2, a));
+        else x[u] = ld4<kStream>(a.in0 + (g << 2));
+        if constexpr (Fn::kInputs >= 2) y[u] = ld4<kStream>(a.in1 + (g << 2));
+        if (a.accumulate) o[u] = alias0 ? x[u] : ld4<kStream>(a.out + (g << 2));
+      }
+    }
+    // phase 2: arithmetic + stores
+#pragma unroll
+    for (int u = 0; u < ELT_UNROLL; ++u) {
+      const long long g = base + (long long)u * stride;
+      if (g < n4) {
+        float4 r;
+        r.x = Fn::apply(x[u].x, y[u].x, a);
+        r.y = Fn::apply(x[u].y, y[u].y, a);
+        r.z = Fn::apply(x[u].z, y[u].z, a);
+        r.w = Fn::apply(x[u].w, y[u].w, a);
+        if (a.accumulate) {
+          r.x = o[u].x + r.x; r.y = o[u].y + r.y; r.z = o[u].z + r.z; r.w = o[u].w + r.w;
+        }
+        st4<kStream>(a.out + (g << 2), r);
+      }
+    }
+  }
+  // tail (n mod 4 elements)
+  const long long t = (n4 << 2) + first;
+  if (t < a.n) {
+    const float x = KIND == ELT_BIAS_ROW ? a.in0[row_offset(t, a)] : a.in0[t];
+    const float y = Fn::kInputs >= 2 ? a.in1[t] : 0.0f;
+    const float r = Fn::apply(x, y, a);
+    a.out[t] = a.accumulate ? a.out[t] + r : r;
+  }
+}
+
+template <int KIND>
+void launch_kind(Context& ctx, const EltArgs& a, cudaStream_t st) {
+  const long long n4 = a.n >> 2;
+  long long blocks = (n4 + (long long)ELT_THREADS * ELT_UNROLL - 1) / ((long long)ELT_THREADS * ELT_UNROLL);
+  const long long cap = (long long)ctx.sm_count * 3;   // three resident CTAs per SM (launch bounds: 85 registers), one wave
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  Launch l(ctx, KC_ELTWISE, st);
+  if (a.streaming) launch_kernel(ctx, elt_stream_kernel<KIND, true>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
+  else launch_kernel(ctx, elt_stream_kernel<KIND, false>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
+}
+
+}  // namespace
+
+bool eltwise_stream_supported(const EltLaunch& e) {
+  if (e.kind <= ELT_NONE || e.kind >= ELT_KIND_COUNT || e.n <= 0) return false;
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!e.out || !aligned(e.out) || !e.in[0] || !aligned(e.in[0])) return false;
+  if (e.nreads >= 2 && (!e.in[1] || !aligned(e.in[1]))) return false;
+  if (e.nreads > 2) return false;
+  if (e.kind == ELT_BIAS_ROW && (e.row <= 0 || (e.row & 3) != 0 || e.n % e.row != 0)) return false;
+  return true;
+}
+
+void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st) {
+  if (!eltwise_stream_supported(e)) fail(EGB_ERR_GPU, "eltwise: unsupported launch (kind %d)", e.kind);
+  EltArgs a;
+  a.out = e.out;
+  a.in0 = e.in[0];
+  a.in1 = e.nreads >= 2 ? e.in[1] : nullptr;
+  a.p0 = e.p[0]; a.p1 = e.p[1]; a.p2 = e.p[2]; a.p3 = e.p[3];
+  a.n = e.n;
+  a.row = e.row > 0 ? e.row : 1;
+  a.accumulate = e.accumulate ? 1 : 0;
+  // bytes this launch moves; beyond about half of the L2 it streams (evict-first)
+  const double bytes = 4.0 * (double)e.n * (1 + (e.kind == ELT_BIAS_ROW ? 0 : e.nreads) + (e.accumulate ? 1 : 0));
+  a.streaming = bytes > 64.0e6 ? 1 : 0;
+  switch (e.kind) {
+#define EGB_ELT_CASE(K) case K: launch_kind<K>(ctx, a, st); break;
+    EGB_ELT_CASE(ELT_COPY) EGB_ELT_CASE(ELT_RELU) EGB_ELT_CASE(ELT_LEAKY) EGB_ELT_CASE(ELT_SIGMOID) EGB_ELT_CASE(ELT_TANH)
+    EGB_ELT_CASE(ELT_SCALE) EGB_ELT_CASE(ELT_SCALE_NEG) EGB_ELT_CASE(ELT_DIV_CONST) EGB_ELT_CASE(ELT_ADD) EGB_ELT_CASE(ELT_SUB)
+    EGB_ELT_CASE(ELT_MUL) EGB_ELT_CASE(ELT_RELU_ADJ) EGB_ELT_CASE(ELT_LEAKY_ADJ) EGB_ELT_CASE(ELT_SIGMOID_ADJ)
+    EGB_ELT_CASE(ELT_TANH_ADJ) EGB_ELT_CASE(ELT_ADAM_M) EGB_ELT_CASE(ELT_ADAM_V) EGB_ELT_CASE(ELT_ADAM_STEP)
+    EGB_ELT_CASE(ELT_BIAS_ROW)
+#undef EGB_ELT_CASE
+    default: fail(EGB_ERR_GPU, "eltwise: unknown kind %d", e.kind);
+  }
+  EGB_CUDA(cudaGetLastError());
+}
+
+}  // namespace egb

@@ -401,6 +401,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           } else if (p.epi == EPI_MASK_LEAKY) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fmul_rn(x[e], (0.0f <= a2[e]) ? 1.0f : p.epi_param);
+          } else if (p.epi == EPI_SIGMOID) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fsub_rn(0.0f, x[e]))));
+          } else if (p.epi == EPI_TANH) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float ep = expf(x[e]), en = expf(__fsub_rn(0.0f, x[e]));
+              x[e] = __fdiv_rn(__fsub_rn(ep, en), __fadd_rn(ep, en));
+            }
           } else if (p.epi == EPI_SGD) {
             // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
 #pragma unroll

@@ -597,6 +597,18 @@ std::string expr_text(const Kernel& k, int reg, int depth) {
   return "r" + std::to_string(reg);
 }
 
+std::string loop_modes_text(const Kernel& k) {
+  std::string s;
+  for (auto& l : k.loops) s += l.mode >= 1 ? "!" : ".";
+  return s;
+}
+
+std::string access_text_of(const Kernel& k, int read_index) {
+  std::map<int, int> loop_pos;
+  for (size_t i = 0; i < k.loops.size(); ++i) loop_pos[k.loops[i].iter] = (int)i;
+  return access_text(read_index < 0 ? k.write : k.reads[(size_t)read_index], loop_pos);
+}
+
 std::string describe_kernel(const Kernel& k) {
   std::map<int, int> loop_pos;
   std::ostringstream ss;

@@ -163,6 +163,10 @@ typedef std::map<int, std::vector<int64_t>> ShapeTable;
 ShapeTable infer_shapes(const Program& prog, const Target& target, const ShapeTable& inputs);
 
 std::string describe_kernel(const Kernel& k);
+// canonical pieces of it: "!.!" (independent / reduction loops in loop order) and the index tuple of the write
+// (read_index < 0) or of one read, e.g. "[I0,I1]", "{I0}", "[I0,2*I1+1,I3]"
+std::string loop_modes_text(const Kernel& k);
+std::string access_text_of(const Kernel& k, int read_index);
 std::string expr_text(const Kernel& k, int reg, int depth = 0);
 
 }  // namespace egb

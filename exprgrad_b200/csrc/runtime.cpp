@@ -1,6 +1,7 @@
 // Launch-plan construction and execution (see runtime.hpp).
 #include "runtime.hpp"
 
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -188,6 +189,13 @@ bool to_row_form(IpProgram& p, int64_t rows, const std::map<uint64_t, int64_t>& 
   return local(p.write);
 }
 
+// db[x] = sum_y dh[y, x]: the adjoint of the row-broadcast bias add (dnn.nim:22-24 through derive)
+bool is_column_sum(const Kernel& k) {
+  static const KernelForm form{".!", "[I1]", "$0", {"[I0,I1]"}};
+  PatMatch m;
+  return match_form(k, form, m);
+}
+
 // Replace runs of consecutive levels that consist only of small row-local generic kernels by one
 // ROWCHAIN node each. Returns true if anything was fused.
 bool fuse_row_chains(Model& m, Plan& plan) {
@@ -257,31 +265,42 @@ bool fuse_row_chains(Model& m, Plan& plan) {
       // the reference's softmax + crossEntropy head and its adjoints, in exactly this wiring?
       const Target& target = *plan.target;
       auto K = [&](int m) -> const Kernel& { return *target.kernels[plan.nodes[members[m]].kernel_index]; };
-      auto text = [&](int m) { return describe_kernel(K(m)); };
       auto acc = [&](int m) { return (int)plan.nodes[members[m]].ip.accumulate; };
       bool ok = members.size() == 6;
       for (int m2 = 0; ok && m2 < 6; ++m2) ok = plan.nodes[members[m2]].kernel_index >= 0;
+      // The six kernels of softmax (dnn.nim:90-94: no max-subtraction) + crossEntropy (base.nim:66-67) and their
+      // derive()d adjoints, matched structurally: expression trees are unified (operand order of commutative
+      // operations and read order do not matter), the index tuple of every operand is checked after binding.
+      static const KernelForm kHead[6] = {
+          {"!.", "[I0]", "exp($0)", {"[I0,I1]"}},                                               // s[y] = sum_x exp(h)
+          {"!!", "[I0,I1]", "div(exp($0),$1)", {"[I0,I1]", "[I0]"}},                            // p = exp(h) / s[y]
+          {"!", "{I0}", "div(mul(negate(div($2,toscalar(shape($1,0)))),$0),$1)", {"{I0}", "{I0}", "[0]"}},  // dp = -(dL/N) y / p
+          {"!!", "[I0,I1]", "mul(div($2,$1),exp($0))", {"[I0,I1]", "[I0]", "[I0,I1]"}},         // dh = dp / s * e
+          {"!.", "[I0]", "mul(negate(exp($0)),div($2,mul($1,$1)))", {"[I0,I1]", "[I0]", "[I0,I1]"}},  // ds = -e dp / s^2
+          {"!!", "[I0,I1]", "mul($1,exp($0))", {"[I0,I1]", "[I0]"}}};                           // dh += ds e
+      PatMatch hm[6];
+      int failed_at = -1;
+      for (int m2 = 0; ok && m2 < 6; ++m2)
+        if (!match_form(K(m2), kHead[m2], hm[m2])) {
+          ok = false;
+          failed_at = m2;
+        }
+      ok = ok && acc(0) == 0 && acc(1) == 0 && acc(2) == 0 && acc(3) == 0 && acc(4) == 0 && acc(5) == 1;
+      if (!ok && members.size() == 6)
+        plan.notes.push_back("row chain of 6 kernels is not the softmax + crossEntropy head" +
+                             (failed_at >= 0 ? " (kernel " + std::to_string(plan.nodes[members[failed_at]].kernel_index) + ": " +
+                                                   describe_kernel(K(failed_at)) + ")"
+                                             : std::string(" (write modes differ)")) +
+                             ": runs as a generic row chain");
       if (ok) {
-        const std::string t2 = text(2);
-        const std::string pre = "loops=! W{I0} R0{I0} R1{I0} R2[0] : div(mul(negate(div(R2,toscalar(shape(T", post = ",0)))),R0),R1)";
-        ok = text(0) == "loops=!. W[I0] R0[I0,I1] : exp(R0)" && text(1) == "loops=!! W[I0,I1] R0[I0,I1] R1[I0] : div(exp(R0),R1)" &&
-             t2.compare(0, pre.size(), pre) == 0 && t2.size() > pre.size() + post.size() &&
-             t2.compare(t2.size() - post.size(), post.size(), post) == 0 &&
-             text(3) == "loops=!! W[I0,I1] R0[I0,I1] R1[I0] R2[I0,I1] : mul(div(R2,R1),exp(R0))" &&
-             text(4) == "loops=!. W[I0] R0[I0,I1] R1[I0] R2[I0,I1] : mul(negate(exp(R0)),div(R2,mul(R1,R1)))" &&
-             text(5) == "loops=!! W[I0,I1] R0[I0,I1] R1[I0] : mul(R1,exp(R0))" && acc(0) == 0 && acc(1) == 0 &&
-             acc(2) == 0 && acc(3) == 0 && acc(4) == 0 && acc(5) == 1;
-      }
-      if (ok) {
-        const int H = K(0).reads[0].tensor, S = K(0).write.tensor, P = K(1).write.tensor;
-        const int Y = K(2).reads[0].tensor, DL = K(2).reads[2].tensor, DP = K(2).write.tensor;
+        const int H = hm[0].tensor_of.at(0), S = K(0).write.tensor, P = K(1).write.tensor;
+        const int Y = hm[2].tensor_of.at(0), DL = hm[2].tensor_of.at(2), DP = K(2).write.tensor;
         const int DH = K(3).write.tensor, DS = K(4).write.tensor;
-        const std::string shape_of = "T" + std::to_string(P) + ",";
-        ok = K(1).reads[0].tensor == H && K(1).reads[1].tensor == S && K(2).reads[1].tensor == P &&
-             text(2).find("shape(" + shape_of) != std::string::npos && K(3).reads[0].tensor == H &&
-             K(3).reads[1].tensor == S && K(3).reads[2].tensor == DP && K(4).reads[0].tensor == H &&
-             K(4).reads[1].tensor == S && K(4).reads[2].tensor == DP && K(5).reads[0].tensor == H &&
-             K(5).reads[1].tensor == DS && K(5).write.tensor == DH;
+        ok = hm[1].tensor_of.at(0) == H && hm[1].tensor_of.at(1) == S && hm[2].tensor_of.at(1) == P &&
+             hm[3].tensor_of.at(0) == H && hm[3].tensor_of.at(1) == S && hm[3].tensor_of.at(2) == DP &&
+             hm[4].tensor_of.at(0) == H && hm[4].tensor_of.at(1) == S && hm[4].tensor_of.at(2) == DP &&
+             hm[5].tensor_of.at(0) == H && hm[5].tensor_of.at(1) == DS && K(5).write.tensor == DH;
+        if (!ok) plan.notes.push_back("softmax + crossEntropy kernels found but wired differently: runs as a generic row chain");
         std::set<int> distinct = {H, S, P, Y, DL, DP, DH, DS};
         const auto& hs = plan.shapes.at(H);
         ok = ok && distinct.size() == 8 && hs.size() == 2 && softmax_xent_supported(hs[1]) && plan.shapes.at(Y) == hs &&
@@ -345,7 +364,7 @@ bool fuse_row_chains(Model& m, Plan& plan) {
               fx.label += " + operand planes";
               drop(j);
             } else if (nj.kind == Node::INTERP && nj.kernel_index >= 0 && !fx.sx_colsum && !nj.ip.accumulate &&
-                       describe_kernel(*target.kernels[nj.kernel_index]) == "loops=.! W[I1] R0[I0,I1] : R0" &&
+                       is_column_sum(*target.kernels[nj.kernel_index]) &&
                        target.kernels[nj.kernel_index]->reads[0].tensor == DH && tensor_len((int)nj.writes[0]) == hs[1]) {
               fx.sx_colsum = (float*)nj.ip.write.base;
               const bool prezeroed = (char*)fx.sx_colsum >= plan.arena && (char*)fx.sx_colsum < plan.arena + plan.zero_bytes;
@@ -416,11 +435,60 @@ bool fuse_row_chains(Model& m, Plan& plan) {
   return true;
 }
 
+// The fixed map forms of the layer library (pattern.cpp) run on template-specialised streaming kernels.
+bool build_eltwise_node(Model& m, Plan& plan, const Kernel& k, int ki, bool overwrite, const std::map<int, void*>& ptrs) {
+  if (m.strict || !m.eltwise) return false;
+  EltSpec es;
+  if (!match_eltwise(k, plan.shapes, es)) return false;
+  EltLaunch e;
+  e.kind = es.kind;
+  e.nreads = es.nreads;
+  e.n = es.n;
+  e.row = es.row;
+  e.accumulate = !overwrite;
+  auto ptr = [&](int tensor) {
+    auto it = ptrs.find(tensor);
+    return it == ptrs.end() ? (float*)nullptr : (float*)it->second;
+  };
+  e.out = ptr(k.write.tensor);
+  for (int q = 0; q < es.nreads && q < 2; ++q) e.in[q] = ptr(es.read_tensor[q]);
+  // literals: constant sub-expressions are folded in float64 and then rounded to the scalar type
+  // (propagateConstants passes.nim:1629-1650, llvmgen.nim:213-218); pow(b, epoch) is a run-time fp32 value
+  switch (es.kind) {
+    case ELT_ADAM_M: case ELT_ADAM_V:
+      e.p[0] = (float)(es.lit[0] - 1.0);
+      e.p[1] = (float)(1.0 - es.lit[0]);
+      break;
+    case ELT_ADAM_STEP:
+      e.p[0] = (float)(0.0 - es.lit[0]);
+      e.p[1] = 1.0f - powf((float)es.lit[1], (float)m.epoch);
+      e.p[2] = 1.0f - powf((float)es.lit[2], (float)m.epoch);
+      e.p[3] = (float)es.lit[3];
+      break;
+    default:
+      for (int q = 0; q < 4; ++q) e.p[q] = (float)es.lit[q];
+  }
+  if (!eltwise_stream_supported(e)) return false;
+  Node n;
+  n.kind = Node::ELTWISE;
+  n.label = std::string("eltwise ") + elt_kind_name(es.kind) + " kernel " + std::to_string(ki) + " -> tensor" +
+            std::to_string(k.write.tensor - 1) + " n=" + std::to_string(es.n) + (e.accumulate ? " +=" : " =");
+  n.elt = e;
+  n.kernel_index = ki;
+  n.uses_epoch = es.uses_epoch;
+  for (auto& r : k.reads) n.reads.push_back(r.tensor);
+  n.writes.push_back(k.write.tensor);
+  if (e.accumulate) n.reads.push_back(k.write.tensor);
+  plan.nodes.push_back(n);
+  return true;
+}
+
 void build_nodes_impl(Model& m, Plan& plan) {
   const std::vector<KernelInfo>& info = plan.info;
   const Target& target = *plan.target;
   Context& ctx = *m.ctx;
   plan.nodes.clear();
+  plan.notes.clear();
   plan.launches_per_run = 0;
   for (void* b : plan.chain_bufs) cudaFree(b);
   plan.chain_bufs.clear();
@@ -602,6 +670,8 @@ void build_nodes_impl(Model& m, Plan& plan) {
       n.writes.push_back(k.write.tensor);
       n.reads.push_back(k.write.tensor);
       plan.nodes.push_back(n);
+    } else if (build_eltwise_node(m, plan, k, (int)ki, inf.overwrite, ptrs)) {
+      // one of the fixed elementwise / optimizer forms: specialised streaming kernel (no interpreter)
     } else {
       Lowered lw = lower_kernel(k, plan.shapes, ptrs, m.epoch, m.strict, inf.overwrite, ctx.sm_count);
       Node n;
@@ -785,12 +855,9 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   // (EGB_DP_FORCE: lay the plan out for data parallelism on a single rank - timing studies of the DP plan)
   static const bool dp_force = getenv("EGB_DP_FORCE") != nullptr;
   const bool dp = comm && (comm_world(comm) > 1 || dp_force);
-  std::vector<std::string> text(nk);
-  for (size_t ki = 0; ki < nk; ++ki) {
+  for (size_t ki = 0; ki < nk; ++ki)
     if (target->kernels[ki]->is_generator())
       fail(EGB_ERR_GENERATOR, "program still contains generator kernels; compile it first");
-    text[ki] = describe_kernel(*target->kernels[ki]);
-  }
   auto same_shape = [&](int a, int b) {
     auto x = plan->shapes.find(a), y = plan->shapes.find(b);
     return x != plan->shapes.end() && y != plan->shapes.end() && x->second == y->second;
@@ -798,19 +865,6 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   auto is_fresh = [&](int t) {
     return prog->tdef(t).kind == TensorKind::Result && !written.count(t) && !read_first.count(t) && t != 0;
   };
-  // "prefix<number>suffix" -> number
-  auto parse_param = [](const std::string& s, const std::string& prefix, const std::string& suffix, float& out) {
-    if (s.size() <= prefix.size() + suffix.size()) return false;
-    if (s.compare(0, prefix.size(), prefix) != 0) return false;
-    if (s.compare(s.size() - suffix.size(), suffix.size(), suffix) != 0) return false;
-    const std::string num = s.substr(prefix.size(), s.size() - prefix.size() - suffix.size());
-    char* end = nullptr;
-    const double v = strtod(num.c_str(), &end);
-    if (!end || *end) return false;
-    out = (float)v;
-    return true;
-  };
-
   for (size_t ki = 0; ki < nk; ++ki) {
     const Kernel& k = *target->kernels[ki];
     KernelInfo& inf = plan->info[ki];
@@ -835,7 +889,7 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
     // a plain column sum (bias gradient) may be fused into the classification head, where the partial sums meet
     // through atomics: keep its (small) result in the zeroed region so that no extra memset node is needed
     if (fuse && !strict && prog->tdef(wt).kind == TensorKind::Result && !written.count(wt) && inf.overwrite && !inf.is_gemm &&
-        !inf.is_conv && describe_kernel(k) == "loops=.! W[I1] R0[I0,I1] : R0")
+        !inf.is_conv && is_column_sum(k))
       needs_zero.insert(wt);
     written.insert(wt);
     if (inf.is_gemm) {
@@ -862,44 +916,40 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
       bool conflict = touched_r.count(c.write.tensor) || touched_w.count(c.write.tensor);
       for (auto& r : c.reads) conflict = conflict || touched_w.count(r.tensor);
       bool take = false;
-      const std::string& t = text[kj];
       const int final_t = inf.final_tensor;
-      if (!conflict && kernel_loops_full(c, plan->shapes)) {
-        float param = 0.0f;
-        if (!has_bias && !has_stage && !has_colsum && t == "loops=!! W[I0,I1] R0[I1] : R0" && c.write.tensor == C &&
-            c.reads[0].tensor != C) {
-          inf.bias_tensor = c.reads[0].tensor;
+      // Structural classification of the candidate (pattern.cpp): which map form it computes and which tensors
+      // its operands are - independent of operand order, register numbering and read order.
+      EltSpec es;
+      const bool is_map = !conflict && match_eltwise(c, plan->shapes, es);
+      if (is_map) {
+        const int r0 = es.read_tensor[0], r1 = es.read_tensor[1];
+        if (!has_bias && !has_stage && !has_colsum && es.kind == ELT_BIAS_ROW && c.write.tensor == C && r0 != C) {
+          inf.bias_tensor = r0;                                             // h[y,x] += b[x]      (dnn.nim:22-24)
           has_bias = take = true;
-        } else if (!has_stage && !has_colsum && c.reads.size() == 1 && c.reads[0].tensor == C &&
-                   is_fresh(c.write.tensor) && same_shape(c.write.tensor, C) &&
-                   (t == "loops=! W{I0} R0{I0} : select(le(0,R0),R0,0)" ||
-                    parse_param(t, "loops=! W{I0} R0{I0} : mul(select(le(0,R0),1,", "),R0)", param))) {
-          inf.epi = t.find("mul(") != std::string::npos ? EPI_LEAKY : EPI_RELU;
-          inf.epi_param = param;
+        } else if (!has_stage && !has_colsum && r0 == C && is_fresh(c.write.tensor) && same_shape(c.write.tensor, C) &&
+                   (es.kind == ELT_RELU || es.kind == ELT_LEAKY || es.kind == ELT_SIGMOID || es.kind == ELT_TANH)) {
+          inf.epi = es.kind == ELT_RELU ? EPI_RELU : es.kind == ELT_LEAKY ? EPI_LEAKY : es.kind == ELT_SIGMOID ? EPI_SIGMOID : EPI_TANH;
+          inf.epi_param = (float)es.lit[0];                                 // activations        (dnn.nim:26-40)
           inf.d_tensor = c.write.tensor;
           has_stage = take = true;
-        } else if (!has_stage && !has_colsum && c.reads.size() == 2 && c.reads[1].tensor == C &&
-                   c.reads[0].tensor != C && is_fresh(c.write.tensor) && same_shape(c.write.tensor, C) &&
-                   same_shape(c.reads[0].tensor, C) && !touched_w.count(c.reads[0].tensor) &&
-                   (t == "loops=! W{I0} R0{I0} R1{I0} : select(le(0,R0),R1,0)" ||
-                    parse_param(t, "loops=! W{I0} R0{I0} R1{I0} : mul(R1,select(le(0,R0),1,", "))", param))) {
-          inf.epi = t.find("mul(") != std::string::npos ? EPI_MASK_LEAKY : EPI_MASK_RELU;
-          inf.epi_param = param;
+        } else if (!has_stage && !has_colsum && (es.kind == ELT_RELU_ADJ || es.kind == ELT_LEAKY_ADJ) && r1 == C && r0 != C &&
+                   is_fresh(c.write.tensor) && same_shape(c.write.tensor, C) && same_shape(r0, C) && !touched_w.count(r0)) {
+          inf.epi = es.kind == ELT_LEAKY_ADJ ? EPI_MASK_LEAKY : EPI_MASK_RELU;   // adjoint masks (derive of select)
+          inf.epi_param = (float)es.lit[0];
           inf.d_tensor = c.write.tensor;
-          inf.h_tensor = c.reads[0].tensor;
+          inf.h_tensor = r0;
           has_stage = take = true;
-        } else if (!has_colsum && t == "loops=.! W[I1] R0[I0,I1] : R0" && c.reads[0].tensor == final_t &&
-                   is_fresh(c.write.tensor)) {
-          inf.colsum_tensor = c.write.tensor;
-          has_colsum = take = true;
-        } else if (!dp && !has_stage && !has_colsum && c.reads.size() == 1 && c.reads[0].tensor == C &&
-                   prog->tdef(c.write.tensor).kind == TensorKind::Param && same_shape(c.write.tensor, C) &&
-                   parse_param(t, "loops=! W{I0} R0{I0} : mul(negate(R0),", ")", param)) {
-          inf.epi = EPI_SGD;
-          inf.epi_param = param;
+        } else if (!dp && !has_stage && !has_colsum && es.kind == ELT_SCALE_NEG && r0 == C &&
+                   prog->tdef(c.write.tensor).kind == TensorKind::Param && same_shape(c.write.tensor, C)) {
+          inf.epi = EPI_SGD;                                                // P += (0 - g) * rate (base.nim:37-38)
+          inf.epi_param = (float)es.lit[0];
           inf.d_tensor = c.write.tensor;
           has_stage = take = true;
         }
+      } else if (!conflict && !has_colsum && is_column_sum(c) && c.reads[0].tensor == final_t && is_fresh(c.write.tensor) &&
+                 kernel_loops_full(c, plan->shapes)) {
+        inf.colsum_tensor = c.write.tensor;                                 // db[x] = sum_y d[y,x]
+        has_colsum = take = true;
       }
       if (take) {
         cinf.absorbed_by = (int)ki;
@@ -1059,6 +1109,7 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       launch_softmax_xent_rows(ctx, n.sx_h, n.sx_y, n.sx_dl, n.sx_s, n.sx_p, n.sx_dp, n.sx_dh, n.sx_ds, n.sx_rows, n.sx_cols,
                                n.sx_colsum, n.sx_out_hi, n.sx_out_mid, n.sx_ld_out, st);
       break;
+    case Node::ELTWISE: launch_eltwise_stream(ctx, n.elt, st); break;
     case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_slots, n.chain_rows, st); break;
     case Node::CONV: {
       const ConvPattern& cv = n.conv;

@@ -13,9 +13,23 @@
 #include "egb_internal.hpp"
 #include "interp.hpp"
 #include "lower.hpp"
+#include "pattern.hpp"
 #include "program.hpp"
 
 namespace egb {
+
+// One launch of a specialised streaming map kernel (eltwise_stream.cu): out (+)= f(in0 [, in1]; p0..p3)
+struct EltLaunch {
+  int kind = 0;        // EltKind (pattern.hpp)
+  int nreads = 0;
+  float* out = nullptr;
+  const float* in[2] = {nullptr, nullptr};
+  float p[4] = {0, 0, 0, 0};
+  int64_t n = 0, row = 0;
+  bool accumulate = false;
+};
+bool eltwise_stream_supported(const EltLaunch& e);
+void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st);
 
 struct DevTensor {
   void* ptr = nullptr;
@@ -30,7 +44,7 @@ struct DevTensor {
 };
 
 struct Node {
-  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN, SOFTMAX_XENT } kind = INTERP;
+  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN, SOFTMAX_XENT, ELTWISE } kind = INTERP;
   std::string label;
   // INTERP
   IpProgram ip;
@@ -58,6 +72,8 @@ struct Node {
   float* sx_colsum = nullptr;                                   // fused bias-gradient column sum of DH (zeroed first)
   __nv_bfloat16 *sx_out_hi = nullptr, *sx_out_mid = nullptr;    // fused operand planes of DH
   int sx_ld_out = 0;
+  // ELTWISE: one of the specialised streaming map kernels (eltwise_stream.cu)
+  EltLaunch elt;
   // CONV
   ConvPattern conv;
   const float *conv_a = nullptr, *conv_b = nullptr;
@@ -112,6 +128,7 @@ struct Plan {
   int bucket_before_kernel = -1;            // the all-reduce runs right before this target kernel
   std::vector<Node> nodes;
   std::vector<void*> chain_bufs;      // device copies of row-chain programs
+  std::vector<std::string> notes;     // planner log: why a fusion / fast path was not taken (describe_plan prints it)
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
   int64_t epoch_built = -1;
@@ -137,6 +154,7 @@ struct Model {
   bool fuse = true;         // epilogue fusion of contraction + elementwise / column-sum / SGD kernels
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   bool rowchain = true;     // runs of small row-local kernels execute in one launch
+  bool eltwise = true;      // fixed elementwise / optimizer forms run on the specialised streaming kernels
   // cluster split-K: contractions with few output tiles spread each tile's reduction over the CTAs of a
   // thread-block cluster (partial tiles meet through distributed shared memory, gemm_tcgen05.cu).
   // (An earlier global-memory variant - RED.ADD partial tiles + last-arriver epilogue - lost on the dense

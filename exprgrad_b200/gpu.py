@@ -186,6 +186,19 @@ class GpuTensor:
             n *= s
         self.buffer = ctx.alloc_buffer(n * self.dtype.itemsize)
 
+    def view(self, shape: Sequence[int]) -> "GpuTensor":
+        """The same buffer under another shape of equal length (tensors.nim `reshape` semantics; no copy)."""
+        v = GpuTensor.__new__(GpuTensor)
+        v.shape = [int(s) for s in shape]
+        v.dtype = self.dtype
+        v.buffer = self.buffer
+        n = 1
+        for s in v.shape:
+            n *= s
+        if n * self.dtype.itemsize != self.buffer.size:
+            raise GpuError("view: shape does not match the buffer size")
+        return v
+
     def read_into(self, tensor: np.ndarray):
         assert list(tensor.shape) == self.shape
         self.buffer.read_into(tensor)
@@ -226,8 +239,8 @@ class GpuEvent:
         return ms.value
 
 
-KERNEL_CLASSES = {"gemm": 0, "split": 1, "fill": 2, "interp": 3, "reduce": 4, "eltwise": 5, "conv": 6, "other": 7,
-                  "all": -1}
+KERNEL_CLASSES = {"gemm": 0, "split": 1, "fill": 2, "interp": 3, "reduce": 4, "eltwise": 5, "conv": 6, "conv_fwd": 6,
+                  "other": 7, "conv_dw": 8, "conv_dimg": 9, "exchange": 10, "all": -1}
 
 
 def set_timing(ctx: GpuContext, enabled: bool):

@@ -46,6 +46,17 @@ class Program:
         check(lib.egb_program_describe(self.handle, target.encode(), buf, need.value, ctypes.byref(need)))
         return buf.value.decode()
 
+    def classify(self, target: str, input_shapes: Dict[str, Sequence[int]]) -> List[str]:
+        """Device kernel family per IR kernel of `target` (host only; see egb_program_classify)."""
+        names, ranks, dims = _pack_shapes(input_shapes)
+        need = ctypes.c_size_t(0)
+        check(lib.egb_program_classify(self.handle, target.encode(), len(input_shapes), names, ranks, dims, None, 0,
+                                       ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        check(lib.egb_program_classify(self.handle, target.encode(), len(input_shapes), names, ranks, dims, buf,
+                                       need.value, ctypes.byref(need)))
+        return [line.split(": ", 1)[1] for line in buf.value.decode().splitlines()]
+
     def tensor_count(self) -> int:
         n = ctypes.c_int(0)
         check(lib.egb_program_tensor_count(self.handle, ctypes.byref(n)))

@@ -88,8 +88,11 @@ int egb_context_set_option(egb_context* ctx, const char* key, int64_t value);
 #define EGB_KC_INTERP 3
 #define EGB_KC_REDUCE 4
 #define EGB_KC_ELTWISE 5
-#define EGB_KC_CONV 6
+#define EGB_KC_CONV 6       /* conv2 forward */
 #define EGB_KC_OTHER 7
+#define EGB_KC_CONV_DW 8    /* conv2 d_filters */
+#define EGB_KC_CONV_DIMG 9  /* conv2 d_images */
+#define EGB_KC_EXCHANGE 10  /* data-parallel gradient exchange (+ fused optimizer update) */
 int egb_context_set_timing(egb_context* ctx, int enabled);
 int egb_context_kernel_time(egb_context* ctx, int kernel_class, double* total_ms, int64_t* launches);
 /* CUDA events on the context's stream (cudaEvent_t behind void*). */
@@ -181,6 +184,11 @@ int egb_program_serialize(egb_program* program, char* buf, size_t cap, size_t* n
 /* One line per kernel of a target: tensors read/written and the canonical text of the kernel
  * (iteration space, accesses, value expression) that the planner matches fused kernels against. */
 int egb_program_describe(egb_program* program, const char* target, char* buf, size_t cap, size_t* needed);
+/* Which device kernel family runs each IR kernel of `target` at the given input shapes: "contraction",
+ * "conv2 ...", "eltwise <form>" (the specialised streaming kernels that replace clgen.nim:74-190 for the fixed
+ * forms of layers/base.nim and layers/dnn.nim) or "generic" (the loop-nest kernel). Host only. */
+int egb_program_classify(egb_program* program, const char* target, int n_args, const char* const* names,
+                         const int* ranks, const int64_t* dims, char* buf, size_t cap, size_t* needed);
 int egb_program_free(egb_program* program);
 int egb_program_tensor_count(egb_program* program, int* count);
 /* kind: 0 result, 1 input, 2 param, 3 cache, 4 random (exprgrad/ir.nim:222-233). dims has room for
