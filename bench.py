@@ -596,7 +596,7 @@ def run_eltwise(args, ctx, timer, rank, world):
         gbs = bpe * n / (k_ms / steps * 1e-3) / 1e9
         res[target] = {"target_ms": ms / steps, "kernels_ms": k_ms / steps, "launches": k_n / steps, "other_launches": (all_n - k_n) / steps,
                        "algorithmic_bytes": bpe * n, "achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"],
-                       "specialised": "interp" not in plan}
+                       "specialised": " interp " not in plan}
     # spot check: relu of the resident tensor
     y = model.call("relu", {"x": dxt})
     assert np.array_equal(y[:256], np.maximum(chunk, 0)), "relu result mismatch"

@@ -26,9 +26,10 @@ typedef int (*PFN_ncclGetUniqueId)(NcclUniqueId*);
 typedef int (*PFN_ncclCommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
 typedef int (*PFN_ncclCommDestroy)(ncclComm_t);
 typedef int (*PFN_ncclAllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*PFN_ncclAllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
 typedef const char* (*PFN_ncclGetErrorString)(int);
 typedef int (*PFN_ncclGetVersion)(int*);
-constexpr int kNcclFloat32 = 7, kNcclSum = 0, kNcclAvg = 4;
+constexpr int kNcclFloat32 = 7, kNcclSum = 0, kNcclAvg = 4, kNcclInt8 = 0;
 
 struct NcclApi {
   void* handle = nullptr;
@@ -36,6 +37,7 @@ struct NcclApi {
   PFN_ncclCommInitRank comm_init_rank = nullptr;
   PFN_ncclCommDestroy comm_destroy = nullptr;
   PFN_ncclAllReduce all_reduce = nullptr;
+  PFN_ncclAllGather all_gather = nullptr;
   PFN_ncclGetErrorString error_string = nullptr;
   PFN_ncclGetVersion get_version = nullptr;
 };
@@ -58,6 +60,7 @@ NcclApi& nccl() {
   api.comm_init_rank = (PFN_ncclCommInitRank)sym("ncclCommInitRank");
   api.comm_destroy = (PFN_ncclCommDestroy)sym("ncclCommDestroy");
   api.all_reduce = (PFN_ncclAllReduce)sym("ncclAllReduce");
+  api.all_gather = (PFN_ncclAllGather)sym("ncclAllGather");
   api.error_string = (PFN_ncclGetErrorString)sym("ncclGetErrorString");
   api.get_version = (PFN_ncclGetVersion)sym("ncclGetVersion");
   return api;
@@ -81,6 +84,87 @@ struct CommHooks {
 
 void comm_all_reduce_avg(CommHooks* c, float* buf, size_t n, cudaStream_t st) { c->all_reduce_avg(buf, n, st); }
 int comm_world(CommHooks* c) { return c ? c->world : 1; }
+int comm_rank(CommHooks* c) { return c ? c->rank : 0; }
+
+// ---- peer windows for the fused exchange kernel (exchange.cu) ----------------------------------------------
+// Every rank exports its plan arena (it contains the gradient bucket) and a small flag area as cudaIpc handles;
+// one ncclAllGather of the 160-byte records distributes them, cudaIpcOpenMemHandle maps the peers' memory into
+// this process (NVLink peer access is enabled lazily by the mapping). One process per GPU, one node.
+namespace {
+struct WindowRecord {
+  cudaIpcMemHandle_t arena, flags;   // 64 bytes each
+  uint64_t arena_bytes, bucket_off, bucket_bytes, magic;
+};
+}  // namespace
+
+void comm_open_window(CommHooks* c, Context& ctx, char* arena, size_t arena_bytes, size_t bucket_off, size_t bucket_bytes,
+                      PeerWindow& w) {
+  const int world = c->world, rank = c->rank;
+  if (world > EX_MAX_WORLD) fail(EGB_ERR_GPU, "peer exchange supports at most %d ranks", EX_MAX_WORLD);
+  w.world = world;
+  w.rank = rank;
+  const size_t fbytes = exchange_flag_bytes();
+  EGB_CUDA(cudaMalloc((void**)&w.local_flags, fbytes));
+  EGB_CUDA(cudaMemsetAsync(w.local_flags, 0, fbytes, ctx.stream));
+  for (int r = 0; r < EX_MAX_WORLD; ++r) {
+    w.arena[r] = nullptr;
+    w.flags[r] = nullptr;
+  }
+  w.arena[rank] = arena;
+  w.flags[rank] = w.local_flags;
+  if (world > 1) {
+    WindowRecord mine;
+    memset(&mine, 0, sizeof(mine));
+    EGB_CUDA(cudaIpcGetMemHandle(&mine.arena, arena));
+    EGB_CUDA(cudaIpcGetMemHandle(&mine.flags, w.local_flags));
+    mine.arena_bytes = arena_bytes;
+    mine.bucket_off = bucket_off;
+    mine.bucket_bytes = bucket_bytes;
+    mine.magic = 0x45474258ull;  // "EGBX"
+    char* dev = nullptr;
+    EGB_CUDA(cudaMalloc((void**)&dev, sizeof(WindowRecord) * (size_t)(world + 1)));
+    std::vector<WindowRecord> all((size_t)world);
+    cudaError_t e = cudaMemcpyAsync(dev, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx.stream);
+    int rc = 0;
+    if (e == cudaSuccess)
+      rc = nccl().all_gather(dev, dev + sizeof(WindowRecord), sizeof(WindowRecord), kNcclInt8, c->comm, ctx.stream);
+    if (e == cudaSuccess && rc == 0)
+      e = cudaMemcpyAsync(all.data(), dev + sizeof(WindowRecord), sizeof(WindowRecord) * (size_t)world, cudaMemcpyDeviceToHost,
+                          ctx.stream);
+    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(ctx.stream);
+    cudaFree(dev);
+    if (rc != 0) nccl_check(rc, "ncclAllGather (peer window handles)");
+    EGB_CUDA(e);
+    for (int r = 0; r < world; ++r) {
+      if (all[(size_t)r].magic != mine.magic || all[(size_t)r].bucket_off != mine.bucket_off ||
+          all[(size_t)r].bucket_bytes != mine.bucket_bytes)
+        fail(EGB_ERR_GPU, "data parallel: rank %d laid out its gradient bucket differently (offset %llu, %llu bytes; here %llu, %llu)"
+                          " - every rank must build the same target with the same per-rank shapes",
+             r, (unsigned long long)all[(size_t)r].bucket_off, (unsigned long long)all[(size_t)r].bucket_bytes,
+             (unsigned long long)mine.bucket_off, (unsigned long long)mine.bucket_bytes);
+      if (r == rank) continue;
+      void *pa = nullptr, *pf = nullptr;
+      EGB_CUDA(cudaIpcOpenMemHandle(&pa, all[(size_t)r].arena, cudaIpcMemLazyEnablePeerAccess));
+      w.opened[w.nopened++] = pa;
+      EGB_CUDA(cudaIpcOpenMemHandle(&pf, all[(size_t)r].flags, cudaIpcMemLazyEnablePeerAccess));
+      w.opened[w.nopened++] = pf;
+      w.arena[r] = (char*)pa;
+      w.flags[r] = (uint32_t*)pf;
+    }
+  } else {
+    EGB_CUDA(cudaStreamSynchronize(ctx.stream));
+  }
+  w.mapped = true;
+}
+
+void comm_close_window(PeerWindow& w) {
+  for (int i = 0; i < w.nopened; ++i)
+    if (w.opened[i]) cudaIpcCloseMemHandle(w.opened[i]);
+  w.nopened = 0;
+  if (w.local_flags) cudaFree(w.local_flags);
+  w.local_flags = nullptr;
+  w.mapped = false;
+}
 
 }  // namespace egb
 

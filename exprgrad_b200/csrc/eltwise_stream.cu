@@ -12,6 +12,8 @@
 // of their neighbours; small ones keep the default policy because the next kernel re-reads them from L2.
 // Arithmetic restates the IR expression operation by operation (file compiled with -fmad=false: the reference
 // emits separate fmul / fadd, llvmgen.nim:219-221; negate is 0 - x, llvm.nim:333-336; division and sqrt IEEE).
+#include <stdlib.h>
+
 #include "egb_internal.hpp"
 #include "pattern.hpp"
 #include "runtime.hpp"
@@ -31,7 +33,7 @@ struct EltArgs {
   long long n;     // elements
   long long row;   // ELT_BIAS_ROW: row length (multiple of 4)
   int accumulate;  // out += f(...) (InstrWrite) instead of out = f(...) (InstrOverwrite)
-  int streaming;   // evict-first loads / stores
+  int streaming;   // evict-first cache policy, bit 0: operand loads, bit 1: load of the destination, bit 2: stores
 };
 
 template <int KIND>
@@ -74,14 +76,13 @@ EGB_ELT_FN(ELT_ADAM_V, 2, return (x * a.p0) + (a.p1 * (y * y));)
 // div(mul(negate(eta), div(m, c1)), add(sqrt(div(v, c2)), eps)); c1 = 1 - pow(b1, epoch), c2 = 1 - pow(b2, epoch)
 EGB_ELT_FN(ELT_ADAM_STEP, 2, return __fdiv_rn(a.p0 * __fdiv_rn(x, a.p1), __fsqrt_rn(__fdiv_rn(y, a.p2)) + a.p3);)
 
-template <bool kStream>
-__device__ __forceinline__ float4 ld4(const float* p) {
-  if constexpr (kStream) return __ldcs(reinterpret_cast<const float4*>(p));
-  else return *reinterpret_cast<const float4*>(p);
+// (the policy bits are uniform across the grid: the branches cost one predicate each)
+__device__ __forceinline__ float4 ld4(const float* p, bool cs) {
+  if (cs) return __ldcs(reinterpret_cast<const float4*>(p));
+  return *reinterpret_cast<const float4*>(p);
 }
-template <bool kStream>
-__device__ __forceinline__ void st4(float* p, float4 v) {
-  if constexpr (kStream) __stcs(reinterpret_cast<float4*>(p), v);
+__device__ __forceinline__ void st4(float* p, float4 v, bool cs) {
+  if (cs) __stcs(reinterpret_cast<float4*>(p), v);
   else *reinterpret_cast<float4*>(p) = v;
 }
 
@@ -91,9 +92,10 @@ __device__ __forceinline__ long long row_offset(long long i, const EltArgs& a) {
   return i % a.row;
 }
 
-template <int KIND, bool kStream>
+template <int KIND>
 __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArgs a) {
   using Fn = EltFn<KIND>;
+  const bool cs_in = (a.streaming & 1) != 0, cs_out_ld = (a.streaming & 2) != 0, cs_st = (a.streaming & 4) != 0;
   pdl_launch_dependents();
   pdl_wait();
   const long long n4 = a.n >> 2;
@@ -110,9 +112,9 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArg
       x[u] = y[u] = o[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g < n4) {
         if constexpr (KIND == ELT_BIAS_ROW) x[u] = *reinterpret_cast<const float4*>(a.in0 + row_offset(g << 2, a));
-        else x[u] = ld4<kStream>(a.in0 + (g << 2));
-        if constexpr (Fn::kInputs >= 2) y[u] = ld4<kStream>(a.in1 + (g << 2));
-        if (a.accumulate) o[u] = alias0 ? x[u] : ld4<kStream>(a.out + (g << 2));
+        else x[u] = ld4(a.in0 + (g << 2), alias0 ? cs_out_ld : cs_in);
+        if constexpr (Fn::kInputs >= 2) y[u] = ld4(a.in1 + (g << 2), cs_in);
+        if (a.accumulate) o[u] = alias0 ? x[u] : ld4(a.out + (g << 2), cs_out_ld);
       }
     }
     // phase 2: arithmetic + stores
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArg
         if (a.accumulate) {
           r.x = o[u].x + r.x; r.y = o[u].y + r.y; r.z = o[u].z + r.z; r.w = o[u].w + r.w;
         }
-        st4<kStream>(a.out + (g << 2), r);
+        st4(a.out + (g << 2), r, cs_st);
       }
     }
   }
@@ -150,8 +152,7 @@ void launch_kind(Context& ctx, const EltArgs& a, cudaStream_t st) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   Launch l(ctx, KC_ELTWISE, st);
-  if (a.streaming) launch_kernel(ctx, elt_stream_kernel<KIND, true>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
-  else launch_kernel(ctx, elt_stream_kernel<KIND, false>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
+  launch_kernel(ctx, elt_stream_kernel<KIND>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
 }
 
 }  // namespace
@@ -178,7 +179,8 @@ void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st) {
   a.accumulate = e.accumulate ? 1 : 0;
   // bytes this launch moves; beyond about half of the L2 it streams (evict-first)
   const double bytes = 4.0 * (double)e.n * (1 + (e.kind == ELT_BIAS_ROW ? 0 : e.nreads) + (e.accumulate ? 1 : 0));
-  a.streaming = bytes > 64.0e6 ? 1 : 0;
+  a.streaming = bytes > 64.0e6 ? 7 : 0;
+  if (const char* pol = getenv("EGB_ELT_POLICY")) a.streaming = bytes > 64.0e6 ? atoi(pol) : 0;   // measurement knob
   switch (e.kind) {
 #define EGB_ELT_CASE(K) case K: launch_kind<K>(ctx, a, st); break;
     EGB_ELT_CASE(ELT_COPY) EGB_ELT_CASE(ELT_RELU) EGB_ELT_CASE(ELT_LEAKY) EGB_ELT_CASE(ELT_SIGMOID) EGB_ELT_CASE(ELT_TANH)

@@ -44,6 +44,7 @@ struct SplitMix {
 }  // namespace
 
 Plan::~Plan() {
+  if (window.mapped) comm_close_window(window);
   for (void* b : chain_bufs) cudaFree(b);
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (arena) cudaFree(arena);
@@ -566,7 +567,37 @@ void build_nodes_impl(Model& m, Plan& plan) {
     const Kernel& k = *target.kernels[ki];
     const KernelInfo& inf = info[ki];
     if (inf.absorbed_by >= 0) continue;  // runs inside the epilogue of its contraction
-    if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes) {
+    if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes && plan.window.mapped) {
+      // one fused kernel: gradient exchange through peer memory + the gradientDescent updates it feeds
+      Node n;
+      n.kind = Node::EXCHANGE;
+      ExchangeParams& xp = n.exchange;
+      memset((void*)&xp, 0, sizeof(xp));
+      xp.rank = plan.window.rank;
+      xp.world = plan.window.world;
+      xp.n = (long long)(plan.bucket_bytes / 4);
+      for (int r = 0; r < xp.world; ++r) {
+        xp.bucket[r] = (float*)(plan.window.arena[r] + plan.bucket_off);
+        xp.flags[r] = plan.window.flags[r];
+      }
+      xp.nseg = (int)plan.exchange_segs.size();
+      for (int q = 0; q < xp.nseg; ++q) {
+        xp.seg[q] = plan.exchange_segs[(size_t)q];
+        xp.seg[q].param = (float*)ptrs[plan.exchange_seg_param[(size_t)q]];
+        n.reads.push_back(plan.exchange_seg_param[(size_t)q]);
+        n.writes.push_back(plan.exchange_seg_param[(size_t)q]);
+      }
+      for (auto& kv : plan.tensors) {
+        const char* p0 = (const char*)kv.second.ptr;
+        if (p0 >= plan.arena + plan.bucket_off && p0 < plan.arena + plan.bucket_off + plan.bucket_bytes) {
+          n.reads.push_back(kv.first);
+          n.writes.push_back(kv.first);
+        }
+      }
+      n.label = "peer exchange of the gradient bucket (" + std::to_string(plan.bucket_bytes) + " bytes, " + std::to_string(xp.world) +
+                " ranks) + " + std::to_string(xp.nseg) + " fused gradientDescent updates";
+      plan.nodes.push_back(n);
+    } else if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes) {
       for (auto& seg : plan.bucket_segments) {
         Node n;
         n.kind = Node::ALLREDUCE;
@@ -583,6 +614,7 @@ void build_nodes_impl(Model& m, Plan& plan) {
         plan.nodes.push_back(n);
       }
     }
+    if (inf.in_exchange && plan.window.mapped) continue;  // its update ran inside the exchange kernel
     if (inf.is_gemm && !m.strict) {
       const GemmPattern& g = inf.gemm;
       Node n;
@@ -853,7 +885,7 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   std::set<int> written, read_first, needs_zero;
   size_t plane_bytes = 0;
   // (EGB_DP_FORCE: lay the plan out for data parallelism on a single rank - timing studies of the DP plan)
-  static const bool dp_force = getenv("EGB_DP_FORCE") != nullptr;
+  const bool dp_force = getenv("EGB_DP_FORCE") != nullptr;
   const bool dp = comm && (comm_world(comm) > 1 || dp_force);
   for (size_t ki = 0; ki < nk; ++ki)
     if (target->kernels[ki]->is_generator())
@@ -989,23 +1021,49 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
   // ---- data parallel: the gradients of the parameters form one contiguous bucket that is
   // all-reduced right before the first optimizer kernel (the first kernel that writes a param/cache)
   std::set<int> bucket;
-  if (comm && (comm_world(comm) > 1 || dp_force)) {
-    auto gt = prog->grad_tensors.find(target_name);
-    if (gt != prog->grad_tensors.end()) {
-      for (int pid : prog->params) {
-        auto g = gt->second.find(pid);
-        if (g != gt->second.end() && written.count(g->second)) bucket.insert(g->second);
+  if (dp) {
+    // first optimizer kernel = the first kernel that writes a parameter or a cache (parser.nim:757-766)
+    for (size_t ki = 0; ki < nk; ++ki) {
+      const TensorKind wk = prog->tdef(target->kernels[ki]->write.tensor).kind;
+      if (wk == TensorKind::Param || wk == TensorKind::Cache) {
+        plan->bucket_before_kernel = (int)ki;
+        break;
       }
-      for (size_t ki = 0; ki < target->kernels.size() && !bucket.empty(); ++ki) {
-        const TensorKind wk = prog->tdef(target->kernels[ki]->write.tensor).kind;
-        if (wk == TensorKind::Param || wk == TensorKind::Cache) {
-          plan->bucket_before_kernel = (int)ki;
-          break;
+    }
+    if (plan->bucket_before_kernel >= 0) {
+      std::set<int> before;   // tensors written by the kernels in front of the optimizer block
+      for (int ki = 0; ki < plan->bucket_before_kernel; ++ki) before.insert(target->kernels[(size_t)ki]->write.tensor);
+      auto gt = prog->grad_tensors.find(target_name);
+      if (gt != prog->grad_tensors.end()) {
+        // the gradient table `generate` recorded (it travels with the serialised program)
+        for (int pid : prog->params) {
+          auto g = gt->second.find(pid);
+          if (g != gt->second.end() && written.count(g->second)) bucket.insert(g->second);
+        }
+      } else {
+        // a program compiled elsewhere (passes.nim) carries no table: the gradients are the result tensors of the
+        // backward block that the optimizer kernels read
+        for (size_t ki = (size_t)plan->bucket_before_kernel; ki < nk; ++ki) {
+          const TensorKind wk = prog->tdef(target->kernels[ki]->write.tensor).kind;
+          if (wk != TensorKind::Param && wk != TensorKind::Cache) continue;
+          for (auto& r : target->kernels[ki]->reads)
+            if (prog->tdef(r.tensor).kind == TensorKind::Result && before.count(r.tensor)) bucket.insert(r.tensor);
         }
       }
-      if (plan->bucket_before_kernel < 0) bucket.clear();
+      if (bucket.empty())
+        fail(EGB_ERR_RUNTIME,
+             "data parallel: target %s updates parameters but no parameter-gradient tensors were found - the replicas "
+             "would train on their own shards without averaging", target_name.c_str());
+      // every gradient must be complete when the exchange runs (it sits in front of the first optimizer kernel)
+      for (size_t ki = (size_t)plan->bucket_before_kernel; ki < nk; ++ki)
+        if (bucket.count(target->kernels[ki]->write.tensor))
+          fail(EGB_ERR_RUNTIME,
+               "data parallel: gradient tensor%d is still written (kernel %zu) after the first optimizer kernel (%d) of "
+               "target %s; split the target so that every backward pass precedes its optimizer",
+               target->kernels[ki]->write.tensor - 1, ki, plan->bucket_before_kernel, target_name.c_str());
     }
   }
+  const bool use_peer = dp && !bucket.empty() && dp_peer && comm_world(comm) <= EX_MAX_WORLD;
   // The bucket is laid out in the order in which the gradients become ready (position of the unit that
   // writes them last) and cut into segments of >= 256 KB: every segment is one all-reduce that can
   // start as soon as its gradients exist and overlaps the adjoint kernels of the layers below it.
@@ -1079,6 +1137,37 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
     t.bytes = (size_t)shape_len(t.shape) * 4;
     plan->tensors[id] = t;
   }
+  if (use_peer) {
+    // gradientDescent updates (P += (0 - g) * rate, base.nim:37-38) whose gradient lives in the bucket run inside
+    // the exchange kernel. Hoisting one to the exchange position is valid when nothing between that position and
+    // the kernel touches the parameter or rewrites the gradient.
+    for (size_t ki = (size_t)plan->bucket_before_kernel; ki < nk && (int)plan->exchange_segs.size() < EX_MAX_SEG; ++ki) {
+      const Kernel& c = *target->kernels[ki];
+      KernelInfo& cinf = plan->info[ki];
+      if (cinf.absorbed_by >= 0 || cinf.overwrite) continue;
+      EltSpec es;
+      if (!match_eltwise(c, plan->shapes, es) || es.kind != ELT_SCALE_NEG) continue;
+      const int G = es.read_tensor[0], P = c.write.tensor;
+      if (!bucket.count(G) || prog->tdef(P).kind != TensorKind::Param) continue;
+      if (shape_len(plan->shapes.at(G)) != shape_len(plan->shapes.at(P))) continue;
+      bool clean = true;
+      for (size_t kj = (size_t)plan->bucket_before_kernel; kj < ki && clean; ++kj) {
+        if (plan->info[kj].in_exchange) continue;
+        const Kernel& o = *target->kernels[kj];
+        clean = o.write.tensor != P && o.write.tensor != G;
+        for (auto& r : o.reads) clean = clean && r.tensor != P;
+      }
+      if (!clean) continue;
+      ExchangeSeg sg;
+      sg.off = (long long)((offs.at(G) - plan->bucket_off) / 4);
+      sg.len = (long long)shape_len(plan->shapes.at(G));
+      sg.rate = (float)es.lit[0];
+      plan->exchange_segs.push_back(sg);
+      plan->exchange_seg_param.push_back(P);
+      cinf.in_exchange = true;
+    }
+    comm_open_window(comm, *ctx, plan->arena, plan->arena_bytes, plan->bucket_off, plan->bucket_bytes, plan->window);
+  }
   Plan* raw = plan.get();
   raw->last_used = ++use_clock;
   build_nodes(*raw);
@@ -1110,6 +1199,7 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
                                n.sx_colsum, n.sx_out_hi, n.sx_out_mid, n.sx_ld_out, st);
       break;
     case Node::ELTWISE: launch_eltwise_stream(ctx, n.elt, st); break;
+    case Node::EXCHANGE: launch_exchange(ctx, n.exchange, st); break;
     case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_slots, n.chain_rows, st); break;
     case Node::CONV: {
       const ConvPattern& cv = n.conv;
@@ -1194,6 +1284,7 @@ static void capture_levels(Model& m, Plan& plan) {
       case Node::CONV: cost[i] = 50.0; break;
       case Node::MEMSET: cost[i] = 1.0; break;
       case Node::ALLREDUCE: cost[i] = 30.0; break;
+      case Node::EXCHANGE: cost[i] = 12.0; break;
       default: cost[i] = 4.0;
     }
     longest[i] = cost[i];

@@ -31,6 +31,37 @@ struct EltLaunch {
 bool eltwise_stream_supported(const EltLaunch& e);
 void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st);
 
+// Data-parallel gradient exchange through peer memory (exchange.cu, dist.cu)
+constexpr int EX_MAX_WORLD = 8;    // ranks of one NVSwitch domain
+constexpr int EX_MAX_CTAS = 128;   // CTAs of the exchange kernel (= flag slots per rank)
+constexpr int EX_MAX_SEG = 32;     // parameters whose gradientDescent update is fused into the exchange
+struct ExchangeSeg {
+  long long off = 0, len = 0;      // floats, relative to the bucket
+  float* param = nullptr;
+  float rate = 0.0f;
+  int pad = 0;
+};
+struct ExchangeParams {
+  float* bucket[EX_MAX_WORLD];     // every rank's gradient bucket (own: local pointer, others: IPC mappings)
+  uint32_t* flags[EX_MAX_WORLD];   // every rank's flag area: ready[world][ctas], done[world][ctas], epoch[ctas]
+  ExchangeSeg seg[EX_MAX_SEG];
+  long long n = 0;                 // floats per bucket (multiple of 4)
+  int rank = 0, world = 1, nseg = 0, pad = 0;
+};
+size_t exchange_flag_bytes();
+void launch_exchange(Context& ctx, const ExchangeParams& p, cudaStream_t st);
+
+// Peer mappings of one plan's arena and flag area on every rank (cudaIpc handles exchanged once per plan)
+struct PeerWindow {
+  bool mapped = false;
+  int world = 1, rank = 0;
+  char* arena[EX_MAX_WORLD] = {};      // base of rank r's arena as seen from this process
+  uint32_t* flags[EX_MAX_WORLD] = {};
+  uint32_t* local_flags = nullptr;     // this rank's flag area (owned)
+  void* opened[2 * EX_MAX_WORLD] = {}; // IPC mappings to close
+  int nopened = 0;
+};
+
 struct DevTensor {
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -44,7 +75,7 @@ struct DevTensor {
 };
 
 struct Node {
-  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN, SOFTMAX_XENT, ELTWISE } kind = INTERP;
+  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN, SOFTMAX_XENT, ELTWISE, EXCHANGE } kind = INTERP;
   std::string label;
   // INTERP
   IpProgram ip;
@@ -74,6 +105,8 @@ struct Node {
   int sx_ld_out = 0;
   // ELTWISE: one of the specialised streaming map kernels (eltwise_stream.cu)
   EltLaunch elt;
+  // EXCHANGE: peer-memory gradient exchange + fused gradientDescent (exchange.cu)
+  ExchangeParams exchange;
   // CONV
   ConvPattern conv;
   const float *conv_a = nullptr, *conv_b = nullptr;
@@ -109,6 +142,7 @@ struct KernelInfo {
   int final_tensor = 0;       // tensor that holds the final epilogue value (C or D)
   bool emit_planes = false;   // the epilogue also writes bf16 operand planes of the final value
   int bn = 0, tiles = 0;  // tile width and tile count of a contraction
+  bool in_exchange = false;  // a gradientDescent update that runs inside the data-parallel exchange kernel
 };
 
 struct Plan {
@@ -126,6 +160,9 @@ struct Plan {
   size_t bucket_off = 0, bucket_bytes = 0;  // contiguous parameter-gradient bucket (data parallel)
   std::vector<std::pair<size_t, size_t>> bucket_segments;  // (arena offset, bytes), in order of readiness
   int bucket_before_kernel = -1;            // the all-reduce runs right before this target kernel
+  PeerWindow window;                        // data parallel: peer mappings for the fused exchange kernel
+  std::vector<ExchangeSeg> exchange_segs;   // gradientDescent updates fused into it (param pointers filled at build)
+  std::vector<int> exchange_seg_param;      // their parameter tensor ids
   std::vector<Node> nodes;
   std::vector<void*> chain_bufs;      // device copies of row-chain programs
   std::vector<std::string> notes;     // planner log: why a fusion / fast path was not taken (describe_plan prints it)
@@ -141,6 +178,13 @@ struct Plan {
 struct CommHooks;  // data-parallel extension (dist.cu)
 void comm_all_reduce_avg(CommHooks* c, float* buf, size_t n, cudaStream_t st);
 int comm_world(CommHooks* c);
+int comm_rank(CommHooks* c);
+// Exchange cudaIpc handles of (arena, flag area) with every rank and map the peers' memory. Collective: every
+// rank calls it at the same point (plan construction of the same target). Checks that all ranks laid the bucket
+// out identically.
+void comm_open_window(CommHooks* c, Context& ctx, char* arena, size_t arena_bytes, size_t bucket_off, size_t bucket_bytes,
+                      PeerWindow& w);
+void comm_close_window(PeerWindow& w);
 
 struct Model {
   Context* ctx = nullptr;
@@ -155,6 +199,9 @@ struct Model {
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   bool rowchain = true;     // runs of small row-local kernels execute in one launch
   bool eltwise = true;      // fixed elementwise / optimizer forms run on the specialised streaming kernels
+  // data parallel: exchange the gradient bucket with the fused peer-memory kernel (exchange.cu); off = the
+  // ncclAllReduce(avg) + separate optimizer kernels of round 1 (kept for comparison and as the > 8 rank path)
+  bool dp_peer = true;
   // cluster split-K: contractions with few output tiles spread each tile's reduction over the CTAs of a
   // thread-block cluster (partial tiles meet through distributed shared memory, gemm_tcgen05.cu).
   // (An earlier global-memory variant - RED.ADD partial tiles + last-arriver epilogue - lost on the dense

@@ -40,7 +40,7 @@ def test_activations_and_adjoints(ctx, act, shape):
         pm.set_option("eltwise", elt)
         outs[elt] = (pm.call("y", {"x": x}), pm.call("dx", {"x": x}))
         plan = pm.describe_plan()
-        assert ("eltwise" in plan) == bool(elt), plan
+        assert (" eltwise eltwise " in plan) == bool(elt), plan
         pm.free()
     for i, target in enumerate(("y", "dx")):
         ref = om.call(target, {"x": x})
@@ -71,10 +71,9 @@ def test_optimizer_updates(ctx, opt, n):
     om.params[tid][...] = p0; pm.params[tid] = p0
     for step in range(3):
         g = np.random.default_rng(10 + step).uniform(-1, 1, n).astype(np.float32)
-        om.fit("step", {"g": g[None]}, batch_size=1) if False else None
         om.epoch += 1; om.apply("step", {"g": g})
         pm.set_option("epoch", step + 1); pm.apply("step", {"g": g})
-    assert "eltwise" in pm.describe_plan() and "interp" not in pm.describe_plan(), pm.describe_plan()
+    assert " eltwise eltwise " in pm.describe_plan() and " interp " not in pm.describe_plan(), pm.describe_plan()
     assert_close(pm.params[tid], om.params[tid], tol=2e-6, what=f"{opt} parameter after 3 steps")
     assert_close(pm.params[tid] - p0, om.params[tid] - p0, tol=1e-4, what=f"{opt} update")
     for cid in sorted(om.caches):
@@ -130,7 +129,7 @@ def test_sigmoid_head_runs_in_the_contraction_epilogue(ctx):
         outs.append(pm.call("predict", {"x": x}))
         plan = pm.describe_plan()
         if fuse:
-            assert plan.count("+2 fused") == 2 and "eltwise" not in plan, plan   # bias + activation per layer
+            assert plan.count("+2 fused") == 2 and " eltwise eltwise " not in plan, plan   # bias + activation per layer
         pm.free()
     assert_close(outs[0], ref, tol=1e-5, what="fused tanh/sigmoid epilogues vs oracle")
     assert_close(outs[0], outs[1], tol=1e-6, what="fused vs unfused")
