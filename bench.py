@@ -504,7 +504,8 @@ def run_conv2(args, ctx, timer, rank, world, cpu=True):
         all_ms, all_n = G.kernel_time(ctx, "all")
         G.set_timing(ctx, False)
         targets[target] = {"target_ms": ms / steps, "launches_per_run": all_n / steps, "all_kernels_ms": all_ms / steps}
-        kern[{"conv": "forward", "dw": "d_filters", "dimg": "d_images"}[target]] = k_ms / max(k_n, 1)
+        # per run of the target (d_images is two launches: zero fill of the image gradient + the kernel)
+        kern[{"conv": "forward", "dw": "d_filters", "dimg": "d_images"}[target]] = k_ms / steps
     total = sum(kern.values())
     hdw, hdi = np.empty(CONV_FIL, np.float32), G.pinned_empty(CONV_IMG)
 

@@ -138,7 +138,16 @@ int egb_context_create(int device, egb_context** out) {
   egb_context* ctx = new egb_context();
   ctx->c.device = device;
   ctx->c.sm_count = prop.multiProcessorCount;
-  EGB_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
+  // The context's stream carries the critical path of every launch plan; the side streams that hold the
+  // parallel branches of a captured graph keep the default (lowest) priority, so when both compete for SMs the
+  // critical path's CTAs are placed first. EGB_STREAM_PRIORITY=0 restores equal priorities (measurement knob).
+  {
+    int least = 0, greatest = 0;
+    EGB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    const char* pr = getenv("EGB_STREAM_PRIORITY");
+    const int prio = (pr && atoi(pr) == 0) ? least : greatest;
+    EGB_CUDA(cudaStreamCreateWithPriority(&ctx->c.stream, cudaStreamNonBlocking, prio));
+  }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   EGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -403,7 +412,11 @@ int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t 
   const int64_t a_ld = (a_pcol + 7) & ~int64_t(7), b_ld = (b_pcol + 7) & ~int64_t(7);
   const size_t a_plane = (size_t)a_prow * a_ld * 2, b_plane = (size_t)b_prow * b_ld * 2;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  char* ws = (char*)c.ensure_scratch(2 * al(a_plane) + 2 * al(b_plane));
+  const size_t planes_total = 2 * al(a_plane) + 2 * al(b_plane);
+  const size_t tail_ws = al(gemm_2cta_workspace_bytes(c.sm_count));
+  const size_t scratch_before = c.scratch_bytes;
+  char* ws = (char*)c.ensure_scratch(planes_total + tail_ws);
+  if (c.scratch_bytes != scratch_before) c.scratch_tail_ws_zeroed = false;   // a new allocation: flags are garbage
   __nv_bfloat16* a_hi = (__nv_bfloat16*)ws;
   __nv_bfloat16* a_mid = (__nv_bfloat16*)(ws + al(a_plane));
   __nv_bfloat16* b_hi = (__nv_bfloat16*)(ws + 2 * al(a_plane));
@@ -416,6 +429,16 @@ int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t 
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.C = C; g.ldc = (int)ldc; g.flags = flags & 3; g.bias = bias; g.alpha = alpha;
   if (flags & 4) { g.epi = EPI_RELU; g.D = C; }
+  if (gemm_2cta_eligible(g)) {
+    // tail-wave split workspace behind the planes (its 4 KB of flags must start out as zero)
+    g.ws = ws + planes_total;
+    g.ws_bytes = tail_ws;
+    if (!c.scratch_tail_ws_zeroed || c.scratch_tail_ws != g.ws) {
+      EGB_CUDA(cudaMemsetAsync(g.ws, 0, 4096, c.stream));
+      c.scratch_tail_ws_zeroed = true;
+      c.scratch_tail_ws = g.ws;
+    }
+  }
   launch_gemm_bf16x3(c, g, c.stream);
   EGB_CATCH
 }

@@ -352,6 +352,13 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
       m->m->last_plan = nullptr;
     }
     m->m->rowchain = value != 0;
+  } else if (k == "keep_intermediates") {
+    if (m->m->keep_intermediates != (value != 0)) {
+      EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
+      m->m->plans.clear();
+      m->m->last_plan = nullptr;
+    }
+    m->m->keep_intermediates = value != 0;
   } else if (k == "dp_peer") {
     if (m->m->dp_peer != (value != 0)) {
       EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
@@ -394,6 +401,9 @@ static DevTensor* find_tensor(egb_model* m, int tensor_id) {
   auto s = m->m->state.find(tensor_id);
   if (s != m->m->state.end()) return &s->second;
   if (m->m->last_plan) {
+    if (m->m->last_plan->unmaterialized.count(tensor_id))
+      fail(EGB_ERR_RUNTIME, "tensor%d is consumed inside a fused contraction epilogue and never stored by this plan; set the "
+                            "model option keep_intermediates=1 to materialise every intermediate", tensor_id - 1);
     auto t = m->m->last_plan->tensors.find(tensor_id);
     if (t != m->m->last_plan->tensors.end()) return &t->second;
   }

@@ -49,6 +49,8 @@ struct Context {
   size_t scratch_bytes = 0;
   size_t launches = 0;  // number of kernel launches issued through this context
   void* ensure_scratch(size_t bytes);
+  bool scratch_tail_ws_zeroed = false;   // standalone GEMM entry point: tail-wave split flags inside the scratch
+  void* scratch_tail_ws = nullptr;
 
   // auxiliary streams + events used to capture independent plan nodes as parallel graph branches
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
@@ -159,6 +161,11 @@ enum GemmFlags {
   GEMM_BIAS = 2,        // + bias[col]     (row-broadcast add, reference dnn.nim:22-24)
   GEMM_RELU = 4,        // (raw entry point only) shorthand for epi = EPI_RELU with D = C
   GEMM_SPLIT_OUT = 8,   // additionally emit bf16 hi/mid planes of the final value
+  // Dead-store elimination (planner): the fp32 form of C / D is consumed inside this epilogue only (fused stages,
+  // column sums, operand planes) and no later kernel reads it - it is computed in registers but not stored.
+  // (The epilogue stores of the dense step are L2-write bound: 6 MB per contraction, profiles/r02b_gemm_trace.txt.)
+  GEMM_SKIP_C = 64,
+  GEMM_SKIP_D = 128,
 };
 
 // Second epilogue stage: one reference kernel fused behind the contraction. v = value stored to C.
@@ -198,11 +205,16 @@ struct GemmArgs {
   int bn = 0;        // 0 = choose
   int cluster_k = 0; // cluster split-K factor: 0 = choose, 1 = off, 2/4/8 = CTAs per output tile
   int sm_budget = 0; // SMs this launch may plan for (0 = all): contractions that run concurrently share the machine
+  // 2-CTA kernel, tail-wave split: zero-initialised workspace of gemm_2cta_workspace_bytes() owned by the caller
+  // (exclusive to this launch site while it runs), or null = whole tiles only
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
 };
 
 // 2-CTA (cta_group::2) variant for large K-major problems with a plain epilogue (gemm_tcgen05_2cta.cu)
 bool gemm_2cta_eligible(const GemmArgs& a);
 void launch_gemm_bf16x3_2cta(Context& ctx, const GemmArgs& a, cudaStream_t st);
+size_t gemm_2cta_workspace_bytes(int sm_count);
 void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* tiles);
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);

@@ -379,7 +379,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (need_c) {
           x[0] += oldc[i].x; x[1] += oldc[i].y; x[2] += oldc[i].z; x[3] += oldc[i].w;
         }
-        if (full) {
+        if (p.flags & GEMM_SKIP_C) {
+          // dead store: nothing reads the fp32 C after this epilogue
+        } else if (full) {
           *reinterpret_cast<float4*>(p.C + off) = make_float4(x[0], x[1], x[2], x[3]);
         } else {
 #pragma unroll
@@ -415,7 +417,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fadd_rn(a2[e], __fmul_rn(0.0f - x[e], p.epi_param));
           }
-          if (p.epi != EPI_NONE) {
+          if (p.epi != EPI_NONE && !(p.flags & GEMM_SKIP_D)) {
             if (full) {
               *reinterpret_cast<float4*>(p.D + off) = make_float4(x[0], x[1], x[2], x[3]);
             } else {
@@ -594,7 +596,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
       __syncwarp();
-      ptx::cluster_arrive();
+      ptx::cluster_arrive_relaxed();   // "done reading the peers' staging buffers": nothing to publish
       if (threadIdx.x == 128) EGB_TRACE(16);
 #pragma unroll
       for (int k = 0; k < MAX_U; ++k) {
@@ -611,6 +613,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         finish_unit(v[k], pre, m0 + (int)crank * rows_per + g * 32, col0);
       }
       __syncwarp();
+      if (threadIdx.x == 128) EGB_TRACE(17);
       ptx::cluster_wait();  // peers may still be reading this CTA's staging buffer until here
     }
   }
@@ -620,7 +623,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // non-epilogue warps take part in the two cluster barriers of the split-K reduction
     __syncwarp();
     ptx::cluster_sync_all();
-    ptx::cluster_arrive();
+    ptx::cluster_arrive_relaxed();
     ptx::cluster_wait();
   }
   ptx::tc_fence_before();

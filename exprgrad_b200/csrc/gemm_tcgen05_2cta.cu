@@ -8,6 +8,13 @@
 // cores of both SMs read B from both shared memories. Per CTA and k-block that is 64 KB instead of
 // 96 KB for the same MMA work.
 //
+// Tail wave ("stream-K" over the last wave only): 4096^3 has 256 pair tiles for 74 CTA pairs = 3.46 waves, so the
+// fourth wave ran 46 % full at the length of a whole wave. When the remainder tiles fit the machine twice or more,
+// each of them is cut along K into `split` units that run side by side in the last wave: the units with part > 0
+// park their raw fp32 accumulators in a global workspace (coalesced, L2-resident: 256 KB per unit) and bump a
+// flag; the part-0 unit of the tile waits for the flag, adds the parked partials to its own accumulator (fixed
+// order) and runs the normal epilogue. No atomics on data, no zero fill; flags clean themselves for the next launch.
+//
 // Roles per CTA (256 threads): warp 0 TMA producer (completion bytes of both CTAs are signalled on the
 // LEADER's full barrier), warp 1 MMA issuer (leader CTA only; commits multicast to both CTAs), warp 2
 // TMEM allocator (`cta_group::2` alloc in both CTAs), warps 4-7 epilogue (each CTA drains its own 128
@@ -38,7 +45,35 @@ struct K2Params {
   int tiles_m, tiles_n;  // pair tiles: 256 x 256
   int accumulate;
   float alpha;
+  // tail wave: tiles [0, full_units) are whole units, every later tile is `split` units of kbps k-blocks each
+  int full_units, split, kbps, num_units;
+  unsigned int* ws_flags;   // per split tile: {arrived, consumed}
+  float4* ws_data;          // per split tile, part - 1, CTA of the pair: 128 x 256 fp32 in (chunk, j4, row) order
 };
+
+struct Unit {
+  int tile, kb0, kb1, part, parts, slot;
+};
+__device__ __forceinline__ Unit get_unit(int u, const K2Params& p, int num_kb) {
+  Unit r;
+  if (u < p.full_units) {
+    r.tile = u; r.kb0 = 0; r.kb1 = num_kb; r.part = 0; r.parts = 1; r.slot = 0;
+  } else {
+    const int v = u - p.full_units;
+    r.slot = v / p.split;
+    r.tile = p.full_units + r.slot;
+    r.part = v % p.split;
+    r.parts = p.split;
+    r.kb0 = r.part * p.kbps;
+    r.kb1 = min(num_kb, r.kb0 + p.kbps);
+  }
+  return r;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   // arrive on the barrier at the same offset in CTA 0 of the pair (peer bit cleared)
@@ -56,7 +91,6 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
   const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int num_tiles = p.tiles_m * p.tiles_n;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES2;
@@ -95,10 +129,12 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     {
       pdl_wait();
       uint32_t it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int u = pair; u < p.num_units; u += num_pairs) {
+        const Unit un = get_unit(u, p, num_kb);
+        const int tile = un.tile;
         const int m0 = (tile % p.tiles_m) * 2 * BM2 + (int)rank * BM2;   // this CTA's A rows
         const int n0 = (tile / p.tiles_m) * BN2 + (int)rank * (BN2 / 2); // this CTA's half of B
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = un.kb0; kb < un.kb1; ++kb, ++it) {
           const int s = it % STAGES2;
           const uint32_t ph = (it / STAGES2) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
@@ -121,13 +157,14 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       // instruction descriptor for the pair: M = 256, N = 256, bf16 x bf16 -> fp32, both K-major
       const uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BM2, BN2);
       uint32_t it = 0, local_tile = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local_tile) {
+      for (int u = pair; u < p.num_units; u += num_pairs, ++local_tile) {
+        const Unit un = get_unit(u, p, num_kb);
         const uint32_t acc = local_tile & 1;
         const uint32_t use = local_tile >> 1;
         ptx::mbar_wait(&tmem_empty[acc], (use & 1) ^ 1, 2);   // both CTAs drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = un.kb0; kb < un.kb1; ++kb, ++it) {
           const int s = it % STAGES2;
           const uint32_t ph = (it / STAGES2) & 1;
           ptx::mbar_wait(&full_bar[s], ph, 3);   // the planes of both CTAs have landed
@@ -141,12 +178,12 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-              ptx::umma_f16<2>(d_tmem, a_mid + adv, b_hi + adv, idesc, (kb | k) != 0);
+              ptx::umma_f16<2>(d_tmem, a_mid + adv, b_hi + adv, idesc, (kb != un.kb0) || (k != 0));
               ptx::umma_f16<2>(d_tmem, a_hi + adv, b_mid + adv, idesc, 1);
               ptx::umma_f16<2>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
             }
             ptx::umma_commit_cta2(&empty_bar[s], 3);                        // slot free in both CTAs
-            if (kb == num_kb - 1) ptx::umma_commit_cta2(&tmem_full[acc], 3); // accumulators complete in both
+            if (kb == un.kb1 - 1) ptx::umma_commit_cta2(&tmem_full[acc], 3); // accumulators complete in both
           }
           __syncwarp();
         }
@@ -157,7 +194,9 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     const int q = warp & 3;
     uint32_t local_tile = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local_tile) {
+    for (int u = pair; u < p.num_units; u += num_pairs, ++local_tile) {
+      const Unit un = get_unit(u, p, num_kb);
+      const int tile = un.tile;
       const uint32_t acc = local_tile & 1;
       const uint32_t use = local_tile >> 1;
       const int m0 = (tile % p.tiles_m) * 2 * BM2 + (int)rank * BM2;
@@ -166,10 +205,60 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       ptx::tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+      const int row_local = q * 32 + lane;
+      unsigned int* const flag = p.ws_flags + 2 * un.slot;
+      if (un.parts > 1 && un.part > 0) {
+        // ---- contributor: park the raw accumulator rows of this CTA (chunk, j4, row order: coalesced 512-byte runs)
+        float4* const dst = p.ws_data + ((size_t)(un.slot * (un.parts - 1) + (un.part - 1)) * 2 + rank) * (BM2 * BN2 / 4);
+        for (int c = 0; c < BN2; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            dst[((c >> 2) + (j >> 2)) * BM2 + row_local] = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+        __threadfence();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          atomicAdd(flag, 1u);
+          mbar_arrive_leader(&tmem_empty[acc]);
+        }
+        continue;
+      }
+      if (un.parts > 1) {
+        // ---- finisher: the other parts of this tile (8 epilogue warps each: 4 per CTA of their pair) have parked
+        if (lane == 0) {
+          const unsigned int need = 8u * (unsigned)(un.parts - 1);
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(flag) < need) {
+            if (clock64() - t0 > 4000000000ll) {
+              printf("egb gemm: split tile %d never received its partial sums\n", tile);
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+      }
       for (int c = 0; c < BN2; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
         ptx::tmem_ld_wait();
+        if (un.parts > 1) {
+          for (int part = 1; part < un.parts; ++part) {
+            const float4* src = p.ws_data + ((size_t)(un.slot * (un.parts - 1) + (part - 1)) * 2 + rank) * (BM2 * BN2 / 4);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldcg(src + ((c >> 2) + (j >> 2)) * BM2 + row_local);
+              r[j] = __float_as_uint(__uint_as_float(r[j]) + t.x);
+              r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + t.y);
+              r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + t.z);
+              r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + t.w);
+            }
+          }
+        }
         const int col0 = n0 + c;
         if (col0 >= p.N) break;
         if (row >= p.M) continue;
@@ -197,7 +286,13 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (lane == 0) {
+        mbar_arrive_leader(&tmem_empty[acc]);
+        if (un.parts > 1 && atomicAdd(flag + 1, 1u) == 7u) {   // last of the 8 finisher warps: reset for the next launch
+          flag[0] = 0u;
+          flag[1] = 0u;
+        }
+      }
     }
   }
 
@@ -234,6 +329,13 @@ bool gemm_2cta_eligible(const GemmArgs& a) {
   return a.M >= 512 && a.N >= 256 && a.K >= 256 && pair_tiles >= 64;
 }
 
+// workspace of the tail-wave split: flags (4 KB) + one parked 256 x 256 fp32 partial per remainder tile (at most
+// pairs / 2 of them at split 2). Must be zero when first used (flags); the kernel leaves the flags zeroed.
+size_t gemm_2cta_workspace_bytes(int sm_count) {
+  const size_t pairs = (size_t)sm_count / 2;
+  return 4096 + (pairs / 2) * (size_t)(2 * BM2) * BN2 * sizeof(float);
+}
+
 void launch_gemm_bf16x3_2cta(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   K2Params p;
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K;
@@ -255,6 +357,27 @@ void launch_gemm_bf16x3_2cta(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   const int tiles = p.tiles_m * p.tiles_n;
   int pairs = ctx.sm_count / 2;
   if (pairs > tiles) pairs = tiles;
+  // tail wave: cut the remainder tiles along K when at least two units of each fit the last wave
+  const int num_kb = (a.K + BK - 1) / BK;
+  p.full_units = tiles;
+  p.split = 1;
+  p.kbps = num_kb;
+  p.ws_flags = nullptr;
+  p.ws_data = nullptr;
+  static const bool no_tail = getenv("EGB_GEMM_NO_TAIL_SPLIT") != nullptr;
+  const int rem = tiles % pairs;
+  if (!no_tail && a.ws && rem > 0 && tiles > pairs && 2 * rem <= pairs && num_kb >= 16) {
+    const int split = 2;   // (deeper splits would shorten the tail further but multiply the parked traffic)
+    const size_t need = gemm_2cta_workspace_bytes(ctx.sm_count);
+    if (a.ws_bytes >= need) {
+      p.full_units = tiles - rem;
+      p.split = split;
+      p.kbps = (num_kb + split - 1) / split;
+      p.ws_flags = reinterpret_cast<unsigned int*>(a.ws);
+      p.ws_data = reinterpret_cast<float4*>(reinterpret_cast<char*>(a.ws) + 4096);
+    }
+  }
+  p.num_units = p.full_units + (tiles - p.full_units) * p.split;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);

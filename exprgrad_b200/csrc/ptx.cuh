@@ -305,6 +305,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void cluster_arrive() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 }
+// arrive without release semantics: signals "this thread has finished READING its peers' shared memory"
+// (the values were already consumed), publishes nothing
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

@@ -673,6 +673,15 @@ void build_nodes_impl(Model& m, Plan& plan) {
         n.gemm.flags |= GEMM_SPLIT_OUT;
         plane_cursor += 2 * bytes;
       }
+      if (gemm_2cta_eligible(n.gemm)) {
+        // workspace of the tail-wave split (gemm_tcgen05_2cta.cu): zeroed with the arena, flags clean themselves
+        const size_t wsb = align_up(gemm_2cta_workspace_bytes(ctx.sm_count), 256);
+        if (plane_cursor + wsb <= plane_cap) {
+          n.gemm.ws = plane_base + plane_cursor;
+          n.gemm.ws_bytes = wsb;
+          plane_cursor += wsb;
+        }
+      }
       plan.nodes.push_back(n);
       if (inf.emit_planes) planes[std::make_pair(inf.final_tensor, 0)] = std::make_pair(n.gemm.out_hi, n.gemm.out_mid);
     } else if (inf.is_conv && !m.strict) {
@@ -828,6 +837,41 @@ void build_nodes_impl(Model& m, Plan& plan) {
         n.label += " sm<=" + std::to_string(budget);
       }
   }
+  // Dead-store elimination: the fp32 form of a contraction's C / D tensor that only its own epilogue consumes
+  // (fused stages, column sums, operand planes) and no later node reads is not written to memory - the same
+  // reasoning as the reference's deadKernelElim (passes.nim:331-350), applied to stores. The epilogues of the
+  // dense step are bound by L2 write bandwidth (C + D + two planes = 6 MB per contraction); this removes a third
+  // to two thirds of it. Option keep_intermediates=1 materialises everything (egb_model_read_tensor on such a
+  // tensor otherwise fails loudly).
+  plan.unmaterialized.clear();
+  if (m.fuse && !m.strict && !m.keep_intermediates) {
+    for (size_t i = 0; i < plan.nodes.size(); ++i) {
+      Node& n = plan.nodes[i];
+      if (n.kind != Node::GEMM || n.kernel_index < 0 || (n.gemm.flags & GEMM_ACCUMULATE)) continue;
+      const KernelInfo& inf = info[(size_t)n.kernel_index];
+      auto dead = [&](int t) {
+        if (t <= 0 || t == target.output || m.prog->tdef(t).kind != TensorKind::Result) return false;
+        for (size_t j = i + 1; j < plan.nodes.size(); ++j)
+          for (auto r : plan.nodes[j].reads)
+            if (r == t) return false;
+        return true;
+      };
+      const int c_t = inf.gemm.c_tensor, d_t = inf.d_tensor;
+      // C is needed in memory unless some fused consumer exists at all (else the contraction itself would be dead)
+      const bool has_consumer = inf.epi != EPI_NONE || inf.colsum_tensor || inf.emit_planes;
+      if (has_consumer && dead(c_t) && (inf.epi != EPI_NONE || inf.final_tensor == c_t)) {
+        n.gemm.flags |= GEMM_SKIP_C;
+        plan.unmaterialized.insert(c_t);
+      }
+      if (d_t && inf.epi != EPI_NONE && inf.epi != EPI_SGD && (inf.colsum_tensor || inf.emit_planes) && dead(d_t)) {
+        n.gemm.flags |= GEMM_SKIP_D;
+        plan.unmaterialized.insert(d_t);
+      }
+      if (n.gemm.flags & (GEMM_SKIP_C | GEMM_SKIP_D))
+        n.label += std::string(" [fp32") + ((n.gemm.flags & GEMM_SKIP_C) ? " C" : "") + ((n.gemm.flags & GEMM_SKIP_D) ? " D" : "") +
+                   " not stored]";
+    }
+  }
   for (auto& n : plan.nodes)
     if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
   plan.epoch_built = m.epoch;
@@ -931,6 +975,7 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
       const size_t a_bytes = std::max((size_t)g.K * pad8(g.M), (size_t)g.M * pad8(g.K)) * 2;
       const size_t b_bytes = std::max((size_t)g.N * pad8(g.K), (size_t)g.K * pad8(g.N)) * 2;
       plane_bytes += 2 * align_up(a_bytes, 256) + 2 * align_up(b_bytes, 256);
+      if (g.M >= 512 && g.N >= 256 && g.K >= 256) plane_bytes += align_up(gemm_2cta_workspace_bytes(ctx->sm_count), 256);  // tail-wave split
       const bool b_copy = !g.trans_b && prefer_transposed_copy(g.K, g.N);
       gemm_choose_config((int)g.M, (int)g.N, (int)g.K, !g.trans_b && !b_copy, ctx->sm_count, &inf.bn, &inf.tiles);
     }

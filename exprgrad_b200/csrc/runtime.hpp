@@ -7,6 +7,7 @@
 #pragma once
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -164,6 +165,7 @@ struct Plan {
   std::vector<ExchangeSeg> exchange_segs;   // gradientDescent updates fused into it (param pointers filled at build)
   std::vector<int> exchange_seg_param;      // their parameter tensor ids
   std::vector<Node> nodes;
+  std::set<int> unmaterialized;       // result tensors whose fp32 form the fused plan never stores (dead stores)
   std::vector<void*> chain_bufs;      // device copies of row-chain programs
   std::vector<std::string> notes;     // planner log: why a fusion / fast path was not taken (describe_plan prints it)
   cudaGraphExec_t graph_exec = nullptr;
@@ -199,6 +201,7 @@ struct Model {
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   bool rowchain = true;     // runs of small row-local kernels execute in one launch
   bool eltwise = true;      // fixed elementwise / optimizer forms run on the specialised streaming kernels
+  bool keep_intermediates = false;  // store every fp32 intermediate even when only a fused epilogue consumes it
   // data parallel: exchange the gradient bucket with the fused peer-memory kernel (exchange.cu); off = the
   // ncclAllReduce(avg) + separate optimizer kernels of round 1 (kept for comparison and as the > 8 rank path)
   bool dp_peer = true;

@@ -93,7 +93,10 @@ def test_bias_row_add_and_arithmetic(ctx):
         r[i, j] += x[i, j]
         i, j = F.Iter("y"), F.Iter("x")
         r[i, j] += bp[j]
-        return [r.target("biased", "gpu"), PL.add(x, y).target("sum", "gpu"), PL.sub(x, y).target("diff", "gpu"),
+        # a raw write with two reads carries no shape constraint (passes.nim:1059-1095): copyShape like a user would
+        s2, d2 = PL.add(x, y), PL.sub(x, y)
+        s2.copy_shape(x); d2.copy_shape(x)
+        return [r.target("biased", "gpu"), s2.target("sum", "gpu"), d2.target("diff", "gpu"),
                 PL.scale(x, 2.5).target("scaled", "gpu"), PL.divide(x, 3.0).target("divided", "gpu")]
     pm = M.compile(*net(), gpu=ctx, seed=0)
     pm.params[pm.params.ids()[0]] = bias

@@ -229,14 +229,41 @@ def test_conv2_full_size_properties(ctx):
     pm.free()
 
 
+def _conv2_exact(img, w):
+    """fp64 d_filters and d_images of loss = sum(out^2) (d_out = 2 out), image by image (the 3.2 GB forward
+    output is not kept)."""
+    n, h, wd, c = img.shape
+    f, kh, kw, _ = w.shape
+    oh, ow = h - kh + 1, wd - kw + 1
+    w64 = w.astype(np.float64)
+    wmat = w64.reshape(f, kh * kw * c).T                       # [taps, F]
+    dw = np.zeros((kh, kw, c, f), np.float64)
+    dimg = np.zeros(img.shape, np.float64)
+    for i in range(n):
+        im = img[i].astype(np.float64)
+        cols = np.stack([im[dy:dy + oh, dx:dx + ow, :] for dy in range(kh) for dx in range(kw)], axis=2)  # [oh,ow,9,c]
+        o = cols.reshape(oh * ow, kh * kw * c) @ wmat            # [pixels, F]
+        dout = 2.0 * o
+        dw += (cols.reshape(oh * ow, kh * kw * c).T @ dout).reshape(kh, kw, c, f)
+        dcols = (dout @ wmat.T).reshape(oh, ow, kh, kw, c)
+        for dy in range(kh):
+            for dx in range(kw):
+                dimg[i, dy:dy + oh, dx:dx + ow, :] += dcols[:, :, dy, dx, :]
+    return np.transpose(dw, (3, 0, 1, 2)), dimg
+
+
 def test_conv2_full_size_matches_oracle(ctx):
     """BASELINE config 4 at full size, element by element (benchmarks/conv2/conv2.nim:337-338 input ranges):
-    the forward convolution, d_filters and d_images of the whole 256x224x224x3 batch against the oracle's
-    threaded loop nests. The adjoint targets are compared on their own outputs; their loss = sum(out^2)
-    makes d_out = 2 * out, so all three tensor-core kernels see full-size data."""
+    forward, d_filters and d_images of the whole 256x224x224x3 batch against the oracle's threaded loop nests AND
+    against an exact fp64 evaluation.
+    Forward and d_images: within the 1e-4 bar of the oracle. d_filters sums 12.6 M products per filter tap; the
+    reference adds them sequentially in fp32 (llvmgen.nim:277-297), which at this length loses ~1e-2 of the result
+    (the running sum reaches 4e7 where one ulp is 4) - the reference's value is only defined to within that error.
+    The device result must be within 1e-4 of the exact value and inside the reference's own error band."""
     from exprgrad_b200 import frontend as F, layers as PL, model as M
     import oracle as o
     from oracle import layers as OL
+    from parity_cases import norm_err
     filters = (64, 3, 3, 3)
     w = np.random.default_rng(1).uniform(-2, 2, filters).astype(np.float32)
     img = np.random.default_rng(0).uniform(0, 1, (256, 224, 224, 3)).astype(np.float32)
@@ -244,12 +271,21 @@ def test_conv2_full_size_matches_oracle(ctx):
     om.params[sorted(om.params)[0]][...] = w
     pm = M.compile(*G.conv2_net(F, PL, filters=filters), gpu=ctx, seed=0)
     pm.params[pm.params.ids()[0]] = w
+    exact = dict(zip(("dw", "dimg"), _conv2_exact(img, w)))
     for target in ("conv", "dw", "dimg"):
         ref = om.call(target, {"img": img})
         got = pm.call(target, {"img": img})
         assert "conv conv2" in pm.describe_plan()
-        e = assert_close(got, ref, what=f"full-size {target}")
-        print(f"conv2 256x224x224x3 {target}: normalised max error vs oracle {e:.2e}")
+        e_ref = norm_err(got, ref)
+        # (forward: 27 terms per output, the oracle itself is exact to fp32 rounding)
+        e_exact, ref_exact = (norm_err(got, exact[target]), norm_err(ref, exact[target])) if target in exact else (e_ref, 0.0)
+        print(f"conv2 256x224x224x3 {target}: device vs oracle {e_ref:.2e}, device vs fp64 {e_exact:.2e}, oracle vs fp64 {ref_exact:.2e}")
+        assert e_exact <= 1e-4, f"{target}: device vs exact {e_exact:.3e}"
+        # within the bar of the reference value, or - where the reference's own sequential fp32 sum is further than
+        # that from the exact result - inside the reference's error band
+        assert e_ref <= max(1e-4, 2.0 * ref_exact), f"{target}: device vs oracle {e_ref:.3e} (oracle vs exact {ref_exact:.3e})"
+        if target != "dw":
+            assert e_ref <= 1e-4, f"{target}: device vs oracle {e_ref:.3e}"
         del ref, got
     pm.free()
 

@@ -39,4 +39,4 @@ print("  start_us   end_us | setup  pdlwait  1st-load  mainloop  epilogue  exit 
 for r in last:
     clk = lambda a, b: (r[b] - r[a]) / 1965.0 if r[a] and r[b] else float("nan")
     print(f"{(r[0]-t0)/1e3:9.2f} {(r[8]-t0)/1e3:9.2f} | {clk(1,2):5.2f} {clk(2,3):7.2f} {clk(3,4):8.2f} {clk(4,5):9.2f} {clk(5,6):9.2f} {clk(6,7):5.2f} | "
-          + " ".join(str(v) for v in r[9:15]) + (f" | epi unit0: tmem_ld {clk(5,15):.2f} transpose {clk(15,16):.2f} finish {clk(16,17):.2f}" if r[13] <= 1 else f" | csk: stage+sync {clk(5,15):.2f} reduce+finish {clk(15,16):.2f} sync {clk(16,6):.2f}"))
+          + " ".join(str(v) for v in r[9:15]) + (f" | epi unit0: tmem_ld {clk(5,15):.2f} transpose {clk(15,16):.2f} finish {clk(16,17):.2f}" if r[13] <= 1 else f" | csk: stage+sync {clk(5,15):.2f} dsmem-reduce {clk(15,16):.2f} finish {clk(16,17):.2f} cluster-wait {clk(17,6):.2f}"))

@@ -8,6 +8,10 @@ echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
 echo "== bench" ; timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/${TAG}_bench.err | tee gpurun_out/${TAG}_bench.json | cut -c1-1500
 tail -5 gpurun_out/${TAG}_bench.err
 echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 2>>gpurun_out/${TAG}_bench.err | tee gpurun_out/${TAG}_bench_ref.json | cut -c1-400
+echo "== dense step timeline"
+timeout 300 python tools/gemm_trace.py 2>&1 | tail -32 | tee gpurun_out/${TAG}_gemm_trace.txt
+echo "-- equal stream priorities"
+EGB_STREAM_PRIORITY=0 timeout 300 python tools/gemm_trace.py 2>&1 | grep "step us"
 echo "== eltwise policy probe"
 for mode in 7 0 1 3 5; do
   echo "-- EGB_ELT_POLICY=$mode"
