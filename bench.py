@@ -367,6 +367,8 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None, batch=DENSE_BAT
     for tid, v in zip(model.params.ids(), params):
         model.params[tid] = v
     if comm is not None and world > 1:
+        if os.environ.get("EGB_DP_NCCL"):
+            model.set_option("dp_peer", 0)   # comparison arm: ncclAllReduce(avg) + separate optimizer kernels
         D.set_data_parallel(model, comm)
     lo, hi = D.shard_rows(B * world, rank, world)
     hx, hy = G.pinned_empty((B, DENSE_SIZES[0])), G.pinned_empty((B, DENSE_SIZES[-1]))

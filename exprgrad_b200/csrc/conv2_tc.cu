@@ -20,8 +20,12 @@
 //   warps 0-3  producers: one pixel each - KH*KW*C loads, split, 8 swizzled 16-byte stores
 //   warp  4    MMA issuer (elect.sync-guarded, convergent warp)
 //   warp  5    TMEM allocator
-//   warps 6-9  epilogue: tcgen05.ld -> padded staging -> 512-byte coalesced stores (a warp's 32 pixels x F
-//              floats are one contiguous 8 KB run of the NHWC output)
+//   warps 6-9  epilogue: tcgen05.ld -> padded staging tile in shared memory -> ONE TMA tensor store per warp and
+//              tile (cp.async.bulk.tensor: a warp's 32 pixels x F floats are a contiguous 8 KB run of the NHWC
+//              output; the box is F + 4 floats wide like the padded tile and the tensor map clips the padding).
+//              The LSU no longer re-reads the tile and issues no global stores: ncu had the kernel at 0.66 of
+//              the HBM roofline with the producers' gathers, the staging traffic and the store loop all
+//              competing for the same load/store pipe. (An accumulating convolution keeps the store loop.)
 #include <stdlib.h>
 
 #include "egb_internal.hpp"
@@ -45,6 +49,7 @@ struct TcParams {
   long total;   // output pixels
   int ntiles;
   int accumulate;
+  int tma_store;   // epilogue stores through the output tensor map
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -66,7 +71,7 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& h, uint
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int KH, int KWC>
-__global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_out, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -209,6 +214,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
       ptx::mbar_wait_sleepy(&tmem_full[acc], (it >> 1) & 1, 14);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)F;
+      if (p.tma_store) {
+        // the previous tile's tensor store must have finished reading the staging tile (it had a whole tile period)
+        if (lane == 0) ptx::bulk_wait_group_read0();
+        __syncwarp();
+      }
       for (int c = 0; c < F; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
@@ -218,9 +228,18 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(mine + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
       ptx::tc_fence_before();
+      if (p.tma_store) ptx::fence_proxy_async();   // this lane's staging writes -> visible to the TMA engine
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);   // the accumulator is free while the tile streams out
       const long pix0 = (long)tile * TILE_P + q * 32;
+      if (p.tma_store) {
+        // rows past the last pixel and the 4 padding columns of every row lie outside the tensor: not written
+        if (lane == 0 && pix0 < p.total) {
+          ptx::tma_store_2d(&tm_out, stage, 0, (int)pix0);
+          ptx::bulk_commit_group();
+        }
+        continue;
+      }
       const long left = p.total - pix0;
       const int nrows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
       float* dst = p.out + (size_t)pix0 * F;   // nrows * F contiguous floats
@@ -238,6 +257,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const TcParams
       }
       __syncwarp();   // the staging rows are rewritten by the next tile
     }
+    if (p.tma_store && lane == 0) ptx::bulk_wait_group0();   // every tensor store has landed before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -832,16 +852,31 @@ void launch_conv2_fwd_tc(Context& ctx, const float* img, const float* w, float* 
   if (p.total <= 0) return;
   p.ntiles = (int)((p.total + TILE_P - 1) / TILE_P);
   p.accumulate = accumulate ? 1 : 0;
+  // output as a 2-D tensor [pixels, F] with a box of 32 pixels x (F + OUT_PAD) floats = the padded staging tile
+  CUtensorMap tm_out;
+  memset(&tm_out, 0, sizeof(tm_out));
+  static const bool no_tma_store = getenv("EGB_CONV_NO_TMA_STORE") != nullptr;
+  p.tma_store = 0;
+  if (!accumulate && !no_tma_store && ctx.encode_tiled && p.total < (long)1 << 31) {
+    cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)p.total};
+    cuuint64_t strides[1] = {(cuuint64_t)F * 4};
+    cuuint32_t box[2] = {(cuuint32_t)(F + OUT_PAD), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx.encode_tiled(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)out, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    p.tma_store = r == CUDA_SUCCESS ? 1 : 0;
+  }
   const size_t smem = tc_smem_bytes(F);
   int grid = ctx.sm_count * 2;
   if (grid > p.ntiles) grid = p.ntiles;
   Launch l(ctx, KC_CONV, st);
   if (C == 3) {
     EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_tc_kernel<3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_kernel(ctx, conv2_fwd_tc_kernel<3, 9>, dim3(grid), dim3(THREADS), smem, st, p);
+    launch_kernel(ctx, conv2_fwd_tc_kernel<3, 9>, dim3(grid), dim3(THREADS), smem, st, tm_out, p);
   } else {
     EGB_CUDA(cudaFuncSetAttribute(conv2_fwd_tc_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_kernel(ctx, conv2_fwd_tc_kernel<3, 3>, dim3(grid), dim3(THREADS), smem, st, p);
+    launch_kernel(ctx, conv2_fwd_tc_kernel<3, 3>, dim3(grid), dim3(THREADS), smem, st, tm_out, p);
   }
   EGB_CUDA(cudaGetLastError());
 }

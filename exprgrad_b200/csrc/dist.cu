@@ -103,6 +103,9 @@ void comm_open_window(CommHooks* c, Context& ctx, char* arena, size_t arena_byte
   if (world > EX_MAX_WORLD) fail(EGB_ERR_GPU, "peer exchange supports at most %d ranks", EX_MAX_WORLD);
   w.world = world;
   w.rank = rank;
+  w.owner = c;
+  EGB_CUDA(cudaMalloc((void**)&w.barrier_buf, 256));
+  EGB_CUDA(cudaMemsetAsync(w.barrier_buf, 0, 256, ctx.stream));
   const size_t fbytes = exchange_flag_bytes();
   EGB_CUDA(cudaMalloc((void**)&w.local_flags, fbytes));
   EGB_CUDA(cudaMemsetAsync(w.local_flags, 0, fbytes, ctx.stream));
@@ -161,6 +164,16 @@ void comm_close_window(PeerWindow& w) {
   for (int i = 0; i < w.nopened; ++i)
     if (w.opened[i]) cudaIpcCloseMemHandle(w.opened[i]);
   w.nopened = 0;
+  // An exported allocation must outlive every mapping of it: the ranks tear a data-parallel plan down together
+  // (as they built it), so a tiny all-reduce serves as the barrier "everybody has closed my arena" before the
+  // caller frees it. (Skipped when the communicator is already gone.)
+  if (w.owner && w.world > 1 && w.owner->comm && w.barrier_buf) {
+    cudaStream_t st = w.owner->ctx->stream;
+    if (nccl().all_reduce(w.barrier_buf, w.barrier_buf, 1, kNcclFloat32, kNcclSum, w.owner->comm, st) == 0)
+      cudaStreamSynchronize(st);
+  }
+  if (w.barrier_buf) cudaFree(w.barrier_buf);
+  w.barrier_buf = nullptr;
   if (w.local_flags) cudaFree(w.local_flags);
   w.local_flags = nullptr;
   w.mapped = false;

@@ -179,7 +179,12 @@ void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st) {
   a.accumulate = e.accumulate ? 1 : 0;
   // bytes this launch moves; beyond about half of the L2 it streams (evict-first)
   const double bytes = 4.0 * (double)e.n * (1 + (e.kind == ELT_BIAS_ROW ? 0 : e.nreads) + (e.accumulate ? 1 : 0));
-  a.streaming = bytes > 64.0e6 ? 7 : 0;
+  // Out-of-place maps stream (evict-first loads and stores: 0.94-0.96 of the copy roofline on 512 MiB tensors).
+  // In-place forms (optimizer updates: the destination is also read) are DRAM-limited differently: the write-back
+  // of a line follows its read by a few MB, same DRAM bytes but 62 % instead of 76 % DRAM activity in ncu
+  // (profiles/r02c_eltwise_ncu.txt); they measured best with the default policy (0.80 vs 0.75 with evict-first).
+  const bool in_place = e.accumulate || e.out == e.in[0] || (e.nreads >= 2 && e.out == e.in[1]);
+  a.streaming = bytes > 64.0e6 ? (in_place ? 0 : 7) : 0;
   if (const char* pol = getenv("EGB_ELT_POLICY")) a.streaming = bytes > 64.0e6 ? atoi(pol) : 0;   // measurement knob
   switch (e.kind) {
 #define EGB_ELT_CASE(K) case K: launch_kind<K>(ctx, a, st); break;

@@ -53,8 +53,11 @@ size_t exchange_flag_bytes();
 void launch_exchange(Context& ctx, const ExchangeParams& p, cudaStream_t st);
 
 // Peer mappings of one plan's arena and flag area on every rank (cudaIpc handles exchanged once per plan)
+struct CommHooks;
 struct PeerWindow {
   bool mapped = false;
+  CommHooks* owner = nullptr;          // communicator the window was opened on (teardown barrier)
+  float* barrier_buf = nullptr;
   int world = 1, rank = 0;
   char* arena[EX_MAX_WORLD] = {};      // base of rank r's arena as seen from this process
   uint32_t* flags[EX_MAX_WORLD] = {};
