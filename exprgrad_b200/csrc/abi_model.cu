@@ -366,6 +366,13 @@ int egb_model_set_option(egb_model* m, const char* key, int64_t value) {
       m->m->last_plan = nullptr;
     }
     m->m->dp_peer = value != 0;
+  } else if (k == "head") {
+    if (m->m->headfuse != (value != 0)) {
+      EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
+      m->m->plans.clear();
+      m->m->last_plan = nullptr;
+    }
+    m->m->headfuse = value != 0;
   } else if (k == "eltwise") {
     if (m->m->eltwise != (value != 0)) {
       EGB_CUDA(cudaStreamSynchronize(m->ctx->c.stream));
@@ -835,7 +842,7 @@ int egb_model_describe_plan(egb_model* m, char* buf, size_t cap, size_t* needed)
     s += "target " + p.target_name + ": " + std::to_string(p.nodes.size()) + " nodes, arena " +
          std::to_string(p.arena_bytes) + " bytes (zeroed per run: " + std::to_string(p.zero_bytes) + "), graph " +
          (p.graph_valid ? "yes" : "no") + "\n";
-    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain", "softmax_xent", "eltwise", "exchange"};
+    static const char* kinds[] = {"interp", "gemm", "split", "memset", "random", "allreduce", "conv", "rowchain", "softmax_xent", "eltwise", "exchange", "head", "headprep"};
     auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
       for (auto x : a)
         for (auto y : b)

@@ -10,6 +10,8 @@
 // link-time dependency on it. The communicator runs on the context's stream and is captured into the
 // plan's CUDA graph together with the compute kernels.
 #include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "abi_model.hpp"
@@ -161,6 +163,16 @@ void comm_open_window(CommHooks* c, Context& ctx, char* arena, size_t arena_byte
 }
 
 void comm_close_window(PeerWindow& w) {
+  if (w.local_flags && getenv("EGB_EXCHANGE_TRACE")) {
+    // phase stamps of the last exchange launch (CTA 0 and the last CTA): start, after A, B, C, D (exchange.cu)
+    unsigned long long t[16];
+    const size_t off = (size_t)(2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) * sizeof(uint32_t);
+    if (cudaMemcpy(t, (char*)w.local_flags + off, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
+      for (int q = 0; q < 2; ++q)
+        fprintf(stderr, "egb exchange trace rank %d %s: handshake %.2f us, reduce+broadcast %.2f us, landed-handshake %.2f us, "
+                        "update %.2f us (start %llu)\n", w.rank, q == 0 ? "cta 0" : "last cta", (t[8 * q + 1] - t[8 * q]) / 1e3,
+                (t[8 * q + 2] - t[8 * q + 1]) / 1e3, (t[8 * q + 3] - t[8 * q + 2]) / 1e3, (t[8 * q + 4] - t[8 * q + 3]) / 1e3, t[8 * q]);
+  }
   for (int i = 0; i < w.nopened; ++i)
     if (w.opened[i]) cudaIpcCloseMemHandle(w.opened[i]);
   w.nopened = 0;

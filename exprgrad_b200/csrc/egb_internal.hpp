@@ -218,6 +218,11 @@ size_t gemm_2cta_workspace_bytes(int sm_count);
 void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, int* tiles);
 
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
+// Latency-optimised kernel for small problems (gemm_lat.cu): TMA-staged epilogue in the TMEM-native layout,
+// push-based cluster split-K
+bool gemm_lat_eligible(const GemmArgs& a);
+bool launch_gemm_lat(Context& ctx, const GemmArgs& a, cudaStream_t st);   // false: not launched (does not fit)
+void gemm_lat_plan(int M, int N, int K, bool b_mn, int sms, int max_ck, int* bn, int* ck);  // host-only
 void gemm_plan(int M, int N, int K, bool b_mn, int sms, int machine_sms, int max_ck, int* bn, int* ck);  // host-only
 
 // Fused softmax + crossEntropy forward/adjoint row kernel (fused_rows.cu)

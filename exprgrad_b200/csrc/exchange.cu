@@ -64,6 +64,11 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
   if (tid == 0) epoch_sm = *epoch_slot + 1;
   __syncthreads();
   const uint32_t epoch = epoch_sm;
+  // phase stamps of CTA 0 and the last CTA (globaltimer, ns): cheap, always on; printed by EGB_EXCHANGE_TRACE
+  unsigned long long* const stamps =
+      reinterpret_cast<unsigned long long*>(my_flags + 2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) + (b == 0 ? 0 : 8);
+  const bool stamp = tid == 0 && (b == 0 || b == G - 1);
+  if (stamp) stamps[0] = globaltimer();
   // ---- A: gradients of this rank are complete -> tell CTA b of every rank, wait for CTA b of every rank
   if (tid < N) {
     __threadfence_system();
@@ -71,6 +76,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
     wait_flag(my_flags + (size_t)tid * EX_MAX_CTAS + b, epoch);
   }
   __syncthreads();
+  if (stamp) stamps[1] = globaltimer();
   // ---- B: reduce slice `me` from all buckets, average, store it into every bucket
   const long long n4 = p.n >> 2;                       // 16-byte groups (bucket tensors are 256-byte aligned)
   const long long S = (n4 + N - 1) / N;                // groups per rank slice
@@ -99,12 +105,14 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
   }
   // ---- C: slice `me`, chunk b has landed everywhere
   __syncthreads();
+  if (stamp) stamps[2] = globaltimer();
   if (tid < N) {
     __threadfence_system();
     st_release_sys(p.flags[tid] + (size_t)(EX_MAX_WORLD + me) * EX_MAX_CTAS + b, epoch);
     wait_flag(my_flags + (size_t)(EX_MAX_WORLD + tid) * EX_MAX_CTAS + b, epoch);
   }
   __syncthreads();
+  if (stamp) stamps[3] = globaltimer();
   // ---- D: gradientDescent from the averaged bucket: chunk b of every slice (exactly the chunks whose flags
   //         this CTA has just seen)
   if (p.nseg > 0) {
@@ -138,11 +146,12 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
     }
   }
   if (tid == 0) *epoch_slot = epoch;
+  if (stamp) stamps[4] = globaltimer();
 }
 
 }  // namespace
 
-size_t exchange_flag_bytes() { return (size_t)(2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) * sizeof(uint32_t); }
+size_t exchange_flag_bytes() { return (size_t)(2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) * sizeof(uint32_t) + 16 * 8; }
 
 void launch_exchange(Context& ctx, const ExchangeParams& p, cudaStream_t st) {
   if (p.world < 1 || p.world > EX_MAX_WORLD) fail(EGB_ERR_GPU, "exchange: world size %d is not supported (max %d)", p.world, EX_MAX_WORLD);

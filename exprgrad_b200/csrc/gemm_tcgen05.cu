@@ -22,6 +22,8 @@
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <stdlib.h>
 
+#include <set>
+
 #include "egb_internal.hpp"
 #include "ptx.cuh"
 
@@ -110,7 +112,11 @@ __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* mi
 
 // kFused = false: plain contraction epilogue (C (+)= alpha * acc), the 4096^3 benchmark path;
 // kFused = true: bias / second stage / operand planes / column sums fused behind the contraction.
-template <bool kFused>
+// kEpi: the second stage (EpiMode) is a COMPILE-TIME parameter. With all stages behind run-time branches the
+// kernel was 16 296 SASS instructions (260 KB); its epilogue runs once per launch with a cold instruction cache,
+// and ncu showed the epilogue warps stalled on instruction fetch (stall_no_instruction 14 per issue,
+// profiles/r02d_dense_gemm_ncu.txt): 2.3 us for the ~600 instructions that finish one 32 x 16 unit.
+template <bool kFused, int kEpi>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_mid,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_mid,
@@ -302,8 +308,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const bool planes_vec = ((p.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 7) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.out_mid) & 7) == 0);
     const bool need_c = (p.flags & GEMM_ACCUMULATE) != 0;
-    const bool need_h = kFused && (p.epi == EPI_MASK_RELU || p.epi == EPI_MASK_LEAKY);
-    const bool need_d = kFused && p.epi == EPI_SGD;
+    constexpr bool need_h = kFused && (kEpi == EPI_MASK_RELU || kEpi == EPI_MASK_LEAKY);
+    constexpr bool need_d = kFused && kEpi == EPI_SGD;
     // One 32-row x 16-column unit in the coalesced layout: v[i] = alpha * acc of row row0 + lr + 8i.
     // Phase 1 of a unit: every global read (bias, old C, mask source / parameter) is issued before the first
     // store - the pointers may alias as far as the compiler knows, so loads interleaved with stores would
@@ -391,33 +397,33 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (kFused) {
           // ---- second stage
           const float a2[4] = {aux[i].x, aux[i].y, aux[i].z, aux[i].w};
-          if (p.epi == EPI_RELU) {
+          if constexpr (kEpi == EPI_RELU) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = (0.0f <= x[e]) ? x[e] : 0.0f;
-          } else if (p.epi == EPI_LEAKY) {
+          } else if constexpr (kEpi == EPI_LEAKY) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fmul_rn((0.0f <= x[e]) ? 1.0f : p.epi_param, x[e]);
-          } else if (p.epi == EPI_MASK_RELU) {
+          } else if constexpr (kEpi == EPI_MASK_RELU) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = (0.0f <= a2[e]) ? x[e] : 0.0f;
-          } else if (p.epi == EPI_MASK_LEAKY) {
+          } else if constexpr (kEpi == EPI_MASK_LEAKY) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fmul_rn(x[e], (0.0f <= a2[e]) ? 1.0f : p.epi_param);
-          } else if (p.epi == EPI_SIGMOID) {
+          } else if constexpr (kEpi == EPI_SIGMOID) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fsub_rn(0.0f, x[e]))));
-          } else if (p.epi == EPI_TANH) {
+          } else if constexpr (kEpi == EPI_TANH) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float ep = expf(x[e]), en = expf(__fsub_rn(0.0f, x[e]));
               x[e] = __fdiv_rn(__fsub_rn(ep, en), __fadd_rn(ep, en));
             }
-          } else if (p.epi == EPI_SGD) {
+          } else if constexpr (kEpi == EPI_SGD) {
             // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fadd_rn(a2[e], __fmul_rn(0.0f - x[e], p.epi_param));
           }
-          if (p.epi != EPI_NONE && !(p.flags & GEMM_SKIP_D)) {
+          if (kEpi != EPI_NONE && !(p.flags & GEMM_SKIP_D)) {
             if (full) {
               *reinterpret_cast<float4*>(p.D + off) = make_float4(x[0], x[1], x[2], x[3]);
             } else {
@@ -756,6 +762,12 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
     launch_gemm_bf16x3_2cta(ctx, a, st);
     return;
   }
+  {
+    // problems that cannot fill the machine with 128 x 256 tiles are latency bound: gemm_lat.cu
+    static const bool lat_always = getenv("EGB_GEMM_LAT_ALWAYS") != nullptr;
+    const bool small = ((a.M + BM - 1) / BM) * ((a.N + 255) / 256) * 2 <= ctx.sm_count;
+    if ((small || lat_always) && gemm_lat_eligible(a) && launch_gemm_lat(ctx, a, st)) return;
+  }
   KParams p;
   p.C = a.C; p.bias = a.bias; p.out_hi = a.out_hi; p.out_mid = a.out_mid;
   p.D = a.D; p.H = a.H; p.colsum = a.colsum;
@@ -799,12 +811,6 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   encode_plane(ctx, &tm_b_hi, a.b_hi, a.N, a.K, a.ldb, p.BN, a.b_mn);
   encode_plane(ctx, &tm_b_mid, a.b_mid, a.N, a.K, a.ldb, p.BN, a.b_mn);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    EGB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    EGB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
   static const bool force_fused = getenv("EGB_GEMM_FUSED_ALWAYS") != nullptr;
   const int tiles = p.tiles_m * p.tiles_n;
   const int num_kb = (a.K + BK - 1) / BK;
@@ -822,7 +828,30 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   const int units = tiles * p.splits;
   const bool fused = force_fused || (a.flags & (GEMM_BIAS | GEMM_SPLIT_OUT)) || a.epi != EPI_NONE || a.colsum || p.splits > 1;
   const int grid = (p.ck > 1 || units < sms) ? units : sms;
-  if (p.ck > 1) {
+  // one instantiation per second-stage mode (compile-time epilogue, see the kernel's comment)
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, KParams);
+  KernelFn fn = nullptr;
+  if (!fused) {
+    fn = gemm_bf16x3_kernel<false, EPI_NONE>;
+  } else {
+    switch (a.epi) {
+      case EPI_NONE: fn = gemm_bf16x3_kernel<true, EPI_NONE>; break;
+      case EPI_RELU: fn = gemm_bf16x3_kernel<true, EPI_RELU>; break;
+      case EPI_LEAKY: fn = gemm_bf16x3_kernel<true, EPI_LEAKY>; break;
+      case EPI_MASK_RELU: fn = gemm_bf16x3_kernel<true, EPI_MASK_RELU>; break;
+      case EPI_MASK_LEAKY: fn = gemm_bf16x3_kernel<true, EPI_MASK_LEAKY>; break;
+      case EPI_SGD: fn = gemm_bf16x3_kernel<true, EPI_SGD>; break;
+      case EPI_SIGMOID: fn = gemm_bf16x3_kernel<true, EPI_SIGMOID>; break;
+      case EPI_TANH: fn = gemm_bf16x3_kernel<true, EPI_TANH>; break;
+      default: fail(EGB_ERR_GPU, "gemm: unknown second-stage mode %d", a.epi);
+    }
+  }
+  static std::set<KernelFn> attr_done;
+  if (!attr_done.count(fn)) {
+    EGB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_done.insert(fn);
+  }
+  {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -830,27 +859,23 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.ck;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    int na = 0;
+    if (p.ck > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = (unsigned)p.ck;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (ctx.pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = ctx.pdl ? 2 : 1;
+    cfg.numAttrs = na;
     Launch l(ctx, KC_GEMM, st);
-    if (fused)
-      EGB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true>, tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p));
-    else
-      EGB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<false>, tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p));
-  } else {
-    Launch l(ctx, KC_GEMM, st);
-    if (fused)
-      launch_kernel(ctx, gemm_bf16x3_kernel<true>, dim3(grid), dim3(NUM_THREADS), smem, st, tm_a_hi, tm_a_mid, tm_b_hi,
-                    tm_b_mid, p);
-    else
-      launch_kernel(ctx, gemm_bf16x3_kernel<false>, dim3(grid), dim3(NUM_THREADS), smem, st, tm_a_hi, tm_a_mid, tm_b_hi,
-                    tm_b_mid, p);
+    EGB_CUDA(cudaLaunchKernelEx(&cfg, fn, tm_a_hi, tm_a_mid, tm_b_hi, tm_b_mid, p));
   }
   EGB_CUDA(cudaGetLastError());
 }

@@ -197,6 +197,120 @@ bool is_column_sum(const Kernel& k) {
   return match_form(k, form, m);
 }
 
+// The classification head in one launch (head_rows.cu): a SOFTMAX_XENT node absorbs the contraction that produces its
+// logits (<= 16 classes) and the contraction that consumes its gradient planes with the class dimension as k. Matched
+// on the lowered nodes (operand pointers, shapes, fused stages) with hazard checks against every node in between;
+// anything else stays as three launches, with a note in the plan.
+bool fuse_head(Model& m, Plan& plan) {
+  auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+    for (auto x : a)
+      for (auto y : b)
+        if (x == y) return true;
+    return false;
+  };
+  bool any = false;
+  for (int xi = 0; xi < (int)plan.nodes.size(); ++xi) {
+    if (plan.nodes[xi].kind != Node::SOFTMAX_XENT) continue;
+    const Node& X = plan.nodes[xi];
+    if (!X.sx_out_hi) continue;
+    int gi = -1, go = -1;
+    for (int j = 0; j < xi; ++j) {
+      const Node& n = plan.nodes[j];
+      if (n.kind == Node::GEMM && n.gemm.C == X.sx_h) gi = j;
+    }
+    for (int j = xi + 1; j < (int)plan.nodes.size(); ++j) {
+      const Node& n = plan.nodes[j];
+      if (n.kind == Node::GEMM && n.gemm.a_hi == X.sx_out_hi && !n.gemm.a_mn && n.gemm.K == X.sx_cols) { go = j; break; }
+    }
+    if (gi < 0 || go < 0) continue;
+    const GemmArgs& in = plan.nodes[gi].gemm;
+    const GemmArgs& out = plan.nodes[go].gemm;
+    std::string why;
+    if (in.M != X.sx_rows || in.N != X.sx_cols || in.ldc != X.sx_cols || in.a_mn || in.epi != EPI_NONE || in.colsum ||
+        (in.flags & ~GEMM_BIAS) != 0 || in.alpha != 1.0f)
+      why = "the contraction in front of the rows has stages the head kernel does not take";
+    else if (out.M != X.sx_rows || out.alpha != 1.0f || (out.flags & GEMM_ACCUMULATE) || out.a_mid != X.sx_out_mid ||
+             out.lda != X.sx_ld_out)
+      why = "the adjoint contraction behind the rows accumulates or reads other planes";
+    // nothing between the absorbed nodes and the fused node's position may touch what moves past it
+    for (int j = gi + 1; j < xi && why.empty(); ++j) {
+      const Node& n = plan.nodes[j];
+      if (hits(n.reads, plan.nodes[gi].writes) || hits(n.writes, plan.nodes[gi].writes) || hits(n.writes, plan.nodes[gi].reads))
+        why = "a node between the logits contraction and the rows uses its tensors";
+    }
+    for (int j = xi + 1; j < go && why.empty(); ++j) {
+      const Node& n = plan.nodes[j];
+      if (hits(n.reads, plan.nodes[go].writes) || hits(n.writes, plan.nodes[go].writes) || hits(n.writes, plan.nodes[go].reads))
+        why = "a node between the rows and the adjoint contraction uses its tensors";
+    }
+    HeadParams h;
+    h.a_hi = in.a_hi; h.a_mid = in.a_mid; h.lda = in.lda; h.Kin = in.K;
+    h.win_hi = in.b_hi; h.win_mid = in.b_mid; h.win_ld = in.ldb; h.win_mn = in.b_mn ? 1 : 0;
+    h.bias_in = (in.flags & GEMM_BIAS) ? in.bias : nullptr;
+    h.Z = in.C;
+    h.Y = X.sx_y; h.DL = X.sx_dl; h.S = X.sx_s; h.P = X.sx_p; h.DP = X.sx_dp; h.DH = X.sx_dh; h.DS = X.sx_ds;
+    h.colsum_dz = X.sx_colsum; h.dh_hi = X.sx_out_hi; h.dh_mid = X.sx_out_mid; h.dh_ld = X.sx_ld_out;
+    h.rows = X.sx_rows; h.cols = X.sx_cols;
+    h.wout_hi = out.b_hi; h.wout_mid = out.b_mid; h.wout_ld = out.ldb; h.wout_mn = out.b_mn ? 1 : 0; h.Nout = out.N;
+    h.bias_out = (out.flags & GEMM_BIAS) ? out.bias : nullptr;
+    h.epi = out.epi; h.epi_param = out.epi_param; h.Hm = out.H; h.C = out.C; h.D = out.D; h.ldc = out.ldc;
+    h.flags = out.flags; h.colsum_out = out.colsum; h.out_hi = out.out_hi; h.out_mid = out.out_mid; h.ld_out = out.ld_out;
+    if (why.empty() && !head_rows_supported(h)) why = "shapes or alignment outside the head kernel's range";
+    if (!why.empty()) {
+      plan.notes.push_back("classification head stays three launches: " + why);
+      continue;
+    }
+    // fp32 tables of both weight operands: built once per run by a small node that depends only on the producers of
+    // the weight planes (normally the plan's root split), so it runs beside the first contractions
+    void* tab = nullptr;
+    EGB_CUDA(cudaMalloc(&tab, head_table_floats(h) * sizeof(float)));
+    plan.chain_bufs.push_back(tab);
+    h.tables = (float*)tab;
+    const int64_t table_id = -((int64_t)1 << 40) - xi;
+    Node prep;
+    prep.kind = Node::HEADPREP;
+    prep.head = h;
+    prep.label = "weight tables of the head kernel";
+    prep.writes.push_back(table_id);
+    int prep_pos = 0;
+    for (int j = 0; j < gi; ++j) {
+      const Node& n = plan.nodes[j];
+      bool producer = false;
+      if (n.kind == Node::SPLIT) {
+        producer = n.split_hi == in.b_hi || n.split_hi == out.b_hi;
+        for (auto& job : n.split_jobs) producer = producer || job.hi == in.b_hi || job.hi == out.b_hi;
+      } else if (n.kind == Node::GEMM) {
+        producer = (n.gemm.flags & GEMM_SPLIT_OUT) && (n.gemm.out_hi == in.b_hi || n.gemm.out_hi == out.b_hi);
+      }
+      if (!producer) continue;
+      for (auto w : n.writes)
+        if (std::find(plan.nodes[gi].reads.begin(), plan.nodes[gi].reads.end(), w) != plan.nodes[gi].reads.end() ||
+            std::find(plan.nodes[go].reads.begin(), plan.nodes[go].reads.end(), w) != plan.nodes[go].reads.end())
+          prep.reads.push_back(w);
+      prep_pos = j + 1;
+    }
+    Node f;
+    f.kind = Node::HEAD;
+    f.head = h;
+    f.label = "head: " + plan.nodes[gi].label + " | " + X.label + " | " + plan.nodes[go].label;
+    for (int j : {gi, xi, go}) {
+      for (auto r : plan.nodes[j].reads) f.reads.push_back(r);
+      for (auto w : plan.nodes[j].writes) f.writes.push_back(w);
+    }
+    f.reads.push_back(table_id);
+    std::vector<Node> kept;
+    for (int j = 0; j < (int)plan.nodes.size(); ++j) {
+      if (j == prep_pos) kept.push_back(prep);
+      if (j == gi || j == go) continue;
+      kept.push_back(j == xi ? f : plan.nodes[j]);
+    }
+    plan.nodes = kept;
+    any = true;
+    xi = -1;  // restart: indices moved
+  }
+  return any;
+}
+
 // Replace runs of consecutive levels that consist only of small row-local generic kernels by one
 // ROWCHAIN node each. Returns true if anything was fused.
 bool fuse_row_chains(Model& m, Plan& plan) {
@@ -816,27 +930,6 @@ void build_nodes_impl(Model& m, Plan& plan) {
   if (m.rowchain && !m.strict) {
     if (fuse_row_chains(m, plan)) compute_levels(plan);
   }
-  // Contractions of one level run concurrently (parallel graph branches). Each needs a whole SM per CTA
-  // (shared memory), so grids that together exceed the machine run in two waves and the level takes twice
-  // as long (timeline: 256 CTAs at level 7 of the dense step). Give every contraction of a level an SM
-  // budget proportional to its work; its tile width / cluster split-K factor is then chosen inside it.
-  if (m.concurrent) {
-    std::map<int, double> level_work;
-    std::map<int, int> level_gemms;
-    for (auto& n : plan.nodes)
-      if (n.kind == Node::GEMM) {
-        level_work[n.level] += (double)n.gemm.M * n.gemm.N * n.gemm.K;
-        level_gemms[n.level]++;
-      }
-    for (auto& n : plan.nodes)
-      if (n.kind == Node::GEMM && level_gemms[n.level] > 1) {
-        const double share = (double)n.gemm.M * n.gemm.N * n.gemm.K / level_work[n.level];
-        int budget = (int)(m.ctx->sm_count * share) / 8 * 8;
-        if (budget < 16) budget = 16;
-        n.gemm.sm_budget = budget;
-        n.label += " sm<=" + std::to_string(budget);
-      }
-  }
   // Dead-store elimination: the fp32 form of a contraction's C / D tensor that only its own epilogue consumes
   // (fused stages, column sums, operand planes) and no later node reads is not written to memory - the same
   // reasoning as the reference's deadKernelElim (passes.nim:331-350), applied to stores. The epilogues of the
@@ -871,6 +964,28 @@ void build_nodes_impl(Model& m, Plan& plan) {
         n.label += std::string(" [fp32") + ((n.gemm.flags & GEMM_SKIP_C) ? " C" : "") + ((n.gemm.flags & GEMM_SKIP_D) ? " D" : "") +
                    " not stored]";
     }
+  }
+  if (m.fuse && m.headfuse && !m.strict && fuse_head(m, plan)) compute_levels(plan);
+  // Contractions of one level run concurrently (parallel graph branches). Each needs a whole SM per CTA
+  // (shared memory), so grids that together exceed the machine run in two waves and the level takes twice
+  // as long (timeline: 256 CTAs at level 7 of the dense step). Give every contraction of a level an SM
+  // budget proportional to its work; its tile width / cluster split-K factor is then chosen inside it.
+  if (m.concurrent) {
+    std::map<int, double> level_work;
+    std::map<int, int> level_gemms;
+    for (auto& n : plan.nodes)
+      if (n.kind == Node::GEMM) {
+        level_work[n.level] += (double)n.gemm.M * n.gemm.N * n.gemm.K;
+        level_gemms[n.level]++;
+      }
+    for (auto& n : plan.nodes)
+      if (n.kind == Node::GEMM && level_gemms[n.level] > 1) {
+        const double share = (double)n.gemm.M * n.gemm.N * n.gemm.K / level_work[n.level];
+        int budget = (int)(m.ctx->sm_count * share) / 8 * 8;
+        if (budget < 16) budget = 16;
+        n.gemm.sm_budget = budget;
+        n.label += " sm<=" + std::to_string(budget);
+      }
   }
   for (auto& n : plan.nodes)
     if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
@@ -1222,6 +1337,19 @@ Plan& Model::get_plan(const std::string& target_name, const std::vector<int>& id
 
 // ------------------------------------------------------------------ execution
 
+// May a HEAD node read its weight planes ahead of griddepcontrol.wait? `pred` is the node launched right before it on
+// the same stream (null: none). Yes if that kernel triggers its dependents only AFTER its own wait (the single-CTA
+// contraction kernels do, in their last epilogue): every earlier kernel of the stream is then complete when the head
+// starts, producers on other streams are full dependencies anyway - only `pred` itself may still be running, so it
+// must not be the one that writes those planes.
+static bool head_may_read_weights_early(const Node* pred, const HeadParams& h) {
+  if (!pred || pred->kind != Node::GEMM) return false;
+  const GemmArgs& g = pred->gemm;
+  if (g.bn == 0 && gemm_2cta_eligible(g)) return false;   // that kernel triggers at its start
+  if ((g.flags & GEMM_SPLIT_OUT) && (g.out_hi == h.win_hi || g.out_hi == h.wout_hi)) return false;
+  return true;
+}
+
 static void launch_node(Model& m, Node& n, cudaStream_t st) {
   Context& ctx = *m.ctx;
   switch (n.kind) {
@@ -1243,6 +1371,8 @@ static void launch_node(Model& m, Node& n, cudaStream_t st) {
       launch_softmax_xent_rows(ctx, n.sx_h, n.sx_y, n.sx_dl, n.sx_s, n.sx_p, n.sx_dp, n.sx_dh, n.sx_ds, n.sx_rows, n.sx_cols,
                                n.sx_colsum, n.sx_out_hi, n.sx_out_mid, n.sx_ld_out, st);
       break;
+    case Node::HEAD: launch_head_rows(ctx, n.head, st); break;
+    case Node::HEADPREP: launch_head_tables(ctx, n.head, st); break;
     case Node::ELTWISE: launch_eltwise_stream(ctx, n.elt, st); break;
     case Node::EXCHANGE: launch_exchange(ctx, n.exchange, st); break;
     case Node::ROWCHAIN: launch_interp_rowchain(ctx, n.chain_progs, n.chain_n, n.chain_slots, n.chain_rows, st); break;
@@ -1277,7 +1407,12 @@ static void capture_levels(Model& m, Plan& plan) {
   bool parallel = false;
   for (auto& nd : plan.nodes) parallel = parallel || ++width[nd.level] > 1;
   if (!m.concurrent || !parallel) {
-    for (auto& nd : plan.nodes) launch_node(m, nd, c.stream);
+    const Node* prev = nullptr;
+    for (auto& nd : plan.nodes) {
+      if (nd.kind == Node::HEAD) nd.head.w_early = head_may_read_weights_early(prev, nd.head) ? 1 : 0;
+      launch_node(m, nd, c.stream);
+      if (nd.kind != Node::MEMSET) prev = &nd;
+    }
     return;
   }
   // Dependency-exact capture: every node waits (through events) only for the earlier nodes it really
@@ -1407,6 +1542,7 @@ static void capture_levels(Model& m, Plan& plan) {
     }
     for (int pj : preds[i])
       if (stream_of[pj] != s) EGB_CUDA(cudaStreamWaitEvent(streams[s], c.fork_events[pj], 0));
+    if (nd.kind == Node::HEAD) nd.head.w_early = head_may_read_weights_early(tail[s] >= 0 ? &plan.nodes[tail[s]] : nullptr, nd.head) ? 1 : 0;
     launch_node(m, nd, streams[s]);
     EGB_CUDA(cudaEventRecord(c.fork_events[i], streams[s]));
     tail[s] = i;

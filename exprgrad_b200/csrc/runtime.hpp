@@ -66,6 +66,45 @@ struct PeerWindow {
   int nopened = 0;
 };
 
+// The classification head as one row kernel (head_rows.cu): skinny contraction -> softmax + crossEntropy rows ->
+// skinny adjoint contraction with its fused stages
+struct HeadParams {
+  // forward contraction z[rows, cols] = a[rows, Kin] * w + bias_in  (operand planes of the absorbed contraction)
+  const __nv_bfloat16 *a_hi = nullptr, *a_mid = nullptr;
+  int lda = 0, Kin = 0;
+  const __nv_bfloat16 *win_hi = nullptr, *win_mid = nullptr;
+  int win_ld = 0, win_mn = 0;
+  const float* bias_in = nullptr;
+  float* Z = nullptr;
+  // softmax + crossEntropy rows (fused_rows.cu)
+  const float *Y = nullptr, *DL = nullptr;
+  float *S = nullptr, *P = nullptr, *DP = nullptr, *DH = nullptr, *DS = nullptr;
+  float* colsum_dz = nullptr;
+  __nv_bfloat16 *dh_hi = nullptr, *dh_mid = nullptr;
+  int dh_ld = 0;
+  int rows = 0, cols = 0;
+  // adjoint contraction g[rows, Nout] = dz[rows, cols] * w' and its fused stages (GemmArgs of the absorbed contraction)
+  const __nv_bfloat16 *wout_hi = nullptr, *wout_mid = nullptr;
+  int wout_ld = 0, wout_mn = 0, Nout = 0;
+  const float* bias_out = nullptr;
+  int epi = EPI_NONE;
+  float epi_param = 0.0f;
+  const float* Hm = nullptr;
+  float *C = nullptr, *D = nullptr;
+  int ldc = 0, flags = 0;
+  float* colsum_out = nullptr;
+  __nv_bfloat16 *out_hi = nullptr, *out_mid = nullptr;
+  int ld_out = 0;
+  float* tables = nullptr;   // fp32 tables of both weight operands (head_tables_kernel), plan-owned
+  int w_early = 0;    // the tables were complete before the predecessor kernel started: fetch them before griddepcontrol.wait
+  unsigned long long* trace = nullptr;   // debug timeline (Context::trace) or null
+  int trace_index = 0;
+};
+bool head_rows_supported(const HeadParams& p);
+size_t head_table_floats(const HeadParams& p);
+void launch_head_tables(Context& ctx, const HeadParams& p, cudaStream_t st);
+void launch_head_rows(Context& ctx, const HeadParams& p, cudaStream_t st);
+
 struct DevTensor {
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -79,7 +118,7 @@ struct DevTensor {
 };
 
 struct Node {
-  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN, SOFTMAX_XENT, ELTWISE, EXCHANGE } kind = INTERP;
+  enum Kind { INTERP, GEMM, SPLIT, MEMSET, RANDOM, ALLREDUCE, CONV, ROWCHAIN, SOFTMAX_XENT, ELTWISE, EXCHANGE, HEAD, HEADPREP } kind = INTERP;
   std::string label;
   // INTERP
   IpProgram ip;
@@ -107,6 +146,8 @@ struct Node {
   float* sx_colsum = nullptr;                                   // fused bias-gradient column sum of DH (zeroed first)
   __nv_bfloat16 *sx_out_hi = nullptr, *sx_out_mid = nullptr;    // fused operand planes of DH
   int sx_ld_out = 0;
+  // HEAD: contraction + softmax/crossEntropy rows + adjoint contraction in one launch (head_rows.cu)
+  HeadParams head;
   // ELTWISE: one of the specialised streaming map kernels (eltwise_stream.cu)
   EltLaunch elt;
   // EXCHANGE: peer-memory gradient exchange + fused gradientDescent (exchange.cu)
@@ -204,6 +245,7 @@ struct Model {
   bool concurrent = true;   // independent plan nodes run on parallel branches of the CUDA graph
   bool rowchain = true;     // runs of small row-local kernels execute in one launch
   bool eltwise = true;      // fixed elementwise / optimizer forms run on the specialised streaming kernels
+  bool headfuse = true;     // skinny contractions around the softmax + crossEntropy rows join the row kernel (head_rows.cu)
   bool keep_intermediates = false;  // store every fp32 intermediate even when only a fused epilogue consumes it
   // data parallel: exchange the gradient bucket with the fused peer-memory kernel (exchange.cu); off = the
   // ncclAllReduce(avg) + separate optimizer kernels of round 1 (kept for comparison and as the > 8 rank path)

@@ -119,6 +119,23 @@ def _bf16_planes(x):
                                              (300, 200, 520, 0, 0), (784, 512, 1024, 1, 1), (128, 64, 128, 0, 0)])
 @pytest.mark.parametrize("bn,ck", [(64, 2), (128, 4), (256, 8), (64, 8)])
 def test_cluster_split_k_configurations(ctx, M, N, K, a_mn, b_mn, bn, ck):
+    _planes_case(ctx, M, N, K, a_mn, b_mn, bn, ck, 0)
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(1024, 512, 784, 0, 0), (1024, 512, 512, 0, 1), (300, 200, 520, 0, 0),
+                                             (784, 512, 1024, 1, 1), (128, 64, 128, 0, 0), (37, 48, 64, 0, 0),
+                                             (129, 36, 200, 1, 0)])
+@pytest.mark.parametrize("bn,ck", [(32, 1), (64, 1), (128, 1), (256, 1), (32, 2), (64, 2), (32, 4), (64, 4)])
+@pytest.mark.parametrize("flags", [0, 1 | 2, 2 | 4])
+def test_latency_kernel_configurations(ctx, M, N, K, a_mn, b_mn, bn, ck, flags):
+    """gemm_lat.cu (TMA-staged epilogue in the TMEM-native layout, push-based cluster split-K): every tile width and
+    split factor it accepts, ragged edges (TMA clips), `+=` on the old contents, bias, relu in place."""
+    if b_mn and bn % 64:
+        pytest.skip("an MN-major B tile is made of 64-column groups")
+    _planes_case(ctx, M, N, K, a_mn, b_mn, bn, ck, flags)
+
+
+def _planes_case(ctx, M, N, K, a_mn, b_mn, bn, ck, xflags):
     """Forced tile width x cluster split-K factor (egb_gemm_planes): each CTA of a cluster reduces a k
     range of one tile and the partial tiles meet through distributed shared memory."""
     import ctypes
@@ -140,11 +157,19 @@ def test_cluster_split_k_configurations(ctx, M, N, K, a_mn, b_mn, bn, ck):
     (a_hi, a_mid), lda = upload(a_st)
     (b_hi, b_mid), ldb = upload(b_st)
     c = ctx.alloc_buffer(M * N * 4); bufs.append(c)
-    c.fill(0.0)
-    flags = (16 if a_mn else 0) | (32 if b_mn else 0)
-    check(lib.egb_gemm_planes(ctx.handle, M, N, K, a_hi, a_mid, lda, b_hi, b_mid, ldb, c.device_ptr, N, flags, None,
-                              ctypes.c_float(1.0), bn | (ck << 16)))
+    c0 = rng.uniform(-1, 1, (M, N)).astype(np.float32) if xflags & 1 else np.zeros((M, N), np.float32)
+    c.write(c0)
+    bias = rng.uniform(-1, 1, (N,)).astype(np.float32)
+    dbias = ctx.alloc_buffer(N * 4); bufs.append(dbias); dbias.write(bias)
+    flags = (16 if a_mn else 0) | (32 if b_mn else 0) | xflags
+    check(lib.egb_gemm_planes(ctx.handle, M, N, K, a_hi, a_mid, lda, b_hi, b_mid, ldb, c.device_ptr, N, flags,
+                              dbias.device_ptr if xflags & 2 else None, ctypes.c_float(1.0), bn | (ck << 16)))
     got = c.read().reshape(M, N)
-    assert_close(got, a.astype(np.float64) @ b.astype(np.float64), what=f"bn{bn} ck{ck}")
+    ref = a.astype(np.float64) @ b.astype(np.float64) + c0
+    if xflags & 2:
+        ref = ref + bias
+    if xflags & 4:
+        ref = np.maximum(ref, 0)
+    assert_close(got, ref, what=f"bn{bn} ck{ck} flags{xflags}")
     for x in bufs:
         x.dealloc()

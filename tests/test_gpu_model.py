@@ -63,10 +63,11 @@ def test_dense_net_plan_uses_tensor_cores_and_graph(ctx):
     pm.apply("train", {"x": x, "y": y})
     pm.apply("train", {"x": x, "y": y})
     plan = pm.describe_plan()
-    assert plan.count(" gemm gemm tensor") == 8, plan  # 3 forward + 2 dX + 3 dW contractions
+    # 3 forward + 2 dX + 3 dW contractions; the logits contraction and the first dX one run inside the head kernel
+    assert plan.count(" gemm gemm tensor") == 6 and plan.count(" head head: gemm tensor") == 1, plan
     assert "graph yes" in plan
     assert plan.count("fused") >= 6, plan     # bias/relu, relu-adjoint/colsum and SGD stages run in GEMM epilogues
-    assert ctx.launch_count - n0 >= 2 * 12     # 8 contractions, merged root splits, fused head, bias updates
+    assert ctx.launch_count - n0 >= 2 * 10     # 6 contractions, merged root splits, fused head, bias updates
     pm.free()
 
 
@@ -88,6 +89,39 @@ def test_fused_and_unfused_plans_agree(ctx):
     for a, b, v in zip(outs[0], outs[1], params):
         assert_close(a, b, tol=1e-6, what="fused vs unfused params")
         assert_close(a - v, b - v, tol=1e-3, what="fused vs unfused update")
+
+
+@pytest.mark.parametrize("sizes,batch", [((784, 512, 512, 10), 1024), ((64, 48, 32, 10), 37), ((40, 24, 1000, 16), 130),
+                                         ((32, 16, 8, 3), 9)])
+def test_head_kernel_matches_three_launches(ctx, sizes, batch):
+    """head_rows.cu (logits contraction + softmax/crossEntropy rows + first adjoint contraction in one launch) against
+    the plan that keeps them apart (option head=0), and both against the oracle."""
+    from exprgrad_b200 import frontend as F, layers as PL, model as M
+    import oracle as o
+    from oracle import layers as OL
+    x, y, params = G.dense_inputs(batch, sizes)
+    outs = []
+    for head in (1, 0):
+        pm = M.compile(*G.dense_net(F, PL, sizes), gpu=ctx, seed=0)
+        pm.set_option("head", head)
+        for tid, v in zip(pm.params.ids(), params):
+            pm.params[tid] = v
+        for _ in range(2):
+            pm.apply("train", {"x": x, "y": y})
+        assert (" head head: " in pm.describe_plan()) == bool(head), pm.describe_plan()
+        outs.append([pm.params[t] for t in pm.params.ids()])
+        pm.free()
+    om = o.compile(*G.dense_net(o, OL, sizes, ct="threads"), seed=0)
+    ids = sorted(om.params)
+    for tid, v in zip(ids, params):
+        om.params[tid][...] = v
+    for _ in range(2):
+        om.apply("train", {"x": x, "y": y})
+    for a, b, tid, v in zip(outs[0], outs[1], ids, params):
+        assert_close(a, b, tol=1e-6, what="head kernel vs three launches: params")
+        assert_close(a - v, b - v, tol=1e-3, what="head kernel vs three launches: update")
+        assert_close(a, om.params[tid], what="head kernel vs oracle")
+        assert_close(a - v, om.params[tid] - v, tol=5e-3, what="head kernel vs oracle: update")
 
 
 @pytest.mark.parametrize("opts", [dict(concurrent=0), dict(rowchain=0), dict(graphs=0), dict(splitk=1),

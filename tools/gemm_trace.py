@@ -38,5 +38,10 @@ t0 = last[0][0]
 print("  start_us   end_us | setup  pdlwait  1st-load  mainloop  epilogue  exit | M N K BN ck grid   (phase times in us at 1.9 GHz clk)")
 for r in last:
     clk = lambda a, b: (r[b] - r[a]) / 1965.0 if r[a] and r[b] else float("nan")
+    if r[13] == 0:   # head_rows kernel
+        print(f"{(r[0]-t0)/1e3:9.2f} {(r[8]-t0)/1e3:9.2f} | head rows={r[9]} classes={r[10]} Kin={r[11]} Nout={r[12]} grid={r[14]}: tables-early {clk(1,2):.2f} pdlwait {clk(2,3):.2f} "
+              f"tables+row {clk(3,4):.2f} forward {clk(4,5):.2f} softmax+stores {clk(5,15):.2f} adjoint+stores {clk(15,16):.2f} colsums {clk(16,6):.2f}")
+        continue
     print(f"{(r[0]-t0)/1e3:9.2f} {(r[8]-t0)/1e3:9.2f} | {clk(1,2):5.2f} {clk(2,3):7.2f} {clk(3,4):8.2f} {clk(4,5):9.2f} {clk(5,6):9.2f} {clk(6,7):5.2f} | "
-          + " ".join(str(v) for v in r[9:15]) + (f" | epi unit0: tmem_ld {clk(5,15):.2f} transpose {clk(15,16):.2f} finish {clk(16,17):.2f}" if r[13] <= 1 else f" | csk: stage+sync {clk(5,15):.2f} dsmem-reduce {clk(15,16):.2f} finish {clk(16,17):.2f} cluster-wait {clk(17,6):.2f}"))
+          + " ".join(str(v) for v in r[9:15]) + (f" | epi unit0: tmem_ld {clk(5,15):.2f} transpose {clk(15,16):.2f} finish {clk(16,17):.2f}" if r[13] <= 1 else f" | csk: stage+sync {clk(5,15):.2f} dsmem-reduce {clk(15,16):.2f} finish {clk(16,17):.2f} cluster-wait {clk(17,6):.2f}")
+          + (f" | finish: inputs {clk(16,18):.2f} math {clk(18,19):.2f} fence {clk(19,20):.2f} tma-store {clk(20,21):.2f} colsum {clk(21,17):.2f}" if len(r) > 21 and r[18] else ""))
