@@ -441,11 +441,16 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None, batch=DENSE_BAT
     })
     if world > 1:
         ex = classes.get("exchange")
-        out["exchange"] = {"kernel": "dp_exchange_sgd_kernel: reduce-scatter + all-gather of the gradient bucket through "
-                                     "peer memory (NVLink 5 / NVSwitch) fused with the SGD update",
-                           "nvlink_bytes_per_rank_per_step": {"read_from_peers": int(DENSE_BUCKET_BYTES * (world - 1) / world),
-                                                              "written_to_peers": int(DENSE_BUCKET_BYTES * (world - 1) / world)},
-                           "eager_ms_per_step": ex["ms_per_step"] if ex else None}
+        # push-only protocol: reduce-scatter and all-gather each store (world-1)/world of the bucket into peer memory,
+        # every 16 payload bytes travel as a 32-byte line that carries its own epoch tag (csrc/exchange.cu)
+        payload = int(DENSE_BUCKET_BYTES * (world - 1) / world)
+        out["exchange"] = {"kernel": "dp_exchange_sgd_kernel x2 (early part of the bucket beside the last contraction, last gradient "
+                                     "behind it): reduce-scatter + all-gather by tagged peer-memory stores (NVLink 5 / NVSwitch), "
+                                     "fused with the SGD update",
+                           "nvlink_bytes_per_rank_per_step": {"read_from_peers": 0, "written_to_peers": 4 * payload,
+                                                              "payload_written_to_peers": 2 * payload},
+                           "eager_ms_per_step": ex["ms_per_step"] if ex else None,
+                           "launches_per_step": ex["launches_per_step"] if ex else None}
     model.free()
     return out
 

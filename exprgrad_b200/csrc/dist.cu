@@ -108,7 +108,8 @@ void comm_open_window(CommHooks* c, Context& ctx, char* arena, size_t arena_byte
   w.owner = c;
   EGB_CUDA(cudaMalloc((void**)&w.barrier_buf, 256));
   EGB_CUDA(cudaMemsetAsync(w.barrier_buf, 0, 256, ctx.stream));
-  const size_t fbytes = exchange_flag_bytes();
+  w.area_stride = (exchange_area_bytes(bucket_bytes, world) + 255) & ~(size_t)255;   // flags + inboxes of one exchange kernel
+  const size_t fbytes = w.area_stride * EX_AREAS;
   EGB_CUDA(cudaMalloc((void**)&w.local_flags, fbytes));
   EGB_CUDA(cudaMemsetAsync(w.local_flags, 0, fbytes, ctx.stream));
   for (int r = 0; r < EX_MAX_WORLD; ++r) {
@@ -167,11 +168,12 @@ void comm_close_window(PeerWindow& w) {
     // phase stamps of the last exchange launch (CTA 0 and the last CTA): start, after A, B, C, D (exchange.cu)
     unsigned long long t[16];
     const size_t off = (size_t)(2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) * sizeof(uint32_t);
-    if (cudaMemcpy(t, (char*)w.local_flags + off, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess)
+    for (int area = 0; area < EX_AREAS; ++area)
+    if (cudaMemcpy(t, (char*)w.local_flags + area * w.area_stride + off, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[0])
       for (int q = 0; q < 2; ++q)
-        fprintf(stderr, "egb exchange trace rank %d %s: handshake %.2f us, reduce+broadcast %.2f us, landed-handshake %.2f us, "
-                        "update %.2f us (start %llu)\n", w.rank, q == 0 ? "cta 0" : "last cta", (t[8 * q + 1] - t[8 * q]) / 1e3,
-                (t[8 * q + 2] - t[8 * q + 1]) / 1e3, (t[8 * q + 3] - t[8 * q + 2]) / 1e3, (t[8 * q + 4] - t[8 * q + 3]) / 1e3, t[8 * q]);
+        fprintf(stderr, "egb exchange %d trace rank %d %s: push %.2f us, reduce + push of the average %.2f us, update %.2f us (start %llu)\n",
+                area, w.rank, q == 0 ? "cta 0" : "last cta", (t[8 * q + 1] - t[8 * q]) / 1e3, (t[8 * q + 2] - t[8 * q + 1]) / 1e3,
+                (t[8 * q + 3] - t[8 * q + 2]) / 1e3, t[8 * q]);
   }
   for (int i = 0; i < w.nopened; ++i)
     if (w.opened[i]) cudaIpcCloseMemHandle(w.opened[i]);

@@ -6,14 +6,14 @@
 // optimizer needs their average. With NCCL this was ncclAllReduce(avg) + one gradientDescent kernel per parameter
 // (base.nim:37-38): +43 / +53 / +112 us on a 68 us step at 2 / 4 / 8 GPUs. Here it is ONE kernel per rank:
 //
-//   A  every CTA tells its partner CTAs on all peers "my rank's gradients are complete" (a flag store into the
-//      peer's memory) and waits for theirs;
-//   B  reduce-scatter: rank r sums slice r of all N buckets (N-1 of them read through NVLink, fixed rank order,
-//      so the result does not depend on timing), divides by N and
-//      all-gather: stores the averaged slice into every rank's bucket (N-1 remote stores);
-//   C  flags again: "slice r has landed everywhere";
-//   D  the gradientDescent update P += (0 - g) * rate of every parameter, straight from the averaged bucket
+//   1  reduce-scatter by PUSH: every rank stores slice s of its gradients into an inbox on rank s (N-1 remote
+//      stores of 1/N of the bucket each);
+//   2  rank r sums slice r (own part + N-1 inbox slots, all local reads, fixed rank order, so the result does not
+//      depend on timing), divides by N and stores the averaged slice into a second inbox on every rank (all-gather
+//      by push);
+//   3  the gradientDescent update P += (0 - g) * rate of every parameter straight from the averaged values
 //      (parameters never leave the rank; replicas stay bit-identical because every rank applies the same values).
+// Lines carry their own epoch tag (see st_ll): no fences, no separate flags, no grid-wide barrier, no atomics.
 //
 // CTA b of a rank only ever talks to CTA b of the other ranks (per-CTA flag slots), so there is no grid-wide
 // barrier and no atomics; flags carry a per-CTA epoch that lives in device memory, which lets the kernel sit in a
@@ -27,6 +27,8 @@ namespace egb {
 namespace {
 
 constexpr int EX_THREADS = 256;
+constexpr size_t FLAG_BYTES = (size_t)(2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) * sizeof(uint32_t) + 16 * 8;
+constexpr size_t INBOX_OFF = (FLAG_BYTES + 255) & ~(size_t)255;
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -55,6 +57,44 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) 
   }
 }
 
+__device__ __forceinline__ void st_cg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+
+// ---- "LL" lines: 16 payload bytes travel as 32 bytes, every 8-byte word = (4 bytes of data, 4-byte epoch tag).
+// An 8-byte word is written atomically, so a reader that sees the tag of this step has the data - no fence and
+// no separate flag behind a burst of remote stores. (Measured on this box, tools/probes/p2p_probe.cu: a fence.sys
+// behind 0.3-1.3 MB of peer stores completes after 8-14 us whatever the size, memcpyPeer of the same bytes takes
+// 10-11 us, while a lone 4-byte store + fence crosses in 2 us: it is the fence after a burst that is slow, not the
+// link. The first two versions of this kernel - pull, then push + flags - spent 2 x 10-17 us in exactly that.)
+__device__ __forceinline__ void st_ll(float* line, float4 v, uint32_t tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(line), "r"(__float_as_uint(v.x)), "r"(tag), "r"(__float_as_uint(v.y)) : "memory");
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(line + 4), "r"(__float_as_uint(v.z)), "r"(tag), "r"(__float_as_uint(v.w)) : "memory");
+}
+__device__ __forceinline__ float4 ld_ll(const float* line, uint32_t tag) {
+  uint32_t a0, f0, a1, f1, b0, g0, b1, g1;
+  const unsigned long long t0 = globaltimer();
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(f0), "=r"(a1), "=r"(f1) : "l"(line) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(g0), "=r"(b1), "=r"(g1) : "l"(line + 4) : "memory");
+    if (f0 == tag && f1 == tag && g0 == tag && g1 == tag) break;
+    if ((++spins & 0xff) == 0 && globaltimer() - t0 > 2000000000ull) {
+      printf("egb exchange: line %p never reached epoch %u (peer missing)\n", (const void*)line, tag);
+      __trap();
+    }
+  }
+  return make_float4(__uint_as_float(a0), __uint_as_float(a1), __uint_as_float(b0), __uint_as_float(b1));
+}
+
+// Per step and CTA b (chunk b of every slice; CTA b of a rank only ever exchanges lines with CTA b of its peers):
+//   1  push: chunk b of slice s of this rank's gradients -> inbox 1, slot `me`, of rank s (every s != me);
+//   2  chunk b of MY slice: own part + the peers' lines as they arrive, summed in rank order (the result does not
+//      depend on timing), averaged, stored into my bucket and pushed into inbox 2, slot `me`, of every peer;
+//   3  every slice: the averaged chunk (own: from the bucket, others: inbox 2 as it arrives) goes into the bucket
+//      (optimizers other than gradientDescent read it there) and through the fused gradientDescent update.
+// Re-use of the inboxes by the next step is safe without further synchronisation: a rank enters step t + 1 only
+// after ITS kernel of step t has ended, i.e. after it received every averaged line of step t, which the peers
+// produced after consuming inbox 1; and a peer writes inbox 2 of step t + 1 only after it has received this rank's
+// step t + 1 contributions, sent after this rank's step t kernel (and its inbox 2 reads) had ended.
 __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __grid_constant__ ExchangeParams p) {
   __shared__ uint32_t epoch_sm;
   pdl_wait();   // every gradient kernel of this rank has completed (no early launch_dependents: the grid spins)
@@ -69,95 +109,116 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
       reinterpret_cast<unsigned long long*>(my_flags + 2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) + (b == 0 ? 0 : 8);
   const bool stamp = tid == 0 && (b == 0 || b == G - 1);
   if (stamp) stamps[0] = globaltimer();
-  // ---- A: gradients of this rank are complete -> tell CTA b of every rank, wait for CTA b of every rank
-  if (tid < N) {
-    __threadfence_system();
-    st_release_sys(p.flags[tid] + (size_t)me * EX_MAX_CTAS + b, epoch);
-    wait_flag(my_flags + (size_t)tid * EX_MAX_CTAS + b, epoch);
-  }
-  __syncthreads();
-  if (stamp) stamps[1] = globaltimer();
-  // ---- B: reduce slice `me` from all buckets, average, store it into every bucket
   const long long n4 = p.n >> 2;                       // 16-byte groups (bucket tensors are 256-byte aligned)
   const long long S = (n4 + N - 1) / N;                // groups per rank slice
   const long long C = (S + G - 1) / G;                 // groups per CTA and slice
+  const size_t inbox2_off = INBOX_OFF + (size_t)N * S * 32;
+  float* const own = p.bucket[me];
+  auto inbox = [&](int rank, size_t off, int slot, long long gi) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(p.flags[rank]) + off) + (((long long)slot * S + gi) << 3);
+  };
+  // ---- 1: push my contributions. Item = (peer index, group of the chunk); four loads in flight per thread.
   {
-    const long long lo = (long long)me * S + (long long)b * C;
-    const long long hi = min(min(lo + C, (long long)(me + 1) * S), n4);
-    const float nf = (float)N;
-    for (long long g = lo + tid; g < hi; g += EX_THREADS) {
-      float4 v[EX_MAX_WORLD];
+    const long long items = C * (N - 1);
+    for (long long base = 0; base < items; base += 4 * EX_THREADS) {
+      float4 v[4];
+      float* dst[4];
 #pragma unroll
-      for (int r = 0; r < EX_MAX_WORLD; ++r)
-        if (r < N) v[r] = ld_cg4(p.bucket[r] + (g << 2));
-      float4 acc = v[0];
-#pragma unroll
-      for (int r = 1; r < EX_MAX_WORLD; ++r)
-        if (r < N) {
-          acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w;
+      for (int u = 0; u < 4; ++u) {
+        const long long it = base + (long long)u * EX_THREADS + tid;
+        dst[u] = nullptr;
+        if (it < items) {
+          const int pi = (int)(it / C);
+          const int sdst = pi + (pi >= me ? 1 : 0);
+          const long long gi = (long long)b * C + (it - (long long)pi * C);      // group inside the slice
+          const long long g = (long long)sdst * S + gi;
+          if (gi < S && g < n4) {
+            v[u] = ld_cg4(own + (g << 2));
+            dst[u] = inbox(sdst, INBOX_OFF, me, gi);
+          }
         }
-      acc.x = __fdiv_rn(acc.x, nf); acc.y = __fdiv_rn(acc.y, nf);
-      acc.z = __fdiv_rn(acc.z, nf); acc.w = __fdiv_rn(acc.w, nf);
+      }
 #pragma unroll
-      for (int r = 0; r < EX_MAX_WORLD; ++r)
-        if (r < N) *reinterpret_cast<float4*>(p.bucket[r] + (g << 2)) = acc;
+      for (int u = 0; u < 4; ++u)
+        if (dst[u]) st_ll(dst[u], v[u], epoch);
     }
   }
-  // ---- C: slice `me`, chunk b has landed everywhere
-  __syncthreads();
-  if (stamp) stamps[2] = globaltimer();
-  if (tid < N) {
-    __threadfence_system();
-    st_release_sys(p.flags[tid] + (size_t)(EX_MAX_WORLD + me) * EX_MAX_CTAS + b, epoch);
-    wait_flag(my_flags + (size_t)(EX_MAX_WORLD + tid) * EX_MAX_CTAS + b, epoch);
+  if (stamp) stamps[1] = globaltimer();
+  // ---- 2: reduce chunk b of my slice (rank order), average, store it into my bucket and push it to every peer
+  {
+    const float nf = (float)N;
+    for (long long gi = (long long)b * C + tid; gi < (long long)(b + 1) * C; gi += EX_THREADS) {
+      const long long g = (long long)me * S + gi;
+      if (gi >= S || g >= n4) break;
+      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      for (int r = 0; r < N; ++r) {
+        const float4 v = r == me ? ld_cg4(own + (g << 2)) : ld_ll(inbox(me, INBOX_OFF, r, gi), epoch);
+        if (r == 0) acc = v;
+        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      }
+      acc.x = __fdiv_rn(acc.x, nf); acc.y = __fdiv_rn(acc.y, nf);
+      acc.z = __fdiv_rn(acc.z, nf); acc.w = __fdiv_rn(acc.w, nf);
+      st_cg4(own + (g << 2), acc);
+      for (int r = 0; r < N; ++r)
+        if (r != me) st_ll(inbox(r, inbox2_off, me, gi), acc, epoch);
+    }
   }
-  __syncthreads();
-  if (stamp) stamps[3] = globaltimer();
-  // ---- D: gradientDescent from the averaged bucket: chunk b of every slice (exactly the chunks whose flags
-  //         this CTA has just seen)
-  if (p.nseg > 0) {
-    float* const mine = p.bucket[me];
-    for (int r = 0; r < N; ++r) {
-      const long long lo = (long long)r * S + (long long)b * C;
-      const long long hi = min(min(lo + C, (long long)(r + 1) * S), n4);
-      for (long long g = lo + tid; g < hi; g += EX_THREADS) {
-        const long long i = g << 2;
-        int s = -1;
-        for (int q = 0; q < p.nseg; ++q)
-          if (i >= p.seg[q].off && i < p.seg[q].off + p.seg[q].len) s = q;
-        if (s < 0) continue;   // alignment padding between tensors
-        const ExchangeSeg sg = p.seg[s];
-        const float4 gv = ld_cg4(mine + i);
-        float* dst = sg.param + (i - sg.off);
-        const long long left = sg.off + sg.len - i;
-        if (left >= 4) {
-          float4 pv = *reinterpret_cast<const float4*>(dst);
-          // P += (0 - g) * rate   (base.nim:37-38; negate is 0 - x, llvm.nim:333-336; un-contracted)
-          pv.x = __fadd_rn(pv.x, __fmul_rn(0.0f - gv.x, sg.rate));
-          pv.y = __fadd_rn(pv.y, __fmul_rn(0.0f - gv.y, sg.rate));
-          pv.z = __fadd_rn(pv.z, __fmul_rn(0.0f - gv.z, sg.rate));
-          pv.w = __fadd_rn(pv.w, __fmul_rn(0.0f - gv.w, sg.rate));
-          *reinterpret_cast<float4*>(dst) = pv;
-        } else {
-          const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
-          for (int e = 0; e < (int)left; ++e) dst[e] = __fadd_rn(dst[e], __fmul_rn(0.0f - ge[e], sg.rate));
-        }
+  __syncthreads();   // (phase 3 re-reads this CTA's part of the bucket with another thread mapping at the slice ends)
+  if (stamp) stamps[2] = globaltimer();
+  // ---- 3: the averaged chunk b of every slice: into the bucket, and gradientDescent straight from it
+  for (int r = 0; r < N; ++r) {
+    const long long lo = (long long)r * S + (long long)b * C;
+    const long long hi = min(min(lo + C, (long long)(r + 1) * S), n4);
+    for (long long g = lo + tid; g < hi; g += EX_THREADS) {
+      const long long i = g << 2;
+      float4 gv;
+      if (r == me) {
+        gv = ld_cg4(own + i);
+      } else {
+        gv = ld_ll(inbox(me, inbox2_off, r, g - (long long)r * S), epoch);
+        st_cg4(own + i, gv);
+      }
+      if (p.nseg == 0) continue;
+      int s = -1;
+      for (int q = 0; q < p.nseg; ++q)
+        if (i >= p.seg[q].off && i < p.seg[q].off + p.seg[q].len) s = q;
+      if (s < 0) continue;   // alignment padding between tensors
+      const ExchangeSeg sg = p.seg[s];
+      float* dst = sg.param + (i - sg.off);
+      const long long left = sg.off + sg.len - i;
+      if (left >= 4) {
+        float4 pv = *reinterpret_cast<const float4*>(dst);
+        // P += (0 - g) * rate   (base.nim:37-38; negate is 0 - x, llvm.nim:333-336; un-contracted)
+        pv.x = __fadd_rn(pv.x, __fmul_rn(0.0f - gv.x, sg.rate));
+        pv.y = __fadd_rn(pv.y, __fmul_rn(0.0f - gv.y, sg.rate));
+        pv.z = __fadd_rn(pv.z, __fmul_rn(0.0f - gv.z, sg.rate));
+        pv.w = __fadd_rn(pv.w, __fmul_rn(0.0f - gv.w, sg.rate));
+        *reinterpret_cast<float4*>(dst) = pv;
+      } else {
+        const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
+        for (int e = 0; e < (int)left; ++e) dst[e] = __fadd_rn(dst[e], __fmul_rn(0.0f - ge[e], sg.rate));
       }
     }
   }
   if (tid == 0) *epoch_slot = epoch;
-  if (stamp) stamps[4] = globaltimer();
+  if (stamp) stamps[3] = globaltimer();
 }
 
 }  // namespace
 
-size_t exchange_flag_bytes() { return (size_t)(2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) * sizeof(uint32_t) + 16 * 8; }
+size_t exchange_flag_bytes() { return FLAG_BYTES; }
+// flag area + the two inboxes (one slot of ceil(n4 / world) lines per source rank each), one peer-mapped allocation
+size_t exchange_area_bytes(size_t bucket_bytes, int world) {
+  const size_t n4 = bucket_bytes / 16, S = (n4 + world - 1) / world;
+  return INBOX_OFF + 2 * (size_t)world * S * 32 + 256;   // two inboxes of `world` slots, 32 bytes per 16 payload bytes
+}
 
 void launch_exchange(Context& ctx, const ExchangeParams& p, cudaStream_t st) {
   if (p.world < 1 || p.world > EX_MAX_WORLD) fail(EGB_ERR_GPU, "exchange: world size %d is not supported (max %d)", p.world, EX_MAX_WORLD);
   if (p.n % 4 != 0) fail(EGB_ERR_GPU, "exchange: bucket length must be a multiple of 4 floats");
   int grid = ctx.sm_count < EX_MAX_CTAS ? ctx.sm_count : EX_MAX_CTAS;
   grid = grid / 8 * 8;
+  if (p.ctas > 0 && p.ctas < grid) grid = p.ctas;
   Launch l(ctx, KC_EXCHANGE, st);
   launch_kernel(ctx, dp_exchange_sgd_kernel, dim3((unsigned)grid), dim3(EX_THREADS), 0, st, p);
   EGB_CUDA(cudaGetLastError());

@@ -682,35 +682,57 @@ void build_nodes_impl(Model& m, Plan& plan) {
     const KernelInfo& inf = info[ki];
     if (inf.absorbed_by >= 0) continue;  // runs inside the epilogue of its contraction
     if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes && plan.window.mapped) {
-      // one fused kernel: gradient exchange through peer memory + the gradientDescent updates it feeds
-      Node n;
-      n.kind = Node::EXCHANGE;
-      ExchangeParams& xp = n.exchange;
-      memset((void*)&xp, 0, sizeof(xp));
-      xp.rank = plan.window.rank;
-      xp.world = plan.window.world;
-      xp.n = (long long)(plan.bucket_bytes / 4);
-      for (int r = 0; r < xp.world; ++r) {
-        xp.bucket[r] = (float*)(plan.window.arena[r] + plan.bucket_off);
-        xp.flags[r] = plan.window.flags[r];
-      }
-      xp.nseg = (int)plan.exchange_segs.size();
-      for (int q = 0; q < xp.nseg; ++q) {
-        xp.seg[q] = plan.exchange_segs[(size_t)q];
-        xp.seg[q].param = (float*)ptrs[plan.exchange_seg_param[(size_t)q]];
-        n.reads.push_back(plan.exchange_seg_param[(size_t)q]);
-        n.writes.push_back(plan.exchange_seg_param[(size_t)q]);
-      }
+      // Fused kernel(s): gradient exchange through peer memory + the gradientDescent updates it feeds. The bucket is
+      // laid out by readiness; when its last tensor (the gradient the step's final contraction produces) is a
+      // sizeable part of it, the bucket is exchanged in two launches: everything that is ready earlier travels on a
+      // side stream while that contraction is still running (few CTAs: it only has the SMs the contraction leaves
+      // free), and only the last gradient's exchange - which then depends on nothing but that contraction and keeps
+      // its programmatic edge - is exposed at the end of the step.
+      size_t last_off = 0;   // arena offset of the bucket tensor with the highest address
       for (auto& kv : plan.tensors) {
-        const char* p0 = (const char*)kv.second.ptr;
-        if (p0 >= plan.arena + plan.bucket_off && p0 < plan.arena + plan.bucket_off + plan.bucket_bytes) {
-          n.reads.push_back(kv.first);
-          n.writes.push_back(kv.first);
-        }
+        const size_t off = (size_t)((const char*)kv.second.ptr - plan.arena);
+        if (off >= plan.bucket_off && off < plan.bucket_off + plan.bucket_bytes) last_off = std::max(last_off, off);
       }
-      n.label = "peer exchange of the gradient bucket (" + std::to_string(plan.bucket_bytes) + " bytes, " + std::to_string(xp.world) +
-                " ranks) + " + std::to_string(xp.nseg) + " fused gradientDescent updates";
-      plan.nodes.push_back(n);
+      const size_t tail_bytes = plan.bucket_off + plan.bucket_bytes - last_off;
+      static const bool one_exchange = getenv("EGB_DP_ONE_EXCHANGE") != nullptr;
+      const bool two = !one_exchange && last_off > plan.bucket_off && tail_bytes * 4 >= plan.bucket_bytes && plan.window.area_stride > 0;
+      for (int part = 0; part < (two ? 2 : 1); ++part) {
+        const size_t r_off = two && part == 1 ? last_off : plan.bucket_off;
+        const size_t r_bytes = !two ? plan.bucket_bytes : part == 0 ? last_off - plan.bucket_off : tail_bytes;
+        Node n;
+        n.kind = Node::EXCHANGE;
+        ExchangeParams& xp = n.exchange;
+        memset((void*)&xp, 0, sizeof(xp));
+        xp.rank = plan.window.rank;
+        xp.world = plan.window.world;
+        xp.n = (long long)(r_bytes / 4);
+        static const int early_ctas = getenv("EGB_DP_EARLY_CTAS") ? atoi(getenv("EGB_DP_EARLY_CTAS")) : 64;
+        xp.ctas = two && part == 0 ? early_ctas : 0;
+        for (int r = 0; r < xp.world; ++r) {
+          xp.bucket[r] = (float*)(plan.window.arena[r] + r_off);
+          xp.flags[r] = (uint32_t*)((char*)plan.window.flags[r] + (size_t)part * plan.window.area_stride);
+        }
+        for (size_t q = 0; q < plan.exchange_segs.size() && xp.nseg < EX_MAX_SEG; ++q) {
+          ExchangeSeg sg = plan.exchange_segs[q];
+          const size_t seg_off = plan.bucket_off + (size_t)sg.off * 4;
+          if (seg_off < r_off || seg_off >= r_off + r_bytes) continue;
+          sg.off = (long long)((seg_off - r_off) / 4);
+          sg.param = (float*)ptrs[plan.exchange_seg_param[q]];
+          xp.seg[xp.nseg++] = sg;
+          n.reads.push_back(plan.exchange_seg_param[q]);
+          n.writes.push_back(plan.exchange_seg_param[q]);
+        }
+        for (auto& kv : plan.tensors) {
+          const char* p0 = (const char*)kv.second.ptr;
+          if (p0 >= plan.arena + r_off && p0 < plan.arena + r_off + r_bytes) {
+            n.reads.push_back(kv.first);
+            n.writes.push_back(kv.first);
+          }
+        }
+        n.label = "peer exchange of the gradient bucket (" + std::to_string(r_bytes) + " bytes" + (two ? (part == 0 ? ", early part" : ", last gradient") : "") +
+                  ", " + std::to_string(xp.world) + " ranks) + " + std::to_string(xp.nseg) + " fused gradientDescent updates";
+        plan.nodes.push_back(n);
+      }
     } else if ((int)ki == plan.bucket_before_kernel && plan.bucket_bytes) {
       for (auto& seg : plan.bucket_segments) {
         Node n;

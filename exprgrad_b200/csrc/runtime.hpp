@@ -35,7 +35,8 @@ void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st);
 // Data-parallel gradient exchange through peer memory (exchange.cu, dist.cu)
 constexpr int EX_MAX_WORLD = 8;    // ranks of one NVSwitch domain
 constexpr int EX_MAX_CTAS = 128;   // CTAs of the exchange kernel (= flag slots per rank)
-constexpr int EX_MAX_SEG = 32;     // parameters whose gradientDescent update is fused into the exchange
+constexpr int EX_MAX_SEG = 32;
+constexpr int EX_AREAS = 2;        // exchange kernels per plan (early part of the bucket / last gradient)     // parameters whose gradientDescent update is fused into the exchange
 struct ExchangeSeg {
   long long off = 0, len = 0;      // floats, relative to the bucket
   float* param = nullptr;
@@ -47,9 +48,11 @@ struct ExchangeParams {
   uint32_t* flags[EX_MAX_WORLD];   // every rank's flag area: ready[world][ctas], done[world][ctas], epoch[ctas]
   ExchangeSeg seg[EX_MAX_SEG];
   long long n = 0;                 // floats per bucket (multiple of 4)
-  int rank = 0, world = 1, nseg = 0, pad = 0;
+  int rank = 0, world = 1, nseg = 0;
+  int ctas = 0;                    // CTAs of this exchange (0 = default); the same on every rank
 };
 size_t exchange_flag_bytes();
+size_t exchange_area_bytes(size_t bucket_bytes, int world);
 void launch_exchange(Context& ctx, const ExchangeParams& p, cudaStream_t st);
 
 // Peer mappings of one plan's arena and flag area on every rank (cudaIpc handles exchanged once per plan)
@@ -61,7 +64,8 @@ struct PeerWindow {
   int world = 1, rank = 0;
   char* arena[EX_MAX_WORLD] = {};      // base of rank r's arena as seen from this process
   uint32_t* flags[EX_MAX_WORLD] = {};
-  uint32_t* local_flags = nullptr;     // this rank's flag area (owned)
+  uint32_t* local_flags = nullptr;     // this rank's flag + inbox areas (owned): EX_AREAS exchanges per plan
+  size_t area_stride = 0;              // bytes between the areas of two exchange nodes
   void* opened[2 * EX_MAX_WORLD] = {}; // IPC mappings to close
   int nopened = 0;
 };

@@ -14,6 +14,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _fused_updates(plan):
+    """gradientDescent updates that run inside the exchange kernel(s) of a plan (the bucket may travel in two launches)"""
+    import re
+    return sum(int(m) for m in re.findall(r"\+ (\d+) fused gradientDescent updates", plan))
+
+
 def _worker(rank, world, port, sizes, per_gpu, steps, out, mode="peer"):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
@@ -52,7 +58,7 @@ def _worker(rank, world, port, sizes, per_gpu, steps, out, mode="peer"):
         plan = pm.describe_plan()
         assert ("allreduce" if mode == "nccl" else " exchange peer exchange") in plan and "graph yes" in plan, plan
         if mode in ("peer", "resume"):
-            assert "6 fused gradientDescent updates" in plan, plan
+            assert _fused_updates(plan) == 6, plan
         got = [pm.params[t] for t in pm.params.ids()]
         if rank == 0:
             out.put(got)
@@ -66,7 +72,10 @@ def _adam_net(d, L, sizes):
     h = L.relu(L.dense(x, sizes[0], sizes[1]))
     h = L.relu(L.dense(h, sizes[1], sizes[2]))
     p = L.softmax(L.dense(h, sizes[2], sizes[3]))
-    return [L.cross_entropy(p, y).backprop(L.adam(0.01)).target("train", "gpu")]
+    # eps = 1e-2: with the default 1e-8 every element's step is ~rate * sign(g) and elements whose shard gradients
+    # nearly cancel amplify summation-order differences without bound (exact fp64 arithmetic is already 9e-5 away
+    # from the oracle's fp32 loop after 3 steps); the default eps is covered on one GPU by test_fashion_net_adam_fit
+    return [L.cross_entropy(p, y).backprop(L.adam(0.01, eps=1e-2)).target("train", "gpu")]
 
 
 @pytest.mark.parametrize("sizes,per_gpu,steps,mode", [((64, 48, 32, 10), 24, 3, "peer"), ((784, 512, 512, 10), 1024, 2, "peer"),
@@ -101,15 +110,6 @@ def test_data_parallel_matches_global_batch_oracle(sizes, per_gpu, steps, mode):
         om.epoch += 1
         om.apply("train", {"x": x, "y": y})
     for g, tid, v in zip(got, ids, params):
-        if mode == "adam":
-            # adam normalises every element's step to ~rate * sign(g): elements whose shard gradients nearly cancel
-            # amplify rounding differences of the summation order (measured on the CPU: exact fp64 arithmetic is
-            # already 9e-5 away from the oracle's fp32 loop after 3 steps on this net). Bulk criterion: 99 % of the
-            # elements within the 1e-4 bar, every element within one step.
-            e = np.abs(g.astype(np.float64) - om.params[tid]) / np.abs(om.params[tid]).max()
-            assert np.quantile(e, 0.99) <= 1e-4, f"adam param tensor{tid - 1}: 99th percentile error {np.quantile(e, 0.99):.3e}"
-            assert e.max() <= 0.02, f"adam param tensor{tid - 1}: max error {e.max():.3e}"
-            continue
         assert_close(g, om.params[tid], what=f"param tensor{tid - 1}")
         assert_close(g - v, om.params[tid] - v, tol=2e-3, what=f"update of tensor{tid - 1}")
 
@@ -145,7 +145,7 @@ def test_single_rank_exchange_plan_matches_plain_plan(opt):
             os.environ.pop("EGB_DP_FORCE", None)
         if dp:
             assert " exchange peer exchange" in plan, plan
-            assert ("6 fused gradientDescent updates" in plan) == (opt == "sgd"), plan
+            assert _fused_updates(plan) == (6 if opt == "sgd" else 0), plan
         outs.append([pm.params[t] for t in pm.params.ids()])
         pm.free()
         if comm is not None:
@@ -186,6 +186,6 @@ def test_bucket_is_found_without_the_gradient_table():
             pm.free(); comm.destroy()
     finally:
         os.environ.pop("EGB_DP_FORCE", None)
-    assert "6 fused gradientDescent updates" in plans[0]
+    assert _fused_updates(plans[0]) == 6
     assert plans[0] == plans[1]
     ctx.destroy()

@@ -12,6 +12,10 @@ from exprgrad_b200 import frontend as F, layers as PL
 import graphs as G
 ctx = eg.new_gpu_context()
 pm = eg.compile(*G.dense_net(F, PL), gpu=ctx, seed=0)
+if os.environ.get("EGB_DP_FORCE"):   # the data-parallel plan layout on one rank (gradient bucket + exchange kernel)
+    from exprgrad_b200 import dist as D
+    comm = D.Comm(ctx, 0, 1)
+    D.set_data_parallel(pm, comm)
 for kv in sys.argv[1:]:          # planner options, e.g. concurrent=0 splitk=0
     k, v = kv.split("="); pm.set_option(k, int(v))
 x, y, params = G.dense_inputs(1024)
@@ -32,7 +36,7 @@ pm.apply("train", {"x": dx, "y": dy}, sync=True)   # one isolated replay: its st
 print(pm.describe_plan())
 pm.free(); ctx.destroy()
 rows = [list(map(int, l.split())) for l in open(OUT)]
-last = [r for r in rows if r[0]][-8:]   # graph replays overwrite the slots of the captured launches
+last = [r for r in rows if r[0]][-9:]   # graph replays overwrite the slots of the captured launches
 last.sort(key=lambda r: r[0])
 t0 = last[0][0]
 print("  start_us   end_us | setup  pdlwait  1st-load  mainloop  epilogue  exit | M N K BN ck grid   (phase times in us at 1.9 GHz clk)")
