@@ -223,6 +223,7 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st);
 bool gemm_lat_eligible(const GemmArgs& a);
 bool launch_gemm_lat(Context& ctx, const GemmArgs& a, cudaStream_t st);   // false: not launched (does not fit)
 void gemm_lat_plan(int M, int N, int K, bool b_mn, int sms, int max_ck, int* bn, int* ck);  // host-only
+int gemm_planned_ctas(const GemmArgs& a, int sm_budget, int machine_sms);                  // host-only
 void gemm_plan(int M, int N, int K, bool b_mn, int sms, int machine_sms, int max_ck, int* bn, int* ck);  // host-only
 
 // Fused softmax + crossEntropy forward/adjoint row kernel (fused_rows.cu)

@@ -754,6 +754,30 @@ void gemm_choose_config(int M, int N, int K, bool b_mn, int sm_count, int* bn, i
   *tiles = ((M + BM - 1) / BM) * ((N + *bn - 1) / *bn);
 }
 
+// CTAs the launch of `a` will occupy when it may plan for `sm_budget` SMs (0 = all) of a machine of `machine_sms`:
+// the planner's view of launch_gemm_bf16x3's dispatch (host only).
+int gemm_planned_ctas(const GemmArgs& a, int sm_budget, int machine_sms) {
+  if (a.M <= 0 || a.N <= 0) return 0;
+  if (a.bn == 0 && gemm_2cta_eligible(a)) return machine_sms;
+  const int sms = (sm_budget > 0 && sm_budget < machine_sms) ? sm_budget : machine_sms;
+  const int tiles_m = (a.M + BM - 1) / BM;
+  const bool small = tiles_m * ((a.N + 255) / 256) * 2 <= machine_sms;
+  int bn = a.bn, ck = a.cluster_k > 0 ? a.cluster_k : 1;
+  if (bn == 0) {
+    int ck_auto = 1;
+    if (small && gemm_lat_eligible(a)) {
+      gemm_lat_plan(a.M, a.N, a.K, a.b_mn, sms, a.cluster_k == 1 ? 1 : (a.cluster_k > 1 ? a.cluster_k : 4), &bn, &ck_auto);
+      if (a.cluster_k == 0) ck = ck_auto;
+      if (ck > 1 && bn > 64) bn = 64;
+    } else {
+      gemm_plan(a.M, a.N, a.K, a.b_mn, sms, machine_sms, a.cluster_k == 1 ? 1 : 8, &bn, &ck_auto);
+      if (a.cluster_k == 0) ck = ck_auto;
+    }
+  }
+  const int units = tiles_m * ((a.N + bn - 1) / bn) * (ck > 1 ? ck : 1);
+  return (ck > 1 || units < sms) ? units : sms;
+}
+
 void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return;
   if (a.K <= 0) fail(EGB_ERR_GPU, "gemm: K must be positive");

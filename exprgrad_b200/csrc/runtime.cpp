@@ -1000,14 +1000,54 @@ void build_nodes_impl(Model& m, Plan& plan) {
         level_work[n.level] += (double)n.gemm.M * n.gemm.N * n.gemm.K;
         level_gemms[n.level]++;
       }
-    for (auto& n : plan.nodes)
+    // The contraction chain that bounds the step (longest path by the capture's cost model) must never wait for
+    // SMs: a side contraction of level L is still running when the chain's contraction of level L + 1 wants to
+    // start (timeline of the dense step: the 64 CTAs of the layer-2 weight gradient kept the 112-CTA layer-1
+    // weight gradient waiting for 3 us), so it only gets the SMs that one leaves free.
+    std::vector<char> chain(plan.nodes.size(), 0);
+    {
+      const int nn = (int)plan.nodes.size();
+      auto hit = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+        for (auto x : a)
+          for (auto y : b)
+            if (x == y) return true;
+        return false;
+      };
+      std::vector<double> longest((size_t)nn, 0.0);
+      std::vector<int> via((size_t)nn, -1);
+      int end = -1;
+      for (int i = 0; i < nn; ++i) {
+        const Node& nd = plan.nodes[(size_t)i];
+        const double cost = nd.kind == Node::GEMM ? 8.0 + 3e-9 * (double)nd.gemm.M * nd.gemm.N * nd.gemm.K : nd.kind == Node::EXCHANGE ? 12.0 : 4.0;
+        longest[(size_t)i] = cost;
+        for (int j = 0; j < i; ++j) {
+          const Node& pj = plan.nodes[(size_t)j];
+          if ((hit(pj.writes, nd.reads) || hit(pj.writes, nd.writes) || hit(pj.reads, nd.writes)) && longest[(size_t)j] + cost > longest[(size_t)i]) {
+            longest[(size_t)i] = longest[(size_t)j] + cost;
+            via[(size_t)i] = j;
+          }
+        }
+        if (end < 0 || longest[(size_t)i] > longest[(size_t)end]) end = i;
+      }
+      for (int i = end; i >= 0; i = via[(size_t)i]) chain[(size_t)i] = 1;
+    }
+    std::map<int, int> chain_need;   // level -> CTAs of the chain's contraction at that level (planned for the whole machine)
+    for (size_t i = 0; i < plan.nodes.size(); ++i) {
+      const Node& n = plan.nodes[i];
+      if (n.kind == Node::GEMM && chain[i] && level_gemms[n.level] == 1) chain_need[n.level] = gemm_planned_ctas(n.gemm, 0, m.ctx->sm_count);
+    }
+    for (size_t i = 0; i < plan.nodes.size(); ++i) {
+      Node& n = plan.nodes[i];
       if (n.kind == Node::GEMM && level_gemms[n.level] > 1) {
         const double share = (double)n.gemm.M * n.gemm.N * n.gemm.K / level_work[n.level];
         int budget = (int)(m.ctx->sm_count * share) / 8 * 8;
+        auto next = chain_need.find(n.level + 1);
+        if (!chain[i] && next != chain_need.end()) budget = std::min(budget, (m.ctx->sm_count - next->second) / 8 * 8);
         if (budget < 16) budget = 16;
         n.gemm.sm_budget = budget;
         n.label += " sm<=" + std::to_string(budget);
       }
+    }
   }
   for (auto& n : plan.nodes)
     if (n.kind != Node::MEMSET && n.kind != Node::ALLREDUCE) plan.launches_per_run++;
