@@ -425,7 +425,7 @@ def run_dense(args, ctx, timer, rank, world, comm, sampler=None, batch=DENSE_BAT
     g = classes.get("gemm", {"ms_per_step": 0.0, "launches_per_step": 0})
     out.update({
         "plan_nodes": plan.count("\n  #"), "cuda_graph": "graph yes" in plan,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_kernel (8 contractions per step; cluster split-K, fused epilogues)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_lat_kernel / gemm_bf16x3_kernel (%d contraction launches per step: cluster split-K, fused epilogues; the two 10-class contractions run inside head_rows_kernel - the rate below divides ALL contraction flops of the step by the contraction launches' time)" % int(g["launches_per_step"]),
                      "achieved": 3 * flop / max(g["ms_per_step"], 1e-9) / 1e9, "peak": peaks["bf16_sustained"],
                      "unit": "TFLOP/s", "frac": 3 * flop / max(g["ms_per_step"], 1e-9) / 1e9 / peaks["bf16_sustained"],
                      "traffic": None, "passes": 3,

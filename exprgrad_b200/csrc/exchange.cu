@@ -19,6 +19,8 @@
 // barrier and no atomics; flags carry a per-CTA epoch that lives in device memory, which lets the kernel sit in a
 // replayed CUDA graph with constant parameters. Per rank and step (N - 1) / N of the bucket crosses NVLink in
 // each direction. Waits are bounded: a peer that never arrives traps the kernel instead of hanging the GPU.
+#include <stdlib.h>
+
 #include "egb_internal.hpp"
 #include "runtime.hpp"
 
@@ -69,7 +71,7 @@ __device__ __forceinline__ void st_ll(float* line, float4 v, uint32_t tag) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(line), "r"(__float_as_uint(v.x)), "r"(tag), "r"(__float_as_uint(v.y)) : "memory");
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(line + 4), "r"(__float_as_uint(v.z)), "r"(tag), "r"(__float_as_uint(v.w)) : "memory");
 }
-__device__ __forceinline__ float4 ld_ll(const float* line, uint32_t tag) {
+__device__ __forceinline__ float4 ld_ll(const float* line, uint32_t tag, uint32_t ll_backoff_ns) {
   uint32_t a0, f0, a1, f1, b0, g0, b1, g1;
   const unsigned long long t0 = globaltimer();
   uint32_t spins = 0;
@@ -77,6 +79,9 @@ __device__ __forceinline__ float4 ld_ll(const float* line, uint32_t tag) {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(f0), "=r"(a1), "=r"(f1) : "l"(line) : "memory");
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(g0), "=r"(b1), "=r"(g1) : "l"(line + 4) : "memory");
     if (f0 == tag && f1 == tag && g0 == tag && g1 == tag) break;
+    // 32 K threads that re-read their line as fast as they can load the L2 with ~4 TB/s of polling - the same L2 the
+    // peers' stores are arriving in; sleep between looks
+    __nanosleep(ll_backoff_ns);
     if ((++spins & 0xff) == 0 && globaltimer() - t0 > 2000000000ull) {
       printf("egb exchange: line %p never reached epoch %u (peer missing)\n", (const void*)line, tag);
       __trap();
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
       if (gi >= S || g >= n4) break;
       float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       for (int r = 0; r < N; ++r) {
-        const float4 v = r == me ? ld_cg4(own + (g << 2)) : ld_ll(inbox(me, INBOX_OFF, r, gi), epoch);
+        const float4 v = r == me ? ld_cg4(own + (g << 2)) : ld_ll(inbox(me, INBOX_OFF, r, gi), epoch, p.backoff_ns);
         if (r == 0) acc = v;
         else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
       }
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
       if (r == me) {
         gv = ld_cg4(own + i);
       } else {
-        gv = ld_ll(inbox(me, inbox2_off, r, g - (long long)r * S), epoch);
+        gv = ld_ll(inbox(me, inbox2_off, r, g - (long long)r * S), epoch, p.backoff_ns);
         st_cg4(own + i, gv);
       }
       if (p.nseg == 0) continue;
@@ -219,8 +224,11 @@ void launch_exchange(Context& ctx, const ExchangeParams& p, cudaStream_t st) {
   int grid = ctx.sm_count < EX_MAX_CTAS ? ctx.sm_count : EX_MAX_CTAS;
   grid = grid / 8 * 8;
   if (p.ctas > 0 && p.ctas < grid) grid = p.ctas;
+  ExchangeParams q = p;
+  static const int backoff = getenv("EGB_DP_BACKOFF_NS") ? atoi(getenv("EGB_DP_BACKOFF_NS")) : 400;
+  q.backoff_ns = backoff;
   Launch l(ctx, KC_EXCHANGE, st);
-  launch_kernel(ctx, dp_exchange_sgd_kernel, dim3((unsigned)grid), dim3(EX_THREADS), 0, st, p);
+  launch_kernel(ctx, dp_exchange_sgd_kernel, dim3((unsigned)grid), dim3(EX_THREADS), 0, st, q);
   EGB_CUDA(cudaGetLastError());
 }
 

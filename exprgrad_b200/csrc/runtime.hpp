@@ -50,6 +50,7 @@ struct ExchangeParams {
   long long n = 0;                 // floats per bucket (multiple of 4)
   int rank = 0, world = 1, nseg = 0;
   int ctas = 0;                    // CTAs of this exchange (0 = default); the same on every rank
+  int backoff_ns = 0;              // sleep between two looks at a line that has not arrived yet
 };
 size_t exchange_flag_bytes();
 size_t exchange_area_bytes(size_t bucket_bytes, int world);
