@@ -50,6 +50,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int UNIT = 32;                       // an epilogue unit is 32 rows x 32 columns
 constexpr int F32_TILE = UNIT * UNIT * 4;      // 4 KB, rows of 128 bytes, SWIZZLE_128B
 constexpr int BF16_TILE = UNIT * UNIT * 2;     // 2 KB, rows of 64 bytes, SWIZZLE_64B
+constexpr int EPI_DYNAMIC = 100;   // template argument: second stage chosen at run time
 constexpr int BAR_BYTES = (2 * MAX_STAGES + 4 + 2 * EPI_WARPS) * 8 + 32 + TRACE_SLOT_WORDS * 8;
 
 struct LParams {
@@ -107,6 +108,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+// Bounded mbarrier wait of this kernel: a protocol bug traps (never hangs the GPU) but does not print - the
+// printf of ptx::mbar_wait costs ~40 instructions at each of the kernel's waits, and a kernel that runs once per
+// step pays for every instruction it carries (measured: +1 800 instructions in this kernel = +6 us per dense step).
+// Set EGB_LAT_WAIT_PRINTF at build time to get the tagged message back.
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef EGB_LAT_WAIT_PRINTF
+  ptx::mbar_wait(bar, parity, tag);
+#else
+  (void)tag;
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!ptx::mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
+#endif
 }
 
 template <int kEpi>
@@ -200,7 +217,7 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        wait_bar(&empty_bar[s], ph ^ 1, 1);
         uint8_t* st = smem + s * stage_bytes;
         const int k0 = kb * BK;
         if (ptx::elect_one()) {
@@ -246,13 +263,13 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const uint32_t acc = local_tile & 1;
       const uint32_t use = local_tile >> 1;
       const int kb0 = (unit % p.ck) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-      ptx::mbar_wait(&tmem_empty[acc], (use & 1) ^ 1, 2);
+      wait_bar(&tmem_empty[acc], (use & 1) ^ 1, 2);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
-        ptx::mbar_wait(&full_bar[s], ph, 3);
+        wait_bar(&full_bar[s], ph, 3);
         ptx::tc_fence_after();
         if (it == 0 && lane == 0) EGB_TRACE(4);
         const uint64_t so = (uint64_t)((uint32_t)(s * stage_bytes) >> 4);
@@ -286,9 +303,11 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     float* const bias_s = reinterpret_cast<float*>(region + max(p.off_bias, 0));
     const bool has_bias = (p.flags & GEMM_BIAS) != 0;
     const bool load_c = (p.flags & GEMM_ACCUMULATE) != 0;
-    constexpr bool need_aux = kEpi == EPI_MASK_RELU || kEpi == EPI_MASK_LEAKY || kEpi == EPI_SGD;
+    // kEpi == EPI_DYNAMIC: the stage is read from the parameters (one kernel image for every launch of a step)
+    const int epi = kEpi == EPI_DYNAMIC ? p.epi : kEpi;
+    const bool need_aux = epi == EPI_MASK_RELU || epi == EPI_MASK_LEAKY || epi == EPI_SGD;
     const bool store_c = !(p.flags & GEMM_SKIP_C);
-    const bool store_d = kEpi != EPI_NONE && !(p.flags & GEMM_SKIP_D);
+    const bool store_d = epi != EPI_NONE && !(p.flags & GEMM_SKIP_D);
     const bool planes = (p.flags & GEMM_SPLIT_OUT) != 0;
     const uint32_t aux_bytes = (load_c ? F32_TILE : 0) + (need_aux ? F32_TILE : 0);
     // cluster split-K roles: the CTA that finishes this warp's accumulator rows
@@ -314,7 +333,7 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     // v[0..31]: the raw accumulator row of this thread (columns col0 .. col0+31 of row row0 + lane)
     auto finish_unit = [&](uint32_t (&r)[32], const int row0, const int col0, const bool live) {
       if (aux_bytes && live) {
-        ptx::mbar_wait(&aux_bar[ew], aux_phase, 5);
+        wait_bar(&aux_bar[ew], aux_phase, 5);
         aux_phase ^= 1;
       }
       __syncwarp();  // bias_s written by the other lanes
@@ -343,39 +362,39 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = 0.0f;   // rows past M: clipped by the stores, must not reach the column sums
           }
-          if (live && p.off_a >= 0 && (store_c || (kEpi == EPI_NONE && p.colsum))) *pa = make_float4(x[0], x[1], x[2], x[3]);
+          if (live && p.off_a >= 0 && (store_c || (epi == EPI_NONE && p.colsum))) *pa = make_float4(x[0], x[1], x[2], x[3]);
           float a2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          if constexpr (need_aux) {
+          if (need_aux) {
             const float4 t = *pb;
             a2[0] = t.x; a2[1] = t.y; a2[2] = t.z; a2[3] = t.w;
           }
-          if constexpr (kEpi == EPI_RELU) {
+          if (epi == EPI_RELU) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = (0.0f <= x[e]) ? x[e] : 0.0f;
-          } else if constexpr (kEpi == EPI_LEAKY) {
+          } else if (epi == EPI_LEAKY) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fmul_rn((0.0f <= x[e]) ? 1.0f : p.epi_param, x[e]);
-          } else if constexpr (kEpi == EPI_MASK_RELU) {
+          } else if (epi == EPI_MASK_RELU) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = (0.0f <= a2[e]) ? x[e] : 0.0f;
-          } else if constexpr (kEpi == EPI_MASK_LEAKY) {
+          } else if (epi == EPI_MASK_LEAKY) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fmul_rn(x[e], (0.0f <= a2[e]) ? 1.0f : p.epi_param);
-          } else if constexpr (kEpi == EPI_SIGMOID) {
+          } else if (kEpi != EPI_DYNAMIC && epi == EPI_SIGMOID) {   // (the transcendental stages keep their own images: ~1 000 instructions each)
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fsub_rn(0.0f, x[e]))));
-          } else if constexpr (kEpi == EPI_TANH) {
+          } else if (kEpi != EPI_DYNAMIC && epi == EPI_TANH) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float ep = expf(x[e]), en = expf(__fsub_rn(0.0f, x[e]));
               x[e] = __fdiv_rn(__fsub_rn(ep, en), __fadd_rn(ep, en));
             }
-          } else if constexpr (kEpi == EPI_SGD) {
+          } else if (epi == EPI_SGD) {
             // P += (0 - g) * rate   (base.nim:37-38; negate is `0 - x`, llvm.nim:333-336)
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = __fadd_rn(a2[e], __fmul_rn(0.0f - x[e], p.epi_param));
           }
-          if constexpr (kEpi != EPI_NONE) {
+          if (epi != EPI_NONE) {
             if (!row_ok) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) x[e] = 0.0f;
@@ -412,7 +431,7 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       if (live && threadIdx.x == 128) EGB_TRACE(21);
       if (p.colsum) {
         // column `lane` of the final tile, rows top to bottom (a row's 32 words sit in 32 different banks)
-        const uint8_t* fin = kEpi != EPI_NONE ? buf_b : buf_a;
+        const uint8_t* fin = epi != EPI_NONE ? buf_b : buf_a;
         float s = 0.0f;
 #pragma unroll 8
         for (int rr = 0; rr < UNIT; ++rr) s += *reinterpret_cast<const float*>(fin + sw128(rr, lane >> 2) + (lane & 3) * 4);
@@ -452,7 +471,7 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const int m0 = (tile % p.tiles_m) * BM;
       const int n0 = (tile / p.tiles_m) * p.BN;
       if (live) {
-        ptx::mbar_wait(&tmem_full[acc], use & 1, 4);
+        wait_bar(&tmem_full[acc], use & 1, 4);
         ptx::tc_fence_after();
         if (unit + (int)gridDim.x >= num_units) pdl_launch_dependents();
         if (local_tile == 0 && threadIdx.x == 128) EGB_TRACE(5);
@@ -488,7 +507,7 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         if (p.ck > 1) {
           // ---- add the pushed partial units in k order (this CTA's own partial takes its place in that order)
           if (live) {
-            ptx::mbar_wait(&recv_bar[ew], 0, 6);
+            wait_bar(&recv_bar[ew], 0, 6);
             // every partial unit for these rows has arrived: the peers that sent them may exit (see the end of the kernel)
             __syncwarp();
             ptx::cluster_arrive_relaxed();
@@ -732,6 +751,12 @@ bool launch_gemm_lat(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                            CUtensorMap, LParams);
   KernelFn fn = nullptr;
+  // One kernel image per second stage. (EGB_GEMM_LAT_ONE_IMAGE: one image for every launch, stage read from the
+  // parameters - measured 62.0 vs 59.0 us per dense step: the run-time stage tests sit on the epilogue's critical
+  // path, and the instruction caches do not carry an image from one launch to the next anyway.)
+  static const bool one_image = getenv("EGB_GEMM_LAT_ONE_IMAGE") != nullptr;
+  if (one_image && a.epi != EPI_SIGMOID && a.epi != EPI_TANH) fn = gemm_lat_kernel<EPI_DYNAMIC>;
+  else
   switch (a.epi) {
     case EPI_NONE: fn = gemm_lat_kernel<EPI_NONE>; break;
     case EPI_RELU: fn = gemm_lat_kernel<EPI_RELU>; break;
