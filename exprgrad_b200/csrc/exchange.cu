@@ -149,59 +149,99 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
     }
   }
   if (stamp) stamps[1] = globaltimer();
-  // ---- 2: reduce chunk b of my slice (rank order), average, store it into my bucket and push it to every peer
+  // ---- 2: reduce chunk b of my slice (rank order), average, store it into my bucket and push it to every peer.
+  //         Four groups per thread and pass: all own loads are issued first, and while the thread waits for one
+  //         peer line the other three are arriving.
   {
     const float nf = (float)N;
-    for (long long gi = (long long)b * C + tid; gi < (long long)(b + 1) * C; gi += EX_THREADS) {
-      const long long g = (long long)me * S + gi;
-      if (gi >= S || g >= n4) break;
-      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      for (int r = 0; r < N; ++r) {
-        const float4 v = r == me ? ld_cg4(own + (g << 2)) : ld_ll(inbox(me, INBOX_OFF, r, gi), epoch, p.backoff_ns);
-        if (r == 0) acc = v;
-        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    const bool pow2 = (N & (N - 1)) == 0;
+    const float inv = 1.0f / nf;      // exact for a power of two: x * inv == x / N bit for bit
+    const long long c_lo = (long long)b * C, c_hi = min((long long)(b + 1) * C, S);
+    for (long long base = c_lo; base < c_hi; base += 4 * EX_THREADS) {
+      float4 acc[4], mine[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long gi = base + (long long)u * EX_THREADS + tid;
+        ok[u] = gi < c_hi && (long long)me * S + gi < n4;
+        if (ok[u]) mine[u] = ld_cg4(own + (((long long)me * S + gi) << 2));
       }
-      acc.x = __fdiv_rn(acc.x, nf); acc.y = __fdiv_rn(acc.y, nf);
-      acc.z = __fdiv_rn(acc.z, nf); acc.w = __fdiv_rn(acc.w, nf);
-      st_cg4(own + (g << 2), acc);
-      for (int r = 0; r < N; ++r)
-        if (r != me) st_ll(inbox(r, inbox2_off, me, gi), acc, epoch);
+      for (int r = 0; r < N; ++r) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const long long gi = base + (long long)u * EX_THREADS + tid;
+          const float4 v = r == me ? mine[u] : ld_ll(inbox(me, INBOX_OFF, r, gi), epoch, p.backoff_ns);
+          if (r == 0) acc[u] = v;
+          else { acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        const long long gi = base + (long long)u * EX_THREADS + tid;
+        float4 a = acc[u];
+        if (pow2) { a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv; }
+        else { a.x = __fdiv_rn(a.x, nf); a.y = __fdiv_rn(a.y, nf); a.z = __fdiv_rn(a.z, nf); a.w = __fdiv_rn(a.w, nf); }
+        st_cg4(own + (((long long)me * S + gi) << 2), a);
+        for (int r = 0; r < N; ++r)
+          if (r != me) st_ll(inbox(r, inbox2_off, me, gi), a, epoch);
+      }
     }
   }
   __syncthreads();   // (phase 3 re-reads this CTA's part of the bucket with another thread mapping at the slice ends)
   if (stamp) stamps[2] = globaltimer();
-  // ---- 3: the averaged chunk b of every slice: into the bucket, and gradientDescent straight from it
+  // ---- 3: the averaged chunk b of every slice: into the bucket, and gradientDescent straight from it (four groups
+  //         per thread and pass: gradient loads / line waits, then parameter loads, then stores)
   for (int r = 0; r < N; ++r) {
     const long long lo = (long long)r * S + (long long)b * C;
     const long long hi = min(min(lo + C, (long long)(r + 1) * S), n4);
-    for (long long g = lo + tid; g < hi; g += EX_THREADS) {
-      const long long i = g << 2;
-      float4 gv;
-      if (r == me) {
-        gv = ld_cg4(own + i);
-      } else {
-        gv = ld_ll(inbox(me, inbox2_off, r, g - (long long)r * S), epoch, p.backoff_ns);
-        st_cg4(own + i, gv);
+    for (long long base = lo; base < hi; base += 4 * EX_THREADS) {
+      float4 gv[4], pv[4];
+      float* dst[4];
+      long long left[4];
+      float rate[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long g = base + (long long)u * EX_THREADS + tid;
+        dst[u] = nullptr;
+        left[u] = -1;
+        if (g >= hi) continue;
+        const long long i = g << 2;
+        left[u] = 0;
+        if (r == me) gv[u] = ld_cg4(own + i);
+        for (int q = 0; q < p.nseg; ++q)
+          if (i >= p.seg[q].off && i < p.seg[q].off + p.seg[q].len) {
+            dst[u] = p.seg[q].param + (i - p.seg[q].off);
+            left[u] = p.seg[q].off + p.seg[q].len - i;
+            rate[u] = p.seg[q].rate;
+          }
+        if (dst[u] && left[u] >= 4) pv[u] = *reinterpret_cast<const float4*>(dst[u]);
       }
-      if (p.nseg == 0) continue;
-      int s = -1;
-      for (int q = 0; q < p.nseg; ++q)
-        if (i >= p.seg[q].off && i < p.seg[q].off + p.seg[q].len) s = q;
-      if (s < 0) continue;   // alignment padding between tensors
-      const ExchangeSeg sg = p.seg[s];
-      float* dst = sg.param + (i - sg.off);
-      const long long left = sg.off + sg.len - i;
-      if (left >= 4) {
-        float4 pv = *reinterpret_cast<const float4*>(dst);
-        // P += (0 - g) * rate   (base.nim:37-38; negate is 0 - x, llvm.nim:333-336; un-contracted)
-        pv.x = __fadd_rn(pv.x, __fmul_rn(0.0f - gv.x, sg.rate));
-        pv.y = __fadd_rn(pv.y, __fmul_rn(0.0f - gv.y, sg.rate));
-        pv.z = __fadd_rn(pv.z, __fmul_rn(0.0f - gv.z, sg.rate));
-        pv.w = __fadd_rn(pv.w, __fmul_rn(0.0f - gv.w, sg.rate));
-        *reinterpret_cast<float4*>(dst) = pv;
-      } else {
-        const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
-        for (int e = 0; e < (int)left; ++e) dst[e] = __fadd_rn(dst[e], __fmul_rn(0.0f - ge[e], sg.rate));
+      if (r != me) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long g = base + (long long)u * EX_THREADS + tid;
+          if (left[u] < 0) continue;
+          gv[u] = ld_ll(inbox(me, inbox2_off, r, g - (long long)r * S), epoch, p.backoff_ns);
+          st_cg4(own + (g << 2), gv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!dst[u]) continue;   // no fused update, or alignment padding between tensors
+        if (left[u] >= 4) {
+          // P += (0 - g) * rate   (base.nim:37-38; negate is 0 - x, llvm.nim:333-336; un-contracted)
+          float4 q = pv[u];
+          q.x = __fadd_rn(q.x, __fmul_rn(0.0f - gv[u].x, rate[u]));
+          q.y = __fadd_rn(q.y, __fmul_rn(0.0f - gv[u].y, rate[u]));
+          q.z = __fadd_rn(q.z, __fmul_rn(0.0f - gv[u].z, rate[u]));
+          q.w = __fadd_rn(q.w, __fmul_rn(0.0f - gv[u].w, rate[u]));
+          *reinterpret_cast<float4*>(dst[u]) = q;
+        } else {
+          const float ge[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+          for (int e = 0; e < (int)left[u]; ++e) dst[u][e] = __fadd_rn(dst[u][e], __fmul_rn(0.0f - ge[e], rate[u]));
+        }
       }
     }
   }
