@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv2_fwd_tc_kernel(const __grid_c
 // inside the tile), accumulated in a three-row ring across the vertically adjacent tiles of a CTA and added
 // to dimg with 16-byte REDs once per row - runs of different CTAs and the 2-pixel halo of neighbouring
 // column tiles still overlap, so the image must be zeroed (or hold the value to accumulate onto) beforehand.
-constexpr int DI_THREADS = 576;   // 8 converter warps, MMA, loader/TMEM allocator, 2 x 4 epilogue warps
+constexpr int DI_GATHER = 256;    // gather threads (8 warps; 4 measured 1.02 ms)
+constexpr int DI_THREADS = 448 + DI_GATHER;   // 8 converter warps, MMA, loader/TMEM allocator, 4 drain + 8 gather warps
 constexpr int DI_STAGES = 2;
 constexpr int DI_TLD = 33;        // row stride of the T tile in shared memory (floats)
 constexpr int RING_LD = 392;      // one input-row segment of a tile: (128 + 2) pixels x 3 channels, padded to 16 bytes
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], 4);   // the four drain warps
       ptx::mbar_init(&t_full[a], 128);     // every drain thread
-      ptx::mbar_init(&t_free[a], 128);     // every gather thread
+      ptx::mbar_init(&t_free[a], DI_GATHER);     // every gather thread
     }
     ptx::fence_barrier_init();
   }
@@ -510,9 +511,9 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
       }
     } else {
       // ---------------------------------------------------- gather warps (14..17)
-      const int gt = threadIdx.x - 448;   // 0..127
-      for (int i = gt; i < 3 * RING_LD; i += 128) sRing[i] = 0.0f;
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const int gt = threadIdx.x - 448;   // 0..DI_GATHER-1
+      for (int i = gt; i < 3 * RING_LD; i += DI_GATHER) sRing[i] = 0.0f;
+      asm volatile("bar.sync 2, %0;" ::"n"(DI_GATHER) : "memory");
       uint32_t it = 0;
       for (int tile = t0; tile < t1; ++tile, ++it) {
         const uint32_t buf = it & 1;
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
         const float* sT = sT0 + buf * TILE_P * DI_TLD;
         ptx::mbar_wait_sleepy(&t_full[buf], (it >> 1) & 1, 28);
         constexpr int XS = TILE_P + KW - 1;   // input pixels of a row segment
-        for (int idx = gt; idx < KH * XS; idx += 128) {   // one (dy, input pixel) per thread: 9 taps -> 3 channels
+        for (int idx = gt; idx < KH * XS; idx += DI_GATHER) {   // one (dy, input pixel) per thread: 9 taps -> 3 channels
           const int dy = idx / XS, X = idx - dy * XS;
           float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
@@ -539,12 +540,12 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
           ring[0] += s0; ring[1] += s1; ring[2] += s2;
         }
         ptx::mbar_arrive(&t_free[buf]);                  // this thread no longer reads the T tile
-        asm volatile("bar.sync 2, 128;" ::: "memory");   // the ring holds this tile
+        asm volatile("bar.sync 2, %0;" ::"n"(DI_GATHER) : "memory");   // the ring holds this tile
         // input row y is complete as far as this run goes; at the end of a column / of the run also y+1, y+2
         const int nflush = (y == p.OH - 1 || tile == t1 - 1) ? 3 : 1;
         const int seg_len = min(SEG, (p.W - x0) * C);   // the segment ends with the image row
         constexpr int Q = (SEG + 3) / 4;
-        for (int idx = gt; idx < nflush * Q; idx += 128) {
+        for (int idx = gt; idx < nflush * Q; idx += DI_GATHER) {
           const int fr = idx / Q, j = (idx - fr * Q) * 4;
           float* ring = sRing + ((y + fr) % 3) * RING_LD + j;
           const float4 val = *reinterpret_cast<const float4*>(ring);
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
             for (int k2 = 0; k2 < 4 && j + k2 < seg_len; ++k2) atomicAdd(dst + k2, e[k2]);
           }
         }
-        asm volatile("bar.sync 2, 128;" ::: "memory");   // ring slots are reused by the next tile
+        asm volatile("bar.sync 2, %0;" ::"n"(DI_GATHER) : "memory");   // ring slots are reused by the next tile
       }
     }
   }
