@@ -210,7 +210,13 @@ int egb_model_create(egb_context* ctx, egb_program* program, uint64_t seed, egb_
 int egb_model_free(egb_model* model);
 /* Options: "strict" 1 = bit-exact mode (every kernel runs on the generic loop-nest kernel with the
  * reference's sequential accumulation order; no tensor cores), "graphs" 0 = launch eagerly instead
- * of replaying a CUDA graph, "epoch" = set model.epoch (exprgrad/model.nim:39). */
+ * of replaying a CUDA graph, "epoch" = set model.epoch (exprgrad/model.nim:39).
+ * Planner switches (default 1; an execution detail each - results stay within the parity bar): "fuse" epilogue
+ * fusion behind contractions, "head" the classification head (logits contraction + softmax/crossEntropy rows +
+ * first adjoint contraction) as one launch, "rowchain" runs of small row-local kernels in one launch, "eltwise"
+ * specialised streaming elementwise / optimizer kernels, "concurrent" independent plan nodes on parallel graph
+ * branches, "splitk" cluster split-K, "keep_intermediates" (default 0) store every fp32 intermediate,
+ * "dp_peer" data parallel: fused peer-memory exchange (1) or in-graph ncclAllReduce + optimizer kernels (0). */
 int egb_model_set_option(egb_model* model, const char* key, int64_t value);
 int egb_model_epoch(egb_model* model, int64_t* epoch);
 /* model.params / model.caches are public in the reference (exprgrad/model.nim:37-38): blocking copies
