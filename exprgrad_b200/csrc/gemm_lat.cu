@@ -643,7 +643,8 @@ void gemm_lat_plan(int M, int N, int K, bool b_mn, int sms, int max_ck, int* bn_
       if (ck > 1 && (ck - 1) * kbps >= num_kb) break;
       const double waves = (double)((tiles * ck + sms - 1) / sms);
       double cost = 2.0 + waves * (kbps * t_kb + 1.0 + 0.4 * (units_per_warp - 1));
-      if (ck > 1) cost += 0.8;
+      static const double split_penalty = getenv("EGB_LAT_SPLIT_PENALTY") ? atof(getenv("EGB_LAT_SPLIT_PENALTY")) : 0.8;
+      if (ck > 1) cost += split_penalty;
       // a full machine finishes later than a half empty one (L2 and launch skew)
       cost += 0.5 * (double)(tiles * ck < sms ? tiles * ck : sms) / sms;
       if (cost < best - 1e-9) {
