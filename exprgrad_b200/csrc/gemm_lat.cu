@@ -680,10 +680,6 @@ bool launch_gemm_lat(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   if (a.epi != EPI_NONE && a.D == a.C) p.flags |= GEMM_SKIP_C;
   p.a_mn = a.a_mn ? 1 : 0;
   p.b_mn = a.b_mn ? 1 : 0;
-  // (measured on the dense step: the dry pass removes 0.4-1.0 us of cold-code stalls from some epilogues but competes
-  // with short main loops for issue slots - 70.4 vs 67.6 us per step; off unless asked for)
-  static const bool dry = getenv("EGB_GEMM_LAT_DRY") != nullptr;
-  p.dry_run = dry ? 1 : 0;
   p.trace = ctx.trace;
   p.trace_index = ctx.trace ? 1 + (int)(ctx.trace_next++ % (TRACE_SLOTS - 1)) : 0;
   const int sms = (a.sm_budget > 0 && a.sm_budget < ctx.sm_count) ? a.sm_budget : ctx.sm_count;
@@ -705,6 +701,12 @@ bool launch_gemm_lat(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   if (ck != 1 && ck != 2 && ck != 4) fail(EGB_ERR_GPU, "gemm: invalid cluster split-K factor %d", ck);
   p.kb_per_split = (num_kb + ck - 1) / ck;
   p.ck = ck;
+  // Dry pass of the epilogue code (see the kernel): it removes 0.4-1.3 us of cold-code stalls from the epilogue but
+  // its shared-memory and TMEM reads compete with the main loop, which is bound by exactly those (a 2 us main loop
+  // became 3 us: 70.4 vs 67.6 us per step when every launch did it). It pays where the main loop is long and the
+  // epilogue is not preceded by a split-K exchange: unsplit launches with >= 6 k-blocks. EGB_GEMM_LAT_DRY=0/1 forces it.
+  static const char* dry_env = getenv("EGB_GEMM_LAT_DRY");
+  p.dry_run = dry_env ? (atoi(dry_env) != 0) : (ck == 1 && num_kb >= 6);
 
   // per-warp epilogue region
   const bool need_aux = a.epi == EPI_MASK_RELU || a.epi == EPI_MASK_LEAKY || a.epi == EPI_SGD;

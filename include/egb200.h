@@ -270,9 +270,13 @@ int egb_comm_info(egb_comm* comm, int* rank, int* world, int* nccl_version);
 /* In-place average of n floats across all ranks on the context's stream (asynchronous). */
 int egb_comm_allreduce_avg_f32(egb_comm* comm, float* device_buf, size_t n);
 /* Make every target that has a backward pass data parallel: the gradients of all parameters are laid
- * out as one contiguous bucket and averaged across ranks (one ncclAllReduce over NVLink) between the
- * last adjoint kernel and the first optimizer kernel, inside the same CUDA graph. comm = NULL turns
- * it off again. With equal-size batch shards this reproduces the reference's global-batch step. */
+ * out as one contiguous bucket and averaged across ranks between the last adjoint kernel and the first
+ * optimizer kernel (where exprgrad/parser.nim:757-766 places the optimizer effects), inside the same CUDA
+ * graph: by the library's own exchange kernel over NVLink / NVSwitch peer memory, fused with the
+ * gradientDescent updates (up to 8 ranks of one node; cudaIpc mappings are exchanged when a plan is built,
+ * which is a collective call - every rank builds the same target with the same per-rank shapes), or with
+ * option "dp_peer" 0 by one ncclAllReduce per bucket segment + the optimizer kernels. comm = NULL turns it
+ * off again. With equal-size batch shards this reproduces the reference's global-batch step. */
 int egb_model_set_data_parallel(egb_model* model, egb_comm* comm);
 
 #ifdef __cplusplus
