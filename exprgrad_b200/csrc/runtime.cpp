@@ -706,7 +706,7 @@ void build_nodes_impl(Model& m, Plan& plan) {
         xp.rank = plan.window.rank;
         xp.world = plan.window.world;
         xp.n = (long long)(r_bytes / 4);
-        static const int early_ctas = getenv("EGB_DP_EARLY_CTAS") ? atoi(getenv("EGB_DP_EARLY_CTAS")) : 64;
+        static const int early_ctas = getenv("EGB_DP_EARLY_CTAS") ? atoi(getenv("EGB_DP_EARLY_CTAS")) : 128;
         xp.ctas = two && part == 0 ? early_ctas : 0;
         for (int r = 0; r < xp.world; ++r) {
           xp.bucket[r] = (float*)(plan.window.arena[r] + r_off);
