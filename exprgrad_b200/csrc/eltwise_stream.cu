@@ -144,6 +144,60 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArg
   }
 }
 
+// adam (exprgrad/layers/base.nim:40-53) as ONE pass: the reference's three kernels
+//   m += m * (b1 - 1) + (1 - b1) * g;   v += v * (b2 - 1) + (1 - b2) * g * g;
+//   p += (-eta * (m / c1)) / (sqrt(v / c2) + eps),   c = 1 - pow(b, epoch)
+// read g twice and m, v twice and write every line they touch: 40 bytes per element. Fused they move 28 (g, m, v, p in;
+// m, v, p out); the arithmetic is the three kernels' own, operation by operation, on the values the third one would
+// have re-read (so results are bit-identical to the separate launches).
+struct AdamArgs {
+  float* p; float* m; float* v; const float* g;
+  float a0, a1, b0, b1, s0, s1, s2, s3;
+  long long n;
+};
+__global__ void __launch_bounds__(ELT_THREADS, 3) adam_fused_kernel(const AdamArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n4 = a.n >> 2;
+  const long long stride = (long long)gridDim.x * ELT_THREADS;
+  const long long first = (long long)blockIdx.x * ELT_THREADS + threadIdx.x;
+  auto one = [&](float g, float& m, float& v, float& p) {
+    m = m + ((m * a.a0) + (a.a1 * g));
+    v = v + ((v * a.b0) + (a.b1 * (g * g)));
+    p = p + __fdiv_rn(a.s0 * __fdiv_rn(m, a.s1), __fsqrt_rn(__fdiv_rn(v, a.s2)) + a.s3);
+  };
+  for (long long base = first; base < n4; base += stride * 2) {
+    float4 g[2], m[2], v[2], p[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = base + (long long)u * stride;
+      if (i < n4) {
+        g[u] = *reinterpret_cast<const float4*>(a.g + (i << 2));
+        m[u] = *reinterpret_cast<const float4*>(a.m + (i << 2));
+        v[u] = *reinterpret_cast<const float4*>(a.v + (i << 2));
+        p[u] = *reinterpret_cast<const float4*>(a.p + (i << 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = base + (long long)u * stride;
+      if (i < n4) {
+        one(g[u].x, m[u].x, v[u].x, p[u].x); one(g[u].y, m[u].y, v[u].y, p[u].y);
+        one(g[u].z, m[u].z, v[u].z, p[u].z); one(g[u].w, m[u].w, v[u].w, p[u].w);
+        *reinterpret_cast<float4*>(a.m + (i << 2)) = m[u];
+        *reinterpret_cast<float4*>(a.v + (i << 2)) = v[u];
+        *reinterpret_cast<float4*>(a.p + (i << 2)) = p[u];
+      }
+    }
+  }
+  const long long t = (n4 << 2) + first;
+  if (t < a.n) {
+    float m = a.m[t], v = a.v[t], p = a.p[t];
+    one(a.g[t], m, v, p);
+    a.m[t] = m; a.v[t] = v; a.p[t] = p;
+  }
+}
+
 template <int KIND>
 void launch_kind(Context& ctx, const EltArgs& a, cudaStream_t st) {
   const long long n4 = a.n >> 2;
@@ -158,6 +212,10 @@ void launch_kind(Context& ctx, const EltArgs& a, cudaStream_t st) {
 }  // namespace
 
 bool eltwise_stream_supported(const EltLaunch& e) {
+  if (e.kind == ELT_ADAM_FUSED) {
+    auto al = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return e.n > 0 && al(e.out) && al(e.in[0]) && al(e.adam_m) && al(e.adam_v);
+  }
   if (e.kind <= ELT_NONE || e.kind >= ELT_KIND_COUNT || e.n <= 0) return false;
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!e.out || !aligned(e.out) || !e.in[0] || !aligned(e.in[0])) return false;
@@ -169,6 +227,24 @@ bool eltwise_stream_supported(const EltLaunch& e) {
 
 void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st) {
   if (!eltwise_stream_supported(e)) fail(EGB_ERR_GPU, "eltwise: unsupported launch (kind %d)", e.kind);
+  if (e.kind == ELT_ADAM_FUSED) {
+    AdamArgs q;
+    q.p = e.out; q.m = e.adam_m; q.v = e.adam_v; q.g = e.in[0];
+    q.a0 = e.p[0]; q.a1 = e.p[1]; q.b0 = e.p2[0]; q.b1 = e.p2[1];
+    q.s0 = e.p3[0]; q.s1 = e.p3[1]; q.s2 = e.p3[2]; q.s3 = e.p3[3];
+    q.n = e.n;
+    const long long n4 = e.n >> 2;
+    long long blocks = (n4 + (long long)ELT_THREADS * 2 - 1) / ((long long)ELT_THREADS * 2);
+    const long long cap = (long long)ctx.sm_count * 3;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    {
+      Launch l(ctx, KC_ELTWISE, st);
+      launch_kernel(ctx, adam_fused_kernel, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, q);
+    }
+    EGB_CUDA(cudaGetLastError());
+    return;
+  }
   EltArgs a;
   a.out = e.out;
   a.in0 = e.in[0];

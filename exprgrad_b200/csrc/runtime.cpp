@@ -197,6 +197,76 @@ bool is_column_sum(const Kernel& k) {
   return match_form(k, form, m);
 }
 
+// adam as one pass over the parameter (eltwise_stream.cu): three ELTWISE nodes - first moment, second moment, step -
+// that the reference emits per parameter (layers/base.nim:40-53) and that read each other's outputs. Matched on the
+// lowered nodes: same length, the same gradient in both moment updates, the step reading exactly those two caches,
+// nothing in between that touches any of the four tensors.
+bool fuse_adam(Plan& plan) {
+  auto hits = [](const std::vector<int64_t>& a, const std::vector<int64_t>& b) {
+    for (auto x : a)
+      for (auto y : b)
+        if (x == y) return true;
+    return false;
+  };
+  bool any = false;
+  for (int i = 0; i < (int)plan.nodes.size(); ++i) {
+    const Node& a = plan.nodes[i];
+    if (a.kind != Node::ELTWISE || a.elt.kind != ELT_ADAM_M || !a.elt.accumulate || a.elt.in[0] != a.elt.out) continue;
+    int jb = -1, jc = -1;
+    for (int j = i + 1; j < (int)plan.nodes.size() && j <= i + 8; ++j) {
+      const Node& n = plan.nodes[j];
+      if (n.kind != Node::ELTWISE) continue;
+      if (jb < 0 && n.elt.kind == ELT_ADAM_V && n.elt.accumulate && n.elt.in[0] == n.elt.out && n.elt.in[1] == a.elt.in[1] &&
+          n.elt.n == a.elt.n)
+        jb = j;
+      else if (jb >= 0 && jc < 0 && n.elt.kind == ELT_ADAM_STEP && n.elt.accumulate && n.elt.in[0] == a.elt.out &&
+               n.elt.in[1] == plan.nodes[jb].elt.out && n.elt.n == a.elt.n)
+        jc = j;
+    }
+    if (jb < 0 || jc < 0) continue;
+    bool clean = true;
+    for (int j = i + 1; j < jc && clean; ++j) {
+      if (j == jb) continue;
+      const Node& n = plan.nodes[j];
+      for (int q : {i, jb, jc})
+        clean = clean && !hits(n.writes, plan.nodes[q].reads) && !hits(n.writes, plan.nodes[q].writes) && !hits(n.reads, plan.nodes[q].writes);
+    }
+    if (!clean) continue;
+    const Node &b = plan.nodes[jb], &c = plan.nodes[jc];
+    Node f;
+    f.kind = Node::ELTWISE;
+    f.elt.kind = ELT_ADAM_FUSED;
+    f.elt.out = c.elt.out;
+    f.elt.in[0] = a.elt.in[1];
+    f.elt.nreads = 1;
+    f.elt.adam_m = a.elt.out;
+    f.elt.adam_v = b.elt.out;
+    f.elt.n = a.elt.n;
+    f.elt.accumulate = true;
+    f.elt.p[0] = a.elt.p[0]; f.elt.p[1] = a.elt.p[1];
+    f.elt.p2[0] = b.elt.p[0]; f.elt.p2[1] = b.elt.p[1];
+    for (int q = 0; q < 4; ++q) f.elt.p3[q] = c.elt.p[q];
+    if (!eltwise_stream_supported(f.elt)) continue;
+    f.uses_epoch = true;
+    f.kernel_index = c.kernel_index;
+    f.label = "eltwise adam (kernels " + std::to_string(a.kernel_index) + " " + std::to_string(b.kernel_index) + " " +
+              std::to_string(c.kernel_index) + " in one pass) n=" + std::to_string((long long)a.elt.n);
+    for (int q : {i, jb, jc}) {
+      for (auto r : plan.nodes[q].reads) f.reads.push_back(r);
+      for (auto w : plan.nodes[q].writes) f.writes.push_back(w);
+    }
+    std::vector<Node> kept;
+    for (int j = 0; j < (int)plan.nodes.size(); ++j) {
+      if (j == i || j == jb) continue;
+      kept.push_back(j == jc ? f : plan.nodes[j]);
+    }
+    plan.nodes = kept;
+    any = true;
+    i = -1;
+  }
+  return any;
+}
+
 // The classification head in one launch (head_rows.cu): a SOFTMAX_XENT node absorbs the contraction that produces its
 // logits (<= 16 classes) and the contraction that consumes its gradient planes with the class dimension as k. Matched
 // on the lowered nodes (operand pointers, shapes, fused stages) with hazard checks against every node in between;
@@ -902,6 +972,7 @@ void build_nodes_impl(Model& m, Plan& plan) {
         it = it->first.first == wtensor ? planes.erase(it) : std::next(it);
     }
   }
+  if (m.fuse && m.eltwise && !m.strict) fuse_adam(plan);
   compute_levels(plan);
   // level order is a topological order: sorting by it makes every run of consecutive levels contiguous
   // (needed by the row-chain fusion) and keeps sequential (eager) execution valid

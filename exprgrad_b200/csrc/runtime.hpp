@@ -28,7 +28,12 @@ struct EltLaunch {
   float p[4] = {0, 0, 0, 0};
   int64_t n = 0, row = 0;
   bool accumulate = false;
+  // fused adam (kind ELT_ADAM_FUSED): out = parameter, in[0] = gradient; first / second moment caches and the
+  // literals of the three reference kernels (m: p[0..1], v: p2[0..1], step: p3[0..3])
+  float *adam_m = nullptr, *adam_v = nullptr;
+  float p2[2] = {0, 0}, p3[4] = {0, 0, 0, 0};
 };
+constexpr int ELT_ADAM_FUSED = 1000;   // node-level fusion of adam-m + adam-v + adam-step (not a single-kernel pattern)
 bool eltwise_stream_supported(const EltLaunch& e);
 void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st);
 

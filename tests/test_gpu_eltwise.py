@@ -74,6 +74,8 @@ def test_optimizer_updates(ctx, opt, n):
         om.epoch += 1; om.apply("step", {"g": g})
         pm.set_option("epoch", step + 1); pm.apply("step", {"g": g})
     assert " eltwise eltwise " in pm.describe_plan() and " interp " not in pm.describe_plan(), pm.describe_plan()
+    if opt == "adam":   # first moment, second moment and step of a parameter run as one pass over it
+        assert "in one pass" in pm.describe_plan() and pm.describe_plan().count(" eltwise eltwise ") == 1, pm.describe_plan()
     assert_close(pm.params[tid], om.params[tid], tol=2e-6, what=f"{opt} parameter after 3 steps")
     assert_close(pm.params[tid] - p0, om.params[tid] - p0, tol=1e-4, what=f"{opt} update")
     for cid in sorted(om.caches):
