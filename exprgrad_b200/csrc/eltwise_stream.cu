@@ -77,7 +77,8 @@ EGB_ELT_FN(ELT_ADAM_V, 2, return (x * a.p0) + (a.p1 * (y * y));)
 EGB_ELT_FN(ELT_ADAM_STEP, 2, return __fdiv_rn(a.p0 * __fdiv_rn(x, a.p1), __fsqrt_rn(__fdiv_rn(y, a.p2)) + a.p3);)
 
 // (the policy bits are uniform across the grid: the branches cost one predicate each)
-__device__ __forceinline__ float4 ld4(const float* p, bool cs) {
+__device__ __forceinline__ float4 ld4(const float* p, bool cs, bool lu = false) {
+  if (lu) return __ldlu(reinterpret_cast<const float4*>(p));   // last use: the line need not stay (the store rewrites it whole)
   if (cs) return __ldcs(reinterpret_cast<const float4*>(p));
   return *reinterpret_cast<const float4*>(p);
 }
@@ -92,10 +93,11 @@ __device__ __forceinline__ long long row_offset(long long i, const EltArgs& a) {
   return i % a.row;
 }
 
-template <int KIND>
+template <int KIND, int UNROLL>
 __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArgs a) {
   using Fn = EltFn<KIND>;
   const bool cs_in = (a.streaming & 1) != 0, cs_out_ld = (a.streaming & 2) != 0, cs_st = (a.streaming & 4) != 0;
+  const bool lu_out = (a.streaming & 8) != 0;
   pdl_launch_dependents();
   pdl_wait();
   const long long n4 = a.n >> 2;
@@ -103,23 +105,23 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArg
   const long long first = (long long)blockIdx.x * ELT_THREADS + threadIdx.x;
   // in-place forms (adam: m += f(m, g)) read the destination as an operand already
   const bool alias0 = KIND != ELT_BIAS_ROW && a.in0 == a.out;
-  for (long long base = first; base < n4; base += stride * ELT_UNROLL) {
-    float4 x[ELT_UNROLL], y[ELT_UNROLL], o[ELT_UNROLL];
+  for (long long base = first; base < n4; base += stride * UNROLL) {
+    float4 x[UNROLL], y[UNROLL], o[UNROLL];
     // phase 1: every load of this iteration
 #pragma unroll
-    for (int u = 0; u < ELT_UNROLL; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       const long long g = base + (long long)u * stride;
       x[u] = y[u] = o[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g < n4) {
         if constexpr (KIND == ELT_BIAS_ROW) x[u] = *reinterpret_cast<const float4*>(a.in0 + row_offset(g << 2, a));
-        else x[u] = ld4(a.in0 + (g << 2), alias0 ? cs_out_ld : cs_in);
+        else x[u] = ld4(a.in0 + (g << 2), alias0 ? cs_out_ld : cs_in, alias0 && lu_out);
         if constexpr (Fn::kInputs >= 2) y[u] = ld4(a.in1 + (g << 2), cs_in);
-        if (a.accumulate) o[u] = alias0 ? x[u] : ld4(a.out + (g << 2), cs_out_ld);
+        if (a.accumulate) o[u] = alias0 ? x[u] : ld4(a.out + (g << 2), cs_out_ld, lu_out);
       }
     }
     // phase 2: arithmetic + stores
 #pragma unroll
-    for (int u = 0; u < ELT_UNROLL; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       const long long g = base + (long long)u * stride;
       if (g < n4) {
         float4 r;
@@ -201,12 +203,17 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) adam_fused_kernel(const AdamAr
 template <int KIND>
 void launch_kind(Context& ctx, const EltArgs& a, cudaStream_t st) {
   const long long n4 = a.n >> 2;
-  long long blocks = (n4 + (long long)ELT_THREADS * ELT_UNROLL - 1) / ((long long)ELT_THREADS * ELT_UNROLL);
+  // Four 16-byte groups per thread in flight (EGB_ELT_UNROLL=2 for measurements: relu-adjoint reaches 0.99 of the copy
+  // roofline with two, relu, bias add and the in-place forms lose 5-13 points).
+  static const int forced = getenv("EGB_ELT_UNROLL") ? atoi(getenv("EGB_ELT_UNROLL")) : 0;
+  const int unroll = forced == 2 ? 2 : ELT_UNROLL;
+  long long blocks = (n4 + (long long)ELT_THREADS * unroll - 1) / ((long long)ELT_THREADS * unroll);
   const long long cap = (long long)ctx.sm_count * 3;   // three resident CTAs per SM (launch bounds: 85 registers), one wave
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   Launch l(ctx, KC_ELTWISE, st);
-  launch_kernel(ctx, elt_stream_kernel<KIND>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
+  if (unroll == 2) launch_kernel(ctx, elt_stream_kernel<KIND, 2>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
+  else launch_kernel(ctx, elt_stream_kernel<KIND, ELT_UNROLL>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
 }
 
 }  // namespace
