@@ -77,6 +77,7 @@ _SIGS = {
     "egb_kernel_run": (I, [P, I, PI64, PI64]),
     "egb_gemm_f32": (I, [P, I, I, I64, I64, I64, P, I64, P, I64, P, I64, I, P, F]),
     "egb_gemm_plan": (I, [I64, I64, I64, I, I, PI, PI]),
+    "egb_gemm_lat_plan": (I, [I64, I64, I64, I, I, PI, PI, PI]),
     "egb_gemm_planes": (I, [P, I64, I64, I64, P, P, I64, P, P, I64, P, I64, I, P, F, I]),
     "egb_split_bf16": (I, [P, P, I64, I64, I64, I, P, P, I64, I]),
     "egb_program_parse": (I, [S, SZ, PP]),

@@ -377,6 +377,16 @@ int egb_gemm_plan(int64_t M, int64_t N, int64_t K, int b_mn_major, int sms, int*
   EGB_CATCH
 }
 
+int egb_gemm_lat_plan(int64_t M, int64_t N, int64_t K, int b_mn_major, int sms, int* bn, int* cluster_k, int* ctas) {
+  EGB_TRY
+  if (M <= 0 || N <= 0 || K <= 0 || sms <= 0) fail(EGB_ERR_GPU, "gemm plan: sizes must be positive");
+  gemm_lat_plan((int)M, (int)N, (int)K, b_mn_major != 0, sms, 4, bn, cluster_k);
+  if (*cluster_k > 1 && *bn > 64) *bn = 64;
+  *ctas = (int)(((M + 127) / 128) * ((N + *bn - 1) / *bn)) * (*cluster_k > 1 ? *cluster_k : 1);
+  if (*cluster_k == 1 && *ctas > sms) *ctas = sms;
+  EGB_CATCH
+}
+
 int egb_gemm_planes(egb_context* ctx, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_mid,
                     int64_t lda, const void* b_hi, const void* b_mid, int64_t ldb, float* C, int64_t ldc,
                     int flags, const float* bias, float alpha, int bn) {

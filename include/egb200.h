@@ -155,6 +155,9 @@ int egb_gemm_f32(egb_context* ctx, int trans_a, int trans_b, int64_t M, int64_t 
  * plan for `sms` SMs. Pure host arithmetic (no device needed): exposed so that the planner's cost model can be
  * checked without a GPU. */
 int egb_gemm_plan(int64_t M, int64_t N, int64_t K, int b_mn_major, int sms, int* bn, int* cluster_k);
+/* The same for the latency kernel that serves small contractions (csrc/gemm_lat.cu: split factors 1, 2, 4; a split
+ * tile is at most 64 columns wide), plus the number of CTAs the launch will occupy. Host arithmetic only. */
+int egb_gemm_lat_plan(int64_t M, int64_t N, int64_t K, int b_mn_major, int sms, int* bn, int* cluster_k, int* ctas);
 /* Same contraction on operands already split into bf16 (hi, mid) planes. By default both are K-major
  * (A stored [M, lda], B stored [N, ldb], K contiguous); flags bit 16: A is MN-major (stored [K, lda], M
  * contiguous), bit 32: B is MN-major (stored [K, ldb], N contiguous). bn = 0 lets the library choose the

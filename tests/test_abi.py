@@ -70,3 +70,34 @@ def test_contraction_planner_invariants():
     assert ck.value >= 4
     check(lib.egb_gemm_plan(1024, 512, 10, 0, 148, ctypes.byref(bn), ctypes.byref(ck)))
     assert ck.value == 1
+
+
+def test_latency_kernel_planner_invariants():
+    """egb_gemm_lat_plan (csrc/gemm_lat.cu): tile width, cluster split-K factor and CTA count of the latency kernel
+    must describe a launchable configuration; the dense-net shapes get the configurations the device timeline was
+    measured with."""
+    import ctypes
+    from exprgrad_b200._ffi import check, lib
+    shapes = [(1024, 512, 784), (1024, 512, 512), (784, 512, 1024), (512, 512, 1024), (128, 4096, 4096), (1, 4, 1), (130, 72, 9),
+              (300, 200, 129), (37, 48, 64)]
+    for (m, n, k) in shapes:
+        for b_mn in (0, 1):
+            for sms in (148, 72, 32, 16):
+                bn, ck, ctas = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+                check(lib.egb_gemm_lat_plan(m, n, k, b_mn, sms, ctypes.byref(bn), ctypes.byref(ck), ctypes.byref(ctas)))
+                bn, ck, ctas = bn.value, ck.value, ctas.value
+                assert 32 <= bn <= 256 and bn % (64 if b_mn else 32) == 0, (m, n, k, b_mn, sms, bn)
+                assert ck in (1, 2, 4)
+                kb = (k + 63) // 64
+                if ck > 1:
+                    assert bn <= 64, "a split tile is pushed through distributed shared memory: at most 64 columns"
+                    assert ctas <= sms, "clusters of a split contraction must be co-resident in one wave"
+                    assert (ck - 1) * ((kb + ck - 1) // ck) < kb, "every CTA of a cluster needs k-blocks"
+                assert 1 <= ctas <= max(sms, ((m + 127) // 128) * ((n + bn - 1) // bn) * ck)
+    def plan(m, n, k, sms=148):
+        bn, ck, ctas = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        check(lib.egb_gemm_lat_plan(m, n, k, 0, sms, ctypes.byref(bn), ctypes.byref(ck), ctypes.byref(ctas)))
+        return bn.value, ck.value, ctas.value
+    assert plan(1024, 512, 784) == (64, 2, 128)      # layer 1 forward
+    assert plan(784, 512, 1024) == (64, 2, 112)      # layer 1 weight gradient
+    assert plan(512, 512, 1024, sms=32) == (64, 1, 32)   # a side contraction inside the SMs the chain leaves free
