@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) dp_exchange_sgd_kernel(const __
   if (stamp) stamps[2] = globaltimer();
   // ---- 3: the averaged chunk b of every slice: into the bucket, and gradientDescent straight from it (four groups
   //         per thread and pass: gradient loads / line waits, then parameter loads, then stores)
-  for (int r = 0; r < N; ++r) {
+  for (int t = 0; t < N; ++t) {
+    const int r = (me + t) % N;   // own slice first (nothing to wait for), the peers' averages are in flight meanwhile
     const long long lo = (long long)r * S + (long long)b * C;
     const long long hi = min(min(lo + C, (long long)(r + 1) * S), n4);
     for (long long base = lo; base < hi; base += 4 * EX_THREADS) {
