@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(DI_THREADS, 1) conv2_dimg_tc_kernel(const Dimg
 // (512 pixels) and summed there with rounded adds; the CTAs meet in dw through atomics at the very end.
 constexpr int DW_THREADS = 448;   // 8 producer warps, MMA, TMEM allocator, 4 epilogue warps
 constexpr int DW_STAGES = 2;
+constexpr int DW_RAW_STAGES = 3;   // raw dout tiles in flight (four - 128 KB per SM - measured the same 0.807 ms: not bound by bytes in flight)
 constexpr int DW_FLUSH = 4;
 
 struct DwParams {
@@ -602,21 +603,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* sS = smem;   // DW_STAGES x (dout_hi, dout_mid, im2col), 16 KB each
-  uint8_t* sRaw = sS + DW_STAGES * 3 * A_BYTES;   // RAW_STAGES raw fp32 dout tiles (bulk-copy ring)
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sRaw + RAW_STAGES * RAW_BYTES);
+  uint8_t* sRaw = sS + DW_STAGES * 3 * A_BYTES;   // DW_RAW_STAGES raw fp32 dout tiles (bulk-copy ring)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sRaw + DW_RAW_STAGES * RAW_BYTES);
   uint64_t* a_empty = a_full + DW_STAGES;
   uint64_t* tmem_full = a_empty + DW_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* raw_full = tmem_empty + 2;
-  uint64_t* raw_empty = raw_full + RAW_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RAW_STAGES);
+  uint64_t* raw_empty = raw_full + DW_RAW_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + DW_RAW_STAGES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < DW_STAGES; ++s) {
       ptx::mbar_init(&a_full[s], 256);
       ptx::mbar_init(&a_empty[s], 1);
     }
-    for (int r = 0; r < RAW_STAGES; ++r) {
+    for (int r = 0; r < DW_RAW_STAGES; ++r) {
       ptx::mbar_init(&raw_full[r], 1);      // the loader's arrive.expect_tx
       ptx::mbar_init(&raw_empty[r], 256);   // every converter thread
     }
@@ -639,15 +640,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
 
   if (warp < 8) {
     // ===================================================== producers: convert the raw dout tile + half an im2col row
-    // (dout arrives through the loader warp's bulk-copy ring, RAW_STAGES tiles ahead: with per-thread
+    // (dout arrives through the loader warp's bulk-copy ring, DW_RAW_STAGES tiles ahead: with per-thread
     // global loads ncu showed 8.7 long-scoreboard stalls per issue and issue slots 23 % busy)
     const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int s = it % DW_STAGES;
       const uint32_t ph = (it / DW_STAGES) & 1;
-      const int rs = it % RAW_STAGES;
-      const uint32_t rph = (it / RAW_STAGES) & 1;
+      const int rs = it % DW_RAW_STAGES;
+      const uint32_t rph = (it / DW_RAW_STAGES) & 1;
       const long pix = (long)tile * TILE_P + row;
       float v[16];
 #pragma unroll
@@ -692,8 +693,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) conv2_dw_tc_kernel(const DwPara
     // ===================================================== loader: bulk copies of the raw dout tiles
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int rs = it % RAW_STAGES;
-      const uint32_t rph = (it / RAW_STAGES) & 1;
+      const int rs = it % DW_RAW_STAGES;
+      const uint32_t rph = (it / DW_RAW_STAGES) & 1;
       ptx::mbar_wait_sleepy(&raw_empty[rs], rph ^ 1, 36);
       if (ptx::elect_one()) {
         const long left = p.total - (long)tile * TILE_P;
@@ -833,8 +834,8 @@ void launch_conv2_dw_tc(Context& ctx, const float* img, const float* dout, float
   p.total = (long)N * p.OH * p.OW;
   if (p.total <= 0) return;
   p.ntiles = (int)((p.total + TILE_P - 1) / TILE_P);
-  const size_t smem = 1024 + (size_t)DW_STAGES * 3 * A_BYTES + (size_t)RAW_STAGES * RAW_BYTES +
-                      (2 * DW_STAGES + 4 + 2 * RAW_STAGES) * 8 + 32;
+  const size_t smem = 1024 + (size_t)DW_STAGES * 3 * A_BYTES + (size_t)DW_RAW_STAGES * RAW_BYTES +
+                      (2 * DW_STAGES + 4 + 2 * DW_RAW_STAGES) * 8 + 32;
   int grid = ctx.sm_count;
   if (grid > p.ntiles) grid = p.ntiles;
   EGB_CUDA(cudaFuncSetAttribute(conv2_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
