@@ -655,7 +655,9 @@ void gemm_lat_plan(int M, int N, int K, bool b_mn, int sms, int max_ck, int* bn_
   for (int bn = 256; bn >= step; bn -= step) {
     if (bn > step && bn - step >= N) continue;  // a narrower tile already covers N
     const int tiles = tiles_m * ((N + bn - 1) / bn);
-    const double t_kb = (128.0 + bn) * 640.0 / 128.0 / 1900.0;
+    // bytes through shared memory per 64-deep k-block / (128 B/clk): TMA writes (128 + bn) * 256, the MMAs read
+    // 3 * (128 + bn) * 128, or (2 * 128 + 3 * bn) * 128 in the two-MMA form (bn <= 128)
+    const double t_kb = (bn <= 128 ? 65536.0 + 640.0 * bn : (128.0 + bn) * 640.0) / 128.0 / 1900.0;
     const int units_per_warp = (((N < bn ? N : bn) + UNIT - 1) / UNIT + 1) / 2;
     for (int ck = 1; ck <= max_ck && ck <= 4; ck *= 2) {
       if (ck > 1 && (bn > 64 || tiles * ck > sms)) break;
