@@ -15,10 +15,10 @@
 //      (parameters never leave the rank; replicas stay bit-identical because every rank applies the same values).
 // Lines carry their own epoch tag (see st_ll): no fences, no separate flags, no grid-wide barrier, no atomics.
 //
-// CTA b of a rank only ever talks to CTA b of the other ranks (per-CTA flag slots), so there is no grid-wide
-// barrier and no atomics; flags carry a per-CTA epoch that lives in device memory, which lets the kernel sit in a
-// replayed CUDA graph with constant parameters. Per rank and step (N - 1) / N of the bucket crosses NVLink in
-// each direction. Waits are bounded: a peer that never arrives traps the kernel instead of hanging the GPU.
+// CTA b of a rank only ever talks to CTA b of the other ranks, so there is no grid-wide barrier; the epoch every
+// line is tagged with lives in device memory (one slot per CTA, advanced by the kernel itself), which lets the kernel
+// sit in a replayed CUDA graph with constant parameters. Per rank and step 2 x (N - 1) / N of the bucket is stored
+// into peer memory. Waits are bounded: a peer that never arrives traps the kernel instead of hanging the GPU.
 #include <stdlib.h>
 
 #include "egb_internal.hpp"
@@ -32,14 +32,6 @@ constexpr int EX_THREADS = 256;
 constexpr size_t FLAG_BYTES = (size_t)(2 * EX_MAX_WORLD * EX_MAX_CTAS + EX_MAX_CTAS) * sizeof(uint32_t) + 16 * 8;
 constexpr size_t INBOX_OFF = (FLAG_BYTES + 255) & ~(size_t)255;
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -47,17 +39,6 @@ __device__ __forceinline__ unsigned long long globaltimer() {
 }
 // peer / freshly written data: always from L2 or the link, never from this SM's L1
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-
-// wait until *flag >= epoch (flags only grow); trap after ~2 s so a missing peer cannot hang the device
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
-  const unsigned long long t0 = globaltimer();
-  while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
-    if (globaltimer() - t0 > 2000000000ull) {
-      printf("egb exchange: rank flag %p never reached epoch %u (peer missing)\n", (const void*)flag, epoch);
-      __trap();
-    }
-  }
-}
 
 __device__ __forceinline__ void st_cg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
 

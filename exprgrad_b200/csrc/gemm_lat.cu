@@ -2,9 +2,9 @@
 // (dense layers and their adjoints: exprgrad/layers/dnn.nim:19-27, passes.nim:519-549).
 //
 // The main loop is the one of gemm_tcgen05.cu (TMA producer warp -> mbarrier ring -> tcgen05.mma issuer ->
-// fp32 accumulator in TMEM, three bf16 products per fp32 product). What differs is everything behind the
-// accumulator, which dominated those launches (device timeline, profiles/r02c_gemm_trace.txt: main loop
-// 0.4-4.0 us, epilogue 3.7-5.5 us per contraction):
+// fp32 accumulator in TMEM, three bf16 products per fp32 product - issued here as TWO MMAs per k-step, see the
+// MMA issuer). What differs is everything behind the accumulator, which dominated those launches (device timeline,
+// profiles/r02c_dense_step_trace_before.txt: main loop 0.4-4.0 us, epilogue 3.7-5.5 us per contraction):
 //
 //   * The epilogue works in the TMEM-native layout - thread t of a warp owns accumulator row t - on units of
 //     32 rows x 32 columns. Every tensor the fused stages read or write moves as ONE 4 KB (fp32) or 2 KB (bf16)
@@ -19,8 +19,8 @@
 //     them into shared memory and sends them with one bulk copy (cp.async.bulk shared::cta -> shared::cluster)
 //     that completes on an mbarrier of the owner - a one-way trip by the copy engine instead of two cluster
 //     barriers and a round trip of per-thread DSMEM loads. Partial sums are added in k order: deterministic.
-//   * The second stage is a compile-time parameter and the unit code exists once: the kernel is ~1/8 of the
-//     size of the general one, which matters for code that runs once per launch.
+//   * The second stage is a compile-time parameter and the unit code exists once: the kernel is a quarter of the
+//     size of the general one (4 100 vs 16 300 instructions), which matters for code that runs once per launch.
 //
 // Restrictions (everything else stays on gemm_tcgen05.cu): fp32 tensors with a 16-byte aligned base and a
 // leading dimension that is a multiple of 4 (TMA), cluster split-K factors 2 and 4 with tiles of at most 64
@@ -326,7 +326,6 @@ gemm_lat_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int rows_per = BM / p.ck;
     const uint32_t owner = p.ck > 1 ? (uint32_t)(q * 32 / rows_per) : 0u;
     const bool finisher = owner == crank;
-    const int fin_per_cta = (rows_per / 32) * 2;                        // finishing warps of a CTA
     const int fl = (q - (int)owner * (rows_per / 32)) * 2 + eh;         // index of this warp's unit among them
     uint32_t aux_phase = 0;
 
