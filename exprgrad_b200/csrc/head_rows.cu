@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_rows_kernel(const HeadPa
   float* const zpart = arow + ROWS * p.Kin;                  // [ROWS][WPR][CP]
   float* const colpart = zpart + ROWS * WPR * CP;            // [ROWS][nout_p]
   float* const colpart_dz = colpart + ROWS * nout_p;         // [ROWS][CP]
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(colpart_dz + ROWS * CP);
+  float* const dzs = colpart_dz + ROWS * CP;                 // [ROWS][CP]  dL/dlogits of each row, for its four warps
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(dzs + ROWS * CP);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wr = warp & (WPR - 1), rl = warp / WPR;          // warp of its row group, row slot of the CTA
   const int chunks = nout_p / COL_TILE;
@@ -171,30 +172,33 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_rows_kernel(const HeadPa
     }
     if (lane < 4) *reinterpret_cast<float4*>(zpart + (rl * WPR + wr) * CP + 4 * lane) = make_float4(z4[0], z4[1], z4[2], z4[3]);
     row_group_sync(rl);
-    float z = 0.0f;
-    if (lane < CP) {
-#pragma unroll
-      for (int w = 0; w < WPR; ++w) z += zpart[(rl * WPR + w) * CP + lane];   // fixed order
-    }
-    HEAD_STAMP(5);
-    if (on && p.bias_in) z = __fadd_rn(z, bv);
-    // ---- softmax + crossEntropy and their adjoints (the arithmetic of fused_rows.cu, one class per lane; at most 16
-    //      classes, lanes 16.. hold zeros: four butterfly steps)
-    const float e = on ? expf(z) : 0.0f;
-    float s = e;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    float t = 0.0f, dsum = 0.0f, dp = 0.0f, pr = 0.0f;
-    if (on) {
-      pr = __fdiv_rn(e, s);
-      dp = __fdiv_rn(__fmul_rn(scale, yv), pr);
-      t = __fmul_rn(__fdiv_rn(dp, s), e);
-      dsum = __fmul_rn(0.0f - e, __fdiv_rn(dp, __fmul_rn(s, s)));
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-    const float dz = on ? __fadd_rn(t, __fmul_rn(dsum, e)) : 0.0f;
+    // ---- softmax + crossEntropy and their adjoints: by ONE warp of the row (the arithmetic of fused_rows.cu, one
+    //      class per lane; at most 16 classes, lanes 16.. hold zeros: four butterfly steps); the others wait for dz.
+    //      (All four warps doing it redundantly was simpler - one barrier less - but 32 warps x ~250 instructions is
+    //      2 000 issue cycles per scheduler for nothing.)
     if (wr == 0) {
+      float z = 0.0f;
+      if (lane < CP) {
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) z += zpart[(rl * WPR + w) * CP + lane];   // fixed order
+      }
+      HEAD_STAMP(5);
+      if (on && p.bias_in) z = __fadd_rn(z, bv);
+      const float e = on ? expf(z) : 0.0f;
+      float s = e;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      float t = 0.0f, dsum = 0.0f, dp = 0.0f, pr = 0.0f;
+      if (on) {
+        pr = __fdiv_rn(e, s);
+        dp = __fdiv_rn(__fmul_rn(scale, yv), pr);
+        t = __fmul_rn(__fdiv_rn(dp, s), e);
+        dsum = __fmul_rn(0.0f - e, __fdiv_rn(dp, __fmul_rn(s, s)));
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+      const float dz = on ? __fadd_rn(t, __fmul_rn(dsum, e)) : 0.0f;
+      if (lane < CP) dzs[rl * CP + lane] = dz;
       if (on) {
         p.Z[idx] = z;
         p.P[idx] = pr;
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_rows_kernel(const HeadPa
       }
       colacc_dz += dz;
     }
+    row_group_sync(rl);   // dz of this row is in shared memory
     HEAD_STAMP(15);
     // ---- adjoint contraction: g[c] = sum_j dz[j] * w'[j, c], 4 columns per lane: warp wr owns columns
     //      [i COL_TILE + wr 128, + 128) of every chunk i
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) head_rows_kernel(const HeadPa
       for (int e2 = 0; e2 < 4; ++e2) gacc[i][e2] = 0.0f;
 #pragma unroll 2
     for (int jj = 0; jj < p.cols; ++jj) {
-      const float d = __shfl_sync(0xffffffffu, dz, jj);
+      const float d = dzs[rl * CP + jj];
       const float* wrow = w_bwd + jj * nout_p + wr * 128 + 4 * lane;
 #pragma unroll
       for (int i = 0; i < MAX_CHUNKS; ++i) {
@@ -304,7 +309,7 @@ int head_nout_p(int nout) { return (nout + COL_TILE - 1) / COL_TILE * COL_TILE; 
 
 size_t head_smem_bytes(const HeadParams& p) {
   const size_t nout_p = (size_t)head_nout_p(p.Nout);
-  return 4 * ((size_t)p.Kin * CP + (size_t)p.cols * nout_p + (size_t)ROWS * p.Kin + ROWS * WPR * CP + ROWS * nout_p + ROWS * CP) + 16;
+  return 4 * ((size_t)p.Kin * CP + (size_t)p.cols * nout_p + (size_t)ROWS * p.Kin + ROWS * WPR * CP + ROWS * nout_p + 2 * ROWS * CP) + 16;
 }
 
 }  // namespace
