@@ -265,7 +265,7 @@ void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st) {
   // Out-of-place maps stream (evict-first loads and stores: 0.94-0.96 of the copy roofline on 512 MiB tensors).
   // In-place forms (optimizer updates: the destination is also read) are DRAM-limited differently: the write-back
   // of a line follows its read by a few MB, same DRAM bytes but 62 % instead of 76 % DRAM activity in ncu
-  // (profiles/r02c_eltwise_ncu.txt); they measured best with the default policy (0.80 vs 0.75 with evict-first).
+  // (profiles/r02c_eltwise_sgd_ncu.txt); they measured best with the default policy (0.80 vs 0.75 with evict-first).
   const bool in_place = e.accumulate || e.out == e.in[0] || (e.nreads >= 2 && e.out == e.in[1]);
   a.streaming = bytes > 64.0e6 ? (in_place ? 0 : 7) : 0;
   if (const char* pol = getenv("EGB_ELT_POLICY")) a.streaming = bytes > 64.0e6 ? atoi(pol) : 0;   // measurement knob
