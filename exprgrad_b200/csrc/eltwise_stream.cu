@@ -24,6 +24,9 @@ namespace {
 
 constexpr int ELT_THREADS = 256;
 constexpr int ELT_UNROLL = 4;
+constexpr int ELT_SCALAR_VARIANT = 1;   // store schedule of the scalar-operand kinds (see elt_stream_kernel; measured: profiles/r04_*)
+constexpr int ELT_SCALAR_SMEM = 73728;  // dynamic shared memory request of variant 1 (bytes; residency bound, never touched)
+constexpr int ELT_LATE_TRIGGER = 0;     // launches that stream more than 64 MB release their dependents at exit
 
 struct EltArgs {
   float* out;
@@ -75,6 +78,11 @@ EGB_ELT_FN(ELT_ADAM_M, 2, return (x * a.p0) + (a.p1 * y);)
 EGB_ELT_FN(ELT_ADAM_V, 2, return (x * a.p0) + (a.p1 * (y * y));)
 // div(mul(negate(eta), div(m, c1)), add(sqrt(div(v, c2)), eps)); c1 = 1 - pow(b1, epoch), c2 = 1 - pow(b2, epoch)
 EGB_ELT_FN(ELT_ADAM_STEP, 2, return __fdiv_rn(a.p0 * __fdiv_rn(x, a.p1), __fsqrt_rn(__fdiv_rn(y, a.p2)) + a.p3);)
+// adjoint of sq(x) under a scalar loss, add(mul(g, x), mul(g, x)): y is ONE element (in1[0], the adjoint seed), loaded
+// once per thread instead of streamed
+EGB_ELT_FN(ELT_SQ_ADJ, 2, return (y * x) + (y * x);)
+template <int KIND>
+constexpr bool kScalarIn1 = KIND == ELT_SQ_ADJ;
 
 // (the policy bits are uniform across the grid: the branches cost one predicate each)
 __device__ __forceinline__ float4 ld4(const float* p, bool cs, bool lu = false) {
@@ -93,18 +101,25 @@ __device__ __forceinline__ long long row_offset(long long i, const EltArgs& a) {
   return i % a.row;
 }
 
-template <int KIND, int UNROLL>
+// VARIANT (scalar-operand kinds only): 0 = results and stores interleaved per unrolled group like every other kind,
+// 1 = all results first, pinned in their registers, then the stores back to back
+template <int KIND, int UNROLL, int VARIANT = 0>
 __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArgs a) {
   using Fn = EltFn<KIND>;
   const bool cs_in = (a.streaming & 1) != 0, cs_out_ld = (a.streaming & 2) != 0, cs_st = (a.streaming & 4) != 0;
   const bool lu_out = (a.streaming & 8) != 0;
-  pdl_launch_dependents();
+  // bit 4: no early trigger - the dependent launch is released when this grid's CTAs exit. A long streaming launch
+  // gains nothing from an early start of its successor, and a successor that becomes co-resident (a one-CTA-per-SM
+  // tensor-core kernel whose warps poll mbarriers while they wait) takes issue slots and LSU bandwidth from it.
+  if (!(a.streaming & 16)) pdl_launch_dependents();
   pdl_wait();
   const long long n4 = a.n >> 2;
   const long long stride = (long long)gridDim.x * ELT_THREADS;
   const long long first = (long long)blockIdx.x * ELT_THREADS + threadIdx.x;
   // in-place forms (adam: m += f(m, g)) read the destination as an operand already
   const bool alias0 = KIND != ELT_BIAS_ROW && a.in0 == a.out;
+  float sc = 0.0f;
+  if constexpr (kScalarIn1<KIND>) sc = __ldg(a.in1);
   for (long long base = first; base < n4; base += stride * UNROLL) {
     float4 x[UNROLL], y[UNROLL], o[UNROLL];
     // phase 1: every load of this iteration
@@ -115,11 +130,39 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArg
       if (g < n4) {
         if constexpr (KIND == ELT_BIAS_ROW) x[u] = *reinterpret_cast<const float4*>(a.in0 + row_offset(g << 2, a));
         else x[u] = ld4(a.in0 + (g << 2), alias0 ? cs_out_ld : cs_in, alias0 && lu_out);
-        if constexpr (Fn::kInputs >= 2) y[u] = ld4(a.in1 + (g << 2), cs_in);
-        if (a.accumulate) o[u] = alias0 ? x[u] : ld4(a.out + (g << 2), cs_out_ld, lu_out);
+        if constexpr (kScalarIn1<KIND>) y[u] = make_float4(sc, sc, sc, sc);
+        else if constexpr (Fn::kInputs >= 2) y[u] = ld4(a.in1 + (g << 2), cs_in);
+        if constexpr (!(kScalarIn1<KIND> && VARIANT == 1))
+          if (a.accumulate) o[u] = alias0 ? x[u] : ld4(a.out + (g << 2), cs_out_ld, lu_out);
       }
     }
     // phase 2: arithmetic + stores
+    if constexpr (kScalarIn1<KIND> && VARIANT == 1) {
+      // overwrite only (the launcher refuses the accumulating form): every result first, in place, one register group
+      // per unrolled load, then the stores back to back. Left to itself the compiler sinks each group's arithmetic next
+      // to its store and reuses one register group for all four results, so a group has to wait until the previous
+      // store has read its operands (r04c ncu of the interleaved form: 56 % DRAM activity where relu has 76 %); the
+      // empty asm makes all results live at once.
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        x[u].x = Fn::apply(x[u].x, sc, a); x[u].y = Fn::apply(x[u].y, sc, a);
+        x[u].z = Fn::apply(x[u].z, sc, a); x[u].w = Fn::apply(x[u].w, sc, a);
+      }
+      static_assert(UNROLL == 4 || UNROLL == 2, "register pinning below is written for 2 or 4 groups");
+      if constexpr (UNROLL == 4)
+        asm volatile("" : "+f"(x[0].x), "+f"(x[0].y), "+f"(x[0].z), "+f"(x[0].w), "+f"(x[1].x), "+f"(x[1].y), "+f"(x[1].z),
+                          "+f"(x[1].w), "+f"(x[2].x), "+f"(x[2].y), "+f"(x[2].z), "+f"(x[2].w), "+f"(x[3].x), "+f"(x[3].y),
+                          "+f"(x[3].z), "+f"(x[3].w) : : "memory");
+      else
+        asm volatile("" : "+f"(x[0].x), "+f"(x[0].y), "+f"(x[0].z), "+f"(x[0].w), "+f"(x[1].x), "+f"(x[1].y), "+f"(x[1].z),
+                          "+f"(x[1].w) : : "memory");
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long long g = base + (long long)u * stride;
+        if (g < n4) st4(a.out + (g << 2), x[u], cs_st);
+      }
+      continue;
+    }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long g = base + (long long)u * stride;
@@ -140,9 +183,11 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArg
   const long long t = (n4 << 2) + first;
   if (t < a.n) {
     const float x = KIND == ELT_BIAS_ROW ? a.in0[row_offset(t, a)] : a.in0[t];
-    const float y = Fn::kInputs >= 2 ? a.in1[t] : 0.0f;
+    float y = 0.0f;
+    if constexpr (kScalarIn1<KIND>) y = sc;
+    else if constexpr (Fn::kInputs >= 2) y = a.in1[t];
     const float r = Fn::apply(x, y, a);
-    a.out[t] = a.accumulate ? a.out[t] + r : r;
+    a.out[t] = (!kScalarIn1<KIND> && a.accumulate) ? a.out[t] + r : r;
   }
 }
 
@@ -212,6 +257,24 @@ void launch_kind(Context& ctx, const EltArgs& a, cudaStream_t st) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   Launch l(ctx, KC_ELTWISE, st);
+  if constexpr (kScalarIn1<KIND>) {
+    // EGB_ELT_SCALAR_VARIANT: measurement knob for the two store schedules of the scalar-operand kinds
+    static const int variant = getenv("EGB_ELT_SCALAR_VARIANT") ? atoi(getenv("EGB_ELT_SCALAR_VARIANT")) : ELT_SCALAR_VARIANT;
+    if (variant == 1) {
+      // Variant 1 needs 48 registers: five of its CTAs fit on an SM. The grid (3 x SMs, one static slice of the tensor per
+      // CTA) is only balanced when every SM gets exactly three, which the hardware does not guarantee for a launch
+      // that trickles in while its predecessor's CTAs retire; an (unused) dynamic shared memory request of a third
+      // of the SM's capacity bounds the residency at three.
+      static const int smem = getenv("EGB_ELT_SCALAR_SMEM") ? atoi(getenv("EGB_ELT_SCALAR_SMEM")) : ELT_SCALAR_SMEM;
+      static bool attr_set = false;
+      if (smem > 48 * 1024 && !attr_set) {
+        EGB_CUDA(cudaFuncSetAttribute(elt_stream_kernel<KIND, ELT_UNROLL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+      }
+      launch_kernel(ctx, elt_stream_kernel<KIND, ELT_UNROLL, 1>, dim3((unsigned)blocks), dim3(ELT_THREADS), (size_t)smem, st, a);
+      return;
+    }
+  }
   if (unroll == 2) launch_kernel(ctx, elt_stream_kernel<KIND, 2>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
   else launch_kernel(ctx, elt_stream_kernel<KIND, ELT_UNROLL>, dim3((unsigned)blocks), dim3(ELT_THREADS), 0, st, a);
 }
@@ -226,7 +289,9 @@ bool eltwise_stream_supported(const EltLaunch& e) {
   if (e.kind <= ELT_NONE || e.kind >= ELT_KIND_COUNT || e.n <= 0) return false;
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!e.out || !aligned(e.out) || !e.in[0] || !aligned(e.in[0])) return false;
-  if (e.nreads >= 2 && (!e.in[1] || !aligned(e.in[1]))) return false;
+  const bool scalar1 = e.kind == ELT_SQ_ADJ;   // in[1] is one element; these kernels only overwrite
+  if (scalar1 && e.accumulate) return false;
+  if (e.nreads >= 2 && (!e.in[1] || (!scalar1 && !aligned(e.in[1])))) return false;
   if (e.nreads > 2) return false;
   if (e.kind == ELT_BIAS_ROW && (e.row <= 0 || (e.row & 3) != 0 || e.n % e.row != 0)) return false;
   return true;
@@ -261,7 +326,8 @@ void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st) {
   a.row = e.row > 0 ? e.row : 1;
   a.accumulate = e.accumulate ? 1 : 0;
   // bytes this launch moves; beyond about half of the L2 it streams (evict-first)
-  const double bytes = 4.0 * (double)e.n * (1 + (e.kind == ELT_BIAS_ROW ? 0 : e.nreads) + (e.accumulate ? 1 : 0));
+  const int streamed_reads = e.kind == ELT_BIAS_ROW ? 0 : e.kind == ELT_SQ_ADJ ? 1 : e.nreads;
+  const double bytes = 4.0 * (double)e.n * (1 + streamed_reads + (e.accumulate ? 1 : 0));
   // Out-of-place maps stream (evict-first loads and stores: 0.94-0.96 of the copy roofline on 512 MiB tensors).
   // In-place forms (optimizer updates: the destination is also read) are DRAM-limited differently: the write-back
   // of a line follows its read by a few MB, same DRAM bytes but 62 % instead of 76 % DRAM activity in ncu
@@ -269,13 +335,15 @@ void launch_eltwise_stream(Context& ctx, const EltLaunch& e, cudaStream_t st) {
   const bool in_place = e.accumulate || e.out == e.in[0] || (e.nreads >= 2 && e.out == e.in[1]);
   a.streaming = bytes > 64.0e6 ? (in_place ? 0 : 7) : 0;
   if (const char* pol = getenv("EGB_ELT_POLICY")) a.streaming = bytes > 64.0e6 ? atoi(pol) : 0;   // measurement knob
+  static const int late = getenv("EGB_ELT_LATE_TRIGGER") ? atoi(getenv("EGB_ELT_LATE_TRIGGER")) : ELT_LATE_TRIGGER;
+  if (late && bytes > 64.0e6) a.streaming |= 16;
   switch (e.kind) {
 #define EGB_ELT_CASE(K) case K: launch_kind<K>(ctx, a, st); break;
     EGB_ELT_CASE(ELT_COPY) EGB_ELT_CASE(ELT_RELU) EGB_ELT_CASE(ELT_LEAKY) EGB_ELT_CASE(ELT_SIGMOID) EGB_ELT_CASE(ELT_TANH)
     EGB_ELT_CASE(ELT_SCALE) EGB_ELT_CASE(ELT_SCALE_NEG) EGB_ELT_CASE(ELT_DIV_CONST) EGB_ELT_CASE(ELT_ADD) EGB_ELT_CASE(ELT_SUB)
     EGB_ELT_CASE(ELT_MUL) EGB_ELT_CASE(ELT_RELU_ADJ) EGB_ELT_CASE(ELT_LEAKY_ADJ) EGB_ELT_CASE(ELT_SIGMOID_ADJ)
     EGB_ELT_CASE(ELT_TANH_ADJ) EGB_ELT_CASE(ELT_ADAM_M) EGB_ELT_CASE(ELT_ADAM_V) EGB_ELT_CASE(ELT_ADAM_STEP)
-    EGB_ELT_CASE(ELT_BIAS_ROW)
+    EGB_ELT_CASE(ELT_BIAS_ROW) EGB_ELT_CASE(ELT_SQ_ADJ)
 #undef EGB_ELT_CASE
     default: fail(EGB_ERR_GPU, "eltwise: unknown kind %d", e.kind);
   }

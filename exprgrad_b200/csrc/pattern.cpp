@@ -192,10 +192,12 @@ bool match_map_shape(const Kernel& k, const ShapeTable& shapes, MapShape& out) {
   out.n = n;
   out.row = k.write.is_raw || wsh->second.empty() ? n : wsh->second.back();
   out.reads.clear();
+  out.scalar_offset.clear();
   for (auto& r : k.reads) {
     auto rsh = shapes.find(r.tensor);
     if (rsh == shapes.end()) return false;
     MapAccess acc = MapAccess::NONE;
+    int64_t scalar_off = 0;
     if (r.is_raw == k.write.is_raw && r.dims.size() == k.write.dims.size()) {
       bool same = true;
       for (size_t d = 0; d < r.dims.size() && same; ++d) same = r.dims[d].same_as(k.write.dims[d]);
@@ -206,8 +208,23 @@ bool match_map_shape(const Kernel& k, const ShapeTable& shapes, MapShape& out) {
     if (acc == MapAccess::NONE && !k.write.is_raw && !r.is_raw && k.write.dims.size() >= 2 && r.dims.size() == 1 &&
         r.dims[0].same_as(k.write.dims.back()) && rsh->second.size() == 1 && rsh->second[0] == wsh->second.back())
       acc = MapAccess::ROW;
+    if (acc == MapAccess::NONE && !r.dims.empty() && (r.is_raw ? r.dims.size() == 1 : r.dims.size() == rsh->second.size())) {
+      // every index a constant inside the tensor: one fixed element, row-major flat offset
+      bool fixed = true;
+      int64_t rn = 1;
+      for (auto d : rsh->second) rn *= d;
+      for (size_t d = 0; d < r.dims.size() && fixed; ++d) {
+        const LinearIndex& li = r.dims[d];
+        const int64_t extent = r.is_raw ? rn : rsh->second[d];
+        fixed = li.setup.empty() && li.factors.empty() && li.constant >= 0 && li.constant < extent;
+        if (fixed) scalar_off = scalar_off * extent + li.constant;
+      }
+      if (fixed) acc = MapAccess::SCALAR;
+      else scalar_off = 0;
+    }
     if (acc == MapAccess::NONE) return false;
     out.reads.push_back(acc);
+    out.scalar_offset.push_back(scalar_off);
   }
   return true;
 }
@@ -219,6 +236,7 @@ struct EltPattern {
   int nreads;
   const char* text;
   bool epoch;
+  int scalar_operand = -1;   // the operand that must be a fixed element (MapAccess::SCALAR); every other one must not be
 };
 
 // The forms of exprgrad/layers/base.nim and dnn.nim and of their adjoints as `derive` emits them
@@ -251,6 +269,11 @@ const EltPattern kPatterns[] = {
     {ELT_ADAM_STEP, 2,
      "div(mul(negate(#0),div($0,sub(1,pow(#1,toscalar(epoch()))))),add(sqrt(div($1,sub(1,pow(#2,toscalar(epoch()))))),#3))",
      true},
+    // adjoint of sq(x) = x * x under a scalar loss (derive of mul, passes.nim:399-403): d[i] = g[0] * x[i] + g[0] * x[i]
+    // (two spellings: a commutative node is tried in the written order first, so each one pins $1 to the seed for one
+    // operand order of the products)
+    {ELT_SQ_ADJ, 2, "add(mul($1,$0),mul($1,$0))", false, 1},
+    {ELT_SQ_ADJ, 2, "add(mul($0,$1),mul($0,$1))", false, 1},
 };
 
 }  // namespace
@@ -258,7 +281,7 @@ const EltPattern kPatterns[] = {
 const char* elt_kind_name(int kind) {
   static const char* names[] = {"none", "copy", "relu", "leakyRelu", "sigmoid", "tanh", "scale", "sgd-axpy", "div-const", "add", "sub",
                                 "mul", "relu-adjoint", "leakyRelu-adjoint", "sigmoid-adjoint", "tanh-adjoint", "adam-m", "adam-v",
-                                "adam-step", "bias-row-add"};
+                                "adam-step", "bias-row-add", "square-adjoint"};
   return kind >= 0 && kind < ELT_KIND_COUNT ? names[kind] : "?";
 }
 
@@ -276,7 +299,7 @@ bool match_eltwise(const Kernel& k, const ShapeTable& shapes, EltSpec& out) {
     // every read of the kernel must be accounted for by the pattern (a read the expression ignores is fine to drop,
     // but then it would not have survived dead-code elimination - treat it as "no match")
     if ((int)m.read_of.size() != p.nreads) continue;
-    bool any_row = false, all_row = true;
+    bool any_row = false, all_row = true, scalars_ok = true;
     EltSpec s;
     s.kind = p.kind;
     s.nreads = p.nreads;
@@ -284,9 +307,15 @@ bool match_eltwise(const Kernel& k, const ShapeTable& shapes, EltSpec& out) {
       const int ri = m.read_of.at(q);
       s.read_tensor[q] = k.reads[ri].tensor;
       s.row_read[q] = ms.reads[ri] == MapAccess::ROW;
+      s.scalar_read[q] = ms.reads[ri] == MapAccess::SCALAR;
+      s.scalar_offset[q] = ms.scalar_offset[ri];
+      scalars_ok = scalars_ok && s.scalar_read[q] == (q == p.scalar_operand);
       any_row = any_row || s.row_read[q];
       all_row = all_row && s.row_read[q];
     }
+    // a fixed-element operand only where the form's kernel loads one (the binding of a commutative pattern is not
+    // unique: mul($1,$0) may have bound the operands the other way round - try the next pattern rather than give up)
+    if (!scalars_ok) continue;
     if (any_row) {
       // the only broadcast form with a dedicated kernel: out[y, x] (+)= b[x]  (bias add, dnn.nim:22-24)
       if (!(p.kind == ELT_COPY && all_row)) return false;

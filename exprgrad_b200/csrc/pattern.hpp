@@ -56,12 +56,15 @@ bool match_form(const Kernel& k, const KernelForm& form, PatMatch& m);
 
 // Access structure of a map kernel: every loop independent, the write covers its whole tensor, and each read
 // either uses the same index tuple as the write on a tensor of the same shape (SAME: identical flat offsets),
-// or is a row broadcast (ROW: the tensor is indexed by the write's last dimension only, dnn.nim:22-24).
-enum class MapAccess { NONE, SAME, ROW };
+// is a row broadcast (ROW: the tensor is indexed by the write's last dimension only, dnn.nim:22-24), or is one
+// fixed element (SCALAR: every index is a constant, e.g. the seed `dL[0]` that `derive` multiplies into the adjoint
+// of a scalar loss, passes.nim:383-403).
+enum class MapAccess { NONE, SAME, ROW, SCALAR };
 struct MapShape {
   int64_t n = 0;          // elements written
   int64_t row = 0;        // extent of the last write dimension
   std::vector<MapAccess> reads;
+  std::vector<int64_t> scalar_offset;   // per read: flat element offset of a SCALAR access (0 otherwise)
 };
 bool match_map_shape(const Kernel& k, const ShapeTable& shapes, MapShape& out);
 
@@ -70,7 +73,7 @@ enum EltKind {
   ELT_NONE = 0,
   ELT_COPY, ELT_RELU, ELT_LEAKY, ELT_SIGMOID, ELT_TANH, ELT_SCALE, ELT_SCALE_NEG, ELT_DIV_CONST,
   ELT_ADD, ELT_SUB, ELT_MUL, ELT_RELU_ADJ, ELT_LEAKY_ADJ, ELT_SIGMOID_ADJ, ELT_TANH_ADJ,
-  ELT_ADAM_M, ELT_ADAM_V, ELT_ADAM_STEP, ELT_BIAS_ROW,
+  ELT_ADAM_M, ELT_ADAM_V, ELT_ADAM_STEP, ELT_BIAS_ROW, ELT_SQ_ADJ,
   ELT_KIND_COUNT
 };
 struct EltSpec {
@@ -78,6 +81,8 @@ struct EltSpec {
   int nreads = 0;
   int read_tensor[3] = {0, 0, 0};   // tensors bound to $0, $1, $2
   bool row_read[3] = {false, false, false};
+  bool scalar_read[3] = {false, false, false};   // operand is one fixed element (MapAccess::SCALAR) ...
+  int64_t scalar_offset[3] = {0, 0, 0};          // ... at this flat offset of its tensor
   double lit[4] = {0, 0, 0, 0};     // captured literals (f64, rounded by the launcher like llvmgen.nim:213-218)
   bool uses_epoch = false;
   int64_t n = 0, row = 0;

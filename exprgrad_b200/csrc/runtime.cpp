@@ -636,7 +636,10 @@ bool build_eltwise_node(Model& m, Plan& plan, const Kernel& k, int ki, bool over
     return it == ptrs.end() ? (float*)nullptr : (float*)it->second;
   };
   e.out = ptr(k.write.tensor);
-  for (int q = 0; q < es.nreads && q < 2; ++q) e.in[q] = ptr(es.read_tensor[q]);
+  for (int q = 0; q < es.nreads && q < 2; ++q) {
+    e.in[q] = ptr(es.read_tensor[q]);
+    if (es.scalar_read[q] && e.in[q]) e.in[q] += es.scalar_offset[q];   // one fixed element of that tensor
+  }
   // literals: constant sub-expressions are folded in float64 and then rounded to the scalar type
   // (propagateConstants passes.nim:1629-1650, llvmgen.nim:213-218); pow(b, epoch) is a run-time fp32 value
   switch (es.kind) {

@@ -1,0 +1,136 @@
+"""Seeded random `++=` graphs for differential tests (native passes vs the oracle's restatement of passes.nim on CPU;
+device kernels vs the oracle's loop nests on the GPU). The same seed builds the same graph with either DSL module
+(`oracle` or `exprgrad_b200.frontend`), like tests/graphs.py.
+
+A graph is a chain of 2-4 kernels over inputs a, b : [R, C], v : [C] and parameters w : [C, 5], u : [C]:
+raw maps, 2-D maps with a row broadcast, shifted reads (conv1-like, test_model.nim:91-97), row / column
+reductions, a contraction, then a scalar loss; targets: the chain's result, the loss, d loss / d a, and an SGD
+step on the parameters the chain used. Expressions are random trees over every differentiable opcode of
+ir.nim:51-76 whose adjoint `derive` knows (passes.nim:383-517), kept inside their domains (sqrt / ln / pow / div see
+e*e + 1) so that the numeric comparison is meaningful; comparisons only look at input values (exact on both sides),
+never at computed ones, so that a last-ulp difference cannot flip a branch."""
+import random
+
+COLS = 6   # C: w is [C, 5], u is [C]
+KOUT = 5
+
+
+def _expr(d, rng, leaves, cmp_leaves, depth):
+    """random expression over `leaves` (Expr objects of this kernel)"""
+    if depth <= 0 or rng.random() < 0.15:
+        if rng.random() < 0.2:
+            return d.lift(rng.choice([0.5, 2.0, -1.5, 3.0, 0.25]))
+        return rng.choice(leaves)
+    sub = lambda: _expr(d, rng, leaves, cmp_leaves, depth - 1)
+    op = rng.choice(["add", "sub", "mul", "div", "neg", "sin", "cos", "exp", "sqrt", "ln", "pow", "select", "max", "min",
+                     "sq", "scale"])
+    if op == "add": return sub() + sub()
+    if op == "sub": return sub() - sub()
+    if op == "mul": return sub() * sub()
+    if op == "div":
+        den = sub()
+        return sub() / (den * den + 1.0)
+    if op == "neg": return -sub()
+    if op == "sin": return d.sin(sub())
+    if op == "cos": return d.cos(sub())
+    if op == "exp": return d.exp(d.sin(sub()))
+    if op == "sqrt":
+        e = sub()
+        return d.sqrt(e * e + 1.0)
+    if op == "ln":
+        e = sub()
+        return d.ln(e * e + 1.0)
+    if op == "pow":
+        e = sub()
+        return d.pow_(e * e + 1.0, rng.choice([1.5, 2.0, 0.5]))
+    if op == "select":
+        x, y = rng.choice(cmp_leaves), rng.choice(cmp_leaves)
+        cond = (x < y) if rng.random() < 0.5 else (x <= d.lift(rng.choice([0.0, 0.25, -0.5])))
+        return d.select(cond, sub(), sub())
+    if op == "max": return d.max_(rng.choice(cmp_leaves), rng.choice(cmp_leaves)) * sub()
+    if op == "min": return d.min_(rng.choice(cmp_leaves), rng.choice(cmp_leaves)) + sub()
+    if op == "sq": return d.sq(sub())
+    return sub() * rng.choice([0.5, 2.0, -1.0])
+
+
+def _through(rng, e, leaf):
+    """keep the chain differentiable: the kernel's value depends on `leaf` whatever the random tree picked"""
+    return e * leaf if rng.random() < 0.5 else e + leaf
+
+
+def random_net(d, L, seed, ct="gpu", depth=3):
+    """-> (graphs, description). Targets: out, loss, da, and train when a parameter was used."""
+    rng = random.Random(seed)
+    a = d.input("a", [-1, COLS]); b = d.input("b", [-1, COLS]); v = d.input("v", [COLS])
+    w = d.param([COLS, KOUT], name="w"); u = d.param([COLS], name="u")
+    cur, kind = a, "RC"      # RC: [R, C] like a and b; RK: [R, 5]; RS: [R, C - 2]; R: [R]; C: [C]
+    used_param = False
+    steps = []
+    for _ in range(rng.randint(2, 4)):
+        r = d.Fun()
+        if kind == "RC":
+            op = rng.choice(["raw", "row", "shift", "rowsum", "colsum", "contract", "bias"])
+        elif kind in ("RK", "RS"):
+            op = rng.choice(["raw1", "rowsum", "colsum"])
+        else:
+            op = "raw1"
+        steps.append(op)
+        if op == "raw":          # r{i} += E(cur{i}, b{i}, a{i})
+            it = d.Iter("it")
+            leaves = [cur.raw[it], b.raw[it]]
+            r.raw[it] += _through(rng, _expr(d, rng, leaves, [a.raw[it], b.raw[it]], depth), leaves[0])
+            r.copy_shape(cur)
+        elif op == "raw1":       # r{i} += E(cur{i})
+            it = d.Iter("it")
+            x = cur.raw[it]
+            r.raw[it] += _through(rng, _expr(d, rng, [x], [d.lift(0.5), d.lift(-0.25)], depth - 1), x)
+            r.copy_shape(cur)
+        elif op == "row":        # r[y, x] += E(cur[y, x], v[x], u[x])
+            y, x = d.Iter("y"), d.Iter("x")
+            leaves = [cur[y, x], v[x], u[x]]
+            r[y, x] += _through(rng, _expr(d, rng, leaves, [a[y, x], v[x]], depth), leaves[0])
+            used_param = True
+        elif op == "bias":       # two kernels writing one tensor (dnn.nim:19-24)
+            y, x = d.Iter("y"), d.Iter("x")
+            r[y, x] += cur[y, x] * v[x]
+            y, x = d.Iter("y"), d.Iter("x")
+            r[y, x] += u[x]
+            used_param = True
+        elif op == "shift":      # r[y, x] += E(cur[y, x + 1], cur[y, x + 2]): x stands alone only in the write, so its
+            # bounds follow r's inferred shape [R, C - 2] (a read cur[y, x] would bound x by C and run x + 1 off the row,
+            # in the reference too: passes.nim:1119-1180 takes the first access an iterator indexes alone)
+            y, x = d.Iter("y"), d.Iter("x")
+            r[y, x] += _through(rng, _expr(d, rng, [cur[y, x + 1], cur[y, x + 2]], [a[y, x + 1], b[y, x + 2]], depth - 1), cur[y, x + 1])
+            kind = "RS"
+        elif op == "rowsum":     # r[y] += E(cur[y, x])
+            y, x = d.Iter("y"), d.Iter("x")
+            r[y] += _through(rng, _expr(d, rng, [cur[y, x]], [d.lift(0.5), d.lift(-0.25)], depth - 1), cur[y, x])
+            kind = "R"
+        elif op == "colsum":     # r[x] += E(cur[y, x])
+            y, x = d.Iter("y"), d.Iter("x")
+            r[x] += _through(rng, _expr(d, rng, [cur[y, x]], [d.lift(0.5), d.lift(-0.25)], depth - 1), cur[y, x])
+            kind = "C"
+        else:                    # contraction r[y, k] += cur[y, x] * w[x, k]
+            y, k, x = d.Iter("y"), d.Iter("k"), d.Iter("x")
+            r[y, k] += cur[y, x] * w[x, k]
+            kind = "RK"
+            used_param = True
+        cur = r
+    loss = d.Fun(); it = d.Iter("it")
+    x = cur.raw[it]
+    loss[0] += _expr(d, rng, [x], [d.lift(0.5), d.lift(-0.25)], 2) * x
+    graphs = [cur.target("out", ct), loss.target("loss", ct), loss.backwards().grad(a).target("da", ct)]
+    if used_param:
+        graphs.append(loss.backprop(L.gradient_descent(0.05)).target("train", ct))
+    return graphs, " > ".join(steps)
+
+
+def random_inputs(np, seed, rows=7):
+    rng = np.random.default_rng(1000 + seed)
+    f = lambda *s: rng.uniform(-1, 1, s).astype(np.float32)
+    return {"a": f(rows, COLS), "b": f(rows, COLS), "v": f(COLS)}
+
+
+def random_params(np, seed):
+    rng = np.random.default_rng(2000 + seed)
+    return {"w": rng.uniform(-1, 1, (COLS, KOUT)).astype(np.float32), "u": rng.uniform(-1, 1, (COLS,)).astype(np.float32)}

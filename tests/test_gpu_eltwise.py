@@ -111,6 +111,32 @@ def test_bias_row_add_and_arithmetic(ctx):
     pm.free()
 
 
+@pytest.mark.parametrize("n_rows", [1, 33, 4096])
+def test_square_adjoint_reads_one_seed_element(ctx, n_rows):
+    """d[i] = s[k] * x[i] + s[k] * x[i] (derive of sq under a scalar loss, passes.nim:399-403) with the seed at a
+    non-zero offset of its tensor, on sizes with and without a 4-element tail: streaming kernel vs numpy (the same two
+    products and one addition in fp32) and vs the generic kernel."""
+    from exprgrad_b200 import frontend as F, model as M
+    rng = np.random.default_rng(n_rows)
+    x = rng.uniform(-2, 2, (n_rows, 63)).astype(np.float32)
+    s = rng.uniform(-2, 2, 4).astype(np.float32)
+
+    def net():
+        xi = F.input("x", [-1, 63]); si = F.input("s", [4])
+        r = F.Fun(); it = F.Iter("it")
+        r.raw[it] += si[2] * xi.raw[it] + xi.raw[it] * si[2]
+        r.copy_shape(xi)
+        return [r.target("y", "gpu")]
+    want = s[2] * x + s[2] * x
+    for elt in (1, 0):
+        pm = M.compile(*net(), gpu=ctx, seed=0)
+        pm.set_option("eltwise", elt)
+        got = pm.call("y", {"x": x, "s": s})
+        assert ("square-adjoint" in pm.describe_plan()) == bool(elt), pm.describe_plan()
+        assert np.array_equal(got, want), f"eltwise={elt}: max diff {np.abs(got - want).max()}"
+        pm.free()
+
+
 def test_sigmoid_head_runs_in_the_contraction_epilogue(ctx):
     """The xor net's sigmoid (examples/xor/xor.nim:20-28) and a tanh layer fuse into the contraction that feeds
     them, like relu / leakyRelu do; results match the unfused plan and the oracle."""

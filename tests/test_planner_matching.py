@@ -68,3 +68,25 @@ def test_transposed_and_strided_accesses_are_not_maps():
     assert _classify([PL.transpose(m).target("t", "gpu")], "t", {"m": [8, 16]}) == ["generic"]
     img = F.input("img", [-1, 8, 8, 2])
     assert _classify([PL.avgpool2(img).target("p", "gpu")], "p", {"img": [2, 8, 8, 2]}) == ["generic"]
+
+
+def _with_seed(expr_of, index=0):
+    from exprgrad_b200 import frontend as F
+    x = F.input("x", [-1, 64]); s = F.input("s", [4])
+    r = F.Fun(); it = F.Iter("it")
+    r.raw[it] += expr_of(x.raw[it], s[index])
+    r.copy_shape(x)
+    return [r.target("y", "gpu")]
+
+
+def test_fixed_element_operand_of_the_square_adjoint():
+    """derive() of sq(x) under a scalar loss multiplies the seed dL[0] into both products (passes.nim:399-403): the
+    seed is ONE element, whatever the order of the products' operands; every other form with a fixed-element
+    operand stays on the generic kernel."""
+    shapes = {"x": [32, 64], "s": [4]}
+    for f in (lambda x, s: s * x + s * x, lambda x, s: x * s + x * s, lambda x, s: s * x + x * s):
+        assert _classify(_with_seed(f), "y", shapes) == ["eltwise square-adjoint n=2048"]
+    assert _classify(_with_seed(lambda x, s: s * x + s * x, index=3), "y", shapes) == ["eltwise square-adjoint n=2048"]
+    assert _classify(_with_seed(lambda x, s: x * s), "y", shapes) == ["generic"]
+    assert _classify(_with_seed(lambda x, s: x + s), "y", shapes) == ["generic"]
+    assert _classify(_with_seed(lambda x, s: s * x + s * s), "y", shapes) == ["generic"]
