@@ -318,9 +318,31 @@ def target_symbol(name: str) -> str:
     return "target_" + hashlib.md5(name.encode()).hexdigest()[:12]
 
 
+_MARCH = None
+
+
+def native_march() -> str:
+    """What `-march=native` resolves to on this host. Built libraries are cached in the source tree and travel with
+    it (to the GPU box): the cache key names the instruction set they were compiled for, so a host with another CPU
+    rebuilds instead of loading code it cannot execute."""
+    global _MARCH
+    if _MARCH is None:
+        _MARCH = "unknown"
+        try:
+            out = subprocess.run(["gcc", "-march=native", "-Q", "--help=target"], capture_output=True, text=True).stdout
+            for line in out.splitlines():
+                parts = line.split()
+                if len(parts) == 2 and parts[0] == "-march=":
+                    _MARCH = parts[1]
+                    break
+        except OSError:
+            pass
+    return _MARCH
+
+
 def build(source: str, openmp: bool = True):
     os.makedirs(BUILD_DIR, exist_ok=True)
-    h = hashlib.sha1((source + str(openmp)).encode()).hexdigest()[:16]
+    h = hashlib.sha1((source + str(openmp) + native_march()).encode()).hexdigest()[:16]
     so = os.path.join(BUILD_DIR, f"oracle_{h}.so")
     if not os.path.exists(so):
         c = os.path.join(BUILD_DIR, f"oracle_{h}.c")
