@@ -572,7 +572,9 @@ struct StreamEvents {
 
 void run_row_stream(Model& model, Context& c, Plan& plan, const RowStream& rs, const Args& a, const void* const* data,
                     const int* on_device, char* out_host) {
-  static thread_local StreamEvents events;
+  // events belong to the device they were created on: one pool per device (a process may open several contexts)
+  static thread_local std::map<int, StreamEvents> events_by_device;
+  StreamEvents& events = events_by_device[c.device];
   for (auto& st : c.aux_stream)
     if (!st) EGB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   cudaStream_t h2d = c.aux_stream[0], d2h = c.aux_stream[1], comp = c.stream;

@@ -9,6 +9,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -82,6 +84,16 @@ constexpr int TRACE_SLOTS = 4096;
 enum KernelClass { KC_GEMM = 0, KC_SPLIT = 1, KC_FILL = 2, KC_INTERP = 3, KC_REDUCE = 4, KC_ELTWISE = 5,
                    KC_CONV = 6 /* conv2 forward */, KC_OTHER = 7, KC_CONV_DW = 8, KC_CONV_DIMG = 9,
                    KC_EXCHANGE = 10 /* data-parallel gradient exchange + optimizer */, KC_COUNT = 11 };
+
+// Function attributes (cudaFuncSetAttribute) belong to the CURRENT device: a process that opens contexts on several
+// devices has to set them once per device, not once per process. True the first time `key` (a kernel's address, or any
+// address that is unique to the call site) is seen on the context's device.
+inline bool first_use_on_device(const Context& ctx, const void* key) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert(std::make_pair(ctx.device, key)).second;
+}
 
 // Kernel launch through cudaLaunchKernelEx so that the PDL attribute can be attached.
 template <typename... KArgs, typename... Args>

@@ -266,11 +266,8 @@ void launch_kind(Context& ctx, const EltArgs& a, cudaStream_t st) {
       // that trickles in while its predecessor's CTAs retire; an (unused) dynamic shared memory request of a third
       // of the SM's capacity bounds the residency at three.
       static const int smem = getenv("EGB_ELT_SCALAR_SMEM") ? atoi(getenv("EGB_ELT_SCALAR_SMEM")) : ELT_SCALAR_SMEM;
-      static bool attr_set = false;
-      if (smem > 48 * 1024 && !attr_set) {
+      if (smem > 48 * 1024 && first_use_on_device(ctx, (const void*)elt_stream_kernel<KIND, ELT_UNROLL, 1>))
         EGB_CUDA(cudaFuncSetAttribute(elt_stream_kernel<KIND, ELT_UNROLL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-      }
       launch_kernel(ctx, elt_stream_kernel<KIND, ELT_UNROLL, 1>, dim3((unsigned)blocks), dim3(ELT_THREADS), (size_t)smem, st, a);
       return;
     }

@@ -794,11 +794,8 @@ bool launch_gemm_lat(Context& ctx, const GemmArgs& a, cudaStream_t st) {
     case EPI_TANH: fn = gemm_lat_kernel<EPI_TANH>; break;
     default: fail(EGB_ERR_GPU, "gemm: unknown second-stage mode %d", a.epi);
   }
-  static std::map<KernelFn, bool> attr_done;
-  if (!attr_done.count(fn)) {
+  if (first_use_on_device(ctx, (const void*)fn))
     EGB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_done[fn] = true;
-  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);

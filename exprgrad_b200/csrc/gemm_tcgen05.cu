@@ -870,11 +870,8 @@ void launch_gemm_bf16x3(Context& ctx, const GemmArgs& a, cudaStream_t st) {
       default: fail(EGB_ERR_GPU, "gemm: unknown second-stage mode %d", a.epi);
     }
   }
-  static std::set<KernelFn> attr_done;
-  if (!attr_done.count(fn)) {
+  if (first_use_on_device(ctx, (const void*)fn))
     EGB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_done.insert(fn);
-  }
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -349,11 +349,8 @@ void launch_gemm_bf16x3_2cta(Context& ctx, const GemmArgs& a, cudaStream_t st) {
   encode_kmajor(ctx, &tm_b_hi, a.b_hi, a.N, a.K, a.ldb);
   encode_kmajor(ctx, &tm_b_mid, a.b_mid, a.N, a.K, a.ldb);
   const size_t smem = 1024 + (size_t)STAGES2 * STAGE_BYTES + (2 * STAGES2 + 4) * 8 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(ctx, (const void*)gemm_bf16x3_2cta_kernel))
     EGB_CUDA(cudaFuncSetAttribute(gemm_bf16x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   const int tiles = p.tiles_m * p.tiles_n;
   int pairs = ctx.sm_count / 2;
   if (pairs > tiles) pairs = tiles;

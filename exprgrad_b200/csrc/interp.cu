@@ -622,11 +622,8 @@ void launch_interp_rowchain(Context& ctx, const IpProgram* dev_progs, int nprogs
   {
     Launch l(ctx, KC_INTERP, st);
     const size_t smem = (size_t)nprogs * sizeof(IpProgram) + (size_t)max_slots * IP_THREADS * sizeof(Slot);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(ctx, (const void*)interp_rowchain_kernel))
       EGB_CUDA(cudaFuncSetAttribute(interp_rowchain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
-    }
     launch_kernel(ctx, interp_rowchain_kernel, dim3((int)(nb < cap ? nb : cap)), dim3(IP_THREADS), smem, st, dev_progs, nprogs,
                   rows);
   }
@@ -652,12 +649,10 @@ void launch_interp(Context& ctx, const IpProgram& prog, int pb, int rb, int poin
   if (prog.vec4 && !strict) {
     const bool smem_slots = prog.nslots <= 24;   // 24 slots x 256 threads x 16 B = 96 KB
     const size_t smem = smem_slots ? (size_t)prog.nslots * IP_THREADS * sizeof(V4) : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(ctx, (const void*)interp_vec4_kernel<true>)) {
       EGB_CUDA(cudaFuncSetAttribute(interp_vec4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       EGB_CUDA(cudaFuncSetAttribute(interp_vec4_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       EGB_CUDA(cudaFuncSetAttribute(interp_vec4_pointsum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
     }
     if (prog.vec4 == 1) {
       const int64_t row_len = prog.loops[prog.npar - 1].count;
