@@ -134,3 +134,54 @@ def random_inputs(np, seed, rows=7):
 def random_params(np, seed):
     rng = np.random.default_rng(2000 + seed)
     return {"w": rng.uniform(-1, 1, (COLS, KOUT)).astype(np.float32), "u": rng.uniform(-1, 1, (COLS,)).astype(np.float32)}
+
+
+def random_cnn(d, L, seed, ct="gpu"):
+    """Random composition of the reference's layer library (layers/dnn.nim:19-100, base.nim:37-67) - CPU-tier passes
+    parity only: conv2 / activations / max- and average pooling (customGrad, strided and divided indices) / upsample
+    (`withShape`) / dropout (`TensorRandom`) / reshape generator / dense / softmax, a loss and an optimizer (adam adds
+    caches and `epoch()`). -> (graphs, description, input shapes)."""
+    rng = random.Random(10_000 + seed)
+    side = rng.choice([8, 12, 16])
+    chans = rng.choice([1, 3])
+    x = d.input("x", [-1, side, side, chans])
+    cur, h, c = x, side, chans
+    steps = []
+    for _ in range(rng.randint(1, 4)):
+        op = rng.choice(["conv", "act", "maxpool", "avgpool", "upsample", "dropout"])
+        if op == "conv" and h >= 5:
+            k = rng.choice([3, 3, 5]) if h >= 7 else 3
+            f = rng.choice([2, 4])
+            cur = L.conv2_layer(cur, c, k, k, f); h, c = h - k + 1, f
+        elif op == "act":
+            cur = getattr(L, rng.choice(["relu", "leaky_relu", "sigmoid", "tanh"]))(cur)
+        elif op == "maxpool" and h >= 4 and h % 2 == 0:
+            cur = L.maxpool2(cur); h //= 2
+        elif op == "avgpool" and h >= 4 and h % 2 == 0:
+            cur = L.avgpool2(cur); h //= 2
+        elif op == "upsample" and h <= 8:
+            cur = L.upsample2(cur); h *= 2
+        elif op == "dropout":
+            cur = L.dropout(cur, 0.25)
+        else:
+            continue
+        steps.append(op)
+    flat = h * h * c
+    cur = cur.reshape([-1, flat])
+    hidden = rng.choice([0, 8])
+    if hidden:
+        cur = L.relu(L.dense(cur, flat, hidden)); flat = hidden
+    outs = rng.choice([1, 4])
+    logits = L.dense(cur, flat, outs)
+    y = d.input("y", [-1, outs])
+    head = rng.choice(["softmax", "sigmoid", "none"]) if outs > 1 else rng.choice(["sigmoid", "none"])
+    if head == "softmax":
+        p = L.softmax(logits); loss = L.cross_entropy(p, y)
+    elif head == "sigmoid":
+        p = L.sigmoid(logits); loss = rng.choice([L.binary_cross_entropy, L.mse])(p, y)
+    else:
+        p = logits; loss = L.mse(p, y)
+    opt = L.adam(0.01) if rng.random() < 0.5 else L.gradient_descent(0.05)
+    steps += [f"reshape[{flat}]", head, "adam" if "adam" in repr(opt) or opt.__qualname__.startswith("adam") else "sgd"]
+    graphs = [p.target("predict", ct), loss.target("loss", ct), loss.backprop(opt).target("train", ct)]
+    return graphs, " > ".join(steps), {"x": [rng.choice([1, 5]), side, side, chans], "y": None, "outs": outs}

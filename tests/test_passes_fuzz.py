@@ -51,3 +51,44 @@ def test_random_graph_shapes_bit_exact(seed, rows):
         for tid in sorted(want):
             got = prog.infer_shapes(target, used, tensor_id=tid)
             assert got == list(want[tid]), f"{what} / {target}: tensor{tid - 1}: oracle {want[tid]} vs library {got}"
+
+
+CNN_SEEDS = list(range(60))
+
+
+def _build_cnn(seed):
+    import oracle as o
+    from oracle import layers as OL
+    from oracle.passes import compile_program
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    ographs, what, shapes = FG.random_cnn(o, OL, seed)
+    oprog = o.ir.to_program(ographs)
+    compile_program(oprog)
+    pgraphs, what2, _ = FG.random_cnn(F, PL, seed)
+    assert what == what2
+    prog = Program.from_graphs(pgraphs).compile()
+    return o, oprog, F, prog, what, shapes
+
+
+@pytest.mark.parametrize("seed", CNN_SEEDS)
+def test_random_layer_stack_compiles_to_the_same_program_and_shapes(seed):
+    """Random stacks of the reference's layers (customGrad pooling, `withShape` upsampling, dropout's random tensor,
+    the reshape generator, adam's caches and epoch()): token-identical compiled programs, bit-exact shapes."""
+    from oracle.passes import infer_shapes
+    o, oprog, F, prog, what, shapes = _build_cnn(seed)
+    want = _tokens(F.serialize(oprog, compiled=True))
+    got = _tokens(prog.serialize())
+    if "grads" in got:
+        i = len(got) - 1 - got[::-1].index("grads")
+        got = got[:i] + got[-1:]
+    assert len(want) == len(got), what
+    for i, (x, y) in enumerate(zip(want, got)):
+        assert x == y, f"{what}: token {i}: oracle {want[max(0, i - 8):i + 4]} vs library {got[max(0, i - 8):i + 4]}"
+    inputs = {"x": shapes["x"], "y": [shapes["x"][0], shapes["outs"]]}
+    for target in oprog.targets:
+        used = {k: v for k, v in inputs.items() if oprog.inputs.get(k) in oprog.targets[target].tensors}
+        want_shapes = infer_shapes(oprog, target, {oprog.inputs[k]: v for k, v in used.items()})
+        for tid in sorted(want_shapes):
+            got_shape = prog.infer_shapes(target, used, tensor_id=tid)
+            assert got_shape == list(want_shapes[tid]), f"{what} / {target}: tensor{tid - 1}: {want_shapes[tid]} vs {got_shape}"

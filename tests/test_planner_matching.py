@@ -90,3 +90,39 @@ def test_fixed_element_operand_of_the_square_adjoint():
     assert _classify(_with_seed(lambda x, s: x * s), "y", shapes) == ["generic"]
     assert _classify(_with_seed(lambda x, s: x + s), "y", shapes) == ["generic"]
     assert _classify(_with_seed(lambda x, s: s * x + s * s), "y", shapes) == ["generic"]
+
+
+def _classify_dropping_unused(prog, target, shapes):
+    """inputs a random graph did not end up using are not inputs of the model (model.nim:395-396)"""
+    shapes = dict(shapes)
+    while True:
+        try:
+            return prog.classify(target, shapes)
+        except Exception as e:
+            if "is not an input to the model" not in str(e):
+                raise
+            del shapes[str(e).split()[0]]
+
+
+def test_every_kernel_of_random_graphs_gets_a_class():
+    """The matchers (contraction, conv2, map forms) look at arbitrary kernels - random expression trees, shifted and
+    strided reads, customGrad adjoints, several writers of one tensor - and must answer, never throw."""
+    import fuzz_graphs as FG
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    seen = set()
+    for seed in range(60):
+        graphs, what = FG.random_net(F, PL, seed)
+        prog = Program.from_graphs(graphs).compile()
+        for target in ("out", "loss", "da"):
+            got = _classify_dropping_unused(prog, target, {"a": [7, FG.COLS], "b": [7, FG.COLS], "v": [FG.COLS]})
+            assert got and all(isinstance(g, str) and g for g in got), (seed, what, target)
+            seen.update(g.split(" ")[0] for g in got)
+    for seed in range(30):
+        graphs, what, sh = FG.random_cnn(F, PL, seed)
+        prog = Program.from_graphs(graphs).compile()
+        for target in ("predict", "loss", "train"):
+            got = prog.classify(target, {"x": sh["x"], "y": [sh["x"][0], sh["outs"]]})
+            assert got and all(isinstance(g, str) and g for g in got), (seed, what, target)
+            seen.update(g.split(" ")[0] for g in got)
+    assert {"generic", "eltwise", "contraction", "conv2"} <= seen
