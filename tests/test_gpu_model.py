@@ -550,13 +550,15 @@ def test_device_api_compile_arg_run(ctx):
     c = F.Fun(); y, x, it = F.Iter("y"), F.Iter("x"), F.Iter("it")
     c[y, x] += F.input("a")[y, it] * F.input("b")[it, x]
     got = run(c.target("c", "gpu"), "c", [a, b, np.zeros((64, 64), np.float32)])
-    assert float(((got - a @ b) ** 2).sum()) < 0.1
+    assert float(((got - a @ b) ** 2).sum()) < 0.1                                    # the reference's own bound
+    assert_close(got, a.astype(np.float64) @ b.astype(np.float64), what="device API matmul")   # 1e-4
 
     img = rng.uniform(0, 1, (68,)).astype(np.float32); fil = rng.uniform(-1, 1, (5,)).astype(np.float32)
     r = F.Fun(); x, dx = F.Iter("x"), F.Iter("dx")
     r[x] += F.input("image")[x + dx] * F.input("filter")[dx]
     got = run(r.target("res", "gpu"), "res", [img, fil, np.zeros((64,), np.float32)])
     assert float(((got - np.correlate(img, fil, "valid")) ** 2).sum()) < 0.1
+    assert_close(got, np.correlate(img.astype(np.float64), fil.astype(np.float64), "valid"), tol=1e-5, what="device API conv1")
 
     xs = np.array([[1, 2, -1], [-2, 0, 3]], np.float32)
     yv = F.Fun(); it = F.Iter("it"); xin = F.input("x")
