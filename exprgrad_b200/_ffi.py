@@ -85,6 +85,7 @@ _SIGS = {
     "egb_program_serialize": (I, [P, P, SZ, ctypes.POINTER(SZ)]),
     "egb_program_describe": (I, [P, S, P, SZ, ctypes.POINTER(SZ)]),
     "egb_program_classify": (I, [P, S, I, ctypes.POINTER(S), PI, PI64, P, SZ, ctypes.POINTER(SZ)]),
+    "egb_program_lower_dump": (I, [P, S, I, ctypes.POINTER(S), PI, PI64, I, I64, P, SZ, ctypes.POINTER(SZ)]),
     "egb_program_free": (I, [P]),
     "egb_program_tensor_count": (I, [P, PI]),
     "egb_program_tensor_info": (I, [P, I, PI, PI, PI64, P, SZ]),

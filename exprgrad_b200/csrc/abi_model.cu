@@ -134,6 +134,64 @@ int egb_program_classify(egb_program* p, const char* target, int n_args, const c
   EGB_CATCH
 }
 
+// The device program of every IR kernel of a target, as text (host only: shape inference + lower.cpp). What the generic
+// loop-nest kernel (interp.cu) would execute is DATA - loops, flattened affine accesses, a register program, literals -
+// so it can be checked without a device: tests/test_lowering_cpu.py runs these programs with an independent
+// interpreter and compares the results with the oracle. Tensor bases are written as tensor ids. One JSON object per line.
+int egb_program_lower_dump(egb_program* p, const char* target, int n_args, const char* const* names, const int* ranks,
+                           const int64_t* dims, int strict, int64_t epoch, char* buf, size_t cap, size_t* needed) {
+  EGB_TRY
+  Program& prog = *p->p;
+  if (!prog.compiled) compile_program(prog);
+  Target* t = prog.find_target(target);
+  if (!t) fail(EGB_ERR_RUNTIME, "%s is not a target of the model", target);
+  Args a = resolve_args(prog, n_args, names, ranks, dims);
+  ShapeTable in;
+  for (size_t i = 0; i < a.ids.size(); ++i) in[a.ids[i]] = a.shapes[i];
+  ShapeTable shapes = infer_shapes(prog, *t, in);
+  for (int id : prog.params) shapes[id] = prog.tdef(id).shape;
+  for (int id : prog.caches) shapes[id] = prog.tdef(id).shape;
+  std::map<int, void*> ptrs;
+  for (auto& kv : shapes) ptrs[kv.first] = reinterpret_cast<void*>((uintptr_t)kv.first << 32);
+  auto num = [](int64_t v) { return std::to_string((long long)v); };
+  auto op_text = [&](const IpTensorOp& op) {
+    std::string s = "{\"tensor\":" + num((int64_t)(op.base >> 32)) + ",\"offset\":" + num(op.offset) + ",\"dst\":" + num(op.dst) +
+                    ",\"terms\":[";
+    for (int q = 0; q < op.nterms; ++q) s += std::string(q ? "," : "") + "[" + num(op.slot[q]) + "," + num(op.coef[q]) + "]";
+    return s + "]}";
+  };
+  auto instrs_text = [&](const IpInstr* ins, int n) {
+    std::string s = "[";
+    for (int q = 0; q < n; ++q)
+      s += std::string(q ? "," : "") + "[" + num(ins[q].op) + "," + num(ins[q].dst) + "," + num(ins[q].a) + "," + num(ins[q].b) +
+           "," + num(ins[q].c) + "," + num(ins[q].imm) + "]";
+    return s + "]";
+  };
+  std::string s;
+  for (size_t ki = 0; ki < t->kernels.size(); ++ki) {
+    const Kernel& k = *t->kernels[ki];
+    if (k.is_generator()) fail(EGB_ERR_GENERATOR, "program still contains generator kernels; compile it first");
+    // every kernel accumulates into its (zero-initialised) result, like the reference before InstrOverwrite
+    Lowered lw = lower_kernel(k, shapes, ptrs, epoch, strict != 0, false, 148);
+    const IpProgram& ip = lw.ip;
+    s += "{\"kernel\":" + num((int64_t)ki) + ",\"npar\":" + num(ip.npar) + ",\"npoints\":" + num(ip.npoints) + ",\"nred\":" + num(ip.nred) +
+         ",\"accumulate\":" + num(ip.accumulate) + ",\"scatter\":" + num(ip.scatter) + ",\"nslots\":" + num(ip.nslots) + ",\"loops\":[";
+    for (int q = 0; q < ip.nloops; ++q)
+      s += std::string(q ? "," : "") + "[" + num(ip.loops[q].start) + "," + num(ip.loops[q].step) + "," + num(ip.loops[q].count) + "," +
+           num(ip.loops[q].slot) + "]";
+    s += "],\"lits\":[";
+    for (int q = 0; q < ip.nlits; ++q) s += std::string(q ? "," : "") + "[" + num(ip.lit_slot[q]) + ",\"" + std::to_string((unsigned long long)ip.lits[q]) + "\"]";
+    s += "],\"array_table\":[";
+    for (int q = 0; q < 64; ++q) s += std::string(q ? "," : "") + num(ip.array_table[q]);
+    s += "],\"index_instrs\":" + instrs_text(ip.index_instrs, ip.nindex_instrs) + ",\"instrs\":" + instrs_text(ip.instrs, ip.ninstrs) +
+         ",\"reads\":[";
+    for (int q = 0; q < ip.nreads; ++q) s += std::string(q ? "," : "") + op_text(ip.reads[q]);
+    s += "],\"write\":" + op_text(ip.write) + "}\n";
+  }
+  copy_out(s, buf, cap, needed);
+  EGB_CATCH
+}
+
 int egb_program_free(egb_program* p) {
   EGB_TRY
   delete p;

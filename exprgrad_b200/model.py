@@ -57,6 +57,18 @@ class Program:
                                        need.value, ctypes.byref(need)))
         return [line.split(": ", 1)[1] for line in buf.value.decode().splitlines()]
 
+    def lower_dump(self, target: str, input_shapes: Dict[str, Sequence[int]], strict: bool = True, epoch: int = 0) -> List[dict]:
+        """The device program of every IR kernel of `target` (host only; see egb_program_lower_dump)."""
+        import json
+        names, ranks, dims = _pack_shapes(input_shapes)
+        need = ctypes.c_size_t(0)
+        check(lib.egb_program_lower_dump(self.handle, target.encode(), len(input_shapes), names, ranks, dims, int(strict), epoch,
+                                         None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        check(lib.egb_program_lower_dump(self.handle, target.encode(), len(input_shapes), names, ranks, dims, int(strict), epoch,
+                                         buf, need.value, ctypes.byref(need)))
+        return [json.loads(line) for line in buf.value.decode().splitlines()]
+
     def tensor_count(self) -> int:
         n = ctypes.c_int(0)
         check(lib.egb_program_tensor_count(self.handle, ctypes.byref(n)))

@@ -192,6 +192,14 @@ int egb_program_describe(egb_program* program, const char* target, char* buf, si
  * forms of layers/base.nim and layers/dnn.nim) or "generic" (the loop-nest kernel). Host only. */
 int egb_program_classify(egb_program* program, const char* target, int n_args, const char* const* names,
                          const int* ranks, const int64_t* dims, char* buf, size_t cap, size_t* needed);
+/* The device program of every IR kernel of `target` at the given input shapes, one JSON object per line (host only):
+ * loops (independent ones first), flattened affine accesses with tensor ids in place of addresses, the register
+ * program and its literal pool - what the generic loop-nest kernel interprets for a kernel no specialised device kernel
+ * takes (the role of the OpenCL source exprgrad/clgen.nim:74-257 prints). `strict` as in egb_model_set_option. The
+ * tests execute these programs with an independent interpreter to check the lowering without a device. */
+int egb_program_lower_dump(egb_program* program, const char* target, int n_args, const char* const* names,
+                           const int* ranks, const int64_t* dims, int strict, int64_t epoch, char* buf, size_t cap,
+                           size_t* needed);
 int egb_program_free(egb_program* program);
 int egb_program_tensor_count(egb_program* program, int* count);
 /* kind: 0 result, 1 input, 2 param, 3 cache, 4 random (exprgrad/ir.nim:222-233). dims has room for

@@ -1,0 +1,123 @@
+"""CPU-only: what csrc/lower.cpp hands to the generic loop-nest kernel, executed by an independent sequential
+interpreter (tests/ip_interp.py) and compared with the oracle - on the reference-shaped graphs and on seeded random
+ones. Checks the lowering (loop partition, flattened accesses, index arithmetic for `y div 2`-style
+indices, register program, literal pool, f64 constant folding like passes.nim:1656-1706) without a device; the device
+kernel that interprets the same programs is compared with the same oracle in the GPU tier."""
+import numpy as np
+import pytest
+
+import fuzz_graphs as FG
+import graphs as G
+from ip_interp import run_target
+from parity_cases import norm_err
+
+# the same operations in the same order as the oracle; numpy's fp32 sin / exp / log / pow may differ from glibc's in
+# the last ulp, and an ill-conditioned random graph amplifies that like any rounding (bound scales with the oracle's own
+# fp32-vs-float64 difference, as in tests/test_gpu_fuzz.py)
+TOL = 2e-6
+
+
+def _oracle(graph_fn, seed_params, inputs, scalar="float32"):
+    import oracle as o
+    from oracle import layers as OL
+    om = o.compile(*graph_fn(o, OL), scalar=scalar, seed=1, openmp=False)
+    return om
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("seed", list(range(0, 36)))
+def test_random_graph_lowering_matches_oracle(seed, strict):
+    if not strict and seed % 3:
+        pytest.skip("the non-strict lowering (loop merging, fast-path flags) runs on every third graph")
+    import oracle as o
+    from oracle import layers as OL
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    res = {}
+    for scalar in ("float32", "float64"):
+        graphs, what = FG.random_net(o, OL, seed, ct="cpu")
+        om = o.compile(*graphs, scalar=scalar, seed=0, openmp=False)
+        inputs = {k: v for k, v in FG.random_inputs(np, seed, rows=4).items() if k in om.program.inputs}
+        names = {om.program.tdef(t).name: t for t in om.params}
+        for k, v in FG.random_params(np, seed).items():
+            if k in names:
+                om.params[names[k]][...] = v
+        out = {t: np.array(om.call(t, inputs)) for t in om.program.targets if t != "train"}
+        if "train" in om.program.targets:
+            om.apply("train", inputs)
+            for tid in sorted(om.params):
+                out[f"param{tid}"] = np.array(om.params[tid])
+        res[scalar] = out
+    ref, ref64 = res["float32"], res["float64"]
+    prog = Program.from_graphs(FG.random_net(F, PL, seed)[0]).compile()
+    params = FG.random_params(np, seed)
+    state0 = {tid: params[k].copy() for k, tid in names.items()}
+    for t in sorted(ref):
+        if t.startswith("param"):
+            continue
+        got = run_target(prog, t, inputs, dict(state0), strict=strict)
+        _compare(got, ref[t], ref64[t], f"seed {seed} ({what}) target {t} strict={strict}")
+    if any(t.startswith("param") for t in ref):
+        state = {tid: v.copy() for tid, v in state0.items()}
+        run_target(prog, "train", inputs, state, strict=strict)
+        for tid in state:
+            _compare(state[tid], ref[f"param{tid}"], ref64[f"param{tid}"], f"seed {seed} ({what}) param{tid} strict={strict}")
+
+
+def _compare(got, ref, ref64, what):
+    if not np.any(ref64):
+        assert not np.any(got), what + ": expected zeros"
+        return
+    cond = norm_err(ref, ref64)
+    e = norm_err(got, ref)
+    assert e <= max(TOL, 10 * cond), f"{what}: normalised max error {e:.2e} (conditioning {cond:.1e})"
+
+
+def test_reference_shaped_graphs_lowering_matches_oracle():
+    """dense step (contractions, bias, relu, softmax + crossEntropy, SGD), conv2 forward / d_filters / d_images (scatter
+    accumulate), conv + leakyRelu + maxpool (customGrad, `y div 2` indices) + reshape + adam with epoch()."""
+    import oracle as o
+    from oracle import layers as OL
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    # dense step
+    sizes = (6, 5, 4, 3)
+    om = o.compile(*G.dense_net(o, OL, sizes, ct="cpu"), seed=1, openmp=False)
+    x, y, params = G.dense_inputs(5, sizes)
+    tids = sorted(om.params)
+    for i, tid in enumerate(tids):
+        om.params[tid][...] = params[i]
+    prog = Program.from_graphs(G.dense_net(F, PL, sizes)).compile()
+    state = {tid: params[i].copy() for i, tid in enumerate(tids)}
+    assert norm_err(run_target(prog, "predict", {"x": x}, dict(state)), om.call("predict", {"x": x})) <= TOL
+    assert norm_err(run_target(prog, "loss", {"x": x, "y": y}, dict(state)), om.call("loss", {"x": x, "y": y})) <= TOL
+    om.apply("train", {"x": x, "y": y})
+    run_target(prog, "train", {"x": x, "y": y}, state)
+    for tid in tids:
+        assert norm_err(state[tid], om.params[tid]) <= TOL, f"dense param tensor{tid - 1}"
+    # conv2: no libm call anywhere -> bit for bit
+    om = o.compile(*G.conv2_net(o, OL, ct="cpu"), seed=1, openmp=False)
+    w = np.random.default_rng(1).uniform(-2, 2, (4, 3, 3, 3)).astype(np.float32)
+    tid = sorted(om.params)[0]
+    om.params[tid][...] = w
+    img = np.random.default_rng(0).uniform(0, 1, (2, 6, 5, 3)).astype(np.float32)
+    prog = Program.from_graphs(G.conv2_net(F, PL)).compile()
+    for t in ("conv", "loss", "dw", "dimg"):
+        got = run_target(prog, t, {"img": img}, {tid: w.copy()})
+        assert np.array_equal(got, om.call(t, {"img": img})), f"conv2 {t}"
+    # fashion net, adam, two epochs
+    om = o.compile(*G.fashion_net(o, OL, ct="cpu"), seed=1, openmp=False)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 1, (3, 12, 12, 1)).astype(np.float32)
+    y = np.zeros((3, 10), np.float32); y[np.arange(3), rng.integers(0, 10, 3)] = 1
+    prog = Program.from_graphs(G.fashion_net(F, PL)).compile()
+    state = {tid: np.array(v) for tid, v in om.params.items()}
+    state.update({tid: np.array(v) for tid, v in om.caches.items()})
+    for epoch in (1, 2):
+        om.epoch = epoch
+        om.apply("train", {"x": x, "y": y})
+        run_target(prog, "train", {"x": x, "y": y}, state, epoch=epoch)
+    for tid in om.params:
+        assert norm_err(state[tid], om.params[tid]) <= 1e-5, f"adam param tensor{tid - 1}"
+    for tid in om.caches:
+        assert norm_err(state[tid], om.caches[tid]) <= 1e-5, f"adam cache tensor{tid - 1}"
