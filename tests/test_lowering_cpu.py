@@ -121,3 +121,45 @@ def test_reference_shaped_graphs_lowering_matches_oracle():
         assert norm_err(state[tid], om.params[tid]) <= 1e-5, f"adam param tensor{tid - 1}"
     for tid in om.caches:
         assert norm_err(state[tid], om.caches[tid]) <= 1e-5, f"adam cache tensor{tid - 1}"
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_random_layer_stack_lowering_matches_oracle(seed):
+    """Random stacks of the reference's layers (tests/fuzz_graphs.py random_cnn): strided and divided indices of the
+    pooling layers, the customGrad adjoint of maxpool2, `withShape` upsampling, the reshape generator, adam's caches and
+    epoch() - one train step through the lowered programs against the oracle."""
+    import oracle as o
+    from oracle import layers as OL
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    graphs, what, sh = FG.random_cnn(o, OL, seed, ct="cpu")
+    if "dropout" in what:
+        pytest.skip("dropout draws a random tensor per call (model.nim:310-314): nothing to compare element-wise")
+    rng = np.random.default_rng(seed)
+    n = 2
+    x = rng.uniform(0, 1, [n] + sh["x"][1:]).astype(np.float32)
+    y = rng.uniform(0.1, 0.9, (n, sh["outs"])).astype(np.float32)
+    res = {}
+    for scalar in ("float32", "float64"):
+        om = o.compile(*FG.random_cnn(o, OL, seed, ct="cpu")[0], scalar=scalar, seed=3, openmp=False)
+        out = {"predict": np.array(om.call("predict", {"x": x})), "loss": np.array(om.call("loss", {"x": x, "y": y}))}
+        start = {tid: np.array(v, np.float32) for tid, v in om.params.items()}
+        om.epoch = 1
+        om.apply("train", {"x": x, "y": y})
+        for tid in om.params:
+            out[f"param{tid}"] = np.array(om.params[tid])
+        for tid in om.caches:
+            out[f"cache{tid}"] = np.array(om.caches[tid])
+        res[scalar] = (out, start, sorted(om.caches))
+    (ref, start, cache_ids), (ref64, _, _) = res["float32"], res["float64"]
+    prog = Program.from_graphs(FG.random_cnn(F, PL, seed)[0]).compile()
+    state = {tid: v.copy() for tid, v in start.items()}
+    for tid in cache_ids:
+        state[tid] = np.zeros(prog.tensor_info(tid)["shape"], np.float32)
+    _compare(run_target(prog, "predict", {"x": x}, dict(state)), ref["predict"], ref64["predict"], f"cnn {seed} ({what}) predict")
+    _compare(run_target(prog, "loss", {"x": x, "y": y}, dict(state)), ref["loss"], ref64["loss"], f"cnn {seed} ({what}) loss")
+    run_target(prog, "train", {"x": x, "y": y}, state, epoch=1)
+    for tid in start:
+        _compare(state[tid], ref[f"param{tid}"], ref64[f"param{tid}"], f"cnn {seed} ({what}) param tensor{tid - 1}")
+    for tid in cache_ids:
+        _compare(state[tid], ref[f"cache{tid}"], ref64[f"cache{tid}"], f"cnn {seed} ({what}) cache tensor{tid - 1}")
