@@ -186,7 +186,31 @@ int egb_program_lower_dump(egb_program* p, const char* target, int n_args, const
     s += "],\"index_instrs\":" + instrs_text(ip.index_instrs, ip.nindex_instrs) + ",\"instrs\":" + instrs_text(ip.instrs, ip.ninstrs) +
          ",\"reads\":[";
     for (int q = 0; q < ip.nreads; ++q) s += std::string(q ? "," : "") + op_text(ip.reads[q]);
-    s += "],\"write\":" + op_text(ip.write) + "}\n";
+    s += "],\"write\":" + op_text(ip.write);
+    // what the planner's matchers make of this kernel (the same order as the planner: contraction, conv2, map form):
+    // the operands and constants a specialised device kernel would be launched with
+    GemmPattern g;
+    ConvPattern cv;
+    EltSpec es;
+    if (match_gemm(k, shapes, g)) {
+      s += ",\"gemm\":{\"a\":" + num(g.a_tensor) + ",\"b\":" + num(g.b_tensor) + ",\"c\":" + num(g.c_tensor) + ",\"ta\":" + num(g.trans_a) +
+           ",\"tb\":" + num(g.trans_b) + ",\"M\":" + num(g.M) + ",\"N\":" + num(g.N) + ",\"K\":" + num(g.K) + ",\"lda\":" + num(g.lda) +
+           ",\"ldb\":" + num(g.ldb) + ",\"ldc\":" + num(g.ldc) + "}";
+    } else if (match_conv2(k, shapes, cv)) {
+      s += ",\"conv2\":{\"kind\":" + num((int)cv.kind) + ",\"img\":" + num(cv.img_tensor) + ",\"fil\":" + num(cv.fil_tensor) + ",\"out\":" +
+           num(cv.out_tensor) + ",\"N\":" + num(cv.N) + ",\"H\":" + num(cv.H) + ",\"W\":" + num(cv.W) + ",\"C\":" + num(cv.C) + ",\"F\":" +
+           num(cv.F) + ",\"KH\":" + num(cv.KH) + ",\"KW\":" + num(cv.KW) + "}";
+    } else if (match_eltwise(k, shapes, es)) {
+      char lit[160];
+      snprintf(lit, sizeof(lit), "[%.17g,%.17g,%.17g,%.17g]", es.lit[0], es.lit[1], es.lit[2], es.lit[3]);
+      s += std::string(",\"eltwise\":{\"form\":\"") + elt_kind_name(es.kind) + "\",\"n\":" + num(es.n) + ",\"row\":" + num(es.row) +
+           ",\"uses_epoch\":" + num(es.uses_epoch) + ",\"lit\":" + lit + ",\"reads\":[";
+      for (int q = 0; q < es.nreads; ++q)
+        s += std::string(q ? "," : "") + "{\"tensor\":" + num(es.read_tensor[q]) + ",\"row\":" + num(es.row_read[q]) + ",\"scalar\":" +
+             num(es.scalar_read[q]) + ",\"offset\":" + num(es.scalar_offset[q]) + "}";
+      s += "]}";
+    }
+    s += "}\n";
   }
   copy_out(s, buf, cap, needed);
   EGB_CATCH
