@@ -300,7 +300,7 @@ def run_matmul(args, ctx, timer, rank, world, sampler, cpu_check=True):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16x3_2cta_kernel (cta_group::2 tcgen05, 256x256 pair tiles)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": 390.0e6, "traffic_source": "profiles/r01l_ncu_full.txt (dram read+write per launch: 336 + 54 MB)",
+                     "traffic": 379.0e6, "traffic_source": "profiles/r02z_matmul_2cta_ncu.txt (dram read + write per launch: 323.6 + 55.3 MB; algorithmic 201 MB)",
                      "passes": passes, "algorithmic_tflops": flop / t_kernel / 1e12, "kernel_ms": t_kernel * 1e3,
                      "kernel_share_of_step": k_ms / max(all_ms, 1e-9),
                      "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a %.0f ms back-to-back region)" % ms
@@ -543,7 +543,12 @@ def run_conv2(args, ctx, timer, rank, world, cpu=True):
            "kernels_ms": kern,
            "roofline": {"bound": "hbm", "kernel": "conv2_fwd_tc_kernel / conv2_dw_tc_kernel / conv2_dimg_tc_kernel (tcgen05 implicit GEMM)",
                         "achieved": 3 * alg / (total * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": 3 * alg / (total * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                        "frac": 3 * alg / (total * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+                        "traffic": 3.328e9 + 3.392e9 + 3.544e9,
+                        "per_kernel_traffic": {"forward": 3.328e9, "d_filters": 3.392e9, "d_images": 3.544e9},
+                        "traffic_source": "profiles/r02d_conv2_fwd_tma_store_ncu.txt (157 MB read + 3.171 GB written), "
+                                          "r02z_conv2_dw_ncu.txt (3.387 GB + 5 MB), r03e_conv2_dimg_ncu.txt (3.389 GB + 155 MB)",
                         "algorithmic_bytes_per_kernel": alg,
                         "per_kernel_frac": {k: alg / (v * 1e-3) / 1e9 / peaks["hbm_gbs"] for k, v in kern.items()},
                         "tflops_fp32": {k: flop / (v * 1e-3) / 1e12 for k, v in kern.items()},
@@ -632,7 +637,9 @@ def run_eltwise(args, ctx, timer, rank, world):
            "config": {"workload": ELT_NAME, "elements": n, "l2": "every tensor is 512 MiB, four times the L2"},
            "roofline": {"bound": "hbm", "kernel": "elt_stream_kernel<sgd-axpy> (P += (0 - g) * rate, base.nim:37-38)",
                         "achieved": dom["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dom["frac"],
-                        "traffic": None, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "peak_source": peaks["source"]},
+                        "traffic": 1.565e9, "traffic_source": "profiles/r02c_eltwise_sgd_ncu.txt (dram read 1.074 GB + write 0.491 GB per launch; "
+                                                                "the tail of the written lines is still in L2 when the kernel ends)",
+                        "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "peak_source": peaks["source"]},
            "per_target": res}
     model.free()
     for t in (dxt, dgt):
