@@ -135,7 +135,17 @@ struct Reader {
     if (*end) fail(EGB_ERR_PARSER, "program text: expected integer, got '%s'", t.c_str());
     return v;
   }
-  int i32() { return (int)i64(); }
+  int i32() {
+    const int64_t v = i64();
+    if (v < INT32_MIN || v > INT32_MAX) fail(EGB_ERR_PARSER, "program text: %lld does not fit a 32-bit field", (long long)v);
+    return (int)v;
+  }
+  // an element count: every element takes at least one token, so a count beyond the rest of the text is malformed
+  int count() {
+    const int v = i32();
+    if (v < 0 || (size_t)v > toks.size() - pos) fail(EGB_ERR_PARSER, "program text: bad element count %d", v);
+    return v;
+  }
   double f64() {
     const std::string& t = next();
     char* end = nullptr;
@@ -166,7 +176,7 @@ Instr read_instr(Reader& r) {
   i.res = r.i32();
   i.tensor = r.i32();
   i.dim = r.i32();
-  int n = r.i32();
+  int n = r.count();
   for (int k = 0; k < n; ++k) i.args.push_back(r.i32());
   i.scalar = r.f64();
   i.index = r.i64();
@@ -176,7 +186,7 @@ Instr read_instr(Reader& r) {
 LinearIndex read_li(Reader& r) {
   r.expect("LI");
   LinearIndex li;
-  int ns = r.i32(), nf = r.i32();
+  int ns = r.count(), nf = r.count();
   li.constant = r.i64();
   for (int k = 0; k < ns; ++k) li.setup.push_back(read_instr(r));
   for (int k = 0; k < nf; ++k) {
@@ -192,7 +202,7 @@ TensorOp read_op(Reader& r, const char* tag) {
   op.tensor = r.i32();
   op.is_raw = r.i32() != 0;
   op.data = r.i32();
-  int n = r.i32();
+  int n = r.count();
   for (int k = 0; k < n; ++k) op.dims.push_back(read_li(r));
   return op;
 }
@@ -202,10 +212,10 @@ std::shared_ptr<Kernel> read_kernel(Reader& r) {
   auto k = std::make_shared<Kernel>();
   k->gen = (GenKind)r.i32();
   k->gen_tensor = r.i32();
-  int nresh = r.i32();
+  int nresh = r.count();
   for (int i = 0; i < nresh; ++i) k->reshape.push_back(r.i64());
   k->nregs = r.i32();
-  int nloops = r.i32(), nreads = r.i32(), ninstrs = r.i32();
+  int nloops = r.count(), nreads = r.count(), ninstrs = r.count();
   k->res = r.i32();
   int has_custom = r.i32();
   for (int i = 0; i < nloops; ++i) {
@@ -225,20 +235,116 @@ std::shared_ptr<Kernel> read_kernel(Reader& r) {
   if (has_custom) {
     r.expect("C");
     k->custom_grad = std::make_shared<CustomGrad>();
-    int nt = r.i32();
+    int nt = r.count();
     for (int i = 0; i < nt; ++i) {
       int t = r.i32();
       k->custom_grad->tensors[t] = r.i32();
     }
-    int nsub = r.i32();
+    int nsub = r.count();
     for (int i = 0; i < nsub; ++i) {
       int a = r.i32();
       k->custom_grad->subs[a] = r.i32();
     }
-    int nk = r.i32();
+    int nk = r.count();
     for (int i = 0; i < nk; ++i) k->custom_grad->kernels.push_back(read_kernel(r));
   }
   return k;
+}
+
+// Referential integrity of a parsed program: every tensor id, register and enumeration value the passes and the
+// planner will index with is inside its table. The text comes from another process (the Nim front-end, a checkpoint
+// file): a damaged one must be an error (ParserError), never an out-of-bounds access.
+struct Validator {
+  const Program& prog;
+  int nt;
+  void tensor(int id, bool allow_none, bool allow_placeholder, const char* what) const {
+    if (id == 0 && allow_none) return;
+    if (id < 0 && allow_placeholder) return;   // gradient placeholders inside customGrad kernels (CustomGrad::tensors)
+    if (id < 1 || id > nt) fail(EGB_ERR_PARSER, "program text: %s refers to tensor %d of %d", what, id, nt);
+  }
+  static void reg(int r, int nregs, bool allow_none, const char* what) {
+    if (r == 0 && allow_none) return;
+    if (r < 1 || r > nregs) fail(EGB_ERR_PARSER, "program text: %s uses register %d of %d", what, r, nregs);
+  }
+  void instr(const Instr& i, int nregs, bool placeholder) const {
+    if (i.op == Op::Invalid) fail(EGB_ERR_PARSER, "program text: invalid instruction");
+    reg(i.res, nregs, false, "an instruction result");
+    for (int a : i.args) reg(a, nregs, false, "an instruction argument");
+    tensor(i.tensor, true, placeholder, "an instruction");
+    if (i.dim < -EGB_MAX_RANK || i.dim > EGB_MAX_RANK) fail(EGB_ERR_PARSER, "program text: dimension %d out of range", i.dim);
+  }
+  void index(const LinearIndex& li, int nregs, bool placeholder) const {
+    for (auto& s : li.setup) instr(s, nregs, placeholder);
+    for (auto& kv : li.factors) reg(kv.first, nregs, false, "an index factor");
+  }
+  void access(const TensorOp& op, int nregs, bool placeholder, bool needs_tensor) const {
+    tensor(op.tensor, !needs_tensor, placeholder, "a tensor access");
+    reg(op.data, nregs, true, "a tensor access");
+    if (op.dims.size() > (size_t)EGB_MAX_RANK) fail(EGB_ERR_PARSER, "program text: access of rank %zu", op.dims.size());
+    for (auto& d : op.dims) index(d, nregs, placeholder);
+  }
+  void kernel(const Kernel& k, bool placeholder, int depth) const {
+    if (depth > 4) fail(EGB_ERR_PARSER, "program text: customGrad kernels nested too deeply");
+    if ((int)k.gen < 0 || (int)k.gen > (int)GenKind::Reshape) fail(EGB_ERR_PARSER, "program text: unknown generator kind %d", (int)k.gen);
+    if (k.nregs < 0 || k.nregs > (1 << 20)) fail(EGB_ERR_PARSER, "program text: %d registers", k.nregs);
+    tensor(k.gen_tensor, !k.is_generator(), placeholder, "a generator");
+    for (auto& l : k.loops) {
+      reg(l.iter, k.nregs, false, "a loop iterator");
+      if (l.step == 0) fail(EGB_ERR_PARSER, "program text: loop with step 0");
+      if (l.mode < 0 || l.mode > 1) fail(EGB_ERR_PARSER, "program text: unknown loop mode %d", l.mode);
+      index(l.start, k.nregs, placeholder);
+      index(l.stop, k.nregs, placeholder);
+    }
+    for (auto& r : k.reads) access(r, k.nregs, placeholder, true);
+    for (auto& i : k.instrs) instr(i, k.nregs, placeholder);
+    access(k.write, k.nregs, placeholder, !k.is_generator() || k.gen == GenKind::Gradient || k.gen == GenKind::Reshape);
+    reg(k.res, k.nregs, true, "a kernel result");
+    if (k.custom_grad) {
+      for (auto& kv : k.custom_grad->tensors) tensor(kv.first, false, true, "a customGrad table");
+      for (auto& kv : k.custom_grad->subs) {
+        tensor(kv.first, false, true, "a customGrad substitution");
+        tensor(kv.second, false, true, "a customGrad substitution");
+      }
+      for (auto& c : k.custom_grad->kernels) kernel(*c, true, depth + 1);
+    }
+  }
+};
+
+void validate_program(const Program& prog) {
+  Validator v{prog, (int)prog.tensors.size()};
+  for (auto& t : prog.tensors) {
+    if ((int)t.kind < 0 || (int)t.kind > (int)TensorKind::Random) fail(EGB_ERR_PARSER, "program text: unknown tensor kind %d", (int)t.kind);
+    if (t.shape.size() > (size_t)EGB_MAX_RANK) fail(EGB_ERR_PARSER, "program text: tensor of rank %zu", t.shape.size());
+    v.tensor(t.cache, true, false, "a cache");
+  }
+  for (auto& t : prog.targets) {
+    v.tensor(t->output, true, false, "a target output");
+    if (t->compile_target < 0 || t->compile_target > 2) fail(EGB_ERR_PARSER, "program text: unknown compile target %d", t->compile_target);
+    for (int id : t->tensors) v.tensor(id, false, false, "a target");
+    for (auto& sc : t->shapes) {
+      v.tensor(sc.dest, false, false, "a shape constraint");
+      if (sc.kind == ShapeKind::Copy) v.tensor(sc.src, false, false, "a shape constraint");
+      if (sc.priority < PRIO_CONDITION || sc.priority > PRIO_USER) fail(EGB_ERR_PARSER, "program text: unknown constraint priority %d", sc.priority);
+      if (sc.rank < 0 || sc.rank > EGB_MAX_RANK) fail(EGB_ERR_PARSER, "program text: rank constraint %d", sc.rank);
+      // constraint indices are evaluated on their own small register files: only the tensors they name are checked
+      for (auto& d : sc.dims)
+        for (auto& s : d.setup) v.tensor(s.tensor, true, false, "a shape constraint");
+      for (auto& rd : sc.reads) {
+        v.tensor(rd.first, false, false, "a shape constraint");
+        for (auto& dim : rd.second)
+          for (auto& li : dim)
+            for (auto& s : li.setup) v.tensor(s.tensor, true, false, "a shape constraint");
+      }
+      for (auto& d : sc.write)
+        for (auto& s : d.setup) v.tensor(s.tensor, true, false, "a shape constraint");
+    }
+    for (auto& k : t->kernels) v.kernel(*k, false, 0);
+  }
+  for (auto& kv : prog.grad_tensors)
+    for (auto& pr : kv.second) {
+      v.tensor(pr.first, false, false, "the gradient table");
+      v.tensor(pr.second, false, false, "the gradient table");
+    }
 }
 
 }  // namespace
@@ -253,12 +359,12 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
   else if (st != "f32") fail(EGB_ERR_PARSER, "unknown scalar type '%s'", st.c_str());
   prog->compiled = r.i32() != 0;
   r.expect("tensors");
-  int nt = r.i32();
+  int nt = r.count();
   for (int i = 0; i < nt; ++i) {
     r.expect("T");
     TensorDef t;
     t.kind = (TensorKind)r.i32();
-    int rank = r.i32();
+    int rank = r.count();
     for (int d = 0; d < rank; ++d) t.shape.push_back(r.i64());
     t.range_lo = r.f64();
     t.range_hi = r.f64();
@@ -267,14 +373,14 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
     prog->tensors.push_back(t);
   }
   r.expect("targets");
-  int ntg = r.i32();
+  int ntg = r.count();
   for (int i = 0; i < ntg; ++i) {
     r.expect("target");
     auto t = std::make_shared<Target>();
     t->name = r.str();
     t->output = r.i32();
     t->compile_target = r.i32();
-    int ns = r.i32(), nk = r.i32(), ntens = r.i32();
+    int ns = r.count(), nk = r.count(), ntens = r.count();
     for (int k = 0; k < ntens; ++k) t->tensors.push_back(r.i32());
     for (int s = 0; s < ns; ++s) {
       r.expect("S");
@@ -287,25 +393,25 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
         sc.src = r.i32();
       } else if (kind == "dims") {
         sc.kind = ShapeKind::Dims;
-        int n = r.i32();
+        int n = r.count();
         for (int d = 0; d < n; ++d) sc.dims.push_back(read_li(r));
       } else if (kind == "rank") {
         sc.kind = ShapeKind::Rank;
         sc.rank = r.i32();
       } else if (kind == "linear") {
         sc.kind = ShapeKind::Linear;
-        int nr = r.i32();
+        int nr = r.count();
         for (int a = 0; a < nr; ++a) {
           int tensor = r.i32();
-          int nd = r.i32();
+          int nd = r.count();
           std::vector<std::vector<LinearIndex>> dims(nd);
           for (int d = 0; d < nd; ++d) {
-            int ni = r.i32();
+            int ni = r.count();
             for (int e = 0; e < ni; ++e) dims[d].push_back(read_li(r));
           }
           sc.reads.emplace_back(tensor, dims);
         }
-        int nw = r.i32();
+        int nw = r.count();
         for (int d = 0; d < nw; ++d) sc.write.push_back(read_li(r));
       } else {
         fail(EGB_ERR_PARSER, "unknown shape constraint kind '%s'", kind.c_str());
@@ -321,11 +427,11 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
   // carry it; the runtime then derives the bucket from the optimizer kernels (runtime.cpp).
   std::string tail = r.next();
   if (tail == "grads") {
-    const int ng = r.i32();
+    const int ng = r.count();
     for (int i = 0; i < ng; ++i) {
       r.expect("G");
       const std::string name = r.str();
-      const int np = r.i32();
+      const int np = r.count();
       auto& table = prog->grad_tensors[name];
       for (int q = 0; q < np; ++q) {
         const int t = r.i32();
@@ -335,6 +441,7 @@ std::shared_ptr<Program> parse_program(const std::string& text) {
     tail = r.next();
   }
   if (tail != "end") fail(EGB_ERR_PARSER, "program text: expected 'end', got '%s'", tail.c_str());
+  validate_program(*prog);
   if (prog->compiled) {
     for (size_t i = 0; i < prog->tensors.size(); ++i) {
       const TensorDef& t = prog->tensors[i];
