@@ -45,10 +45,11 @@ def test_compiled_program_matches_oracle(name):
         assert a == b, f"token {i}: oracle {want[max(0, i - 8):i + 4]} vs library {got[max(0, i - 8):i + 4]}"
 
 
-def test_serialize_parse_round_trip():
+@pytest.mark.parametrize("name", sorted(G.ALL))
+def test_serialize_parse_round_trip(name):
     from exprgrad_b200 import frontend as F, layers as PL
     from exprgrad_b200.model import Program
-    prog = Program.from_graphs(G.dense_net(F, PL)).compile()
+    prog = Program.from_graphs(G.ALL[name](F, PL)).compile()
     text = prog.serialize()
     again = Program(text)
     assert _tokens(again.serialize()) == _tokens(text)
