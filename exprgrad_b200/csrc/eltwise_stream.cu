@@ -138,11 +138,12 @@ __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArg
     }
     // phase 2: arithmetic + stores
     if constexpr (kScalarIn1<KIND> && VARIANT == 1) {
-      // overwrite only (the launcher refuses the accumulating form): every result first, in place, one register group
-      // per unrolled load, then the stores back to back. Left to itself the compiler sinks each group's arithmetic next
-      // to its store and reuses one register group for all four results, so a group has to wait until the previous
-      // store has read its operands (r04c ncu of the interleaved form: 56 % DRAM activity where relu has 76 %); the
-      // empty asm makes all results live at once.
+      // overwrite only (the launcher refuses the accumulating form), no destination operand, no broadcast copies of
+      // the seed: 48 registers and 243 instructions where the general body has 67 and 392. Measured 5.7 TB/s standalone
+      // on a 3.2 GB tensor against 4.3 for the general body (profiles/r04d_stream_variants.txt; ncu of the general
+      // body: 56 % DRAM activity where relu has 76 %, r04c). Which difference matters was not isolated: ptxas sinks each
+      // group's arithmetic next to its store in both and reuses one register group for all four results (the empty
+      // asm below does not prevent it), so operand reuse behind the stores is NOT the explanation.
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         x[u].x = Fn::apply(x[u].x, sc, a); x[u].y = Fn::apply(x[u].y, sc, a);
