@@ -101,8 +101,8 @@ __device__ __forceinline__ long long row_offset(long long i, const EltArgs& a) {
   return i % a.row;
 }
 
-// VARIANT (scalar-operand kinds only): 0 = results and stores interleaved per unrolled group like every other kind,
-// 1 = all results first, pinned in their registers, then the stores back to back
+// VARIANT (scalar-operand kinds only): 0 = the general body (destination operand, accumulate path, 4-wide copy of the
+// one-element operand), 1 = a body without them (overwrite only), what ships
 template <int KIND, int UNROLL, int VARIANT = 0>
 __global__ void __launch_bounds__(ELT_THREADS, 3) elt_stream_kernel(const EltArgs a) {
   using Fn = EltFn<KIND>;
