@@ -137,12 +137,19 @@ def run_program(p, tensors):
             out[widx] = acc
 
 
-def run_target(prog, target, inputs, state, strict=True, epoch=0):
+def run_target(prog, target, inputs, state, strict=True, epoch=0, cache=None):
     """Run every kernel of `target` in order, the way the reference does (model.nim:275-318, 385-411): results start
     at zero, every kernel accumulates. `inputs`: name -> array, `state`: tensor id -> array of the parameters / caches
-    (updated in place). Returns the target's output tensor."""
+    (updated in place). Returns the target's output tensor. `cache`: optional dict that keeps the dumped programs per
+    (target, input shapes, epoch) across calls."""
     shapes = {k: list(v.shape) for k, v in inputs.items()}
-    dump = prog.lower_dump(target, shapes, strict=strict, epoch=epoch)
+    key = (target, tuple(sorted((k, tuple(v)) for k, v in shapes.items())), strict, epoch)
+    if cache is not None and key in cache:
+        dump = cache[key]
+    else:
+        dump = prog.lower_dump(target, shapes, strict=strict, epoch=epoch)
+        if cache is not None:
+            cache[key] = dump
     names = {}
     for tid in range(1, prog.tensor_count() + 1):
         info = prog.tensor_info(tid)

@@ -18,7 +18,7 @@ f32 = np.float32
 o = L = BE = None
 
 
-@pytest.fixture(autouse=True, params=["oracle", pytest.param("b200", marks=pytest.mark.gpu),
+@pytest.fixture(autouse=True, params=["oracle", "b200_host", pytest.param("b200", marks=pytest.mark.gpu),
                                       pytest.param("b200_strict", marks=pytest.mark.gpu)])
 def backend(request):
     be = make_backend(request.param)
