@@ -715,16 +715,29 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    def extra(fn):
+        """a secondary block of a single-GPU run must not take the primary line down with it: report the failure in place
+        (multi-rank blocks are not wrapped - a rank that skips a collective would leave the others waiting)"""
+        if world > 1:
+            return fn()
+        try:
+            return fn()
+        except Exception as e:   # noqa: BLE001
+            return {"error": f"{type(e).__name__}: {e}"[:500]}
+
     if workload == "matmul":
         out = run_matmul(args, ctx, timer, rank, world, sampler)
         if not args.no_dense:
-            out["dense_train"] = run_dense(args, ctx, timer, rank, world, comm, sampler)
-            if rank == 0 and not args.no_cpu:
-                out["dense_train"]["cpu_baseline"], _ = cpu_dense_sample()
+            def dense_block():
+                d = run_dense(args, ctx, timer, rank, world, comm, sampler)
+                if rank == 0 and not args.no_cpu:
+                    d["cpu_baseline"], _ = cpu_dense_sample()
+                return d
+            out["dense_train"] = extra(dense_block)
         if world == 1 and not args.no_conv:
-            out["conv2_fwd_bwd"] = run_conv2(args, ctx, timer, rank, world)
+            out["conv2_fwd_bwd"] = extra(lambda: run_conv2(args, ctx, timer, rank, world))
         if world == 1 and not args.no_eltwise:
-            out["eltwise"] = run_eltwise(args, ctx, timer, rank, world)
+            out["eltwise"] = extra(lambda: run_eltwise(args, ctx, timer, rank, world))
     elif workload == "dense":
         out = run_dense(args, ctx, timer, rank, world, comm, sampler, exact=True)
         if rank == 0 and world == 1 and not args.no_cpu:
