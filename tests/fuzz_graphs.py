@@ -185,3 +185,75 @@ def random_cnn(d, L, seed, ct="gpu"):
     steps += [f"reshape[{flat}]", head, "adam" if "adam" in repr(opt) or opt.__qualname__.startswith("adam") else "sgd"]
     graphs = [p.target("predict", ct), loss.target("loss", ct), loss.backprop(opt).target("train", ct)]
     return graphs, " > ".join(steps), {"x": [rng.choice([1, 5]), side, side, chans], "y": None, "outs": outs}
+
+
+def random_index_net(d, L, seed, ct="gpu"):
+    """Kernels whose INDICES do the work - explicit loop bounds, strided / divided / modular / wrapped accesses, iterator
+    and shape values inside expressions, array literals, scatter writes, `withShape` (ir.nim:51-76 IndexDiv / Mod / Wrap /
+    ToScalar / Shape / Len / Array*; test_model.nim:91-154, 233-263 hold one small case of each) - chained two or three deep,
+    with a loss and its gradient. Inputs: a : [R, 12], v : [12]. -> (graphs, description)."""
+    rng = random.Random(20_000 + seed)
+    a = d.input("a", [-1, 12]); v = d.input("v", [12])
+    cur, kind = a, "2d"          # "2d": [R, C] with C a multiple of 6 unless noted; "1d": [n]
+    steps = []
+    for _ in range(rng.randint(1, 3)):
+        r = d.Fun()
+        if kind == "2d":
+            op = rng.choice(["stride", "updiv", "modrow", "iterval", "array", "rowstencil", "colmean", "flatten_wrap"])
+        else:
+            op = rng.choice(["stencil", "wrap", "scatter", "lenmean"])
+        steps.append(op)
+        if op == "stride":           # r[y, x] += sum_k c_k * cur[y, s x + k]: strided reads, shape [R, C / s]
+            s = rng.choice([2, 3]); y, x = d.Iter("y"), d.Iter("x")
+            e = None
+            for k in range(s):
+                t = cur[y, x * s + k] * rng.choice([0.5, 1.0, -2.0])
+                e = t if e is None else e + t
+            r[y, x] += e
+            kind = "2d_odd"
+        elif op == "updiv":          # r[y, x] += cur[y, x div 2] * c: divided index, explicit shape (dnn.nim:81-88)
+            y, x = d.Iter("y"), d.Iter("x")
+            r[y, x] += cur[y, x // 2] * rng.choice([1.0, 0.25])
+            r.with_shape(cur.shape[0], cur.shape[1] * 2)
+        elif op == "modrow":         # r[y, x] += cur[y, x] * v[x mod 3]
+            y, x = d.Iter("y"), d.Iter("x")
+            r[y, x] += cur[y, x] * v[x % 3]
+        elif op == "iterval":        # iterator and shape values inside the expression
+            y, x = d.Iter("y"), d.Iter("x")
+            r[y, x] += cur[y, x] * d.to_scalar(x + 1) / d.to_scalar(cur.shape[1])
+        elif op == "array":          # array literal indexed by an expression of the iterator
+            y, x = d.Iter("y"), d.Iter("x")
+            arr = d.lift([rng.choice([0.5, 1.5, -1.0]) for _ in range(3)])
+            r[y, x] += cur[y, x] * arr[x % 3] + d.to_scalar(d.array_len(arr))
+        elif op == "rowstencil":     # explicit bounds on the column loop: r[y, x - 1] += ...
+            y = d.Iter("y"); x = d.Iter("x", 1, cur.shape[1] - 1)
+            r[y, x - 1] += (cur[y, x - 1] + cur[y, x] * 2.0 + cur[y, x + 1]) / 4.0
+            kind = "2d_odd"
+        elif op == "colmean":        # r[x] += cur[y, x] / rows
+            y, x = d.Iter("y"), d.Iter("x")
+            r[x] += cur[y, x] / d.to_scalar(cur.shape[0])
+            kind = "1d"
+        elif op == "flatten_wrap":   # r{i} += cur{wrap(i + k, len)}: a circular shift of the flattened tensor
+            it = d.Iter("it")
+            r.raw[it] += cur.raw[d.wrap(it + rng.choice([1, 5]), cur.len())] * 0.5
+            r.copy_shape(cur)
+        elif op == "stencil":        # 1-D blur with explicit bounds (test_model.nim:109-117)
+            x = d.Iter("x", 1, cur.shape[0] - 1)
+            r[x - 1] += (cur[x - 1] + cur[x] + cur[x + 1]) / 3.0
+        elif op == "wrap":           # circular shift
+            x = d.Iter("x")
+            r[x] += cur[d.wrap(x + rng.choice([1, 2, 7]), cur.shape[0])] - cur[x] * 0.5
+            r.copy_shape(cur)
+        elif op == "scatter":        # r[x div 2] += cur[x]: the write index is not an iterator
+            x = d.Iter("x")
+            r[x // 2] += cur[x] * rng.choice([1.0, -0.5])
+        else:                        # lenmean: r[0] += cur[x] / len
+            x = d.Iter("x")
+            r[0] += cur[x] / d.to_scalar(cur.len())
+            kind = "scalar"
+        cur = r
+        if kind in ("2d_odd", "scalar"):
+            break
+    loss = d.Fun(); it = d.Iter("it")
+    loss[0] += d.sq(cur.raw[it]) * 0.5 + cur.raw[it]
+    return [cur.target("out", ct), loss.target("loss", ct), loss.backwards().grad(a).target("da", ct)], " > ".join(steps)

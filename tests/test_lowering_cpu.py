@@ -173,3 +173,30 @@ def _layer_stack_case(seed, strict):
         _compare(state[tid], ref[f"param{tid}"], ref64[f"param{tid}"], f"cnn {seed} ({what}) param tensor{tid - 1}")
     for tid in cache_ids:
         _compare(state[tid], ref[f"cache{tid}"], ref64[f"cache{tid}"], f"cnn {seed} ({what}) cache tensor{tid - 1}")
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_random_index_graph_lowering_matches_oracle(seed, strict):
+    """explicit loop bounds, strided / divided / modular / wrapped accesses, iterator and shape values in expressions,
+    array literals, scatter writes: value, loss and gradient through the lowered programs, both lowering modes"""
+    import oracle as o
+    from oracle import layers as OL
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    rng = np.random.default_rng(seed)
+    full = {"a": rng.uniform(-1, 1, (4, 12)).astype(np.float32), "v": rng.uniform(-1, 1, 12).astype(np.float32)}
+    res = {}
+    for scalar in ("float32", "float64"):
+        graphs, what = FG.random_index_net(o, OL, seed, ct="cpu")
+        try:
+            om = o.compile(*graphs, scalar=scalar, seed=0, openmp=False)
+        except (o.GradientError, o.ShapeError):
+            pytest.skip("a compile-time error of the reference (no derive rule for ArrayRead, underconstrained scatter "
+                        "shape): error parity is checked in tests/test_passes_fuzz.py")
+        inputs = {k: v for k, v in full.items() if k in om.program.inputs}
+        res[scalar] = {t: np.array(om.call(t, inputs)) for t in ("out", "loss", "da")}
+    prog = Program.from_graphs(FG.random_index_net(F, PL, seed)[0]).compile()
+    for t in ("out", "loss", "da"):
+        got = run_target(prog, t, inputs, {}, strict=strict)
+        _compare(got, res["float32"][t], res["float64"][t], f"index graph {seed} ({what}) target {t} strict={strict}")

@@ -115,3 +115,21 @@ def test_every_map_form_is_covered():
     _check_target(prog, "leaky", {"x": [5, 6]}, label="leaky")
     for name in ("eltwise tanh", "eltwise tanh-adjoint", "eltwise sub", "eltwise div-const", "eltwise leakyRelu"):
         assert SEEN[name] > 0, name
+
+
+@pytest.mark.parametrize("seed", list(range(30)))
+def test_random_index_graphs(seed):
+    """indices that only LOOK like a map or a contraction (strided, divided, wrapped, shifted by explicit bounds): whatever
+    the matchers still claim must compute what the IR kernel computes"""
+    import exprgrad_b200 as eg
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    graphs, what = FG.random_index_net(F, PL, seed)
+    try:
+        prog = Program.from_graphs(graphs).compile()
+    except (eg.GradientError, eg.ShapeError):
+        pytest.skip("compile-time error of the reference (see tests/test_passes_fuzz.py)")
+    used = {prog.tensor_info(t)["name"] for t in range(1, prog.tensor_count() + 1) if prog.tensor_info(t)["kind"] == "input"}
+    shapes = {k: v for k, v in {"a": [5, 12], "v": [12]}.items() if k in used}
+    for target in ("out", "loss", "da"):
+        _check_target(prog, target, shapes, label=f"index graph {seed} ({what})")
