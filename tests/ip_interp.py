@@ -119,17 +119,23 @@ def run_program(p, tensors):
             _decode(loops, npar, len(loops), 0, s)
             run_instrs(p["index_instrs"], s, p["array_table"])
             widx = _flat(p["write"], s)
+            assert 0 <= widx < out.size, f"kernel {p['kernel']}: write at {widx} of {out.size}"
             if p["accumulate"]:
                 acc = out[widx]
         for r in range(p["nred"]):
             _decode(loops, npar, len(loops), r, s)
             run_instrs(p["index_instrs"], s, p["array_table"])
             for rd in p["reads"]:
-                s[rd["dst"]] = _fu(tensors[rd["tensor"]][_flat(rd, s)])
+                src = tensors[rd["tensor"]]
+                idx = _flat(rd, s)
+                # numpy would wrap a negative index silently; the device would read outside the tensor
+                assert 0 <= idx < src.size, f"kernel {p['kernel']}: read of tensor {rd['tensor']} at {idx} of {src.size}"
+                s[rd["dst"]] = _fu(src[idx])
             run_instrs(p["instrs"], s, p["array_table"])
             v = _f(s[p["write"]["dst"]])
             if p["scatter"]:
                 w = _flat(p["write"], s)
+                assert 0 <= w < out.size, f"kernel {p['kernel']}: scatter write at {w} of {out.size}"
                 out[w] = out[w] + v if p["accumulate"] else v
             else:
                 acc = np.float32(acc + v)
