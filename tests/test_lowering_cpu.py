@@ -200,3 +200,50 @@ def test_random_index_graph_lowering_matches_oracle(seed, strict):
     for t in ("out", "loss", "da"):
         got = run_target(prog, t, inputs, {}, strict=strict)
         _compare(got, res["float32"][t], res["float64"][t], f"index graph {seed} ({what}) target {t} strict={strict}")
+
+
+def test_rarely_used_opcodes_lowering_matches_oracle():
+    """Boolean connectives (dsl.nim:48-50 - `or` builds InstrAnd in the reference, restated as is), Eq on scalars, ToIndex
+    (fptosi truncation towards zero, llvmgen.nim:229-236), Mod / IndexDiv on a computed index, pow with a tensor
+    exponent, nested selects."""
+    import oracle as o
+    from oracle import layers as OL  # noqa: F401
+    from exprgrad_b200 import frontend as F
+    from exprgrad_b200.model import Program
+
+    def net(d):
+        a = d.input("a", [-1, 6]); b = d.input("b", [-1, 6]); v = d.input("v", [6])
+        graphs = []
+        r = d.Fun(); y, x = d.Iter("y"), d.Iter("x")
+        r[y, x] += d.select((a[y, x] < 0.25).and_(b[y, x] < 0.5), a[y, x] * 2.0, d.select((a[y, x] < -0.5).or_(b[y, x] <= 0.0), b[y, x], -a[y, x]))
+        graphs.append(r.target("bools", "cpu"))
+        r = d.Fun(); y, x = d.Iter("y"), d.Iter("x")
+        r[y, x] += d.select(a[y, x].eq(b[y, x]), d.lift(1.0), d.lift(0.0)) + d.to_scalar(d.to_index(a[y, x] * 3.7)) * v[x]
+        graphs.append(r.target("toindex", "cpu"))
+        r = d.Fun(); y, x = d.Iter("y"), d.Iter("x")
+        r[y, x] += a[y, (x * 5 + 1) % 6] * v[(x + 3) // 2]
+        r.copy_shape(a)          # x stands alone only in the write: nothing else would bound it
+        graphs.append(r.target("modidx", "cpu"))
+        r = d.Fun(); it = d.Iter("it")
+        r.raw[it] += d.pow_(a.raw[it] * a.raw[it] + 1.0, b.raw[it])
+        r.copy_shape(a)
+        loss = d.Fun(); it = d.Iter("it"); loss[0] += r.raw[it]
+        graphs += [r.target("pow", "cpu"), loss.backwards().grad(b).target("dpow_db", "cpu"),
+                   loss.backwards().grad(a).target("dpow_da", "cpu")]
+        return graphs
+    rng = np.random.default_rng(7)
+    a = rng.uniform(-1, 1, (5, 6)).astype(np.float32); b = rng.uniform(-1, 1, (5, 6)).astype(np.float32)
+    a[0, 0] = b[0, 0]; a[1, 2] = b[1, 2]
+    v = rng.uniform(-1, 1, 6).astype(np.float32)
+    om = o.compile(*net(o), seed=0, openmp=False)
+    prog = Program.from_graphs(net(F)).compile()
+    full = {"a": a, "b": b, "v": v}
+    for target in ("bools", "toindex", "modidx", "pow", "dpow_db", "dpow_da"):
+        used = {k: full[k] for k in full if om.program.inputs.get(k) in om.program.targets[target].tensors}
+        ref = np.array(om.call(target, used))
+        for strict in (True, False):
+            got = run_target(prog, target, used, {}, strict=strict)
+            if target in ("bools", "toindex", "modidx"):
+                assert np.array_equal(got, ref), f"{target} strict={strict}"
+            else:
+                assert norm_err(got, ref) <= 5e-6, f"{target} strict={strict}: {norm_err(got, ref):.2e}"
