@@ -247,3 +247,25 @@ def test_rarely_used_opcodes_lowering_matches_oracle():
                 assert np.array_equal(got, ref), f"{target} strict={strict}"
             else:
                 assert norm_err(got, ref) <= 5e-6, f"{target} strict={strict}: {norm_err(got, ref):.2e}"
+
+
+def test_empty_batch_through_the_host_side():
+    """zero rows: shape inference gives [0, n] results, every lowered program has zero points (or a zero-trip reduction),
+    the loss is 0 and a train step leaves the parameters alone - like the oracle"""
+    import oracle as o
+    from oracle import layers as OL
+    from exprgrad_b200 import frontend as F, layers as PL
+    from exprgrad_b200.model import Program
+    sizes = (6, 5, 4, 3)
+    om = o.compile(*G.dense_net(o, OL, sizes, ct="cpu"), seed=1, openmp=False)
+    x = np.zeros((0, 6), np.float32); y = np.zeros((0, 3), np.float32)
+    prog = Program.from_graphs(G.dense_net(F, PL, sizes)).compile()
+    state = {tid: np.array(v) for tid, v in om.params.items()}
+    got = run_target(prog, "predict", {"x": x}, dict(state))
+    assert got.shape == om.call("predict", {"x": x}).shape == (0, 3)
+    assert np.array_equal(run_target(prog, "loss", {"x": x, "y": y}, dict(state)), om.call("loss", {"x": x, "y": y}))
+    before = {k: v.copy() for k, v in state.items()}
+    run_target(prog, "train", {"x": x, "y": y}, state)
+    om.apply("train", {"x": x, "y": y})
+    for tid in state:
+        assert np.array_equal(state[tid], before[tid]) and np.array_equal(om.params[tid], before[tid])
