@@ -5,7 +5,7 @@ The reference itself cannot produce them here: it needs Nim >= 1.6 and LLVM 13, 
 closed-form numpy (tests/test_oracle_numpy.py) and on finite differences (tests/test_oracle_fuzz.py); these files
 freeze its results for the reduced-size configurations of BASELINE.json so that
   * the oracle itself is checked for drift between hosts (another gcc / glibc / CPU: tests/test_golden.py, CPU tier),
-  * the device path is compared with committed numbers as well as with the live oracle (tests/test_gpu_golden.py).
+  * the device path is compared with committed numbers as well as with the live oracle (tests/test_zgolden_gpu.py).
 
 usage: python tests/golden/make_golden.py        (writes *.npz + shapes.json next to this file)"""
 import json

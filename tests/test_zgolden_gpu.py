@@ -1,7 +1,8 @@
 """GPU parity against COMMITTED vectors (tests/golden/*.npz; generated from the oracle by tests/golden/make_golden.py):
 the same comparisons the live-oracle tests make, but nothing under oracle/ is imported here - the device path stands
 against frozen numbers. Bars: SURVEY 8(d), normalised max error 1e-4 per tensor (parameter UPDATES 2e-3: they are
-differences of nearly equal fp32 numbers)."""
+differences of nearly equal fp32 numbers). (The file name sorts behind the live-oracle GPU tests on purpose: this file was added
+after the last GPU run of the round, and `pytest -x` should reach everything that has run on a B200 before it.)"""
 import os
 
 import numpy as np
